@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the hot path (Renderer::Accumulate x spp + Renderer::Render) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One STEP = one frame of the workload: ResetAccumulator, Accumulate() for the workload's sample count, Render().
+Default workload = BASELINE.json configs[1] (C2): Scenes::Default, 1920x1080 (rendered 1920x1088), 64 spp,
+median-of-means with 8 buckets, max_bounces 16, MIS on. `value` is Mrays/s (extension + shadow rays actually traced, counted on
+the device) with the scene resident in HBM; `e2e` is the same through the public API with host buffers (scene upload from host,
+frame download to pinned host memory every step). Prints ONE JSON line on rank 0.
+
+--impl reference times the reference's CPU path. The reference itself cannot be built here (MSVC-only C++, glm/VCL/PPL absent,
+SURVEY §8c), so this arm runs the oracle port (oracle/liboracle_fast.so, all host threads) on a bounded sample of the same
+workload. It is the ONE place besides cpu_baseline where bench.py executes oracle/ code, as the thing being measured on the CPU.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "cpu-raytracing-experiments_b200")
+sys.path[:0] = [ROOT, PKG]
+
+WORKLOADS = {
+    # name: scene, width, height(internal, multiple of 16), spp, max_bounces, K
+    "c1": dict(desc="C1 default 9-sphere scene 1280x720 1spp max_bounces=8 MIS K=5 (1 sample lands in bucket 1)", scene="default", w=1280, h=720, spp=5, mb=8, K=5),
+    "c2": dict(desc="C2 default 9-sphere scene 1920x1080 (internal 1920x1088) 64spp median-of-means K=8 max_bounces=16 MIS brute-force", scene="default", w=1920, h=1088, spp=64, mb=16, K=8),
+    "c3": dict(desc="C3 random 100k-sphere BVH scene 1920x1080 (internal 1920x1088) 16spp K=8 max_bounces=16 NEE+MIS", scene="random100000", w=1920, h=1088, spp=16, mb=16, K=8),
+    "c4": dict(desc="C4 random 1M-sphere BVH scene 3840x2160 32spp K=8 max_bounces=16", scene="random1000000", w=3840, h=2160, spp=32, mb=16, K=8),
+}
+METRIC, UNIT = "Mrays/s", "Mrays/s"
+
+
+def make_scene(name):
+    import scenes
+    if name == "default":
+        return scenes.default_scene()
+    return scenes.random_scene(int(name[len("random"):]))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p)); return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False); self.p = None; self.gpu = gpu
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15); self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().strip().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_run(wl, scene, samples, fast=True):
+    """Times the oracle port on all host threads: `samples` x Accumulate at the workload's size (+ Render when a round completes)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    threads = os.cpu_count() or 1
+    o = oracle_py.Oracle(wl["w"], wl["h"], max_bounces=wl["mb"], K=wl["K"], fast=fast)
+    o.set_scene(scene)
+    if wl["scene"] != "default":
+        o.close(); o = oracle_py.Oracle(wl["w"], wl["h"], max_bounces=wl["mb"], K=wl["K"], flags=oracle_py.ORC_BVH, fast=fast); o.set_scene(scene)
+    o.reset_counters()
+    t0 = time.perf_counter(); o.accumulate(samples, threads=threads); o.render(); dt = time.perf_counter() - t0
+    c = o.counters(); rays = c["extension_rays"] + c["shadow_rays"]
+    o.close()
+    return dict(seconds=dt, rays=rays, paths=wl["w"] * wl["h"] * samples, threads=threads, mode="stream-BVH (BVH.hpp:320-358 restated)" if wl["scene"] != "default" else "brute force (as shipped, USEBVH false)")
+
+
+def run_reference(args, wl, rank):
+    """--impl reference: the CPU path on the box's host cores, one bounded sample per step."""
+    if rank != 0:
+        return
+    scene = make_scene(wl["scene"])
+    per_step = 1  # 1 spp of the workload's frame per step (~1-3 s on the host cores)
+    for _ in range(args.warmup):
+        cpu_oracle_run(wl, scene, per_step)
+    secs, rays, paths = 0.0, 0, 0
+    threads = mode = None
+    for _ in range(args.steps):
+        r = cpu_oracle_run(wl, scene, per_step); secs += r["seconds"]; rays += r["rays"]; paths += r["paths"]; threads, mode = r["threads"], r["mode"]
+    v = rays / secs / 1e6
+    sample = f"{per_step} spp of the {wl['w']}x{wl['h']} frame per step ({paths // args.steps} paths), {args.steps} steps; oracle port -O3 -march=native, {mode}"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"]}, "paths_per_s": paths / secs,
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference cannot be compiled here (MSVC-only, glm/VCL/PPL absent): oracle port timed instead",
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1); ap.add_argument("--steps", type=int, default=5); ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"]); ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true"); ap.add_argument("--no-profile-pass", action="store_true")
+    ap.add_argument("--samples-in-flight", type=int, default=8)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, wl, rank); return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        dist.barrier()
+    import b2r, b2r_dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libb2r has no CPU fallback")
+    dev = torch.device(f"cuda:{local}"); torch.cuda.set_device(dev)
+    warm = max(args.warmup, 3)
+
+    scene = make_scene(wl["scene"])
+    ps = b2r.PreparedScene(scene, wl["w"], wl["h"])  # host BVH build + light list: scene (re)build, outside the hot path
+    stream = torch.cuda.current_stream(dev)
+    K, spp = wl["K"], wl["spp"]
+    shard = b2r_dist.shard_kwargs(rank, world, K)
+    r = b2r.Renderer(ps, wl["w"], wl["h"], max_bounces=wl["mb"], buckets=K, device=local, stream=stream.cuda_stream,
+                     samples_in_flight=args.samples_in_flight, **shard)
+    # weak scaling: every rank renders `spp` samples of its own buckets per step => world*spp sample indices per step
+    step_samples = spp * world
+    local_buckets = b2r_dist.buckets_tensor(r, dev)
+
+    def step(to_host_fb=None, upload=False):
+        if upload:
+            r.SetScene(ps)  # host -> device: spheres, materials, lights, flattened BVH, camera
+        r.ResetAccumulator()
+        r.Accumulate(step_samples)
+        if world > 1:
+            combined = b2r_dist.combine_buckets(local_buckets)  # the one collective: NCCL all-reduce of the bucket sums
+            ok = r.Render(to_host=to_host_fb is not None and rank == 0, out=to_host_fb, dev_buckets=combined.data_ptr())
+        else:
+            ok = r.Render(to_host=to_host_fb is not None, out=to_host_fb)
+        assert ok
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(n, **kw):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(n):
+            step(**kw)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        return ms
+
+    for _ in range(warm):
+        step()
+    barrier()
+    r.reset_counters()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms_total = timed(args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    cnt = r.counters()
+    rays_local = cnt["extension_rays"] + cnt["shadow_rays"]
+    if world > 1:
+        t = torch.tensor([rays_local, cnt["launches"]], device=dev, dtype=torch.float64); dist.all_reduce(t); rays_total, launches = float(t[0]), int(t[1])
+    else:
+        rays_total, launches = float(rays_local), cnt["launches"]
+    secs = ms_total / 1e3
+    value = rays_total / secs / 1e6
+    paths_total = wl["w"] * wl["h"] * spp * world * args.steps
+
+    # ---- e2e: same steps through the public API with HOST buffers (scene upload + frame download each step)
+    fb_host = torch.empty((wl["h"], wl["w"], 4), dtype=torch.float32, pin_memory=True).numpy()
+    for _ in range(2):
+        step(to_host_fb=fb_host, upload=True)
+    r.reset_counters()
+    ms_e2e = timed(args.steps, to_host_fb=fb_host, upload=True)
+    c2 = r.counters(); rays_e2e = c2["extension_rays"] + c2["shadow_rays"]
+    if world > 1:
+        t = torch.tensor([rays_e2e], device=dev, dtype=torch.float64); dist.all_reduce(t); rays_e2e = float(t[0])
+    wide, _ms = r.wide_nodes()
+    h2d = len(ps.prims) * 20 + len(ps.material) * 32 + max(1, len(ps.lights)) * 32 + wide.shape[0] * 128 + 44
+    d2h = wl["w"] * wl["h"] * 16 if rank == 0 else 0
+    e2e_value = rays_e2e / (ms_e2e / 1e3) / 1e6
+
+    # ---- per-kernel pass: the same K steps launched kernel by kernel with an event pair around every launch (roofline)
+    roof = None; kernel_ms = None
+    hbm_peak, peak_src, sm_max = peaks()
+    if not args.no_profile_pass:
+        r.set_flags(b2r.FLAG_NO_GRAPH); r.SetCamera(ps.camera)
+        step(); r.sync(); r.kernel_times(reset=True); r.reset_counters()
+        for _ in range(args.steps):
+            step()
+        r.sync()
+        kt = r.kernel_times(reset=True); pc = r.counters()
+        r.set_flags(0); r.SetCamera(ps.camera)
+        kernel_ms = {k: {"ms": v[0], "launches": int(v[1])} for k, v in kt.items() if v[1]}
+        total_kernel_ms = sum(v[0] for v in kt.values())
+        ext, shadow, hits, events, dropped = pc["extension_rays"], pc["shadow_rays"], pc["shaded_hits"], pc["radiance_events"], pc["dropped"]
+        primaries = wl["w"] * wl["h"] * spp * args.steps
+        if kt["bounce_brute"][1]:
+            # DESIGN.md "Algorithmic bytes": 44 B path record read per non-primary ray + 44 B written per continuing path (= every
+            # non-primary ray was written once) + 24 B radiance read-modify-write per contribution + 12 B per dropped path
+            name, ms, n = "k_bounce_brute", kt["bounce_brute"][0], kt["bounce_brute"][1]
+            alg = 88.0 * (ext - primaries) + 24.0 * events + 12.0 * dropped
+        else:
+            # dominant kernel of the BVH pipeline = closest-hit traversal: 32 B ray read + 8 B hit written per extension ray from HBM;
+            # node/sphere fetches are L2-resident and reported separately through the box/sphere counters
+            name, ms, n = "k_intersect_closest", kt["intersect_closest"][0], kt["intersect_closest"][1]
+            alg = 40.0 * ext
+        achieved = alg / (ms / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                "peak_source": peak_src, "avg_launch_ms": ms / n, "launches": int(n), "algorithmic_bytes_per_launch": alg / n,
+                "kernel_share_of_step": ms / total_kernel_ms if total_kernel_ms else None,
+                "timing": "CUDA event pair around every launch, non-graph pass of the same steps on the launching stream"}
+        # FP32 view (never tensor cores): 20 flop per sphere test (BVH.hpp:251-265), ~250 per shaded hit
+        if kt["bounce_brute"][1]:
+            n_prims = len(ps.prims)
+            flops = 20.0 * n_prims * (ext + shadow) + 250.0 * hits  # shadow: upper bound (any-hit exits early)
+            fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+            roof["fp32"] = {"achieved_tflops": flops / (ms / 1e3) / 1e12, "peak_tflops": fp32_peak, "frac": flops / (ms / 1e3) / 1e12 / fp32_peak,
+                            "note": "accounting flops (20/sphere test, 250/shaded hit); shadow tests counted at their upper bound"}
+        ncu = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(ncu):
+            try:
+                tr = json.load(open(ncu)).get(args.workload, {}).get(name)
+                if tr:
+                    roof["traffic"] = tr["dram_bytes_per_launch"]; roof["traffic_source"] = tr.get("source")
+            except Exception:
+                pass
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): oracle port on a bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_cpu = 8 if wl["scene"] == "default" else 1
+        c = cpu_oracle_run(wl, scene, n_cpu)
+        cpu = {"value": c["rays"] / c["seconds"] / 1e6, "unit": UNIT, "cores": c["threads"], "kind": "port",
+               "sample": f"{n_cpu} spp of the {wl['w']}x{wl['h']} frame ({c['paths']} paths, {c['rays']} rays) in {c['seconds']:.2f} s; oracle port -O3 -march=native, {c['mode']}",
+               "paths_per_s": c["paths"] / c["seconds"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "samples_per_step_per_gpu": spp, "samples_in_flight": args.samples_in_flight,
+                       "partition": f"sample buckets b%{world}==rank, scene+BVH replicated, one NCCL all-reduce of bucket sums per frame" if world > 1 else "single GPU",
+                       "l2": "no flush needed: each step streams >1 GB of path-queue records (>> 126 MB L2); RNG-unique samples every step"},
+            "paths_per_s": paths_total / secs, "rays_per_step": rays_total / args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
+                    "includes": "upload_scene (pack + 128-B BVH flatten on host, H2D), set_camera, reset, Accumulate x spp, Render, D2H of the RGBA32F frame into pinned memory"},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "kernel_ms": kernel_ms,
+        }
+        print(json.dumps(line))
+    r.close()
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

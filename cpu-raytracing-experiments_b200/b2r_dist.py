@@ -1,0 +1,48 @@
+"""Multi-GPU plumbing: one process per GPU, sample buckets partitioned over the ranks, ONE collective per resolved frame.
+
+Partition (BASELINE north_star): scene + BVH replicated; rank g of G owns the median-of-means buckets
+{b : b % G == g} and renders exactly the sample indices acc with acc % K in that set (RNG streams are a pure function of
+(acc, pixel, bounce), Renderer.hpp:117,255,362, so no rank needs another's state). Nothing is exchanged while rendering.
+At resolve every bucket buffer has a single owner and is zero elsewhere, so the combine is one all-reduce (sum) of the
+[K][3][npix] array over NCCL/NVLink (gloo on CPU for the tests) — adding zeros is exact, the result is bit-identical to a
+single-GPU render of the same samples.
+"""
+import numpy as np
+
+
+def owned_buckets(rank, world, K):
+    if K % world:
+        raise ValueError(f"bucket count {K} must be a multiple of the world size {world}")
+    return [b for b in range(K) if b % world == rank]
+
+
+def shard_kwargs(rank, world, K):
+    """bucket_first / bucket_stride for b2r_config."""
+    owned_buckets(rank, world, K)
+    return dict(bucket_first=rank, bucket_stride=world) if world > 1 else dict(bucket_first=0, bucket_stride=0)
+
+
+def owns_sample(acc, rank, world, K):
+    return world <= 1 or (acc % K) % world == rank
+
+
+class _DevArray:
+    """Zero-copy view of a raw device pointer for torch.as_tensor (CUDA array interface v2)."""
+
+    def __init__(self, ptr, n_floats):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def buckets_tensor(renderer, device):
+    import torch
+    ptr, nbytes = renderer.device_buckets()
+    return torch.as_tensor(_DevArray(ptr, nbytes // 4), device=device)
+
+
+def combine_buckets(local_buckets, group=None):
+    """All ranks end with every bucket: out-of-place all-reduce(sum) of the owner-only bucket arrays (torch tensor, any device)."""
+    import torch.distributed as dist
+    out = local_buckets.clone()
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out

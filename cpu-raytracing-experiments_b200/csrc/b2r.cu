@@ -1,0 +1,510 @@
+// b2r.cu — context management and the C ABI of libb2r.so (include/b2r.h). Host code drives the sm_100a kernels of
+// b2r_device.cuh; there is no CPU rendering path in this library.
+#include "b2r_device.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace b2r;
+
+namespace {
+
+thread_local std::string g_error;
+int fail(int code, const std::string& what) { g_error = what; return code; }
+#define CU(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail(B2R_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
+
+enum KernelKind { KK_GENERATE = 0, KK_BRUTE, KK_CLOSEST, KK_SHADE, KK_SHADOW, KK_ACCUMULATE, KK_RESOLVE, KK_COUNT };
+
+struct BatchArgs { uint32_t n; uint32_t acc[kMaxSlots]; };
+__global__ void k_set_batch(BatchDev* dst, const BatchArgs a) {
+	if (threadIdx.x == 0) dst->n_slots = a.n;
+	if (threadIdx.x < a.n) dst->acc[threadIdx.x] = a.acc[threadIdx.x];
+}
+
+template <typename T> int dev_alloc(T** p, size_t count) {
+	if (*p) { cudaFree(*p); *p = nullptr; }
+	if (count == 0) count = 1;
+	CU(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+	return B2R_OK;
+}
+template <typename T> void dev_free(T** p) { if (*p) { cudaFree(*p); *p = nullptr; } }
+
+}  // namespace
+
+struct b2r_ctx {
+	b2r_config cfg{};
+	cudaStream_t stream = nullptr, own_stream = nullptr;
+	bool have_scene = false, have_camera = false, use_bvh = false;
+	uint32_t accumulations = 0;
+	uint32_t slots = 8;
+	int sm_count = 0;
+	// scene
+	float4 *d_prims = nullptr, *d_mat_albedo = nullptr, *d_mat_emission = nullptr, *d_light_sphere = nullptr, *d_light_emit = nullptr, *d_hdri = nullptr;
+	int32_t* d_prim_mat = nullptr;
+	WideNode* d_wide = nullptr;
+	WideBvh wide_host;
+	// frame
+	float4 *d_A[2] = {nullptr, nullptr}, *d_B[2] = {nullptr, nullptr}, *d_SA = nullptr, *d_SB = nullptr, *d_fb = nullptr;
+	float *d_T[2] = {nullptr, nullptr}, *d_SL = nullptr, *d_rad = nullptr, *d_acc = nullptr;
+	float2* d_H = nullptr;
+	uint32_t* d_counts = nullptr; size_t counts_bytes = 0;
+	unsigned long long* d_stats = nullptr;
+	BatchDev* d_batch = nullptr;
+	Params params{};
+	// launch
+	int grid_brute_first = 0, grid_brute = 0, grid_closest = 0, grid_shade = 0, grid_shadow = 0, grid_stream = 0;
+	cudaGraphExec_t graph_exec = nullptr; bool graph_valid = false;
+	uint64_t launches = 0;
+	// profiling (B2R_FLAG_NO_GRAPH): events around every launch
+	struct Timed { int kind; cudaEvent_t a, b; };
+	std::vector<Timed> timed;
+	double kernel_ms[8] = {0}; uint64_t kernel_launches[8] = {0};
+};
+
+namespace {
+
+int ensure_device(b2r_ctx* c) { CU(cudaSetDevice(c->cfg.device)); return B2R_OK; }
+
+void drop_graph(b2r_ctx* c) {
+	if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+	c->graph_valid = false;
+}
+
+int alloc_frame(b2r_ctx* c) {
+	const uint32_t w = c->cfg.width, h = c->cfg.height, npix = w * h, mb = c->cfg.max_bounces, K = c->cfg.buckets;
+	const size_t cap = static_cast<size_t>(c->slots) * npix;
+	if (cap >= (1ull << 32)) return fail(B2R_ERR_ARG, "samples_in_flight * pixels exceeds the 32-bit queue index");
+	int rc;
+	for (int s = 0; s < 2; s++) {
+		if ((rc = dev_alloc(&c->d_A[s], cap))) return rc;
+		if ((rc = dev_alloc(&c->d_B[s], cap))) return rc;
+		if ((rc = dev_alloc(&c->d_T[s], 3 * cap))) return rc;
+	}
+	if ((rc = dev_alloc(&c->d_H, cap))) return rc;
+	if ((rc = dev_alloc(&c->d_SA, cap))) return rc;
+	if ((rc = dev_alloc(&c->d_SB, cap))) return rc;
+	if ((rc = dev_alloc(&c->d_SL, 3 * cap))) return rc;
+	if ((rc = dev_alloc(&c->d_rad, 3 * cap))) return rc;
+	if ((rc = dev_alloc(&c->d_acc, static_cast<size_t>(K) * 3 * npix))) return rc;
+	if ((rc = dev_alloc(&c->d_fb, static_cast<size_t>(npix)))) return rc;
+	c->counts_bytes = (static_cast<size_t>(mb) + 1) * 4 * sizeof(uint32_t);
+	if ((rc = dev_alloc(&c->d_counts, (static_cast<size_t>(mb) + 1) * 4))) return rc;
+	if (!c->d_stats) { if ((rc = dev_alloc(&c->d_stats, static_cast<size_t>(ST_COUNT)))) return rc; CU(cudaMemset(c->d_stats, 0, ST_COUNT * sizeof(unsigned long long))); }
+	if (!c->d_batch) { if ((rc = dev_alloc(&c->d_batch, static_cast<size_t>(1)))) return rc; }
+	CU(cudaMemset(c->d_rad, 0, 3 * cap * sizeof(float)));
+	CU(cudaMemset(c->d_acc, 0, static_cast<size_t>(K) * 3 * npix * sizeof(float)));
+	Params& p = c->params;
+	p.frame.width = w; p.frame.height = h; p.frame.h_tiles = w / 16; p.frame.npix = npix;
+	p.frame.max_bounces = mb; p.frame.buckets = K; p.frame.flags = c->cfg.flags;
+	for (int s = 0; s < 2; s++) { p.q.A[s] = c->d_A[s]; p.q.B[s] = c->d_B[s]; p.q.T[s] = c->d_T[s]; }
+	p.q.H = c->d_H; p.q.SA = c->d_SA; p.q.SB = c->d_SB; p.q.SL = c->d_SL; p.q.cap = static_cast<uint32_t>(cap);
+	p.cnt.paths = c->d_counts; p.cnt.shadow = c->d_counts + (mb + 1); p.cnt.work_a = c->d_counts + 2 * (mb + 1); p.cnt.work_b = c->d_counts + 3 * (mb + 1);
+	p.cnt.stats = c->d_stats;
+	p.batch = c->d_batch; p.rad = c->d_rad; p.acc = c->d_acc;
+	c->accumulations = 0;
+	drop_graph(c);
+	return B2R_OK;
+}
+
+int compute_grids(b2r_ctx* c) {
+	auto occ = [&](const void* fn, int block, int* out) -> int {
+		int n = 0; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, block, 0));
+		*out = (n < 1 ? 1 : n) * c->sm_count; return B2R_OK;
+	};
+	int rc;
+	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<true, false>), kBlock, &c->grid_brute_first))) return rc;
+	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<false, false>), kBlock, &c->grid_brute))) return rc;
+	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_closest<false>), kTravBlock, &c->grid_closest))) return rc;
+	if ((rc = occ(reinterpret_cast<const void*>(&k_shade), kBlock, &c->grid_shade))) return rc;
+	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_shadow<false>), kTravBlock, &c->grid_shadow))) return rc;
+	c->grid_stream = c->sm_count * 8;
+	return B2R_OK;
+}
+
+// One launch; in profiling mode bracketed by events.
+template <typename F> int launch(b2r_ctx* c, int kind, bool profile, F&& f) {
+	b2r_ctx::Timed t{kind, nullptr, nullptr};
+	if (profile) { CU(cudaEventCreate(&t.a)); CU(cudaEventCreate(&t.b)); CU(cudaEventRecord(t.a, c->stream)); }
+	f();
+	CU(cudaGetLastError());
+	if (profile) { CU(cudaEventRecord(t.b, c->stream)); c->timed.push_back(t); }
+	c->launches++;
+	return B2R_OK;
+}
+
+// Enqueue one wavefront batch (everything after k_set_batch): counters reset, max_bounces rounds, fold into buckets.
+int enqueue_batch(b2r_ctx* c, bool profile) {
+	const Params& p = c->params;
+	const bool count = (c->cfg.flags & B2R_FLAG_COUNT_TESTS) != 0;
+	const uint32_t mb = c->cfg.max_bounces;
+	cudaStream_t st = c->stream;
+	CU(cudaMemsetAsync(c->d_counts, 0, c->counts_bytes, st));
+	int rc;
+	if (!c->use_bvh) {
+		for (uint32_t b = 0; b < mb; b++) {
+			rc = launch(c, KK_BRUTE, profile, [&] {
+				if (b == 0) { if (count) k_bounce_brute<true, true><<<c->grid_brute_first, kBlock, 0, st>>>(p, b); else k_bounce_brute<true, false><<<c->grid_brute_first, kBlock, 0, st>>>(p, b); }
+				else { if (count) k_bounce_brute<false, true><<<c->grid_brute, kBlock, 0, st>>>(p, b); else k_bounce_brute<false, false><<<c->grid_brute, kBlock, 0, st>>>(p, b); }
+			});
+			if (rc) return rc;
+		}
+	} else {
+		if ((rc = launch(c, KK_GENERATE, profile, [&] { k_generate<<<c->grid_stream, kBlock, 0, st>>>(p); }))) return rc;
+		const bool mis = !(c->cfg.flags & B2R_FLAG_NO_MIS);
+		for (uint32_t b = 0; b < mb; b++) {
+			if ((rc = launch(c, KK_CLOSEST, profile, [&] { if (count) k_intersect_closest<true><<<c->grid_closest, kTravBlock, 0, st>>>(p, b); else k_intersect_closest<false><<<c->grid_closest, kTravBlock, 0, st>>>(p, b); }))) return rc;
+			if ((rc = launch(c, KK_SHADE, profile, [&] { k_shade<<<c->grid_shade, kBlock, 0, st>>>(p, b); }))) return rc;
+			if (mis && b + 1 < mb) {
+				if ((rc = launch(c, KK_SHADOW, profile, [&] { if (count) k_intersect_shadow<true><<<c->grid_shadow, kTravBlock, 0, st>>>(p, b); else k_intersect_shadow<false><<<c->grid_shadow, kTravBlock, 0, st>>>(p, b); }))) return rc;
+			}
+		}
+	}
+	return launch(c, KK_ACCUMULATE, profile, [&] { k_accumulate<<<c->grid_stream, kBlock, 0, st>>>(p); });
+}
+
+int run_batch(b2r_ctx* c, const BatchArgs& args) {
+	const bool no_graph = (c->cfg.flags & B2R_FLAG_NO_GRAPH) != 0;
+	k_set_batch<<<1, kMaxSlots, 0, c->stream>>>(c->d_batch, args);
+	CU(cudaGetLastError());
+	if (no_graph) return enqueue_batch(c, true);
+	if (!c->graph_valid) {
+		drop_graph(c);
+		cudaGraph_t graph = nullptr;
+		const uint64_t before = c->launches;
+		CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+		int rc = enqueue_batch(c, false);
+		cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+		c->launches = before;
+		if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+		if (e != cudaSuccess) return fail(B2R_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+		e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+		cudaGraphDestroy(graph);
+		if (e != cudaSuccess) return fail(B2R_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+		c->graph_valid = true;
+	}
+	CU(cudaGraphLaunch(c->graph_exec, c->stream));
+	const uint32_t mb = c->cfg.max_bounces;
+	const bool mis = !(c->cfg.flags & B2R_FLAG_NO_MIS);
+	c->launches += c->use_bvh ? 2 + static_cast<uint64_t>(mb) * 2 + (mis ? mb - 1 : 0) : static_cast<uint64_t>(mb) + 1;
+	return B2R_OK;
+}
+
+int collect_timings(b2r_ctx* c) {
+	if (c->timed.empty()) return B2R_OK;
+	CU(cudaStreamSynchronize(c->stream));
+	for (auto& t : c->timed) {
+		float ms = 0.0f; CU(cudaEventElapsedTime(&ms, t.a, t.b));
+		c->kernel_ms[t.kind] += ms; c->kernel_launches[t.kind]++;
+		cudaEventDestroy(t.a); cudaEventDestroy(t.b);
+	}
+	c->timed.clear();
+	return B2R_OK;
+}
+
+bool owns_sample(const b2r_ctx* c, uint32_t acc) {
+	const uint32_t stride = c->cfg.bucket_stride;
+	if (stride <= 1) return true;
+	return ((acc % c->cfg.buckets) % stride) == c->cfg.bucket_first;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* b2r_last_error(void) { return g_error.c_str(); }
+int b2r_abi_version(void) { return B2R_ABI_VERSION; }
+
+int b2r_create(b2r_ctx** out, const b2r_config* cfg) {
+	if (!out || !cfg) return fail(B2R_ERR_ARG, "null argument");
+	*out = nullptr;
+	if (cfg->width == 0 || cfg->height == 0 || cfg->width % 16 || cfg->height % 16) return fail(B2R_ERR_ARG, "width/height must be non-zero multiples of 16 (Renderer::RequiredTiling)");
+	if (static_cast<uint64_t>(cfg->width) * cfg->height > kPixMask) return fail(B2R_ERR_ARG, "image too large (2^26 pixels max)");
+	if (cfg->buckets < 1 || cfg->buckets > 64) return fail(B2R_ERR_ARG, "buckets must be in 1..64");
+	if (cfg->max_bounces < 1 || cfg->max_bounces > 1024) return fail(B2R_ERR_ARG, "max_bounces must be in 1..1024");
+	if (cfg->bucket_stride > 1 && cfg->bucket_first >= cfg->bucket_stride) return fail(B2R_ERR_ARG, "bucket_first must be < bucket_stride");
+	if (cfg->samples_in_flight > static_cast<uint32_t>(kMaxSlots)) return fail(B2R_ERR_ARG, "samples_in_flight must be <= 64");
+	int n_dev = 0;
+	cudaError_t e = cudaGetDeviceCount(&n_dev);
+	if (e != cudaSuccess || n_dev == 0) return fail(B2R_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libb2r has no CPU fallback)");
+	if (cfg->device < 0 || cfg->device >= n_dev) return fail(B2R_ERR_ARG, "device ordinal out of range");
+	b2r_ctx* c = new b2r_ctx();
+	c->cfg = *cfg;
+	c->slots = cfg->samples_in_flight ? cfg->samples_in_flight : 8u;
+	int rc = ensure_device(c);
+	if (!rc) { cudaDeviceProp prop; e = cudaGetDeviceProperties(&prop, cfg->device); if (e != cudaSuccess) rc = fail(B2R_ERR_CUDA, cudaGetErrorString(e)); else c->sm_count = prop.multiProcessorCount; }
+	if (!rc) { e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking); if (e != cudaSuccess) rc = fail(B2R_ERR_CUDA, cudaGetErrorString(e)); c->stream = c->own_stream; }
+	if (!rc) rc = compute_grids(c);
+	if (!rc) rc = alloc_frame(c);
+	if (rc) { b2r_destroy(c); return rc; }
+	*out = c;
+	return B2R_OK;
+}
+
+void b2r_destroy(b2r_ctx* c) {
+	if (!c) return;
+	cudaSetDevice(c->cfg.device);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	drop_graph(c);
+	for (auto& t : c->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+	dev_free(&c->d_prims); dev_free(&c->d_mat_albedo); dev_free(&c->d_mat_emission); dev_free(&c->d_light_sphere); dev_free(&c->d_light_emit);
+	dev_free(&c->d_hdri); dev_free(&c->d_prim_mat); dev_free(&c->d_wide);
+	for (int s = 0; s < 2; s++) { dev_free(&c->d_A[s]); dev_free(&c->d_B[s]); dev_free(&c->d_T[s]); }
+	dev_free(&c->d_H); dev_free(&c->d_SA); dev_free(&c->d_SB); dev_free(&c->d_SL); dev_free(&c->d_rad); dev_free(&c->d_acc); dev_free(&c->d_fb);
+	dev_free(&c->d_counts); dev_free(&c->d_stats); dev_free(&c->d_batch);
+	if (c->own_stream) cudaStreamDestroy(c->own_stream);
+	delete c;
+}
+
+int b2r_resize(b2r_ctx* c, uint32_t width, uint32_t height) {
+	if (!c) return fail(B2R_ERR_ARG, "null context");
+	if (width == 0 || height == 0 || width % 16 || height % 16) return fail(B2R_ERR_ARG, "width/height must be non-zero multiples of 16");
+	if (static_cast<uint64_t>(width) * height > kPixMask) return fail(B2R_ERR_ARG, "image too large");
+	int rc = ensure_device(c); if (rc) return rc;
+	CU(cudaStreamSynchronize(c->stream));
+	if (width == c->cfg.width && height == c->cfg.height) return b2r_reset(c);
+	c->cfg.width = width; c->cfg.height = height;
+	return alloc_frame(c);
+}
+
+int b2r_reset(b2r_ctx* c) {
+	if (!c) return fail(B2R_ERR_ARG, "null context");
+	int rc = ensure_device(c); if (rc) return rc;
+	c->accumulations = 0;
+	const size_t npix = static_cast<size_t>(c->cfg.width) * c->cfg.height;
+	CU(cudaMemsetAsync(c->d_acc, 0, static_cast<size_t>(c->cfg.buckets) * 3 * npix * sizeof(float), c->stream));
+	return B2R_OK;
+}
+
+int b2r_set_stream(b2r_ctx* c, void* cuda_stream) {
+	if (!c) return fail(B2R_ERR_ARG, "null context");
+	int rc = ensure_device(c); if (rc) return rc;
+	CU(cudaStreamSynchronize(c->stream));
+	c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+	drop_graph(c);
+	return B2R_OK;
+}
+
+int b2r_sync(b2r_ctx* c) {
+	if (!c) return fail(B2R_ERR_ARG, "null context");
+	int rc = ensure_device(c); if (rc) return rc;
+	CU(cudaStreamSynchronize(c->stream));
+	return collect_timings(c);
+}
+
+int b2r_set_flags(b2r_ctx* c, uint32_t flags) {
+	if (!c) return fail(B2R_ERR_ARG, "null context");
+	int rc = ensure_device(c); if (rc) return rc;
+	CU(cudaStreamSynchronize(c->stream));
+	c->cfg.flags = flags; c->params.frame.flags = flags;
+	if (c->have_scene) {
+		const uint32_t n = c->params.scene.n_prims;
+		c->use_bvh = (flags & B2R_FLAG_FORCE_BVH) ? true : (flags & B2R_FLAG_FORCE_BRUTE) ? false : n > 32;
+	}
+	drop_graph(c);
+	return B2R_OK;
+}
+
+int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* nodes, uint32_t n_prims, uint32_t n_nodes,
+                     const b2r_material* materials, uint32_t n_mat, const int32_t* light_geom_idx, uint32_t n_lights,
+                     const b2r_sphere* geometry, uint32_t n_geom, const float ambient[3], const float* hdri_rgba, int32_t hdri_w, int32_t hdri_h) {
+	if (!c || !prims || !nodes || !materials || !geometry || n_prims == 0 || n_mat == 0) return fail(B2R_ERR_ARG, "null or empty scene array");
+	if (n_geom != n_prims) return fail(B2R_ERR_ARG, "geometry and BVH-order primitive counts differ");
+	if (n_lights && !light_geom_idx) return fail(B2R_ERR_ARG, "null light list");
+	if (!validate_reference_bvh(nodes, n_nodes, n_prims)) return fail(B2R_ERR_BVH, "node array is not a 2n-1 binary tree with adjacent children and single-sphere leaves");
+	const float amb[3] = {ambient ? ambient[0] : 0.0f, ambient ? ambient[1] : 0.0f, ambient ? ambient[2] : 0.0f};
+	const bool has_ambient = sel_max(amb[0], sel_max(amb[1], amb[2])) > 0.0f;
+	if (has_ambient && (!hdri_rgba || hdri_w <= 0 || hdri_h <= 0)) return fail(B2R_ERR_ARG, "ambient > 0 needs an HDRI (the reference terminates without one, Application.cpp:225-229)");
+	for (uint32_t i = 0; i < n_prims; i++) if (prims[i].material_ID < 0 || static_cast<uint32_t>(prims[i].material_ID) >= n_mat) return fail(B2R_ERR_ARG, "material_ID out of range");
+	for (uint32_t i = 0; i < n_lights; i++) if (light_geom_idx[i] < 0 || static_cast<uint32_t>(light_geom_idx[i]) >= n_geom) return fail(B2R_ERR_ARG, "light index out of range");
+	int rc = ensure_device(c); if (rc) return rc;
+	CU(cudaStreamSynchronize(c->stream));
+
+	flatten_bvh(nodes, n_nodes, prims, n_prims, c->wide_host);
+	if (c->wide_host.max_stack > static_cast<uint32_t>(kTraversalStack)) return fail(B2R_ERR_BVH, "tree needs a deeper traversal stack than kTraversalStack");
+
+	PackedScene ps; pack_scene(prims, n_prims, materials, n_mat, light_geom_idx, n_lights, geometry, ps);
+	auto &h_prims = ps.prims, &h_alb = ps.mat_albedo, &h_em = ps.mat_emission, &h_ls = ps.light_sphere, &h_le = ps.light_emit; auto& h_pm = ps.prim_mat;
+	if ((rc = dev_alloc(&c->d_prims, h_prims.size()))) return rc;
+	if ((rc = dev_alloc(&c->d_prim_mat, h_pm.size()))) return rc;
+	if ((rc = dev_alloc(&c->d_mat_albedo, h_alb.size()))) return rc;
+	if ((rc = dev_alloc(&c->d_mat_emission, h_em.size()))) return rc;
+	if ((rc = dev_alloc(&c->d_light_sphere, h_ls.size()))) return rc;
+	if ((rc = dev_alloc(&c->d_light_emit, h_le.size()))) return rc;
+	if ((rc = dev_alloc(&c->d_wide, c->wide_host.nodes.size()))) return rc;
+	CU(cudaMemcpy(c->d_prims, h_prims.data(), h_prims.size() * sizeof(float4), cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(c->d_prim_mat, h_pm.data(), h_pm.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(c->d_mat_albedo, h_alb.data(), h_alb.size() * sizeof(float4), cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(c->d_mat_emission, h_em.data(), h_em.size() * sizeof(float4), cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(c->d_light_sphere, h_ls.data(), h_ls.size() * sizeof(float4), cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(c->d_light_emit, h_le.data(), h_le.size() * sizeof(float4), cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(c->d_wide, c->wide_host.nodes.data(), c->wide_host.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice));
+	if (has_ambient) {
+		const size_t texels = static_cast<size_t>(hdri_w) * hdri_h;
+		if ((rc = dev_alloc(&c->d_hdri, texels))) return rc;
+		CU(cudaMemcpy(c->d_hdri, hdri_rgba, texels * sizeof(float4), cudaMemcpyHostToDevice));
+	}
+	SceneDev& s = c->params.scene;
+	s.prims = c->d_prims; s.prim_mat = c->d_prim_mat; s.mat_albedo = c->d_mat_albedo; s.mat_emission = c->d_mat_emission;
+	s.light_sphere = c->d_light_sphere; s.light_emit = c->d_light_emit; s.wide = c->d_wide; s.hdri = has_ambient ? c->d_hdri : nullptr;
+	s.n_prims = n_prims; s.n_mat = n_mat; s.n_lights = n_lights;
+	s.light_sel_pdf = 1.0f / static_cast<float>(n_lights);  // Renderer.hpp:78
+	s.ambient[0] = amb[0]; s.ambient[1] = amb[1]; s.ambient[2] = amb[2]; s.has_ambient = has_ambient ? 1 : 0;
+	s.hdri_w = hdri_w; s.hdri_h = hdri_h; s.hdri_fw = static_cast<float>(hdri_w - 1); s.hdri_fh = static_cast<float>(hdri_h - 1);  // Application.cpp:230-231
+	c->use_bvh = (c->cfg.flags & B2R_FLAG_FORCE_BVH) ? true : (c->cfg.flags & B2R_FLAG_FORCE_BRUTE) ? false : n_prims > 32;
+	c->have_scene = true;
+	drop_graph(c);
+	return B2R_OK;
+}
+
+int b2r_set_camera(b2r_ctx* c, const float pos[3], const float q[4], float half_width, float half_height, float z, float exposure) {
+	if (!c || !pos || !q) return fail(B2R_ERR_ARG, "null argument");
+	int rc = ensure_device(c); if (rc) return rc;
+	CU(cudaStreamSynchronize(c->stream));
+	CameraParams& cam = c->params.frame.cam;
+	cam.px = pos[0]; cam.py = pos[1]; cam.pz = pos[2]; cam.qw = q[0]; cam.qx = q[1]; cam.qy = q[2]; cam.qz = q[3];
+	cam.half_width = half_width; cam.half_height = half_height; cam.z = z; cam.exposure = exposure;
+	c->have_camera = true;
+	drop_graph(c);
+	return B2R_OK;
+}
+
+int b2r_accumulate(b2r_ctx* c, uint32_t n_samples) {
+	if (!c) return fail(B2R_ERR_ARG, "null context");
+	if (!c->have_scene || !c->have_camera) return fail(B2R_ERR_STATE, "upload_scene and set_camera must precede accumulate");
+	int rc = ensure_device(c); if (rc) return rc;
+	BatchArgs args; args.n = 0;
+	for (uint32_t s = 0; s < n_samples; s++) {
+		const uint32_t acc = ++c->accumulations;  // pre-increment: the first sample has index 1 (Renderer.hpp:74, Q1)
+		if (owns_sample(c, acc)) args.acc[args.n++] = acc;
+		if (args.n == c->slots || (s + 1 == n_samples && args.n)) { if ((rc = run_batch(c, args))) return rc; args.n = 0; }
+	}
+	return B2R_OK;
+}
+
+int b2r_resolve(b2r_ctx* c, float* rgba_out_host, int tonemap) { return b2r_resolve_from(c, nullptr, rgba_out_host, tonemap); }
+
+int b2r_resolve_from(b2r_ctx* c, const void* dev_buckets, float* rgba_out_host, int tonemap) {
+	if (!c) return fail(B2R_ERR_ARG, "null context");
+	int rc = ensure_device(c); if (rc) return rc;
+	if (c->accumulations == 0 || c->accumulations % c->cfg.buckets) return B2R_ERR_NOT_READY;  // Renderer.hpp:437
+	const float scale = c->params.frame.cam.exposure / static_cast<float>(c->accumulations / c->cfg.buckets);  // :439
+	const bool profile = (c->cfg.flags & B2R_FLAG_NO_GRAPH) != 0;
+	Params rp = c->params;
+	if (dev_buckets) rp.acc = const_cast<float*>(static_cast<const float*>(dev_buckets));
+	rc = launch(c, KK_RESOLVE, profile, [&] { k_resolve<<<c->grid_stream, kBlock, 0, c->stream>>>(rp, c->d_fb, scale, tonemap); });
+	if (rc) return rc;
+	if (rgba_out_host) CU(cudaMemcpyAsync(rgba_out_host, c->d_fb, static_cast<size_t>(c->params.frame.npix) * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return collect_timings(c);
+}
+
+int b2r_get_accumulations(b2r_ctx* c, uint32_t* out) { if (!c || !out) return fail(B2R_ERR_ARG, "null argument"); *out = c->accumulations; return B2R_OK; }
+int b2r_set_accumulations(b2r_ctx* c, uint32_t acc) { if (!c) return fail(B2R_ERR_ARG, "null context"); c->accumulations = acc; return B2R_OK; }
+
+int b2r_read_buckets(b2r_ctx* c, float* out_host) {
+	if (!c || !out_host) return fail(B2R_ERR_ARG, "null argument");
+	int rc = ensure_device(c); if (rc) return rc;
+	CU(cudaMemcpyAsync(out_host, c->d_acc, static_cast<size_t>(c->cfg.buckets) * 3 * c->params.frame.npix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return collect_timings(c);
+}
+int b2r_write_buckets(b2r_ctx* c, const float* in_host) {
+	if (!c || !in_host) return fail(B2R_ERR_ARG, "null argument");
+	int rc = ensure_device(c); if (rc) return rc;
+	CU(cudaMemcpyAsync(c->d_acc, in_host, static_cast<size_t>(c->cfg.buckets) * 3 * c->params.frame.npix * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return B2R_OK;
+}
+int b2r_device_buckets(b2r_ctx* c, void** dev_ptr, size_t* bytes) {
+	if (!c || !dev_ptr || !bytes) return fail(B2R_ERR_ARG, "null argument");
+	*dev_ptr = c->d_acc; *bytes = static_cast<size_t>(c->cfg.buckets) * 3 * c->params.frame.npix * sizeof(float);
+	return B2R_OK;
+}
+int b2r_device_framebuffer(b2r_ctx* c, void** dev_ptr, size_t* bytes) {
+	if (!c || !dev_ptr || !bytes) return fail(B2R_ERR_ARG, "null argument");
+	*dev_ptr = c->d_fb; *bytes = static_cast<size_t>(c->params.frame.npix) * sizeof(float4);
+	return B2R_OK;
+}
+
+int b2r_read_counters(b2r_ctx* c, uint64_t out[10]) {
+	if (!c || !out) return fail(B2R_ERR_ARG, "null argument");
+	int rc = ensure_device(c); if (rc) return rc;
+	unsigned long long h[ST_COUNT];
+	CU(cudaMemcpyAsync(h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	out[0] = h[ST_EXT]; out[1] = h[ST_SHADOW]; out[2] = h[ST_HITS]; out[3] = h[ST_TERM]; out[4] = h[ST_DROPPED]; out[5] = h[ST_SPHERE]; out[6] = h[ST_BOX];
+	out[7] = c->launches; out[8] = h[ST_EVENTS]; out[9] = 0;
+	return collect_timings(c);
+}
+int b2r_reset_counters(b2r_ctx* c) {
+	if (!c) return fail(B2R_ERR_ARG, "null context");
+	int rc = ensure_device(c); if (rc) return rc;
+	CU(cudaMemsetAsync(c->d_stats, 0, ST_COUNT * sizeof(unsigned long long), c->stream));
+	c->launches = 0;
+	return B2R_OK;
+}
+int b2r_read_kernel_times(b2r_ctx* c, double ms_out[8], uint64_t launches_out[8], int reset) {
+	if (!c || !ms_out || !launches_out) return fail(B2R_ERR_ARG, "null argument");
+	int rc = ensure_device(c); if (rc) return rc;
+	if ((rc = collect_timings(c))) return rc;
+	for (int i = 0; i < 8; i++) { ms_out[i] = c->kernel_ms[i]; launches_out[i] = c->kernel_launches[i]; if (reset) { c->kernel_ms[i] = 0; c->kernel_launches[i] = 0; } }
+	return B2R_OK;
+}
+
+int b2r_generate_rays(b2r_ctx* c, uint32_t acc, float* out_host) {
+	if (!c || !out_host) return fail(B2R_ERR_ARG, "null argument");
+	if (!c->have_camera) return fail(B2R_ERR_STATE, "set_camera first");
+	int rc = ensure_device(c); if (rc) return rc;
+	float* d = nullptr; const size_t n = static_cast<size_t>(c->params.frame.npix) * 6;
+	if ((rc = dev_alloc(&d, n))) return rc;
+	k_tap_generate<<<c->grid_stream, kBlock, 0, c->stream>>>(c->params, acc, d);
+	cudaError_t e = cudaGetLastError();
+	if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	cudaFree(d); c->launches++;
+	if (e != cudaSuccess) return fail(B2R_ERR_CUDA, cudaGetErrorString(e));
+	return B2R_OK;
+}
+
+static int trace_common(b2r_ctx* c, const float* rays, const float* tfar_in, uint32_t n, int shadow, float* tfar_out, int32_t* prim_out, uint8_t* occ_out) {
+	if (!c || !rays) return fail(B2R_ERR_ARG, "null argument");
+	if (!c->have_scene) return fail(B2R_ERR_STATE, "upload_scene first");
+	if (n == 0) return B2R_OK;
+	int rc = ensure_device(c); if (rc) return rc;
+	float *d_rays = nullptr, *d_tin = nullptr, *d_tout = nullptr; int32_t* d_prim = nullptr; uint8_t* d_occ = nullptr;
+	if ((rc = dev_alloc(&d_rays, static_cast<size_t>(n) * 6)) || (rc = dev_alloc(&d_tin, static_cast<size_t>(n))) || (rc = dev_alloc(&d_tout, static_cast<size_t>(n))) ||
+	    (rc = dev_alloc(&d_prim, static_cast<size_t>(n))) || (rc = dev_alloc(&d_occ, static_cast<size_t>(n)))) { cudaFree(d_rays); cudaFree(d_tin); cudaFree(d_tout); cudaFree(d_prim); cudaFree(d_occ); return rc; }
+	cudaError_t e = cudaMemcpyAsync(d_rays, rays, static_cast<size_t>(n) * 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+	if (e == cudaSuccess && shadow) e = cudaMemcpyAsync(d_tin, tfar_in, static_cast<size_t>(n) * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+	if (e == cudaSuccess) {
+		k_tap_trace<<<c->grid_stream, kBlock, 0, c->stream>>>(c->params.scene, d_rays, d_tin, n, c->use_bvh ? 1 : 0, shadow, d_tout, d_prim, d_occ);
+		e = cudaGetLastError(); c->launches++;
+	}
+	if (e == cudaSuccess && !shadow) { e = cudaMemcpyAsync(tfar_out, d_tout, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost, c->stream); if (e == cudaSuccess) e = cudaMemcpyAsync(prim_out, d_prim, static_cast<size_t>(n) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream); }
+	if (e == cudaSuccess && shadow) e = cudaMemcpyAsync(occ_out, d_occ, static_cast<size_t>(n), cudaMemcpyDeviceToHost, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	cudaFree(d_rays); cudaFree(d_tin); cudaFree(d_tout); cudaFree(d_prim); cudaFree(d_occ);
+	if (e != cudaSuccess) return fail(B2R_ERR_CUDA, cudaGetErrorString(e));
+	return B2R_OK;
+}
+int b2r_trace_closest(b2r_ctx* c, const float* rays_host, uint32_t n, float* tfar_out, int32_t* prim_out) {
+	if (!tfar_out || !prim_out) return fail(B2R_ERR_ARG, "null argument");
+	return trace_common(c, rays_host, nullptr, n, 0, tfar_out, prim_out, nullptr);
+}
+int b2r_trace_shadow(b2r_ctx* c, const float* rays_host, const float* tfar_host, uint32_t n, uint8_t* occluded_out) {
+	if (!tfar_host || !occluded_out) return fail(B2R_ERR_ARG, "null argument");
+	return trace_common(c, rays_host, tfar_host, n, 1, nullptr, nullptr, occluded_out);
+}
+int b2r_read_wide_nodes(b2r_ctx* c, void* out_host, uint32_t* n_wide_nodes, uint32_t* max_stack) {
+	if (!c) return fail(B2R_ERR_ARG, "null context");
+	if (!c->have_scene) return fail(B2R_ERR_STATE, "upload_scene first");
+	if (n_wide_nodes) *n_wide_nodes = static_cast<uint32_t>(c->wide_host.nodes.size());
+	if (max_stack) *max_stack = c->wide_host.max_stack;
+	if (out_host) std::memcpy(out_host, c->wide_host.nodes.data(), c->wide_host.nodes.size() * sizeof(WideNode));
+	return B2R_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,297 @@
+// b2r_host.cpp — host-side scene preparation (no CUDA): the reference's SAH sweep BVH with bit-identical node and
+// leaf order (BVH.hpp:90-206), the 4-wide flattening for the GPU, the light list (Scene.hpp:12-16) and the camera
+// set-up (Camera.hpp:21-32,47-50). The reference builds its BVH on one host thread as well; only the flattening is new.
+#include "b2r_host.h"
+#include "b2r_math.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+namespace b2r {
+namespace {
+
+struct Box { float lo[3], hi[3]; };
+
+inline Box void_box() {  // Node() default: min = +FLT_MAX, max = -FLT_MAX (BVH.hpp:28-29)
+	return Box{{FLT_MAX, FLT_MAX, FLT_MAX}, {-FLT_MAX, -FLT_MAX, -FLT_MAX}};
+}
+inline void grow(Box& a, const Box& b) {  // Node::operator|= (BVH.hpp:35-39) with glm::min / glm::max
+	for (int k = 0; k < 3; k++) { a.lo[k] = sel_min(a.lo[k], b.lo[k]); a.hi[k] = sel_max(a.hi[k], b.hi[k]); }
+}
+// Node::half_area() (BVH.hpp:58-67). The loop there ends before the x extent is used, so the SAH "area" is just
+// extent.y * extent.z. Reproduced because it decides every split.
+inline float sah_measure(const Box& b) {
+	const float ey = b.hi[1] - b.lo[1], ez = b.hi[2] - b.lo[2];
+	return 0.0f + ey * ez;
+}
+inline int widest_axis(const Box& b) {  // Node::largest_axis (BVH.hpp:48-54)
+	const float e[3] = {b.hi[0] - b.lo[0], b.hi[1] - b.lo[1], b.hi[2] - b.lo[2]};
+	int best = 0;
+	if (e[best] < e[1]) best = 1;
+	if (e[best] < e[2]) best = 2;
+	return best;
+}
+inline b2r_bvh_node to_node(const Box& b, uint32_t first, uint32_t count) {
+	b2r_bvh_node n;
+	for (int k = 0; k < 3; k++) { n.min_bound[k] = b.lo[k]; n.max_bound[k] = b.hi[k]; }
+	n.first_id = first; n.prim_count = count;
+	return n;
+}
+
+struct BuildJob { uint32_t node, begin, count; };
+
+}  // namespace
+
+void build_reference_bvh(const b2r_sphere* geometry, uint32_t n, std::vector<b2r_bvh_node>& nodes,
+                         std::vector<b2r_sphere>& prims, std::vector<uint32_t>& prim_ids) {
+	nodes.clear(); prims.clear(); prim_ids.clear();
+	if (n == 0) { nodes.push_back(to_node(void_box(), 0, 0)); return; }
+	nodes.reserve(2u * static_cast<size_t>(n));
+
+	// per-primitive boxes (Sphere::bounds, Primitives.hpp:13-16) and centroids ((max+min)*0.5, BVH.hpp:55-57)
+	std::vector<Box> box(n);
+	std::vector<float> centroid[3];
+	for (auto& c : centroid) c.resize(n);
+	for (uint32_t i = 0; i < n; i++) {
+		const float r = sqrtf(geometry[i].radius_sq);
+		for (int k = 0; k < 3; k++) {
+			box[i].lo[k] = geometry[i].position[k] - r;
+			box[i].hi[k] = geometry[i].position[k] + r;
+			centroid[k][i] = (box[i].hi[k] + box[i].lo[k]) * 0.5f;
+		}
+	}
+	// three index lists ordered by centroid (BVH.hpp:118-122). The reference's std::ranges::sort leaves tie order
+	// implementation-defined (Q19); ties are broken by the lower original index here (== MSVC for n <= 32).
+	std::vector<uint32_t> order[3];
+	for (int k = 0; k < 3; k++) {
+		order[k].resize(n);
+		std::iota(order[k].begin(), order[k].end(), 0u);
+		const float* key = centroid[k].data();
+		std::stable_sort(order[k].begin(), order[k].end(), [key](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+	}
+
+	Box root = void_box();
+	for (uint32_t i = 0; i < n; i++) grow(root, box[i]);  // BVH.hpp:125
+	nodes.push_back(to_node(root, 0, 0));
+
+	std::vector<float> suffix_cost(n);     // accum_cost: SAH cost of the right part starting at i (BVH.hpp:154)
+	std::vector<uint8_t> goes_left(n);
+	std::vector<uint32_t> scratch(n);
+	std::vector<BuildJob> todo;
+	todo.push_back({0u, 0u, n});
+	while (!todo.empty()) {
+		const BuildJob job = todo.back(); todo.pop_back();
+		if (job.count <= 1) {  // leaf, always one sphere (BVH.hpp:133-137)
+			nodes[job.node].first_id = job.begin; nodes[job.node].prim_count = job.count;
+			continue;
+		}
+		const uint32_t begin = job.begin, end = job.begin + job.count;
+		const uint32_t pair = static_cast<uint32_t>(nodes.size());
+		nodes[job.node].first_id = pair;
+		Box here; for (int k = 0; k < 3; k++) { here.lo[k] = nodes[job.node].min_bound[k]; here.hi[k] = nodes[job.node].max_bound[k]; }
+
+		// fallback split = median on the widest axis, at the "do not split" cost area*(count-1) (BVH.hpp:144, :80-82)
+		uint32_t cut = begin + (job.count + 1) / 2; int cut_axis = widest_axis(here);
+		float cut_cost = sah_measure(here) * (static_cast<float>(job.count) - 1.0f);
+		for (int k = 0; k < 3; k++) {
+			const uint32_t* ids = order[k].data();
+			// right-to-left sweep. The reference's chunked early exit degenerates into one full sweep (Q18), and its
+			// `first_right` guard can never cut the left sweep short, so neither appears here.
+			Box acc = void_box();
+			for (uint32_t i = end - 1; i > begin; --i) {
+				grow(acc, box[ids[i]]);
+				suffix_cost[i] = sah_measure(acc) * static_cast<float>(end - i);
+			}
+			acc = void_box();
+			for (uint32_t i = begin; i + 1 < end; ++i) {  // left-to-right sweep (BVH.hpp:163-170)
+				grow(acc, box[ids[i]]);
+				const float left = sah_measure(acc) * static_cast<float>(i + 1 - begin);
+				if (left > cut_cost) break;
+				const float total = left + suffix_cost[i + 1];
+				if (total < cut_cost) { cut = i + 1; cut_axis = k; cut_cost = total; }
+			}
+		}
+		{  // keep the other two lists consistent with the chosen cut, preserving their order (BVH.hpp:173-184)
+			const uint32_t* ids = order[cut_axis].data();
+			for (uint32_t i = begin; i < cut; ++i) goes_left[ids[i]] = 1;
+			for (uint32_t i = cut; i < end; ++i) goes_left[ids[i]] = 0;
+			for (int k = 0; k < 3; k++) {
+				if (k == cut_axis) continue;
+				uint32_t* a = order[k].data();
+				uint32_t l = begin, r = 0;
+				for (uint32_t i = begin; i < end; ++i) { const uint32_t id = a[i]; if (goes_left[id]) a[l++] = id; else scratch[r++] = id; }
+				std::memcpy(a + l, scratch.data(), static_cast<size_t>(r) * sizeof(uint32_t));
+			}
+		}
+		// child boxes from list 0 (BVH.hpp:109-113,188); larger-measure child stored first, smaller range built first (:190-197)
+		Box part[2] = {void_box(), void_box()};
+		for (uint32_t i = begin; i < cut; ++i) grow(part[0], box[order[0][i]]);
+		for (uint32_t i = cut; i < end; ++i) grow(part[1], box[order[0][i]]);
+		const uint32_t first_is_right = sah_measure(part[0]) < sah_measure(part[1]) ? 1u : 0u;
+		nodes.push_back(to_node(part[first_is_right], 0, 0));
+		nodes.push_back(to_node(part[1 - first_is_right], 0, 0));
+		const uint32_t pb[2] = {begin, cut}, pc[2] = {cut - begin, end - cut};
+		const uint32_t bigger = pc[0] < pc[1] ? 1u : 0u;  // index of the larger range
+		// range r lives in node pair + (r == first_is_right ? 0 : 1)
+		todo.push_back({pair + (bigger ^ first_is_right), pb[bigger], pc[bigger]});
+		todo.push_back({pair + ((1 - bigger) ^ first_is_right), pb[1 - bigger], pc[1 - bigger]});
+	}
+	prims.resize(n); prim_ids.resize(n);
+	for (uint32_t i = 0; i < n; i++) { prim_ids[i] = order[0][i]; prims[i] = geometry[order[0][i]]; }  // BVH.hpp:201-205
+}
+
+bool validate_reference_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, uint32_t n_prims) {
+	if (n_nodes == 0) return false;
+	if (n_prims == 0) return n_nodes == 1;
+	if (n_nodes != 2 * n_prims - 1) return false;
+	for (uint32_t i = 0; i < n_nodes; i++) {
+		if (nodes[i].prim_count == 0) { if (nodes[i].first_id == 0 || static_cast<uint64_t>(nodes[i].first_id) + 1 >= n_nodes) return false; }
+		else if (nodes[i].prim_count != 1 || nodes[i].first_id >= n_prims) return false;
+	}
+	return true;
+}
+
+namespace {
+constexpr float kBoxPad = 4.0e-7f;  // outward padding, relative to |coordinate| + 1
+inline float pad_down(float v) { return v - (fabsf(v) + 1.0f) * kBoxPad; }
+inline float pad_up(float v) { return v + (fabsf(v) + 1.0f) * kBoxPad; }
+inline float surface(const b2r_bvh_node& n) {  // true half surface area: only used to pick which child to open
+	const float ex = n.max_bound[0] - n.min_bound[0], ey = n.max_bound[1] - n.min_bound[1], ez = n.max_bound[2] - n.min_bound[2];
+	return ex * ey + ey * ez + ez * ex;
+}
+inline float int_as_float(int32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
+}  // namespace
+
+void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* prims, uint32_t n_prims, WideBvh& out) {
+	out.nodes.clear(); out.max_stack = 0; out.depth = 0;
+	auto set_empty = [](WideNode& w, int k) { for (int j = 0; j < 8; j++) w.slot[k][j] = 0.0f; w.slot[k][6] = int_as_float(kEmptyLink); };
+	auto set_leaf = [&](WideNode& w, int k, uint32_t prim) {
+		const b2r_sphere& s = prims[prim];
+		w.slot[k][0] = s.position[0]; w.slot[k][1] = s.position[1]; w.slot[k][2] = s.position[2]; w.slot[k][3] = s.radius_sq;
+		w.slot[k][4] = 0.0f; w.slot[k][5] = 0.0f; w.slot[k][6] = int_as_float(~static_cast<int32_t>(prim)); w.slot[k][7] = 0.0f;
+	};
+	if (n_prims == 0 || n_nodes == 0) {
+		WideNode w; for (int k = 0; k < 4; k++) set_empty(w, k);
+		out.nodes.push_back(w); return;
+	}
+	if (nodes[0].prim_count != 0) {  // single sphere: the root is a leaf
+		WideNode w; for (int k = 0; k < 4; k++) set_empty(w, k);
+		set_leaf(w, 0, nodes[0].first_id);
+		out.nodes.push_back(w); return;
+	}
+	// breadth-first: queue entries are binary inner nodes that become wide nodes
+	struct Pending { uint32_t bin; uint32_t level; };
+	std::vector<Pending> queue; queue.push_back({0u, 1u});
+	std::vector<uint32_t> inner_children;   // per wide node: how many of its slots are inner (for the stack bound)
+	out.nodes.reserve(n_nodes / 2 + 1);
+	for (size_t head = 0; head < queue.size(); head++) {
+		const Pending cur = queue[head];
+		out.depth = std::max(out.depth, cur.level);
+		uint32_t kids[4]; int nk = 2;
+		kids[0] = nodes[cur.bin].first_id; kids[1] = kids[0] + 1;
+		while (nk < 4) {  // open the inner child with the largest surface until four slots are used
+			int pick = -1; float best = -1.0f;
+			for (int k = 0; k < nk; k++) if (nodes[kids[k]].prim_count == 0) { const float a = surface(nodes[kids[k]]); if (a > best) { best = a; pick = k; } }
+			if (pick < 0) break;
+			const uint32_t open = kids[pick];
+			kids[pick] = nodes[open].first_id; kids[nk++] = nodes[open].first_id + 1;
+		}
+		WideNode w; uint32_t n_inner = 0;
+		for (int k = 0; k < 4; k++) {
+			if (k >= nk) { set_empty(w, k); continue; }
+			const b2r_bvh_node& c = nodes[kids[k]];
+			if (c.prim_count != 0) { set_leaf(w, k, c.first_id); continue; }
+			w.slot[k][0] = pad_down(c.min_bound[0]); w.slot[k][1] = pad_down(c.min_bound[1]); w.slot[k][2] = pad_down(c.min_bound[2]);
+			w.slot[k][3] = pad_up(c.max_bound[0]); w.slot[k][4] = pad_up(c.max_bound[1]); w.slot[k][5] = pad_up(c.max_bound[2]);
+			w.slot[k][6] = int_as_float(static_cast<int32_t>(queue.size())); w.slot[k][7] = 0.0f;  // its wide index = its queue position
+			queue.push_back({kids[k], cur.level + 1});
+			n_inner++;
+		}
+		out.nodes.push_back(w);
+		inner_children.push_back(n_inner);
+	}
+	// worst-case stack: going into one inner child leaves (inner-1) siblings pushed. Children have larger indices (BFS),
+	// so one reverse pass computes need[node] = max over inner children (inner-1 + need[child]).
+	std::vector<uint32_t> need(out.nodes.size(), 0);
+	for (size_t i = out.nodes.size(); i-- > 0;) {
+		uint32_t worst = 0;
+		for (int k = 0; k < 4; k++) {
+			int32_t link; std::memcpy(&link, &out.nodes[i].slot[k][6], 4);
+			if (link >= 0) worst = std::max(worst, inner_children[i] - 1 + need[static_cast<size_t>(link)]);
+		}
+		need[i] = worst;
+	}
+	out.max_stack = need[0];
+}
+
+void pack_scene(const b2r_sphere* prims, uint32_t n_prims, const b2r_material* materials, uint32_t n_mat,
+                const int32_t* light_geom_idx, uint32_t n_lights, const b2r_sphere* geometry, PackedScene& out) {
+	auto f4 = [](float x, float y, float z, float w) { float4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; };
+	out.prims.resize(n_prims); out.prim_mat.resize(n_prims);
+	for (uint32_t i = 0; i < n_prims; i++) {
+		out.prims[i] = f4(prims[i].position[0], prims[i].position[1], prims[i].position[2], prims[i].radius_sq);
+		out.prim_mat[i] = prims[i].material_ID;
+	}
+	out.mat_albedo.resize(n_mat); out.mat_emission.resize(n_mat);
+	for (uint32_t i = 0; i < n_mat; i++) {
+		const float* e = materials[i].emission;
+		const bool emissive = sel_max(e[0], sel_max(e[1], e[2])) > FLT_EPSILON;  // is_emissive, Renderer.hpp:201
+		out.mat_albedo[i] = f4(materials[i].albedo[0], materials[i].albedo[1], materials[i].albedo[2], emissive ? 1.0f : 0.0f);
+		out.mat_emission[i] = f4(e[0], e[1], e[2], 0.0f);
+	}
+	out.light_sphere.resize(n_lights ? n_lights : 1, f4(0, 0, 0, 0)); out.light_emit.resize(n_lights ? n_lights : 1, f4(0, 0, 0, 0));
+	for (uint32_t i = 0; i < n_lights; i++) {  // NEE reads the light from scene.geometry, original order (Renderer.hpp:261-262,277)
+		const b2r_sphere& g = geometry[light_geom_idx[i]];
+		const float* e = materials[g.material_ID].emission;
+		out.light_sphere[i] = f4(g.position[0], g.position[1], g.position[2], g.radius_sq);
+		out.light_emit[i] = f4(e[0], e[1], e[2], int_as_float(light_geom_idx[i]));
+	}
+}
+
+}  // namespace b2r
+
+// ---------------------------------------------------------------------------------------------- C ABI (host-only part)
+extern "C" {
+
+int b2r_bvh_build(const b2r_sphere* geometry, uint32_t n, b2r_bvh_node* nodes_out, b2r_sphere* prims_out,
+                  uint32_t* prim_ids_out, uint32_t* n_nodes_out) {
+	if ((n && !geometry) || !nodes_out) return B2R_ERR_ARG;
+	std::vector<b2r_bvh_node> nodes; std::vector<b2r_sphere> prims; std::vector<uint32_t> ids;
+	b2r::build_reference_bvh(geometry, n, nodes, prims, ids);
+	std::memcpy(nodes_out, nodes.data(), nodes.size() * sizeof(b2r_bvh_node));
+	if (prims_out && n) std::memcpy(prims_out, prims.data(), prims.size() * sizeof(b2r_sphere));
+	if (prim_ids_out && n) std::memcpy(prim_ids_out, ids.data(), ids.size() * sizeof(uint32_t));
+	if (n_nodes_out) *n_nodes_out = static_cast<uint32_t>(nodes.size());
+	return B2R_OK;
+}
+
+int b2r_find_lights(const b2r_sphere* geometry, uint32_t n, const b2r_material* materials, uint32_t n_mat,
+                    int32_t* out, uint32_t* n_out) {
+	if ((n && !geometry) || (n && !materials) || !n_out) return B2R_ERR_ARG;
+	uint32_t count = 0;
+	for (uint32_t i = 0; i < n; i++) {  // Scene.hpp:12-16: dot(emission, emission) > 0
+		const int32_t m = geometry[i].material_ID;
+		if (m < 0 || static_cast<uint32_t>(m) >= n_mat) return B2R_ERR_ARG;
+		const float* e = materials[m].emission;
+		if (e[0] * e[0] + e[1] * e[1] + e[2] * e[2] > 0.0f) { if (out) out[count] = static_cast<int32_t>(i); count++; }
+	}
+	*n_out = count;
+	return B2R_OK;
+}
+
+int b2r_camera_lookat(const float eye[3], const float dir[3], uint32_t width, uint32_t height, float focal_length_mm,
+                      float exposure, float out11[11]) {
+	if (!eye || !dir || !out11) return B2R_ERR_ARG;
+	out11[0] = eye[0]; out11[1] = eye[1]; out11[2] = eye[2];
+	b2r::look_at_quat(b2r::f3{dir[0], dir[1], dir[2]}, out11 + 3);
+	const float inv_half_tan = (-2.0f / 24.0f) * focal_length_mm;  // Projection::UpdateLens, Camera.hpp:21-26 (24 mm sensor)
+	out11[7] = static_cast<float>(width) * 0.5f;                   // Projection::Resize, Camera.hpp:28-32
+	out11[8] = static_cast<float>(height) * 0.5f;
+	out11[9] = out11[8] * inv_half_tan;
+	out11[10] = exposure;
+	return B2R_OK;
+}
+
+}  // extern "C"

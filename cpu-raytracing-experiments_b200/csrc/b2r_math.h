@@ -1,0 +1,291 @@
+// b2r_math.h — scalar device math of the path tracer (RNG, camera, tangent frames, light sampling, tonemap).
+//
+// Every function is host+device so the CUDA kernels (b2r_kernels.cu) and the host-side scene code
+// (b2r_host.cpp) share one definition. Arithmetic contract (DESIGN.md "Numerics"): IEEE binary32,
+// round-to-nearest, no contraction — the library is compiled with `nvcc -fmad=false` / `g++ -ffp-contract=off`,
+// and a fused multiply-add appears only where fma_rn() is written out (the closest-hit sphere test, which is
+// where the reference uses FMA intrinsics, BVH.hpp:252-260; and box tests, which never decide a result).
+// With that, each function below returns bit-identical results on sm_100a and on the host.
+// file:line citations are into the reference (/root/reference) whose behaviour each function reproduces.
+#pragma once
+#include <stdint.h>
+#include <float.h>
+#include <math.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define B2R_HD __host__ __device__ __forceinline__
+#else
+#define B2R_HD inline
+#endif
+
+namespace b2r {
+
+struct f3 { float x, y, z; };
+struct TangentQuat { float w, x, y; };  // z component is always 0 (Sampling.hpp:149-158)
+
+B2R_HD uint32_t bits(float f) {
+#if defined(__CUDA_ARCH__)
+	return __float_as_uint(f);
+#else
+	uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+B2R_HD float from_bits(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+	return __uint_as_float(u);
+#else
+	float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+B2R_HD float fma_rn(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+	return __fmaf_rn(a, b, c);
+#else
+	return fmaf(a, b, c);
+#endif
+}
+B2R_HD float round_even(float x) {
+#if defined(__CUDA_ARCH__)
+	return rintf(x);
+#else
+	return nearbyintf(x);
+#endif
+}
+B2R_HD bool sign_set(float f) { return (bits(f) >> 31) != 0u; }
+// select-style max/min: NaN and signed-zero behaviour of std::max/std::min/glm::max/glm::min
+B2R_HD float sel_max(float a, float b) { return (a < b) ? b : a; }
+B2R_HD float sel_min(float a, float b) { return (b < a) ? b : a; }
+
+// ------------------------------------------------------------------ counter-based RNG (Random.hpp)
+// One stream per (sample index, pixel seed + branch): state0 = hash_2d(acc, seed + branch) (Renderer.hpp:117,255,362)
+B2R_HD uint32_t hash_2d(uint32_t x, uint32_t y) {  // Random.hpp:45-50
+	const uint32_t m = 0x41c64e6du;
+	uint32_t qx = m * ((x >> 1) ^ y), qy = m * ((y >> 1) ^ x);
+	return m * (qx ^ (qy >> 3));
+}
+B2R_HD uint32_t hash_u32(uint32_t i) {  // Random.hpp:36-43
+	i ^= i >> 16; i *= 0x21f0aaadu; i ^= i >> 15; i *= 0xd35a2d97u; i ^= i >> 15;
+	return i ^ 0xe6fe3bebu;
+}
+struct Pcg {  // Random.hpp:10-29: output(previous state), then LCG step
+	uint32_t state;
+	B2R_HD uint32_t next_u32() {
+		uint32_t v = state;
+		state = v * 747796405u + 2891336453u;
+		v = ((v >> ((v >> 28) + 4u)) ^ v) * 277803737u;
+		return (v >> 22) ^ v;
+	}
+	B2R_HD float next_unit() {  // Random.hpp:5,26-29 — in [0,1], 1.0f reachable (Q4)
+#if defined(__CUDA_ARCH__)
+		return __uint2float_rn(next_u32()) * 0x1p-32f;
+#else
+		return static_cast<float>(next_u32()) * 0x1p-32f;
+#endif
+	}
+	B2R_HD uint32_t next_below(uint32_t range) {  // Random.hpp:31-34
+		uint32_t v = static_cast<uint32_t>(next_unit() * static_cast<float>(range));
+		return v < range - 1u ? v : range - 1u;
+	}
+};
+// pixel seed (Renderer.hpp:106-108, Q2): t = tile*256 + ID is the pixel's tile-order index
+B2R_HD uint32_t pixel_seed(uint32_t t, uint32_t max_bounces) { return t * (max_bounces * 2u + 1u); }
+
+// ------------------------------------------------------------------ small vector helpers (glm scalar semantics)
+B2R_HD float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+B2R_HD f3 cross3(f3 a, f3 b) { return {a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
+B2R_HD f3 scale3(f3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+B2R_HD f3 unit3(f3 v) { return scale3(v, 1.0f / sqrtf(dot3(v, v))); }  // glm::normalize = v * inversesqrt(dot)
+
+// ------------------------------------------------------------------ camera (Camera.hpp)
+struct CameraParams {  // View + Projection as generate_ray reads them (Camera.hpp:80-88)
+	float px, py, pz;         // view.pos
+	float qw, qx, qy, qz;     // view.orient
+	float half_width, half_height, z, exposure;
+};
+// glm quat * vec3:  v + ((q.xyz × v) * w + q.xyz × (q.xyz × v)) * 2
+B2R_HD f3 quat_rotate(float qw, float qx, float qy, float qz, f3 v) {
+	f3 q{qx, qy, qz};
+	f3 uv = cross3(q, v), uuv = cross3(q, uv);
+	return {v.x + (uv.x * qw + uuv.x) * 2.0f, v.y + (uv.y * qw + uuv.y) * 2.0f, v.z + (uv.z * qw + uuv.z) * 2.0f};
+}
+B2R_HD f3 camera_dir(const CameraParams& c, int32_t x, int32_t y, float s0, float s1) {  // Camera.hpp:80-88 (pinhole, Q22)
+	f3 v{static_cast<float>(x) + s0 - c.half_width, static_cast<float>(y) + s1 - c.half_height, c.z};
+	return unit3(quat_rotate(c.qw, c.qx, c.qy, c.qz, v));
+}
+// glm::quatLookAt(normalize(forward), {0,1,0}) (Camera.hpp:47-50): RH basis {right, up', -dir} -> quat_cast
+B2R_HD void look_at_quat(f3 forward, float out_wxyz[4]) {
+	f3 d = unit3(forward);
+	f3 back{-d.x, -d.y, -d.z};
+	f3 r = cross3(f3{0.0f, 1.0f, 0.0f}, back);
+	f3 right = scale3(r, 1.0f / sqrtf(sel_max(0.00001f, dot3(r, r))));
+	f3 up = cross3(back, right);
+	// trace-based branch selection of glm::quat_cast on the column-major 3x3 {right, up, back}
+	float tw = right.x + up.y + back.z, tx = right.x - up.y - back.z, ty = up.y - right.x - back.z, tz = back.z - right.x - up.y;
+	int sel = 0; float big = tw;
+	if (tx > big) { big = tx; sel = 1; }
+	if (ty > big) { big = ty; sel = 2; }
+	if (tz > big) { big = tz; sel = 3; }
+	float v = sqrtf(big + 1.0f) * 0.5f, m = 0.25f / v;
+	float a = (up.z - back.y) * m, b = (back.x - right.z) * m, c = (right.y - up.x) * m;     // antisymmetric parts
+	float sxy = (right.y + up.x) * m, sxz = (back.x + right.z) * m, syz = (up.z + back.y) * m; // symmetric parts
+	if (sel == 0) { out_wxyz[0] = v; out_wxyz[1] = a; out_wxyz[2] = b; out_wxyz[3] = c; }
+	else if (sel == 1) { out_wxyz[0] = a; out_wxyz[1] = v; out_wxyz[2] = sxy; out_wxyz[3] = sxz; }
+	else if (sel == 2) { out_wxyz[0] = b; out_wxyz[1] = sxy; out_wxyz[2] = v; out_wxyz[3] = syz; }
+	else { out_wxyz[0] = c; out_wxyz[1] = sxz; out_wxyz[2] = syz; out_wxyz[3] = v; }
+}
+
+// ------------------------------------------------------------------ trig approximations (VectorMath.hpp:625-662)
+#define B2R_PI 3.14159265358979323846264338327950288f
+#define B2R_TWO_PI 6.28318530717958647692528676655900576f
+#define B2R_HALF_PI 1.57079632679489661923132169163975144f
+#define B2R_INV_PI 0.318309886183790671537767526745028724f
+#define B2R_INV_TWO_PI 0.159154943091895335768883763372514362f
+
+B2R_HD void sincos_poly(float x, float* s_out, float* c_out) {  // fast_sincos, VectorMath.hpp:644-662
+	const float q = round_even(x * B2R_INV_PI);
+	const uint32_t flip = static_cast<uint32_t>(static_cast<int32_t>(q)) << 31;  // odd multiple of pi -> negate
+	x += q * (-0.78515625f * 4.0f);                       // 4-step Cody-Waite reduction of x - q*pi
+	x += q * (-0.00024187564849853515625f * 4.0f);
+	x += q * (-3.7747668102383613586e-08f * 4.0f);
+	x += q * (-1.2816720341285448015e-12f * 4.0f);
+	x = B2R_HALF_PI - (B2R_HALF_PI - x);
+	const float x2 = x * x;
+	x = from_bits(bits(x) ^ flip);
+	float s = 2.6083159809786593541503e-06f, c = -2.71811842367242206819355e-07f;
+	s = s * x2 - 0.0001981069071916863322258f;  c = c * x2 + 2.47990446951007470488548e-05f;
+	s = s * x2 + 0.00833307858556509017944336f; c = c * x2 - 0.00138888787478208541870117f;
+	s = s * x2 - 0.166666597127914428710938f;   c = c * x2 + 0.0416666641831398010253906f;
+	s = x2 * (s * x) + x;                       c = c * x2 - 0.5f; c = c * x2 + 1.0f;
+	c = from_bits(bits(c) ^ flip);
+	if (from_bits(bits(s) & 0x7fffffffu) > 1.0f) s = 0.0f;
+	if (from_bits(bits(c) & 0x7fffffffu) > 1.0f) c = 0.0f;
+	*s_out = s; *c_out = c;
+}
+B2R_HD float asin_poly(float x) {  // fast_asin, VectorMath.hpp:625-630
+	float f = from_bits(bits(x) & 0x7fffffffu);
+	f = (f < 1.0f) ? 1.0f - (1.0f - f) : 1.0f;
+	f = B2R_HALF_PI - sqrtf(1.0f - f) * (1.5707963267f + f * (-0.213300989f + f * (0.077980478f + f * -0.02164095f)));
+	return from_bits((bits(f) & 0x7fffffffu) | (bits(x) & 0x80000000u));
+}
+B2R_HD float atan2_poly(float y, float x) {  // fast_atan2, VectorMath.hpp:632-642
+	const float a = from_bits(bits(x) & 0x7fffffffu), b = from_bits(bits(y) & 0x7fffffffu);
+	const float lo = sel_min(a, b), hi = sel_max(a, b);
+	float k = hi == 0.0f ? 0.0f : lo / hi;
+	k = 1.0f - (1.0f - k);
+	const float k2 = k * k;
+	float r = k * (0.43157974f * k2 + 1.0f) / ((0.05831938f * k2 + 0.76443945f) * k2 + 1.0f);
+	if (b > a) r = B2R_HALF_PI - r;
+	if (x < 0.0f) r = B2R_PI - r;
+	return from_bits((bits(r) & 0x7fffffffu) | (bits(y) & 0x80000000u));
+}
+
+// ------------------------------------------------------------------ tangent frames and sampling (Sampling.hpp)
+B2R_HD f3 sphere_coords(float phi_turns, float sin_t, float cos_t) {  // spherical_to_cartesian, Sampling.hpp:77-84
+	float sp, cp; sincos_poly(phi_turns * B2R_TWO_PI, &sp, &cp);
+	return {sin_t * cp, sin_t * sp, cos_t};
+}
+B2R_HD f3 cosine_hemisphere(float u0, float u1) {  // hemisphere, Sampling.hpp:92-94
+	return sphere_coords(u1, sqrtf(u0), sqrtf(sel_max(0.0f, 1.0f - u0)));
+}
+B2R_HD TangentQuat tangent_frame(f3 n) {  // tangent_space, Sampling.hpp:150-159 (Frisvad quaternion; z == 0)
+	if (n.z < -1.0f + FLT_EPSILON) return {0.0f, 0.0f, 1.0f};
+	float s = sqrtf(2.0f * (n.z + 1.0f)), inv = 1.0f / s;
+	return {s * 0.5f, -n.y * inv, n.x * inv};
+}
+B2R_HD f3 frame_to_local(TangentQuat t, f3 v) {  // to_local, Sampling.hpp:161-169
+	float k = 2.0f * (v.z * t.w + v.x * t.y - t.x * v.y);
+	return {v.x - t.y * k, v.y + t.x * k, k * t.w - v.z};
+}
+B2R_HD f3 frame_to_world(TangentQuat t, f3 v) {  // to_world, Sampling.hpp:171-179
+	float k = 2.0f * (v.z * t.w - v.x * t.y + t.x * v.y);
+	return {v.x + t.y * k, v.y - t.x * k, k * t.w - v.z};
+}
+B2R_HD void branchless_onb(f3 n, f3* u, f3* v) {  // orthonormal_basis, Sampling.hpp:116-131 (sign-bit variant)
+	const uint32_t sg = bits(n.z) & 0x80000000u;
+	const float s = from_bits(0x3f800000u ^ sg);
+	const float z = -1.0f / (s + n.z);
+	const float snx = from_bits(sg ^ bits(n.x));
+	const float nyz = n.y * z;
+	const float t = n.x * nyz;
+	*u = f3{1.0f + (snx * n.x) * z, from_bits(sg ^ bits(t)), -snx};
+	*v = f3{t, s + nyz * n.y, -n.y};
+}
+B2R_HD float cone_pdf(float cos_max) { return B2R_INV_TWO_PI / sel_max(1e-6f, 1.0f - cos_max); }  // Sampling.hpp:192-194
+B2R_HD float sphere_light_pdf(float r2, float d2) {  // spherePdf, Sampling.hpp:196-200
+	float s2 = r2 / d2;
+	return cone_pdf(sqrtf(sel_max(0.0f, 1.0f - s2)));
+}
+// sample_direction_to_sphere, Sampling.hpp:220-239. wc: unit vector to the light centre.
+B2R_HD f3 sample_sphere_cone(f3 wc, float sin2_max, float center_dist, float r2, float u0, float u1, float* dist_out, float* pdf_out) {
+	const float cos_max = sqrtf(sel_max(0.0f, 1.0f - sin2_max));
+	*pdf_out = cone_pdf(cos_max);
+	const bool small_angle = sin2_max < 0.00068523f;  // Taylor branch below ~1.5 degrees
+	float cos_t = 1.0f - u0 * (1.0f - cos_max);
+	float sin_t = sqrtf(sin2_max * u0);
+	const float src = small_angle ? sin_t : cos_t;
+	const float other = sqrtf(sel_max(0.0f, 1.0f - src * src));
+	cos_t = small_angle ? other : cos_t;
+	sin_t = small_angle ? sin_t : other;
+	const float h = center_dist * sin_t;
+	*dist_out = center_dist * cos_t - sqrtf(sel_max(0.0f, r2 - h * h)) - 1e-5f;
+	const f3 l = sphere_coords(u1, sin_t, cos_t);
+	f3 bx, by; branchless_onb(wc, &bx, &by);
+	return {bx.x * l.x + by.x * l.y + wc.x * l.z, bx.y * l.x + by.y * l.y + wc.y * l.z, bx.z * l.x + by.z * l.y + wc.z * l.z};
+}
+B2R_HD float power_heuristic(float f, float g) { float f2 = f * f; return f2 / sel_max(1e-6f, f2 + g * g); }  // Sampling.hpp:241-244
+B2R_HD float power_heuristic_over_f(float f, float g) { return f / sel_max(1e-6f, f * f + g * g); }         // Sampling.hpp:245-247
+
+// ------------------------------------------------------------------ sphere tests (BVH.hpp:236-305)
+// Closest hit, one lane of the SIMD block BVH.hpp:251-267: returns the candidate distance, or a negative number /
+// NaN-free sentinel when the lane's store mask is clear. sphere = {cx, cy, cz, r^2}.
+B2R_HD bool sphere_hit_closest(float cx, float cy, float cz, float r2, float ox, float oy, float oz, float dx, float dy, float dz, float* dist_out) {
+	float tx = cx - ox;
+	float b = dx * tx;
+	float disc = fma_rn(-tx, tx, r2);
+	float ty = cy - oy;
+	b = fma_rn(dy, ty, b);
+	disc = fma_rn(-ty, ty, disc);
+	float tz = cz - oz;
+	b = fma_rn(dz, tz, b);
+	disc = fma_rn(-tz, tz, disc);
+	disc = fma_rn(b, b, disc);
+	// The reference takes the square root unconditionally and masks afterwards (:262-265): a negative discriminant gives
+	// NaN (fails the ordered compare) and -0 keeps its sign bit (masked out). Both are exactly "bit pattern above +inf",
+	// so the root is only evaluated for discriminants in [+0, +inf].
+	if (bits(disc) > 0x7f800000u) return false;
+	const float root = sqrtf(disc);
+	float d = b - root;
+	if (sign_set(d)) d = b + root;  // blendv on the sign bit (:264)
+	*dist_out = d;
+	return !sign_set(d);            // NaN/inf distances fail the caller's `d < tfar`
+}
+// Any hit along [0, tfar): BVH.hpp:294-300 (glm dot products, no FMA)
+B2R_HD bool sphere_hit_any(float cx, float cy, float cz, float r2, float ox, float oy, float oz, float dx, float dy, float dz, float tfar) {
+	f3 p{cx - ox, cy - oy, cz - oz};
+	float b = dot3(f3{dx, dy, dz}, p);
+	float disc = b * b - dot3(p, p) + r2;
+	if (disc < 0.0f) return false;
+	disc = sqrtf(disc);
+	float d = (b >= disc) ? b - disc : b + disc;
+	return !(d < 0.0f || d >= tfar);
+}
+
+// ------------------------------------------------------------------ resolve (Renderer.hpp:436-478, Color.hpp:47-73)
+B2R_HD float lane_min(float a, float b) { return (a < b) ? a : b; }  // _mm256_min_ps / _mm256_max_ps operand semantics
+B2R_HD float lane_max(float a, float b) { return (a > b) ? a : b; }
+B2R_HD float median_of_3(float a, float b, float c) { return lane_max(lane_min(a, b), lane_min(lane_max(a, b), c)); }  // Sampling.hpp:8-12
+B2R_HD float median_of_5(float a, float b, float c, float d, float e) {  // Sampling.hpp:13-21
+	return median_of_3(lane_max(lane_min(a, b), lane_min(c, d)), lane_min(lane_max(a, b), lane_max(c, d)), e);
+}
+B2R_HD float aces_curve(float x) { return (x * (x + 0.0245786f) - 0.000090537f) / (x * (0.983729f * x + 0.4329510f) + 0.238081f); }  // Color.hpp:47-49
+B2R_HD void aces_tonemap(float* r, float* g, float* b) {  // tonemapping(Vec8f&...), Color.hpp:66-73
+	float x = aces_curve(*r * 0.59719f + *g * 0.35458f + *b * 0.04823f);
+	float y = aces_curve(*r * 0.07600f + *g * 0.90834f + *b * 0.01566f);
+	float z = aces_curve(*r * 0.02840f + *g * 0.13383f + *b * 0.83777f);
+	*r = lane_min(1.0f, lane_max(0.0f, x * 1.604750f + y * -0.53108f + z * -0.07367f));
+	*g = lane_min(1.0f, lane_max(0.0f, x * -0.10208f + y * 1.10813f + z * -0.00605f));
+	*b = lane_min(1.0f, lane_max(0.0f, x * -0.00327f + y * -0.07276f + z * 1.07602f));
+}
+
+}  // namespace b2r

@@ -1,0 +1,292 @@
+// b2r_shade.h — per-path shading and BVH traversal routines of the wavefront path tracer, host+device.
+//
+// The sm_100a kernels (b2r_device.cuh) call these from their persistent loops. They are also plain C++ so that
+// tests/hostcheck can run the very same routines on the build box (which has no GPU) and compare them bit-for-bit
+// with the oracle; nothing in libb2r.so executes them on the CPU.
+#pragma once
+#include <vector_types.h>
+#include <vector_functions.h>
+#include "b2r_math.h"
+#include "b2r_host.h"
+
+namespace b2r {
+
+constexpr int kMaxSlots = 64;          // samples in flight per batch (pid keeps 6 slot bits)
+constexpr uint32_t kPixMask = (1u << 26) - 1u;
+
+B2R_HD int32_t as_int(float f) { return static_cast<int32_t>(bits(f)); }
+B2R_HD float from_int(int32_t v) { return from_bits(static_cast<uint32_t>(v)); }
+B2R_HD float4 ldg4(const float4* p) {
+#if defined(__CUDA_ARCH__)
+	return __ldg(p);
+#else
+	return *p;
+#endif
+}
+B2R_HD int32_t ldg_i32(const int32_t* p) {
+#if defined(__CUDA_ARCH__)
+	return __ldg(p);
+#else
+	return *p;
+#endif
+}
+
+enum Stat { ST_EXT = 0, ST_SHADOW, ST_HITS, ST_TERM, ST_DROPPED, ST_SPHERE, ST_BOX, ST_EVENTS, ST_COUNT };
+
+struct SceneDev {
+	const float4* prims;        // [n_prims] {c.xyz, r^2}, BVH leaf order (acceleration_structure.prims)
+	const int32_t* prim_mat;    // [n_prims] material_ID
+	const float4* mat_albedo;   // [n_mat] {albedo.rgb, emissive ? 1 : 0}  (max(emission) > FLT_EPSILON, Renderer.hpp:201)
+	const float4* mat_emission; // [n_mat] {emission.rgb, 0}
+	const float4* light_sphere; // [n_lights] scene.geometry[light] {c.xyz, r^2}   (Renderer.hpp:261-262)
+	const float4* light_emit;   // [n_lights] {emission.rgb of its material, as_float(light_primID)}
+	const WideNode* wide;       // flattened BVH
+	const float4* hdri;         // equirect RGBA32F or null
+	uint32_t n_prims, n_mat, n_lights;
+	float light_sel_pdf;        // 1 / n_lights (Renderer.hpp:78)
+	float ambient[3]; int32_t has_ambient;  // Renderer.hpp:79
+	int32_t hdri_w, hdri_h; float hdri_fw, hdri_fh;
+};
+struct FrameDev {
+	CameraParams cam;
+	uint32_t width, height, h_tiles, npix;
+	uint32_t max_bounces, buckets, flags;
+};
+struct BatchDev {  // one wavefront batch: n_slots samples traced together
+	uint32_t n_slots;
+	uint32_t acc[kMaxSlots];  // sample index (the reference's `accumulations` value, Q1) of each slot
+};
+struct QueueDev {
+	float4* A[2]; float4* B[2]; float* T[2];
+	float2* H;
+	float4* SA; float4* SB; float* SL;
+	uint32_t cap;
+};
+struct CountDev {            // zeroed at the start of every batch; index = bounce
+	uint32_t* paths;         // [mb+1] paths entering bounce b
+	uint32_t* shadow;        // [mb]   shadow rays queued at bounce b
+	uint32_t* work_a;        // [mb]   work-fetch cursors of the traversal kernels
+	uint32_t* work_b;        // [mb]
+	unsigned long long* stats;  // [ST_COUNT] cumulative since reset_counters
+};
+struct Params {
+	SceneDev scene; FrameDev frame; QueueDev q; CountDev cnt;
+	const BatchDev* batch;
+	float* rad;   // RAD
+	float* acc;   // ACC
+};
+
+// ---------------------------------------------------------------------------------------------- small helpers
+// tile-order pixel index -> pixel coordinates (Renderer.hpp:85-88,114-115)
+B2R_HD void pixel_xy(uint32_t t, uint32_t h_tiles, int32_t* x, int32_t* y) {
+	const uint32_t tile = t >> 8, id = t & 255u;
+	*x = static_cast<int32_t>((tile % h_tiles) * 16u + (id & 15u));
+	*y = static_cast<int32_t>((tile / h_tiles) * 16u + (id >> 4));
+}
+
+struct PathState { float ox, oy, oz, dx, dy, dz, tr, tg, tb, pdf; uint32_t pid; };
+
+// primary ray of (slot, pixel t): Renderer.hpp:97-127
+B2R_HD PathState primary_path(const FrameDev& fr, uint32_t acc, uint32_t slot, uint32_t t) {
+	Pcg rng{hash_2d(acc, pixel_seed(t, fr.max_bounces))};
+	const float s0 = rng.next_unit(), s1 = rng.next_unit();
+	int32_t x, y; pixel_xy(t, fr.h_tiles, &x, &y);
+	const f3 d = camera_dir(fr.cam, x, y, s0, s1);
+	PathState s;
+	s.ox = fr.cam.px; s.oy = fr.cam.py; s.oz = fr.cam.pz; s.dx = d.x; s.dy = d.y; s.dz = d.z;
+	s.tr = s.tg = s.tb = 1.0f; s.pdf = 0.0f; s.pid = (slot << 26) | t;
+	return s;
+}
+
+
+// ---------------------------------------------------------------------------------------------- shading
+struct Surface { f3 P; TangentQuat T; float n_dot_v; f3 albedo; bool emissive; int32_t mat; float r2; };
+struct ShadowRay { f3 o, d; float tfar; f3 L; };
+
+// closest-hit shader, Renderer.hpp:169-214
+B2R_HD Surface shade_surface(const SceneDev& sc, const PathState& s, float depth, int32_t prim) {
+	const float4 sp = ldg4(sc.prims + prim);
+	const f3 D{s.dx, s.dy, s.dz};
+	const f3 hp{s.ox + D.x * depth, s.oy + D.y * depth, s.oz + D.z * depth};
+	f3 N = unit3(f3{hp.x - sp.x, hp.y - sp.y, hp.z - sp.z});
+	if (dot3(N, D) >= 0.0f) N = f3{-N.x, -N.y, -N.z};  // backface
+	Surface sf;
+	sf.T = tangent_frame(N);
+	sf.n_dot_v = frame_to_local(sf.T, f3{-D.x, -D.y, -D.z}).z;
+	sf.P = f3{hp.x + N.x * 1e-4f, hp.y + N.y * 1e-4f, hp.z + N.z * 1e-4f};
+	sf.mat = ldg_i32(sc.prim_mat + prim);
+	const float4 al = ldg4(sc.mat_albedo + sf.mat);
+	sf.albedo = f3{al.x, al.y, al.z}; sf.emissive = al.w != 0.0f; sf.r2 = sp.w;
+	return sf;
+}
+// next-event estimation, Renderer.hpp:249-298. Returns false when no shadow ray is produced.
+B2R_HD bool shade_light_sample(const SceneDev& sc, const Surface& sf, const PathState& s, int32_t hit_prim,
+                                                   uint32_t acc, uint32_t seed, uint32_t bounce, ShadowRay* out) {
+	if (sc.n_lights == 0u) return false;  // undefined in the reference (Q15); defined here as "no light sampling"
+	Pcg rng{hash_2d(acc, seed + bounce * 2u)};  // Q3
+	const float u0 = rng.next_unit(), u1 = rng.next_unit();
+	const uint32_t pick = rng.next_below(sc.n_lights);
+	const float4 ls = ldg4(sc.light_sphere + pick), le = ldg4(sc.light_emit + pick);
+	if (as_int(le.w) == hit_prim) return false;  // Q9: geometry index vs BVH-order index, as in the reference
+	f3 wc{ls.x - sf.P.x, ls.y - sf.P.y, ls.z - sf.P.z};
+	const float d2 = dot3(wc, wc);
+	if (d2 <= ls.w) return false;
+	const float dist = sqrtf(d2);
+	wc = scale3(wc, 1.0f / dist);
+	const float sin2 = ls.w / d2;
+	const float n_dot_w = (2.0f * sf.T.w) * (wc.z * sf.T.w + wc.x * sf.T.y - sf.T.x * wc.y) - wc.z;  // Renderer.hpp:271
+	if (n_dot_w < 0.0f && sin2 < n_dot_w * n_dot_w) return false;
+	float ldist, lpdf;
+	const f3 L = sample_sphere_cone(wc, sin2, dist, ls.w, u0, u1, &ldist, &lpdf);
+	const f3 ll = frame_to_local(sf.T, L);
+	if (ll.z < 0.0f) return false;
+	f3 rad{le.x * s.tr, le.y * s.tg, le.z * s.tb};
+	const float f = B2R_INV_PI * sel_max(0.0f, ll.z);  // Closure<Lambertian>::eval, DataStreams.hpp:169-172
+	rad = f3{rad.x * (sf.albedo.x * f), rad.y * (sf.albedo.y * f), rad.z * (sf.albedo.z * f)};
+	lpdf *= sc.light_sel_pdf;
+	const float bpdf = B2R_INV_PI * sel_max(0.0f, ll.z);
+	const float w = power_heuristic_over_f(lpdf, bpdf);
+	rad = scale3(rad, w);
+	if (sel_max(sel_max(rad.x, rad.y), rad.z) <= 0.0f) return false;
+	out->o = sf.P; out->d = L; out->tfar = ldist; out->L = rad;
+	return true;
+}
+// emissive-hit contribution, Renderer.hpp:319-353
+B2R_HD f3 shade_emission(const SceneDev& sc, const Surface& sf, const PathState& s, float depth, uint32_t bounce, bool mis) {
+	const float4 em = ldg4(sc.mat_emission + sf.mat);
+	if (!mis) return f3{s.tr * em.x, s.tg * em.y, s.tb * em.z};  // this repo's MIS-off (Q23)
+	if (bounce == 0) return f3{em.x, em.y, em.z};
+	const float d2 = depth * (depth + sf.n_dot_v * (2.0f * sqrtf(sf.r2))) + sf.r2;  // law of cosines, Renderer.hpp:331
+	const float w = power_heuristic(s.pdf, sc.light_sel_pdf * sphere_light_pdf(sf.r2, d2));
+	return f3{(s.tr * w) * em.x, (s.tg * w) * em.y, (s.tb * w) * em.z};
+}
+// BRDF sampling + Russian roulette, Renderer.hpp:359-403. Returns false when the path is terminated by roulette.
+B2R_HD bool shade_continue(const Surface& sf, PathState* s, uint32_t acc, uint32_t seed, uint32_t bounce) {
+	Pcg rng{hash_2d(acc, seed + bounce * 2u + 1u)};
+	const float u0 = rng.next_unit(), u1 = rng.next_unit();
+	const f3 dl = cosine_hemisphere(u0, u1);
+	f3 thr{s->tr * sf.albedo.x, s->tg * sf.albedo.y, s->tb * sf.albedo.z};
+	const float q = 1.0f - sel_max(thr.x, sel_max(thr.y, thr.z));
+	if (rng.next_unit() < q) return false;
+	thr = scale3(thr, 1.0f / sel_max(FLT_EPSILON, 1.0f - q));
+	const f3 dw = frame_to_world(sf.T, dl);
+	s->ox = sf.P.x; s->oy = sf.P.y; s->oz = sf.P.z; s->dx = dw.x; s->dy = dw.y; s->dz = dw.z;
+	s->tr = thr.x; s->tg = thr.y; s->tb = thr.z;
+	s->pdf = B2R_INV_PI * sel_max(0.0f, dw.z);  // pdf of the world-space direction (Q10)
+	return true;
+}
+// miss shader with ambient sky, Renderer.hpp:411-420 + Sky::operator(), Primitives.hpp:35-46
+B2R_HD f3 shade_sky(const SceneDev& sc, const PathState& s) {
+	const float u = sc.hdri_fw * (0.5f + B2R_INV_TWO_PI * atan2_poly(s.dz, s.dx));
+	const float v = sc.hdri_fh * (0.5f - B2R_INV_PI * asin_poly(s.dy));
+	const float4 tx = ldg4(sc.hdri + (static_cast<int32_t>(v) * sc.hdri_w + static_cast<int32_t>(u)));
+	// Q14: all three channels are scaled by throughput.r
+	return f3{s.tr * (tx.x * sc.ambient[0]), s.tr * (tx.y * sc.ambient[1]), s.tr * (tx.z * sc.ambient[2])};
+}
+B2R_HD void rad_add(float* rad, uint32_t npix, uint32_t pid, f3 a, f3 b) {
+	const uint32_t slot = pid >> 26, t = pid & kPixMask;
+	float* r = rad + static_cast<size_t>(slot) * 3u * npix + t;
+	r[0] = (r[0] + a.x) + b.x; r[npix] = (r[npix] + a.y) + b.y; r[2u * npix] = (r[2u * npix] + a.z) + b.z;
+}
+B2R_HD void rad_zero(float* rad, uint32_t npix, uint32_t pid) {
+	const uint32_t slot = pid >> 26, t = pid & kPixMask;
+	float* r = rad + static_cast<size_t>(slot) * 3u * npix + t;
+	r[0] = 0.0f; r[npix] = 0.0f; r[2u * npix] = 0.0f;
+}
+
+// ---------------------------------------------------------------------------------------------- BVH traversal
+// Per-thread traversal of the 4-wide tree with a short stack in local memory. Inner slots: slab test clipped to
+// [0, limit]; leaf slots hold the sphere itself, so a leaf costs no extra fetch. Children are visited nearest first.
+struct Ray { float ox, oy, oz, dx, dy, dz; };
+
+B2R_HD void slab(const float4 a, const float4 b, float ix, float iy, float iz, float nx, float ny, float nz,
+                                     float limit, float* tnear, bool* hit) {
+	// box = {a.x,a.y,a.z | a.w,b.x,b.y}; t = plane*inv - origin*inv as one FMA (box tests never decide a result)
+	const float x0 = fma_rn(a.x, ix, nx), x1 = fma_rn(a.w, ix, nx);
+	const float y0 = fma_rn(a.y, iy, ny), y1 = fma_rn(b.x, iy, ny);
+	const float z0 = fma_rn(a.z, iz, nz), z1 = fma_rn(b.y, iz, nz);
+	const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+	const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), limit));
+	*tnear = t0; *hit = t0 <= t1 * 1.0000004f;
+}
+#define B2R_CSWAP(ka, la, kb, lb) { const bool sw = kb < ka; const uint32_t tk = sw ? kb : ka, tl = sw ? lb : la; kb = sw ? ka : kb; lb = sw ? la : lb; ka = tk; la = tl; }
+
+// Closest hit == brute force over all spheres: a candidate replaces the best when d < best, or d == best with a lower
+// sphere index (the brute-force loop keeps the first of equal distances, BVH.hpp:265); nodes are culled only when
+// their entry distance is beyond the best.
+template <bool COUNT>
+B2R_HD void traverse_closest(const WideNode* __restrict__ wide, const Ray& r, float* best_out, int32_t* prim_out,
+                                                 uint32_t* c_sphere, uint32_t* c_box) {
+	const float ix = 1.0f / r.dx, iy = 1.0f / r.dy, iz = 1.0f / r.dz;
+	const float nx = -(r.ox * ix), ny = -(r.oy * iy), nz = -(r.oz * iz);
+	float best = FLT_MAX; int32_t prim = -1;
+	uint2 stack[kTraversalStack]; int sp = 0;
+	uint32_t node = 0;
+	for (;;) {
+		const float4* n = reinterpret_cast<const float4*>(wide + node);
+		uint32_t key[4]; uint32_t link[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const float4 a = ldg4(n + 2 * k), b = ldg4(n + 2 * k + 1);
+			const int32_t l = as_int(b.z);
+			key[k] = 0xffffffffu; link[k] = 0u;
+			if (l >= 0) {
+				float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, best, &tn, &h);
+				if (COUNT) (*c_box)++;
+				if (h) { key[k] = bits(tn); link[k] = static_cast<uint32_t>(l); }
+			} else if (l != kEmptyLink) {
+				float d; if (COUNT) (*c_sphere)++;
+				if (sphere_hit_closest(a.x, a.y, a.z, a.w, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, &d)) {
+					const int32_t id = ~l;
+					if (d < best || (d == best && id < prim)) { best = d; prim = id; }
+				}
+			}
+		}
+		// sort the (entry distance, link) pairs; non-negative floats order like their bit patterns, misses (0xffffffff) last
+		B2R_CSWAP(key[0], link[0], key[1], link[1]); B2R_CSWAP(key[2], link[2], key[3], link[3]);
+		B2R_CSWAP(key[0], link[0], key[2], link[2]); B2R_CSWAP(key[1], link[1], key[3], link[3]);
+		B2R_CSWAP(key[1], link[1], key[2], link[2]);
+		if (key[3] != 0xffffffffu) stack[sp++] = make_uint2(link[3], key[3]);
+		if (key[2] != 0xffffffffu) stack[sp++] = make_uint2(link[2], key[2]);
+		if (key[1] != 0xffffffffu) stack[sp++] = make_uint2(link[1], key[1]);
+		if (key[0] != 0xffffffffu && from_bits(key[0]) <= best) { node = link[0]; continue; }
+		bool found = false;
+		while (sp > 0) {
+			const uint2 e = stack[--sp];
+			if (from_bits(e.y) <= best) { node = e.x; found = true; break; }
+		}
+		if (!found) break;
+	}
+	*best_out = best; *prim_out = prim;
+}
+// Any hit along [0, tfar) — Traverse_shadow semantics (BVH.hpp:290-305): order-independent boolean.
+template <bool COUNT>
+B2R_HD bool traverse_any(const WideNode* __restrict__ wide, const Ray& r, float tfar, uint32_t* c_sphere, uint32_t* c_box) {
+	const float ix = 1.0f / r.dx, iy = 1.0f / r.dy, iz = 1.0f / r.dz;
+	const float nx = -(r.ox * ix), ny = -(r.oy * iy), nz = -(r.oz * iz);
+	uint32_t stack[kTraversalStack]; int sp = 0;
+	uint32_t node = 0;
+	for (;;) {
+		const float4* n = reinterpret_cast<const float4*>(wide + node);
+		uint32_t next = 0xffffffffu;
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const float4 a = ldg4(n + 2 * k), b = ldg4(n + 2 * k + 1);
+			const int32_t l = as_int(b.z);
+			if (l >= 0) {
+				float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, tfar, &tn, &h);
+				if (COUNT) (*c_box)++;
+				if (h) { if (next != 0xffffffffu) stack[sp++] = next; next = static_cast<uint32_t>(l); }
+			} else if (l != kEmptyLink) {
+				if (COUNT) (*c_sphere)++;
+				if (sphere_hit_any(a.x, a.y, a.z, a.w, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, tfar)) return true;
+			}
+		}
+		if (next != 0xffffffffu) { node = next; continue; }
+		if (sp == 0) return false;
+		node = stack[--sp];
+	}
+}
+
+
+}  // namespace b2r

@@ -1,0 +1,158 @@
+/* b2r.h — C ABI of the B200-native wavefront path tracer (libb2r.so).
+ *
+ * Drop-in boundary for ONE hot path of Borx25/CPU-Raytracing-experiments: Renderer::Accumulate
+ * (Renderer.hpp:73-434), Renderer::Render (Renderer.hpp:436-478) and the ray-stream / BVH machinery under
+ * them. The reference has no FFI of its own (one header-only C++ class template used directly by the app,
+ * Application.cpp:373-382); these entry points are what a binding for that class would need, and the C++
+ * mirror in cpu-raytracing-experiments_b200/host/ (Renderer.hpp, Scene.hpp, Camera.hpp, BVH.hpp) forwards
+ * the reference's own member functions to them. INTEGRATION.md shows the reference-side change.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns B2R_OK (0) or a
+ * negative B2R_ERR_* code and never throws; input arrays are caller-owned and copied during the call;
+ * one host thread per context (the reference is single-threaded at this boundary, Application.cpp:361-382);
+ * all device work of a context runs on one CUDA stream (b2r_set_stream). There is NO CPU fallback: without a
+ * CUDA device every call that needs one fails with B2R_ERR_CUDA.
+ */
+#ifndef B2R_H_
+#define B2R_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2R_ABI_VERSION 1
+
+/* ---- PODs, layout-identical to the reference so its vectors can be passed as-is ---------------------- */
+typedef struct b2r_sphere {      /* Sphere, Primitives.hpp:7-17 (alignas(16) => 32 B) */
+	float position[3];
+	float radius_sq;
+	int32_t material_ID;
+	int32_t _pad[3];
+} b2r_sphere;
+
+typedef struct b2r_material {    /* Material, Primitives.hpp:18-27 (alignas(32) => 96 B); hot path reads albedo + emission */
+	float albedo[3], F0[3], F80[3], emission[3], transmission[3];
+	float roughness, IOR_minus_one;
+	float _pad[7];
+} b2r_material;
+
+typedef struct b2r_bvh_node {    /* BoundingVolumeHierarchy<Sphere>::Node, BVH.hpp:18-27 (32 B) */
+	float min_bound[3];
+	uint32_t first_id;           /* inner: index of the adjacent child pair; leaf: first primitive */
+	float max_bound[3];
+	uint32_t prim_count;         /* 0 = inner node, 1 = leaf (leaf size is always 1, BVH.hpp:133) */
+} b2r_bvh_node;
+
+/* ---- configuration (RendererPolicy NTTP + compile-time #defines of the reference, made run-time) ---- */
+enum {
+	B2R_FLAG_FORCE_BRUTE = 1u << 0, /* USEBVH false semantics at any scene size: test every ray against every sphere (BVH.hpp:311-318) */
+	B2R_FLAG_FORCE_BVH   = 1u << 1, /* always use the flattened-BVH traversal kernels (default: brute <= 32 spheres, BVH above) */
+	B2R_FLAG_NO_MIS      = 1u << 2, /* this repo's "MIS off" (SURVEY Q23): no light sampling, radiance += throughput*emission */
+	B2R_FLAG_COUNT_TESTS = 1u << 3, /* also count sphere / box tests (slower; for roofline accounting) */
+	B2R_FLAG_NO_GRAPH    = 1u << 4, /* launch kernels one by one instead of replaying a CUDA graph (profiling) */
+};
+
+typedef struct b2r_config {
+	uint32_t width, height;      /* multiples of 16 (Renderer::RequiredTiling(), Renderer.hpp:36) */
+	uint32_t max_bounces;        /* RendererPolicy::max_bounces, Renderer.hpp:24 (reference: 16) */
+	uint32_t buckets;            /* AccumulationBuckets, Renderer.hpp:41 (reference: 5); 1..64 */
+	uint32_t flags;              /* B2R_FLAG_* */
+	int32_t  device;             /* CUDA ordinal */
+	uint32_t bucket_first;       /* multi-GPU: this context renders the samples whose bucket b = acc % buckets */
+	uint32_t bucket_stride;      /*            satisfies b % bucket_stride == bucket_first (0/1 => all)   */
+	uint32_t samples_in_flight;  /* samples traced together per wavefront batch; 0 = default (8) */
+} b2r_config;
+
+enum {
+	B2R_OK = 0,
+	B2R_ERR_ARG = -1,            /* null pointer, size not a multiple of 16, bad bucket count, ... */
+	B2R_ERR_CUDA = -2,           /* CUDA runtime error or no device (see b2r_last_error) */
+	B2R_ERR_STATE = -3,          /* call order: e.g. accumulate before upload_scene */
+	B2R_ERR_NO_LIGHTS = -4,      /* reserved: a scene without emissive spheres is accepted and simply gets no light sampling */
+	B2R_ERR_BVH = -5,            /* malformed node array or traversal stack bound exceeded */
+	B2R_ERR_NOT_READY = 1,       /* b2r_resolve: accumulations % buckets != 0 — Render() is a no-op then (Renderer.hpp:437) */
+};
+
+typedef struct b2r_ctx b2r_ctx;
+
+/* ---- host-side scene preparation (replaces BVH.hpp:90-206 and Scene.hpp:12-16; runs on the CPU like the reference) */
+
+/* BoundingVolumeHierarchy<Sphere>(span<const Sphere>) — BVH.hpp:90-206. nodes_out holds 2n-1 nodes (1 if n==0),
+ * prims_out the spheres in leaf order (BVH.hpp:201-205), prim_ids_out[i] = geometry index of prims_out[i] (may be NULL). */
+int b2r_bvh_build(const b2r_sphere* geometry, uint32_t n, b2r_bvh_node* nodes_out, b2r_sphere* prims_out,
+                  uint32_t* prim_ids_out, uint32_t* n_nodes_out);
+/* LightingAcceleration(geometry, material) — Scene.hpp:12-16. Returns the count via n_out; out may be NULL to size. */
+int b2r_find_lights(const b2r_sphere* geometry, uint32_t n, const b2r_material* materials, uint32_t n_mat,
+                    int32_t* out, uint32_t* n_out);
+/* View(eye, forward) + Projection::Resize/UpdateLens — Camera.hpp:21-32,47-50. out11 = pos[3], orient wxyz[4],
+ * half_width, half_height, z, exposure: the exact arguments of b2r_set_camera. */
+int b2r_camera_lookat(const float eye[3], const float dir[3], uint32_t width, uint32_t height, float focal_length_mm,
+                      float exposure, float out11[11]);
+
+/* ---- renderer life cycle (Renderer<Policy>, Renderer.hpp:28-68) -------------------------------------- */
+int  b2r_create(b2r_ctx** out, const b2r_config* cfg);             /* Renderer(const Scene&) + Resize, :51-63 */
+void b2r_destroy(b2r_ctx* ctx);
+int  b2r_resize(b2r_ctx* ctx, uint32_t width, uint32_t height);     /* Renderer::Resize, :53-63 (resets the accumulator) */
+int  b2r_reset(b2r_ctx* ctx);                                       /* Renderer::ResetAccumulator, :64-67 */
+int  b2r_set_stream(b2r_ctx* ctx, void* cuda_stream);               /* run on a caller-owned cudaStream_t (NULL = own stream) */
+int  b2r_sync(b2r_ctx* ctx);
+
+/* Scene (Scene.hpp:19-26) as the renderer reads it: spheres in BVH leaf order + nodes (acceleration_structure),
+ * materials, the light list (indices into geometry) and geometry in original order (read by NEE, Renderer.hpp:261-262),
+ * sky (Primitives.hpp:29-47; hdri_rgba may be NULL when ambient is 0). Flattens the nodes to the 128-byte GPU layout. */
+int  b2r_upload_scene(b2r_ctx* ctx, const b2r_sphere* prims_bvh_order, const b2r_bvh_node* nodes, uint32_t n_prims,
+                      uint32_t n_nodes, const b2r_material* materials, uint32_t n_mat, const int32_t* light_geom_idx,
+                      uint32_t n_lights, const b2r_sphere* geometry, uint32_t n_geom, const float ambient[3],
+                      const float* hdri_rgba, int32_t hdri_w, int32_t hdri_h);
+/* Camera (Camera.hpp:61-88): view.pos, view.orient (w,x,y,z), projection.half_width/half_height/z, exp */
+int  b2r_set_camera(b2r_ctx* ctx, const float pos[3], const float orient_wxyz[4], float half_width, float half_height,
+                    float z, float exposure);
+
+/* ---- the hot path ---------------------------------------------------------------------------------- */
+/* Renderer::Accumulate() n_samples times (Renderer.hpp:73-434): accumulations += n_samples; each new sample index
+ * acc lands in bucket acc % buckets (this context renders only the buckets it owns). Asynchronous on the stream. */
+int  b2r_accumulate(b2r_ctx* ctx, uint32_t n_samples);
+/* Renderer::Render() (Renderer.hpp:436-478): median-of-K bucket sums * exposure/(accumulations/K), ACES tonemap
+ * (tonemap=0: linear), RGBA32F, row 0 = y 0. rgba_out_host: width*height*4 floats (NULL: leave it on the device).
+ * Returns B2R_ERR_NOT_READY and writes nothing unless accumulations % buckets == 0. Synchronises. */
+int  b2r_resolve(b2r_ctx* ctx, float* rgba_out_host, int tonemap);
+/* Same, reading the K bucket sums from another device array of the same layout (e.g. the NCCL-combined buckets of a
+ * multi-GPU frame) instead of this context's own accumulator. dev_buckets == NULL means the context's own. */
+int  b2r_resolve_from(b2r_ctx* ctx, const void* dev_buckets, float* rgba_out_host, int tonemap);
+
+/* ---- taps: parity, metrics, resume, multi-GPU plumbing --------------------------------------------- */
+int  b2r_get_accumulations(b2r_ctx* ctx, uint32_t* out);
+int  b2r_set_accumulations(b2r_ctx* ctx, uint32_t acc);            /* resume / jump to a sample index (RNG is stateless, Q2-Q3) */
+int  b2r_read_buckets(b2r_ctx* ctx, float* out_host);               /* [buckets][3][width*height], pixels in tile order t = tile*256+ID */
+int  b2r_write_buckets(b2r_ctx* ctx, const float* in_host);         /* checkpoint restore */
+int  b2r_device_buckets(b2r_ctx* ctx, void** dev_ptr, size_t* bytes); /* device address of the same array (NCCL / P2P combine) */
+int  b2r_device_framebuffer(b2r_ctx* ctx, void** dev_ptr, size_t* bytes);
+/* counters since the last reset: [0] extension rays, [1] shadow rays, [2] shaded hits, [3] terminated paths,
+ * [4] dropped at max_bounces (Q11), [5] sphere tests, [6] box tests (5,6 only with B2R_FLAG_COUNT_TESTS), [7] kernel launches,
+ * [8] radiance contributions written (light samples, emissive hits, sky), [9] reserved */
+int  b2r_read_counters(b2r_ctx* ctx, uint64_t out[10]);
+int  b2r_reset_counters(b2r_ctx* ctx);
+/* per-kernel device time (ms) and launch counts accumulated while B2R_FLAG_NO_GRAPH profiling is on:
+ * index 0 generate, 1 bounce_brute, 2 intersect_closest, 3 shade, 4 intersect_shadow, 5 accumulate, 6 resolve */
+int  b2r_read_kernel_times(b2r_ctx* ctx, double ms_out[8], uint64_t launches_out[8], int reset);
+int  b2r_set_flags(b2r_ctx* ctx, uint32_t flags);
+
+/* Camera::generate_ray for every pixel of sample index acc (Renderer.hpp:113-127): out_host[t*6 + {o.xyz, d.xyz}] */
+int  b2r_generate_rays(b2r_ctx* ctx, uint32_t acc, float* out_host);
+/* BoundingVolumeHierarchy::Traverse / Traverse_shadow on caller rays (public surface, Application.cpp:282-298):
+ * rays_host[n*6] = origin, dir. closest: tfar_out[n] (FLT_MAX on miss), prim_out[n] (BVH-order index or -1). */
+int  b2r_trace_closest(b2r_ctx* ctx, const float* rays_host, uint32_t n, float* tfar_out, int32_t* prim_out);
+int  b2r_trace_shadow(b2r_ctx* ctx, const float* rays_host, const float* tfar_host, uint32_t n, uint8_t* occluded_out);
+/* the flattened 128-byte node array (for the layout round-trip test): out may be NULL to size */
+int  b2r_read_wide_nodes(b2r_ctx* ctx, void* out_host, uint32_t* n_wide_nodes, uint32_t* max_stack);
+
+const char* b2r_last_error(void);   /* text of the last failure on this thread */
+int  b2r_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2R_H_ */

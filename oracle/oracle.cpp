@@ -463,7 +463,7 @@ static void accumulate_tile(Ctx& c, uint32_t LaunchIndex, TileScratch& S) {
 		const size_t hit_count = active_rays - miss_count;  // :243
 		n_shaded += hit_count;
 
-		if (mis) {
+		if (mis && light_count > 0) {  // zero lights is undefined in the reference (1/0, prims[0] of an empty list, Q15): defined here as "no light sampling"
 			size_t shadow_index = 0;
 			for (size_t i = 0; i < hit_count; i++) {  // NEE :249-298
 				const int32_t ID = static_cast<int32_t>(S.RayID[miss_count + i]);

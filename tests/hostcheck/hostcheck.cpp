@@ -1,0 +1,102 @@
+// hostcheck.cpp — TEST HARNESS (built by tests/conftest.py with g++, never part of libb2r.so).
+//
+// Runs the product's own host+device routines (csrc/b2r_math.h, csrc/b2r_shade.h, csrc/b2r_host.cpp) on the CPU so the
+// CPU-only test tier can compare them bit-for-bit with the oracle on the build box, where no GPU exists. The control
+// flow below mirrors one path through k_bounce_brute / k_intersect_closest + k_shade + k_intersect_shadow
+// (csrc/b2r_device.cuh); the GPU tier (-m gpu) then checks the kernels themselves through the C ABI.
+#include "b2r_shade.h"
+#include <cstring>
+#include <vector>
+
+using namespace b2r;
+
+extern "C" {
+
+// One sample (`acc`) for every pixel: rad_out[3][npix] (tile order). counters: ext rays, shadow rays, hits, term, dropped.
+int hc_render_sample(const b2r_sphere* prims, const b2r_bvh_node* nodes, uint32_t n_prims, uint32_t n_nodes,
+                     const b2r_material* materials, uint32_t n_mat, const int32_t* lights, uint32_t n_lights,
+                     const b2r_sphere* geometry, const float cam11[11], uint32_t width, uint32_t height,
+                     uint32_t max_bounces, uint32_t flags, uint32_t acc, int use_bvh, float* rad_out, uint64_t counters[5]) {
+	PackedScene ps; pack_scene(prims, n_prims, materials, n_mat, lights, n_lights, geometry, ps);
+	WideBvh wide; flatten_bvh(nodes, n_nodes, prims, n_prims, wide);
+	if (wide.max_stack > static_cast<uint32_t>(kTraversalStack)) return B2R_ERR_BVH;
+	SceneDev sc{};
+	sc.prims = ps.prims.data(); sc.prim_mat = ps.prim_mat.data(); sc.mat_albedo = ps.mat_albedo.data(); sc.mat_emission = ps.mat_emission.data();
+	sc.light_sphere = ps.light_sphere.data(); sc.light_emit = ps.light_emit.data(); sc.wide = wide.nodes.data(); sc.hdri = nullptr;
+	sc.n_prims = n_prims; sc.n_mat = n_mat; sc.n_lights = n_lights; sc.light_sel_pdf = 1.0f / static_cast<float>(n_lights); sc.has_ambient = 0;
+	FrameDev fr{};
+	fr.cam = CameraParams{cam11[0], cam11[1], cam11[2], cam11[3], cam11[4], cam11[5], cam11[6], cam11[7], cam11[8], cam11[9], cam11[10]};
+	fr.width = width; fr.height = height; fr.h_tiles = width / 16; fr.npix = width * height; fr.max_bounces = max_bounces; fr.buckets = 1; fr.flags = flags;
+	const bool mis = !(flags & B2R_FLAG_NO_MIS);
+	std::memset(rad_out, 0, sizeof(float) * 3 * fr.npix);
+	for (int k = 0; k < 5; k++) counters[k] = 0;
+	uint32_t cs = 0, cb = 0;
+	for (uint32_t t = 0; t < fr.npix; t++) {
+		PathState s = primary_path(fr, acc, 0, t);
+		const uint32_t seed = pixel_seed(t, max_bounces);
+		for (uint32_t bounce = 0; bounce < max_bounces; bounce++) {
+			counters[0]++;
+			const bool last = bounce + 1 >= max_bounces;
+			float best = FLT_MAX; int32_t prim = -1;
+			if (use_bvh) traverse_closest<false>(sc.wide, Ray{s.ox, s.oy, s.oz, s.dx, s.dy, s.dz}, &best, &prim, &cs, &cb);
+			else for (uint32_t j = 0; j < n_prims; j++) {
+				const float4 sp = sc.prims[j]; float d;
+				if (sphere_hit_closest(sp.x, sp.y, sp.z, sp.w, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, &d) && d < best) { best = d; prim = static_cast<int32_t>(j); }
+			}
+			if (prim < 0) { counters[3]++; break; }  // miss: terminated, radiance stays
+			counters[2]++;
+			const Surface sf = shade_surface(sc, s, best, prim);
+			if (last) { rad_zero(rad_out, fr.npix, s.pid); counters[4]++; break; }
+			ShadowRay sr; bool want_shadow = mis && shade_light_sample(sc, sf, s, prim, acc, seed, bounce, &sr);
+			f3 e{0, 0, 0};
+			if (sf.emissive) e = shade_emission(sc, sf, s, best, bounce, mis);
+			if (want_shadow) {
+				counters[1]++;
+				bool occ = false;
+				if (use_bvh) occ = traverse_any<false>(sc.wide, Ray{sr.o.x, sr.o.y, sr.o.z, sr.d.x, sr.d.y, sr.d.z}, sr.tfar, &cs, &cb);
+				else for (uint32_t j = 0; j < n_prims && !occ; j++) {
+					const float4 sp = sc.prims[j];
+					occ = sphere_hit_any(sp.x, sp.y, sp.z, sp.w, sr.o.x, sr.o.y, sr.o.z, sr.d.x, sr.d.y, sr.d.z, sr.tfar);
+				}
+				if (occ) want_shadow = false;
+			}
+			if (want_shadow || sf.emissive) rad_add(rad_out, fr.npix, s.pid, want_shadow ? sr.L : f3{0, 0, 0}, e);
+			if (!shade_continue(sf, &s, acc, seed, bounce)) { counters[3]++; break; }
+		}
+	}
+	return 0;
+}
+
+// flatten_bvh tap: out may be null to size
+int hc_flatten(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* prims, uint32_t n_prims, void* out, uint32_t* n_wide, uint32_t* max_stack) {
+	WideBvh w; flatten_bvh(nodes, n_nodes, prims, n_prims, w);
+	*n_wide = static_cast<uint32_t>(w.nodes.size()); *max_stack = w.max_stack;
+	if (out) std::memcpy(out, w.nodes.data(), w.nodes.size() * sizeof(WideNode));
+	return 0;
+}
+
+// scalar taps of csrc/b2r_math.h for function-level comparison with the oracle
+uint32_t hc_hash_2d(uint32_t x, uint32_t y) { return hash_2d(x, y); }
+uint32_t hc_hash_u32(uint32_t x) { return hash_u32(x); }
+void hc_pcg3(uint32_t state, float out[2], uint32_t* bounded, uint32_t range, uint32_t* state_out) { Pcg r{state}; out[0] = r.next_unit(); out[1] = r.next_unit(); *bounded = r.next_below(range); *state_out = r.state; }
+void hc_sincos(float x, float* s, float* c) { sincos_poly(x, s, c); }
+float hc_asin(float x) { return asin_poly(x); }
+float hc_atan2(float y, float x) { return atan2_poly(y, x); }
+void hc_hemisphere(float u0, float u1, float out[3]) { f3 v = cosine_hemisphere(u0, u1); out[0] = v.x; out[1] = v.y; out[2] = v.z; }
+void hc_tangent(const float n[3], float out_wxyz[4]) { TangentQuat q = tangent_frame(f3{n[0], n[1], n[2]}); out_wxyz[0] = q.w; out_wxyz[1] = q.x; out_wxyz[2] = q.y; out_wxyz[3] = 0.0f; }
+void hc_to_local(const float q[4], const float v[3], float out[3]) { f3 r = frame_to_local(TangentQuat{q[0], q[1], q[2]}, f3{v[0], v[1], v[2]}); out[0] = r.x; out[1] = r.y; out[2] = r.z; }
+void hc_to_world(const float q[4], const float v[3], float out[3]) { f3 r = frame_to_world(TangentQuat{q[0], q[1], q[2]}, f3{v[0], v[1], v[2]}); out[0] = r.x; out[1] = r.y; out[2] = r.z; }
+void hc_onb(const float n[3], float out[6]) { f3 a, b; branchless_onb(f3{n[0], n[1], n[2]}, &a, &b); out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = b.x; out[4] = b.y; out[5] = b.z; }
+void hc_sample_sphere(const float wc[3], float s2, float cd, float r2, float u0, float u1, float out[5]) {
+	float d, p; f3 L = sample_sphere_cone(f3{wc[0], wc[1], wc[2]}, s2, cd, r2, u0, u1, &d, &p); out[0] = L.x; out[1] = L.y; out[2] = L.z; out[3] = d; out[4] = p;
+}
+float hc_sphere_pdf(float r2, float d2) { return sphere_light_pdf(r2, d2); }
+float hc_power(float f, float g) { return power_heuristic(f, g); }
+float hc_power_over_f(float f, float g) { return power_heuristic_over_f(f, g); }
+float hc_median5(const float v[5]) { return median_of_5(v[0], v[1], v[2], v[3], v[4]); }
+void hc_tonemap(float rgb[3]) { aces_tonemap(rgb, rgb + 1, rgb + 2); }
+// closest / any sphere tests: returns 1 and the distance when the candidate is valid
+int hc_sphere_closest(const float s[4], const float ray[6], float* d) { return sphere_hit_closest(s[0], s[1], s[2], s[3], ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], d) ? 1 : 0; }
+int hc_sphere_any(const float s[4], const float ray[6], float tfar) { return sphere_hit_any(s[0], s[1], s[2], s[3], ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], tfar) ? 1 : 0; }
+
+}  // extern "C"

@@ -1,0 +1,41 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/b2r.h declares; no compute without a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import b2r
+from conftest import ROOT, have_gpu
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "b2r.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2r_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert header_symbols() == sorted(b2r.ABI_SYMBOLS)
+
+
+def test_library_exports_every_symbol():
+    L = C.CDLL(b2r.LIB_PATH)
+    for s in header_symbols():
+        assert hasattr(L, s), s
+    assert b2r.lib().b2r_abi_version() == 1
+
+
+def test_struct_layouts_match_reference_pods():
+    import scenes
+    assert scenes.SPHERE_DTYPE.itemsize == 32 and scenes.MATERIAL_DTYPE.itemsize == 96 and scenes.NODE_DTYPE.itemsize == 32
+    assert C.sizeof(b2r.Config) == 36
+
+
+@pytest.mark.skipif(have_gpu(), reason="CPU-box behaviour")
+def test_no_cpu_fallback():
+    """Without a CUDA device the renderer refuses to exist: the product has no CPU path."""
+    import scenes
+    with pytest.raises(b2r.B2RError) as e:
+        b2r.Renderer(scenes.default_scene(), 64, 64)
+    assert e.value.code == b2r.ERR_CUDA

@@ -1,0 +1,216 @@
+"""GPU parity tests (-m gpu): the sm_100a kernels, called through the C ABI (libb2r.so), against the CPU oracle on the same
+scene, camera, seeds and bounce count; against committed golden fixtures; and, at BASELINE.json's full sizes, through
+size-independent properties (BVH traversal == brute force on the GPU itself, oracle spot-check tiles, sample-range additivity).
+
+Tolerances (north_star): BVH node and leaf order bit-exact; per-sample pixel radiance within 1e-4 relative with the fraction of
+divergent pixels reported (asserted small); converged image RMSE < 1e-3. The brute-force pipeline is in fact bit-exact.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import b2r
+import oracle_py
+import scenes
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+REL_TOL = 1e-4
+
+
+def divergent_fraction(a, b):
+    """fraction of pixels whose radiance differs by more than 1e-4 relative in any channel/bucket"""
+    rel = np.abs(a - b) / np.maximum(np.abs(b), 1e-6)
+    return float((rel > REL_TOL).any(axis=tuple(range(a.ndim - 1))).mean())
+
+
+def oracle_for(sc, w, h, mb, K, flags=0):
+    o = oracle_py.Oracle(w, h, max_bounces=mb, K=K, flags=flags); o.set_scene(sc); return o
+
+
+# ------------------------------------------------------------------------------------------------ stage-level parity
+def test_camera_rays_bit_exact():
+    sc = scenes.default_scene()
+    for (w, h, mb, acc) in [(1280, 720, 8, 1), (1920, 1088, 16, 64), (320, 192, 16, 1024)]:
+        r = b2r.Renderer(sc, w, h, max_bounces=mb)
+        o = oracle_for(sc, w, h, mb, 5)
+        assert r.generate_rays(acc).tobytes() == o.generate_rays(acc).tobytes()
+        r.close()
+
+
+@pytest.mark.parametrize("n,flags", [(9, 0), (300, b2r.FLAG_FORCE_BRUTE), (300, b2r.FLAG_FORCE_BVH), (20000, b2r.FLAG_FORCE_BVH)])
+def test_traverse_api_vs_bruteforce_oracle(n, flags):
+    """BoundingVolumeHierarchy::Traverse / Traverse_shadow on caller rays (Application.cpp:282-298)."""
+    sc = scenes.default_scene() if n == 9 else scenes.random_scene(n, light_every=50)
+    r = b2r.Renderer(sc, 64, 64, flags=flags); o = oracle_for(sc, 64, 64, 16, 1)
+    rs = np.random.RandomState(n)
+    m = 20000 if n <= 300 else 3000
+    span = 3.0 if n == 9 else 150.0
+    rays = np.zeros((m, 6), np.float32); rays[:, :3] = rs.uniform(-span, span, (m, 3)); d = rs.randn(m, 3); rays[:, 3:] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    t, p = r.trace_closest(rays); to, po = o.trace_closest(rays)
+    mismatch = float((p != po).mean())
+    print(f"closest-hit prim mismatch fraction n={n} flags={flags}: {mismatch:.2e}")
+    if flags != b2r.FLAG_FORCE_BVH:
+        assert mismatch == 0.0 and t.tobytes() == to.tobytes()
+    else:
+        assert mismatch < 1e-3 and np.array_equal(t[p == po], to[p == po])
+    tf = rs.uniform(1.0, 2 * span, m).astype(np.float32)
+    occ = r.trace_shadow(rays, tf); occ_o = o.trace_shadow(rays, tf)
+    assert float((occ != occ_o).mean()) < (1e-3 if flags == b2r.FLAG_FORCE_BVH else 1e-12)
+    r.close()
+
+
+# ------------------------------------------------------------------------------------------------ per-sample radiance
+def test_c1_default_scene_720p_one_sample():
+    """BASELINE configs[0]: default scene, 1280x720, 1 spp, max_bounces 8 — the reference's own CPU-runnable case."""
+    sc = scenes.default_scene()
+    r = b2r.Renderer(sc, 1280, 720, max_bounces=8, buckets=5); r.Accumulate(1)
+    o = oracle_for(sc, 1280, 720, 8, 5); o.accumulate(1)
+    g, ref = r.buckets_host(), o.buckets()
+    frac = divergent_fraction(g, ref)
+    print(f"C1 divergent pixel fraction {frac:.3e}; bit-exact: {g.tobytes() == ref.tobytes()}")
+    assert frac == 0.0 and g.tobytes() == ref.tobytes()
+    gc, oc = r.counters(), o.counters()
+    assert gc["extension_rays"] == oc["extension_rays"] and gc["shaded_hits"] == oc["shaded_hits"]
+    assert gc["terminated"] == oc["terminated"] and gc["dropped"] == oc["dropped"] and gc["shadow_rays"] <= oc["shadow_rays"]
+    r.close()
+
+
+def test_golden_fixture_without_oracle():
+    g = json.load(open(os.path.join(G, "oracle_frames.json")))
+    sc = scenes.default_scene()
+    r = b2r.Renderer(sc, 320, 192, max_bounces=8, buckets=5); r.Accumulate(5)
+    assert hashlib.sha256(r.buckets_host().tobytes()).hexdigest() == g["default_320x192_mb8_K5_acc5"]["sha256_buckets"]
+    assert r.Render()
+    assert hashlib.sha256(r.framebuffer.tobytes()).hexdigest() == g["default_320x192_render_sha256"]
+    r2 = b2r.Renderer(sc, 160, 96, max_bounces=16, buckets=1); r2.accumulations = 63; r2.Accumulate(1)
+    assert hashlib.sha256(r2.buckets_host().tobytes()).hexdigest() == g["default_160x96_mb16_K1_acc64"]["sha256_buckets"]
+    sc3 = scenes.random_scene(2000, light_every=50)
+    r3 = b2r.Renderer(sc3, 160, 96, max_bounces=8, buckets=1, flags=b2r.FLAG_FORCE_BRUTE); r3.Accumulate(1)
+    assert hashlib.sha256(r3.buckets_host().tobytes()).hexdigest() == g["random2000_160x96_mb8_K1_acc1"]["sha256_buckets"]
+    for x in (r, r2, r3): x.close()
+
+
+@pytest.mark.parametrize("K,n", [(5, 65), (8, 64)])
+def test_c2_median_of_means_resolve(K, n):
+    """BASELINE configs[1] semantics at reduced size: n samples into K buckets, median-of-means + ACES (Renderer.hpp:436-478).
+    K=5/65 is the reference-exact variant (Q21), K=8/64 this repo's definition of '8 buckets'."""
+    sc = scenes.default_scene()
+    w, h = 480, 272
+    r = b2r.Renderer(sc, w, h, max_bounces=16, buckets=K); o = oracle_for(sc, w, h, 16, K)
+    for step in (n - K, K):  # Render() is a no-op unless accumulations % K == 0 (Renderer.hpp:437)
+        r.Accumulate(step); o.accumulate(step)
+    assert r.accumulations == n and r.Render()
+    rc, ref = o.render(); assert rc == 0
+    assert divergent_fraction(r.buckets_host(), o.buckets()) == 0.0
+    rmse = float(np.sqrt(np.mean((r.framebuffer - ref) ** 2)))
+    print(f"K={K} converged tonemapped RMSE {rmse:.3e}; framebuffer bit-exact: {r.framebuffer.tobytes() == ref.tobytes()}")
+    assert rmse < 1e-3 and np.all(r.framebuffer[..., 3] == 1.0)
+    lin = np.zeros_like(r.framebuffer); assert r.Render(tonemap=False, out=lin)
+    assert float(np.sqrt(np.mean((lin - o.render(tonemap=False)[1]) ** 2))) < 1e-3
+    r.Accumulate(1); before = r.framebuffer.copy(); assert not r.Render() and np.array_equal(before, r.framebuffer)
+    r.close()
+
+
+@pytest.mark.parametrize("n,w,h,mb", [(600, 192, 112, 6), (5000, 160, 96, 8)])
+def test_bvh_pipeline_vs_bruteforce_oracle(n, w, h, mb):
+    """The flattened-BVH wavefront (intersect -> shade -> shadow kernels) against the brute-force oracle (the semantics the
+    reference ships, USEBVH false). Divergent = grazing hits where a padded box and the float sphere test disagree."""
+    sc = scenes.random_scene(n, light_every=40)
+    r = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=2, flags=b2r.FLAG_FORCE_BVH); r.Accumulate(4)
+    o = oracle_for(sc, w, h, mb, 2); o.accumulate(4)
+    frac = divergent_fraction(r.buckets_host(), o.buckets())
+    print(f"BVH pipeline n={n}: divergent pixel fraction {frac:.3e}")
+    assert frac < 2e-3
+    gc, oc = r.counters(), o.counters()
+    assert abs(gc["extension_rays"] - oc["extension_rays"]) <= 1e-3 * oc["extension_rays"]
+    r.close()
+
+
+def test_bvh_equals_brute_on_gpu_at_scale():
+    """Size-independent property at C3's scene size: on the GPU, BVH traversal and brute force over all 100k spheres produce
+    the same image for the same sample (tiles of the full 1920x1088 frame are too slow for the CPU oracle, not for the GPU)."""
+    sc = scenes.random_scene(100000)
+    ps = b2r.PreparedScene(sc, 640, 368)
+    a = b2r.Renderer(ps, 640, 368, max_bounces=16, buckets=1, flags=b2r.FLAG_FORCE_BVH, samples_in_flight=1); a.Accumulate(1)
+    b = b2r.Renderer(ps, 640, 368, max_bounces=16, buckets=1, flags=b2r.FLAG_FORCE_BRUTE, samples_in_flight=1); b.Accumulate(1)
+    frac = divergent_fraction(a.buckets_host(), b.buckets_host())
+    print(f"100k spheres, GPU BVH vs GPU brute force: divergent pixel fraction {frac:.3e}")
+    assert frac < 2e-3
+    a.close(); b.close()
+
+
+def test_c3_full_size_oracle_spot_tiles():
+    """BASELINE configs[2] at full size (100k spheres, 1920x1088 internal, MIS): 48 random 16x16 tiles of one sample are
+    re-rendered by the oracle (tiles are independent, Renderer.hpp:84) in stream-BVH mode and compared."""
+    sc = scenes.random_scene(100000)
+    w, h = 1920, 1088
+    r = b2r.Renderer(sc, w, h, max_bounces=16, buckets=8, samples_in_flight=2); r.Accumulate(2)
+    o = oracle_for(sc, w, h, 16, 8, flags=oracle_py.ORC_BVH)
+    tiles = np.random.RandomState(0).choice((w // 16) * (h // 16), 48, replace=False).astype(np.uint32)
+    o.accumulate_tiles(tiles, 2)
+    g, ref = r.buckets_host(), o.buckets()
+    idx = (tiles[:, None] * 256 + np.arange(256)[None, :]).ravel()
+    frac = divergent_fraction(g[:, :, idx], ref[:, :, idx])
+    print(f"C3 full-size spot tiles: divergent pixel fraction {frac:.3e} over {len(idx)} pixels")
+    assert frac < 5e-3
+    r.close()
+
+
+# ------------------------------------------------------------------------------------------------ interface behaviour
+def test_white_furnace_known_answer():
+    sc = scenes.white_furnace()
+    r = b2r.Renderer(sc, 64, 48, max_bounces=16, buckets=1); r.Accumulate(3)
+    assert np.all(r.buckets_host() == 3.0)
+    r.close()
+
+
+def test_sample_ranges_are_additive_and_resumable():
+    """RNG is a pure function of (sample index, pixel, bounce) (Q2-Q3): rendering samples 1..10 at once, in pieces, with a
+    different batch width, or after a bucket checkpoint restore gives identical bucket sums; graph and non-graph launches agree."""
+    sc = scenes.default_scene(); w, h = 256, 144
+    a = b2r.Renderer(sc, w, h, max_bounces=8, buckets=5); a.Accumulate(10); A = a.buckets_host()
+    b = b2r.Renderer(sc, w, h, max_bounces=8, buckets=5, samples_in_flight=3, flags=b2r.FLAG_NO_GRAPH)
+    b.Accumulate(4); ck = b.buckets_host(); b.ResetAccumulator(); b.write_buckets(ck); b.accumulations = 4; b.Accumulate(6)
+    assert A.tobytes() == b.buckets_host().tobytes()
+    kt = b.kernel_times(); assert kt["bounce_brute"][1] > 0 and kt["bounce_brute"][0] > 0.0
+    a.ResetAccumulator(); assert a.accumulations == 0 and not a.buckets_host().any()
+    a.Resize(128, 80); a.Accumulate(5); assert a.Render() and a.framebuffer.shape == (80, 128, 4)
+    o = oracle_for(sc, 128, 80, 8, 5); o.accumulate(5)
+    assert a.buckets_host().tobytes() == o.buckets().tobytes()
+    a.close(); b.close()
+
+
+def test_bucket_ownership_partitions_the_frame():
+    """Multi-GPU split: contexts owning buckets {b : b % G == g} together reproduce the single-context buckets."""
+    sc = scenes.default_scene(); w, h, K = 192, 112, 8
+    full = b2r.Renderer(sc, w, h, max_bounces=8, buckets=K); full.Accumulate(16); F = full.buckets_host()
+    parts = np.zeros_like(F)
+    for g in range(4):
+        r = b2r.Renderer(sc, w, h, max_bounces=8, buckets=K, bucket_first=g, bucket_stride=4); r.Accumulate(16)
+        P = r.buckets_host()
+        owned = [k for k in range(K) if k % 4 == g]
+        assert not P[[k for k in range(K) if k not in owned]].any()
+        parts += P; r.close()
+    assert parts.tobytes() == F.tobytes()
+    full.close()
+
+
+def test_error_behaviour():
+    sc = scenes.default_scene()
+    with pytest.raises(b2r.B2RError) as e:
+        b2r.Renderer(sc, 100, 64)
+    assert e.value.code == b2r.ERR_ARG
+    r = b2r.Renderer(None, 64, 64)
+    with pytest.raises(b2r.B2RError) as e:
+        r.Accumulate(1)
+    assert e.value.code == b2r.ERR_STATE
+    ps = b2r.PreparedScene(sc, 64, 64); bad = ps.nodes.copy(); bad["first_id"][0] = 0
+    ps.nodes = bad
+    with pytest.raises(b2r.B2RError) as e:
+        r.SetScene(ps)
+    assert e.value.code == b2r.ERR_BVH
+    r.close()

@@ -1,0 +1,104 @@
+"""Known-answer and invariant tests of the oracle (SURVEY.md §8c "other pins to build")."""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_py
+import scenes
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_golden_frames():
+    g = json.load(open(os.path.join(G, "oracle_frames.json")))
+    sc = scenes.default_scene()
+    o = oracle_py.Oracle(320, 192, max_bounces=8, K=5); o.set_scene(sc); o.accumulate(5)
+    rec = g["default_320x192_mb8_K5_acc5"]
+    assert hashlib.sha256(o.buckets().tobytes()).hexdigest() == rec["sha256_buckets"]  # also: result independent of thread count
+    assert {k: int(v) for k, v in o.counters().items()} == rec["counters"]
+    rc, img = o.render(); assert rc == 0
+    assert hashlib.sha256(img.tobytes()).hexdigest() == g["default_320x192_render_sha256"]
+    nodes, prims, ids = o.bvh()
+    assert [int(v) for v in ids] == g["default_bvh"]["prim_ids"]
+    assert hashlib.sha256(nodes.tobytes()).hexdigest() == g["default_bvh"]["sha256_nodes"]
+
+
+def test_scene_generator_is_stable():
+    g = json.load(open(os.path.join(G, "oracle_frames.json")))
+    sc = scenes.random_scene(2000, light_every=50)
+    assert hashlib.sha256(sc["geometry"].tobytes()).hexdigest() == g["random2000_bvh"]["scene_sha256"]
+    # vectorised PCG == the scalar oracle PCG
+    L = oracle_py.lib(); st = C.c_uint32(scenes._hash_u32(0x04D15A07))
+    ref = [float(L.orc_rand_unit_float(C.byref(st))) for _ in range(64)]
+    assert list(scenes.pcg_unit_floats(scenes._hash_u32(0x04D15A07), 64)) == ref
+
+
+def test_white_furnace():
+    """Application.cpp:218-223 with a 1x1 white HDRI: albedo-1 sphere in a uniform white sky vanishes; every linear pixel of
+    every sample equals ambient exactly. Paths still inside at max_bounces are dropped (Q11), so use few pixels that can trap."""
+    sc = scenes.white_furnace()
+    o = oracle_py.Oracle(64, 48, max_bounces=16, K=1); o.set_scene(sc); o.accumulate(3)
+    b = o.buckets()[0]
+    dropped = o.counters()["dropped"]
+    assert dropped == 0  # a convex sphere cannot trap a path
+    assert np.all(b == 3.0)
+
+
+def test_bvh_invariants():
+    for n in (1, 2, 3, 9, 64, 1000):
+        sc = scenes.random_scene(n, light_every=7)
+        o = oracle_py.Oracle(16, 16); o.set_scene(sc)
+        nodes, prims, ids = o.bvh()
+        assert len(nodes) == 2 * n - 1
+        assert sorted(ids.tolist()) == list(range(n))
+        assert np.array_equal(prims, sc["geometry"][ids])
+        leaves = nodes[nodes["prim_count"] != 0]
+        assert np.all(leaves["prim_count"] == 1) and sorted(leaves["first_id"].tolist()) == list(range(n))
+        for nd in nodes[nodes["prim_count"] == 0]:
+            a, b = nodes[nd["first_id"]], nodes[nd["first_id"] + 1]
+            da, db = a["max_bound"] - a["min_bound"], b["max_bound"] - b["min_bound"]
+            assert da[1] * da[2] >= db[1] * db[2]  # child 0 has the larger y*z "half area" (Q17, BVH.hpp:190-195)
+            assert np.all(np.minimum(a["min_bound"], b["min_bound"]) == nd["min_bound"]) and np.all(np.maximum(a["max_bound"], b["max_bound"]) == nd["max_bound"])
+
+
+def test_median_network_vs_sort():
+    L = oracle_py.lib(); rs = np.random.RandomState(3)
+    for _ in range(500):
+        v = rs.rand(5).astype(np.float32)
+        assert float(L.orc_median5(v.ctypes.data_as(C.POINTER(C.c_float)))) == float(np.sort(v)[2])
+    for K in (1, 3, 5, 7, 8, 16):
+        v = rs.rand(K).astype(np.float32); s = np.sort(v)
+        want = s[K // 2] if K % 2 else np.float32((s[K // 2 - 1] + s[K // 2]) * np.float32(0.5))
+        assert float(L.orc_median_k(v.ctypes.data_as(C.POINTER(C.c_float)), K)) == float(want)
+
+
+def test_brute_vs_stream_bvh_modes_agree():
+    """USEBVH true (BVH.hpp:320-358, restated) vs the shipped brute force: same (tfar, primID) apart from grazing hits."""
+    sc = scenes.random_scene(500, light_every=25)
+    a = oracle_py.Oracle(96, 64, max_bounces=6, K=1); a.set_scene(sc); a.accumulate(1)
+    b = oracle_py.Oracle(96, 64, max_bounces=6, K=1, flags=oracle_py.ORC_BVH); b.set_scene(sc); b.accumulate(1)
+    x, y = a.buckets(), b.buckets()
+    rel = np.abs(x - y) / np.maximum(np.abs(x), 1e-6)
+    assert (rel > 1e-4).any(axis=(0, 1)).mean() < 5e-3
+    assert b.counters()["box_tests"] > 0 and b.counters()["sphere_tests"] < a.counters()["sphere_tests"]
+
+
+def test_slot_exact_quirk_is_small():
+    """Q7/Q16: the reference's slot-dependent SIMD/tail formula mix vs the canonical FMA-everywhere rule."""
+    sc = scenes.default_scene()
+    a = oracle_py.Oracle(160, 96, max_bounces=8, K=1); a.set_scene(sc); a.accumulate(1)
+    b = oracle_py.Oracle(160, 96, max_bounces=8, K=1, flags=oracle_py.ORC_SLOT_EXACT); b.set_scene(sc); b.accumulate(1)
+    x, y = a.buckets(), b.buckets()
+    rel = np.abs(x - y) / np.maximum(np.abs(x), 1e-6)
+    assert (rel > 1e-4).any(axis=(0, 1)).mean() < 2e-3
+
+
+def test_render_only_on_full_rounds():
+    sc = scenes.default_scene()
+    o = oracle_py.Oracle(32, 32, max_bounces=4, K=5); o.set_scene(sc)
+    o.accumulate(4); assert o.render()[0] == 1  # Renderer.hpp:437
+    o.accumulate(1); rc, img = o.render(); assert rc == 0 and np.all(img[..., 3] == 1.0) and img[..., :3].max() <= 1.0
