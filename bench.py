@@ -52,22 +52,61 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled every 5 ms from a thread
+    (nvidia_ml_py), falling back to `nvidia-smi -lms` when NVML cannot be loaded."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False); self.p = None; self.gpu = gpu
+        self.gpu = gpu; self.sm = []; self.reasons = set(); self.mx = None; self.power = []; self.t = None; self.p = None; self.f = None; self.run = False
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            idx = self.gpu
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.run = True
+
+            def loop():
+                while self.run:
+                    try:
+                        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        r = get_reasons(h)
+                        for k, b in bits.items():
+                            if r & b:
+                                self.reasons.add(k)
+                        self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1e3)
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+            self.t = threading.Thread(target=loop, daemon=True); self.t.start()
         except Exception:
-            self.p = None
+            self.t = None
+            try:
+                self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+                self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
+                time.sleep(0.3)
+            except Exception:
+                self.p = None
 
     def stop(self):
+        if self.t is not None:
+            self.run = False; self.t.join(timeout=1.0)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons), "samples": len(self.sm),
+                    "power_w_max": max(self.power) if self.power else None, "source": "nvml"}
         if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15); self.p.terminate()
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        self.p.terminate()
         try:
             self.p.wait(timeout=5)
         except Exception:
@@ -86,7 +125,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         os.unlink(self.f.name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def cpu_oracle_run(wl, scene, samples, fast=True):
@@ -134,7 +173,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1); ap.add_argument("--steps", type=int, default=5); ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"]); ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true"); ap.add_argument("--no-profile-pass", action="store_true")
-    ap.add_argument("--samples-in-flight", type=int, default=8)
+    ap.add_argument("--samples-in-flight", type=int, default=0, help="0 = library default (auto)")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel (for ncu); never used for a reported number")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     wl = WORKLOADS[args.workload]
@@ -160,26 +200,36 @@ def main():
 
     scene = make_scene(wl["scene"])
     ps = b2r.PreparedScene(scene, wl["w"], wl["h"])  # host BVH build + light list: scene (re)build, outside the hot path
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(device=dev)  # a real (non-default) stream: the library launches on it and the timing events are recorded on it
+    torch.cuda.set_stream(stream)
     K, spp = wl["K"], wl["spp"]
     shard = b2r_dist.shard_kwargs(rank, world, K)
     r = b2r.Renderer(ps, wl["w"], wl["h"], max_bounces=wl["mb"], buckets=K, device=local, stream=stream.cuda_stream,
-                     samples_in_flight=args.samples_in_flight, **shard)
+                     samples_in_flight=args.samples_in_flight, flags=b2r.FLAG_NO_GRAPH if args.no_graph else 0, **shard)
     # weak scaling: every rank renders `spp` samples of its own buckets per step => world*spp sample indices per step
     step_samples = spp * world
     local_buckets = b2r_dist.buckets_tensor(r, dev)
 
+    dbg = bool(os.environ.get("B2R_BENCH_DEBUG"))
+
     def step(to_host_fb=None, upload=False):
+        t0 = time.perf_counter()
         if upload:
             r.SetScene(ps)  # host -> device: spheres, materials, lights, flattened BVH, camera
+        t1 = time.perf_counter()
         r.ResetAccumulator()
         r.Accumulate(step_samples)
+        if dbg:
+            r.sync(); print(f"[dbg] upload {t1 - t0:.4f}s accumulate {time.perf_counter() - t1:.4f}s", file=sys.stderr)
+        t2 = time.perf_counter()
         if world > 1:
             combined = b2r_dist.combine_buckets(local_buckets)  # the one collective: NCCL all-reduce of the bucket sums
             ok = r.Render(to_host=to_host_fb is not None and rank == 0, out=to_host_fb, dev_buckets=combined.data_ptr())
         else:
             ok = r.Render(to_host=to_host_fb is not None, out=to_host_fb)
         assert ok
+        if dbg:
+            print(f"[dbg] render {time.perf_counter() - t2:.4f}s total {time.perf_counter() - t0:.4f}s", file=sys.stderr)
 
     def barrier():
         if world > 1:
@@ -195,6 +245,8 @@ def main():
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
+        if dbg:
+            print(f"[dbg] timed region {ms:.2f} ms for {n} steps", file=sys.stderr)
         if world > 1:
             t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
         return ms

@@ -22,7 +22,7 @@ except ImportError:  # imported as a top-level module from the package directory
     import scenes as _scenes
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2r.so")
+LIB_PATH = os.environ.get("B2R_LIB_PATH", os.path.join(_HERE, "libb2r.so"))  # override: kernel A/B experiments only
 
 FLAG_FORCE_BRUTE, FLAG_FORCE_BVH, FLAG_NO_MIS, FLAG_COUNT_TESTS, FLAG_NO_GRAPH = 1, 2, 4, 8, 16
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NO_LIGHTS, ERR_BVH, NOT_READY = 0, -1, -2, -3, -4, -5, 1

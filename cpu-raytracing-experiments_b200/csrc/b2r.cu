@@ -29,6 +29,16 @@ template <typename T> int dev_alloc(T** p, size_t count) {
 	CU(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
 	return B2R_OK;
 }
+// grow-only variant for the scene tables: a re-upload of a scene of the same size (Application.cpp:508-510 does one per
+// geometry edit) reuses the allocations instead of paying cudaFree/cudaMalloc every time
+template <typename T> int dev_reserve(T** p, size_t* capacity, size_t count) {
+	if (count == 0) count = 1;
+	if (*p && *capacity >= count) return B2R_OK;
+	if (*p) { cudaFree(*p); *p = nullptr; *capacity = 0; }
+	CU(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+	*capacity = count;
+	return B2R_OK;
+}
 template <typename T> void dev_free(T** p) { if (*p) { cudaFree(*p); *p = nullptr; } }
 
 }  // namespace
@@ -44,6 +54,7 @@ struct b2r_ctx {
 	float4 *d_prims = nullptr, *d_mat_albedo = nullptr, *d_mat_emission = nullptr, *d_light_sphere = nullptr, *d_light_emit = nullptr, *d_hdri = nullptr;
 	int32_t* d_prim_mat = nullptr;
 	WideNode* d_wide = nullptr;
+	size_t cap_prims = 0, cap_prim_mat = 0, cap_mat_albedo = 0, cap_mat_emission = 0, cap_light_sphere = 0, cap_light_emit = 0, cap_wide = 0, cap_hdri = 0;
 	WideBvh wide_host;
 	// frame
 	float4 *d_A[2] = {nullptr, nullptr}, *d_B[2] = {nullptr, nullptr}, *d_SA = nullptr, *d_SB = nullptr, *d_fb = nullptr;
@@ -74,6 +85,9 @@ void drop_graph(b2r_ctx* c) {
 
 int alloc_frame(b2r_ctx* c) {
 	const uint32_t w = c->cfg.width, h = c->cfg.height, npix = w * h, mb = c->cfg.max_bounces, K = c->cfg.buckets;
+	if (c->cfg.samples_in_flight == 0) {  // default: about 64M paths per wavefront batch (keeps the late, thin bounces a small share)
+		uint32_t s = (64u << 20) / npix; c->slots = s < 4u ? 4u : s > 32u ? 32u : s;
+	}
 	const size_t cap = static_cast<size_t>(c->slots) * npix;
 	if (cap >= (1ull << 32)) return fail(B2R_ERR_ARG, "samples_in_flight * pixels exceeds the 32-bit queue index");
 	int rc;
@@ -114,8 +128,8 @@ int compute_grids(b2r_ctx* c) {
 		*out = (n < 1 ? 1 : n) * c->sm_count; return B2R_OK;
 	};
 	int rc;
-	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<true, false>), kBlock, &c->grid_brute_first))) return rc;
-	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<false, false>), kBlock, &c->grid_brute))) return rc;
+	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<true, false>), kBruteBlock, &c->grid_brute_first))) return rc;
+	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<false, false>), kBruteBlock, &c->grid_brute))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_closest<false>), kTravBlock, &c->grid_closest))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_shade), kBlock, &c->grid_shade))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_shadow<false>), kTravBlock, &c->grid_shadow))) return rc;
@@ -145,8 +159,8 @@ int enqueue_batch(b2r_ctx* c, bool profile) {
 	if (!c->use_bvh) {
 		for (uint32_t b = 0; b < mb; b++) {
 			rc = launch(c, KK_BRUTE, profile, [&] {
-				if (b == 0) { if (count) k_bounce_brute<true, true><<<c->grid_brute_first, kBlock, 0, st>>>(p, b); else k_bounce_brute<true, false><<<c->grid_brute_first, kBlock, 0, st>>>(p, b); }
-				else { if (count) k_bounce_brute<false, true><<<c->grid_brute, kBlock, 0, st>>>(p, b); else k_bounce_brute<false, false><<<c->grid_brute, kBlock, 0, st>>>(p, b); }
+				if (b == 0) { if (count) k_bounce_brute<true, true><<<c->grid_brute_first, kBruteBlock, 0, st>>>(p, b); else k_bounce_brute<true, false><<<c->grid_brute_first, kBruteBlock, 0, st>>>(p, b); }
+				else { if (count) k_bounce_brute<false, true><<<c->grid_brute, kBruteBlock, 0, st>>>(p, b); else k_bounce_brute<false, false><<<c->grid_brute, kBruteBlock, 0, st>>>(p, b); }
 			});
 			if (rc) return rc;
 		}
@@ -232,7 +246,7 @@ int b2r_create(b2r_ctx** out, const b2r_config* cfg) {
 	if (cfg->device < 0 || cfg->device >= n_dev) return fail(B2R_ERR_ARG, "device ordinal out of range");
 	b2r_ctx* c = new b2r_ctx();
 	c->cfg = *cfg;
-	c->slots = cfg->samples_in_flight ? cfg->samples_in_flight : 8u;
+	c->slots = cfg->samples_in_flight;  // 0 = chosen from the image size in alloc_frame
 	int rc = ensure_device(c);
 	if (!rc) { cudaDeviceProp prop; e = cudaGetDeviceProperties(&prop, cfg->device); if (e != cudaSuccess) rc = fail(B2R_ERR_CUDA, cudaGetErrorString(e)); else c->sm_count = prop.multiProcessorCount; }
 	if (!rc) { e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking); if (e != cudaSuccess) rc = fail(B2R_ERR_CUDA, cudaGetErrorString(e)); c->stream = c->own_stream; }
@@ -327,25 +341,26 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 
 	PackedScene ps; pack_scene(prims, n_prims, materials, n_mat, light_geom_idx, n_lights, geometry, ps);
 	auto &h_prims = ps.prims, &h_alb = ps.mat_albedo, &h_em = ps.mat_emission, &h_ls = ps.light_sphere, &h_le = ps.light_emit; auto& h_pm = ps.prim_mat;
-	if ((rc = dev_alloc(&c->d_prims, h_prims.size()))) return rc;
-	if ((rc = dev_alloc(&c->d_prim_mat, h_pm.size()))) return rc;
-	if ((rc = dev_alloc(&c->d_mat_albedo, h_alb.size()))) return rc;
-	if ((rc = dev_alloc(&c->d_mat_emission, h_em.size()))) return rc;
-	if ((rc = dev_alloc(&c->d_light_sphere, h_ls.size()))) return rc;
-	if ((rc = dev_alloc(&c->d_light_emit, h_le.size()))) return rc;
-	if ((rc = dev_alloc(&c->d_wide, c->wide_host.nodes.size()))) return rc;
-	CU(cudaMemcpy(c->d_prims, h_prims.data(), h_prims.size() * sizeof(float4), cudaMemcpyHostToDevice));
-	CU(cudaMemcpy(c->d_prim_mat, h_pm.data(), h_pm.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-	CU(cudaMemcpy(c->d_mat_albedo, h_alb.data(), h_alb.size() * sizeof(float4), cudaMemcpyHostToDevice));
-	CU(cudaMemcpy(c->d_mat_emission, h_em.data(), h_em.size() * sizeof(float4), cudaMemcpyHostToDevice));
-	CU(cudaMemcpy(c->d_light_sphere, h_ls.data(), h_ls.size() * sizeof(float4), cudaMemcpyHostToDevice));
-	CU(cudaMemcpy(c->d_light_emit, h_le.data(), h_le.size() * sizeof(float4), cudaMemcpyHostToDevice));
-	CU(cudaMemcpy(c->d_wide, c->wide_host.nodes.data(), c->wide_host.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice));
+	if ((rc = dev_reserve(&c->d_prims, &c->cap_prims, h_prims.size()))) return rc;
+	if ((rc = dev_reserve(&c->d_prim_mat, &c->cap_prim_mat, h_pm.size()))) return rc;
+	if ((rc = dev_reserve(&c->d_mat_albedo, &c->cap_mat_albedo, h_alb.size()))) return rc;
+	if ((rc = dev_reserve(&c->d_mat_emission, &c->cap_mat_emission, h_em.size()))) return rc;
+	if ((rc = dev_reserve(&c->d_light_sphere, &c->cap_light_sphere, h_ls.size()))) return rc;
+	if ((rc = dev_reserve(&c->d_light_emit, &c->cap_light_emit, h_le.size()))) return rc;
+	if ((rc = dev_reserve(&c->d_wide, &c->cap_wide, c->wide_host.nodes.size()))) return rc;
+	CU(cudaMemcpyAsync(c->d_prims, h_prims.data(), h_prims.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->d_prim_mat, h_pm.data(), h_pm.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->d_mat_albedo, h_alb.data(), h_alb.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->d_mat_emission, h_em.data(), h_em.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->d_light_sphere, h_ls.data(), h_ls.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->d_light_emit, h_le.data(), h_le.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->d_wide, c->wide_host.nodes.data(), c->wide_host.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice, c->stream));
 	if (has_ambient) {
 		const size_t texels = static_cast<size_t>(hdri_w) * hdri_h;
-		if ((rc = dev_alloc(&c->d_hdri, texels))) return rc;
-		CU(cudaMemcpy(c->d_hdri, hdri_rgba, texels * sizeof(float4), cudaMemcpyHostToDevice));
+		if ((rc = dev_reserve(&c->d_hdri, &c->cap_hdri, texels))) return rc;
+		CU(cudaMemcpyAsync(c->d_hdri, hdri_rgba, texels * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
 	}
+	CU(cudaStreamSynchronize(c->stream));  // the staging vectors above go out of scope
 	SceneDev& s = c->params.scene;
 	s.prims = c->d_prims; s.prim_mat = c->d_prim_mat; s.mat_albedo = c->d_mat_albedo; s.mat_emission = c->d_mat_emission;
 	s.light_sphere = c->d_light_sphere; s.light_emit = c->d_light_emit; s.wide = c->d_wide; s.hdri = has_ambient ? c->d_hdri : nullptr;

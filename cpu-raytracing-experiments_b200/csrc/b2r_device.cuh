@@ -64,14 +64,41 @@ __device__ __forceinline__ uint32_t block_append(bool keep, uint32_t* counter, u
 }
 
 // ---------------------------------------------------------------------------------------------- brute-force pipeline
-// One fused kernel per bounce: intersect all spheres (BVH.hpp:311-318 as shipped, USEBVH false) -> closest-hit shader
-// -> light sample + inline any-hit -> emissive -> BRDF sample / roulette -> compacted append to the next queue.
-// Spheres are staged in shared memory (tiles of kBruteTile) and read as warp-uniform broadcasts.
+// One fused kernel per bounce (BVH.hpp:311-318 as shipped, USEBVH false): every ray is tested against every sphere, then the
+// hits are shaded: closest-hit shader -> light sample + inline any-hit -> emissive -> BRDF sample / roulette -> append.
+// Two things keep the SIMT lanes busy:
+//   * the scene (spheres, materials, lights) is staged in shared memory and read as warp-uniform broadcasts;
+//   * between intersection and shading the CTA compacts its hits through shared memory (index, distance, sphere), so the
+//     long shading code runs on dense warps while warps left without hits skip it — misses cost one intersection loop.
+#ifndef B2R_BRUTE_MIN_BLOCKS
+#define B2R_BRUTE_MIN_BLOCKS 7      // resident CTAs per SM the register allocation is bounded for
+#endif
+constexpr int kBruteBlock = 128;       // threads per CTA
+constexpr int kBruteWarps = kBruteBlock / 32;
+constexpr int kSmemTable = 64;         // materials / lights kept in shared memory when they fit
+
+// rank of each flagged thread inside the CTA and the CTA total; one barrier. `s_cnt` must not be reused before another barrier.
+__device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t* s_cnt, uint32_t* total) {
+	const uint32_t ballot = __ballot_sync(0xffffffffu, flag);
+	const uint32_t warp = threadIdx.x >> 5;
+	if (lane_id() == 0) s_cnt[warp] = __popc(ballot);
+	__syncthreads();
+	uint32_t off = 0, tot = 0;
+#pragma unroll
+	for (uint32_t w = 0; w < kBruteWarps; w++) { const uint32_t c = s_cnt[w]; off += (w < warp) ? c : 0u; tot += c; }
+	*total = tot;
+	return off + __popc(ballot & ((1u << lane_id()) - 1u));
+}
+
 template <bool FIRST, bool COUNT>
-__global__ void __launch_bounds__(kBlock, 2) k_bounce_brute(const Params p, const uint32_t bounce) {
+__global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_brute(const Params p, const uint32_t bounce) {
 	__shared__ float4 s_prim[kBruteTile];
-	__shared__ uint32_t s_warp[kBlock / 32 + 1];
-	const SceneDev& sc = p.scene;
+	__shared__ int32_t s_prim_mat[kBruteTile];
+	__shared__ float4 s_table[4][kSmemTable];  // mat_albedo, mat_emission, light_sphere, light_emit
+	__shared__ uint32_t s_hit_i[kBruteBlock]; __shared__ float s_hit_t[kBruteBlock]; __shared__ int32_t s_hit_prim[kBruteBlock];
+	__shared__ float s_hit_d[FIRST ? 3 : 1][kBruteBlock];
+	__shared__ uint32_t s_cnt_a[kBruteWarps], s_cnt_b[kBruteWarps], s_base;
+	SceneDev sc = p.scene;
 	const uint32_t n_in = FIRST ? p.batch->n_slots * p.frame.npix : p.cnt.paths[bounce];
 	const int side = bounce & 1;
 	const uint32_t n_tiles = (sc.n_prims + kBruteTile - 1) / kBruteTile;
@@ -79,47 +106,90 @@ __global__ void __launch_bounds__(kBlock, 2) k_bounce_brute(const Params p, cons
 	const bool last = bounce + 1 >= p.frame.max_bounces;
 	uint32_t c_shadow = 0, c_hits = 0, c_term = 0, c_drop = 0, c_events = 0, c_sphere = 0;
 
-	if (n_tiles == 1) {  // whole scene fits: stage once per CTA
-		for (uint32_t j = threadIdx.x; j < sc.n_prims; j += blockDim.x) s_prim[j] = ldg4(sc.prims + j);
-		__syncthreads();
+	// stage the scene tables once per CTA (persistent: amortised over the whole launch)
+	if (n_tiles == 1) {
+		for (uint32_t j = threadIdx.x; j < sc.n_prims; j += blockDim.x) { s_prim[j] = sc.prims[j]; s_prim_mat[j] = sc.prim_mat[j]; }
+		sc.prim_mat = s_prim_mat; sc.prims = s_prim;
 	}
-	for (uint32_t base = blockIdx.x * kBlock; base < n_in; base += gridDim.x * kBlock) {
+	if (sc.n_mat <= kSmemTable) {
+		for (uint32_t j = threadIdx.x; j < sc.n_mat; j += blockDim.x) { s_table[0][j] = sc.mat_albedo[j]; s_table[1][j] = sc.mat_emission[j]; }
+		sc.mat_albedo = s_table[0]; sc.mat_emission = s_table[1];
+	}
+	if (sc.n_lights <= kSmemTable) {
+		for (uint32_t j = threadIdx.x; j < sc.n_lights; j += blockDim.x) { s_table[2][j] = sc.light_sphere[j]; s_table[3][j] = sc.light_emit[j]; }
+		sc.light_sphere = s_table[2]; sc.light_emit = s_table[3];
+	}
+	__syncthreads();
+
+	for (uint32_t base = blockIdx.x * kBruteBlock; base < n_in; base += gridDim.x * kBruteBlock) {
+		// ---------------- phase 1: one ray per thread, closest hit over every sphere (ties -> lowest BVH-order index, strict <, Q6)
 		const uint32_t i = base + threadIdx.x;
 		const bool live = i < n_in;
-		PathState s;
-		if (live) s = FIRST ? primary_path(p.frame, p.batch->acc[i / p.frame.npix], i / p.frame.npix, i % p.frame.npix) : load_path(p.q, side, i);
-		// ---- closest hit over every sphere, ties to the lowest BVH-order index (strict <, Q6)
+		float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0;
+		if (live) {
+			if (FIRST) {
+				const PathState s0 = primary_path(p.frame, p.batch->acc[i / p.frame.npix], i / p.frame.npix, i % p.frame.npix);
+				ox = s0.ox; oy = s0.oy; oz = s0.oz; dx = s0.dx; dy = s0.dy; dz = s0.dz;
+			} else {
+				const float4 a = p.q.A[side][i], b = p.q.B[side][i];
+				ox = a.x; oy = a.y; oz = a.z; dx = a.w; dy = b.x; dz = b.y;
+			}
+		}
 		float best = FLT_MAX; int32_t prim = -1;
 		for (uint32_t tile = 0; tile < n_tiles; tile++) {
 			const uint32_t first = tile * kBruteTile, cnt = min(static_cast<uint32_t>(kBruteTile), sc.n_prims - first);
 			if (n_tiles > 1) {
 				__syncthreads();
-				for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) s_prim[j] = ldg4(sc.prims + first + j);
+				for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) s_prim[j] = p.scene.prims[first + j];
 				__syncthreads();
 			}
 			if (live) {
 				for (uint32_t j = 0; j < cnt; j++) {
 					const float4 sp = s_prim[j]; float d;
-					if (sphere_hit_closest(sp.x, sp.y, sp.z, sp.w, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, &d) && d < best) { best = d; prim = static_cast<int32_t>(first + j); }
+					if (sphere_hit_closest(sp.x, sp.y, sp.z, sp.w, ox, oy, oz, dx, dy, dz, &d) && d < best) { best = d; prim = static_cast<int32_t>(first + j); }
 				}
 				if (COUNT) c_sphere += cnt;
 			}
 		}
-		// ---- shade
-		bool keep = false, want_shadow = false, emissive = false, hit = live && prim >= 0;
-		Surface sf; ShadowRay sr; f3 e_add{0.0f, 0.0f, 0.0f};
-		uint32_t acc = 0, seed = 0;
-		if (hit) {
-			acc = p.batch->acc[s.pid >> 26]; seed = pixel_seed(s.pid & kPixMask, p.frame.max_bounces);
-			sf = shade_surface(sc, s, best, prim);
-			c_hits++;
-			if (!last) {  // at the last bounce the whole radiance of a surviving hit path is dropped (Q11): nothing to add
-				if (mis) want_shadow = shade_light_sample(sc, sf, s, prim, acc, seed, bounce, &sr);
-				emissive = sf.emissive;
-				if (emissive) e_add = shade_emission(sc, sf, s, best, bounce, mis);
+		const bool is_hit = live && prim >= 0;
+		if (live && !is_hit) {  // miss shader (Renderer.hpp:408-420): the path ends, its radiance stays at the pixel
+			c_term++;
+			if (sc.has_ambient) {
+				const PathState sm = FIRST ? primary_path(p.frame, p.batch->acc[i / p.frame.npix], i / p.frame.npix, i % p.frame.npix) : load_path(p.q, side, i);
+				rad_add(p.rad, p.frame.npix, sm.pid, shade_sky(sc, sm), f3{0.0f, 0.0f, 0.0f}); c_events++;
 			}
 		}
-		// ---- shadow ray: any hit along [0, tfar) (BVH.hpp:290-305)
+		// ---------------- compaction of the hits through shared memory
+		uint32_t n_hits;
+		const uint32_t slot = block_rank(is_hit, s_cnt_a, &n_hits);
+		if (is_hit) {
+			s_hit_i[slot] = i; s_hit_t[slot] = best; s_hit_prim[slot] = prim;
+			if (FIRST) { s_hit_d[0][slot] = dx; s_hit_d[FIRST ? 1 : 0][slot] = dy; s_hit_d[FIRST ? 2 : 0][slot] = dz; }
+		}
+		__syncthreads();
+		// ---------------- phase 2: dense warps shade the hits
+		const bool shade = threadIdx.x < n_hits;
+		bool keep = false, want_shadow = false, emissive = false;
+		PathState s; Surface sf; ShadowRay sr; f3 e_add{0.0f, 0.0f, 0.0f};
+		uint32_t acc = 0, seed = 0; float depth = 0.0f; int32_t hprim = -1;
+		if (shade) {
+			const uint32_t hi = s_hit_i[threadIdx.x]; depth = s_hit_t[threadIdx.x]; hprim = s_hit_prim[threadIdx.x];
+			if (FIRST) {
+				const uint32_t sl = hi / p.frame.npix, t = hi - sl * p.frame.npix;
+				s.ox = p.frame.cam.px; s.oy = p.frame.cam.py; s.oz = p.frame.cam.pz;
+				s.dx = s_hit_d[0][threadIdx.x]; s.dy = s_hit_d[FIRST ? 1 : 0][threadIdx.x]; s.dz = s_hit_d[FIRST ? 2 : 0][threadIdx.x];
+				s.tr = s.tg = s.tb = 1.0f; s.pdf = 0.0f; s.pid = (sl << 26) | t;
+			} else s = load_path(p.q, side, hi);
+			acc = p.batch->acc[s.pid >> 26]; seed = pixel_seed(s.pid & kPixMask, p.frame.max_bounces);
+			sf = shade_surface(sc, s, depth, hprim);
+			c_hits++;
+			if (!last) {  // at the last bounce the whole radiance of a surviving hit path is dropped (Q11): nothing to add
+				if (mis) want_shadow = shade_light_sample(sc, sf, s, hprim, acc, seed, bounce, &sr);
+				emissive = sf.emissive;
+				if (emissive) e_add = shade_emission(sc, sf, s, depth, bounce, mis);
+			}
+		}
+		// shadow ray: any hit along [0, tfar) (BVH.hpp:290-305)
 		if (n_tiles == 1) {
 			if (want_shadow) {
 				c_shadow++;
@@ -134,7 +204,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_bounce_brute(const Params p, cons
 			for (uint32_t tile = 0; tile < n_tiles; tile++) {
 				const uint32_t first = tile * kBruteTile, cnt = min(static_cast<uint32_t>(kBruteTile), sc.n_prims - first);
 				__syncthreads();
-				for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) s_prim[j] = ldg4(sc.prims + first + j);
+				for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) s_prim[j] = p.scene.prims[first + j];
 				__syncthreads();
 				if (want_shadow) {
 					if (COUNT) c_sphere += cnt;
@@ -145,8 +215,8 @@ __global__ void __launch_bounds__(kBlock, 2) k_bounce_brute(const Params p, cons
 				}
 			}
 		}
-		// ---- contributions: unoccluded light sample first, then emission (order of Renderer.hpp:304-353)
-		if (hit) {
+		// contributions: unoccluded light sample first, then emission (order of Renderer.hpp:304-353); then the next segment
+		if (shade) {
 			if (last) { rad_zero(p.rad, p.frame.npix, s.pid); c_drop++; }
 			else {
 				if (want_shadow || emissive) {
@@ -156,12 +226,13 @@ __global__ void __launch_bounds__(kBlock, 2) k_bounce_brute(const Params p, cons
 				keep = shade_continue(sf, &s, acc, seed, bounce);
 				if (!keep) c_term++;  // roulette: path ends here, radiance stays at the pixel (Renderer.hpp:379-381,424-430)
 			}
-		} else if (live) {  // miss (Renderer.hpp:408-420)
-			c_term++;
-			if (sc.has_ambient) { rad_add(p.rad, p.frame.npix, s.pid, shade_sky(sc, s), f3{0.0f, 0.0f, 0.0f}); c_events++; }
 		}
-		const uint32_t dst = block_append(keep, p.cnt.paths + bounce + 1, s_warp);
-		if (keep) store_path(p.q, side ^ 1, dst, s);
+		// ---------------- append the survivors to the next queue: one atomic per CTA
+		uint32_t n_keep;
+		const uint32_t rank = block_rank(keep, s_cnt_b, &n_keep);
+		if (threadIdx.x == 0) s_base = n_keep ? atomicAdd(p.cnt.paths + bounce + 1, n_keep) : 0u;
+		__syncthreads();
+		if (keep) store_path(p.q, side ^ 1, s_base + rank, s);
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.cnt.stats + ST_EXT, static_cast<unsigned long long>(n_in));
 	stat_add(p.cnt.stats, ST_SHADOW, c_shadow); stat_add(p.cnt.stats, ST_HITS, c_hits); stat_add(p.cnt.stats, ST_TERM, c_term);
@@ -176,25 +247,81 @@ __global__ void __launch_bounds__(kBlock) k_generate(const Params p) {
 		store_path(p.q, 0, i, primary_path(p.frame, p.batch->acc[i / p.frame.npix], i / p.frame.npix, i % p.frame.npix));
 	if (blockIdx.x == 0 && threadIdx.x == 0) p.cnt.paths[0] = n;
 }
-// closest-hit traversal of queue side (bounce & 1): persistent warps fetch 32 rays at a time
+// Work distribution of the traversal kernels: every warp owns a pool of ray indices claimed kTravChunk at a time from the
+// bounce's cursor (one atomic per chunk); lanes whose ray has finished are refilled from the pool as soon as fewer than
+// kRefillBelow lanes of the warp are still traversing, so a warp never idles behind its longest ray.
+constexpr uint32_t kTravChunk = 128, kRefillBelow = 24;
+struct WarpPool {
+	uint32_t next = 0, end = 0; bool dry = false;  // warp-uniform
+	// hands ray indices to the lanes flagged `idle`; returns the lane's index or 0xffffffff
+	__device__ __forceinline__ uint32_t take(bool idle, uint32_t* cursor, uint32_t n_in) {
+		const uint32_t mask = __ballot_sync(0xffffffffu, idle);
+		uint32_t mine = 0xffffffffu;
+		uint32_t want = __popc(mask), given = 0;
+		while (want > given && !dry) {
+			if (next >= end) {
+				uint32_t b = 0;
+				if (lane_id() == 0) b = atomicAdd(cursor, kTravChunk);
+				b = __shfl_sync(0xffffffffu, b, 0);
+				if (b >= n_in) { dry = true; break; }
+				next = b; end = min(b + kTravChunk, n_in);
+			}
+			const uint32_t n = min(want - given, end - next);
+			const uint32_t rank = __popc(mask & ((1u << lane_id()) - 1u));
+			if (idle && rank >= given && rank < given + n) mine = next + (rank - given);
+			next += n; given += n;
+		}
+		return mine;
+	}
+};
+// Node staging: the lanes of a warp sit on 32 different 128-byte nodes. Read naively that is 8 x LDG.128 with 32 lines each
+// (256 L1 wavefronts per step — the first version was bound by exactly that). Instead the warp copies the 32 nodes
+// cooperatively, 8 lanes x 16 B per node so each copy instruction touches 4 lines, straight into shared memory (cp.async,
+// no register staging); every lane then reads its own node back with conflict-free LDS.128 (rows padded to 144 B).
+constexpr int kNodeRowF4 = 9;  // 8 float4 of payload + 1 of padding per staged node
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+	const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void warp_stage_nodes(const WideNode* __restrict__ wide, float4* s_rows /*[32][kNodeRowF4] of this warp*/, uint32_t my_node, uint32_t live) {
+	const uint32_t lane = lane_id(), part = lane & 7u;
+#pragma unroll
+	for (uint32_t j = 0; j < 8; j++) {
+		const uint32_t owner = 4u * j + (lane >> 3);
+		const uint32_t nd = __shfl_sync(0xffffffffu, my_node, owner);
+		if ((live >> owner) & 1u) cp_async16(s_rows + owner * kNodeRowF4 + part, reinterpret_cast<const float4*>(wide + nd) + part);
+	}
+	asm volatile("cp.async.wait_all;" ::: "memory");
+	__syncwarp();
+}
+// closest-hit traversal of queue side (bounce & 1)
 template <bool COUNT>
 __global__ void __launch_bounds__(kTravBlock) k_intersect_closest(const Params p, const uint32_t bounce) {
 	const uint32_t n_in = p.cnt.paths[bounce];
 	const int side = bounce & 1;
+	const WideNode* __restrict__ wide = p.scene.wide;
 	uint32_t c_sphere = 0, c_box = 0;
+	__shared__ float4 s_nodes[kTravBlock / 32][32 * kNodeRowF4];
+	float4* rows = s_nodes[threadIdx.x >> 5];
+	WarpPool pool; TravClosest t; bool active = false; uint32_t idx = 0;
+	t.node = 0u;
 	for (;;) {
-		uint32_t base = 0;
-		if (lane_id() == 0) base = atomicAdd(p.cnt.work_a + bounce, 32u);
-		base = __shfl_sync(0xffffffffu, base, 0);
-		if (base >= n_in) break;
-		const uint32_t i = base + lane_id();
-		if (i < n_in) {
-			const float4 a = p.q.A[side][i], b = p.q.B[side][i];
-			const Ray r{a.x, a.y, a.z, a.w, b.x, b.y};
-			float best; int32_t prim;
-			traverse_closest<COUNT>(p.scene.wide, r, &best, &prim, &c_sphere, &c_box);
-			p.q.H[i] = make_float2(best, __int_as_float(prim));
+		const uint32_t got = pool.take(!active, p.cnt.work_a + bounce, n_in);
+		if (got != 0xffffffffu) {
+			idx = got; active = true;
+			const float4 a = p.q.A[side][idx], b = p.q.B[side][idx];
+			t.begin(Ray{a.x, a.y, a.z, a.w, b.x, b.y});
 		}
+		uint32_t live = __ballot_sync(0xffffffffu, active);
+		if (live == 0u) break;
+		do {
+			warp_stage_nodes(wide, rows, t.node, live);
+			if (active && !t.template step_staged<COUNT>(rows + lane_id() * kNodeRowF4, &c_sphere, &c_box)) {
+				p.q.H[idx] = make_float2(t.best, __int_as_float(t.prim));
+				active = false;
+			}
+			live = __ballot_sync(0xffffffffu, active);
+		} while (live != 0u && (pool.dry || __popc(live) >= kRefillBelow));
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.cnt.stats + ST_EXT, static_cast<unsigned long long>(n_in));
 	if (COUNT) { stat_add(p.cnt.stats, ST_SPHERE, c_sphere); stat_add(p.cnt.stats, ST_BOX, c_box); }
@@ -247,21 +374,33 @@ __global__ void __launch_bounds__(kBlock, 2) k_shade(const Params p, const uint3
 template <bool COUNT>
 __global__ void __launch_bounds__(kTravBlock) k_intersect_shadow(const Params p, const uint32_t bounce) {
 	const uint32_t n_in = p.cnt.shadow[bounce];
+	const WideNode* __restrict__ wide = p.scene.wide;
 	uint32_t c_sphere = 0, c_box = 0, c_events = 0;
+	__shared__ float4 s_nodes[kTravBlock / 32][32 * kNodeRowF4];
+	float4* rows = s_nodes[threadIdx.x >> 5];
+	WarpPool pool; TravAny t; bool active = false; uint32_t idx = 0, pid = 0;
+	t.node = 0u;
 	for (;;) {
-		uint32_t base = 0;
-		if (lane_id() == 0) base = atomicAdd(p.cnt.work_b + bounce, 32u);
-		base = __shfl_sync(0xffffffffu, base, 0);
-		if (base >= n_in) break;
-		const uint32_t i = base + lane_id();
-		if (i < n_in) {
-			const float4 a = p.q.SA[i], b = p.q.SB[i];
-			const Ray r{a.x, a.y, a.z, a.w, b.x, b.y};
-			if (!traverse_any<COUNT>(p.scene.wide, r, b.z, &c_sphere, &c_box)) {
-				const f3 L{p.q.SL[i], p.q.SL[p.q.cap + i], p.q.SL[2u * p.q.cap + i]};
-				rad_add(p.rad, p.frame.npix, __float_as_uint(b.w), L, f3{0.0f, 0.0f, 0.0f}); c_events++;
-			}
+		const uint32_t got = pool.take(!active, p.cnt.work_b + bounce, n_in);
+		if (got != 0xffffffffu) {
+			idx = got; active = true;
+			const float4 a = p.q.SA[idx], b = p.q.SB[idx];
+			pid = __float_as_uint(b.w);
+			t.begin(Ray{a.x, a.y, a.z, a.w, b.x, b.y}, b.z);
 		}
+		uint32_t live = __ballot_sync(0xffffffffu, active);
+		if (live == 0u) break;
+		do {
+			warp_stage_nodes(wide, rows, t.node, live);
+			if (active && !t.template step_staged<COUNT>(rows + lane_id() * kNodeRowF4, &c_sphere, &c_box)) {
+				if (!t.occluded) {
+					const f3 L{p.q.SL[idx], p.q.SL[p.q.cap + idx], p.q.SL[2u * p.q.cap + idx]};
+					rad_add(p.rad, p.frame.npix, pid, L, f3{0.0f, 0.0f, 0.0f}); c_events++;
+				}
+				active = false;
+			}
+			live = __ballot_sync(0xffffffffu, active);
+		} while (live != 0u && (pool.dry || __popc(live) >= kRefillBelow));
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.cnt.stats + ST_SHADOW, static_cast<unsigned long long>(n_in));
 	stat_add(p.cnt.stats, ST_EVENTS, c_events);

@@ -198,6 +198,8 @@ void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* 
 			const uint32_t open = kids[pick];
 			kids[pick] = nodes[open].first_id; kids[nk++] = nodes[open].first_id + 1;
 		}
+		// slot order: inner children first, then leaves (lanes of a warp then mostly run the same kind of test per slot)
+		std::stable_sort(kids, kids + nk, [&](uint32_t x, uint32_t y) { return (nodes[x].prim_count == 0) > (nodes[y].prim_count == 0); });
 		WideNode w; uint32_t n_inner = 0;
 		for (int k = 0; k < 4; k++) {
 			if (k >= nk) { set_empty(w, k); continue; }

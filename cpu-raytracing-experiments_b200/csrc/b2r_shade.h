@@ -16,6 +16,7 @@ constexpr uint32_t kPixMask = (1u << 26) - 1u;
 
 B2R_HD int32_t as_int(float f) { return static_cast<int32_t>(bits(f)); }
 B2R_HD float from_int(int32_t v) { return from_bits(static_cast<uint32_t>(v)); }
+// read-only global data (BVH nodes): LDG through the read-only path
 B2R_HD float4 ldg4(const float4* p) {
 #if defined(__CUDA_ARCH__)
 	return __ldg(p);
@@ -23,13 +24,8 @@ B2R_HD float4 ldg4(const float4* p) {
 	return *p;
 #endif
 }
-B2R_HD int32_t ldg_i32(const int32_t* p) {
-#if defined(__CUDA_ARCH__)
-	return __ldg(p);
-#else
-	return *p;
-#endif
-}
+// scene tables (spheres, materials, lights): generic loads, because the brute-force kernels point SceneDev at shared-memory copies
+B2R_HD float4 ld4(const float4* p) { return *p; }
 
 enum Stat { ST_EXT = 0, ST_SHADOW, ST_HITS, ST_TERM, ST_DROPPED, ST_SPHERE, ST_BOX, ST_EVENTS, ST_COUNT };
 
@@ -105,7 +101,7 @@ struct ShadowRay { f3 o, d; float tfar; f3 L; };
 
 // closest-hit shader, Renderer.hpp:169-214
 B2R_HD Surface shade_surface(const SceneDev& sc, const PathState& s, float depth, int32_t prim) {
-	const float4 sp = ldg4(sc.prims + prim);
+	const float4 sp = ld4(sc.prims + prim);
 	const f3 D{s.dx, s.dy, s.dz};
 	const f3 hp{s.ox + D.x * depth, s.oy + D.y * depth, s.oz + D.z * depth};
 	f3 N = unit3(f3{hp.x - sp.x, hp.y - sp.y, hp.z - sp.z});
@@ -114,8 +110,8 @@ B2R_HD Surface shade_surface(const SceneDev& sc, const PathState& s, float depth
 	sf.T = tangent_frame(N);
 	sf.n_dot_v = frame_to_local(sf.T, f3{-D.x, -D.y, -D.z}).z;
 	sf.P = f3{hp.x + N.x * 1e-4f, hp.y + N.y * 1e-4f, hp.z + N.z * 1e-4f};
-	sf.mat = ldg_i32(sc.prim_mat + prim);
-	const float4 al = ldg4(sc.mat_albedo + sf.mat);
+	sf.mat = sc.prim_mat[prim];
+	const float4 al = ld4(sc.mat_albedo + sf.mat);
 	sf.albedo = f3{al.x, al.y, al.z}; sf.emissive = al.w != 0.0f; sf.r2 = sp.w;
 	return sf;
 }
@@ -126,7 +122,7 @@ B2R_HD bool shade_light_sample(const SceneDev& sc, const Surface& sf, const Path
 	Pcg rng{hash_2d(acc, seed + bounce * 2u)};  // Q3
 	const float u0 = rng.next_unit(), u1 = rng.next_unit();
 	const uint32_t pick = rng.next_below(sc.n_lights);
-	const float4 ls = ldg4(sc.light_sphere + pick), le = ldg4(sc.light_emit + pick);
+	const float4 ls = ld4(sc.light_sphere + pick), le = ld4(sc.light_emit + pick);
 	if (as_int(le.w) == hit_prim) return false;  // Q9: geometry index vs BVH-order index, as in the reference
 	f3 wc{ls.x - sf.P.x, ls.y - sf.P.y, ls.z - sf.P.z};
 	const float d2 = dot3(wc, wc);
@@ -153,7 +149,7 @@ B2R_HD bool shade_light_sample(const SceneDev& sc, const Surface& sf, const Path
 }
 // emissive-hit contribution, Renderer.hpp:319-353
 B2R_HD f3 shade_emission(const SceneDev& sc, const Surface& sf, const PathState& s, float depth, uint32_t bounce, bool mis) {
-	const float4 em = ldg4(sc.mat_emission + sf.mat);
+	const float4 em = ld4(sc.mat_emission + sf.mat);
 	if (!mis) return f3{s.tr * em.x, s.tg * em.y, s.tb * em.z};  // this repo's MIS-off (Q23)
 	if (bounce == 0) return f3{em.x, em.y, em.z};
 	const float d2 = depth * (depth + sf.n_dot_v * (2.0f * sqrtf(sf.r2))) + sf.r2;  // law of cosines, Renderer.hpp:331
@@ -195,12 +191,15 @@ B2R_HD void rad_zero(float* rad, uint32_t npix, uint32_t pid) {
 }
 
 // ---------------------------------------------------------------------------------------------- BVH traversal
-// Per-thread traversal of the 4-wide tree with a short stack in local memory. Inner slots: slab test clipped to
-// [0, limit]; leaf slots hold the sphere itself, so a leaf costs no extra fetch. Children are visited nearest first.
+// Per-lane traversal of the 4-wide tree, written as a resumable state machine: *_begin() arms a ray, *_step() visits ONE node
+// and returns false when the ray is finished. The persistent kernels keep 32 such machines per warp and refill finished lanes
+// with new rays, so a warp is not held up by its longest ray. Inner slots: slab test clipped to [0, limit]; leaf slots hold
+// the sphere itself (no leaf fetch). Slots are ordered inner-first by the flattener, which keeps the lanes of a warp on the
+// same kind of test. The closest-hit machine visits children nearest first and keeps a short stack in local memory.
 struct Ray { float ox, oy, oz, dx, dy, dz; };
 
 B2R_HD void slab(const float4 a, const float4 b, float ix, float iy, float iz, float nx, float ny, float nz,
-                                     float limit, float* tnear, bool* hit) {
+                 float limit, float* tnear, bool* hit) {
 	// box = {a.x,a.y,a.z | a.w,b.x,b.y}; t = plane*inv - origin*inv as one FMA (box tests never decide a result)
 	const float x0 = fma_rn(a.x, ix, nx), x1 = fma_rn(a.w, ix, nx);
 	const float y0 = fma_rn(a.y, iy, ny), y1 = fma_rn(b.x, iy, ny);
@@ -211,32 +210,54 @@ B2R_HD void slab(const float4 a, const float4 b, float ix, float iy, float iz, f
 }
 #define B2R_CSWAP(ka, la, kb, lb) { const bool sw = kb < ka; const uint32_t tk = sw ? kb : ka, tl = sw ? lb : la; kb = sw ? ka : kb; lb = sw ? la : lb; ka = tk; la = tl; }
 
-// Closest hit == brute force over all spheres: a candidate replaces the best when d < best, or d == best with a lower
-// sphere index (the brute-force loop keeps the first of equal distances, BVH.hpp:265); nodes are culled only when
-// their entry distance is beyond the best.
-template <bool COUNT>
-B2R_HD void traverse_closest(const WideNode* __restrict__ wide, const Ray& r, float* best_out, int32_t* prim_out,
-                                                 uint32_t* c_sphere, uint32_t* c_box) {
-	const float ix = 1.0f / r.dx, iy = 1.0f / r.dy, iz = 1.0f / r.dz;
-	const float nx = -(r.ox * ix), ny = -(r.oy * iy), nz = -(r.oz * iz);
-	float best = FLT_MAX; int32_t prim = -1;
-	uint2 stack[kTraversalStack]; int sp = 0;
-	uint32_t node = 0;
-	for (;;) {
+struct TravBase {
+	float ox, oy, oz, dx, dy, dz;   // ray
+	float ix, iy, iz, nx, ny, nz;   // 1/d and -o/d
+	uint32_t node; int sp;
+	B2R_HD void arm(const Ray& r) {
+		ox = r.ox; oy = r.oy; oz = r.oz; dx = r.dx; dy = r.dy; dz = r.dz;
+		ix = 1.0f / r.dx; iy = 1.0f / r.dy; iz = 1.0f / r.dz;
+		nx = -(r.ox * ix); ny = -(r.oy * iy); nz = -(r.oz * iz);
+		node = 0u; sp = 0;
+	}
+};
+// Closest hit == brute force over all spheres (BVH.hpp:311-318): a candidate replaces the best when d < best, or d == best with
+// a lower sphere index (the brute-force loop keeps the first of equal distances, BVH.hpp:265); a node is culled only when its
+// entry distance is beyond the best.
+struct TravClosest : TravBase {
+	float best; int32_t prim;
+	uint2 stack[kTraversalStack];
+	B2R_HD void begin(const Ray& r) { arm(r); best = FLT_MAX; prim = -1; }
+	template <bool COUNT>
+	B2R_HD bool step(const WideNode* __restrict__ wide, uint32_t* c_sphere, uint32_t* c_box) {
 		const float4* n = reinterpret_cast<const float4*>(wide + node);
-		uint32_t key[4]; uint32_t link[4];
+		float4 a[4], b[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++) { a[k] = ldg4(n + 2 * k); b[k] = ldg4(n + 2 * k + 1); }
+		return visit<COUNT>(a, b, c_sphere, c_box);
+	}
+	// same, with the node's eight float4 already staged at `n` (shared memory in the kernels)
+	template <bool COUNT>
+	B2R_HD bool step_staged(const float4* n, uint32_t* c_sphere, uint32_t* c_box) {
+		float4 a[4], b[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++) { a[k] = n[2 * k]; b[k] = n[2 * k + 1]; }
+		return visit<COUNT>(a, b, c_sphere, c_box);
+	}
+	template <bool COUNT>
+	B2R_HD bool visit(const float4 (&a)[4], const float4 (&b)[4], uint32_t* c_sphere, uint32_t* c_box) {
+		uint32_t key[4], link[4];
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
-			const float4 a = ldg4(n + 2 * k), b = ldg4(n + 2 * k + 1);
-			const int32_t l = as_int(b.z);
+			const int32_t l = as_int(b[k].z);
 			key[k] = 0xffffffffu; link[k] = 0u;
 			if (l >= 0) {
-				float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, best, &tn, &h);
+				float tn; bool h; slab(a[k], b[k], ix, iy, iz, nx, ny, nz, best, &tn, &h);
 				if (COUNT) (*c_box)++;
 				if (h) { key[k] = bits(tn); link[k] = static_cast<uint32_t>(l); }
 			} else if (l != kEmptyLink) {
 				float d; if (COUNT) (*c_sphere)++;
-				if (sphere_hit_closest(a.x, a.y, a.z, a.w, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, &d)) {
+				if (sphere_hit_closest(a[k].x, a[k].y, a[k].z, a[k].w, ox, oy, oz, dx, dy, dz, &d)) {
 					const int32_t id = ~l;
 					if (d < best || (d == best && id < prim)) { best = d; prim = id; }
 				}
@@ -249,44 +270,67 @@ B2R_HD void traverse_closest(const WideNode* __restrict__ wide, const Ray& r, fl
 		if (key[3] != 0xffffffffu) stack[sp++] = make_uint2(link[3], key[3]);
 		if (key[2] != 0xffffffffu) stack[sp++] = make_uint2(link[2], key[2]);
 		if (key[1] != 0xffffffffu) stack[sp++] = make_uint2(link[1], key[1]);
-		if (key[0] != 0xffffffffu && from_bits(key[0]) <= best) { node = link[0]; continue; }
-		bool found = false;
+		if (key[0] != 0xffffffffu && from_bits(key[0]) <= best) { node = link[0]; return true; }
 		while (sp > 0) {
 			const uint2 e = stack[--sp];
-			if (from_bits(e.y) <= best) { node = e.x; found = true; break; }
+			if (from_bits(e.y) <= best) { node = e.x; return true; }
 		}
-		if (!found) break;
+		return false;
 	}
-	*best_out = best; *prim_out = prim;
-}
-// Any hit along [0, tfar) — Traverse_shadow semantics (BVH.hpp:290-305): order-independent boolean.
-template <bool COUNT>
-B2R_HD bool traverse_any(const WideNode* __restrict__ wide, const Ray& r, float tfar, uint32_t* c_sphere, uint32_t* c_box) {
-	const float ix = 1.0f / r.dx, iy = 1.0f / r.dy, iz = 1.0f / r.dz;
-	const float nx = -(r.ox * ix), ny = -(r.oy * iy), nz = -(r.oz * iz);
-	uint32_t stack[kTraversalStack]; int sp = 0;
-	uint32_t node = 0;
-	for (;;) {
+};
+// Any hit along [0, tfar) — Traverse_shadow semantics (BVH.hpp:290-305): an order-independent boolean.
+struct TravAny : TravBase {
+	float tfar; bool occluded;
+	uint32_t stack[kTraversalStack];
+	B2R_HD void begin(const Ray& r, float limit) { arm(r); tfar = limit; occluded = false; }
+	template <bool COUNT>
+	B2R_HD bool step(const WideNode* __restrict__ wide, uint32_t* c_sphere, uint32_t* c_box) {
 		const float4* n = reinterpret_cast<const float4*>(wide + node);
+		float4 a[4], b[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++) { a[k] = ldg4(n + 2 * k); b[k] = ldg4(n + 2 * k + 1); }
+		return visit<COUNT>(a, b, c_sphere, c_box);
+	}
+	template <bool COUNT>
+	B2R_HD bool step_staged(const float4* n, uint32_t* c_sphere, uint32_t* c_box) {
+		float4 a[4], b[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++) { a[k] = n[2 * k]; b[k] = n[2 * k + 1]; }
+		return visit<COUNT>(a, b, c_sphere, c_box);
+	}
+	template <bool COUNT>
+	B2R_HD bool visit(const float4 (&a)[4], const float4 (&b)[4], uint32_t* c_sphere, uint32_t* c_box) {
 		uint32_t next = 0xffffffffu;
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
-			const float4 a = ldg4(n + 2 * k), b = ldg4(n + 2 * k + 1);
-			const int32_t l = as_int(b.z);
+			const int32_t l = as_int(b[k].z);
 			if (l >= 0) {
-				float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, tfar, &tn, &h);
+				float tn; bool h; slab(a[k], b[k], ix, iy, iz, nx, ny, nz, tfar, &tn, &h);
 				if (COUNT) (*c_box)++;
 				if (h) { if (next != 0xffffffffu) stack[sp++] = next; next = static_cast<uint32_t>(l); }
 			} else if (l != kEmptyLink) {
 				if (COUNT) (*c_sphere)++;
-				if (sphere_hit_any(a.x, a.y, a.z, a.w, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, tfar)) return true;
+				if (sphere_hit_any(a[k].x, a[k].y, a[k].z, a[k].w, ox, oy, oz, dx, dy, dz, tfar)) { occluded = true; return false; }
 			}
 		}
-		if (next != 0xffffffffu) { node = next; continue; }
+		if (next != 0xffffffffu) { node = next; return true; }
 		if (sp == 0) return false;
 		node = stack[--sp];
+		return true;
 	}
+};
+// whole-ray wrappers (trace taps, host check)
+template <bool COUNT>
+B2R_HD void traverse_closest(const WideNode* __restrict__ wide, const Ray& r, float* best_out, int32_t* prim_out, uint32_t* c_sphere, uint32_t* c_box) {
+	TravClosest t; t.begin(r);
+	while (t.template step<COUNT>(wide, c_sphere, c_box)) {}
+	*best_out = t.best; *prim_out = t.prim;
 }
-
+template <bool COUNT>
+B2R_HD bool traverse_any(const WideNode* __restrict__ wide, const Ray& r, float tfar, uint32_t* c_sphere, uint32_t* c_box) {
+	TravAny t; t.begin(r, tfar);
+	while (t.template step<COUNT>(wide, c_sphere, c_box)) {}
+	return t.occluded;
+}
 
 }  // namespace b2r

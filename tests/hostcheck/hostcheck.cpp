@@ -100,3 +100,17 @@ int hc_sphere_closest(const float s[4], const float ray[6], float* d) { return s
 int hc_sphere_any(const float s[4], const float ray[6], float tfar) { return sphere_hit_any(s[0], s[1], s[2], s[3], ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], tfar) ? 1 : 0; }
 
 }  // extern "C"
+
+// per-ray traversal statistics (steps = wide nodes visited, box and sphere tests) for caller rays: tuning aid
+extern "C" int hc_trace_stats(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* prims, uint32_t n_prims, const float* rays, uint32_t n,
+                              uint32_t* steps, uint32_t* boxes, uint32_t* spheres, int32_t* prim_out) {
+	WideBvh w; flatten_bvh(nodes, n_nodes, prims, n_prims, w);
+	for (uint32_t i = 0; i < n; i++) {
+		const float* r = rays + 6 * static_cast<size_t>(i);
+		TravClosest t; t.begin(Ray{r[0], r[1], r[2], r[3], r[4], r[5]});
+		uint32_t cs = 0, cb = 0, st = 0;
+		do { st++; } while (t.step<true>(w.nodes.data(), &cs, &cb));
+		steps[i] = st; boxes[i] = cb; spheres[i] = cs; prim_out[i] = t.prim;
+	}
+	return 0;
+}
