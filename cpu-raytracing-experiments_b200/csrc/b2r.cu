@@ -55,7 +55,7 @@ struct b2r_ctx {
 	int32_t* d_prim_mat = nullptr;
 	WideNode* d_wide = nullptr;
 	size_t cap_prims = 0, cap_prim_mat = 0, cap_mat_albedo = 0, cap_mat_emission = 0, cap_light_sphere = 0, cap_light_emit = 0, cap_wide = 0, cap_hdri = 0;
-	WideBvh wide_host;
+	WideBvh wide_host; uint64_t wide_key = 0; bool have_wide = false;
 	// frame
 	float4 *d_A[2] = {nullptr, nullptr}, *d_B[2] = {nullptr, nullptr}, *d_SA = nullptr, *d_SB = nullptr, *d_fb = nullptr;
 	float *d_T[2] = {nullptr, nullptr}, *d_SL = nullptr, *d_rad = nullptr, *d_acc = nullptr;
@@ -312,6 +312,7 @@ int b2r_set_flags(b2r_ctx* c, uint32_t flags) {
 	if (!c) return fail(B2R_ERR_ARG, "null context");
 	int rc = ensure_device(c); if (rc) return rc;
 	CU(cudaStreamSynchronize(c->stream));
+	if ((c->cfg.flags ^ flags) & B2R_FLAG_REFERENCE_TREE) return fail(B2R_ERR_STATE, "B2R_FLAG_REFERENCE_TREE can only be chosen at b2r_create");
 	c->cfg.flags = flags; c->params.frame.flags = flags;
 	if (c->have_scene) {
 		const uint32_t n = c->params.scene.n_prims;
@@ -336,8 +337,17 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 	int rc = ensure_device(c); if (rc) return rc;
 	CU(cudaStreamSynchronize(c->stream));
 
-	flatten_bvh(nodes, n_nodes, prims, n_prims, c->wide_host);
-	if (c->wide_host.max_stack > static_cast<uint32_t>(kTraversalStack)) return fail(B2R_ERR_BVH, "tree needs a deeper traversal stack than kTraversalStack");
+	{  // derived traversal layout, cached on the sphere array (and on which topology was asked for)
+		uint64_t key = 1469598103934665603ull ^ ((c->cfg.flags & B2R_FLAG_REFERENCE_TREE) ? 0x9e3779b97f4a7c15ull : 0ull);
+		const uint64_t* w = reinterpret_cast<const uint64_t*>(prims);
+		for (size_t i = 0; i < static_cast<size_t>(n_prims) * (sizeof(b2r_sphere) / 8); i++) key = (key ^ w[i]) * 1099511628211ull;
+		if (!c->have_wide || key != c->wide_key) {
+			if (c->cfg.flags & B2R_FLAG_REFERENCE_TREE) flatten_bvh(nodes, n_nodes, prims, n_prims, c->wide_host);
+			else { std::vector<b2r_bvh_node> tree; build_traversal_tree(prims, n_prims, tree); flatten_bvh(tree.data(), static_cast<uint32_t>(tree.size()), prims, n_prims, c->wide_host); }
+			c->wide_key = key; c->have_wide = true;
+		}
+	}
+	if (c->wide_host.max_stack > static_cast<uint32_t>(kTraversalStack)) { c->have_wide = false; return fail(B2R_ERR_BVH, "tree needs a deeper traversal stack than kTraversalStack"); }
 
 	PackedScene ps; pack_scene(prims, n_prims, materials, n_mat, light_geom_idx, n_lights, geometry, ps);
 	auto &h_prims = ps.prims, &h_alb = ps.mat_albedo, &h_em = ps.mat_emission, &h_ls = ps.light_sphere, &h_le = ps.light_emit; auto& h_pm = ps.prim_mat;

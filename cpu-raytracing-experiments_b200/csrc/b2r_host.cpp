@@ -297,3 +297,82 @@ int b2r_camera_lookat(const float eye[3], const float dir[3], uint32_t width, ui
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------- traversal tree
+// The reference's tree (above) must keep its node order, quirks included: its split "area" is only extent.y*extent.z (Q17),
+// which yields long, overlapping boxes — about 46 wide-node visits and 58 sphere tests per primary ray on the 100k-sphere
+// scene. Traversal results do not depend on the tree (closest hit == brute force over all spheres; leaf links carry the
+// reference's leaf index), so the GPU walks a tree built for traversal instead: binned SAH over the true surface area,
+// one sphere per leaf, emitted in the same {box, first_id, prim_count} node format so flatten_bvh() is shared.
+namespace b2r {
+namespace {
+struct TBox { float lo[3], hi[3]; };
+inline TBox tbox_empty() { return TBox{{FLT_MAX, FLT_MAX, FLT_MAX}, {-FLT_MAX, -FLT_MAX, -FLT_MAX}}; }
+inline void tbox_grow(TBox& a, const TBox& b) { for (int k = 0; k < 3; k++) { a.lo[k] = fminf(a.lo[k], b.lo[k]); a.hi[k] = fmaxf(a.hi[k], b.hi[k]); } }
+inline float tbox_area(const TBox& b) { const float x = b.hi[0] - b.lo[0], y = b.hi[1] - b.lo[1], z = b.hi[2] - b.lo[2]; return x * y + y * z + z * x; }
+}  // namespace
+
+void build_traversal_tree(const b2r_sphere* prims, uint32_t n, std::vector<b2r_bvh_node>& nodes) {
+	nodes.clear();
+	if (n == 0) { nodes.push_back(to_node(void_box(), 0, 0)); return; }
+	constexpr int kBins = 16;
+	std::vector<TBox> box(n); std::vector<float> cen(3 * static_cast<size_t>(n)); std::vector<uint32_t> ids(n);
+	for (uint32_t i = 0; i < n; i++) {
+		const float r = sqrtf(prims[i].radius_sq);
+		for (int k = 0; k < 3; k++) { box[i].lo[k] = prims[i].position[k] - r; box[i].hi[k] = prims[i].position[k] + r; cen[3 * static_cast<size_t>(i) + k] = prims[i].position[k]; }
+		ids[i] = i;
+	}
+	auto emit = [&](const TBox& b, uint32_t first, uint32_t count) { b2r_bvh_node nd; for (int k = 0; k < 3; k++) { nd.min_bound[k] = b.lo[k]; nd.max_bound[k] = b.hi[k]; } nd.first_id = first; nd.prim_count = count; nodes.push_back(nd); return static_cast<uint32_t>(nodes.size() - 1); };
+	TBox root = tbox_empty(); for (uint32_t i = 0; i < n; i++) tbox_grow(root, box[i]);
+	emit(root, 0, 0);
+	struct Job { uint32_t node, begin, end; };
+	std::vector<Job> todo; todo.push_back({0u, 0u, n});
+	nodes.reserve(2 * static_cast<size_t>(n));
+	while (!todo.empty()) {
+		const Job j = todo.back(); todo.pop_back();
+		const uint32_t count = j.end - j.begin;
+		if (count == 1) { nodes[j.node].first_id = ids[j.begin]; nodes[j.node].prim_count = 1; continue; }
+		// centroid bounds
+		float clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+		for (uint32_t i = j.begin; i < j.end; i++) for (int k = 0; k < 3; k++) { const float c = cen[3 * static_cast<size_t>(ids[i]) + k]; clo[k] = fminf(clo[k], c); chi[k] = fmaxf(chi[k], c); }
+		int best_axis = -1, best_bin = 0; float best_cost = FLT_MAX;
+		for (int axis = 0; axis < 3; axis++) {
+			const float ext = chi[axis] - clo[axis];
+			if (!(ext > 0.0f)) continue;
+			TBox bb[kBins]; uint32_t bc[kBins];
+			for (int b = 0; b < kBins; b++) { bb[b] = tbox_empty(); bc[b] = 0; }
+			const float scale = kBins / ext;
+			for (uint32_t i = j.begin; i < j.end; i++) {
+				int b = static_cast<int>((cen[3 * static_cast<size_t>(ids[i]) + axis] - clo[axis]) * scale); if (b >= kBins) b = kBins - 1;
+				tbox_grow(bb[b], box[ids[i]]); bc[b]++;
+			}
+			float right_area[kBins]; uint32_t right_cnt[kBins];
+			TBox acc = tbox_empty(); uint32_t cnt = 0;
+			for (int b = kBins - 1; b > 0; b--) { tbox_grow(acc, bb[b]); cnt += bc[b]; right_area[b] = cnt ? tbox_area(acc) : 0.0f; right_cnt[b] = cnt; }
+			acc = tbox_empty(); cnt = 0;
+			for (int b = 0; b + 1 < kBins; b++) {
+				tbox_grow(acc, bb[b]); cnt += bc[b];
+				if (cnt == 0 || right_cnt[b + 1] == 0) continue;
+				const float cost = tbox_area(acc) * cnt + right_area[b + 1] * right_cnt[b + 1];
+				if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
+			}
+		}
+		uint32_t mid;
+		if (best_axis < 0) mid = j.begin + count / 2;  // all centroids coincide: split the list in half
+		else {
+			const float scale = kBins / (chi[best_axis] - clo[best_axis]);
+			auto it = std::partition(ids.begin() + j.begin, ids.begin() + j.end, [&](uint32_t id) {
+				int b = static_cast<int>((cen[3 * static_cast<size_t>(id) + best_axis] - clo[best_axis]) * scale); if (b >= kBins) b = kBins - 1;
+				return b <= best_bin; });
+			mid = static_cast<uint32_t>(it - ids.begin());
+			if (mid == j.begin || mid == j.end) mid = j.begin + count / 2;
+		}
+		TBox l = tbox_empty(), r = tbox_empty();
+		for (uint32_t i = j.begin; i < mid; i++) tbox_grow(l, box[ids[i]]);
+		for (uint32_t i = mid; i < j.end; i++) tbox_grow(r, box[ids[i]]);
+		const uint32_t pair = emit(l, 0, 0); emit(r, 0, 0);
+		nodes[j.node].first_id = pair; nodes[j.node].prim_count = 0;
+		todo.push_back({pair, j.begin, mid}); todo.push_back({pair + 1, mid, j.end});
+	}
+}
+}  // namespace b2r

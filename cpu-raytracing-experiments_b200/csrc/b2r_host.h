@@ -30,6 +30,8 @@ void build_reference_bvh(const b2r_sphere* geometry, uint32_t n, std::vector<b2r
                          std::vector<b2r_sphere>& prims, std::vector<uint32_t>& prim_ids);
 // Checks the invariants the flattening relies on (children adjacent, leaf size 1, indices in range). Returns false if malformed.
 bool validate_reference_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, uint32_t n_prims);
+// A second binary tree over the same spheres (reference leaf order kept in the leaf links), built for traversal speed.
+void build_traversal_tree(const b2r_sphere* prims_bvh_order, uint32_t n, std::vector<b2r_bvh_node>& nodes);
 // Collapse the binary tree 2 -> 4 wide and inline the leaf spheres.
 void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* prims, uint32_t n_prims, WideBvh& out);
 

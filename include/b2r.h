@@ -53,6 +53,7 @@ enum {
 	B2R_FLAG_NO_MIS      = 1u << 2, /* this repo's "MIS off" (SURVEY Q23): no light sampling, radiance += throughput*emission */
 	B2R_FLAG_COUNT_TESTS = 1u << 3, /* also count sphere / box tests (slower; for roofline accounting) */
 	B2R_FLAG_NO_GRAPH    = 1u << 4, /* launch kernels one by one instead of replaying a CUDA graph (profiling) */
+	B2R_FLAG_REFERENCE_TREE = 1u << 5, /* traverse the flattened REFERENCE tree (BVH.hpp:90-206 topology) instead of the tree built for traversal */
 };
 
 typedef struct b2r_config {
@@ -102,7 +103,10 @@ int  b2r_sync(b2r_ctx* ctx);
 
 /* Scene (Scene.hpp:19-26) as the renderer reads it: spheres in BVH leaf order + nodes (acceleration_structure),
  * materials, the light list (indices into geometry) and geometry in original order (read by NEE, Renderer.hpp:261-262),
- * sky (Primitives.hpp:29-47; hdri_rgba may be NULL when ambient is 0). Flattens the nodes to the 128-byte GPU layout. */
+ * sky (Primitives.hpp:29-47; hdri_rgba may be NULL when ambient is 0). The node array is validated; the GPU traverses a 128-byte
+ * 4-wide layout whose leaves are exactly prims_bvh_order (hit indices are BVH-order indices). By default its topology is rebuilt
+ * for traversal speed (results do not depend on it: closest hit == brute force); B2R_FLAG_REFERENCE_TREE flattens `nodes` itself.
+ * The derived layout is cached per context and reused while the spheres are unchanged. */
 int  b2r_upload_scene(b2r_ctx* ctx, const b2r_sphere* prims_bvh_order, const b2r_bvh_node* nodes, uint32_t n_prims,
                       uint32_t n_nodes, const b2r_material* materials, uint32_t n_mat, const int32_t* light_geom_idx,
                       uint32_t n_lights, const b2r_sphere* geometry, uint32_t n_geom, const float ambient[3],

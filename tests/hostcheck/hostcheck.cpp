@@ -13,12 +13,15 @@ using namespace b2r;
 extern "C" {
 
 // One sample (`acc`) for every pixel: rad_out[3][npix] (tile order). counters: ext rays, shadow rays, hits, term, dropped.
+// use_bvh: 0 brute force, 1 flattened reference tree, 2 traversal tree (libb2r's default).
 int hc_render_sample(const b2r_sphere* prims, const b2r_bvh_node* nodes, uint32_t n_prims, uint32_t n_nodes,
                      const b2r_material* materials, uint32_t n_mat, const int32_t* lights, uint32_t n_lights,
                      const b2r_sphere* geometry, const float cam11[11], uint32_t width, uint32_t height,
                      uint32_t max_bounces, uint32_t flags, uint32_t acc, int use_bvh, float* rad_out, uint64_t counters[5]) {
 	PackedScene ps; pack_scene(prims, n_prims, materials, n_mat, lights, n_lights, geometry, ps);
-	WideBvh wide; flatten_bvh(nodes, n_nodes, prims, n_prims, wide);
+	WideBvh wide;
+	if (use_bvh == 2) { std::vector<b2r_bvh_node> tree; build_traversal_tree(prims, n_prims, tree); flatten_bvh(tree.data(), static_cast<uint32_t>(tree.size()), prims, n_prims, wide); }  // what libb2r uploads by default
+	else flatten_bvh(nodes, n_nodes, prims, n_prims, wide);  // B2R_FLAG_REFERENCE_TREE
 	if (wide.max_stack > static_cast<uint32_t>(kTraversalStack)) return B2R_ERR_BVH;
 	SceneDev sc{};
 	sc.prims = ps.prims.data(); sc.prim_mat = ps.prim_mat.data(); sc.mat_albedo = ps.mat_albedo.data(); sc.mat_emission = ps.mat_emission.data();
@@ -104,7 +107,9 @@ int hc_sphere_any(const float s[4], const float ray[6], float tfar) { return sph
 // per-ray traversal statistics (steps = wide nodes visited, box and sphere tests) for caller rays: tuning aid
 extern "C" int hc_trace_stats(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* prims, uint32_t n_prims, const float* rays, uint32_t n,
                               uint32_t* steps, uint32_t* boxes, uint32_t* spheres, int32_t* prim_out) {
-	WideBvh w; flatten_bvh(nodes, n_nodes, prims, n_prims, w);
+	WideBvh w;
+	if (n_nodes == 0) { std::vector<b2r_bvh_node> tn; build_traversal_tree(prims, n_prims, tn); flatten_bvh(tn.data(), static_cast<uint32_t>(tn.size()), prims, n_prims, w); }
+	else flatten_bvh(nodes, n_nodes, prims, n_prims, w);
 	for (uint32_t i = 0; i < n; i++) {
 		const float* r = rays + 6 * static_cast<size_t>(i);
 		TravClosest t; t.begin(Ray{r[0], r[1], r[2], r[3], r[4], r[5]});

@@ -115,15 +115,15 @@ def test_c2_median_of_means_resolve(K, n):
     r.close()
 
 
-@pytest.mark.parametrize("n,w,h,mb", [(600, 192, 112, 6), (5000, 160, 96, 8)])
-def test_bvh_pipeline_vs_bruteforce_oracle(n, w, h, mb):
+@pytest.mark.parametrize("n,w,h,mb,tree", [(600, 192, 112, 6, 0), (5000, 160, 96, 8, 0), (5000, 160, 96, 8, b2r.FLAG_REFERENCE_TREE)])
+def test_bvh_pipeline_vs_bruteforce_oracle(n, w, h, mb, tree):
     """The flattened-BVH wavefront (intersect -> shade -> shadow kernels) against the brute-force oracle (the semantics the
     reference ships, USEBVH false). Divergent = grazing hits where a padded box and the float sphere test disagree."""
     sc = scenes.random_scene(n, light_every=40)
-    r = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=2, flags=b2r.FLAG_FORCE_BVH); r.Accumulate(4)
+    r = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=2, flags=b2r.FLAG_FORCE_BVH | tree); r.Accumulate(4)
     o = oracle_for(sc, w, h, mb, 2); o.accumulate(4)
     frac = divergent_fraction(r.buckets_host(), o.buckets())
-    print(f"BVH pipeline n={n}: divergent pixel fraction {frac:.3e}")
+    print(f"BVH pipeline n={n} tree={tree}: divergent pixel fraction {frac:.3e}")
     assert frac < 2e-3
     gc, oc = r.counters(), o.counters()
     assert abs(gc["extension_rays"] - oc["extension_rays"]) <= 1e-3 * oc["extension_rays"]

@@ -86,7 +86,7 @@ def render_hc(hostcheck, sc, w, h, mb, acc, use_bvh, flags=0):
     return rad, list(cnt)
 
 
-@pytest.mark.parametrize("name,w,h,mb,use_bvh", [("default", 320, 192, 8, 0), ("default", 160, 96, 16, 1), ("random", 160, 96, 8, 0), ("random", 160, 96, 8, 1)])
+@pytest.mark.parametrize("name,w,h,mb,use_bvh", [("default", 320, 192, 8, 0), ("default", 160, 96, 16, 1), ("default", 160, 96, 16, 2), ("random", 160, 96, 8, 0), ("random", 160, 96, 8, 1), ("random", 160, 96, 8, 2)])
 def test_per_sample_radiance_bit_exact(hostcheck, name, w, h, mb, use_bvh):
     """Same scene, camera, seeds and bounce count: the product routines reproduce the oracle's per-sample radiance bit-for-bit
     (brute force and 4-wide BVH traversal), and count the same rays."""
