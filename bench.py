@@ -149,7 +149,7 @@ def run_reference(args, wl, rank):
     if rank != 0:
         return
     scene = make_scene(wl["scene"])
-    per_step = 1  # 1 spp of the workload's frame per step (~1-3 s on the host cores)
+    per_step = 4 if wl["scene"] == "default" else 1  # a few spp of the workload's frame per step: a bounded sample (~0.1-20 s on the host cores)
     for _ in range(args.warmup):
         cpu_oracle_run(wl, scene, per_step)
     secs, rays, paths = 0.0, 0, 0

@@ -214,3 +214,20 @@ def test_error_behaviour():
         r.SetScene(ps)
     assert e.value.code == b2r.ERR_BVH
     r.close()
+
+
+def test_cpp_mirror_frame_loop(tmp_path):
+    """examples/frame_loop.cpp = the reference's per-frame driver (Application.cpp:361-406) on the C++ mirror
+    (host/Renderer.hpp etc.): builds with g++, links libb2r.so, and must land on the same frame as the Python path."""
+    import re
+    import subprocess
+    from conftest import ROOT, PKG
+    exe = str(tmp_path / "frame_loop")
+    subprocess.check_call(["g++", "-std=c++20", "-O2", os.path.join(ROOT, "examples", "frame_loop.cpp"), "-I", os.path.join(PKG, "host"),
+                           "-L", PKG, "-lb2r", f"-Wl,-rpath,{PKG}", "-o", exe])
+    out = subprocess.check_output([exe, "250", "130", "5"], text=True)   # padded to 256x144 like Application.cpp:367-372
+    m = re.search(r"\[(\d+) X (\d+)\].*mean tonemapped value ([0-9.]+) after (\d+) accumulations", out)
+    assert m and (int(m.group(1)), int(m.group(2)), int(m.group(4))) == (256, 144, 5)
+    r = b2r.Renderer(scenes.default_scene(), 256, 144, max_bounces=16, buckets=5); r.Accumulate(5); assert r.Render()
+    assert abs(float(m.group(3)) - float(r.framebuffer[..., :3].mean(dtype=np.float64))) < 1e-5
+    r.close()
