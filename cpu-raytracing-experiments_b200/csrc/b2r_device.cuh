@@ -92,11 +92,12 @@ __device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t* s_cnt, uint3
 
 template <bool FIRST, bool COUNT>
 __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_brute(const Params p, const uint32_t bounce) {
+	constexpr int kQ = 2 * kBruteBlock;  // hit queue: up to kBruteBlock-1 waiting + kBruteBlock new
 	__shared__ float4 s_prim[kBruteTile];
 	__shared__ int32_t s_prim_mat[kBruteTile];
 	__shared__ float4 s_table[4][kSmemTable];  // mat_albedo, mat_emission, light_sphere, light_emit
-	__shared__ uint32_t s_hit_i[kBruteBlock]; __shared__ float s_hit_t[kBruteBlock]; __shared__ int32_t s_hit_prim[kBruteBlock];
-	__shared__ float s_hit_d[FIRST ? 3 : 1][kBruteBlock];
+	__shared__ uint32_t s_hit_i[kQ]; __shared__ float s_hit_t[kQ]; __shared__ int32_t s_hit_prim[kQ];
+	__shared__ float s_hit_d[FIRST ? 3 : 1][FIRST ? kQ : 1];
 	__shared__ uint32_t s_cnt_a[kBruteWarps], s_cnt_b[kBruteWarps], s_base;
 	SceneDev sc = p.scene;
 	const uint32_t n_in = FIRST ? p.batch->n_slots * p.frame.npix : p.cnt.paths[bounce];
@@ -121,63 +122,75 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 	}
 	__syncthreads();
 
-	for (uint32_t base = blockIdx.x * kBruteBlock; base < n_in; base += gridDim.x * kBruteBlock) {
-		// ---------------- phase 1: one ray per thread, closest hit over every sphere (ties -> lowest BVH-order index, strict <, Q6)
-		const uint32_t i = base + threadIdx.x;
-		const bool live = i < n_in;
-		float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0;
-		if (live) {
-			if (FIRST) {
-				const PathState s0 = primary_path(p.frame, p.batch->acc[i / p.frame.npix], i / p.frame.npix, i % p.frame.npix);
-				ox = s0.ox; oy = s0.oy; oz = s0.oz; dx = s0.dx; dy = s0.dy; dz = s0.dz;
-			} else {
-				const float4 a = p.q.A[side][i], b = p.q.B[side][i];
-				ox = a.x; oy = a.y; oz = a.z; dx = a.w; dy = b.x; dz = b.y;
-			}
-		}
-		float best = FLT_MAX; int32_t prim = -1;
-		for (uint32_t tile = 0; tile < n_tiles; tile++) {
-			const uint32_t first = tile * kBruteTile, cnt = min(static_cast<uint32_t>(kBruteTile), sc.n_prims - first);
-			if (n_tiles > 1) {
-				__syncthreads();
-				for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) s_prim[j] = p.scene.prims[first + j];
-				__syncthreads();
-			}
+	uint32_t queued = 0;                       // hits waiting in shared memory (CTA-uniform)
+	uint32_t base = blockIdx.x * kBruteBlock;
+	for (;;) {
+		const bool more = base < n_in;         // CTA-uniform
+		if (more) {
+			// ---------------- phase 1: one ray per thread, closest hit over every sphere (ties -> lowest BVH-order index, strict <, Q6)
+			const uint32_t i = base + threadIdx.x;
+			const bool live = i < n_in;
+			float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0;
 			if (live) {
-				for (uint32_t j = 0; j < cnt; j++) {
-					const float4 sp = s_prim[j]; float d;
-					if (sphere_hit_closest(sp.x, sp.y, sp.z, sp.w, ox, oy, oz, dx, dy, dz, &d) && d < best) { best = d; prim = static_cast<int32_t>(first + j); }
+				if (FIRST) {
+					const PathState s0 = primary_path(p.frame, p.batch->acc[i / p.frame.npix], i / p.frame.npix, i % p.frame.npix);
+					ox = s0.ox; oy = s0.oy; oz = s0.oz; dx = s0.dx; dy = s0.dy; dz = s0.dz;
+				} else {
+					const float4 a = p.q.A[side][i], b = p.q.B[side][i];
+					ox = a.x; oy = a.y; oz = a.z; dx = a.w; dy = b.x; dz = b.y;
 				}
-				if (COUNT) c_sphere += cnt;
 			}
-		}
-		const bool is_hit = live && prim >= 0;
-		if (live && !is_hit) {  // miss shader (Renderer.hpp:408-420): the path ends, its radiance stays at the pixel
-			c_term++;
-			if (sc.has_ambient) {
-				const PathState sm = FIRST ? primary_path(p.frame, p.batch->acc[i / p.frame.npix], i / p.frame.npix, i % p.frame.npix) : load_path(p.q, side, i);
-				rad_add(p.rad, p.frame.npix, sm.pid, shade_sky(sc, sm), f3{0.0f, 0.0f, 0.0f}); c_events++;
+			float best = FLT_MAX; int32_t prim = -1;
+			for (uint32_t tile = 0; tile < n_tiles; tile++) {
+				const uint32_t first = tile * kBruteTile, cnt = min(static_cast<uint32_t>(kBruteTile), sc.n_prims - first);
+				if (n_tiles > 1) {
+					__syncthreads();
+					for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) s_prim[j] = p.scene.prims[first + j];
+					__syncthreads();
+				}
+				if (live) {
+					for (uint32_t j = 0; j < cnt; j++) {
+						const float4 sp = s_prim[j]; float d;
+						if (sphere_hit_closest(sp.x, sp.y, sp.z, sp.w, ox, oy, oz, dx, dy, dz, &d) && d < best) { best = d; prim = static_cast<int32_t>(first + j); }
+					}
+					if (COUNT) c_sphere += cnt;
+				}
 			}
+			const bool is_hit = live && prim >= 0;
+			if (live && !is_hit) {  // miss shader (Renderer.hpp:408-420): the path ends, its radiance stays at the pixel
+				c_term++;
+				if (sc.has_ambient) {
+					const PathState sm = FIRST ? primary_path(p.frame, p.batch->acc[i / p.frame.npix], i / p.frame.npix, i % p.frame.npix) : load_path(p.q, side, i);
+					rad_add(p.rad, p.frame.npix, sm.pid, shade_sky(sc, sm), f3{0.0f, 0.0f, 0.0f}); c_events++;
+				}
+			}
+			// ---------------- the CTA's hits join the shared-memory queue
+			uint32_t n_hits;
+			const uint32_t slot = queued + block_rank(is_hit, s_cnt_a, &n_hits);
+			if (is_hit) {
+				s_hit_i[slot] = i; s_hit_t[slot] = best; s_hit_prim[slot] = prim;
+				if (FIRST) { s_hit_d[0][slot] = dx; s_hit_d[FIRST ? 1 : 0][slot] = dy; s_hit_d[FIRST ? 2 : 0][slot] = dz; }
+			}
+			queued += n_hits;
+			base += gridDim.x * kBruteBlock;
+			__syncthreads();
 		}
-		// ---------------- compaction of the hits through shared memory
-		uint32_t n_hits;
-		const uint32_t slot = block_rank(is_hit, s_cnt_a, &n_hits);
-		if (is_hit) {
-			s_hit_i[slot] = i; s_hit_t[slot] = best; s_hit_prim[slot] = prim;
-			if (FIRST) { s_hit_d[0][slot] = dx; s_hit_d[FIRST ? 1 : 0][slot] = dy; s_hit_d[FIRST ? 2 : 0][slot] = dz; }
-		}
-		__syncthreads();
-		// ---------------- phase 2: dense warps shade the hits
-		const bool shade = threadIdx.x < n_hits;
+		// shade only full CTAs of hits (every warp dense), or whatever is left once the rays are exhausted
+		if (queued < static_cast<uint32_t>(kBruteBlock) && more) continue;
+		if (queued == 0) break;
+		// ---------------- phase 2: dense warps shade queued hits (taken from the tail of the queue)
+		const uint32_t take = min(queued, static_cast<uint32_t>(kBruteBlock));
+		const uint32_t qi = queued - take + threadIdx.x;
+		const bool shade = threadIdx.x < take;
 		bool keep = false, want_shadow = false, emissive = false;
 		PathState s; Surface sf; ShadowRay sr; f3 e_add{0.0f, 0.0f, 0.0f};
 		uint32_t acc = 0, seed = 0; float depth = 0.0f; int32_t hprim = -1;
 		if (shade) {
-			const uint32_t hi = s_hit_i[threadIdx.x]; depth = s_hit_t[threadIdx.x]; hprim = s_hit_prim[threadIdx.x];
+			const uint32_t hi = s_hit_i[qi]; depth = s_hit_t[qi]; hprim = s_hit_prim[qi];
 			if (FIRST) {
 				const uint32_t sl = hi / p.frame.npix, t = hi - sl * p.frame.npix;
 				s.ox = p.frame.cam.px; s.oy = p.frame.cam.py; s.oz = p.frame.cam.pz;
-				s.dx = s_hit_d[0][threadIdx.x]; s.dy = s_hit_d[FIRST ? 1 : 0][threadIdx.x]; s.dz = s_hit_d[FIRST ? 2 : 0][threadIdx.x];
+				s.dx = s_hit_d[0][FIRST ? qi : 0]; s.dy = s_hit_d[FIRST ? 1 : 0][FIRST ? qi : 0]; s.dz = s_hit_d[FIRST ? 2 : 0][FIRST ? qi : 0];
 				s.tr = s.tg = s.tb = 1.0f; s.pdf = 0.0f; s.pid = (sl << 26) | t;
 			} else s = load_path(p.q, side, hi);
 			acc = p.batch->acc[s.pid >> 26]; seed = pixel_seed(s.pid & kPixMask, p.frame.max_bounces);
@@ -189,6 +202,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 				if (emissive) e_add = shade_emission(sc, sf, s, depth, bounce, mis);
 			}
 		}
+		queued -= take;
 		// shadow ray: any hit along [0, tfar) (BVH.hpp:290-305)
 		if (n_tiles == 1) {
 			if (want_shadow) {
@@ -229,7 +243,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 		}
 		// ---------------- append the survivors to the next queue: one atomic per CTA
 		uint32_t n_keep;
-		const uint32_t rank = block_rank(keep, s_cnt_b, &n_keep);
+		const uint32_t rank = block_rank(keep, s_cnt_b, &n_keep);  // its barrier also orders the queue reads above before the next phase 1 writes
 		if (threadIdx.x == 0) s_base = n_keep ? atomicAdd(p.cnt.paths + bounce + 1, n_keep) : 0u;
 		__syncthreads();
 		if (keep) store_path(p.q, side ^ 1, s_base + rank, s);
