@@ -131,7 +131,7 @@ int compute_grids(b2r_ctx* c) {
 	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<true, false>), kBruteBlock, &c->grid_brute_first))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<false, false>), kBruteBlock, &c->grid_brute))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_closest<false>), kTravBlock, &c->grid_closest))) return rc;
-	if ((rc = occ(reinterpret_cast<const void*>(&k_shade), kBlock, &c->grid_shade))) return rc;
+	if ((rc = occ(reinterpret_cast<const void*>(&k_shade), kBruteBlock, &c->grid_shade))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_shadow<false>), kTravBlock, &c->grid_shadow))) return rc;
 	c->grid_stream = c->sm_count * 8;
 	return B2R_OK;
@@ -169,7 +169,7 @@ int enqueue_batch(b2r_ctx* c, bool profile) {
 		const bool mis = !(c->cfg.flags & B2R_FLAG_NO_MIS);
 		for (uint32_t b = 0; b < mb; b++) {
 			if ((rc = launch(c, KK_CLOSEST, profile, [&] { if (count) k_intersect_closest<true><<<c->grid_closest, kTravBlock, 0, st>>>(p, b); else k_intersect_closest<false><<<c->grid_closest, kTravBlock, 0, st>>>(p, b); }))) return rc;
-			if ((rc = launch(c, KK_SHADE, profile, [&] { k_shade<<<c->grid_shade, kBlock, 0, st>>>(p, b); }))) return rc;
+			if ((rc = launch(c, KK_SHADE, profile, [&] { k_shade<<<c->grid_shade, kBruteBlock, 0, st>>>(p, b); }))) return rc;
 			if (mis && b + 1 < mb) {
 				if ((rc = launch(c, KK_SHADOW, profile, [&] { if (count) k_intersect_shadow<true><<<c->grid_shadow, kTravBlock, 0, st>>>(p, b); else k_intersect_shadow<false><<<c->grid_shadow, kTravBlock, 0, st>>>(p, b); }))) return rc;
 			}

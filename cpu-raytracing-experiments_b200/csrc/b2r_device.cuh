@@ -45,24 +45,6 @@ __device__ __forceinline__ void store_path(const QueueDev& q, int side, uint32_t
 	t[i] = s.tr; t[q.cap + i] = s.tg; t[2u * q.cap + i] = s.tb;
 }
 
-// Append `keep` threads of the CTA to a queue: one atomic per CTA (warp ballots -> shared prefix -> single atomicAdd).
-// Returns the destination index (valid when keep). Must be called by all threads of the CTA.
-__device__ __forceinline__ uint32_t block_append(bool keep, uint32_t* counter, uint32_t* s_warp /*[blockDim/32 + 1]*/) {
-	const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
-	const uint32_t warp = threadIdx.x >> 5, lane = lane_id(), n_warps = blockDim.x >> 5;
-	if (lane == 0) s_warp[warp] = __popc(ballot);
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		uint32_t run = 0;
-		for (uint32_t w = 0; w < n_warps; w++) { const uint32_t c = s_warp[w]; s_warp[w] = run; run += c; }
-		s_warp[n_warps] = run ? atomicAdd(counter, run) : 0u;
-	}
-	__syncthreads();
-	const uint32_t dst = s_warp[n_warps] + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u));
-	__syncthreads();  // s_warp is reused by the next call
-	return dst;
-}
-
 // ---------------------------------------------------------------------------------------------- brute-force pipeline
 // One fused kernel per bounce (BVH.hpp:311-318 as shipped, USEBVH false): every ray is tested against every sphere, then the
 // hits are shaded: closest-hit shader -> light sample + inline any-hit -> emissive -> BRDF sample / roulette -> append.
@@ -340,23 +322,48 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_closest(const Params p
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.cnt.stats + ST_EXT, static_cast<unsigned long long>(n_in));
 	if (COUNT) { stat_add(p.cnt.stats, ST_SPHERE, c_sphere); stat_add(p.cnt.stats, ST_BOX, c_box); }
 }
-// shade the hit records: light sample -> shadow queue, emission, BRDF sample / roulette -> next path queue
-__global__ void __launch_bounds__(kBlock, 2) k_shade(const Params p, const uint32_t bounce) {
-	__shared__ uint32_t s_warp[kBlock / 32 + 1];
+// shade the hit records: light sample -> shadow queue, emission, BRDF sample / roulette -> next path queue.
+// Same CTA structure as the brute-force kernel: hits are collected in a shared-memory queue and shaded a full CTA at a time.
+__global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_shade(const Params p, const uint32_t bounce) {
+	constexpr int kQ = 2 * kBruteBlock;
+	__shared__ uint32_t s_hit_i[kQ]; __shared__ float s_hit_t[kQ]; __shared__ int32_t s_hit_prim[kQ];
+	__shared__ uint32_t s_cnt_a[kBruteWarps], s_cnt_b[kBruteWarps], s_cnt_c[kBruteWarps], s_base, s_sbase;
 	const SceneDev& sc = p.scene;
 	const uint32_t n_in = p.cnt.paths[bounce];
 	const int side = bounce & 1;
 	const bool mis = !(p.frame.flags & B2R_FLAG_NO_MIS);
 	const bool last = bounce + 1 >= p.frame.max_bounces;
 	uint32_t c_hits = 0, c_term = 0, c_drop = 0, c_events = 0;
-	for (uint32_t base = blockIdx.x * kBlock; base < n_in; base += gridDim.x * kBlock) {
-		const uint32_t i = base + threadIdx.x;
-		const bool live = i < n_in;
-		PathState s; float depth = FLT_MAX; int32_t prim = -1;
-		if (live) { s = load_path(p.q, side, i); const float2 h = p.q.H[i]; depth = h.x; prim = __float_as_int(h.y); }
-		bool keep = false, want_shadow = false; ShadowRay sr;
-		const bool hit = live && prim >= 0;
-		if (hit) {
+	uint32_t queued = 0, base = blockIdx.x * kBruteBlock;
+	for (;;) {
+		const bool more = base < n_in;
+		if (more) {
+			const uint32_t i = base + threadIdx.x;
+			const bool live = i < n_in;
+			float depth = FLT_MAX; int32_t prim = -1;
+			if (live) { const float2 h = p.q.H[i]; depth = h.x; prim = __float_as_int(h.y); }
+			const bool is_hit = live && prim >= 0;
+			if (live && !is_hit) {  // miss shader (Renderer.hpp:408-420)
+				c_term++;
+				if (sc.has_ambient) { const PathState sm = load_path(p.q, side, i); rad_add(p.rad, p.frame.npix, sm.pid, shade_sky(sc, sm), f3{0.0f, 0.0f, 0.0f}); c_events++; }
+			}
+			uint32_t n_hits;
+			const uint32_t slot = queued + block_rank(is_hit, s_cnt_a, &n_hits);
+			if (is_hit) { s_hit_i[slot] = i; s_hit_t[slot] = depth; s_hit_prim[slot] = prim; }
+			queued += n_hits;
+			base += gridDim.x * kBruteBlock;
+			__syncthreads();
+		}
+		if (queued < static_cast<uint32_t>(kBruteBlock) && more) continue;
+		if (queued == 0) break;
+		const uint32_t take = min(queued, static_cast<uint32_t>(kBruteBlock));
+		const uint32_t qi = queued - take + threadIdx.x;
+		const bool shade = threadIdx.x < take;
+		queued -= take;
+		bool keep = false, want_shadow = false; ShadowRay sr; PathState s; uint32_t pid = 0;
+		if (shade) {
+			const uint32_t hi = s_hit_i[qi]; const float depth = s_hit_t[qi]; const int32_t prim = s_hit_prim[qi];
+			s = load_path(p.q, side, hi); pid = s.pid;
 			const uint32_t acc = p.batch->acc[s.pid >> 26], seed = pixel_seed(s.pid & kPixMask, p.frame.max_bounces);
 			const Surface sf = shade_surface(sc, s, depth, prim);
 			c_hits++;
@@ -367,19 +374,22 @@ __global__ void __launch_bounds__(kBlock, 2) k_shade(const Params p, const uint3
 				keep = shade_continue(sf, &s, acc, seed, bounce);
 				if (!keep) c_term++;
 			}
-		} else if (live) {
-			c_term++;
-			if (sc.has_ambient) { rad_add(p.rad, p.frame.npix, s.pid, shade_sky(sc, s), f3{0.0f, 0.0f, 0.0f}); c_events++; }
 		}
-		const uint32_t pid = s.pid;  // shade_continue keeps pid
-		const uint32_t sdst = block_append(want_shadow, p.cnt.shadow + bounce, s_warp);
+		uint32_t n_shadow, n_keep;
+		const uint32_t srank = block_rank(want_shadow, s_cnt_b, &n_shadow);  // barrier: queue reads above are done before the next phase 1 writes
+		const uint32_t rank = block_rank(keep, s_cnt_c, &n_keep);
+		if (threadIdx.x == 0) {
+			s_sbase = n_shadow ? atomicAdd(p.cnt.shadow + bounce, n_shadow) : 0u;
+			s_base = n_keep ? atomicAdd(p.cnt.paths + bounce + 1, n_keep) : 0u;
+		}
+		__syncthreads();
 		if (want_shadow) {
-			p.q.SA[sdst] = make_float4(sr.o.x, sr.o.y, sr.o.z, sr.d.x);
-			p.q.SB[sdst] = make_float4(sr.d.y, sr.d.z, sr.tfar, __uint_as_float(pid));
-			p.q.SL[sdst] = sr.L.x; p.q.SL[p.q.cap + sdst] = sr.L.y; p.q.SL[2u * p.q.cap + sdst] = sr.L.z;
+			const uint32_t d = s_sbase + srank;
+			p.q.SA[d] = make_float4(sr.o.x, sr.o.y, sr.o.z, sr.d.x);
+			p.q.SB[d] = make_float4(sr.d.y, sr.d.z, sr.tfar, __uint_as_float(pid));
+			p.q.SL[d] = sr.L.x; p.q.SL[p.q.cap + d] = sr.L.y; p.q.SL[2u * p.q.cap + d] = sr.L.z;
 		}
-		const uint32_t dst = block_append(keep, p.cnt.paths + bounce + 1, s_warp);
-		if (keep) store_path(p.q, side ^ 1, dst, s);
+		if (keep) store_path(p.q, side ^ 1, s_base + rank, s);
 	}
 	stat_add(p.cnt.stats, ST_HITS, c_hits); stat_add(p.cnt.stats, ST_TERM, c_term);
 	stat_add(p.cnt.stats, ST_DROPPED, c_drop); stat_add(p.cnt.stats, ST_EVENTS, c_events);
@@ -425,14 +435,32 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_shadow(const Params p,
 // Fold the batch's per-sample radiance into its median-of-means bucket, in sample order (Renderer.hpp:424-430 adds one
 // sample at a time; bucket = acc % K, :82), and clear RAD for the next batch.
 __global__ void __launch_bounds__(kBlock) k_accumulate(const Params p) {
-	const uint32_t n = 3u * p.frame.npix, npix = p.frame.npix, slots = p.batch->n_slots;
+	__shared__ uint32_t s_order[kMaxSlots];   // slots grouped by bucket, increasing sample index inside a bucket
+	__shared__ uint32_t s_first[kMaxSlots + 1];  // group boundaries per bucket (buckets <= 64)
+	const uint32_t npix4 = p.frame.npix / 4u, n = 3u * npix4, slots = p.batch->n_slots, K = p.frame.buckets;
+	if (threadIdx.x == 0) {
+		uint32_t m = 0;
+		for (uint32_t k = 0; k < K; k++) { s_first[k] = m; for (uint32_t s = 0; s < slots; s++) if (p.batch->acc[s] % K == k) s_order[m++] = s; }
+		s_first[K] = m;
+	}
+	__syncthreads();
+	float4* __restrict__ rad = reinterpret_cast<float4*>(p.rad); float4* __restrict__ acc = reinterpret_cast<float4*>(p.acc);
+	const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		const uint32_t c = i / npix, t = i - c * npix;
-		for (uint32_t s = 0; s < slots; s++) {
-			const uint32_t k = p.batch->acc[s] % p.frame.buckets;
-			float* src = p.rad + (static_cast<size_t>(s) * 3u + c) * npix + t;
-			float* dst = p.acc + (static_cast<size_t>(k) * 3u + c) * npix + t;
-			*dst += *src; *src = 0.0f;
+		const uint32_t c = i / npix4, t4 = i - c * npix4;
+		for (uint32_t k = 0; k < K; k++) {
+			const uint32_t b0 = s_first[k], b1 = s_first[k + 1];
+			if (b0 == b1) continue;
+			float4* dst = acc + (static_cast<size_t>(k) * 3u + c) * npix4 + t4;
+			float4 sum = *dst;
+			for (uint32_t j = b0; j < b1; j += 4u) {  // four independent loads in flight, added in sample order
+				float4 v[4];
+#pragma unroll
+				for (uint32_t u = 0; u < 4u; u++) v[u] = (j + u < b1) ? rad[(static_cast<size_t>(s_order[j + u]) * 3u + c) * npix4 + t4] : zero;
+#pragma unroll
+				for (uint32_t u = 0; u < 4u; u++) if (j + u < b1) { sum.x += v[u].x; sum.y += v[u].y; sum.z += v[u].z; sum.w += v[u].w; rad[(static_cast<size_t>(s_order[j + u]) * 3u + c) * npix4 + t4] = zero; }
+			}
+			*dst = sum;
 		}
 	}
 }

@@ -221,46 +221,42 @@ struct TravBase {
 		node = 0u; sp = 0;
 	}
 };
+// node access: STAGED = the node's eight float4 were copied to shared memory by the warp (kernels); otherwise read-only LDG
+template <bool STAGED> B2R_HD float4 node_f4(const float4* n, int i) { return STAGED ? n[i] : ldg4(n + i); }
+
 // Closest hit == brute force over all spheres (BVH.hpp:311-318): a candidate replaces the best when d < best, or d == best with
 // a lower sphere index (the brute-force loop keeps the first of equal distances, BVH.hpp:265); a node is culled only when its
-// entry distance is beyond the best.
+// entry distance is beyond the best. Inner slots are slab-tested in one uniform pass; leaf slots are only marked there and
+// their spheres tested in a second, compact loop, so a few lanes with leaves do not drag the whole warp through four
+// sphere tests.
 struct TravClosest : TravBase {
 	float best; int32_t prim;
 	uint2 stack[kTraversalStack];
 	B2R_HD void begin(const Ray& r) { arm(r); best = FLT_MAX; prim = -1; }
-	template <bool COUNT>
-	B2R_HD bool step(const WideNode* __restrict__ wide, uint32_t* c_sphere, uint32_t* c_box) {
-		const float4* n = reinterpret_cast<const float4*>(wide + node);
-		float4 a[4], b[4];
-#pragma unroll
-		for (int k = 0; k < 4; k++) { a[k] = ldg4(n + 2 * k); b[k] = ldg4(n + 2 * k + 1); }
-		return visit<COUNT>(a, b, c_sphere, c_box);
-	}
-	// same, with the node's eight float4 already staged at `n` (shared memory in the kernels)
-	template <bool COUNT>
-	B2R_HD bool step_staged(const float4* n, uint32_t* c_sphere, uint32_t* c_box) {
-		float4 a[4], b[4];
-#pragma unroll
-		for (int k = 0; k < 4; k++) { a[k] = n[2 * k]; b[k] = n[2 * k + 1]; }
-		return visit<COUNT>(a, b, c_sphere, c_box);
-	}
-	template <bool COUNT>
-	B2R_HD bool visit(const float4 (&a)[4], const float4 (&b)[4], uint32_t* c_sphere, uint32_t* c_box) {
-		uint32_t key[4], link[4];
+	template <bool COUNT, bool STAGED>
+	B2R_HD bool visit(const float4* n, uint32_t* c_sphere, uint32_t* c_box) {
+		uint32_t key[4], link[4]; uint32_t leaves = 0u;
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
-			const int32_t l = as_int(b[k].z);
-			key[k] = 0xffffffffu; link[k] = 0u;
-			if (l >= 0) {
-				float tn; bool h; slab(a[k], b[k], ix, iy, iz, nx, ny, nz, best, &tn, &h);
-				if (COUNT) (*c_box)++;
-				if (h) { key[k] = bits(tn); link[k] = static_cast<uint32_t>(l); }
-			} else if (l != kEmptyLink) {
-				float d; if (COUNT) (*c_sphere)++;
-				if (sphere_hit_closest(a[k].x, a[k].y, a[k].z, a[k].w, ox, oy, oz, dx, dy, dz, &d)) {
-					const int32_t id = ~l;
-					if (d < best || (d == best && id < prim)) { best = d; prim = id; }
-				}
+			const float4 a = node_f4<STAGED>(n, 2 * k), b = node_f4<STAGED>(n, 2 * k + 1);
+			const int32_t l = as_int(b.z);
+			float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, best, &tn, &h);
+			const bool inner = l >= 0;
+			if (COUNT && inner) (*c_box)++;
+			key[k] = (inner && h) ? bits(tn) : 0xffffffffu; link[k] = static_cast<uint32_t>(l);
+			leaves |= (!inner && l != kEmptyLink) ? (1u << k) : 0u;
+		}
+		while (leaves) {
+#if defined(__CUDA_ARCH__)
+			const int k = __ffs(static_cast<int>(leaves)) - 1;
+#else
+			const int k = __builtin_ctz(leaves);
+#endif
+			leaves &= leaves - 1u;
+			const float4 sp = node_f4<STAGED>(n, 2 * k); const int32_t id = ~as_int(node_f4<STAGED>(n, 2 * k + 1).z);
+			float d; if (COUNT) (*c_sphere)++;
+			if (sphere_hit_closest(sp.x, sp.y, sp.z, sp.w, ox, oy, oz, dx, dy, dz, &d)) {
+				if (d < best || (d == best && id < prim)) { best = d; prim = id; }
 			}
 		}
 		// sort the (entry distance, link) pairs; non-negative floats order like their bit patterns, misses (0xffffffff) last
@@ -277,47 +273,49 @@ struct TravClosest : TravBase {
 		}
 		return false;
 	}
+	template <bool COUNT>
+	B2R_HD bool step(const WideNode* __restrict__ wide, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, false>(reinterpret_cast<const float4*>(wide + node), c_sphere, c_box); }
+	template <bool COUNT>
+	B2R_HD bool step_staged(const float4* n, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, true>(n, c_sphere, c_box); }
 };
 // Any hit along [0, tfar) — Traverse_shadow semantics (BVH.hpp:290-305): an order-independent boolean.
 struct TravAny : TravBase {
 	float tfar; bool occluded;
 	uint32_t stack[kTraversalStack];
 	B2R_HD void begin(const Ray& r, float limit) { arm(r); tfar = limit; occluded = false; }
-	template <bool COUNT>
-	B2R_HD bool step(const WideNode* __restrict__ wide, uint32_t* c_sphere, uint32_t* c_box) {
-		const float4* n = reinterpret_cast<const float4*>(wide + node);
-		float4 a[4], b[4];
-#pragma unroll
-		for (int k = 0; k < 4; k++) { a[k] = ldg4(n + 2 * k); b[k] = ldg4(n + 2 * k + 1); }
-		return visit<COUNT>(a, b, c_sphere, c_box);
-	}
-	template <bool COUNT>
-	B2R_HD bool step_staged(const float4* n, uint32_t* c_sphere, uint32_t* c_box) {
-		float4 a[4], b[4];
-#pragma unroll
-		for (int k = 0; k < 4; k++) { a[k] = n[2 * k]; b[k] = n[2 * k + 1]; }
-		return visit<COUNT>(a, b, c_sphere, c_box);
-	}
-	template <bool COUNT>
-	B2R_HD bool visit(const float4 (&a)[4], const float4 (&b)[4], uint32_t* c_sphere, uint32_t* c_box) {
-		uint32_t next = 0xffffffffu;
+	template <bool COUNT, bool STAGED>
+	B2R_HD bool visit(const float4* n, uint32_t* c_sphere, uint32_t* c_box) {
+		uint32_t next = 0xffffffffu, leaves = 0u;
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
-			const int32_t l = as_int(b[k].z);
-			if (l >= 0) {
-				float tn; bool h; slab(a[k], b[k], ix, iy, iz, nx, ny, nz, tfar, &tn, &h);
-				if (COUNT) (*c_box)++;
-				if (h) { if (next != 0xffffffffu) stack[sp++] = next; next = static_cast<uint32_t>(l); }
-			} else if (l != kEmptyLink) {
-				if (COUNT) (*c_sphere)++;
-				if (sphere_hit_any(a[k].x, a[k].y, a[k].z, a[k].w, ox, oy, oz, dx, dy, dz, tfar)) { occluded = true; return false; }
-			}
+			const float4 a = node_f4<STAGED>(n, 2 * k), b = node_f4<STAGED>(n, 2 * k + 1);
+			const int32_t l = as_int(b.z);
+			float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, tfar, &tn, &h);
+			const bool inner = l >= 0;
+			if (COUNT && inner) (*c_box)++;
+			if (inner && h) { if (next != 0xffffffffu) stack[sp++] = next; next = static_cast<uint32_t>(l); }
+			leaves |= (!inner && l != kEmptyLink) ? (1u << k) : 0u;
+		}
+		while (leaves) {
+#if defined(__CUDA_ARCH__)
+			const int k = __ffs(static_cast<int>(leaves)) - 1;
+#else
+			const int k = __builtin_ctz(leaves);
+#endif
+			leaves &= leaves - 1u;
+			const float4 sp = node_f4<STAGED>(n, 2 * k);
+			if (COUNT) (*c_sphere)++;
+			if (sphere_hit_any(sp.x, sp.y, sp.z, sp.w, ox, oy, oz, dx, dy, dz, tfar)) { occluded = true; return false; }
 		}
 		if (next != 0xffffffffu) { node = next; return true; }
 		if (sp == 0) return false;
 		node = stack[--sp];
 		return true;
 	}
+	template <bool COUNT>
+	B2R_HD bool step(const WideNode* __restrict__ wide, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, false>(reinterpret_cast<const float4*>(wide + node), c_sphere, c_box); }
+	template <bool COUNT>
+	B2R_HD bool step_staged(const float4* n, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, true>(n, c_sphere, c_box); }
 };
 // whole-ray wrappers (trace taps, host check)
 template <bool COUNT>
