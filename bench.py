@@ -128,20 +128,35 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
-def cpu_oracle_run(wl, scene, samples, fast=True):
+# bounded CPU samples: full frames for the 9-sphere scene; a fixed random subset of 16x16 tiles for the BVH scenes (every tile is an
+# independent unit of the reference's parallel_for, Renderer.hpp:75-84), sized for roughly 5-20 s of host time
+CPU_TILE_SAMPLE = {"c3": 1024, "c4": 384}
+
+
+def cpu_oracle_run(wl, scene, samples, fast=True, workload_name=None):
     """Times the oracle port on all host threads: `samples` x Accumulate at the workload's size (+ Render when a round completes)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
     import oracle_py
     threads = os.cpu_count() or 1
-    o = oracle_py.Oracle(wl["w"], wl["h"], max_bounces=wl["mb"], K=wl["K"], fast=fast)
+    bvh = wl["scene"] != "default"
+    o = oracle_py.Oracle(wl["w"], wl["h"], max_bounces=wl["mb"], K=wl["K"], flags=oracle_py.ORC_BVH if bvh else 0, fast=fast)
     o.set_scene(scene)
-    if wl["scene"] != "default":
-        o.close(); o = oracle_py.Oracle(wl["w"], wl["h"], max_bounces=wl["mb"], K=wl["K"], flags=oracle_py.ORC_BVH, fast=fast); o.set_scene(scene)
     o.reset_counters()
-    t0 = time.perf_counter(); o.accumulate(samples, threads=threads); o.render(); dt = time.perf_counter() - t0
+    n_tiles_all = (wl["w"] // 16) * (wl["h"] // 16)
+    n_tiles = min(n_tiles_all, CPU_TILE_SAMPLE.get(workload_name, n_tiles_all)) if bvh else n_tiles_all
+    t0 = time.perf_counter()
+    if n_tiles < n_tiles_all:
+        tiles = np.random.RandomState(1).choice(n_tiles_all, n_tiles, replace=False).astype(np.uint32)
+        o.accumulate_tiles(tiles, samples, threads=threads)
+    else:
+        o.accumulate(samples, threads=threads); o.render()
+    dt = time.perf_counter() - t0
     c = o.counters(); rays = c["extension_rays"] + c["shadow_rays"]
     o.close()
-    return dict(seconds=dt, rays=rays, paths=wl["w"] * wl["h"] * samples, threads=threads, mode="stream-BVH (BVH.hpp:320-358 restated)" if wl["scene"] != "default" else "brute force (as shipped, USEBVH false)")
+    what = f"{samples} spp of {n_tiles} of the {n_tiles_all} 16x16 tiles of the {wl['w']}x{wl['h']} frame" if n_tiles < n_tiles_all else f"{samples} spp of the {wl['w']}x{wl['h']} frame"
+    return dict(seconds=dt, rays=rays, paths=n_tiles * 256 * samples, threads=threads, what=what,
+                mode="stream-BVH (BVH.hpp:320-358 restated)" if bvh else "brute force (as shipped, USEBVH false)")
 
 
 def run_reference(args, wl, rank):
@@ -151,13 +166,13 @@ def run_reference(args, wl, rank):
     scene = make_scene(wl["scene"])
     per_step = 4 if wl["scene"] == "default" else 1  # a few spp of the workload's frame per step: a bounded sample (~0.1-20 s on the host cores)
     for _ in range(args.warmup):
-        cpu_oracle_run(wl, scene, per_step)
+        cpu_oracle_run(wl, scene, per_step, workload_name=args.workload)
     secs, rays, paths = 0.0, 0, 0
     threads = mode = None
     for _ in range(args.steps):
-        r = cpu_oracle_run(wl, scene, per_step); secs += r["seconds"]; rays += r["rays"]; paths += r["paths"]; threads, mode = r["threads"], r["mode"]
+        r = cpu_oracle_run(wl, scene, per_step, workload_name=args.workload); secs += r["seconds"]; rays += r["rays"]; paths += r["paths"]; threads, mode = r["threads"], r["mode"]; what = r["what"]
     v = rays / secs / 1e6
-    sample = f"{per_step} spp of the {wl['w']}x{wl['h']} frame per step ({paths // args.steps} paths), {args.steps} steps; oracle port -O3 -march=native, {mode}"
+    sample = f"{what} per step ({paths // args.steps} paths), {args.steps} steps; oracle port -O3 -march=native, {mode}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -334,9 +349,9 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_cpu = 8 if wl["scene"] == "default" else 1
-        c = cpu_oracle_run(wl, scene, n_cpu)
+        c = cpu_oracle_run(wl, scene, n_cpu, workload_name=args.workload)
         cpu = {"value": c["rays"] / c["seconds"] / 1e6, "unit": UNIT, "cores": c["threads"], "kind": "port",
-               "sample": f"{n_cpu} spp of the {wl['w']}x{wl['h']} frame ({c['paths']} paths, {c['rays']} rays) in {c['seconds']:.2f} s; oracle port -O3 -march=native, {c['mode']}",
+               "sample": f"{c['what']} ({c['paths']} paths, {c['rays']} rays) in {c['seconds']:.2f} s; oracle port -O3 -march=native, {c['mode']}",
                "paths_per_s": c["paths"] / c["seconds"]}
 
     if rank == 0:
