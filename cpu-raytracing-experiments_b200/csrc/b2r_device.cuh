@@ -7,7 +7,7 @@
 //     pixel's tile-order index (tile*256 + ID) and slot the sample-in-flight index inside the batch.
 //   radiance RAD[(slot*3 + c)*npix + t]: a path's running radiance lives at its pixel (one path per pixel per sample)
 //     and is touched only when a contribution arrives (unoccluded light sample, emissive hit, sky).
-//   hit queue H[i] = {tfar, as_float(prim)} and shadow queue SA/SB/SL: BVH pipeline only.
+//   hit queue H[i] = {tfar, as_float(prim)} and shadow queue SA/SB/SL/SE (ray, light-sample radiance, pending emission): BVH pipeline only.
 //   buckets ACC[(k*3 + c)*npix + t]: running sums per median-of-means bucket (AccumulationTile, Renderer.hpp:43-46).
 // All kernels are persistent (grid = SM count x resident CTAs, looping over a device-side count), so a whole batch —
 // max_bounces rounds — is enqueued, or replayed as one CUDA graph, without host synchronisation.
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_shade(con
 		const uint32_t qi = queued - take + threadIdx.x;
 		const bool shade = threadIdx.x < take;
 		queued -= take;
-		bool keep = false, want_shadow = false; ShadowRay sr; PathState s; uint32_t pid = 0;
+		bool keep = false, want_shadow = false; ShadowRay sr; PathState s; uint32_t pid = 0; f3 emit{0.0f, 0.0f, 0.0f};
 		if (shade) {
 			const uint32_t hi = s_hit_i[qi]; const float depth = s_hit_t[qi]; const int32_t prim = s_hit_prim[qi];
 			s = load_path(p.q, side, hi); pid = s.pid;
@@ -370,7 +370,12 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_shade(con
 			if (last) { rad_zero(p.rad, p.frame.npix, s.pid); c_drop++; }  // Q11
 			else {
 				if (mis) want_shadow = shade_light_sample(sc, sf, s, prim, acc, seed, bounce, &sr);
-				if (sf.emissive) { rad_add(p.rad, p.frame.npix, s.pid, shade_emission(sc, sf, s, depth, bounce, mis), f3{0.0f, 0.0f, 0.0f}); c_events++; }
+				if (sf.emissive) {
+					// the reference adds the light sample first, then the emission (Renderer.hpp:304-353): when a shadow ray is
+					// pending the emission travels with it and k_intersect_shadow adds both in that order
+					emit = shade_emission(sc, sf, s, depth, bounce, mis);
+					if (!want_shadow) { rad_add(p.rad, p.frame.npix, s.pid, emit, f3{0.0f, 0.0f, 0.0f}); c_events++; }
+				}
 				keep = shade_continue(sf, &s, acc, seed, bounce);
 				if (!keep) c_term++;
 			}
@@ -388,6 +393,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_shade(con
 			p.q.SA[d] = make_float4(sr.o.x, sr.o.y, sr.o.z, sr.d.x);
 			p.q.SB[d] = make_float4(sr.d.y, sr.d.z, sr.tfar, __uint_as_float(pid));
 			p.q.SL[d] = sr.L.x; p.q.SL[p.q.cap + d] = sr.L.y; p.q.SL[2u * p.q.cap + d] = sr.L.z;
+			p.q.SE[d] = emit.x; p.q.SE[p.q.cap + d] = emit.y; p.q.SE[2u * p.q.cap + d] = emit.z;
 		}
 		if (keep) store_path(p.q, side ^ 1, s_base + rank, s);
 	}
@@ -417,9 +423,11 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_shadow(const Params p,
 		do {
 			warp_stage_nodes(wide, rows, t.node, live);
 			if (active && !t.template step_staged<COUNT>(rows + lane_id() * kNodeRowF4, &c_sphere, &c_box)) {
-				if (!t.occluded) {
-					const f3 L{p.q.SL[idx], p.q.SL[p.q.cap + idx], p.q.SL[2u * p.q.cap + idx]};
-					rad_add(p.rad, p.frame.npix, pid, L, f3{0.0f, 0.0f, 0.0f}); c_events++;
+				const f3 E{p.q.SE[idx], p.q.SE[p.q.cap + idx], p.q.SE[2u * p.q.cap + idx]};  // emission of the same hit (usually 0)
+				const bool has_e = E.x != 0.0f || E.y != 0.0f || E.z != 0.0f;
+				if (!t.occluded || has_e) {
+					const f3 L = t.occluded ? f3{0.0f, 0.0f, 0.0f} : f3{p.q.SL[idx], p.q.SL[p.q.cap + idx], p.q.SL[2u * p.q.cap + idx]};
+					rad_add(p.rad, p.frame.npix, pid, L, E); c_events++;
 				}
 				active = false;
 			}

@@ -231,3 +231,31 @@ def test_cpp_mirror_frame_loop(tmp_path):
     r = b2r.Renderer(scenes.default_scene(), 256, 144, max_bounces=16, buckets=5); r.Accumulate(5); assert r.Render()
     assert abs(float(m.group(3)) - float(r.framebuffer[..., :3].mean(dtype=np.float64))) < 1e-5
     r.close()
+
+
+@pytest.mark.parametrize("n,K,mb,flags", [(1, 1, 1, 0), (2, 3, 2, 0), (33, 5, 4, 0), (33, 64, 3, b2r.FLAG_FORCE_BRUTE), (1500, 7, 5, b2r.FLAG_FORCE_BRUTE), (9, 8, 40, 0)])
+def test_edge_configurations(n, K, mb, flags):
+    """Smallest scenes (single sphere = single-leaf tree), the 32/33-sphere brute/BVH switch, multi-tile brute force (1500 > 1024
+    spheres per shared-memory tile), extreme bucket counts (1, 64) and bounce limits (1, 40), ragged batches (n_samples not a
+    multiple of the batch width): bucket sums bit-exact vs the oracle."""
+    sc = scenes.default_scene() if n == 9 else scenes.random_scene(n, light_every=max(1, n // 3))
+    w, h = 96, 64
+    samples = K + 3 if K < 20 else K
+    r = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=K, flags=flags, samples_in_flight=5); r.Accumulate(samples)
+    o = oracle_for(sc, w, h, mb, K); o.accumulate(samples)
+    g, ref = r.buckets_host(), o.buckets()
+    frac = divergent_fraction(g, ref)
+    assert frac == 0.0 and g.tobytes() == ref.tobytes(), (n, K, mb, frac)
+    r.accumulations = (samples // K) * K
+    if r.accumulations:
+        o.set_accumulations(r.accumulations)
+        assert r.Render() and r.framebuffer.tobytes() == o.render()[1].tobytes()
+    r.close()
+
+
+def test_no_mis_variant_matches_oracle_definition():
+    sc = scenes.default_scene()
+    r = b2r.Renderer(sc, 160, 96, max_bounces=8, buckets=1, flags=b2r.FLAG_NO_MIS); r.Accumulate(2)
+    o = oracle_for(sc, 160, 96, 8, 1, flags=oracle_py.ORC_NO_MIS); o.accumulate(2)
+    assert r.buckets_host().tobytes() == o.buckets().tobytes() and r.counters()["shadow_rays"] == 0
+    r.close()
