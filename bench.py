@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true"); ap.add_argument("--no-profile-pass", action="store_true")
     ap.add_argument("--samples-in-flight", type=int, default=0, help="0 = library default (auto)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel (for ncu); never used for a reported number")
+    ap.add_argument("--combine", default="p2p", choices=["p2p", "nccl"], help="multi-GPU frame combine: resolve kernel reads peer buckets over NVLink (p2p) or NCCL all-reduce then resolve")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     wl = WORKLOADS[args.workload]
@@ -224,6 +225,9 @@ def main():
     # weak scaling: every rank renders `spp` samples of its own buckets per step => world*spp sample indices per step
     step_samples = spp * world
     local_buckets = b2r_dist.buckets_tensor(r, dev)
+    use_p2p = world > 1 and args.combine == "p2p"
+    if use_p2p:
+        b2r_dist.open_peers(r)
 
     dbg = bool(os.environ.get("B2R_BENCH_DEBUG"))
 
@@ -237,7 +241,13 @@ def main():
         if dbg:
             r.sync(); print(f"[dbg] upload {t1 - t0:.4f}s accumulate {time.perf_counter() - t1:.4f}s", file=sys.stderr)
         t2 = time.perf_counter()
-        if world > 1:
+        if use_p2p:
+            # fused combine: rank 0's resolve kernel pulls every bucket from its owner over NVLink. The two barriers order it after
+            # every rank's last bounce and before any rank's next ResetAccumulator.
+            r.sync(); dist.barrier()
+            ok = r.RenderPeers(to_host=to_host_fb is not None, out=to_host_fb) if rank == 0 else True
+            dist.barrier()
+        elif world > 1:
             combined = b2r_dist.combine_buckets(local_buckets)  # the one collective: NCCL all-reduce of the bucket sums
             ok = r.Render(to_host=to_host_fb is not None and rank == 0, out=to_host_fb, dev_buckets=combined.data_ptr())
         else:
@@ -359,7 +369,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "samples_per_step_per_gpu": spp, "samples_in_flight": args.samples_in_flight,
-                       "partition": f"sample buckets b%{world}==rank, scene+BVH replicated, one NCCL all-reduce of bucket sums per frame" if world > 1 else "single GPU",
+                       "partition": (f"sample buckets b%{world}==rank, scene+BVH replicated; " + ("resolve kernel on rank 0 reads peer bucket arrays over NVLink (CUDA IPC), 2 barriers per frame" if use_p2p else "one NCCL all-reduce of bucket sums per frame")) if world > 1 else "single GPU",
                        "l2": "no flush needed: each step streams >1 GB of path-queue records (>> 126 MB L2); RNG-unique samples every step"},
             "paths_per_s": paths_total / secs, "rays_per_step": rays_total / args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,

@@ -46,3 +46,20 @@ def combine_buckets(local_buckets, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
     return out
+
+
+def open_peers(renderer, group=None):
+    """Fused alternative to combine_buckets: exchange CUDA IPC handles of the bucket arrays once (all_gather_object) and map the
+    peers' arrays, so Renderer.RenderPeers() pulls each bucket from its owner over NVLink inside the resolve kernel. Per frame the
+    only cross-rank operation left is a barrier that orders the resolve after every rank's last bounce."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    handles = [None] * world
+    mine = renderer.ipc_export_buckets()
+    if world > 1:
+        dist.all_gather_object(handles, mine, group=group)
+    else:
+        handles = [mine]
+    renderer.ipc_open_peers(handles, rank)
+    return world

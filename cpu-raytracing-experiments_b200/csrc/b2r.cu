@@ -72,6 +72,8 @@ struct b2r_ctx {
 	struct Timed { int kind; cudaEvent_t a, b; };
 	std::vector<Timed> timed;
 	double kernel_ms[8] = {0}; uint64_t kernel_launches[8] = {0};
+	// peers' bucket arrays mapped through CUDA IPC (multi-GPU fused resolve)
+	std::vector<void*> peer_acc; uint32_t my_rank = 0;
 };
 
 namespace {
@@ -262,6 +264,7 @@ void b2r_destroy(b2r_ctx* c) {
 	if (!c) return;
 	cudaSetDevice(c->cfg.device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
+	for (size_t r = 0; r < c->peer_acc.size(); r++) if (c->peer_acc[r] && r != c->my_rank) cudaIpcCloseMemHandle(c->peer_acc[r]);
 	drop_graph(c);
 	for (auto& t : c->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
 	dev_free(&c->d_prims); dev_free(&c->d_mat_albedo); dev_free(&c->d_mat_emission); dev_free(&c->d_light_sphere); dev_free(&c->d_light_emit);
@@ -410,21 +413,65 @@ int b2r_accumulate(b2r_ctx* c, uint32_t n_samples) {
 	return B2R_OK;
 }
 
-int b2r_resolve(b2r_ctx* c, float* rgba_out_host, int tonemap) { return b2r_resolve_from(c, nullptr, rgba_out_host, tonemap); }
-
-int b2r_resolve_from(b2r_ctx* c, const void* dev_buckets, float* rgba_out_host, int tonemap) {
-	if (!c) return fail(B2R_ERR_ARG, "null context");
+static int resolve_with(b2r_ctx* c, const BucketPtrs& bp, float* rgba_out_host, int tonemap) {
 	int rc = ensure_device(c); if (rc) return rc;
 	if (c->accumulations == 0 || c->accumulations % c->cfg.buckets) return B2R_ERR_NOT_READY;  // Renderer.hpp:437
 	const float scale = c->params.frame.cam.exposure / static_cast<float>(c->accumulations / c->cfg.buckets);  // :439
 	const bool profile = (c->cfg.flags & B2R_FLAG_NO_GRAPH) != 0;
-	Params rp = c->params;
-	if (dev_buckets) rp.acc = const_cast<float*>(static_cast<const float*>(dev_buckets));
-	rc = launch(c, KK_RESOLVE, profile, [&] { k_resolve<<<c->grid_stream, kBlock, 0, c->stream>>>(rp, c->d_fb, scale, tonemap); });
+	rc = launch(c, KK_RESOLVE, profile, [&] { k_resolve<<<c->grid_stream, kBlock, 0, c->stream>>>(c->params.frame, bp, c->d_fb, scale, tonemap); });
 	if (rc) return rc;
 	if (rgba_out_host) CU(cudaMemcpyAsync(rgba_out_host, c->d_fb, static_cast<size_t>(c->params.frame.npix) * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
 	return collect_timings(c);
+}
+
+int b2r_resolve(b2r_ctx* c, float* rgba_out_host, int tonemap) { return b2r_resolve_from(c, nullptr, rgba_out_host, tonemap); }
+
+int b2r_resolve_from(b2r_ctx* c, const void* dev_buckets, float* rgba_out_host, int tonemap) {
+	if (!c) return fail(B2R_ERR_ARG, "null context");
+	const float* base = dev_buckets ? static_cast<const float*>(dev_buckets) : c->d_acc;
+	BucketPtrs bp{};
+	for (uint32_t k = 0; k < c->cfg.buckets; k++) bp.k[k] = base + static_cast<size_t>(k) * 3 * c->params.frame.npix;
+	return resolve_with(c, bp, rgba_out_host, tonemap);
+}
+
+int b2r_ipc_export_buckets(b2r_ctx* c, unsigned char handle_out[64]) {
+	if (!c || !handle_out) return fail(B2R_ERR_ARG, "null argument");
+	int rc = ensure_device(c); if (rc) return rc;
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	cudaIpcMemHandle_t h; CU(cudaIpcGetMemHandle(&h, c->d_acc));
+	std::memcpy(handle_out, &h, 64);
+	return B2R_OK;
+}
+int b2r_ipc_close(b2r_ctx* c) {
+	if (!c) return fail(B2R_ERR_ARG, "null context");
+	int rc = ensure_device(c); if (rc) return rc;
+	CU(cudaStreamSynchronize(c->stream));
+	for (size_t r = 0; r < c->peer_acc.size(); r++) if (c->peer_acc[r] && r != c->my_rank) cudaIpcCloseMemHandle(c->peer_acc[r]);
+	c->peer_acc.clear();
+	return B2R_OK;
+}
+int b2r_ipc_open_peers(b2r_ctx* c, const unsigned char* peer_handles, uint32_t n_peers, uint32_t my_rank) {
+	if (!c || !peer_handles || n_peers == 0 || my_rank >= n_peers) return fail(B2R_ERR_ARG, "bad peer list");
+	if (c->cfg.buckets % n_peers) return fail(B2R_ERR_ARG, "bucket count must be a multiple of the number of peers");
+	int rc = b2r_ipc_close(c); if (rc) return rc;
+	c->peer_acc.assign(n_peers, nullptr); c->my_rank = my_rank;
+	for (uint32_t r = 0; r < n_peers; r++) {
+		if (r == my_rank) { c->peer_acc[r] = c->d_acc; continue; }
+		cudaIpcMemHandle_t h; std::memcpy(&h, peer_handles + 64 * static_cast<size_t>(r), 64);
+		cudaError_t e = cudaIpcOpenMemHandle(&c->peer_acc[r], h, cudaIpcMemLazyEnablePeerAccess);
+		if (e != cudaSuccess) { c->peer_acc[r] = nullptr; b2r_ipc_close(c); return fail(B2R_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
+	}
+	return B2R_OK;
+}
+int b2r_resolve_peers(b2r_ctx* c, float* rgba_out_host, int tonemap) {
+	if (!c) return fail(B2R_ERR_ARG, "null context");
+	if (c->peer_acc.empty()) return fail(B2R_ERR_STATE, "b2r_ipc_open_peers first");
+	const uint32_t G = static_cast<uint32_t>(c->peer_acc.size());
+	BucketPtrs bp{};
+	for (uint32_t k = 0; k < c->cfg.buckets; k++)  // bucket k lives on rank k % G (b2r_config.bucket_first/stride)
+		bp.k[k] = static_cast<const float*>(c->peer_acc[k % G]) + static_cast<size_t>(k) * 3 * c->params.frame.npix;
+	return resolve_with(c, bp, rgba_out_host, tonemap);
 }
 
 int b2r_get_accumulations(b2r_ctx* c, uint32_t* out) { if (!c || !out) return fail(B2R_ERR_ARG, "null argument"); *out = c->accumulations; return B2R_OK; }

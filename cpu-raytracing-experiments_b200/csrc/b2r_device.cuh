@@ -474,28 +474,32 @@ __global__ void __launch_bounds__(kBlock) k_accumulate(const Params p) {
 }
 // median of K bucket sums. K == 5 is the reference's network (Sampling.hpp:13-21); other K are this repo's definition:
 // odd K -> middle order statistic, even K -> mean of the two middle ones.
-__device__ __forceinline__ float median_buckets(const float* acc, uint32_t K, uint32_t stride, uint32_t t) {
-	if (K == 5) return median_of_5(acc[t], acc[stride + t], acc[2u * stride + t], acc[3u * stride + t], acc[4u * stride + t]);
-	if (K == 3) return median_of_3(acc[t], acc[stride + t], acc[2u * stride + t]);
-	if (K == 1) return acc[t];
+// where each bucket's [3][npix] sums live: this GPU's accumulator, or — multi-GPU — the owner's HBM mapped over NVLink
+struct BucketPtrs { const float* k[64]; };
+__device__ __forceinline__ float median_buckets_at(const BucketPtrs& bp, uint32_t K, uint32_t off) {
+	if (K == 5) return median_of_5(bp.k[0][off], bp.k[1][off], bp.k[2][off], bp.k[3][off], bp.k[4][off]);
+	if (K == 3) return median_of_3(bp.k[0][off], bp.k[1][off], bp.k[2][off]);
+	if (K == 1) return bp.k[0][off];
 	float v[64];
 	for (uint32_t k = 0; k < K; k++) {  // insertion sort
-		float x = acc[static_cast<size_t>(k) * stride + t]; int j = static_cast<int>(k) - 1;
+		float x = bp.k[k][off]; int j = static_cast<int>(k) - 1;
 		while (j >= 0 && v[j] > x) { v[j + 1] = v[j]; j--; }
 		v[j + 1] = x;
 	}
 	return (K & 1u) ? v[K / 2u] : (v[K / 2u - 1u] + v[K / 2u]) * 0.5f;
 }
-// Renderer::Render, Renderer.hpp:436-478: one thread per pixel (tile order in, raster RGBA out)
-__global__ void __launch_bounds__(kBlock) k_resolve(const Params p, float4* __restrict__ fb, const float scale, const int tonemap) {
-	const uint32_t npix = p.frame.npix, K = p.frame.buckets;
+// Renderer::Render, Renderer.hpp:436-478: one thread per pixel (tile order in, raster RGBA out). With peer pointers this one
+// kernel is the whole multi-GPU combine: the median network pulls each bucket from its owner over NVLink (coalesced 128-byte
+// peer loads) — no all-reduce, no staging copy.
+__global__ void __launch_bounds__(kBlock) k_resolve(const FrameDev frame, const __grid_constant__ BucketPtrs bp, float4* __restrict__ fb, const float scale, const int tonemap) {
+	const uint32_t npix = frame.npix, K = frame.buckets;
 	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < npix; t += gridDim.x * blockDim.x) {
-		float r = scale * median_buckets(p.acc, K, 3u * npix, t);
-		float g = scale * median_buckets(p.acc + npix, K, 3u * npix, t);
-		float b = scale * median_buckets(p.acc + 2u * npix, K, 3u * npix, t);
+		float r = scale * median_buckets_at(bp, K, t);
+		float g = scale * median_buckets_at(bp, K, npix + t);
+		float b = scale * median_buckets_at(bp, K, 2u * npix + t);
 		if (tonemap) aces_tonemap(&r, &g, &b);
-		int32_t x, y; pixel_xy(t, p.frame.h_tiles, &x, &y);
-		fb[static_cast<size_t>(y) * p.frame.width + x] = make_float4(r, g, b, 1.0f);
+		int32_t x, y; pixel_xy(t, frame.h_tiles, &x, &y);
+		fb[static_cast<size_t>(y) * frame.width + x] = make_float4(r, g, b, 1.0f);
 	}
 }
 

@@ -134,6 +134,15 @@ int  b2r_read_buckets(b2r_ctx* ctx, float* out_host);               /* [buckets]
 int  b2r_write_buckets(b2r_ctx* ctx, const float* in_host);         /* checkpoint restore */
 int  b2r_device_buckets(b2r_ctx* ctx, void** dev_ptr, size_t* bytes); /* device address of the same array (NCCL / P2P combine) */
 int  b2r_device_framebuffer(b2r_ctx* ctx, void** dev_ptr, size_t* bytes);
+/* Multi-GPU resolve over peer memory (NVLink P2P), the fused alternative to combine-then-resolve: every process exports its
+ * bucket array as a 64-byte CUDA IPC handle, exchanges the handles (any transport), opens its peers' arrays, and the resolve
+ * kernel reads bucket k straight from its owner's HBM (owner = k % n_peers, b2r_config.bucket_*), so no bucket is copied or
+ * reduced first. Callers must order the resolve after every peer's b2r_sync (one barrier). peer_handles: n_peers x 64 bytes in
+ * rank order (the entry of `my_rank` is ignored). b2r_ipc_close drops the mappings. */
+int  b2r_ipc_export_buckets(b2r_ctx* ctx, unsigned char handle_out[64]);
+int  b2r_ipc_open_peers(b2r_ctx* ctx, const unsigned char* peer_handles, uint32_t n_peers, uint32_t my_rank);
+int  b2r_ipc_close(b2r_ctx* ctx);
+int  b2r_resolve_peers(b2r_ctx* ctx, float* rgba_out_host, int tonemap);
 /* counters since the last reset: [0] extension rays, [1] shadow rays, [2] shaded hits, [3] terminated paths,
  * [4] dropped at max_bounces (Q11), [5] sphere tests, [6] box tests (5,6 only with B2R_FLAG_COUNT_TESTS), [7] kernel launches,
  * [8] radiance contributions written (light samples, emissive hits, sky), [9] reserved */
