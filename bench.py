@@ -33,6 +33,8 @@ WORKLOADS = {
     "c2": dict(desc="C2 default 9-sphere scene 1920x1080 (internal 1920x1088) 64spp median-of-means K=8 max_bounces=16 MIS brute-force", scene="default", w=1920, h=1088, spp=64, mb=16, K=8),
     "c3": dict(desc="C3 random 100k-sphere BVH scene 1920x1080 (internal 1920x1088) 16spp K=8 max_bounces=16 NEE+MIS", scene="random100000", w=1920, h=1088, spp=16, mb=16, K=8),
     "c4": dict(desc="C4 random 1M-sphere BVH scene 3840x2160 32spp K=8 max_bounces=16", scene="random1000000", w=3840, h=2160, spp=32, mb=16, K=8),
+    # C5: progressive convergence run; the frame's 1024 samples are SPLIT over the ranks by bucket (strong scaling)
+    "c5": dict(desc="C5 progressive 3840x2160 1024spp on the C3 100k-sphere scene, K=8 buckets split over the GPUs, max_bounces=16", scene="random100000", w=3840, h=2160, spp=1024, mb=16, K=8, strong=True),
 }
 METRIC, UNIT = "Mrays/s", "Mrays/s"
 
@@ -130,7 +132,7 @@ class ClockSampler:
 
 # bounded CPU samples: full frames for the 9-sphere scene; a fixed random subset of 16x16 tiles for the BVH scenes (every tile is an
 # independent unit of the reference's parallel_for, Renderer.hpp:75-84), sized for roughly 5-20 s of host time
-CPU_TILE_SAMPLE = {"c3": 1024, "c4": 384}
+CPU_TILE_SAMPLE = {"c3": 1024, "c4": 384, "c5": 1024}
 
 
 def cpu_oracle_run(wl, scene, samples, fast=True, workload_name=None):
@@ -223,7 +225,9 @@ def main():
     r = b2r.Renderer(ps, wl["w"], wl["h"], max_bounces=wl["mb"], buckets=K, device=local, stream=stream.cuda_stream,
                      samples_in_flight=args.samples_in_flight, flags=b2r.FLAG_NO_GRAPH if args.no_graph else 0, **shard)
     # weak scaling: every rank renders `spp` samples of its own buckets per step => world*spp sample indices per step
-    step_samples = spp * world
+    # (C5 is the strong-scaling run: the frame's spp are divided among the ranks)
+    strong = bool(wl.get("strong"))
+    step_samples = spp if strong else spp * world
     local_buckets = b2r_dist.buckets_tensor(r, dev)
     use_p2p = world > 1 and args.combine == "p2p"
     if use_p2p:
@@ -293,7 +297,7 @@ def main():
         rays_total, launches = float(rays_local), cnt["launches"]
     secs = ms_total / 1e3
     value = rays_total / secs / 1e6
-    paths_total = wl["w"] * wl["h"] * spp * world * args.steps
+    paths_total = wl["w"] * wl["h"] * step_samples * args.steps
 
     # ---- e2e: same steps through the public API with HOST buffers (scene upload + frame download each step)
     fb_host = torch.empty((wl["h"], wl["w"], 4), dtype=torch.float32, pin_memory=True).numpy()
@@ -323,7 +327,7 @@ def main():
         kernel_ms = {k: {"ms": v[0], "launches": int(v[1])} for k, v in kt.items() if v[1]}
         total_kernel_ms = sum(v[0] for v in kt.values())
         ext, shadow, hits, events, dropped = pc["extension_rays"], pc["shadow_rays"], pc["shaded_hits"], pc["radiance_events"], pc["dropped"]
-        primaries = wl["w"] * wl["h"] * spp * args.steps
+        primaries = wl["w"] * wl["h"] * (step_samples // world) * args.steps
         if kt["bounce_brute"][1]:
             # DESIGN.md "Algorithmic bytes": 44 B path record read per non-primary ray + 44 B written per continuing path (= every
             # non-primary ray was written once) + 24 B radiance read-modify-write per contribution + 12 B per dropped path
@@ -367,8 +371,8 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "samples_per_step_per_gpu": spp, "samples_in_flight": args.samples_in_flight,
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "samples_per_step_per_gpu": step_samples // world, "samples_in_flight": args.samples_in_flight,
                        "partition": (f"sample buckets b%{world}==rank, scene+BVH replicated; " + ("resolve kernel on rank 0 reads peer bucket arrays over NVLink (CUDA IPC), 2 barriers per frame" if use_p2p else "one NCCL all-reduce of bucket sums per frame")) if world > 1 else "single GPU",
                        "l2": "no flush needed: each step streams >1 GB of path-queue records (>> 126 MB L2); RNG-unique samples every step"},
             "paths_per_s": paths_total / secs, "rays_per_step": rays_total / args.steps,

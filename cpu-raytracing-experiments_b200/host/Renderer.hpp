@@ -81,6 +81,8 @@ struct Renderer {
 	}
 	// BoundingVolumeHierarchy::Traverse on caller rays (focus picking, Application.cpp:282-298): rays = n x {origin, dir}
 	void Traverse(const float* rays, uint32_t n, float* tfar_out, int32_t* prim_out) { check(b2r_trace_closest(ctx, rays, n, tfar_out, prim_out)); }
+	// BoundingVolumeHierarchy::Traverse_shadow (BVH.hpp:362): occluded_out[i] = 1 when anything lies within [0, tfar[i]) along ray i
+	void Traverse_shadow(const float* rays, const float* tfar, uint32_t n, uint8_t* occluded_out) { check(b2r_trace_shadow(ctx, rays, tfar, n, occluded_out)); }
 	b2r_ctx* handle() { return ctx; }
 
 private:

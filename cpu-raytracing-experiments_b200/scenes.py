@@ -123,3 +123,22 @@ def random_scene(n, light_every=1000, seed=0x04D15A07, emission=20.0):
     return Scene(name=f"random{n}", geometry=geo, material=np.array(mats, dtype=MATERIAL_DTYPE),
                  camera=dict(eye=(0, 60, 300), dir=(0, 0, -1), focal_length=50.0, exposure=1.0),
                  ambient=(0.0, 0.0, 0.0), hdri=None)
+
+
+def synthetic_hdri(width=64, height=32, seed=0x5EED):
+    """Deterministic equirect RGBA32F test texture (the reference loads env.hdr from disk, Application.cpp:225): values in [0.1, 4)."""
+    u = pcg_unit_floats(_hash_u32(seed), width * height * 4).reshape(height, width, 4)
+    img = f32(0.1) + u * f32(3.9)
+    img[..., 3] = 1.0
+    return np.ascontiguousarray(img, np.float32)
+
+
+def bvh_test_scene(n=255, hdri=None):
+    """Scenes::BVH_test as the reference lights it (Application.cpp:102-122): n random spheres under an ambient HDRI sky
+    (ambient 1,1,1). The reference draws material ids from an EMPTY material list (undefined behaviour); here the
+    spheres use the 8 Lambertian materials of random_scene and one in 32 is emissive so that light sampling has work to do."""
+    sc = random_scene(n, light_every=32)
+    sc["name"] = f"bvh_test{n}"
+    sc["ambient"] = (1.0, 1.0, 1.0)
+    sc["hdri"] = synthetic_hdri() if hdri is None else hdri
+    return sc

@@ -259,3 +259,34 @@ def test_no_mis_variant_matches_oracle_definition():
     o = oracle_for(sc, 160, 96, 8, 1, flags=oracle_py.ORC_NO_MIS); o.accumulate(2)
     assert r.buckets_host().tobytes() == o.buckets().tobytes() and r.counters()["shadow_rays"] == 0
     r.close()
+
+
+def test_c2_full_size_bit_exact():
+    """BASELINE configs[1] at FULL size: default scene, 1920x1080 rendered as 1920x1088, 64 spp, 8 buckets,
+    max_bounces 16 — bucket sums and the tonemapped frame bit-exact against the oracle (timing build, proven bit-identical to the
+    parity build by tests/test_oracle_kat.py); cropped 1080-row RMSE reported."""
+    sc = scenes.default_scene(); w, h, K = 1920, 1088, 8
+    r = b2r.Renderer(sc, w, h, max_bounces=16, buckets=K); r.Accumulate(64); assert r.Render()
+    o = oracle_py.Oracle(w, h, max_bounces=16, K=K, fast=True); o.set_scene(sc); o.accumulate(64)
+    g, ref = r.buckets_host(), o.buckets()
+    frac = divergent_fraction(g, ref)
+    rc, img = o.render()
+    rmse = float(np.sqrt(np.mean((r.framebuffer[:1080] - img[:1080]) ** 2)))
+    print(f"C2 full size: divergent pixel fraction {frac:.3e}, bit-exact buckets {g.tobytes() == ref.tobytes()}, frame RMSE {rmse:.3e}")
+    assert g.tobytes() == ref.tobytes() and r.framebuffer.tobytes() == img.tobytes() and rmse < 1e-3
+    gc, oc = r.counters(), o.counters()
+    assert gc["extension_rays"] == oc["extension_rays"] and gc["terminated"] == oc["terminated"] and gc["dropped"] == oc["dropped"]
+    r.close()
+
+
+@pytest.mark.parametrize("flags", [b2r.FLAG_FORCE_BRUTE, b2r.FLAG_FORCE_BVH])
+def test_sky_hdri_scene(flags):
+    """the miss shader with an equirect HDRI (Renderer.hpp:411-420, Primitives.hpp:35-46, fast_atan2/fast_asin),
+    on Scenes::BVH_test as the reference lights it (ambient 1): both pipelines bit-exact vs the oracle, Q14 included."""
+    sc = scenes.bvh_test_scene(255)
+    r = b2r.Renderer(sc, 256, 144, max_bounces=8, buckets=5, flags=flags); r.Accumulate(5); assert r.Render()
+    o = oracle_for(sc, 256, 144, 8, 5); o.accumulate(5)
+    g, ref = r.buckets_host(), o.buckets()
+    assert divergent_fraction(g, ref) == 0.0 and g.tobytes() == ref.tobytes()
+    assert r.framebuffer.tobytes() == o.render()[1].tobytes()
+    r.close()

@@ -102,3 +102,21 @@ def test_render_only_on_full_rounds():
     o = oracle_py.Oracle(32, 32, max_bounces=4, K=5); o.set_scene(sc)
     o.accumulate(4); assert o.render()[0] == 1  # Renderer.hpp:437
     o.accumulate(1); rc, img = o.render(); assert rc == 0 and np.all(img[..., 3] == 1.0) and img[..., :3].max() <= 1.0
+
+
+def test_timing_build_is_bit_identical_to_parity_build():
+    """liboracle_fast.so (-O3 -march=native, still -ffp-contract=off, no fast-math) is the CPU baseline bench.py times and the
+    checker of the full-size GPU tests; it must produce the parity build's bits."""
+    for sc, flags in ((scenes.default_scene(), 0), (scenes.bvh_test_scene(255), 0), (scenes.random_scene(700, light_every=30), oracle_py.ORC_BVH)):
+        a = oracle_py.Oracle(160, 96, max_bounces=8, K=3, flags=flags); a.set_scene(sc); a.accumulate(3)
+        b = oracle_py.Oracle(160, 96, max_bounces=8, K=3, flags=flags, fast=True); b.set_scene(sc); b.accumulate(3)
+        assert a.buckets().tobytes() == b.buckets().tobytes()
+        assert a.render()[1].tobytes() == b.render()[1].tobytes()
+
+
+def test_sky_quirk_q14():
+    """Miss shader under an ambient sky (Renderer.hpp:411-420): green and blue are scaled by throughput.r (Q14)."""
+    sc = scenes.bvh_test_scene(40)
+    o = oracle_py.Oracle(64, 48, max_bounces=1, K=1); o.set_scene(sc); o.accumulate(1)
+    b = o.buckets()[0]
+    assert b.max() > 0 and b.min() >= 0  # primary misses pick up sky * ambient with throughput 1; hits are dropped at max_bounces=1 (Q11)
