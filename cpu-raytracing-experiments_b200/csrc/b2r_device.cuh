@@ -17,7 +17,7 @@
 
 namespace b2r {
 
-constexpr int kBruteTile = 1024;       // spheres staged per shared-memory tile in the brute-force kernels
+constexpr int kBruteTile = 256;        // spheres staged per shared-memory tile in the brute-force kernels
 constexpr int kBlock = 256;            // threads per CTA, shading kernels
 constexpr int kTravBlock = 128;        // threads per CTA, traversal kernels
 
@@ -76,6 +76,7 @@ template <bool FIRST, bool COUNT>
 __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_brute(const Params p, const uint32_t bounce) {
 	constexpr int kQ = 2 * kBruteBlock;  // hit queue: up to kBruteBlock-1 waiting + kBruteBlock new
 	__shared__ float4 s_prim[kBruteTile];
+	__shared__ float4 s_pre[FIRST ? kBruteTile : 1];  // bounce 0: {c - o, r^2 - |c - o|^2} per sphere for the shared camera origin
 	__shared__ int32_t s_prim_mat[kBruteTile];
 	__shared__ float4 s_table[4][kSmemTable];  // mat_albedo, mat_emission, light_sphere, light_emit
 	__shared__ uint32_t s_hit_i[kQ]; __shared__ float s_hit_t[kQ]; __shared__ int32_t s_hit_prim[kQ];
@@ -91,7 +92,10 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 
 	// stage the scene tables once per CTA (persistent: amortised over the whole launch)
 	if (n_tiles == 1) {
-		for (uint32_t j = threadIdx.x; j < sc.n_prims; j += blockDim.x) { s_prim[j] = sc.prims[j]; s_prim_mat[j] = sc.prim_mat[j]; }
+		for (uint32_t j = threadIdx.x; j < sc.n_prims; j += blockDim.x) {
+			const float4 sp = sc.prims[j]; s_prim[j] = sp; s_prim_mat[j] = sc.prim_mat[j];
+			if (FIRST) { const SpherePre q = sphere_prepare(sp.x, sp.y, sp.z, sp.w, p.frame.cam.px, p.frame.cam.py, p.frame.cam.pz); s_pre[j] = make_float4(q.tx, q.ty, q.tz, q.disc0); }
+		}
 		sc.prim_mat = s_prim_mat; sc.prims = s_prim;
 	}
 	if (sc.n_mat <= kSmemTable) {
@@ -127,13 +131,19 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 				const uint32_t first = tile * kBruteTile, cnt = min(static_cast<uint32_t>(kBruteTile), sc.n_prims - first);
 				if (n_tiles > 1) {
 					__syncthreads();
-					for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) s_prim[j] = p.scene.prims[first + j];
+					for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
+						const float4 sp = p.scene.prims[first + j]; s_prim[j] = sp;
+						if (FIRST) { const SpherePre q = sphere_prepare(sp.x, sp.y, sp.z, sp.w, p.frame.cam.px, p.frame.cam.py, p.frame.cam.pz); s_pre[j] = make_float4(q.tx, q.ty, q.tz, q.disc0); }
+					}
 					__syncthreads();
 				}
 				if (live) {
+#pragma unroll 3
 					for (uint32_t j = 0; j < cnt; j++) {
-						const float4 sp = s_prim[j]; float d;
-						if (sphere_hit_closest(sp.x, sp.y, sp.z, sp.w, ox, oy, oz, dx, dy, dz, &d) && d < best) { best = d; prim = static_cast<int32_t>(first + j); }
+						float d; bool h;
+						if (FIRST) { const float4 q = s_pre[FIRST ? j : 0]; h = sphere_hit_prepared(SpherePre{q.x, q.y, q.z, q.w}, dx, dy, dz, &d); }
+						else { const float4 sp = s_prim[j]; h = sphere_hit_closest(sp.x, sp.y, sp.z, sp.w, ox, oy, oz, dx, dy, dz, &d); }
+						if (h && d < best) { best = d; prim = static_cast<int32_t>(first + j); }
 					}
 					if (COUNT) c_sphere += cnt;
 				}
@@ -143,7 +153,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 				c_term++;
 				if (sc.has_ambient) {
 					const PathState sm = FIRST ? primary_path(p.frame, p.batch->acc[i / p.frame.npix], i / p.frame.npix, i % p.frame.npix) : load_path(p.q, side, i);
-					rad_add(p.rad, p.frame.npix, sm.pid, shade_sky(sc, sm), f3{0.0f, 0.0f, 0.0f}); c_events++;
+					rad_add(p.rad, p.frame.npix, sm.pid, shade_sky(sc, sm), f3{0.0f, 0.0f, 0.0f}, true, false); c_events++;
 				}
 			}
 			// ---------------- the CTA's hits join the shared-memory queue
@@ -190,6 +200,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 			if (want_shadow) {
 				c_shadow++;
 				if (COUNT) c_sphere += sc.n_prims;
+#pragma unroll 3
 				for (uint32_t j = 0; j < sc.n_prims; j++) {
 					const float4 sp = s_prim[j];
 					if (sphere_hit_any(sp.x, sp.y, sp.z, sp.w, sr.o.x, sr.o.y, sr.o.z, sr.d.x, sr.d.y, sr.d.z, sr.tfar)) { want_shadow = false; break; }
@@ -215,10 +226,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 		if (shade) {
 			if (last) { rad_zero(p.rad, p.frame.npix, s.pid); c_drop++; }
 			else {
-				if (want_shadow || emissive) {
-					const f3 l = want_shadow ? sr.L : f3{0.0f, 0.0f, 0.0f};
-					rad_add(p.rad, p.frame.npix, s.pid, l, e_add); c_events++;
-				}
+				if (want_shadow || emissive) { rad_add(p.rad, p.frame.npix, s.pid, sr.L, e_add, want_shadow, emissive); c_events++; }
 				keep = shade_continue(sf, &s, acc, seed, bounce);
 				if (!keep) c_term++;  // roulette: path ends here, radiance stays at the pixel (Renderer.hpp:379-381,424-430)
 			}
@@ -345,7 +353,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_shade(con
 			const bool is_hit = live && prim >= 0;
 			if (live && !is_hit) {  // miss shader (Renderer.hpp:408-420)
 				c_term++;
-				if (sc.has_ambient) { const PathState sm = load_path(p.q, side, i); rad_add(p.rad, p.frame.npix, sm.pid, shade_sky(sc, sm), f3{0.0f, 0.0f, 0.0f}); c_events++; }
+				if (sc.has_ambient) { const PathState sm = load_path(p.q, side, i); rad_add(p.rad, p.frame.npix, sm.pid, shade_sky(sc, sm), f3{0.0f, 0.0f, 0.0f}, true, false); c_events++; }
 			}
 			uint32_t n_hits;
 			const uint32_t slot = queued + block_rank(is_hit, s_cnt_a, &n_hits);
@@ -374,7 +382,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_shade(con
 					// the reference adds the light sample first, then the emission (Renderer.hpp:304-353): when a shadow ray is
 					// pending the emission travels with it and k_intersect_shadow adds both in that order
 					emit = shade_emission(sc, sf, s, depth, bounce, mis);
-					if (!want_shadow) { rad_add(p.rad, p.frame.npix, s.pid, emit, f3{0.0f, 0.0f, 0.0f}); c_events++; }
+					if (!want_shadow) { rad_add(p.rad, p.frame.npix, s.pid, emit, f3{0.0f, 0.0f, 0.0f}, true, false); c_events++; }
 				}
 				keep = shade_continue(sf, &s, acc, seed, bounce);
 				if (!keep) c_term++;
@@ -427,7 +435,7 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_shadow(const Params p,
 				const bool has_e = E.x != 0.0f || E.y != 0.0f || E.z != 0.0f;
 				if (!t.occluded || has_e) {
 					const f3 L = t.occluded ? f3{0.0f, 0.0f, 0.0f} : f3{p.q.SL[idx], p.q.SL[p.q.cap + idx], p.q.SL[2u * p.q.cap + idx]};
-					rad_add(p.rad, p.frame.npix, pid, L, E); c_events++;
+					rad_add(p.rad, p.frame.npix, pid, L, E, !t.occluded, has_e); c_events++;
 				}
 				active = false;
 			}

@@ -239,17 +239,17 @@ B2R_HD float power_heuristic_over_f(float f, float g) { return f / sel_max(1e-6f
 // ------------------------------------------------------------------ sphere tests (BVH.hpp:236-305)
 // Closest hit, one lane of the SIMD block BVH.hpp:251-267: returns the candidate distance, or a negative number /
 // NaN-free sentinel when the lane's store mask is clear. sphere = {cx, cy, cz, r^2}.
-B2R_HD bool sphere_hit_closest(float cx, float cy, float cz, float r2, float ox, float oy, float oz, float dx, float dy, float dz, float* dist_out) {
-	float tx = cx - ox;
-	float b = dx * tx;
-	float disc = fma_rn(-tx, tx, r2);
-	float ty = cy - oy;
-	b = fma_rn(dy, ty, b);
-	disc = fma_rn(-ty, ty, disc);
-	float tz = cz - oz;
-	b = fma_rn(dz, tz, b);
-	disc = fma_rn(-tz, tz, disc);
-	disc = fma_rn(b, b, disc);
+// The part of the test that depends only on (sphere, ray origin): t = c - o and r^2 - |t|^2 in the reference's FMA order.
+// Camera rays share one origin, so the bounce-0 kernel evaluates this once per sphere instead of once per ray.
+struct SpherePre { float tx, ty, tz, disc0; };
+B2R_HD SpherePre sphere_prepare(float cx, float cy, float cz, float r2, float ox, float oy, float oz) {
+	SpherePre p; p.tx = cx - ox; p.ty = cy - oy; p.tz = cz - oz;
+	p.disc0 = fma_rn(-p.tz, p.tz, fma_rn(-p.ty, p.ty, fma_rn(-p.tx, p.tx, r2)));
+	return p;
+}
+B2R_HD bool sphere_hit_prepared(const SpherePre& p, float dx, float dy, float dz, float* dist_out) {
+	const float b = fma_rn(dz, p.tz, fma_rn(dy, p.ty, dx * p.tx));
+	const float disc = fma_rn(b, b, p.disc0);
 	// The reference takes the square root unconditionally and masks afterwards (:262-265): a negative discriminant gives
 	// NaN (fails the ordered compare) and -0 keeps its sign bit (masked out). Both are exactly "bit pattern above +inf",
 	// so the root is only evaluated for discriminants in [+0, +inf].
@@ -259,6 +259,9 @@ B2R_HD bool sphere_hit_closest(float cx, float cy, float cz, float r2, float ox,
 	if (sign_set(d)) d = b + root;  // blendv on the sign bit (:264)
 	*dist_out = d;
 	return !sign_set(d);            // NaN/inf distances fail the caller's `d < tfar`
+}
+B2R_HD bool sphere_hit_closest(float cx, float cy, float cz, float r2, float ox, float oy, float oz, float dx, float dy, float dz, float* dist_out) {
+	return sphere_hit_prepared(sphere_prepare(cx, cy, cz, r2, ox, oy, oz), dx, dy, dz, dist_out);
 }
 // Any hit along [0, tfar): BVH.hpp:294-300 (glm dot products, no FMA)
 B2R_HD bool sphere_hit_any(float cx, float cy, float cz, float r2, float ox, float oy, float oz, float dx, float dy, float dz, float tfar) {

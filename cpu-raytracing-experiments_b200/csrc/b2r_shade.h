@@ -179,10 +179,20 @@ B2R_HD f3 shade_sky(const SceneDev& sc, const PathState& s) {
 	// Q14: all three channels are scaled by throughput.r
 	return f3{s.tr * (tx.x * sc.ambient[0]), s.tr * (tx.y * sc.ambient[1]), s.tr * (tx.z * sc.ambient[2])};
 }
-B2R_HD void rad_add(float* rad, uint32_t npix, uint32_t pid, f3 a, f3 b) {
+// Adds up to two contributions, in this order, to the path's radiance at its pixel. Only one thread ever touches a given
+// (sample, pixel) entry during a launch, so on the device the additions are issued as fire-and-forget reductions (RED.ADD.F32:
+// same-address operations of one thread stay ordered, the result is the plain left-to-right float sum) and the warp does not
+// wait for an HBM read-modify-write round trip.
+B2R_HD void rad_add(float* rad, uint32_t npix, uint32_t pid, f3 a, f3 b, bool has_a = true, bool has_b = true) {
 	const uint32_t slot = pid >> 26, t = pid & kPixMask;
 	float* r = rad + static_cast<size_t>(slot) * 3u * npix + t;
-	r[0] = (r[0] + a.x) + b.x; r[npix] = (r[npix] + a.y) + b.y; r[2u * npix] = (r[2u * npix] + a.z) + b.z;
+#if defined(__CUDA_ARCH__)
+	if (has_a) { atomicAdd(r, a.x); atomicAdd(r + npix, a.y); atomicAdd(r + 2u * npix, a.z); }
+	if (has_b) { atomicAdd(r, b.x); atomicAdd(r + npix, b.y); atomicAdd(r + 2u * npix, b.z); }
+#else
+	if (has_a) { r[0] += a.x; r[npix] += a.y; r[2u * npix] += a.z; }
+	if (has_b) { r[0] += b.x; r[npix] += b.y; r[2u * npix] += b.z; }
+#endif
 }
 B2R_HD void rad_zero(float* rad, uint32_t npix, uint32_t pid) {
 	const uint32_t slot = pid >> 26, t = pid & kPixMask;

@@ -63,7 +63,7 @@ int hc_render_sample(const b2r_sphere* prims, const b2r_bvh_node* nodes, uint32_
 				}
 				if (occ) want_shadow = false;
 			}
-			if (want_shadow || sf.emissive) rad_add(rad_out, fr.npix, s.pid, want_shadow ? sr.L : f3{0, 0, 0}, e);
+			if (want_shadow || sf.emissive) rad_add(rad_out, fr.npix, s.pid, sr.L, e, want_shadow, sf.emissive);
 			if (!shade_continue(sf, &s, acc, seed, bounce)) { counters[3]++; break; }
 		}
 	}
