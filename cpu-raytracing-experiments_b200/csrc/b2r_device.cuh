@@ -298,6 +298,15 @@ __device__ __forceinline__ void warp_stage_nodes(const WideNode* __restrict__ wi
 	asm volatile("cp.async.wait_all;" ::: "memory");
 	__syncwarp();
 }
+// Per-thread traversal stack of the persistent kernels: the first kSmemStack entries live in shared memory, laid out
+// [entry][thread] so a warp's accesses are conflict-free whatever the lanes' depths; deeper entries (rare) overflow to local.
+constexpr int kSmemStack = 16;
+struct HybridStack {
+	uint32_t* sm;  // &s_stack[0][threadIdx.x]
+	uint32_t spill[kTraversalStack - kSmemStack];
+	__device__ __forceinline__ void put(int i, uint32_t v) { if (i < kSmemStack) sm[i * kTravBlock] = v; else spill[i - kSmemStack] = v; }
+	__device__ __forceinline__ uint32_t get(int i) const { return i < kSmemStack ? sm[i * kTravBlock] : spill[i - kSmemStack]; }
+};
 // closest-hit traversal of queue side (bounce & 1)
 template <bool COUNT>
 __global__ void __launch_bounds__(kTravBlock) k_intersect_closest(const Params p, const uint32_t bounce) {
@@ -306,9 +315,10 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_closest(const Params p
 	const WideNode* __restrict__ wide = p.scene.wide;
 	uint32_t c_sphere = 0, c_box = 0;
 	__shared__ float4 s_nodes[kTravBlock / 32][32 * kNodeRowF4];
+	__shared__ uint32_t s_stack[kSmemStack][kTravBlock];
 	float4* rows = s_nodes[threadIdx.x >> 5];
-	WarpPool pool; TravClosest t; bool active = false; uint32_t idx = 0;
-	t.node = 0u;
+	WarpPool pool; TravClosestT<HybridStack> t; bool active = false; uint32_t idx = 0;
+	t.node = 0u; t.stack.sm = &s_stack[0][threadIdx.x];
 	for (;;) {
 		const uint32_t got = pool.take(!active, p.cnt.work_a + bounce, n_in);
 		if (got != 0xffffffffu) {
@@ -415,9 +425,10 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_shadow(const Params p,
 	const WideNode* __restrict__ wide = p.scene.wide;
 	uint32_t c_sphere = 0, c_box = 0, c_events = 0;
 	__shared__ float4 s_nodes[kTravBlock / 32][32 * kNodeRowF4];
+	__shared__ uint32_t s_stack[kSmemStack][kTravBlock];
 	float4* rows = s_nodes[threadIdx.x >> 5];
-	WarpPool pool; TravAny t; bool active = false; uint32_t idx = 0, pid = 0;
-	t.node = 0u;
+	WarpPool pool; TravAnyT<HybridStack> t; bool active = false; uint32_t idx = 0, pid = 0;
+	t.node = 0u; t.stack.sm = &s_stack[0][threadIdx.x];
 	for (;;) {
 		const uint32_t got = pool.take(!active, p.cnt.work_b + bounce, n_in);
 		if (got != 0xffffffffu) {

@@ -220,6 +220,19 @@ B2R_HD void slab(const float4 a, const float4 b, float ix, float iy, float iz, f
 }
 #define B2R_CSWAP(ka, la, kb, lb) { const bool sw = kb < ka; const uint32_t tk = sw ? kb : ka, tl = sw ? lb : la; kb = sw ? ka : kb; lb = sw ? la : lb; ka = tk; la = tl; }
 
+// Traversal stacks hold one 32-bit word per entry: wide-node index << 10 | the top 10 bits of the (non-negative) entry distance,
+// truncated, i.e. a lower bound that is still good for culling when the entry is popped. The storage is a policy: a plain array
+// for whole-ray callers, shared memory with a local-memory overflow in the persistent kernels (a 64-entry per-thread array in
+// local memory made the stack the largest L1/L2 client of the first version — more sectors than the nodes themselves).
+constexpr uint32_t kMaxWideNodes = 1u << 22;
+struct ArrayStack {
+	uint32_t e[kTraversalStack];
+	B2R_HD void put(int i, uint32_t v) { e[i] = v; }
+	B2R_HD uint32_t get(int i) const { return e[i]; }
+};
+B2R_HD uint32_t pack_entry(uint32_t node, uint32_t tnear_bits) { return (node << 10) | (tnear_bits >> 21); }
+B2R_HD float entry_tnear(uint32_t e) { return from_bits((e & 0x3ffu) << 21); }
+
 struct TravBase {
 	float ox, oy, oz, dx, dy, dz;   // ray
 	float ix, iy, iz, nx, ny, nz;   // 1/d and -o/d
@@ -239,9 +252,10 @@ template <bool STAGED> B2R_HD float4 node_f4(const float4* n, int i) { return ST
 // entry distance is beyond the best. Inner slots are slab-tested in one uniform pass; leaf slots are only marked there and
 // their spheres tested in a second, compact loop, so a few lanes with leaves do not drag the whole warp through four
 // sphere tests.
-struct TravClosest : TravBase {
+template <class Stack>
+struct TravClosestT : TravBase {
 	float best; int32_t prim;
-	uint2 stack[kTraversalStack];
+	Stack stack;
 	B2R_HD void begin(const Ray& r) { arm(r); best = FLT_MAX; prim = -1; }
 	template <bool COUNT, bool STAGED>
 	B2R_HD bool visit(const float4* n, uint32_t* c_sphere, uint32_t* c_box) {
@@ -273,13 +287,13 @@ struct TravClosest : TravBase {
 		B2R_CSWAP(key[0], link[0], key[1], link[1]); B2R_CSWAP(key[2], link[2], key[3], link[3]);
 		B2R_CSWAP(key[0], link[0], key[2], link[2]); B2R_CSWAP(key[1], link[1], key[3], link[3]);
 		B2R_CSWAP(key[1], link[1], key[2], link[2]);
-		if (key[3] != 0xffffffffu) stack[sp++] = make_uint2(link[3], key[3]);
-		if (key[2] != 0xffffffffu) stack[sp++] = make_uint2(link[2], key[2]);
-		if (key[1] != 0xffffffffu) stack[sp++] = make_uint2(link[1], key[1]);
+		if (key[3] != 0xffffffffu) stack.put(sp++, pack_entry(link[3], key[3]));
+		if (key[2] != 0xffffffffu) stack.put(sp++, pack_entry(link[2], key[2]));
+		if (key[1] != 0xffffffffu) stack.put(sp++, pack_entry(link[1], key[1]));
 		if (key[0] != 0xffffffffu && from_bits(key[0]) <= best) { node = link[0]; return true; }
 		while (sp > 0) {
-			const uint2 e = stack[--sp];
-			if (from_bits(e.y) <= best) { node = e.x; return true; }
+			const uint32_t e = stack.get(--sp);
+			if (entry_tnear(e) <= best) { node = e >> 10; return true; }
 		}
 		return false;
 	}
@@ -289,9 +303,10 @@ struct TravClosest : TravBase {
 	B2R_HD bool step_staged(const float4* n, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, true>(n, c_sphere, c_box); }
 };
 // Any hit along [0, tfar) — Traverse_shadow semantics (BVH.hpp:290-305): an order-independent boolean.
-struct TravAny : TravBase {
+template <class Stack>
+struct TravAnyT : TravBase {
 	float tfar; bool occluded;
-	uint32_t stack[kTraversalStack];
+	Stack stack;
 	B2R_HD void begin(const Ray& r, float limit) { arm(r); tfar = limit; occluded = false; }
 	template <bool COUNT, bool STAGED>
 	B2R_HD bool visit(const float4* n, uint32_t* c_sphere, uint32_t* c_box) {
@@ -303,7 +318,7 @@ struct TravAny : TravBase {
 			float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, tfar, &tn, &h);
 			const bool inner = l >= 0;
 			if (COUNT && inner) (*c_box)++;
-			if (inner && h) { if (next != 0xffffffffu) stack[sp++] = next; next = static_cast<uint32_t>(l); }
+			if (inner && h) { if (next != 0xffffffffu) stack.put(sp++, next); next = static_cast<uint32_t>(l); }
 			leaves |= (!inner && l != kEmptyLink) ? (1u << k) : 0u;
 		}
 		while (leaves) {
@@ -319,7 +334,7 @@ struct TravAny : TravBase {
 		}
 		if (next != 0xffffffffu) { node = next; return true; }
 		if (sp == 0) return false;
-		node = stack[--sp];
+		node = stack.get(--sp);
 		return true;
 	}
 	template <bool COUNT>
@@ -327,6 +342,8 @@ struct TravAny : TravBase {
 	template <bool COUNT>
 	B2R_HD bool step_staged(const float4* n, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, true>(n, c_sphere, c_box); }
 };
+using TravClosest = TravClosestT<ArrayStack>;
+using TravAny = TravAnyT<ArrayStack>;
 // whole-ray wrappers (trace taps, host check)
 template <bool COUNT>
 B2R_HD void traverse_closest(const WideNode* __restrict__ wide, const Ray& r, float* best_out, int32_t* prim_out, uint32_t* c_sphere, uint32_t* c_box) {
