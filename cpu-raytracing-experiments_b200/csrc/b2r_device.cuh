@@ -281,8 +281,8 @@ struct WarpPool {
 // Node staging: the lanes of a warp sit on 32 different 128-byte nodes. Read naively that is 8 x LDG.128 with 32 lines each
 // (256 L1 wavefronts per step — the first version was bound by exactly that). Instead the warp copies the 32 nodes
 // cooperatively, 8 lanes x 16 B per node so each copy instruction touches 4 lines, straight into shared memory (cp.async,
-// no register staging); every lane then reads its own node back with conflict-free LDS.128 (rows padded to 144 B).
-constexpr int kNodeRowF4 = 9;  // 8 float4 of payload + 1 of padding per staged node
+// no register staging); every lane then reads its own node back with LDS.128.
+constexpr int kNodeRowF4 = 8;  // 128-byte rows; the eight 16-byte parts of a row are XOR-swizzled by the owning lane (conflict-free fill and reads)
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
 	const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
@@ -293,7 +293,7 @@ __device__ __forceinline__ void warp_stage_nodes(const WideNode* __restrict__ wi
 	for (uint32_t j = 0; j < 8; j++) {
 		const uint32_t owner = 4u * j + (lane >> 3);
 		const uint32_t nd = __shfl_sync(0xffffffffu, my_node, owner);
-		if ((live >> owner) & 1u) cp_async16(s_rows + owner * kNodeRowF4 + part, reinterpret_cast<const float4*>(wide + nd) + part);
+		if ((live >> owner) & 1u) cp_async16(s_rows + owner * kNodeRowF4 + (part ^ (owner & 7u)), reinterpret_cast<const float4*>(wide + nd) + part);
 	}
 	asm volatile("cp.async.wait_all;" ::: "memory");
 	__syncwarp();
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_closest(const Params p
 	const int side = bounce & 1;
 	const WideNode* __restrict__ wide = p.scene.wide;
 	uint32_t c_sphere = 0, c_box = 0;
-	__shared__ float4 s_nodes[kTravBlock / 32][32 * kNodeRowF4];
+	__shared__ __align__(128) float4 s_nodes[kTravBlock / 32][32 * kNodeRowF4];
 	__shared__ uint32_t s_stack[kSmemStack][kTravBlock];
 	float4* rows = s_nodes[threadIdx.x >> 5];
 	WarpPool pool; TravClosestT<HybridStack> t; bool active = false; uint32_t idx = 0;
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_closest(const Params p
 		if (live == 0u) break;
 		do {
 			warp_stage_nodes(wide, rows, t.node, live);
-			if (active && !t.template step_staged<COUNT>(rows + lane_id() * kNodeRowF4, &c_sphere, &c_box)) {
+			if (active && !t.template step_staged<COUNT>(rows + lane_id() * kNodeRowF4, lane_id() & 7u, &c_sphere, &c_box)) {
 				p.q.H[idx] = make_float2(t.best, __int_as_float(t.prim));
 				active = false;
 			}
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_shadow(const Params p,
 	const uint32_t n_in = p.cnt.shadow[bounce];
 	const WideNode* __restrict__ wide = p.scene.wide;
 	uint32_t c_sphere = 0, c_box = 0, c_events = 0;
-	__shared__ float4 s_nodes[kTravBlock / 32][32 * kNodeRowF4];
+	__shared__ __align__(128) float4 s_nodes[kTravBlock / 32][32 * kNodeRowF4];
 	__shared__ uint32_t s_stack[kSmemStack][kTravBlock];
 	float4* rows = s_nodes[threadIdx.x >> 5];
 	WarpPool pool; TravAnyT<HybridStack> t; bool active = false; uint32_t idx = 0, pid = 0;
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_shadow(const Params p,
 		if (live == 0u) break;
 		do {
 			warp_stage_nodes(wide, rows, t.node, live);
-			if (active && !t.template step_staged<COUNT>(rows + lane_id() * kNodeRowF4, &c_sphere, &c_box)) {
+			if (active && !t.template step_staged<COUNT>(rows + lane_id() * kNodeRowF4, lane_id() & 7u, &c_sphere, &c_box)) {
 				const f3 E{p.q.SE[idx], p.q.SE[p.q.cap + idx], p.q.SE[2u * p.q.cap + idx]};  // emission of the same hit (usually 0)
 				const bool has_e = E.x != 0.0f || E.y != 0.0f || E.z != 0.0f;
 				if (!t.occluded || has_e) {

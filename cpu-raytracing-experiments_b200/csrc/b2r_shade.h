@@ -245,7 +245,8 @@ struct TravBase {
 	}
 };
 // node access: STAGED = the node's eight float4 were copied to shared memory by the warp (kernels); otherwise read-only LDG
-template <bool STAGED> B2R_HD float4 node_f4(const float4* n, int i) { return STAGED ? n[i] : ldg4(n + i); }
+// (staged rows are XOR-swizzled by the owning lane, `swz` = lane & 7, so both the cooperative fill and the per-lane reads are bank-conflict-free)
+template <bool STAGED> B2R_HD float4 node_f4(const float4* n, int i, uint32_t swz) { return STAGED ? n[static_cast<uint32_t>(i) ^ swz] : ldg4(n + i); }
 
 // Closest hit == brute force over all spheres (BVH.hpp:311-318): a candidate replaces the best when d < best, or d == best with
 // a lower sphere index (the brute-force loop keeps the first of equal distances, BVH.hpp:265); a node is culled only when its
@@ -258,11 +259,11 @@ struct TravClosestT : TravBase {
 	Stack stack;
 	B2R_HD void begin(const Ray& r) { arm(r); best = FLT_MAX; prim = -1; }
 	template <bool COUNT, bool STAGED>
-	B2R_HD bool visit(const float4* n, uint32_t* c_sphere, uint32_t* c_box) {
+	B2R_HD bool visit(const float4* n, uint32_t swz, uint32_t* c_sphere, uint32_t* c_box) {
 		uint32_t key[4], link[4]; uint32_t leaves = 0u;
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
-			const float4 a = node_f4<STAGED>(n, 2 * k), b = node_f4<STAGED>(n, 2 * k + 1);
+			const float4 a = node_f4<STAGED>(n, 2 * k, swz), b = node_f4<STAGED>(n, 2 * k + 1, swz);
 			const int32_t l = as_int(b.z);
 			float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, best, &tn, &h);
 			const bool inner = l >= 0;
@@ -277,7 +278,7 @@ struct TravClosestT : TravBase {
 			const int k = __builtin_ctz(leaves);
 #endif
 			leaves &= leaves - 1u;
-			const float4 sp = node_f4<STAGED>(n, 2 * k); const int32_t id = ~as_int(node_f4<STAGED>(n, 2 * k + 1).z);
+			const float4 sp = node_f4<STAGED>(n, 2 * k, swz); const int32_t id = ~as_int(node_f4<STAGED>(n, 2 * k + 1, swz).z);
 			float d; if (COUNT) (*c_sphere)++;
 			if (sphere_hit_closest(sp.x, sp.y, sp.z, sp.w, ox, oy, oz, dx, dy, dz, &d)) {
 				if (d < best || (d == best && id < prim)) { best = d; prim = id; }
@@ -298,9 +299,9 @@ struct TravClosestT : TravBase {
 		return false;
 	}
 	template <bool COUNT>
-	B2R_HD bool step(const WideNode* __restrict__ wide, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, false>(reinterpret_cast<const float4*>(wide + node), c_sphere, c_box); }
+	B2R_HD bool step(const WideNode* __restrict__ wide, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, false>(reinterpret_cast<const float4*>(wide + node), 0u, c_sphere, c_box); }
 	template <bool COUNT>
-	B2R_HD bool step_staged(const float4* n, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, true>(n, c_sphere, c_box); }
+	B2R_HD bool step_staged(const float4* n, uint32_t swz, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, true>(n, swz, c_sphere, c_box); }
 };
 // Any hit along [0, tfar) — Traverse_shadow semantics (BVH.hpp:290-305): an order-independent boolean.
 template <class Stack>
@@ -309,11 +310,11 @@ struct TravAnyT : TravBase {
 	Stack stack;
 	B2R_HD void begin(const Ray& r, float limit) { arm(r); tfar = limit; occluded = false; }
 	template <bool COUNT, bool STAGED>
-	B2R_HD bool visit(const float4* n, uint32_t* c_sphere, uint32_t* c_box) {
+	B2R_HD bool visit(const float4* n, uint32_t swz, uint32_t* c_sphere, uint32_t* c_box) {
 		uint32_t next = 0xffffffffu, leaves = 0u;
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
-			const float4 a = node_f4<STAGED>(n, 2 * k), b = node_f4<STAGED>(n, 2 * k + 1);
+			const float4 a = node_f4<STAGED>(n, 2 * k, swz), b = node_f4<STAGED>(n, 2 * k + 1, swz);
 			const int32_t l = as_int(b.z);
 			float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, tfar, &tn, &h);
 			const bool inner = l >= 0;
@@ -328,7 +329,7 @@ struct TravAnyT : TravBase {
 			const int k = __builtin_ctz(leaves);
 #endif
 			leaves &= leaves - 1u;
-			const float4 sp = node_f4<STAGED>(n, 2 * k);
+			const float4 sp = node_f4<STAGED>(n, 2 * k, swz);
 			if (COUNT) (*c_sphere)++;
 			if (sphere_hit_any(sp.x, sp.y, sp.z, sp.w, ox, oy, oz, dx, dy, dz, tfar)) { occluded = true; return false; }
 		}
@@ -338,9 +339,9 @@ struct TravAnyT : TravBase {
 		return true;
 	}
 	template <bool COUNT>
-	B2R_HD bool step(const WideNode* __restrict__ wide, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, false>(reinterpret_cast<const float4*>(wide + node), c_sphere, c_box); }
+	B2R_HD bool step(const WideNode* __restrict__ wide, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, false>(reinterpret_cast<const float4*>(wide + node), 0u, c_sphere, c_box); }
 	template <bool COUNT>
-	B2R_HD bool step_staged(const float4* n, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, true>(n, c_sphere, c_box); }
+	B2R_HD bool step_staged(const float4* n, uint32_t swz, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, true>(n, swz, c_sphere, c_box); }
 };
 using TravClosest = TravClosestT<ArrayStack>;
 using TravAny = TravAnyT<ArrayStack>;
