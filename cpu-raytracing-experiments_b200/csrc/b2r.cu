@@ -351,7 +351,7 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 			c->wide_key = key; c->have_wide = true;
 		}
 	}
-	if (c->wide_host.max_stack > static_cast<uint32_t>(kTraversalStack)) { c->have_wide = false; return fail(B2R_ERR_BVH, "tree needs a deeper traversal stack than kTraversalStack"); }
+	if (c->wide_host.max_stack + 3u > static_cast<uint32_t>(kTraversalStack)) { c->have_wide = false; return fail(B2R_ERR_BVH, "tree needs a deeper traversal stack than kTraversalStack (3 slots of headroom for the branch-free pushes)"); }
 	if (c->wide_host.nodes.size() >= kMaxWideNodes) { c->have_wide = false; return fail(B2R_ERR_BVH, "more than 2^22 traversal nodes (stack entries keep 22 node bits)"); }
 
 	PackedScene ps; pack_scene(prims, n_prims, materials, n_mat, light_geom_idx, n_lights, geometry, ps);

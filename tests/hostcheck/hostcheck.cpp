@@ -22,7 +22,7 @@ int hc_render_sample(const b2r_sphere* prims, const b2r_bvh_node* nodes, uint32_
 	WideBvh wide;
 	if (use_bvh == 2) { std::vector<b2r_bvh_node> tree; build_traversal_tree(prims, n_prims, tree); flatten_bvh(tree.data(), static_cast<uint32_t>(tree.size()), prims, n_prims, wide); }  // what libb2r uploads by default
 	else flatten_bvh(nodes, n_nodes, prims, n_prims, wide);  // B2R_FLAG_REFERENCE_TREE
-	if (wide.max_stack > static_cast<uint32_t>(kTraversalStack)) return B2R_ERR_BVH;
+	if (wide.max_stack + 3u > static_cast<uint32_t>(kTraversalStack)) return B2R_ERR_BVH;
 	SceneDev sc{};
 	sc.prims = ps.prims.data(); sc.prim_mat = ps.prim_mat.data(); sc.mat_albedo = ps.mat_albedo.data(); sc.mat_emission = ps.mat_emission.data();
 	sc.light_sphere = ps.light_sphere.data(); sc.light_emit = ps.light_emit.data(); sc.wide = wide.nodes.data(); sc.hdri = nullptr;
