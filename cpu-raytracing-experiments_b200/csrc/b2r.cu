@@ -379,7 +379,7 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 	SceneDev& s = c->params.scene;
 	s.prims = c->d_prims; s.prim_mat = c->d_prim_mat; s.mat_albedo = c->d_mat_albedo; s.mat_emission = c->d_mat_emission;
 	s.light_sphere = c->d_light_sphere; s.light_emit = c->d_light_emit; s.wide = c->d_wide; s.hdri = has_ambient ? c->d_hdri : nullptr;
-	s.n_prims = n_prims; s.n_mat = n_mat; s.n_lights = n_lights;
+	s.n_prims = n_prims; s.n_mat = n_mat; s.n_lights = n_lights; s.stack_tn_bits = c->wide_host.tn_bits;
 	s.light_sel_pdf = 1.0f / static_cast<float>(n_lights);  // Renderer.hpp:78
 	s.ambient[0] = amb[0]; s.ambient[1] = amb[1]; s.ambient[2] = amb[2]; s.has_ambient = has_ambient ? 1 : 0;
 	s.hdri_w = hdri_w; s.hdri_h = hdri_h; s.hdri_fw = static_cast<float>(hdri_w - 1); s.hdri_fh = static_cast<float>(hdri_h - 1);  // Application.cpp:230-231

@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_closest(const Params p
 		if (live == 0u) break;
 		do {
 			warp_stage_nodes(wide, rows, t.node, live);
-			if (active && !t.template step_staged<COUNT>(rows + lane_id() * kNodeRowF4, lane_id() & 7u, &c_sphere, &c_box)) {
+			if (active && !t.template step_staged<COUNT>(rows + lane_id() * kNodeRowF4, lane_id() & 7u, p.scene.stack_tn_bits, &c_sphere, &c_box)) {
 				p.q.H[idx] = make_float2(t.best, __int_as_float(t.prim));
 				active = false;
 			}
@@ -542,7 +542,7 @@ __global__ void k_tap_trace(const SceneDev sc, const float* __restrict__ rays, c
 		uint32_t cs = 0, cb = 0;
 		if (!shadow) {
 			float best = FLT_MAX; int32_t prim = -1;
-			if (use_bvh) traverse_closest<false>(sc.wide, r, &best, &prim, &cs, &cb);
+			if (use_bvh) traverse_closest<false>(sc.wide, sc.stack_tn_bits, r, &best, &prim, &cs, &cb);
 			else for (uint32_t j = 0; j < sc.n_prims; j++) {
 				const float4 sp = ldg4(sc.prims + j); float d;
 				if (sphere_hit_closest(sp.x, sp.y, sp.z, sp.w, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, &d) && d < best) { best = d; prim = static_cast<int32_t>(j); }

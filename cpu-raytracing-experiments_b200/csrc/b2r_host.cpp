@@ -165,7 +165,7 @@ inline float int_as_float(int32_t v) { float f; std::memcpy(&f, &v, 4); return f
 }  // namespace
 
 void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* prims, uint32_t n_prims, WideBvh& out) {
-	out.nodes.clear(); out.max_stack = 0; out.depth = 0;
+	out.nodes.clear(); out.max_stack = 0; out.depth = 0; out.tn_bits = 31;
 	auto set_empty = [](WideNode& w, int k) { for (int j = 0; j < 8; j++) w.slot[k][j] = 0.0f; w.slot[k][6] = int_as_float(kEmptyLink); };
 	auto set_leaf = [&](WideNode& w, int k, uint32_t prim) {
 		const b2r_sphere& s = prims[prim];
@@ -226,6 +226,8 @@ void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* 
 		need[i] = worst;
 	}
 	out.max_stack = need[0];
+	uint32_t node_bits = 1; while ((1ull << node_bits) < out.nodes.size()) node_bits++;
+	out.tn_bits = 32u - node_bits;
 }
 
 void pack_scene(const b2r_sphere* prims, uint32_t n_prims, const b2r_material* materials, uint32_t n_mat,

@@ -22,6 +22,7 @@ constexpr int kTraversalStack = 64;  // entries per thread; upload fails with B2
 struct WideBvh {
 	std::vector<WideNode> nodes;   // nodes[0] = root, breadth-first (top of the tree is contiguous)
 	uint32_t max_stack = 0;        // worst-case traversal stack occupancy for this tree
+	uint32_t tn_bits = 10;         // low bits of a 32-bit stack entry that carry the entry distance (rest: node index)
 	uint32_t depth = 0;
 };
 

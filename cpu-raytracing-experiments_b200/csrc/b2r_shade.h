@@ -39,6 +39,7 @@ struct SceneDev {
 	const WideNode* wide;       // flattened BVH
 	const float4* hdri;         // equirect RGBA32F or null
 	uint32_t n_prims, n_mat, n_lights;
+	uint32_t stack_tn_bits;     // traversal stack entry split (WideBvh::tn_bits)
 	float light_sel_pdf;        // 1 / n_lights (Renderer.hpp:78)
 	float ambient[3]; int32_t has_ambient;  // Renderer.hpp:79
 	int32_t hdri_w, hdri_h; float hdri_fw, hdri_fh;
@@ -220,18 +221,20 @@ B2R_HD void slab(const float4 a, const float4 b, float ix, float iy, float iz, f
 }
 #define B2R_CSWAP(ka, la, kb, lb) { const bool sw = kb < ka; const uint32_t tk = sw ? kb : ka, tl = sw ? lb : la; kb = sw ? ka : kb; lb = sw ? la : lb; ka = tk; la = tl; }
 
-// Traversal stacks hold one 32-bit word per entry: wide-node index << 10 | the top 10 bits of the (non-negative) entry distance,
-// truncated, i.e. a lower bound that is still good for culling when the entry is popped. The storage is a policy: a plain array
+// Traversal stacks hold one 32-bit word per entry: wide-node index in the high bits, and in the remaining `tn_bits` low bits the
+// leading bits of the (non-negative) entry distance, truncated, i.e. a lower bound that still culls when the entry is popped.
+// tn_bits = 32 - bits needed for a node index (16 at 100k spheres: 8 mantissa bits; 13 at 1M), chosen by the flattener. The storage is a policy: a plain array
 // for whole-ray callers, shared memory with a local-memory overflow in the persistent kernels (a 64-entry per-thread array in
 // local memory made the stack the largest L1/L2 client of the first version — more sectors than the nodes themselves).
-constexpr uint32_t kMaxWideNodes = 1u << 22;
+constexpr uint32_t kMaxWideNodes = 1u << 22;  // leaves >= 10 bits for the distance
 struct ArrayStack {
 	uint32_t e[kTraversalStack];
 	B2R_HD void put(int i, uint32_t v) { e[i] = v; }
 	B2R_HD uint32_t get(int i) const { return e[i]; }
 };
-B2R_HD uint32_t pack_entry(uint32_t node, uint32_t tnear_bits) { return (node << 10) | (tnear_bits >> 21); }
-B2R_HD float entry_tnear(uint32_t e) { return from_bits((e & 0x3ffu) << 21); }
+B2R_HD uint32_t pack_entry(uint32_t node, uint32_t tnear_bits, uint32_t tn_bits) { return (node << tn_bits) | (tnear_bits >> (31u - tn_bits)); }
+B2R_HD float entry_tnear(uint32_t e, uint32_t tn_bits) { return from_bits((e & ((1u << tn_bits) - 1u)) << (31u - tn_bits)); }
+B2R_HD uint32_t entry_node(uint32_t e, uint32_t tn_bits) { return e >> tn_bits; }
 
 struct TravBase {
 	float ox, oy, oz, dx, dy, dz;   // ray
@@ -259,7 +262,7 @@ struct TravClosestT : TravBase {
 	Stack stack;
 	B2R_HD void begin(const Ray& r) { arm(r); best = FLT_MAX; prim = -1; }
 	template <bool COUNT, bool STAGED>
-	B2R_HD bool visit(const float4* n, uint32_t swz, uint32_t* c_sphere, uint32_t* c_box) {
+	B2R_HD bool visit(const float4* n, uint32_t swz, uint32_t tn_bits, uint32_t* c_sphere, uint32_t* c_box) {
 		uint32_t key[4], link[4]; uint32_t leaves = 0u;
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
@@ -288,20 +291,20 @@ struct TravClosestT : TravBase {
 		B2R_CSWAP(key[0], link[0], key[1], link[1]); B2R_CSWAP(key[2], link[2], key[3], link[3]);
 		B2R_CSWAP(key[0], link[0], key[2], link[2]); B2R_CSWAP(key[1], link[1], key[3], link[3]);
 		B2R_CSWAP(key[1], link[1], key[2], link[2]);
-		if (key[3] != 0xffffffffu) stack.put(sp++, pack_entry(link[3], key[3]));
-		if (key[2] != 0xffffffffu) stack.put(sp++, pack_entry(link[2], key[2]));
-		if (key[1] != 0xffffffffu) stack.put(sp++, pack_entry(link[1], key[1]));
+		if (key[3] != 0xffffffffu) stack.put(sp++, pack_entry(link[3], key[3], tn_bits));
+		if (key[2] != 0xffffffffu) stack.put(sp++, pack_entry(link[2], key[2], tn_bits));
+		if (key[1] != 0xffffffffu) stack.put(sp++, pack_entry(link[1], key[1], tn_bits));
 		if (key[0] != 0xffffffffu && from_bits(key[0]) <= best) { node = link[0]; return true; }
 		while (sp > 0) {
 			const uint32_t e = stack.get(--sp);
-			if (entry_tnear(e) <= best) { node = e >> 10; return true; }
+			if (entry_tnear(e, tn_bits) <= best) { node = entry_node(e, tn_bits); return true; }
 		}
 		return false;
 	}
 	template <bool COUNT>
-	B2R_HD bool step(const WideNode* __restrict__ wide, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, false>(reinterpret_cast<const float4*>(wide + node), 0u, c_sphere, c_box); }
+	B2R_HD bool step(const WideNode* __restrict__ wide, uint32_t tn_bits, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, false>(reinterpret_cast<const float4*>(wide + node), 0u, tn_bits, c_sphere, c_box); }
 	template <bool COUNT>
-	B2R_HD bool step_staged(const float4* n, uint32_t swz, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, true>(n, swz, c_sphere, c_box); }
+	B2R_HD bool step_staged(const float4* n, uint32_t swz, uint32_t tn_bits, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, true>(n, swz, tn_bits, c_sphere, c_box); }
 };
 // Any hit along [0, tfar) — Traverse_shadow semantics (BVH.hpp:290-305): an order-independent boolean.
 template <class Stack>
@@ -347,9 +350,9 @@ using TravClosest = TravClosestT<ArrayStack>;
 using TravAny = TravAnyT<ArrayStack>;
 // whole-ray wrappers (trace taps, host check)
 template <bool COUNT>
-B2R_HD void traverse_closest(const WideNode* __restrict__ wide, const Ray& r, float* best_out, int32_t* prim_out, uint32_t* c_sphere, uint32_t* c_box) {
+B2R_HD void traverse_closest(const WideNode* __restrict__ wide, uint32_t tn_bits, const Ray& r, float* best_out, int32_t* prim_out, uint32_t* c_sphere, uint32_t* c_box) {
 	TravClosest t; t.begin(r);
-	while (t.template step<COUNT>(wide, c_sphere, c_box)) {}
+	while (t.template step<COUNT>(wide, tn_bits, c_sphere, c_box)) {}
 	*best_out = t.best; *prim_out = t.prim;
 }
 template <bool COUNT>

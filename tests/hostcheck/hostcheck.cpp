@@ -41,7 +41,7 @@ int hc_render_sample(const b2r_sphere* prims, const b2r_bvh_node* nodes, uint32_
 			counters[0]++;
 			const bool last = bounce + 1 >= max_bounces;
 			float best = FLT_MAX; int32_t prim = -1;
-			if (use_bvh) traverse_closest<false>(sc.wide, Ray{s.ox, s.oy, s.oz, s.dx, s.dy, s.dz}, &best, &prim, &cs, &cb);
+			if (use_bvh) traverse_closest<false>(sc.wide, wide.tn_bits, Ray{s.ox, s.oy, s.oz, s.dx, s.dy, s.dz}, &best, &prim, &cs, &cb);
 			else for (uint32_t j = 0; j < n_prims; j++) {
 				const float4 sp = sc.prims[j]; float d;
 				if (sphere_hit_closest(sp.x, sp.y, sp.z, sp.w, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, &d) && d < best) { best = d; prim = static_cast<int32_t>(j); }
@@ -114,7 +114,7 @@ extern "C" int hc_trace_stats(const b2r_bvh_node* nodes, uint32_t n_nodes, const
 		const float* r = rays + 6 * static_cast<size_t>(i);
 		TravClosest t; t.begin(Ray{r[0], r[1], r[2], r[3], r[4], r[5]});
 		uint32_t cs = 0, cb = 0, st = 0;
-		do { st++; } while (t.step<true>(w.nodes.data(), &cs, &cb));
+		do { st++; } while (t.step<true>(w.nodes.data(), w.tn_bits, &cs, &cb));
 		steps[i] = st; boxes[i] = cb; spheres[i] = cs; prim_out[i] = t.prim;
 	}
 	return 0;

@@ -290,3 +290,22 @@ def test_sky_hdri_scene(flags):
     assert divergent_fraction(g, ref) == 0.0 and g.tobytes() == ref.tobytes()
     assert r.framebuffer.tobytes() == o.render()[1].tobytes()
     r.close()
+
+
+def test_c4_size_oracle_spot_tiles():
+    """BASELINE configs[3] size (1M spheres, 3840x2160, max_bounces 16): one sample, 24 random tiles re-rendered by the oracle in
+    stream-BVH mode. Also exercises the 22-bit node index / 13-bit distance split of the traversal stack entries."""
+    sc = scenes.random_scene(1000000)
+    w, h = 3840, 2160
+    r = b2r.Renderer(sc, w, h, max_bounces=16, buckets=8, samples_in_flight=1); r.Accumulate(1)
+    wide, max_stack = r.wide_nodes()
+    assert max_stack + 3 <= 64 and len(wide) < (1 << 22)
+    o = oracle_for(sc, w, h, 16, 8, flags=oracle_py.ORC_BVH)
+    tiles = np.random.RandomState(4).choice((w // 16) * (h // 16), 24, replace=False).astype(np.uint32)
+    o.accumulate_tiles(tiles, 1)
+    g, ref = r.buckets_host(), o.buckets()
+    idx = (tiles[:, None] * 256 + np.arange(256)[None, :]).ravel()
+    frac = divergent_fraction(g[:, :, idx], ref[:, :, idx])
+    print(f"C4-size spot tiles: divergent pixel fraction {frac:.3e} over {len(idx)} pixels; {len(wide)} wide nodes, stack bound {max_stack}")
+    assert frac < 5e-3
+    r.close()
