@@ -114,6 +114,7 @@ int alloc_frame(b2r_ctx* c) {
 	CU(cudaMemset(c->d_acc, 0, static_cast<size_t>(K) * 3 * npix * sizeof(float)));
 	Params& p = c->params;
 	p.frame.width = w; p.frame.height = h; p.frame.h_tiles = w / 16; p.frame.npix = npix;
+	p.frame.h_tiles_magic = magic_for(w / 16); p.frame.npix_magic = magic_for(npix);
 	p.frame.max_bounces = mb; p.frame.buckets = K; p.frame.flags = c->cfg.flags;
 	for (int s = 0; s < 2; s++) { p.q.A[s] = c->d_A[s]; p.q.B[s] = c->d_B[s]; p.q.T[s] = c->d_T[s]; }
 	p.q.H = c->d_H; p.q.SA = c->d_SA; p.q.SB = c->d_SB; p.q.SL = c->d_SL; p.q.SE = c->d_SE; p.q.cap = static_cast<uint32_t>(cap);

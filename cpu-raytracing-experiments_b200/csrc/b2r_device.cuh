@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 	__shared__ float4 s_table[4][kSmemTable];  // mat_albedo, mat_emission, light_sphere, light_emit
 	__shared__ uint32_t s_hit_i[kQ]; __shared__ float s_hit_t[kQ]; __shared__ int32_t s_hit_prim[kQ];
 	__shared__ float s_hit_d[FIRST ? 3 : 1][FIRST ? kQ : 1];
-	__shared__ uint32_t s_cnt_a[kBruteWarps], s_cnt_b[kBruteWarps], s_base;
+	__shared__ float s_shadow[11][kQ];         // shadow-ray queue: o.xyz, d.xyz, tfar, L.rgb, pid
+	__shared__ uint32_t s_cnt_a[kBruteWarps], s_cnt_b[kBruteWarps], s_cnt_c[kBruteWarps], s_base;
 	SceneDev sc = p.scene;
 	const uint32_t n_in = FIRST ? p.batch->n_slots * p.frame.npix : p.cnt.paths[bounce];
 	const int side = bounce & 1;
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 	}
 	__syncthreads();
 
-	uint32_t queued = 0;                       // hits waiting in shared memory (CTA-uniform)
+	uint32_t queued = 0, s_queued = 0;         // hits / shadow rays waiting in shared memory (CTA-uniform)
 	uint32_t base = blockIdx.x * kBruteBlock;
 	for (;;) {
 		const bool more = base < n_in;         // CTA-uniform
@@ -119,7 +120,8 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 			float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0;
 			if (live) {
 				if (FIRST) {
-					const PathState s0 = primary_path(p.frame, p.batch->acc[i / p.frame.npix], i / p.frame.npix, i % p.frame.npix);
+					const uint32_t sl0 = div_by(i, p.frame.npix, p.frame.npix_magic);
+					const PathState s0 = primary_path(p.frame, p.batch->acc[sl0], sl0, i - sl0 * p.frame.npix);
 					ox = s0.ox; oy = s0.oy; oz = s0.oz; dx = s0.dx; dy = s0.dy; dz = s0.dz;
 				} else {
 					const float4 a = p.q.A[side][i], b = p.q.B[side][i];
@@ -152,7 +154,8 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 			if (live && !is_hit) {  // miss shader (Renderer.hpp:408-420): the path ends, its radiance stays at the pixel
 				c_term++;
 				if (sc.has_ambient) {
-					const PathState sm = FIRST ? primary_path(p.frame, p.batch->acc[i / p.frame.npix], i / p.frame.npix, i % p.frame.npix) : load_path(p.q, side, i);
+					const uint32_t slm = FIRST ? div_by(i, p.frame.npix, p.frame.npix_magic) : 0u;
+					const PathState sm = FIRST ? primary_path(p.frame, p.batch->acc[slm], slm, i - slm * p.frame.npix) : load_path(p.q, side, i);
 					rad_add(p.rad, p.frame.npix, sm.pid, shade_sky(sc, sm), f3{0.0f, 0.0f, 0.0f}, true, false); c_events++;
 				}
 			}
@@ -167,76 +170,105 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 			base += gridDim.x * kBruteBlock;
 			__syncthreads();
 		}
-		// shade only full CTAs of hits (every warp dense), or whatever is left once the rays are exhausted
-		if (queued < static_cast<uint32_t>(kBruteBlock) && more) continue;
-		if (queued == 0) break;
-		// ---------------- phase 2: dense warps shade queued hits (taken from the tail of the queue)
-		const uint32_t take = min(queued, static_cast<uint32_t>(kBruteBlock));
-		const uint32_t qi = queued - take + threadIdx.x;
-		const bool shade = threadIdx.x < take;
-		bool keep = false, want_shadow = false, emissive = false;
-		PathState s; Surface sf; ShadowRay sr; f3 e_add{0.0f, 0.0f, 0.0f};
-		uint32_t acc = 0, seed = 0; float depth = 0.0f; int32_t hprim = -1;
-		if (shade) {
-			const uint32_t hi = s_hit_i[qi]; depth = s_hit_t[qi]; hprim = s_hit_prim[qi];
-			if (FIRST) {
-				const uint32_t sl = hi / p.frame.npix, t = hi - sl * p.frame.npix;
-				s.ox = p.frame.cam.px; s.oy = p.frame.cam.py; s.oz = p.frame.cam.pz;
-				s.dx = s_hit_d[0][FIRST ? qi : 0]; s.dy = s_hit_d[FIRST ? 1 : 0][FIRST ? qi : 0]; s.dz = s_hit_d[FIRST ? 2 : 0][FIRST ? qi : 0];
-				s.tr = s.tg = s.tb = 1.0f; s.pdf = 0.0f; s.pid = (sl << 26) | t;
-			} else s = load_path(p.q, side, hi);
-			acc = p.batch->acc[s.pid >> 26]; seed = pixel_seed(s.pid & kPixMask, p.frame.max_bounces);
-			sf = shade_surface(sc, s, depth, hprim);
-			c_hits++;
-			if (!last) {  // at the last bounce the whole radiance of a surviving hit path is dropped (Q11): nothing to add
-				if (mis) want_shadow = shade_light_sample(sc, sf, s, hprim, acc, seed, bounce, &sr);
-				emissive = sf.emissive;
-				if (emissive) e_add = shade_emission(sc, sf, s, depth, bounce, mis);
+		// ---------------- phase 2: shade queued hits — only full CTAs of them (every warp dense), or the rest once rays run out
+		if (queued >= static_cast<uint32_t>(kBruteBlock) || (!more && queued > 0)) {
+			const uint32_t take = min(queued, static_cast<uint32_t>(kBruteBlock));
+			const uint32_t qi = queued - take + threadIdx.x;
+			const bool shade = threadIdx.x < take;
+			queued -= take;
+			bool keep = false, want_shadow = false;
+			PathState s; ShadowRay sr; uint32_t pid = 0;
+			if (shade) {
+				const uint32_t hi = s_hit_i[qi]; const float depth = s_hit_t[qi]; const int32_t hprim = s_hit_prim[qi];
+				if (FIRST) {
+					const uint32_t sl = div_by(hi, p.frame.npix, p.frame.npix_magic), t = hi - sl * p.frame.npix;
+					s.ox = p.frame.cam.px; s.oy = p.frame.cam.py; s.oz = p.frame.cam.pz;
+					s.dx = s_hit_d[0][FIRST ? qi : 0]; s.dy = s_hit_d[FIRST ? 1 : 0][FIRST ? qi : 0]; s.dz = s_hit_d[FIRST ? 2 : 0][FIRST ? qi : 0];
+					s.tr = s.tg = s.tb = 1.0f; s.pdf = 0.0f; s.pid = (sl << 26) | t;
+				} else s = load_path(p.q, side, hi);
+				pid = s.pid;
+				const uint32_t acc = p.batch->acc[s.pid >> 26], seed = pixel_seed(s.pid & kPixMask, p.frame.max_bounces);
+				const Surface sf = shade_surface(sc, s, depth, hprim);
+				c_hits++;
+				if (last) { rad_zero(p.rad, p.frame.npix, s.pid); c_drop++; }  // survivors of the last bounce lose their radiance (Q11)
+				else {
+					if (mis) want_shadow = shade_light_sample(sc, sf, s, hprim, acc, seed, bounce, &sr);
+					if (sf.emissive) {
+						// light sample first, then emission (Renderer.hpp:304-353). The shadow test of an emissive hit (rare) is done
+						// right here so that order holds; every other shadow ray goes to the queue and is tested by dense warps.
+						const f3 e_add = shade_emission(sc, sf, s, depth, bounce, mis);
+						if (want_shadow) {
+							c_shadow++;
+							bool occluded = false;
+							for (uint32_t j = 0; j < sc.n_prims && !occluded; j++) {
+								const float4 sp = sc.prims[j];  // shared-memory copy when the scene fits one tile, global otherwise
+								occluded = sphere_hit_any(sp.x, sp.y, sp.z, sp.w, sr.o.x, sr.o.y, sr.o.z, sr.d.x, sr.d.y, sr.d.z, sr.tfar);
+							}
+							if (COUNT) c_sphere += sc.n_prims;
+							rad_add(p.rad, p.frame.npix, s.pid, sr.L, e_add, !occluded, true);
+							want_shadow = false;
+						} else rad_add(p.rad, p.frame.npix, s.pid, e_add, f3{0.0f, 0.0f, 0.0f}, true, false);
+						c_events++;
+					}
+					keep = shade_continue(sf, &s, acc, seed, bounce);
+					if (!keep) c_term++;  // roulette: path ends here, radiance stays at the pixel (Renderer.hpp:379-381,424-430)
+				}
 			}
-		}
-		queued -= take;
-		// shadow ray: any hit along [0, tfar) (BVH.hpp:290-305)
-		if (n_tiles == 1) {
+			// shadow rays -> shared-memory queue; survivors -> next path queue (one atomic per CTA)
+			uint32_t n_shadow, n_keep;
+			const uint32_t sslot = s_queued + block_rank(want_shadow, s_cnt_c, &n_shadow);  // barrier: hit-queue reads above precede the next phase 1
+			const uint32_t rank = block_rank(keep, s_cnt_b, &n_keep);
 			if (want_shadow) {
+				s_shadow[0][sslot] = sr.o.x; s_shadow[1][sslot] = sr.o.y; s_shadow[2][sslot] = sr.o.z;
+				s_shadow[3][sslot] = sr.d.x; s_shadow[4][sslot] = sr.d.y; s_shadow[5][sslot] = sr.d.z; s_shadow[6][sslot] = sr.tfar;
+				s_shadow[7][sslot] = sr.L.x; s_shadow[8][sslot] = sr.L.y; s_shadow[9][sslot] = sr.L.z; s_shadow[10][sslot] = __uint_as_float(pid);
+			}
+			s_queued += n_shadow;
+			if (threadIdx.x == 0) s_base = n_keep ? atomicAdd(p.cnt.paths + bounce + 1, n_keep) : 0u;
+			__syncthreads();
+			if (keep) store_path(p.q, side ^ 1, s_base + rank, s);
+		}
+		// ---------------- phase 3: any-hit test of queued shadow rays (BVH.hpp:290-305), again a full CTA at a time
+		const bool drained = !more && queued == 0;
+		if (s_queued >= static_cast<uint32_t>(kBruteBlock) || (drained && s_queued > 0)) {
+			const uint32_t take = min(s_queued, static_cast<uint32_t>(kBruteBlock));
+			const uint32_t qi = s_queued - take + threadIdx.x;
+			const bool test = threadIdx.x < take;
+			s_queued -= take;
+			float sox = 0, soy = 0, soz = 0, sdx = 0, sdy = 0, sdz = 0, stfar = 0; f3 L{0.0f, 0.0f, 0.0f}; uint32_t spid = 0;
+			if (test) {
+				sox = s_shadow[0][qi]; soy = s_shadow[1][qi]; soz = s_shadow[2][qi]; sdx = s_shadow[3][qi]; sdy = s_shadow[4][qi]; sdz = s_shadow[5][qi];
+				stfar = s_shadow[6][qi]; L = f3{s_shadow[7][qi], s_shadow[8][qi], s_shadow[9][qi]}; spid = __float_as_uint(s_shadow[10][qi]);
 				c_shadow++;
-				if (COUNT) c_sphere += sc.n_prims;
+			}
+			bool occluded = !test;
+			if (n_tiles == 1) {
+				if (COUNT && test) c_sphere += sc.n_prims;
 #pragma unroll 3
 				for (uint32_t j = 0; j < sc.n_prims; j++) {
 					const float4 sp = s_prim[j];
-					if (sphere_hit_any(sp.x, sp.y, sp.z, sp.w, sr.o.x, sr.o.y, sr.o.z, sr.d.x, sr.d.y, sr.d.z, sr.tfar)) { want_shadow = false; break; }
+					if (!occluded && sphere_hit_any(sp.x, sp.y, sp.z, sp.w, sox, soy, soz, sdx, sdy, sdz, stfar)) occluded = true;
+					if (__all_sync(0xffffffffu, occluded)) break;
 				}
-			}
-		} else {
-			if (want_shadow) c_shadow++;
-			for (uint32_t tile = 0; tile < n_tiles; tile++) {
-				const uint32_t first = tile * kBruteTile, cnt = min(static_cast<uint32_t>(kBruteTile), sc.n_prims - first);
-				__syncthreads();
-				for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) s_prim[j] = p.scene.prims[first + j];
-				__syncthreads();
-				if (want_shadow) {
-					if (COUNT) c_sphere += cnt;
-					for (uint32_t j = 0; j < cnt; j++) {
-						const float4 sp = s_prim[j];
-						if (sphere_hit_any(sp.x, sp.y, sp.z, sp.w, sr.o.x, sr.o.y, sr.o.z, sr.d.x, sr.d.y, sr.d.z, sr.tfar)) { want_shadow = false; break; }
+			} else {
+				for (uint32_t tile = 0; tile < n_tiles; tile++) {
+					const uint32_t first = tile * kBruteTile, cnt = min(static_cast<uint32_t>(kBruteTile), sc.n_prims - first);
+					__syncthreads();
+					for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) s_prim[j] = p.scene.prims[first + j];
+					__syncthreads();
+					if (!occluded) {
+						if (COUNT) c_sphere += cnt;
+						for (uint32_t j = 0; j < cnt && !occluded; j++) {
+							const float4 sp = s_prim[j];
+							occluded = sphere_hit_any(sp.x, sp.y, sp.z, sp.w, sox, soy, soz, sdx, sdy, sdz, stfar);
+						}
 					}
 				}
 			}
+			if (test && !occluded) { rad_add(p.rad, p.frame.npix, spid, L, f3{0.0f, 0.0f, 0.0f}, true, false); c_events++; }
+			__syncthreads();  // shadow-queue reads above precede the next phase 2 writes
 		}
-		// contributions: unoccluded light sample first, then emission (order of Renderer.hpp:304-353); then the next segment
-		if (shade) {
-			if (last) { rad_zero(p.rad, p.frame.npix, s.pid); c_drop++; }
-			else {
-				if (want_shadow || emissive) { rad_add(p.rad, p.frame.npix, s.pid, sr.L, e_add, want_shadow, emissive); c_events++; }
-				keep = shade_continue(sf, &s, acc, seed, bounce);
-				if (!keep) c_term++;  // roulette: path ends here, radiance stays at the pixel (Renderer.hpp:379-381,424-430)
-			}
-		}
-		// ---------------- append the survivors to the next queue: one atomic per CTA
-		uint32_t n_keep;
-		const uint32_t rank = block_rank(keep, s_cnt_b, &n_keep);  // its barrier also orders the queue reads above before the next phase 1 writes
-		if (threadIdx.x == 0) s_base = n_keep ? atomicAdd(p.cnt.paths + bounce + 1, n_keep) : 0u;
-		__syncthreads();
-		if (keep) store_path(p.q, side ^ 1, s_base + rank, s);
+		if (drained && s_queued == 0) break;
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.cnt.stats + ST_EXT, static_cast<unsigned long long>(n_in));
 	stat_add(p.cnt.stats, ST_SHADOW, c_shadow); stat_add(p.cnt.stats, ST_HITS, c_hits); stat_add(p.cnt.stats, ST_TERM, c_term);
@@ -248,7 +280,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 __global__ void __launch_bounds__(kBlock) k_generate(const Params p) {
 	const uint32_t n = p.batch->n_slots * p.frame.npix;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-		store_path(p.q, 0, i, primary_path(p.frame, p.batch->acc[i / p.frame.npix], i / p.frame.npix, i % p.frame.npix));
+		{ const uint32_t sl = div_by(i, p.frame.npix, p.frame.npix_magic); store_path(p.q, 0, i, primary_path(p.frame, p.batch->acc[sl], sl, i - sl * p.frame.npix)); }
 	if (blockIdx.x == 0 && threadIdx.x == 0) p.cnt.paths[0] = n;
 }
 // Work distribution of the traversal kernels: every warp owns a pool of ray indices claimed kTravChunk at a time from the
@@ -517,7 +549,7 @@ __global__ void __launch_bounds__(kBlock) k_resolve(const FrameDev frame, const 
 		float g = scale * median_buckets_at(bp, K, npix + t);
 		float b = scale * median_buckets_at(bp, K, 2u * npix + t);
 		if (tonemap) aces_tonemap(&r, &g, &b);
-		int32_t x, y; pixel_xy(t, frame.h_tiles, &x, &y);
+		int32_t x, y; pixel_xy(t, frame, &x, &y);
 		fb[static_cast<size_t>(y) * frame.width + x] = make_float4(r, g, b, 1.0f);
 	}
 }
@@ -527,7 +559,7 @@ __global__ void k_tap_generate(const Params p, const uint32_t acc, float* __rest
 	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < p.frame.npix; t += gridDim.x * blockDim.x) {
 		Pcg rng{hash_2d(acc, pixel_seed(t, p.frame.max_bounces))};
 		const float s0 = rng.next_unit(), s1 = rng.next_unit();
-		int32_t x, y; pixel_xy(t, p.frame.h_tiles, &x, &y);
+		int32_t x, y; pixel_xy(t, p.frame, &x, &y);
 		const f3 d = camera_dir(p.frame.cam, x, y, s0, s1);
 		float* o = out + static_cast<size_t>(t) * 6u;
 		o[0] = p.frame.cam.px; o[1] = p.frame.cam.py; o[2] = p.frame.cam.pz; o[3] = d.x; o[4] = d.y; o[5] = d.z;

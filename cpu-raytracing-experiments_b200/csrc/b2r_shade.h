@@ -48,7 +48,19 @@ struct FrameDev {
 	CameraParams cam;
 	uint32_t width, height, h_tiles, npix;
 	uint32_t max_bounces, buckets, flags;
+	uint32_t h_tiles_magic, npix_magic;  // floor(2^32 / d) for div_by()
 };
+// x / d for a launch-constant divisor without the ~20-instruction integer division: q = mulhi(x, floor(2^32/d)) is q or q-1.
+B2R_HD uint32_t div_by(uint32_t x, uint32_t d, uint32_t magic) {
+#if defined(__CUDA_ARCH__)
+	uint32_t q = __umulhi(x, magic);
+#else
+	uint32_t q = static_cast<uint32_t>((static_cast<uint64_t>(x) * magic) >> 32);
+#endif
+	if (x - q * d >= d) q++;
+	return q;
+}
+B2R_HD uint32_t magic_for(uint32_t d) { return d <= 1u ? 0xffffffffu : static_cast<uint32_t>((1ull << 32) / d); }
 struct BatchDev {  // one wavefront batch: n_slots samples traced together
 	uint32_t n_slots;
 	uint32_t acc[kMaxSlots];  // sample index (the reference's `accumulations` value, Q1) of each slot
@@ -75,10 +87,11 @@ struct Params {
 
 // ---------------------------------------------------------------------------------------------- small helpers
 // tile-order pixel index -> pixel coordinates (Renderer.hpp:85-88,114-115)
-B2R_HD void pixel_xy(uint32_t t, uint32_t h_tiles, int32_t* x, int32_t* y) {
+B2R_HD void pixel_xy(uint32_t t, const FrameDev& fr, int32_t* x, int32_t* y) {
 	const uint32_t tile = t >> 8, id = t & 255u;
-	*x = static_cast<int32_t>((tile % h_tiles) * 16u + (id & 15u));
-	*y = static_cast<int32_t>((tile / h_tiles) * 16u + (id >> 4));
+	const uint32_t ty = div_by(tile, fr.h_tiles, fr.h_tiles_magic), tx = tile - ty * fr.h_tiles;
+	*x = static_cast<int32_t>(tx * 16u + (id & 15u));
+	*y = static_cast<int32_t>(ty * 16u + (id >> 4));
 }
 
 struct PathState { float ox, oy, oz, dx, dy, dz, tr, tg, tb, pdf; uint32_t pid; };
@@ -87,7 +100,7 @@ struct PathState { float ox, oy, oz, dx, dy, dz, tr, tg, tb, pdf; uint32_t pid; 
 B2R_HD PathState primary_path(const FrameDev& fr, uint32_t acc, uint32_t slot, uint32_t t) {
 	Pcg rng{hash_2d(acc, pixel_seed(t, fr.max_bounces))};
 	const float s0 = rng.next_unit(), s1 = rng.next_unit();
-	int32_t x, y; pixel_xy(t, fr.h_tiles, &x, &y);
+	int32_t x, y; pixel_xy(t, fr, &x, &y);
 	const f3 d = camera_dir(fr.cam, x, y, s0, s1);
 	PathState s;
 	s.ox = fr.cam.px; s.oy = fr.cam.py; s.oz = fr.cam.pz; s.dx = d.x; s.dy = d.y; s.dz = d.z;

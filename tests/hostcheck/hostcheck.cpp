@@ -29,7 +29,7 @@ int hc_render_sample(const b2r_sphere* prims, const b2r_bvh_node* nodes, uint32_
 	sc.n_prims = n_prims; sc.n_mat = n_mat; sc.n_lights = n_lights; sc.light_sel_pdf = 1.0f / static_cast<float>(n_lights); sc.has_ambient = 0;
 	FrameDev fr{};
 	fr.cam = CameraParams{cam11[0], cam11[1], cam11[2], cam11[3], cam11[4], cam11[5], cam11[6], cam11[7], cam11[8], cam11[9], cam11[10]};
-	fr.width = width; fr.height = height; fr.h_tiles = width / 16; fr.npix = width * height; fr.max_bounces = max_bounces; fr.buckets = 1; fr.flags = flags;
+	fr.width = width; fr.height = height; fr.h_tiles = width / 16; fr.npix = width * height; fr.h_tiles_magic = magic_for(fr.h_tiles); fr.npix_magic = magic_for(fr.npix); fr.max_bounces = max_bounces; fr.buckets = 1; fr.flags = flags;
 	const bool mis = !(flags & B2R_FLAG_NO_MIS);
 	std::memset(rad_out, 0, sizeof(float) * 3 * fr.npix);
 	for (int k = 0; k < 5; k++) counters[k] = 0;
