@@ -363,6 +363,8 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_cpu = 8 if wl["scene"] == "default" else 1
+        if wl["scene"] == "default":
+            cpu_oracle_run(wl, scene, 2, workload_name=args.workload)  # untimed warm-up: thread start-up, CPU clocks, caches
         c = cpu_oracle_run(wl, scene, n_cpu, workload_name=args.workload)
         cpu = {"value": c["rays"] / c["seconds"] / 1e6, "unit": UNIT, "cores": c["threads"], "kind": "port",
                "sample": f"{c['what']} ({c['paths']} paths, {c['rays']} rays) in {c['seconds']:.2f} s; oracle port -O3 -march=native, {c['mode']}",
