@@ -58,7 +58,7 @@ struct b2r_ctx {
 	WideBvh wide_host; uint64_t wide_key = 0; bool have_wide = false;
 	// frame
 	float4 *d_A[2] = {nullptr, nullptr}, *d_B[2] = {nullptr, nullptr}, *d_SA = nullptr, *d_SB = nullptr, *d_fb = nullptr;
-	float *d_T[2] = {nullptr, nullptr}, *d_SL = nullptr, *d_SE = nullptr, *d_rad = nullptr, *d_acc = nullptr;
+	float *d_T[2] = {nullptr, nullptr}, *d_SL = nullptr, *d_rad = nullptr, *d_acc = nullptr;
 	float2* d_H = nullptr;
 	uint32_t* d_counts = nullptr; size_t counts_bytes = 0;
 	unsigned long long* d_stats = nullptr;
@@ -102,7 +102,6 @@ int alloc_frame(b2r_ctx* c) {
 	if ((rc = dev_alloc(&c->d_SA, cap))) return rc;
 	if ((rc = dev_alloc(&c->d_SB, cap))) return rc;
 	if ((rc = dev_alloc(&c->d_SL, 3 * cap))) return rc;
-	if ((rc = dev_alloc(&c->d_SE, 3 * cap))) return rc;
 	if ((rc = dev_alloc(&c->d_rad, 3 * cap))) return rc;
 	if ((rc = dev_alloc(&c->d_acc, static_cast<size_t>(K) * 3 * npix))) return rc;
 	if ((rc = dev_alloc(&c->d_fb, static_cast<size_t>(npix)))) return rc;
@@ -117,7 +116,7 @@ int alloc_frame(b2r_ctx* c) {
 	p.frame.h_tiles_magic = magic_for(w / 16); p.frame.npix_magic = magic_for(npix);
 	p.frame.max_bounces = mb; p.frame.buckets = K; p.frame.flags = c->cfg.flags;
 	for (int s = 0; s < 2; s++) { p.q.A[s] = c->d_A[s]; p.q.B[s] = c->d_B[s]; p.q.T[s] = c->d_T[s]; }
-	p.q.H = c->d_H; p.q.SA = c->d_SA; p.q.SB = c->d_SB; p.q.SL = c->d_SL; p.q.SE = c->d_SE; p.q.cap = static_cast<uint32_t>(cap);
+	p.q.H = c->d_H; p.q.SA = c->d_SA; p.q.SB = c->d_SB; p.q.SL = c->d_SL; p.q.cap = static_cast<uint32_t>(cap);
 	p.cnt.paths = c->d_counts; p.cnt.shadow = c->d_counts + (mb + 1); p.cnt.work_a = c->d_counts + 2 * (mb + 1); p.cnt.work_b = c->d_counts + 3 * (mb + 1);
 	p.cnt.stats = c->d_stats;
 	p.batch = c->d_batch; p.rad = c->d_rad; p.acc = c->d_acc;
@@ -271,7 +270,7 @@ void b2r_destroy(b2r_ctx* c) {
 	dev_free(&c->d_prims); dev_free(&c->d_mat_albedo); dev_free(&c->d_mat_emission); dev_free(&c->d_light_sphere); dev_free(&c->d_light_emit);
 	dev_free(&c->d_hdri); dev_free(&c->d_prim_mat); dev_free(&c->d_wide);
 	for (int s = 0; s < 2; s++) { dev_free(&c->d_A[s]); dev_free(&c->d_B[s]); dev_free(&c->d_T[s]); }
-	dev_free(&c->d_H); dev_free(&c->d_SA); dev_free(&c->d_SB); dev_free(&c->d_SL); dev_free(&c->d_SE); dev_free(&c->d_rad); dev_free(&c->d_acc); dev_free(&c->d_fb);
+	dev_free(&c->d_H); dev_free(&c->d_SA); dev_free(&c->d_SB); dev_free(&c->d_SL); dev_free(&c->d_rad); dev_free(&c->d_acc); dev_free(&c->d_fb);
 	dev_free(&c->d_counts); dev_free(&c->d_stats); dev_free(&c->d_batch);
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
 	delete c;

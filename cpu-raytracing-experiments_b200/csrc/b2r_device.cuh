@@ -7,7 +7,7 @@
 //     pixel's tile-order index (tile*256 + ID) and slot the sample-in-flight index inside the batch.
 //   radiance RAD[(slot*3 + c)*npix + t]: a path's running radiance lives at its pixel (one path per pixel per sample)
 //     and is touched only when a contribution arrives (unoccluded light sample, emissive hit, sky).
-//   hit queue H[i] = {tfar, as_float(prim)} and shadow queue SA/SB/SL/SE (ray, light-sample radiance, pending emission): BVH pipeline only.
+//   hit queue H[i] = {tfar, as_float(prim)} and shadow queue SA/SB/SL (ray, light-sample radiance): BVH pipeline only.
 //   buckets ACC[(k*3 + c)*npix + t]: running sums per median-of-means bucket (AccumulationTile, Renderer.hpp:43-46).
 // All kernels are persistent (grid = SM count x resident CTAs, looping over a device-side count), so a whole batch —
 // max_bounces rounds — is enqueued, or replayed as one CUDA graph, without host synchronisation.
@@ -286,7 +286,10 @@ __global__ void __launch_bounds__(kBlock) k_generate(const Params p) {
 // Work distribution of the traversal kernels: every warp owns a pool of ray indices claimed kTravChunk at a time from the
 // bounce's cursor (one atomic per chunk); lanes whose ray has finished are refilled from the pool as soon as fewer than
 // kRefillBelow lanes of the warp are still traversing, so a warp never idles behind its longest ray.
-constexpr uint32_t kTravChunk = 128, kRefillBelow = 24;
+#ifndef B2R_REFILL_BELOW
+#define B2R_REFILL_BELOW 24
+#endif
+constexpr uint32_t kTravChunk = 128, kRefillBelow = B2R_REFILL_BELOW;
 struct WarpPool {
 	uint32_t next = 0, end = 0; bool dry = false;  // warp-uniform
 	// hands ray indices to the lanes flagged `idle`; returns the lane's index or 0xffffffff
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_shade(con
 	const int side = bounce & 1;
 	const bool mis = !(p.frame.flags & B2R_FLAG_NO_MIS);
 	const bool last = bounce + 1 >= p.frame.max_bounces;
-	uint32_t c_hits = 0, c_term = 0, c_drop = 0, c_events = 0;
+	uint32_t c_hits = 0, c_term = 0, c_drop = 0, c_events = 0, c_inline_shadow = 0;
 	uint32_t queued = 0, base = blockIdx.x * kBruteBlock;
 	for (;;) {
 		const bool more = base < n_in;
@@ -410,7 +413,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_shade(con
 		const uint32_t qi = queued - take + threadIdx.x;
 		const bool shade = threadIdx.x < take;
 		queued -= take;
-		bool keep = false, want_shadow = false; ShadowRay sr; PathState s; uint32_t pid = 0; f3 emit{0.0f, 0.0f, 0.0f};
+		bool keep = false, want_shadow = false; ShadowRay sr; PathState s; uint32_t pid = 0;
 		if (shade) {
 			const uint32_t hi = s_hit_i[qi]; const float depth = s_hit_t[qi]; const int32_t prim = s_hit_prim[qi];
 			s = load_path(p.q, side, hi); pid = s.pid;
@@ -421,10 +424,17 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_shade(con
 			else {
 				if (mis) want_shadow = shade_light_sample(sc, sf, s, prim, acc, seed, bounce, &sr);
 				if (sf.emissive) {
-					// the reference adds the light sample first, then the emission (Renderer.hpp:304-353): when a shadow ray is
-					// pending the emission travels with it and k_intersect_shadow adds both in that order
-					emit = shade_emission(sc, sf, s, depth, bounce, mis);
-					if (!want_shadow) { rad_add(p.rad, p.frame.npix, s.pid, emit, f3{0.0f, 0.0f, 0.0f}, true, false); c_events++; }
+					// the reference adds the light sample first, then the emission (Renderer.hpp:304-353). For the (rare) emissive hit
+					// that also has a shadow ray the any-hit traversal is done right here so that order holds; every other shadow ray
+					// goes to the shadow queue and is traced by k_intersect_shadow.
+					const f3 emit = shade_emission(sc, sf, s, depth, bounce, mis);
+					if (want_shadow) {
+						uint32_t cs = 0, cb = 0;
+						const bool occluded = traverse_any<false>(sc.wide, Ray{sr.o.x, sr.o.y, sr.o.z, sr.d.x, sr.d.y, sr.d.z}, sr.tfar, &cs, &cb);
+						rad_add(p.rad, p.frame.npix, s.pid, sr.L, emit, !occluded, true);
+						want_shadow = false; c_inline_shadow++;
+					} else rad_add(p.rad, p.frame.npix, s.pid, emit, f3{0.0f, 0.0f, 0.0f}, true, false);
+					c_events++;
 				}
 				keep = shade_continue(sf, &s, acc, seed, bounce);
 				if (!keep) c_term++;
@@ -443,12 +453,11 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_shade(con
 			p.q.SA[d] = make_float4(sr.o.x, sr.o.y, sr.o.z, sr.d.x);
 			p.q.SB[d] = make_float4(sr.d.y, sr.d.z, sr.tfar, __uint_as_float(pid));
 			p.q.SL[d] = sr.L.x; p.q.SL[p.q.cap + d] = sr.L.y; p.q.SL[2u * p.q.cap + d] = sr.L.z;
-			p.q.SE[d] = emit.x; p.q.SE[p.q.cap + d] = emit.y; p.q.SE[2u * p.q.cap + d] = emit.z;
 		}
 		if (keep) store_path(p.q, side ^ 1, s_base + rank, s);
 	}
 	stat_add(p.cnt.stats, ST_HITS, c_hits); stat_add(p.cnt.stats, ST_TERM, c_term);
-	stat_add(p.cnt.stats, ST_DROPPED, c_drop); stat_add(p.cnt.stats, ST_EVENTS, c_events);
+	stat_add(p.cnt.stats, ST_DROPPED, c_drop); stat_add(p.cnt.stats, ST_EVENTS, c_events); stat_add(p.cnt.stats, ST_SHADOW, c_inline_shadow);
 }
 // shadow rays of this bounce: any-hit traversal, unoccluded light samples are added to the pixel's radiance
 template <bool COUNT>
@@ -474,11 +483,9 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_shadow(const Params p,
 		do {
 			warp_stage_nodes(wide, rows, t.node, live);
 			if (active && !t.template step_staged<COUNT>(rows + lane_id() * kNodeRowF4, lane_id() & 7u, &c_sphere, &c_box)) {
-				const f3 E{p.q.SE[idx], p.q.SE[p.q.cap + idx], p.q.SE[2u * p.q.cap + idx]};  // emission of the same hit (usually 0)
-				const bool has_e = E.x != 0.0f || E.y != 0.0f || E.z != 0.0f;
-				if (!t.occluded || has_e) {
-					const f3 L = t.occluded ? f3{0.0f, 0.0f, 0.0f} : f3{p.q.SL[idx], p.q.SL[p.q.cap + idx], p.q.SL[2u * p.q.cap + idx]};
-					rad_add(p.rad, p.frame.npix, pid, L, E, !t.occluded, has_e); c_events++;
+				if (!t.occluded) {
+					const f3 L{p.q.SL[idx], p.q.SL[p.q.cap + idx], p.q.SL[2u * p.q.cap + idx]};
+					rad_add(p.rad, p.frame.npix, pid, L, f3{0.0f, 0.0f, 0.0f}, true, false); c_events++;
 				}
 				active = false;
 			}

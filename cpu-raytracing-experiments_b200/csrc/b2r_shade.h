@@ -68,7 +68,7 @@ struct BatchDev {  // one wavefront batch: n_slots samples traced together
 struct QueueDev {
 	float4* A[2]; float4* B[2]; float* T[2];
 	float2* H;
-	float4* SA; float4* SB; float* SL; float* SE;
+	float4* SA; float4* SB; float* SL;
 	uint32_t cap;
 };
 struct CountDev {            // zeroed at the start of every batch; index = bounce
