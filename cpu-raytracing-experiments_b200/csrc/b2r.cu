@@ -87,8 +87,8 @@ void drop_graph(b2r_ctx* c) {
 
 int alloc_frame(b2r_ctx* c) {
 	const uint32_t w = c->cfg.width, h = c->cfg.height, npix = w * h, mb = c->cfg.max_bounces, K = c->cfg.buckets;
-	if (c->cfg.samples_in_flight == 0) {  // default: about 64M paths per wavefront batch (keeps the late, thin bounces a small share)
-		uint32_t s = (64u << 20) / npix; c->slots = s < 4u ? 4u : s > 32u ? 32u : s;
+	if (c->cfg.samples_in_flight == 0) {  // default: about 128M paths per wavefront batch (keeps the late, thin bounces a small share)
+		uint32_t s = (128u << 20) / npix; c->slots = s < 4u ? 4u : s > static_cast<uint32_t>(kMaxSlots) ? static_cast<uint32_t>(kMaxSlots) : s;
 	}
 	const size_t cap = static_cast<size_t>(c->slots) * npix;
 	if (cap >= (1ull << 32)) return fail(B2R_ERR_ARG, "samples_in_flight * pixels exceeds the 32-bit queue index");

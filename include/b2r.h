@@ -64,7 +64,7 @@ typedef struct b2r_config {
 	int32_t  device;             /* CUDA ordinal */
 	uint32_t bucket_first;       /* multi-GPU: this context renders the samples whose bucket b = acc % buckets */
 	uint32_t bucket_stride;      /*            satisfies b % bucket_stride == bucket_first (0/1 => all)   */
-	uint32_t samples_in_flight;  /* samples traced together per wavefront batch (<= 64); 0 = auto (~64M paths, 4..32) */
+	uint32_t samples_in_flight;  /* samples traced together per wavefront batch (<= 64); 0 = auto (~128M paths, 4..64) */
 } b2r_config;
 
 enum {
