@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 	const bool mis = !(p.frame.flags & B2R_FLAG_NO_MIS);
 	const bool last = bounce + 1 >= p.frame.max_bounces;
 	uint32_t c_shadow = 0, c_hits = 0, c_term = 0, c_drop = 0, c_events = 0, c_sphere = 0;
+	if (blockIdx.x * kBruteBlock >= n_in) return;  // thin late bounces: CTAs without a first chunk leave before staging anything
 
 	// stage the scene tables once per CTA (persistent: amortised over the whole launch)
 	if (n_tiles == 1) {
@@ -387,6 +388,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_shade(con
 	const bool mis = !(p.frame.flags & B2R_FLAG_NO_MIS);
 	const bool last = bounce + 1 >= p.frame.max_bounces;
 	uint32_t c_hits = 0, c_term = 0, c_drop = 0, c_events = 0, c_inline_shadow = 0;
+	if (blockIdx.x * kBruteBlock >= n_in) return;
 	uint32_t queued = 0, base = blockIdx.x * kBruteBlock;
 	for (;;) {
 		const bool more = base < n_in;

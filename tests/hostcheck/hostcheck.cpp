@@ -119,3 +119,18 @@ extern "C" int hc_trace_stats(const b2r_bvh_node* nodes, uint32_t n_nodes, const
 	}
 	return 0;
 }
+
+// histogram of visited wide-node indices below `top` (BFS order: the first nodes are the top of the tree): tuning aid
+extern "C" int hc_trace_top_share(const b2r_sphere* prims, uint32_t n_prims, const float* rays, uint32_t n, uint32_t top, uint64_t* visits_top, uint64_t* visits_all) {
+	std::vector<b2r_bvh_node> tn; build_traversal_tree(prims, n_prims, tn);
+	WideBvh w; flatten_bvh(tn.data(), static_cast<uint32_t>(tn.size()), prims, n_prims, w);
+	uint64_t a = 0, b = 0;
+	for (uint32_t i = 0; i < n; i++) {
+		const float* r = rays + 6 * static_cast<size_t>(i);
+		TravClosest t; t.begin(Ray{r[0], r[1], r[2], r[3], r[4], r[5]});
+		uint32_t cs = 0, cb = 0; bool more = true;
+		while (more) { b++; if (t.node < top) a++; more = t.step<false>(w.nodes.data(), w.tn_bits, &cs, &cb); }
+	}
+	*visits_top = a; *visits_all = b;
+	return 0;
+}

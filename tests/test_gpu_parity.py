@@ -309,3 +309,24 @@ def test_c4_size_oracle_spot_tiles():
     print(f"C4-size spot tiles: divergent pixel fraction {frac:.3e} over {len(idx)} pixels; {len(wide)} wide nodes, stack bound {max_stack}")
     assert frac < 5e-3
     r.close()
+
+
+def test_randomised_configurations_bit_exact():
+    """Fuzz: random scenes (sizes on both sides of the brute/BVH switch), cameras, image sizes, bucket counts, bounce limits,
+    batch widths and starting sample indices — bucket sums must equal the oracle's bit for bit every time."""
+    rs = np.random.RandomState(20261018)
+    for trial in range(12):
+        n = int(rs.choice([3, 9, 31, 32, 33, 60, 200, 700]))
+        sc = scenes.random_scene(n, light_every=int(rs.randint(1, max(2, n // 2))), seed=int(rs.randint(1, 2 ** 31)))
+        eye = rs.uniform([-150, 10, 150], [150, 90, 320]); look = np.array([0.0, 40.0, 0.0]) - eye
+        sc["camera"] = dict(eye=tuple(eye), dir=tuple(look), focal_length=float(rs.uniform(20, 80)), exposure=float(rs.uniform(0.5, 2.0)))
+        if rs.rand() < 0.4:
+            sc["ambient"] = tuple(rs.uniform(0.0, 1.0, 3)); sc["hdri"] = scenes.synthetic_hdri(int(rs.randint(1, 40)), int(rs.randint(1, 20)), seed=trial)
+        w, h = 16 * int(rs.randint(1, 9)), 16 * int(rs.randint(1, 7))
+        K, mb, sif = int(rs.randint(1, 10)), int(rs.randint(1, 20)), int(rs.randint(1, 9))
+        start, samples = int(rs.randint(0, 5000)), int(rs.randint(1, 12))
+        r = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=K, samples_in_flight=sif); r.accumulations = start; r.Accumulate(samples)
+        o = oracle_for(sc, w, h, mb, K); o.set_accumulations(start); o.accumulate(samples)
+        g, ref = r.buckets_host(), o.buckets()
+        assert g.tobytes() == ref.tobytes(), dict(trial=trial, n=n, w=w, h=h, K=K, mb=mb, sif=sif, start=start, samples=samples, frac=divergent_fraction(g, ref))
+        r.close()
