@@ -359,16 +359,18 @@ def main():
             except Exception:
                 pass
 
-    # ---- CPU baseline beside it (rank 0, N=1 only): oracle port on a bounded sample of the same workload
+    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample of the same workload, on the box's host
+    # cores. Run as a fresh `bench.py --impl reference` process so that its threads see the same conditions as the reference arm
+    # the driver launches (inside this process, after CUDA/torch start-up, the same code ran at about half the speed).
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_cpu = 8 if wl["scene"] == "default" else 1
-        if wl["scene"] == "default":
-            cpu_oracle_run(wl, scene, 2, workload_name=args.workload)  # untimed warm-up: thread start-up, CPU clocks, caches
-        c = cpu_oracle_run(wl, scene, n_cpu, workload_name=args.workload)
-        cpu = {"value": c["rays"] / c["seconds"] / 1e6, "unit": UNIT, "cores": c["threads"], "kind": "port",
-               "sample": f"{c['what']} ({c['paths']} paths, {c['rays']} rays) in {c['seconds']:.2f} s; oracle port -O3 -march=native, {c['mode']}",
-               "paths_per_s": c["paths"] / c["seconds"]}
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload, "--steps", "2", "--warmup", "1"],
+                                 capture_output=True, text=True, timeout=900).stdout.strip().splitlines()[-1]
+            ref = json.loads(out)
+            cpu = dict(ref["cpu_baseline"]); cpu["paths_per_s"] = ref.get("paths_per_s")
+        except Exception as e:  # never let the baseline leg break the GPU line
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
 
     if rank == 0:
         line = {
