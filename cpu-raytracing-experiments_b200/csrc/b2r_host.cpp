@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstring>
 #include <numeric>
+#include <cstdio>
 
 namespace b2r {
 namespace {
@@ -378,3 +379,46 @@ void build_traversal_tree(const b2r_sphere* prims, uint32_t n, std::vector<b2r_b
 	}
 }
 }  // namespace b2r
+
+// ---------------------------------------------------------------------------------------------- frame output
+// Image::Store (Image.cpp:71-74): stbi_flip_vertically_on_write(true); stbi_write_hdr(path, w, h, 4, rgba). The file format is
+// the published Radiance RGBE format with per-scanline run-length encoding; the mantissa/exponent split follows stb's
+// linear_to_rgbe (frexp of the largest channel, truncating conversion).
+extern "C" int b2r_write_hdr(const char* path, const float* rgba, uint32_t width, uint32_t height) {
+	if (!path || !rgba || width == 0 || height == 0) return B2R_ERR_ARG;
+	FILE* f = std::fopen(path, "wb");
+	if (!f) return B2R_ERR_ARG;
+	std::fprintf(f, "#?RADIANCE\n# Written by libb2r\nFORMAT=32-bit_rle_rgbe\n\nEXPOSURE=          1.0000000000000\n\n-Y %u +X %u\n", height, width);
+	std::vector<unsigned char> rgbe(static_cast<size_t>(width) * 4), line;
+	for (uint32_t row = 0; row < height; row++) {
+		const float* src = rgba + static_cast<size_t>(height - 1 - row) * width * 4;  // vertical flip
+		for (uint32_t x = 0; x < width; x++) {
+			const float r = src[4 * x], g = src[4 * x + 1], b = src[4 * x + 2];
+			const float m = fmaxf(r, fmaxf(g, b));
+			unsigned char* o = &rgbe[4 * static_cast<size_t>(x)];
+			if (m < 1e-32f) { o[0] = o[1] = o[2] = o[3] = 0; continue; }
+			int e; const float n = frexpf(m, &e) * 256.0f / m;
+			o[0] = static_cast<unsigned char>(r * n); o[1] = static_cast<unsigned char>(g * n); o[2] = static_cast<unsigned char>(b * n); o[3] = static_cast<unsigned char>(e + 128);
+		}
+		if (width < 8 || width >= 32768) { std::fwrite(rgbe.data(), 1, rgbe.size(), f); continue; }  // flat scanline
+		line.clear(); line.push_back(2); line.push_back(2); line.push_back(static_cast<unsigned char>(width >> 8)); line.push_back(static_cast<unsigned char>(width & 255));
+		for (int c = 0; c < 4; c++) {  // each component separately: runs (128+n, value) for n >= 3 equal bytes, else literals (n, bytes...)
+			uint32_t x = 0;
+			while (x < width) {
+				uint32_t run = 1; while (x + run < width && run < 127 && rgbe[4 * (x + run) + c] == rgbe[4 * x + c]) run++;
+				if (run >= 3) { line.push_back(static_cast<unsigned char>(128 + run)); line.push_back(rgbe[4 * x + c]); x += run; continue; }
+				uint32_t lit = x, n = 0;  // literal span until the next run of >= 3
+				while (lit < width && n < 128) {
+					uint32_t r2 = 1; while (lit + r2 < width && r2 < 3 && rgbe[4 * (lit + r2) + c] == rgbe[4 * lit + c]) r2++;
+					if (r2 >= 3) break;
+					lit++; n++;
+				}
+				line.push_back(static_cast<unsigned char>(n)); for (uint32_t k = 0; k < n; k++) line.push_back(rgbe[4 * (x + k) + c]);
+				x += n;
+			}
+		}
+		std::fwrite(line.data(), 1, line.size(), f);
+	}
+	const bool ok = std::fclose(f) == 0;
+	return ok ? B2R_OK : B2R_ERR_ARG;
+}

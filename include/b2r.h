@@ -162,6 +162,10 @@ int  b2r_trace_shadow(b2r_ctx* ctx, const float* rays_host, const float* tfar_ho
 /* the flattened 128-byte node array (for the layout round-trip test): out may be NULL to size */
 int  b2r_read_wide_nodes(b2r_ctx* ctx, void* out_host, uint32_t* n_wide_nodes, uint32_t* max_stack);
 
+/* Image::Store (Image.cpp:71-74 -> stbi_write_hdr with vertical flip, called on F5, Application.cpp:254-257): writes the
+ * RGBA32F framebuffer as a Radiance .hdr (32-bit_rle_rgbe, rows written top-down = framebuffer rows in reverse, alpha dropped). */
+int  b2r_write_hdr(const char* path, const float* rgba, uint32_t width, uint32_t height);
+
 const char* b2r_last_error(void);   /* text of the last failure on this thread */
 int  b2r_abi_version(void);
 

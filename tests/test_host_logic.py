@@ -52,3 +52,42 @@ def test_abi_argument_errors():
         cfg = b2r.Config(w, hgt, 16, k, 0, 0, 0, 0, 0)
         assert L.b2r_create(C.byref(h), C.byref(cfg)) == b2r.ERR_ARG and not h.value
     assert L.b2r_accumulate(None, 1) == b2r.ERR_ARG and b"null" in L.b2r_last_error()
+
+
+def _read_hdr(path):
+    """Minimal Radiance RGBE reader (RLE scanlines) for the test."""
+    data = open(path, "rb").read()
+    head, _, rest = data.partition(b"\n\n-Y ")
+    assert head.startswith(b"#?RADIANCE") and b"FORMAT=32-bit_rle_rgbe" in head
+    dims, _, body = rest.partition(b"\n")
+    h, _, w = dims.partition(b" +X "); h, w = int(h), int(w)
+    out = np.zeros((h, w, 4), np.uint8); pos = 0
+    for y in range(h):
+        if 8 <= w < 32768:
+            assert body[pos] == 2 and body[pos + 1] == 2 and (body[pos + 2] << 8 | body[pos + 3]) == w; pos += 4
+            for c in range(4):
+                x = 0
+                while x < w:
+                    n = body[pos]; pos += 1
+                    if n > 128:
+                        out[y, x:x + n - 128, c] = body[pos]; pos += 1; x += n - 128
+                    else:
+                        out[y, x:x + n, c] = np.frombuffer(body[pos:pos + n], np.uint8); pos += n; x += n
+        else:
+            out[y] = np.frombuffer(body[pos:pos + 4 * w], np.uint8).reshape(w, 4); pos += 4 * w
+    assert pos == len(body)
+    scale = np.ldexp(1.0, out[..., 3].astype(np.int32) - 136)
+    return out[..., :3] * scale[..., None] * (out[..., 3:] > 0)
+
+
+@pytest.mark.parametrize("w,h", [(5, 3), (64, 17), (333, 9)])
+def test_hdr_writer_roundtrip(tmp_path, w, h):
+    """Image::Store (Image.cpp:71-74): RGBE precision is 8 mantissa bits of the largest channel; rows are flipped."""
+    rs = np.random.RandomState(w)
+    img = np.zeros((h, w, 4), np.float32); img[..., :3] = rs.rand(h, w, 3) ** 3 * 5; img[..., 3] = 1
+    img[0, : w // 2, :3] = 0.25; img[1:, -1, :3] = 0  # runs and exact zeros
+    b2r.write_hdr(tmp_path / "f.hdr", img)
+    back = _read_hdr(tmp_path / "f.hdr")[::-1]
+    tol = img[..., :3].max(axis=2, keepdims=True) / 128 + 1e-30
+    assert np.all(np.abs(back - img[..., :3]) <= tol)
+    assert np.array_equal(back[0, : w // 2], img[0, : w // 2, :3])
