@@ -2,8 +2,11 @@
 // Renderer: build Scenes::Default (Application.cpp:33-101), pad the viewport to the tiling, then Accumulate -> Render each frame
 // and print the same read-out ("[W X H] : ms : fps : Msamples/s", Application.cpp:400-403).
 //   g++ -std=c++20 -O2 examples/frame_loop.cpp -I cpu-raytracing-experiments_b200/host -L cpu-raytracing-experiments_b200 -lb2r -Wl,-rpath,$PWD/cpu-raytracing-experiments_b200 -o frame_loop
+#include <cfloat>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
+#include <memory>
 #include "Renderer.hpp"
 
 using b2r_host::vec3;
@@ -36,6 +39,22 @@ int main(int argc, char** argv) {
 	auto t0 = std::chrono::steady_clock::now();
 	for (uint32_t f = 0; f < frames; f++) { renderer.Accumulate(); renderer.Render(); }  // Application.cpp:379-380
 	const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / frames;
+	// focus picking exactly as Application.cpp:282-298 writes it: a hand-built RayStream<8>, one ray, BVH::Traverse<8>
+	{
+		auto depth_ray = std::make_unique<RayStream<8>>();
+		depth_ray->hit.matID[0] = -1; depth_ray->hit.primID[0] = -1; depth_ray->hit.tfar[0] = FLT_MAX;
+		auto* raygen_buffer = depth_ray->path.input;
+		const float q[4] = {scene.camera.view.orient.w, scene.camera.view.orient.x, scene.camera.view.orient.y, scene.camera.view.orient.z};
+		(void)q;
+		float ray[6] = {scene.camera.view.pos.x, scene.camera.view.pos.y, scene.camera.view.pos.z, 0.1f, -0.4f, -1.0f};
+		const float inv = 1.0f / std::sqrt(ray[3] * ray[3] + ray[4] * ray[4] + ray[5] * ray[5]);
+		raygen_buffer->p.x[0] = ray[0]; raygen_buffer->p.y[0] = ray[1]; raygen_buffer->p.z[0] = ray[2];
+		raygen_buffer->dir.x[0] = ray[3] * inv; raygen_buffer->dir.y[0] = ray[4] * inv; raygen_buffer->dir.z[0] = ray[5] * inv;
+		scene.acceleration_structure.Traverse<8>(*depth_ray->path.input, depth_ray->hit, 1);
+		float t2; int32_t p2; const float r6[6] = {ray[0], ray[1], ray[2], ray[3] * inv, ray[4] * inv, ray[5] * inv};
+		renderer.Traverse(r6, 1, &t2, &p2);
+		std::printf("focus pick: prim %d mat %d depth %.6f (renderer path: prim %d depth %.6f)\n", depth_ray->hit.primID[0], depth_ray->hit.matID[0], depth_ray->hit.tfar[0], p2, t2);
+	}
 	double sum = 0; for (auto& p : renderer.framebuffer) sum += p.x + p.y + p.z;
 	std::printf("[%u X %u] : %.3fms : %.1ffps : %.1fMsamples/s  (mean tonemapped value %.5f after %u accumulations)\n", viewport_width, viewport_height, ms, 1000.0 / ms,
 	            viewport_width * viewport_height * 1e-3 / ms, sum / (3.0 * renderer.framebuffer.size()), renderer.accumulations);

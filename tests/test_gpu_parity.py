@@ -226,6 +226,8 @@ def test_cpp_mirror_frame_loop(tmp_path):
     subprocess.check_call(["g++", "-std=c++20", "-O2", os.path.join(ROOT, "examples", "frame_loop.cpp"), "-I", os.path.join(PKG, "host"),
                            "-L", PKG, "-lb2r", f"-Wl,-rpath,{PKG}", "-o", exe])
     out = subprocess.check_output([exe, "250", "130", "5"], text=True)   # padded to 256x144 like Application.cpp:367-372
+    fp = re.search(r"focus pick: prim (-?\d+) mat (-?\d+) depth ([0-9.]+) \(renderer path: prim (-?\d+) depth ([0-9.]+)\)", out)
+    assert fp and int(fp.group(1)) == int(fp.group(4)) >= 0 and fp.group(3) == fp.group(5)  # BVH::Traverse<8> == Renderer::Traverse
     m = re.search(r"\[(\d+) X (\d+)\].*mean tonemapped value ([0-9.]+) after (\d+) accumulations", out)
     assert m and (int(m.group(1)), int(m.group(2)), int(m.group(4))) == (256, 144, 5)
     r = b2r.Renderer(scenes.default_scene(), 256, 144, max_bounces=16, buckets=5); r.Accumulate(5); assert r.Render()
