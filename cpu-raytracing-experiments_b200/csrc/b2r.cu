@@ -91,7 +91,7 @@ int alloc_frame(b2r_ctx* c) {
 		uint32_t s = (128u << 20) / npix; c->slots = s < 4u ? 4u : s > static_cast<uint32_t>(kMaxSlots) ? static_cast<uint32_t>(kMaxSlots) : s;
 	}
 	const size_t cap = static_cast<size_t>(c->slots) * npix;
-	if (cap >= (1ull << 32)) return fail(B2R_ERR_ARG, "samples_in_flight * pixels exceeds the 32-bit queue index");
+	if (3 * cap >= (1ull << 32)) return fail(B2R_ERR_ARG, "samples_in_flight * pixels too large: the three-plane queue arrays are indexed with 32 bits");
 	int rc;
 	for (int s = 0; s < 2; s++) {
 		if ((rc = dev_alloc(&c->d_A[s], cap))) return rc;
