@@ -332,3 +332,19 @@ def test_randomised_configurations_bit_exact():
         g, ref = r.buckets_host(), o.buckets()
         assert g.tobytes() == ref.tobytes(), dict(trial=trial, n=n, w=w, h=h, K=K, mb=mb, sif=sif, start=start, samples=samples, frac=divergent_fraction(g, ref))
         r.close()
+
+
+def test_c3_converged_image_at_reduced_size():
+    """BASELINE configs[2] semantics (100k-sphere scene, 16 spp, K = 8, NEE + MIS, max_bounces 16) at 480x272: the resolved,
+    tonemapped frame against the CPU oracle (stream-BVH restatement of BVH.hpp:320-358) — RMSE < 1e-3, divergent fraction reported."""
+    sc = scenes.random_scene(100000); w, h, K = 480, 272, 8
+    r = b2r.Renderer(sc, w, h, max_bounces=16, buckets=K); r.Accumulate(16); assert r.Render()
+    o = oracle_py.Oracle(w, h, max_bounces=16, K=K, flags=oracle_py.ORC_BVH, fast=True); o.set_scene(sc); o.accumulate(16)
+    rc, img = o.render(); assert rc == 0
+    frac = divergent_fraction(r.buckets_host(), o.buckets())
+    rmse = float(np.sqrt(np.mean((r.framebuffer - img) ** 2)))
+    lin = np.zeros_like(r.framebuffer); assert r.Render(tonemap=False, out=lin)
+    rmse_lin = float(np.sqrt(np.mean((lin - o.render(tonemap=False)[1]) ** 2)))
+    print(f"C3 scene 480x272 16 spp: divergent pixel fraction {frac:.3e}, tonemapped RMSE {rmse:.3e}, linear RMSE {rmse_lin:.3e}")
+    assert rmse < 1e-3 and frac < 5e-3
+    r.close()
