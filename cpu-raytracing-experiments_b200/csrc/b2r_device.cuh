@@ -336,14 +336,31 @@ __device__ __forceinline__ void warp_stage_nodes(const WideNode* __restrict__ wi
 }
 // Per-thread traversal stack of the persistent kernels: the first kSmemStack entries live in shared memory, laid out
 // [entry][thread] so a warp's accesses are conflict-free whatever the lanes' depths; deeper entries (rare) overflow to local.
-constexpr int kSmemStack = 16;
+#ifndef B2R_SMEM_STACK
+#define B2R_SMEM_STACK 16
+#endif
+constexpr int kSmemStack = B2R_SMEM_STACK;
+constexpr uint32_t kNoNode = 0xffffffffu;
 struct HybridStack {
 	uint32_t* sm;  // &s_stack[0][threadIdx.x]
 	uint32_t spill[kTraversalStack - kSmemStack];
 	__device__ __forceinline__ void put(int i, uint32_t v) { if (i < kSmemStack) sm[i * kTravBlock] = v; else spill[i - kSmemStack] = v; }
 	__device__ __forceinline__ uint32_t get(int i) const { return i < kSmemStack ? sm[i * kTravBlock] : spill[i - kSmemStack]; }
 };
+// The traversal kernels run 32 per-lane walks per warp (b2r_shade.h describes the tree and the per-lane state machines). One
+// loop iteration = one wide-node visit for every live lane: the warp stages the lanes' 32 nodes through shared memory
+// (warp_stage_nodes); the four slab tests run as one straight-line pass; leaf slots (sphere inlined in the node) are tested
+// right away from the staged row; finished lanes are refilled from the warp's pool as soon as fewer than kRefillBelow lanes
+// are alive. Results do not depend on any of this: the closest hit is the minimum over every sphere whose ancestors' boxes pass
+// (== brute force, ties to the lowest index), any-hit is an order-independent boolean.
+// Measured and rejected (round 1, C3): postponing the leaf tests until a dozen lanes hold one ("speculative traversal", spheres
+// re-fetched from scene.prims) — 20 % slower, the later culling and the re-fetch cost more than the denser sphere tests save;
+// ordering the children with the slot index in the low key bits and min/max pairs — same SASS size as the compare-and-swap
+// network (the compiler already emits VIMNMX), 5 % slower; refill thresholds 16/20/28 and 12/20 stack entries in shared memory —
+// flat; full-sweep SAH and a cost-optimal 2->4 collapse of the traversal tree — 12.3 instead of 12.4 node visits per ray.
+
 // closest-hit traversal of queue side (bounce & 1)
+// (63 registers without a minimum-blocks bound = 8 resident CTAs; bounding it to 8 costs 4 %, fewer resident CTAs cost 3-15 %)
 template <bool COUNT>
 __global__ void __launch_bounds__(kTravBlock) k_intersect_closest(const Params p, const uint32_t bounce) {
 	const uint32_t n_in = p.cnt.paths[bounce];
@@ -461,35 +478,66 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_shade(con
 	stat_add(p.cnt.stats, ST_HITS, c_hits); stat_add(p.cnt.stats, ST_TERM, c_term);
 	stat_add(p.cnt.stats, ST_DROPPED, c_drop); stat_add(p.cnt.stats, ST_EVENTS, c_events); stat_add(p.cnt.stats, ST_SHADOW, c_inline_shadow);
 }
-// shadow rays of this bounce: any-hit traversal, unoccluded light samples are added to the pixel's radiance
+// shadow rays of this bounce: any-hit traversal (same walk as above without ordering: the first hit child is visited next, the
+// others are pushed; the first occluding leaf sphere ends the ray), unoccluded light samples are added to the
+// pixel's radiance
 template <bool COUNT>
-__global__ void __launch_bounds__(kTravBlock) k_intersect_shadow(const Params p, const uint32_t bounce) {
+__global__ void __launch_bounds__(kTravBlock, 8) k_intersect_shadow(const Params p, const uint32_t bounce) {
 	const uint32_t n_in = p.cnt.shadow[bounce];
 	const WideNode* __restrict__ wide = p.scene.wide;
 	uint32_t c_sphere = 0, c_box = 0, c_events = 0;
 	__shared__ __align__(128) float4 s_nodes[kTravBlock / 32][32 * kNodeRowF4];
 	__shared__ uint32_t s_stack[kSmemStack][kTravBlock];
 	float4* rows = s_nodes[threadIdx.x >> 5];
-	WarpPool pool; TravAnyT<HybridStack> t; bool active = false; uint32_t idx = 0, pid = 0;
-	t.node = 0u; t.stack.sm = &s_stack[0][threadIdx.x];
+	const float4* row = rows + lane_id() * kNodeRowF4; const uint32_t swz = lane_id() & 7u;
+	HybridStack stack; stack.sm = &s_stack[0][threadIdx.x];
+	WarpPool pool;
+	float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, ix = 0, iy = 0, iz = 0, nx = 0, ny = 0, nz = 0, tfar = 0;
+	uint32_t node = 0u, idx = 0, pid = 0; int sp = 0; bool active = false;
 	for (;;) {
 		const uint32_t got = pool.take(!active, p.cnt.work_b + bounce, n_in);
 		if (got != 0xffffffffu) {
 			idx = got; active = true;
 			const float4 a = p.q.SA[idx], b = p.q.SB[idx];
-			pid = __float_as_uint(b.w);
-			t.begin(Ray{a.x, a.y, a.z, a.w, b.x, b.y}, b.z);
+			ox = a.x; oy = a.y; oz = a.z; dx = a.w; dy = b.x; dz = b.y; tfar = b.z; pid = __float_as_uint(b.w);
+			ix = 1.0f / dx; iy = 1.0f / dy; iz = 1.0f / dz;
+			nx = -(ox * ix); ny = -(oy * iy); nz = -(oz * iz);
+			node = 0u; sp = 0;
 		}
 		uint32_t live = __ballot_sync(0xffffffffu, active);
 		if (live == 0u) break;
 		do {
-			warp_stage_nodes(wide, rows, t.node, live);
-			if (active && !t.template step_staged<COUNT>(rows + lane_id() * kNodeRowF4, lane_id() & 7u, &c_sphere, &c_box)) {
-				if (!t.occluded) {
-					const f3 L{p.q.SL[idx], p.q.SL[p.q.cap + idx], p.q.SL[2u * p.q.cap + idx]};
-					rad_add(p.rad, p.frame.npix, pid, L, f3{0.0f, 0.0f, 0.0f}, true, false); c_events++;
+			warp_stage_nodes(wide, rows, node, live);
+			if (active) {
+				uint32_t next = kNoNode, leaves = 0u;
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					const float4 a = row[static_cast<uint32_t>(2 * k) ^ swz], b = row[static_cast<uint32_t>(2 * k + 1) ^ swz];
+					const int32_t l = __float_as_int(b.z);
+					float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, tfar, &tn, &h);
+					const bool inner = l >= 0;
+					if (COUNT && inner) c_box++;
+					if (inner && h) { if (next != kNoNode) stack.put(sp++, next); next = static_cast<uint32_t>(l); }
+					leaves |= (!inner && l != kEmptyLink) ? (1u << k) : 0u;
 				}
-				active = false;
+				bool occluded = false;
+				while (leaves) {
+					const uint32_t k = static_cast<uint32_t>(__ffs(static_cast<int>(leaves)) - 1);
+					leaves &= leaves - 1u;
+					const float4 s4 = row[(2u * k) ^ swz];
+					if (COUNT) c_sphere++;
+					if (sphere_hit_any(s4.x, s4.y, s4.z, s4.w, ox, oy, oz, dx, dy, dz, tfar)) { occluded = true; break; }
+				}
+				if (occluded) active = false;  // the light sample is dropped
+				else {
+					if (next == kNoNode && sp > 0) next = stack.get(--sp);
+					node = next;
+					if (next == kNoNode) {  // walked the whole tree without an occluder
+						const f3 L{p.q.SL[idx], p.q.SL[p.q.cap + idx], p.q.SL[2u * p.q.cap + idx]};
+						rad_add(p.rad, p.frame.npix, pid, L, f3{0.0f, 0.0f, 0.0f}, true, false); c_events++;
+						active = false;
+					}
+				}
 			}
 			live = __ballot_sync(0xffffffffu, active);
 		} while (live != 0u && (pool.dry || __popc(live) >= kRefillBelow));

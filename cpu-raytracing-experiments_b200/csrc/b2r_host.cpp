@@ -228,7 +228,7 @@ void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* 
 	}
 	out.max_stack = need[0];
 	uint32_t node_bits = 1; while ((1ull << node_bits) < out.nodes.size()) node_bits++;
-	out.tn_bits = 32u - node_bits;
+	out.tn_bits = std::min(32u - node_bits, 29u);  // >= 2 low key bits are dropped: the kernels keep the slot index there
 }
 
 void pack_scene(const b2r_sphere* prims, uint32_t n_prims, const b2r_material* materials, uint32_t n_mat,
