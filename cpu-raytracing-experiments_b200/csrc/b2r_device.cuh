@@ -360,7 +360,8 @@ struct HybridStack {
 // flat; full-sweep SAH and a cost-optimal 2->4 collapse of the traversal tree — 12.3 instead of 12.4 node visits per ray.
 
 // closest-hit traversal of queue side (bounce & 1)
-// (63 registers without a minimum-blocks bound = 8 resident CTAs; bounding it to 8 costs 4 %, fewer resident CTAs cost 3-15 %)
+// (63 registers without a minimum-blocks bound = 8 resident CTAs. Measured: bounding it to 8 costs 4 %; 71/79/96 registers with
+// 7/6/5 CTAs cost 3/5/16 %; 56/48 registers with 9/10 CTAs and a shorter shared-memory stack cost 5/8 %.)
 template <bool COUNT>
 __global__ void __launch_bounds__(kTravBlock) k_intersect_closest(const Params p, const uint32_t bounce) {
 	const uint32_t n_in = p.cnt.paths[bounce];
