@@ -318,7 +318,8 @@ struct WarpPool {
 // (256 L1 wavefronts per step — the first version was bound by exactly that). Instead the warp copies the 32 nodes
 // cooperatively, 8 lanes x 16 B per node so each copy instruction touches 4 lines, straight into shared memory (cp.async,
 // no register staging); every lane then reads its own node back with LDS.128.
-constexpr int kNodeRowF4 = 8;  // 128-byte rows; the eight 16-byte parts of a row are XOR-swizzled by the owning lane (conflict-free fill and reads)
+constexpr int kNodeRowF4 = 9;  // 128-byte node in a 144-byte row: the 16-byte pad makes the cooperative fill and the per-lane LDS.128 reads conflict-free
+                               // with plain immediate offsets (an XOR swizzle did the same at two extra address instructions per read)
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
 	const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
@@ -329,23 +330,48 @@ __device__ __forceinline__ void warp_stage_nodes(const WideNode* __restrict__ wi
 	for (uint32_t j = 0; j < 8; j++) {
 		const uint32_t owner = 4u * j + (lane >> 3);
 		const uint32_t nd = __shfl_sync(0xffffffffu, my_node, owner);
-		if ((live >> owner) & 1u) cp_async16(s_rows + owner * kNodeRowF4 + (part ^ (owner & 7u)), reinterpret_cast<const float4*>(wide + nd) + part);
+		if ((live >> owner) & 1u) cp_async16(s_rows + owner * kNodeRowF4 + part, reinterpret_cast<const float4*>(wide + nd) + part);
 	}
 	asm volatile("cp.async.wait_all;" ::: "memory");
 	__syncwarp();
 }
-// Per-thread traversal stack of the persistent kernels: the first kSmemStack entries live in shared memory, laid out
-// [entry][thread] so a warp's accesses are conflict-free whatever the lanes' depths; deeper entries (rare) overflow to local.
+// Per-thread traversal stack of the persistent kernels: kSmemStack entries in shared memory, laid out [entry][thread] so a
+// warp's accesses are conflict-free whatever the lanes' depths. The hot path never tests for overflow per access: once per node
+// visit room() makes sure three more entries fit, and if they do not (rare: the host bounds the worst case, typical rays use a
+// handful) the kEvict oldest entries move to a local-memory backing store and come back through refill() when the shared part
+// has run empty — LIFO order is kept because the oldest entries are the last to be popped.
 #ifndef B2R_SMEM_STACK
 #define B2R_SMEM_STACK 16
 #endif
-constexpr int kSmemStack = B2R_SMEM_STACK;
+constexpr int kSmemStack = B2R_SMEM_STACK, kEvict = 8;
 constexpr uint32_t kNoNode = 0xffffffffu;
-struct HybridStack {
-	uint32_t* sm;  // &s_stack[0][threadIdx.x]
-	uint32_t spill[kTraversalStack - kSmemStack];
-	__device__ __forceinline__ void put(int i, uint32_t v) { if (i < kSmemStack) sm[i * kTravBlock] = v; else spill[i - kSmemStack] = v; }
-	__device__ __forceinline__ uint32_t get(int i) const { return i < kSmemStack ? sm[i * kTravBlock] : spill[i - kSmemStack]; }
+static_assert(kSmemStack >= kEvict + 3 && kTraversalStack % kEvict == 0, "stack geometry");
+__device__ __forceinline__ void stack_st(uint32_t sm, int i, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(sm + static_cast<uint32_t>(i) * (kTravBlock * 4u)), "r"(v)); }
+__device__ __forceinline__ uint32_t stack_ld(uint32_t sm, int i) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sm + static_cast<uint32_t>(i) * (kTravBlock * 4u))); return v; }
+// the rare paths are real calls that see only the backing array, so the per-ray state stays in registers
+__device__ __noinline__ int stack_evict(uint32_t sm, uint32_t* backing, int sp) {
+	for (int j = 0; j < kEvict; j++) backing[j] = stack_ld(sm, j);
+	for (int j = kEvict; j < sp; j++) stack_st(sm, j - kEvict, stack_ld(sm, j));
+	return sp - kEvict;
+}
+__device__ __noinline__ void stack_restore(uint32_t sm, const uint32_t* backing) { for (int j = 0; j < kEvict; j++) stack_st(sm, j, backing[j]); }
+struct SmemStack {
+	uint32_t sm;       // 32-bit shared-window address of s_stack[0][threadIdx.x]: every access is one LD/ST.shared with an IMAD'd offset
+	int spilled;       // entries in the backing store
+	uint32_t* backing; // [kTraversalStack] in local memory, declared by the kernel
+	__device__ __forceinline__ void bind(const uint32_t* slot0, uint32_t* local_backing) { sm = static_cast<uint32_t>(__cvta_generic_to_shared(slot0)); backing = local_backing; spilled = 0; }
+	__device__ __forceinline__ void reset() { spilled = 0; }
+	__device__ __forceinline__ void put(int i, uint32_t v) { stack_st(sm, i, v); }
+	__device__ __forceinline__ uint32_t get(int i) const { return stack_ld(sm, i); }
+	__device__ __forceinline__ int room(int sp) {
+		if (sp > kSmemStack - 3) { sp = stack_evict(sm, backing + spilled, sp); spilled += kEvict; }
+		return sp;
+	}
+	__device__ __forceinline__ int refill() {
+		if (spilled == 0) return 0;
+		spilled -= kEvict; stack_restore(sm, backing + spilled);
+		return kEvict;
+	}
 };
 // The traversal kernels run 32 per-lane walks per warp (b2r_shade.h describes the tree and the per-lane state machines). One
 // loop iteration = one wide-node visit for every live lane: the warp stages the lanes' 32 nodes through shared memory
@@ -371,8 +397,9 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_closest(const Params p
 	__shared__ __align__(128) float4 s_nodes[kTravBlock / 32][32 * kNodeRowF4];
 	__shared__ uint32_t s_stack[kSmemStack][kTravBlock];
 	float4* rows = s_nodes[threadIdx.x >> 5];
-	WarpPool pool; TravClosestT<HybridStack> t; bool active = false; uint32_t idx = 0;
-	t.node = 0u; t.stack.sm = &s_stack[0][threadIdx.x];
+	WarpPool pool; TravClosestT<SmemStack> t; bool active = false; uint32_t idx = 0;
+	uint32_t backing[kTraversalStack];
+	t.node = 0u; t.stack.bind(&s_stack[0][threadIdx.x], backing);
 	for (;;) {
 		const uint32_t got = pool.take(!active, p.cnt.work_a + bounce, n_in);
 		if (got != 0xffffffffu) {
@@ -384,7 +411,7 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_closest(const Params p
 		if (live == 0u) break;
 		do {
 			warp_stage_nodes(wide, rows, t.node, live);
-			if (active && !t.template step_staged<COUNT>(rows + lane_id() * kNodeRowF4, lane_id() & 7u, p.scene.stack_tn_bits, &c_sphere, &c_box)) {
+			if (active && !t.template step_staged<COUNT>(rows + lane_id() * kNodeRowF4, p.scene.stack_tn_bits, &c_sphere, &c_box)) {
 				p.q.H[idx] = make_float2(t.best, __int_as_float(t.prim));
 				active = false;
 			}
@@ -490,8 +517,9 @@ __global__ void __launch_bounds__(kTravBlock, 8) k_intersect_shadow(const Params
 	__shared__ __align__(128) float4 s_nodes[kTravBlock / 32][32 * kNodeRowF4];
 	__shared__ uint32_t s_stack[kSmemStack][kTravBlock];
 	float4* rows = s_nodes[threadIdx.x >> 5];
-	const float4* row = rows + lane_id() * kNodeRowF4; const uint32_t swz = lane_id() & 7u;
-	HybridStack stack; stack.sm = &s_stack[0][threadIdx.x];
+	const float4* row = rows + lane_id() * kNodeRowF4;
+	uint32_t backing[kTraversalStack];
+	SmemStack stack; stack.bind(&s_stack[0][threadIdx.x], backing);
 	WarpPool pool;
 	float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, ix = 0, iy = 0, iz = 0, nx = 0, ny = 0, nz = 0, tfar = 0;
 	uint32_t node = 0u, idx = 0, pid = 0; int sp = 0; bool active = false;
@@ -503,7 +531,7 @@ __global__ void __launch_bounds__(kTravBlock, 8) k_intersect_shadow(const Params
 			ox = a.x; oy = a.y; oz = a.z; dx = a.w; dy = b.x; dz = b.y; tfar = b.z; pid = __float_as_uint(b.w);
 			ix = 1.0f / dx; iy = 1.0f / dy; iz = 1.0f / dz;
 			nx = -(ox * ix); ny = -(oy * iy); nz = -(oz * iz);
-			node = 0u; sp = 0;
+			node = 0u; sp = 0; stack.reset();
 		}
 		uint32_t live = __ballot_sync(0xffffffffu, active);
 		if (live == 0u) break;
@@ -511,9 +539,10 @@ __global__ void __launch_bounds__(kTravBlock, 8) k_intersect_shadow(const Params
 			warp_stage_nodes(wide, rows, node, live);
 			if (active) {
 				uint32_t next = kNoNode, leaves = 0u;
+				sp = stack.room(sp);
 #pragma unroll
 				for (int k = 0; k < 4; k++) {
-					const float4 a = row[static_cast<uint32_t>(2 * k) ^ swz], b = row[static_cast<uint32_t>(2 * k + 1) ^ swz];
+					const float4 a = row[2 * k], b = row[2 * k + 1];
 					const int32_t l = __float_as_int(b.z);
 					float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, tfar, &tn, &h);
 					const bool inner = l >= 0;
@@ -525,13 +554,13 @@ __global__ void __launch_bounds__(kTravBlock, 8) k_intersect_shadow(const Params
 				while (leaves) {
 					const uint32_t k = static_cast<uint32_t>(__ffs(static_cast<int>(leaves)) - 1);
 					leaves &= leaves - 1u;
-					const float4 s4 = row[(2u * k) ^ swz];
+					const float4 s4 = row[2u * k];
 					if (COUNT) c_sphere++;
 					if (sphere_hit_any(s4.x, s4.y, s4.z, s4.w, ox, oy, oz, dx, dy, dz, tfar)) { occluded = true; break; }
 				}
 				if (occluded) active = false;  // the light sample is dropped
 				else {
-					if (next == kNoNode && sp > 0) next = stack.get(--sp);
+					if (next == kNoNode) { if (sp == 0) sp = stack.refill(); if (sp > 0) next = stack.get(--sp); }
 					node = next;
 					if (next == kNoNode) {  // walked the whole tree without an occluder
 						const f3 L{p.q.SL[idx], p.q.SL[p.q.cap + idx], p.q.SL[2u * p.q.cap + idx]};

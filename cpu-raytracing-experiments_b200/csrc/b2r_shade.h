@@ -244,6 +244,9 @@ struct ArrayStack {
 	uint32_t e[kTraversalStack];
 	B2R_HD void put(int i, uint32_t v) { e[i] = v; }
 	B2R_HD uint32_t get(int i) const { return e[i]; }
+	B2R_HD int room(int sp) { return sp; }   // called before the (up to three) pushes of a node visit
+	B2R_HD int refill() { return 0; }        // called when the stack has run empty: entries brought back from a backing store
+	B2R_HD void reset() {}
 };
 B2R_HD uint32_t pack_entry(uint32_t node, uint32_t tnear_bits, uint32_t tn_bits) { return (node << tn_bits) | (tnear_bits >> (31u - tn_bits)); }
 B2R_HD float entry_tnear(uint32_t e, uint32_t tn_bits) { return from_bits((e & ((1u << tn_bits) - 1u)) << (31u - tn_bits)); }
@@ -261,8 +264,7 @@ struct TravBase {
 	}
 };
 // node access: STAGED = the node's eight float4 were copied to shared memory by the warp (kernels); otherwise read-only LDG
-// (staged rows are XOR-swizzled by the owning lane, `swz` = lane & 7, so both the cooperative fill and the per-lane reads are bank-conflict-free)
-template <bool STAGED> B2R_HD float4 node_f4(const float4* n, int i, uint32_t swz) { return STAGED ? n[static_cast<uint32_t>(i) ^ swz] : ldg4(n + i); }
+template <bool STAGED> B2R_HD float4 node_f4(const float4* n, int i) { return STAGED ? n[i] : ldg4(n + i); }
 
 // Closest hit == brute force over all spheres (BVH.hpp:311-318): a candidate replaces the best when d < best, or d == best with
 // a lower sphere index (the brute-force loop keeps the first of equal distances, BVH.hpp:265); a node is culled only when its
@@ -273,13 +275,13 @@ template <class Stack>
 struct TravClosestT : TravBase {
 	float best; int32_t prim;
 	Stack stack;
-	B2R_HD void begin(const Ray& r) { arm(r); best = FLT_MAX; prim = -1; }
+	B2R_HD void begin(const Ray& r) { arm(r); best = FLT_MAX; prim = -1; stack.reset(); }
 	template <bool COUNT, bool STAGED>
-	B2R_HD bool visit(const float4* n, uint32_t swz, uint32_t tn_bits, uint32_t* c_sphere, uint32_t* c_box) {
+	B2R_HD bool visit(const float4* n, uint32_t tn_bits, uint32_t* c_sphere, uint32_t* c_box) {
 		uint32_t key[4], link[4]; uint32_t leaves = 0u;
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
-			const float4 a = node_f4<STAGED>(n, 2 * k, swz), b = node_f4<STAGED>(n, 2 * k + 1, swz);
+			const float4 a = node_f4<STAGED>(n, 2 * k), b = node_f4<STAGED>(n, 2 * k + 1);
 			const int32_t l = as_int(b.z);
 			float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, best, &tn, &h);
 			const bool inner = l >= 0;
@@ -294,7 +296,7 @@ struct TravClosestT : TravBase {
 			const int k = __builtin_ctz(leaves);
 #endif
 			leaves &= leaves - 1u;
-			const float4 sp = node_f4<STAGED>(n, 2 * k, swz); const int32_t id = ~as_int(node_f4<STAGED>(n, 2 * k + 1, swz).z);
+			const float4 sp = node_f4<STAGED>(n, 2 * k); const int32_t id = ~as_int(node_f4<STAGED>(n, 2 * k + 1).z);
 			float d; if (COUNT) (*c_sphere)++;
 			if (sphere_hit_closest(sp.x, sp.y, sp.z, sp.w, ox, oy, oz, dx, dy, dz, &d)) {
 				if (d < best || (d == best && id < prim)) { best = d; prim = id; }
@@ -304,20 +306,24 @@ struct TravClosestT : TravBase {
 		B2R_CSWAP(key[0], link[0], key[1], link[1]); B2R_CSWAP(key[2], link[2], key[3], link[3]);
 		B2R_CSWAP(key[0], link[0], key[2], link[2]); B2R_CSWAP(key[1], link[1], key[3], link[3]);
 		B2R_CSWAP(key[1], link[1], key[2], link[2]);
+		sp = stack.room(sp);
 		if (key[3] != 0xffffffffu) stack.put(sp++, pack_entry(link[3], key[3], tn_bits));
 		if (key[2] != 0xffffffffu) stack.put(sp++, pack_entry(link[2], key[2], tn_bits));
 		if (key[1] != 0xffffffffu) stack.put(sp++, pack_entry(link[1], key[1], tn_bits));
 		if (key[0] != 0xffffffffu && from_bits(key[0]) <= best) { node = link[0]; return true; }
-		while (sp > 0) {
-			const uint32_t e = stack.get(--sp);
-			if (entry_tnear(e, tn_bits) <= best) { node = entry_node(e, tn_bits); return true; }
+		for (;;) {
+			while (sp > 0) {
+				const uint32_t e = stack.get(--sp);
+				if (entry_tnear(e, tn_bits) <= best) { node = entry_node(e, tn_bits); return true; }
+			}
+			sp = stack.refill();
+			if (sp == 0) return false;
 		}
-		return false;
 	}
 	template <bool COUNT>
-	B2R_HD bool step(const WideNode* __restrict__ wide, uint32_t tn_bits, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, false>(reinterpret_cast<const float4*>(wide + node), 0u, tn_bits, c_sphere, c_box); }
+	B2R_HD bool step(const WideNode* __restrict__ wide, uint32_t tn_bits, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, false>(reinterpret_cast<const float4*>(wide + node), tn_bits, c_sphere, c_box); }
 	template <bool COUNT>
-	B2R_HD bool step_staged(const float4* n, uint32_t swz, uint32_t tn_bits, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, true>(n, swz, tn_bits, c_sphere, c_box); }
+	B2R_HD bool step_staged(const float4* n, uint32_t tn_bits, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, true>(n, tn_bits, c_sphere, c_box); }
 };
 // Any hit along [0, tfar) — Traverse_shadow semantics (BVH.hpp:290-305): an order-independent boolean.
 template <class Stack>
@@ -326,11 +332,11 @@ struct TravAnyT : TravBase {
 	Stack stack;
 	B2R_HD void begin(const Ray& r, float limit) { arm(r); tfar = limit; occluded = false; }
 	template <bool COUNT, bool STAGED>
-	B2R_HD bool visit(const float4* n, uint32_t swz, uint32_t* c_sphere, uint32_t* c_box) {
+	B2R_HD bool visit(const float4* n, uint32_t* c_sphere, uint32_t* c_box) {
 		uint32_t next = 0xffffffffu, leaves = 0u;
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
-			const float4 a = node_f4<STAGED>(n, 2 * k, swz), b = node_f4<STAGED>(n, 2 * k + 1, swz);
+			const float4 a = node_f4<STAGED>(n, 2 * k), b = node_f4<STAGED>(n, 2 * k + 1);
 			const int32_t l = as_int(b.z);
 			float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, tfar, &tn, &h);
 			const bool inner = l >= 0;
@@ -345,7 +351,7 @@ struct TravAnyT : TravBase {
 			const int k = __builtin_ctz(leaves);
 #endif
 			leaves &= leaves - 1u;
-			const float4 sp = node_f4<STAGED>(n, 2 * k, swz);
+			const float4 sp = node_f4<STAGED>(n, 2 * k);
 			if (COUNT) (*c_sphere)++;
 			if (sphere_hit_any(sp.x, sp.y, sp.z, sp.w, ox, oy, oz, dx, dy, dz, tfar)) { occluded = true; return false; }
 		}
@@ -355,9 +361,9 @@ struct TravAnyT : TravBase {
 		return true;
 	}
 	template <bool COUNT>
-	B2R_HD bool step(const WideNode* __restrict__ wide, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, false>(reinterpret_cast<const float4*>(wide + node), 0u, c_sphere, c_box); }
+	B2R_HD bool step(const WideNode* __restrict__ wide, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, false>(reinterpret_cast<const float4*>(wide + node), c_sphere, c_box); }
 	template <bool COUNT>
-	B2R_HD bool step_staged(const float4* n, uint32_t swz, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, true>(n, swz, c_sphere, c_box); }
+	B2R_HD bool step_staged(const float4* n, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, true>(n, c_sphere, c_box); }
 };
 using TravClosest = TravClosestT<ArrayStack>;
 using TravAny = TravAnyT<ArrayStack>;
