@@ -72,6 +72,19 @@ __device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t* s_cnt, uint3
 	return off + __popc(ballot & ((1u << lane_id()) - 1u));
 }
 
+// two flags ranked behind ONE barrier (the shading phase ranks its shadow rays and its surviving paths together)
+__device__ __forceinline__ void block_rank2(bool fa, bool fb, uint32_t* s_a, uint32_t* s_b, uint32_t* rank_a, uint32_t* total_a, uint32_t* rank_b, uint32_t* total_b) {
+	const uint32_t ba = __ballot_sync(0xffffffffu, fa), bb = __ballot_sync(0xffffffffu, fb);
+	const uint32_t warp = threadIdx.x >> 5, below = (1u << lane_id()) - 1u;
+	if (lane_id() == 0) { s_a[warp] = __popc(ba); s_b[warp] = __popc(bb); }
+	__syncthreads();
+	uint32_t oa = 0, ta = 0, ob = 0, tb = 0;
+#pragma unroll
+	for (uint32_t w = 0; w < kBruteWarps; w++) { const uint32_t ca = s_a[w], cb = s_b[w]; oa += (w < warp) ? ca : 0u; ta += ca; ob += (w < warp) ? cb : 0u; tb += cb; }
+	*total_a = ta; *total_b = tb;
+	*rank_a = oa + __popc(ba & below); *rank_b = ob + __popc(bb & below);
+}
+
 template <bool FIRST, bool COUNT>
 __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_brute(const Params p, const uint32_t bounce) {
 	constexpr int kQ = 2 * kBruteBlock;  // hit queue: up to kBruteBlock-1 waiting + kBruteBlock new
@@ -216,9 +229,9 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 				}
 			}
 			// shadow rays -> shared-memory queue; survivors -> next path queue (one atomic per CTA)
-			uint32_t n_shadow, n_keep;
-			const uint32_t sslot = s_queued + block_rank(want_shadow, s_cnt_c, &n_shadow);  // barrier: hit-queue reads above precede the next phase 1
-			const uint32_t rank = block_rank(keep, s_cnt_b, &n_keep);
+			uint32_t n_shadow, n_keep, srank, rank;
+			block_rank2(want_shadow, keep, s_cnt_c, s_cnt_b, &srank, &n_shadow, &rank, &n_keep);  // barrier: hit-queue reads above precede the next phase 1
+			const uint32_t sslot = s_queued + srank;
 			if (want_shadow) {
 				s_shadow[0][sslot] = sr.o.x; s_shadow[1][sslot] = sr.o.y; s_shadow[2][sslot] = sr.o.z;
 				s_shadow[3][sslot] = sr.d.x; s_shadow[4][sslot] = sr.d.y; s_shadow[5][sslot] = sr.d.z; s_shadow[6][sslot] = sr.tfar;
@@ -487,9 +500,8 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_shade(con
 				if (!keep) c_term++;
 			}
 		}
-		uint32_t n_shadow, n_keep;
-		const uint32_t srank = block_rank(want_shadow, s_cnt_b, &n_shadow);  // barrier: queue reads above are done before the next phase 1 writes
-		const uint32_t rank = block_rank(keep, s_cnt_c, &n_keep);
+		uint32_t n_shadow, n_keep, srank, rank;
+		block_rank2(want_shadow, keep, s_cnt_b, s_cnt_c, &srank, &n_shadow, &rank, &n_keep);  // barrier: queue reads above are done before the next phase 1 writes
 		if (threadIdx.x == 0) {
 			s_sbase = n_shadow ? atomicAdd(p.cnt.shadow + bounce, n_shadow) : 0u;
 			s_base = n_keep ? atomicAdd(p.cnt.paths + bounce + 1, n_keep) : 0u;

@@ -130,6 +130,33 @@ def test_bvh_pipeline_vs_bruteforce_oracle(n, w, h, mb, tree):
     r.close()
 
 
+def test_deep_traversal_stack_nested_spheres():
+    """Every box of this scene overlaps every other (4096 large spheres whose centres sit within two units), so each node visit
+    hits all its children and the per-lane traversal stack grows by three per level: the shared-memory part of the stack
+    (16 entries) overflows on essentially every ray and the bulk evict / refill path of the persistent kernels runs. Results
+    must still equal brute force."""
+    sc = scenes.random_scene(4096, light_every=64)
+    rs = np.random.RandomState(7)
+    g = sc["geometry"]
+    g["position"][:] = rs.uniform(-1.0, 1.0, (len(g), 3)).astype(np.float32)
+    g["radius_sq"][:] = (rs.uniform(5.0, 6.0, len(g)).astype(np.float32)) ** 2
+    lights = np.arange(0, len(g), 64)  # the emissive spheres: small, on a shell around the cluster, so that shadow rays are traced too
+    d = rs.randn(len(lights), 3); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    g["position"][lights] = (40.0 * d).astype(np.float32); g["radius_sq"][lights] = np.float32(4.0)
+    sc["camera"] = dict(eye=(0, 2, 30), dir=(0, -0.05, -1), focal_length=50.0, exposure=1.0)
+    w, h, mb = 96, 64, 4
+    r = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=1, flags=b2r.FLAG_FORCE_BVH); r.Accumulate(2)
+    _, max_stack = r.wide_nodes()
+    assert max_stack > 13, max_stack  # deeper than the shared-memory stack minus its three slots of headroom
+    o = oracle_for(sc, w, h, mb, 1); o.accumulate(2)
+    frac = divergent_fraction(r.buckets_host(), o.buckets())
+    gc, oc = r.counters(), o.counters()
+    print(f"nested spheres: worst-case stack {max_stack}, divergent pixel fraction {frac:.3e}, rays {gc['extension_rays']}/{oc['extension_rays']}, shadow rays {gc['shadow_rays']}")
+    assert frac < 2e-3 and gc["shadow_rays"] > 1000
+    assert abs(gc["extension_rays"] - oc["extension_rays"]) <= 1e-3 * oc["extension_rays"]
+    r.close()
+
+
 def test_bvh_equals_brute_on_gpu_at_scale():
     """Size-independent property at C3's scene size: on the GPU, BVH traversal and brute force over all 100k spheres produce
     the same image for the same sample (tiles of the full 1920x1088 frame are too slow for the CPU oracle, not for the GPU)."""
