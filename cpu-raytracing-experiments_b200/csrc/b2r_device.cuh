@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 					const uint32_t sl0 = div_by(i, p.frame.npix, p.frame.npix_magic);
 					const PathState s0 = primary_path(p.frame, p.batch->acc[sl0], sl0, i - sl0 * p.frame.npix);
 					ox = s0.ox; oy = s0.oy; oz = s0.oz; dx = s0.dx; dy = s0.dy; dz = s0.dz;
+					rad_zero(p.rad, p.frame.npix, s0.pid);  // a path's radiance starts at 0 here (coalesced stores); contributions are added after a CTA barrier
 				} else {
 					const float4 a = p.q.A[side][i], b = p.q.B[side][i];
 					ox = a.x; oy = a.y; oz = a.z; dx = a.w; dy = b.x; dz = b.y;
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 __global__ void __launch_bounds__(kBlock) k_generate(const Params p) {
 	const uint32_t n = p.batch->n_slots * p.frame.npix;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-		{ const uint32_t sl = div_by(i, p.frame.npix, p.frame.npix_magic); store_path(p.q, 0, i, primary_path(p.frame, p.batch->acc[sl], sl, i - sl * p.frame.npix)); }
+		{ const uint32_t sl = div_by(i, p.frame.npix, p.frame.npix_magic); const PathState s = primary_path(p.frame, p.batch->acc[sl], sl, i - sl * p.frame.npix); store_path(p.q, 0, i, s); rad_zero(p.rad, p.frame.npix, s.pid); }
 	if (blockIdx.x == 0 && threadIdx.x == 0) p.cnt.paths[0] = n;
 }
 // Work distribution of the traversal kernels: every warp owns a pool of ray indices claimed kTravChunk at a time from the
@@ -591,7 +592,8 @@ __global__ void __launch_bounds__(kTravBlock, 8) k_intersect_shadow(const Params
 
 // ---------------------------------------------------------------------------------------------- accumulate + resolve
 // Fold the batch's per-sample radiance into its median-of-means bucket, in sample order (Renderer.hpp:424-430 adds one
-// sample at a time; bucket = acc % K, :82), and clear RAD for the next batch.
+// sample at a time; bucket = acc % K, :82). RAD is not cleared here: the primary-ray stage of the next batch starts every
+// (sample, pixel) entry at 0 with a plain store, which halves this kernel's HBM traffic.
 __global__ void __launch_bounds__(kBlock) k_accumulate(const Params p) {
 	__shared__ uint32_t s_order[kMaxSlots];   // slots grouped by bucket, increasing sample index inside a bucket
 	__shared__ uint32_t s_first[kMaxSlots + 1];  // group boundaries per bucket (buckets <= 64)
@@ -602,7 +604,7 @@ __global__ void __launch_bounds__(kBlock) k_accumulate(const Params p) {
 		s_first[K] = m;
 	}
 	__syncthreads();
-	float4* __restrict__ rad = reinterpret_cast<float4*>(p.rad); float4* __restrict__ acc = reinterpret_cast<float4*>(p.acc);
+	const float4* __restrict__ rad = reinterpret_cast<const float4*>(p.rad); float4* __restrict__ acc = reinterpret_cast<float4*>(p.acc);
 	const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const uint32_t c = i / npix4, t4 = i - c * npix4;
@@ -616,7 +618,7 @@ __global__ void __launch_bounds__(kBlock) k_accumulate(const Params p) {
 #pragma unroll
 				for (uint32_t u = 0; u < 4u; u++) v[u] = (j + u < b1) ? rad[(static_cast<size_t>(s_order[j + u]) * 3u + c) * npix4 + t4] : zero;
 #pragma unroll
-				for (uint32_t u = 0; u < 4u; u++) if (j + u < b1) { sum.x += v[u].x; sum.y += v[u].y; sum.z += v[u].z; sum.w += v[u].w; rad[(static_cast<size_t>(s_order[j + u]) * 3u + c) * npix4 + t4] = zero; }
+				for (uint32_t u = 0; u < 4u; u++) if (j + u < b1) { sum.x += v[u].x; sum.y += v[u].y; sum.z += v[u].z; sum.w += v[u].w; }
 			}
 			*dst = sum;
 		}
@@ -630,6 +632,7 @@ __device__ __forceinline__ float median_buckets_at(const BucketPtrs& bp, uint32_
 	if (K == 5) return median_of_5(bp.k[0][off], bp.k[1][off], bp.k[2][off], bp.k[3][off], bp.k[4][off]);
 	if (K == 3) return median_of_3(bp.k[0][off], bp.k[1][off], bp.k[2][off]);
 	if (K == 1) return bp.k[0][off];
+	if (K == 8) return median_of_8(bp.k[0][off], bp.k[1][off], bp.k[2][off], bp.k[3][off], bp.k[4][off], bp.k[5][off], bp.k[6][off], bp.k[7][off]);
 	float v[64];
 	for (uint32_t k = 0; k < K; k++) {  // insertion sort
 		float x = bp.k[k][off]; int j = static_cast<int>(k) - 1;

@@ -281,6 +281,18 @@ B2R_HD float median_of_3(float a, float b, float c) { return lane_max(lane_min(a
 B2R_HD float median_of_5(float a, float b, float c, float d, float e) {  // Sampling.hpp:13-21
 	return median_of_3(lane_max(lane_min(a, b), lane_min(c, d)), lane_min(lane_max(a, b), lane_max(c, d)), e);
 }
+// median of 8 (this repo's even-K definition: mean of the two middle order statistics) with Batcher's 19 compare-exchanges in
+// registers; each exchange outputs a permutation of its inputs, so the result equals sorting the eight values.
+#define B2R_CE(a, b) { const bool sw_ = b < a; const float lo_ = sw_ ? b : a; b = sw_ ? a : b; a = lo_; }
+B2R_HD float median_of_8(float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7) {
+	B2R_CE(v0, v1); B2R_CE(v2, v3); B2R_CE(v4, v5); B2R_CE(v6, v7);
+	B2R_CE(v0, v2); B2R_CE(v1, v3); B2R_CE(v4, v6); B2R_CE(v5, v7);
+	B2R_CE(v1, v2); B2R_CE(v5, v6);
+	B2R_CE(v0, v4); B2R_CE(v1, v5); B2R_CE(v2, v6); B2R_CE(v3, v7);
+	B2R_CE(v2, v4); B2R_CE(v3, v5);
+	B2R_CE(v1, v2); B2R_CE(v3, v4); B2R_CE(v5, v6);
+	return (v3 + v4) * 0.5f;
+}
 B2R_HD float aces_curve(float x) { return (x * (x + 0.0245786f) - 0.000090537f) / (x * (0.983729f * x + 0.4329510f) + 0.238081f); }  // Color.hpp:47-49
 B2R_HD void aces_tonemap(float* r, float* g, float* b) {  // tonemapping(Vec8f&...), Color.hpp:66-73
 	float x = aces_curve(*r * 0.59719f + *g * 0.35458f + *b * 0.04823f);

@@ -37,6 +37,7 @@ def hostcheck():
     lib.hc_power.restype = f; lib.hc_power.argtypes = [f, f]
     lib.hc_power_over_f.restype = f; lib.hc_power_over_f.argtypes = [f, f]
     lib.hc_median5.restype = f; lib.hc_median5.argtypes = [C.c_void_p]
+    lib.hc_median8.restype = f; lib.hc_median8.argtypes = [C.c_void_p]
     lib.hc_sphere_closest.restype = C.c_int; lib.hc_sphere_closest.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(f)]
     lib.hc_sphere_any.restype = C.c_int; lib.hc_sphere_any.argtypes = [C.c_void_p, C.c_void_p, f]
     lib.hc_pcg3.argtypes = [u, C.c_void_p, C.POINTER(u), u, C.POINTER(u)]

@@ -98,6 +98,7 @@ float hc_power(float f, float g) { return power_heuristic(f, g); }
 float hc_power_over_f(float f, float g) { return power_heuristic_over_f(f, g); }
 float hc_median5(const float v[5]) { return median_of_5(v[0], v[1], v[2], v[3], v[4]); }
 void hc_tonemap(float rgb[3]) { aces_tonemap(rgb, rgb + 1, rgb + 2); }
+float hc_median8(const float v[8]) { return median_of_8(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]); }
 // closest / any sphere tests: returns 1 and the distance when the candidate is valid
 int hc_sphere_closest(const float s[4], const float ray[6], float* d) { return sphere_hit_closest(s[0], s[1], s[2], s[3], ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], d) ? 1 : 0; }
 int hc_sphere_any(const float s[4], const float ray[6], float tfar) { return sphere_hit_any(s[0], s[1], s[2], s[3], ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], tfar) ? 1 : 0; }

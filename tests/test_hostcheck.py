@@ -53,6 +53,9 @@ def test_scalar_math_bit_exact(hostcheck):
         assert float(L.orc_power_heuristic_over_f(f(u0), f(u1))) == float(hostcheck.hc_power_over_f(f(u0), f(u1)))
         v5 = rs.rand(5).astype(np.float32)
         assert float(L.orc_median5(p(v5))) == float(hostcheck.hc_median5(v5.ctypes.data))
+        v8 = rs.choice(rs.rand(5).astype(np.float32), 8) if rs.rand() < 0.3 else rs.rand(8).astype(np.float32)  # with and without ties
+        L.orc_median_k.restype = C.c_float; hostcheck.hc_median8.restype = C.c_float
+        assert float(L.orc_median_k(p(np.ascontiguousarray(v8)), 8)) == float(hostcheck.hc_median8(np.ascontiguousarray(v8).ctypes.data))
 
 
 def test_sphere_tests_match_bruteforce_oracle(hostcheck):
