@@ -30,6 +30,16 @@ __device__ __forceinline__ void stat_add(unsigned long long* stats, int which, u
 	if (lane_id() == 0 && s) atomicAdd(stats + which, static_cast<unsigned long long>(s));
 }
 
+// Shared-memory reads through a 32-bit shared-window address. nvcc for sm_100a re-derives the window base of a __shared__ array
+// (S2UR SR_CgaCtaId + UMOV + ULEA) next to its uses, loops included; an address taken once and kept in a (uniform) register does not.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+	uint32_t a; asm volatile("mov.u32 %0, %1;" : "=r"(a) : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))));  // opaque: computed once, not rematerialised
+	return a;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+	float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+	return v;
+}
 __device__ __forceinline__ PathState load_path(const QueueDev& q, int side, uint32_t i) {
 	const float4 a = q.A[side][i], b = q.B[side][i];
 	PathState s; s.ox = a.x; s.oy = a.y; s.oz = a.z; s.dx = a.w; s.dy = b.x; s.dz = b.y; s.pdf = b.z; s.pid = __float_as_uint(b.w);
@@ -123,6 +133,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 	}
 	__syncthreads();
 
+	const uint32_t a_prim = smem_addr(s_prim), a_pre = smem_addr(s_pre);
 	uint32_t queued = 0, s_queued = 0;         // hits / shadow rays waiting in shared memory (CTA-uniform)
 	uint32_t base = blockIdx.x * kBruteBlock;
 	for (;;) {
@@ -131,13 +142,13 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 			// ---------------- phase 1: one ray per thread, closest hit over every sphere (ties -> lowest BVH-order index, strict <, Q6)
 			const uint32_t i = base + threadIdx.x;
 			const bool live = i < n_in;
-			float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0;
+			float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0; uint32_t pid0 = 0;
 			if (live) {
 				if (FIRST) {
 					const uint32_t sl0 = div_by(i, p.frame.npix, p.frame.npix_magic);
 					const PathState s0 = primary_path(p.frame, p.batch->acc[sl0], sl0, i - sl0 * p.frame.npix);
 					ox = s0.ox; oy = s0.oy; oz = s0.oz; dx = s0.dx; dy = s0.dy; dz = s0.dz;
-					rad_zero(p.rad, p.frame.npix, s0.pid);  // a path's radiance starts at 0 here (coalesced stores); contributions are added after a CTA barrier
+					pid0 = s0.pid; rad_zero(p.rad, p.frame.npix, s0.pid);  // a path's radiance starts at 0 here (coalesced stores); contributions are added after a CTA barrier
 				} else {
 					const float4 a = p.q.A[side][i], b = p.q.B[side][i];
 					ox = a.x; oy = a.y; oz = a.z; dx = a.w; dy = b.x; dz = b.y;
@@ -158,8 +169,8 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 #pragma unroll 3
 					for (uint32_t j = 0; j < cnt; j++) {
 						float d; bool h;
-						if (FIRST) { const float4 q = s_pre[FIRST ? j : 0]; h = sphere_hit_prepared(SpherePre{q.x, q.y, q.z, q.w}, dx, dy, dz, &d); }
-						else { const float4 sp = s_prim[j]; h = sphere_hit_closest(sp.x, sp.y, sp.z, sp.w, ox, oy, oz, dx, dy, dz, &d); }
+						if (FIRST) { const float4 q = lds_f4(a_pre + j * 16u); h = sphere_hit_prepared(SpherePre{q.x, q.y, q.z, q.w}, dx, dy, dz, &d); }
+						else { const float4 sp = lds_f4(a_prim + j * 16u); h = sphere_hit_closest(sp.x, sp.y, sp.z, sp.w, ox, oy, oz, dx, dy, dz, &d); }
 						if (h && d < best) { best = d; prim = static_cast<int32_t>(first + j); }
 					}
 					if (COUNT) c_sphere += cnt;
@@ -178,7 +189,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 			uint32_t n_hits;
 			const uint32_t slot = queued + block_rank(is_hit, s_cnt_a, &n_hits);
 			if (is_hit) {
-				s_hit_i[slot] = i; s_hit_t[slot] = best; s_hit_prim[slot] = prim;
+				s_hit_i[slot] = FIRST ? pid0 : i; s_hit_t[slot] = best; s_hit_prim[slot] = prim;  // bounce 0 queues the path id itself (no queue record to index)
 				if (FIRST) { s_hit_d[0][slot] = dx; s_hit_d[FIRST ? 1 : 0][slot] = dy; s_hit_d[FIRST ? 2 : 0][slot] = dz; }
 			}
 			queued += n_hits;
@@ -196,10 +207,9 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 			if (shade) {
 				const uint32_t hi = s_hit_i[qi]; const float depth = s_hit_t[qi]; const int32_t hprim = s_hit_prim[qi];
 				if (FIRST) {
-					const uint32_t sl = div_by(hi, p.frame.npix, p.frame.npix_magic), t = hi - sl * p.frame.npix;
 					s.ox = p.frame.cam.px; s.oy = p.frame.cam.py; s.oz = p.frame.cam.pz;
 					s.dx = s_hit_d[0][FIRST ? qi : 0]; s.dy = s_hit_d[FIRST ? 1 : 0][FIRST ? qi : 0]; s.dz = s_hit_d[FIRST ? 2 : 0][FIRST ? qi : 0];
-					s.tr = s.tg = s.tb = 1.0f; s.pdf = 0.0f; s.pid = (sl << 26) | t;
+					s.tr = s.tg = s.tb = 1.0f; s.pdf = 0.0f; s.pid = hi;
 				} else s = load_path(p.q, side, hi);
 				pid = s.pid;
 				const uint32_t acc = p.batch->acc[s.pid >> 26], seed = pixel_seed(s.pid & kPixMask, p.frame.max_bounces);
@@ -259,10 +269,14 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 			bool occluded = !test;
 			if (n_tiles == 1) {
 				if (COUNT && test) c_sphere += sc.n_prims;
-#pragma unroll 3
-				for (uint32_t j = 0; j < sc.n_prims; j++) {
-					const float4 sp = s_prim[j];
-					if (!occluded && sphere_hit_any(sp.x, sp.y, sp.z, sp.w, sox, soy, soz, sdx, sdy, sdz, stfar)) occluded = true;
+				for (uint32_t j0 = 0; j0 < sc.n_prims; j0 += 3u) {  // three spheres per early-out vote
+#pragma unroll
+					for (uint32_t u = 0; u < 3u; u++) {
+						if (j0 + u < sc.n_prims) {
+							const float4 sp = lds_f4(a_prim + (j0 + u) * 16u);
+							if (!occluded && sphere_hit_any(sp.x, sp.y, sp.z, sp.w, sox, soy, soz, sdx, sdy, sdz, stfar)) occluded = true;
+						}
+					}
 					if (__all_sync(0xffffffffu, occluded)) break;
 				}
 			} else {
