@@ -330,9 +330,10 @@ def main():
         primaries = wl["w"] * wl["h"] * (step_samples // world) * args.steps
         if kt["bounce_brute"][1]:
             # DESIGN.md "Algorithmic bytes": 44 B path record read per non-primary ray + 44 B written per continuing path (= every
-            # non-primary ray was written once) + 24 B radiance read-modify-write per contribution + 12 B per dropped path
+            # non-primary ray was written once) + 12 B radiance entry started per primary path + 24 B radiance read-modify-write
+            # per contribution + 12 B per dropped path
             name, ms, n = "k_bounce_brute", kt["bounce_brute"][0], kt["bounce_brute"][1]
-            alg = 88.0 * (ext - primaries) + 24.0 * events + 12.0 * dropped
+            alg = 88.0 * (ext - primaries) + 12.0 * primaries + 24.0 * events + 12.0 * dropped
         else:
             # dominant kernel of the BVH pipeline = closest-hit traversal: 32 B ray read + 8 B hit written per extension ray from HBM;
             # node/sphere fetches are L2-resident and reported separately through the box/sphere counters
@@ -356,6 +357,8 @@ def main():
                 tr = json.load(open(ncu)).get(args.workload, {}).get(name)
                 if tr:
                     roof["traffic"] = tr["dram_bytes_per_launch"]; roof["traffic_source"] = tr.get("source")
+                    if tr.get("issue_slots_busy_pct") is not None:  # the binding resource of these kernels (ncu, not live): instruction issue
+                        roof["issue"] = {"slots_busy_pct": tr["issue_slots_busy_pct"], "source": "ncu smsp__issue_active, same capture as traffic"}
             except Exception:
                 pass
 

@@ -676,6 +676,11 @@ void orc_get_camera_raw(const Ctx* c, float out[11]) {
 	out[3] = c->cam_orient.w; out[4] = c->cam_orient.x; out[5] = c->cam_orient.y; out[6] = c->cam_orient.z;
 	out[7] = c->half_width; out[8] = c->half_height; out[9] = c->cam_z; out[10] = c->exposure;
 }
+// one camera ray for caller-supplied sub-pixel samples (Camera::generate_ray, Camera.hpp:80-88): known-answer tap
+void orc_generate_ray_at(const Ctx* c, int32_t x, int32_t y, const float samples[2], float out[6]) {
+	V3 o, d; generate_ray(*c, x, y, samples, &o, &d);
+	out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = d.x; out[4] = d.y; out[5] = d.z;
+}
 void orc_reset(Ctx* c) { c->accumulations = 0; std::fill(c->accumulator.begin(), c->accumulator.end(), 0.0f); }  // Renderer.hpp:64-67
 void orc_set_accumulations(Ctx* c, uint32_t acc) { c->accumulations = acc; }
 uint32_t orc_get_accumulations(const Ctx* c) { return c->accumulations; }
@@ -751,6 +756,14 @@ void orc_trace_closest(const Ctx* c, const float* rays, uint32_t n, float* tfar_
 	for (uint32_t i = 0; i < n; i++) {
 		const float* r = rays + static_cast<size_t>(i) * 6; float tf = FLT_MAX; int32_t pid = -1;
 		for (size_t p = 0; p < c->bvh.prims.size(); p++) sphere_closest_fma(c->bvh.prims[p], static_cast<int32_t>(p), r[0], r[1], r[2], r[3], r[4], r[5], tf, pid);
+		tfar_out[i] = tf; prim_out[i] = pid;
+	}
+}
+// the scalar-tail formula of the closest-hit loop (BVH.hpp:270-286) for every ray: known-answer tap
+void orc_trace_closest_scalar(const Ctx* c, const float* rays, uint32_t n, float* tfar_out, int32_t* prim_out) {
+	for (uint32_t i = 0; i < n; i++) {
+		const float* r = rays + static_cast<size_t>(i) * 6; float tf = FLT_MAX; int32_t pid = -1;
+		for (size_t p = 0; p < c->bvh.prims.size(); p++) sphere_closest_scalar(c->bvh.prims[p], static_cast<int32_t>(p), r[0], r[1], r[2], r[3], r[4], r[5], tf, pid);
 		tfar_out[i] = tf; prim_out[i] = pid;
 	}
 }

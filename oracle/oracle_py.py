@@ -19,7 +19,7 @@ def build(force=False):
     need = force or not all(os.path.exists(os.path.join(_HERE, n)) for n in ("liboracle.so", "liboracle_fast.so"))
     if need:
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so", "liboracle_fast.so"], stdout=subprocess.DEVNULL)
-    if os.path.isdir("/root/reference") and (force or not os.path.exists(os.path.join(_HERE, "_ref", "librefrng.so"))):
+    if os.path.isdir("/root/reference") and (force or not all(os.path.exists(os.path.join(_HERE, "_ref", n)) for n in ("librefrng.so", "librefsampling.so", "librefbvh.so"))):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -32,6 +32,7 @@ def _load(fast=False):
     lib.orc_set_camera_lookat.argtypes = [_p, _fp, _fp, _f, _f]
     lib.orc_set_camera_raw.argtypes = [_p, _fp, _fp, _f, _f, _f, _f]
     lib.orc_get_camera_raw.argtypes = [_p, _fp]
+    lib.orc_generate_ray_at.argtypes = [_p, _i, _i, _fp, _fp]
     lib.orc_reset.argtypes = [_p]
     lib.orc_set_accumulations.argtypes = [_p, _u]
     lib.orc_get_accumulations.restype = _u; lib.orc_get_accumulations.argtypes = [_p]
@@ -48,6 +49,7 @@ def _load(fast=False):
     lib.orc_generate_rays.argtypes = [_p, _u, _fp]
     lib.orc_trace_closest.argtypes = [_p, _fp, _u, _fp, _p]
     lib.orc_trace_shadow.argtypes = [_p, _fp, _fp, _u, _p]
+    lib.orc_trace_closest_scalar.argtypes = [_p, _fp, _u, _fp, _p]
     lib.orc_build_bvh.restype = _u; lib.orc_build_bvh.argtypes = [_p, _u, _p, _p, _p]
     for name, res, args in [
         ("orc_hash_u32", _u, [_u]), ("orc_hash_2d", _u, [_u, _u]), ("orc_pcg_generate", _u, [_up]),

@@ -1,0 +1,1 @@
+#include "b2r_mini_glm.hpp"

@@ -5,6 +5,14 @@
 * rng_kat.json    — outputs of the reference's OWN Random.hpp/Bitmanip.hpp, compiled verbatim into oracle/_ref/librefrng.so
                     (oracle/Makefile `ref`): hash_u32, hash_2d, pcg streams, rand_bounded_int, make_unit_float, bitreverse.
                     These pin the oracle's RNG layer to the reference itself.
+* sampling_kat.json — outputs of the reference's OWN Sampling.hpp, VectorMath.hpp:581-662 and Color.hpp:30-74, compiled verbatim into
+                    oracle/_ref/librefsampling.so: fast_sincos/asin/atan2, median 3/5, hemisphere, orthonormal_basis, tangent_space,
+                    to_local/to_world, conePdf/spherePdf, sample_direction_to_sphere, powerHeuristic(_over_f), ACES tonemapping
+                    (scalar and Vec8f); and of Camera.hpp:5-59,81-87 (Projection, View, generate_ray). These pin the oracle's
+                    sampling / scalar-math / tonemap / camera layer to the reference itself.
+* bvh_kat.json    — outputs of the reference's OWN BVH builder (BVH.hpp:17-87,91-206) and sphere loops (:239-287 closest hit — AVX2+FMA block and
+                    scalar tail — and :292-304 shadow), compiled verbatim into oracle/_ref/librefbvh.so: digests of node arrays and leaf
+                    order for the default and random scenes, Node::half_area() values (Q17), hit distances / ids / occlusion flags.
 * survey_kat.json — the known-answer table of SURVEY.md §8c (derived from the same reference file), transcribed.
 * oracle_frames.json — outputs of the ORACLE (not the reference, which cannot be built: SURVEY §8c) on small inputs: bucket-sum
                     checksums, counters, BVH order. They pin the oracle against accidental change and give the GPU tests a
@@ -51,6 +59,215 @@ def gen_rng():
         for rng in (1, 2, 3, 100, 1000):
             st = u(s0); out["bounded"].append([s0, rng, ref.ref_rand_bounded_int(C.byref(st), u(rng))])
     json.dump(out, open(os.path.join(HERE, "golden", "rng_kat.json"), "w"), indent=0)
+
+
+def ref_sampling_lib():
+    oracle_py.build()
+    ref = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "librefsampling.so"))
+    f = C.c_float
+    for n in ("ref_fast_asin", "ref_fast_atan2", "ref_median3", "ref_median5", "ref_cone_pdf", "ref_sphere_pdf", "ref_power_heuristic", "ref_power_heuristic_over_f"):
+        getattr(ref, n).restype = f
+    ref.ref_fast_asin.argtypes = [f]; ref.ref_fast_atan2.argtypes = [f, f]; ref.ref_median3.argtypes = [f, f, f]; ref.ref_median5.argtypes = [C.c_void_p]
+    ref.ref_cone_pdf.argtypes = [f]; ref.ref_sphere_pdf.argtypes = [f, f]; ref.ref_power_heuristic.argtypes = [f, f]; ref.ref_power_heuristic_over_f.argtypes = [f, f]
+    ref.ref_fast_sincos.argtypes = [f, C.POINTER(f), C.POINTER(f)]
+    ref.ref_hemisphere.argtypes = [f, f, C.c_void_p]
+    for n in ("ref_orthonormal_basis", "ref_tangent_space"):
+        getattr(ref, n).argtypes = [C.c_void_p, C.c_void_p]
+    for n in ("ref_to_local", "ref_to_world"):
+        getattr(ref, n).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    ref.ref_sample_direction_to_sphere.argtypes = [C.c_void_p, f, f, f, f, f, C.c_void_p]
+    ref.ref_tonemap_scalar.argtypes = [C.c_void_p]; ref.ref_tonemap_vec8.argtypes = [C.c_void_p] * 3
+    return ref
+
+
+def sampling_inputs(seed=20261018, n=160):
+    """The inputs of the sampling known-answer vectors: shared by the generator and by the live cross-check test."""
+    rs = np.random.RandomState(seed); F = np.float32
+    unit = rs.randn(n, 3); unit = (unit / np.linalg.norm(unit, axis=1, keepdims=True)).astype(F)
+    near_pole = np.array([[1e-4, 0, -1], [0, 3e-4, -0.99999994], [0, 0, -1], [0, 0, 1], [1, 0, 0], [0, -1, 0], [2e-4, -1e-4, -0.9999999]], F)
+    return {
+        "sincos": np.concatenate([rs.uniform(0, 2 * np.pi, n), [0.0, np.pi / 2, np.pi, 2 * np.pi, 6.2831855, -1.0, 40.0, 1e-30]]).astype(F),
+        "asin": np.concatenate([rs.uniform(-1.2, 1.2, n), [0.0, 1.0, -1.0, 1e-40]]).astype(F),
+        "atan2": np.concatenate([rs.uniform(-2, 2, (n, 2)), [[0, 0], [0, 1], [1, 0], [-1, 0], [0, -1], [1, 1], [-0.0, -1.0]]]).astype(F),
+        "median": rs.rand(n, 5).astype(F),
+        "unit01": np.concatenate([rs.rand(n, 2), [[0, 0], [1, 1], [1, 0], [0, 1], [0.5, 0.25]]]).astype(F),
+        "normals": np.concatenate([unit, near_pole]).astype(F),
+        "vectors": rs.uniform(-1, 1, (n + len(near_pole), 3)).astype(F),
+        # sample_direction_to_sphere: sin^2(theta_max) spread over both branches of the small-angle switch, centre distance, two uniforms
+        "cone": np.stack([rs.rand(n) ** 6, rs.uniform(0.05, 400, n), rs.rand(n), rs.rand(n)], axis=1).astype(F),
+        "pairs": np.concatenate([rs.rand(n, 2) * 5, [[0, 0], [1e-4, 1e-4], [3, 0]]]).astype(F),
+        "rgb": np.concatenate([rs.rand(n, 3) * 4, rs.rand(16, 3) * 1e-3, [[0, 0, 0], [100, 50, 1]]]).astype(F),
+    }
+
+
+def eval_sampling(fn, inp):
+    """fn: dict of callables with the ref_* signatures (reference library or oracle adapter). Returns hex-float records."""
+    f = C.c_float; H = lambda a: [float(v).hex() for v in np.asarray(a, np.float32).ravel()]
+    out = {k: [] for k in ("sincos", "asin", "atan2", "median3", "median5", "hemisphere", "onb", "tangent", "to_local", "to_world", "cone_pdf", "sphere_pdf",
+                           "sample_sphere", "power", "power_over_f", "tonemap")}
+    for x in inp["sincos"]:
+        s, c = f(), f(); fn["sincos"](f(x), C.byref(s), C.byref(c)); out["sincos"].append(H([s.value, c.value]))
+    for x in inp["asin"]:
+        out["asin"].append(H([fn["asin"](f(x))]))
+    for y, x in inp["atan2"]:
+        out["atan2"].append(H([fn["atan2"](f(y), f(x))]))
+    for v in inp["median"]:
+        v = np.ascontiguousarray(v)
+        if "median3" in fn:
+            out["median3"].append(H([fn["median3"](f(v[0]), f(v[1]), f(v[2]))]))
+        out["median5"].append(H([fn["median5"](v.ctypes.data)]))
+    for t, s in inp["unit01"]:
+        o = np.zeros(3, np.float32); fn["hemisphere"](f(t), f(s), o.ctypes.data); out["hemisphere"].append(H(o))
+    for nrm, vec in zip(inp["normals"], inp["vectors"]):
+        nrm = np.ascontiguousarray(nrm); vec = np.ascontiguousarray(vec)
+        o6 = np.zeros(6, np.float32); fn["onb"](nrm.ctypes.data, o6.ctypes.data); out["onb"].append(H(o6))
+        q = np.zeros(4, np.float32); fn["tangent"](nrm.ctypes.data, q.ctypes.data); out["tangent"].append(H(q))
+        o = np.zeros(3, np.float32); fn["to_local"](q.ctypes.data, vec.ctypes.data, o.ctypes.data); out["to_local"].append(H(o))
+        o = np.zeros(3, np.float32); fn["to_world"](q.ctypes.data, vec.ctypes.data, o.ctypes.data); out["to_world"].append(H(o))
+    for (s2, cd, t, s), wc in zip(inp["cone"], inp["normals"]):
+        wc = np.ascontiguousarray(wc); r2 = np.float32(s2 * cd * cd)
+        o5 = np.zeros(5, np.float32); fn["sample_sphere"](wc.ctypes.data, f(s2), f(cd), f(r2), f(t), f(s), o5.ctypes.data); out["sample_sphere"].append(H(o5))
+        out["sphere_pdf"].append(H([fn["sphere_pdf"](f(r2), f(np.float32(cd * cd)))]))
+        if "cone_pdf" in fn:
+            out["cone_pdf"].append(H([fn["cone_pdf"](f(t))]))
+    for a, b in inp["pairs"]:
+        out["power"].append(H([fn["power"](f(a), f(b))])); out["power_over_f"].append(H([fn["power_over_f"](f(a), f(b))]))
+    for rgb in inp["rgb"]:
+        o = np.ascontiguousarray(rgb).copy(); fn["tonemap"](o.ctypes.data); out["tonemap"].append(H(o))
+    return out
+
+
+def ref_sampling_fns(ref):
+    def tonemap_vec8(p):  # lane 0 of the Vec8f overload Renderer::Render uses (Renderer.hpp:461-473), checked against the scalar overload's formula too
+        rgb = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), (3,))
+        r, g, b = (np.full(8, rgb[i], np.float32) for i in range(3))
+        ref.ref_tonemap_vec8(r.ctypes.data, g.ctypes.data, b.ctypes.data)
+        rgb[0], rgb[1], rgb[2] = r[0], g[0], b[0]
+    return {"sincos": ref.ref_fast_sincos, "asin": ref.ref_fast_asin, "atan2": ref.ref_fast_atan2, "median3": ref.ref_median3, "median5": ref.ref_median5,
+            "hemisphere": ref.ref_hemisphere, "onb": ref.ref_orthonormal_basis, "tangent": ref.ref_tangent_space, "to_local": ref.ref_to_local,
+            "to_world": ref.ref_to_world, "cone_pdf": ref.ref_cone_pdf, "sphere_pdf": ref.ref_sphere_pdf, "sample_sphere": ref.ref_sample_direction_to_sphere,
+            "power": ref.ref_power_heuristic, "power_over_f": ref.ref_power_heuristic_over_f, "tonemap": tonemap_vec8}
+
+
+def camera_inputs(seed=20261018, n=24):
+    """(eye, dir, W, H, focal_mm) set-ups — the default scene's camera (Application.cpp:95-100), C3's, and random ones — each with
+    a few pixels and sub-pixel samples."""
+    rs = np.random.RandomState(seed); F = np.float32
+    cams = [((-0.2, 0.3, 1.0), (0.1, -0.4, -1.0), 1280, 720, 40.0), ((0.0, 60.0, 300.0), (0.0, 0.0, -1.0), 1920, 1088, 50.0),
+            ((1.0, 2.0, 3.0), (0.0, -1.0, 1e-3), 640, 368, 24.0), ((0.0, 0.0, 0.0), (0.0, 0.0, 1.0), 320, 192, 85.0)]
+    for _ in range(n):
+        d = rs.randn(3); cams.append((tuple(rs.uniform(-50, 50, 3)), tuple(d), int(rs.randint(1, 240)) * 16, int(rs.randint(1, 135)) * 16, float(rs.uniform(12, 200))))
+    out = []
+    for eye, d, w, h, fl in cams:
+        px = [(0, 0), (w - 1, h - 1), (w // 2, h // 2)] + [(int(rs.randint(0, w)), int(rs.randint(0, h))) for _ in range(5)]
+        out.append({"eye": [float(F(v)) for v in eye], "dir": [float(F(v)) for v in d], "w": w, "h": h, "focal": float(F(fl)),
+                    "pixels": [[x, y, float(F(rs.rand())), float(F(rs.rand()))] for x, y in px]})
+    return out
+
+
+def eval_camera_ref(ref, cams):
+    H = lambda a: [float(v).hex() for v in np.asarray(a, np.float32).ravel()]
+    f = C.c_float; ref.ref_generate_ray.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, f, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    rows = []
+    for c in cams:
+        eye = np.array(c["eye"], np.float32); d = np.array(c["dir"], np.float32)
+        for x, y, s0, s1 in c["pixels"]:
+            smp = np.array([s0, s1], np.float32); o6 = np.zeros(6, np.float32); cam7 = np.zeros(7, np.float32)
+            ref.ref_generate_ray(eye.ctypes.data, d.ctypes.data, c["w"], c["h"], f(c["focal"]), x, y, smp.ctypes.data, o6.ctypes.data, cam7.ctypes.data)
+            rows.append(H(o6) + H(cam7))
+    return rows
+
+
+def eval_camera_oracle(cams):
+    """the oracle's Camera restatement on the same inputs: ray (6 floats) + orient wxyz, half_width, half_height, z"""
+    H = lambda a: [float(v).hex() for v in np.asarray(a, np.float32).ravel()]
+    rows = []
+    for c in cams:
+        o = oracle_py.Oracle(c["w"], c["h"], max_bounces=2, K=1)
+        o.L.orc_set_camera_lookat(o.h, oracle_py.farr(*c["eye"]), oracle_py.farr(*c["dir"]), c["focal"], 1.0)
+        raw = o.camera_raw()
+        for x, y, s0, s1 in c["pixels"]:
+            o6 = (C.c_float * 6)(); o.L.orc_generate_ray_at(o.h, x, y, oracle_py.farr(s0, s1), o6)
+            rows.append(H(o6[:]) + H(raw[3:10]))
+        o.close()
+    return rows
+
+
+def gen_sampling():
+    ref = ref_sampling_lib()
+    out = eval_sampling(ref_sampling_fns(ref), sampling_inputs())
+    out["camera"] = eval_camera_ref(ref, camera_inputs())
+    out["_inputs"] = "tests/gen_golden.py sampling_inputs(seed=20261018, n=160)"
+    json.dump(out, open(os.path.join(HERE, "golden", "sampling_kat.json"), "w"), indent=0)
+
+
+# ---------------------------------------------------------------- reference BVH builder and sphere loops (oracle/_ref/librefbvh.so)
+def ref_bvh_lib():
+    oracle_py.build()
+    ref = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "librefbvh.so"))
+    ref.ref_bvh_build.restype = C.c_uint32; ref.ref_bvh_build.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    ref.ref_node_half_area.restype = C.c_float; ref.ref_node_half_area.argtypes = [C.c_void_p, C.c_void_p]
+    ref.ref_intersect_closest.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    ref.ref_intersect_shadow.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    return ref
+
+
+def bvh_scenes():
+    """(name, geometry) pairs of the BVH known-answer vectors: no two spheres share a centroid coordinate except in `default`
+    (whose nine spheres sit inside the insertion-sort range of both std::sort implementations, SURVEY Q19)."""
+    out = [("default", scenes.default_scene()["geometry"])]
+    for n in (1, 2, 3, 4, 5, 9, 33, 100, 1000, 5000):
+        out.append((f"random{n}", scenes.random_scene(n)["geometry"]))
+    out.append(("random777_light_every_10", scenes.random_scene(777, light_every=10, seed=0xB0B)["geometry"]))
+    return [(k, np.ascontiguousarray(g)) for k, g in out]
+
+
+def bvh_digest(nodes_bytes, prims):
+    """sha256 of the 32-byte node records and of the reordered spheres' named fields (the records' padding is not compared)."""
+    fields = np.concatenate([prims["position"].astype(np.float32).view(np.uint32), prims["radius_sq"].astype(np.float32).view(np.uint32)[:, None],
+                             prims["material_ID"].astype(np.int32).view(np.uint32)[:, None]], axis=1)
+    return {"n_nodes": len(nodes_bytes) // 32, "sha256_nodes": hashlib.sha256(nodes_bytes).hexdigest(), "sha256_prims": hashlib.sha256(fields.tobytes()).hexdigest()}
+
+
+def ref_bvh_build(ref, geo):
+    n = len(geo); nodes = np.zeros((max(2 * n - 1, 1), 32), np.uint8); prims = np.zeros(n, geo.dtype)
+    nn = ref.ref_bvh_build(geo.ctypes.data, n, nodes.ctypes.data, prims.ctypes.data)
+    return nodes[:nn].tobytes(), prims
+
+
+def intersect_inputs(seed=20261018):
+    """seeded rays for the sphere-loop vectors, against the `default` and `random100` scenes in the reference's BVH leaf order"""
+    rs = np.random.RandomState(seed); out = []
+    for scene_name, span in (("default", 3.0), ("random100", 150.0)):
+        for n in (256, 64, 8):      # multiples of 8: every ray goes through the AVX2+FMA block (BVH.hpp:250-268)
+            rays = np.zeros((n, 6), np.float32); rays[:, :3] = rs.uniform(-span, span, (n, 3)); d = rs.randn(n, 3); rays[:, 3:] = d / np.linalg.norm(d, axis=1, keepdims=True)
+            out.append((scene_name, "simd", rays, rs.uniform(0.5, 2 * span, n).astype(np.float32)))
+        for n in (7, 5, 1):         # fewer than 8: every ray goes through the scalar tail (:270-286)
+            rays = np.zeros((n, 6), np.float32); rays[:, :3] = rs.uniform(-span, span, (n, 3)); d = rs.randn(n, 3); rays[:, 3:] = d / np.linalg.norm(d, axis=1, keepdims=True)
+            out.append((scene_name, "tail", rays, rs.uniform(0.5, 2 * span, n).astype(np.float32)))
+    return out
+
+
+def gen_bvh():
+    ref = ref_bvh_lib()
+    out = {"builds": {}, "half_area": [], "intersect": []}
+    built = {}
+    for name, geo in bvh_scenes():
+        nodes, prims = ref_bvh_build(ref, geo); built[name] = prims
+        out["builds"][name] = bvh_digest(nodes, prims)
+    rs = np.random.RandomState(3)
+    for _ in range(40):  # Q17: Node::half_area() is d.y*d.z only
+        lo = rs.uniform(-10, 10, 3).astype(np.float32); hi = (lo + rs.uniform(0, 20, 3)).astype(np.float32)
+        out["half_area"].append([[float(v).hex() for v in lo], [float(v).hex() for v in hi], float(ref.ref_node_half_area(lo.ctypes.data, hi.ctypes.data)).hex()])
+    for scene_name, kind, rays, tfar in intersect_inputs():
+        prims = built[scene_name]; n = len(rays)
+        tf = np.zeros(n, np.float32); pid = np.zeros(n, np.int32); occ = np.zeros(n, np.uint8)
+        ref.ref_intersect_closest(prims.ctypes.data, len(prims), rays.ctypes.data, n, tf.ctypes.data, pid.ctypes.data)
+        ref.ref_intersect_shadow(prims.ctypes.data, len(prims), rays.ctypes.data, tfar.ctypes.data, n, occ.ctypes.data)
+        out["intersect"].append({"scene": scene_name, "kind": kind, "n": n, "sha256_tfar": hashlib.sha256(tf.tobytes()).hexdigest(),
+                                 "sha256_prim": hashlib.sha256(pid.tobytes()).hexdigest(), "sha256_occluded": hashlib.sha256(occ.tobytes()).hexdigest(),
+                                 "hits": int((pid >= 0).sum()), "occluded": int(occ.sum())})
+    json.dump(out, open(os.path.join(HERE, "golden", "bvh_kat.json"), "w"), indent=0)
 
 
 def gen_survey():
@@ -107,5 +324,5 @@ def gen_frames():
 
 
 if __name__ == "__main__":
-    gen_rng(); gen_survey(); gen_frames()
+    gen_rng(); gen_sampling(); gen_bvh(); gen_survey(); gen_frames()
     print("golden vectors written")
