@@ -14,6 +14,8 @@ struct vec3 {
 	explicit vec3(float s) : x(s), y(s), z(s) {}
 	vec3(float a, float b_, float c) : x(a), y(b_), z(c) {}
 	vec3& operator*=(float s) { x *= s; y *= s; z *= s; return *this; }
+	vec3& operator*=(const vec3& o) { x *= o.x; y *= o.y; z *= o.z; return *this; }
+	vec3& operator+=(const vec3& o) { x += o.x; y += o.y; z += o.z; return *this; }
 	float& operator[](int i) { return (&x)[i]; }
 	const float& operator[](int i) const { return (&x)[i]; }
 };
@@ -50,7 +52,6 @@ inline float mix(float a, float b, float t) { return a * (1.0f - t) + b * t; }  
 inline vec3 mix(vec3 a, vec3 b, float t) { return a * (1.0f - t) + b * t; }
 // ---- what Camera.hpp:5-59,81-87 needs (glm/geometric.inl, gtc/quaternion.inl, gtx/quaternion.inl as published)
 inline vec3 operator-(vec3 a) { return {-a.x, -a.y, -a.z}; }
-inline vec3& operator+=(vec3& a, vec3 b) { a.x += b.x; a.y += b.y; a.z += b.z; return a; }
 inline vec3 cross(vec3 x, vec3 y) { return {x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y}; }
 inline float atan(float x) { return std::atan(x); }
 inline vec3 operator*(quat q, vec3 v) {  // v + ((uv * q.w) + uuv) * 2
