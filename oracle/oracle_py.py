@@ -181,3 +181,67 @@ def tile_to_raster(buf_tileorder, width, height):
     a = np.asarray(buf_tileorder).reshape(buf_tileorder.shape[:-1] + (vt, ht, 16, 16))
     a = np.moveaxis(a, -2, -3)  # vt,16,ht,16
     return a.reshape(buf_tileorder.shape[:-1] + (height, width))
+
+
+# ---------------------------------------------------------------------------------------------- the reference itself
+REF_RENDERER_PATH = os.path.join(_HERE, "_ref", "librefrenderer.so")
+REF_MAX_BOUNCES = (1, 2, 4, 8, 16)  # Renderer<>'s max_bounces is a template argument: the values instantiated by ref_renderer_wrap.cpp
+ORC_SLOT_EXACT = 2  # oracle flag: closest-hit SIMD blocks of 8 + scalar tail by stream slot, exactly as BVH.hpp:250-286
+
+
+def have_reference_renderer():
+    return os.path.exists(REF_RENDERER_PATH)
+
+
+_ref_renderer = None
+
+
+def _ref_renderer_lib():
+    global _ref_renderer
+    if _ref_renderer is None:
+        L = C.CDLL(REF_RENDERER_PATH)
+        L.ref_renderer_create.restype = _p
+        L.ref_renderer_create.argtypes = [_p, _u, _p, _u, _p, _p, _f, _f, _p, _p, _i, _i, _u, _u, _u]
+        L.ref_renderer_destroy.argtypes = [_p]; L.ref_renderer_accumulate.argtypes = [_p, _u]; L.ref_renderer_set_accumulations.argtypes = [_p, _u]
+        L.ref_renderer_accumulations.restype = _u; L.ref_renderer_accumulations.argtypes = [_p]
+        L.ref_renderer_read_buckets.argtypes = [_p, _p]; L.ref_renderer_render.restype = C.c_int; L.ref_renderer_render.argtypes = [_p, _p, _u]
+        L.ref_renderer_light_count.restype = _u; L.ref_renderer_light_count.argtypes = [_p]
+        _ref_renderer = L
+    return _ref_renderer
+
+
+class ReferenceRenderer:
+    """The reference's OWN Renderer<> (Renderer.hpp) compiled from /root/reference by oracle/ref_renderer_build.sh — same calls as
+    Oracle: accumulate(n), buckets() -> [5][3][npix] (tile order), render() -> (acted, RGBA32F raster frame). K is fixed at 5."""
+
+    def __init__(self, scene, width, height, max_bounces=16):
+        if max_bounces not in REF_MAX_BOUNCES:
+            raise ValueError(f"max_bounces must be one of {REF_MAX_BOUNCES} (template instantiations)")
+        self.L = _ref_renderer_lib(); self.w, self.h = width, height
+        sd = _scene_dtypes()
+        self._geo = np.ascontiguousarray(scene["geometry"], dtype=sd[0]); self._mat = np.ascontiguousarray(scene["material"], dtype=sd[1])
+        cam = scene["camera"]; eye = farr(*cam["eye"]); d = farr(*cam["dir"]); amb = farr(*scene["ambient"])
+        hd = scene.get("hdri"); hp, hw, hh = None, 0, 0
+        if hd is not None:
+            self._hdri = np.ascontiguousarray(hd, dtype=np.float32); hp = self._hdri.ctypes.data; hh, hw = self._hdri.shape[:2]
+        self.hnd = self.L.ref_renderer_create(self._geo.ctypes.data, len(self._geo), self._mat.ctypes.data, len(self._mat), C.cast(eye, _p), C.cast(d, _p),
+                                              cam["focal_length"], cam["exposure"], C.cast(amb, _p), hp, hw, hh, width, height, max_bounces)
+        if not self.hnd:
+            raise RuntimeError("ref_renderer_create failed")
+
+    def close(self):
+        if self.hnd:
+            self.L.ref_renderer_destroy(self.hnd); self.hnd = None
+
+    def accumulate(self, n=1):
+        self.L.ref_renderer_accumulate(self.hnd, n)
+
+    def set_accumulations(self, acc):
+        self.L.ref_renderer_set_accumulations(self.hnd, acc)
+
+    def buckets(self):
+        out = np.zeros((5, 3, self.w * self.h), np.float32); self.L.ref_renderer_read_buckets(self.hnd, out.ctypes.data); return out
+
+    def render(self):
+        fb = np.zeros((self.h, self.w, 4), np.float32)
+        return bool(self.L.ref_renderer_render(self.hnd, fb.ctypes.data, fb.size)), fb

@@ -13,6 +13,9 @@
 * bvh_kat.json    — outputs of the reference's OWN BVH builder (BVH.hpp:17-87,91-206) and sphere loops (:239-287 closest hit — AVX2+FMA block and
                     scalar tail — and :292-304 shadow), compiled verbatim into oracle/_ref/librefbvh.so: digests of node arrays and leaf
                     order for the default and random scenes, Node::half_area() values (Q17), hit distances / ids / occlusion flags.
+* renderer_kat.json — outputs of the reference's OWN Renderer<>::Accumulate / Render (Renderer.hpp and everything it includes, compiled into
+                    oracle/_ref/librefrenderer.so by oracle/ref_renderer_build.sh): digests of the five bucket-sum planes and of the
+                    tonemapped RGBA32F frame for small renders of the default, random, white-furnace and sky/HDRI scenes.
 * survey_kat.json — the known-answer table of SURVEY.md §8c (derived from the same reference file), transcribed.
 * oracle_frames.json — outputs of the ORACLE (not the reference, which cannot be built: SURVEY §8c) on small inputs: bucket-sum
                     checksums, counters, BVH order. They pin the oracle against accidental change and give the GPU tests a
@@ -270,6 +273,52 @@ def gen_bvh():
     json.dump(out, open(os.path.join(HERE, "golden", "bvh_kat.json"), "w"), indent=0)
 
 
+# ---------------------------------------------------------------- the reference's own Renderer<> (oracle/_ref/librefrenderer.so)
+def renderer_cases():
+    """(name, scene, width, height, max_bounces, samples, first_sample) — small frames the reference renders in well under a second.
+    max_bounces is a template argument of Renderer<>: only the instantiated values (oracle_py.REF_MAX_BOUNCES) can be used."""
+    # (no zero-light scene: with MIS on the reference divides by the light count and reads prims[0] of an empty list, SURVEY Q15)
+    sky = scenes.bvh_test_scene(40, hdri=scenes.synthetic_hdri())
+    return [
+        ("default_64x48_mb8", scenes.default_scene(), 64, 48, 8, 5, 0),
+        ("default_160x96_mb16", scenes.default_scene(), 160, 96, 16, 10, 0),
+        ("default_96x64_mb16_from_acc60", scenes.default_scene(), 96, 64, 16, 5, 60),
+        ("default_64x64_mb1", scenes.default_scene(), 64, 64, 1, 5, 0),
+        ("default_64x64_mb2", scenes.default_scene(), 64, 64, 2, 5, 0),
+        ("random300_64x48_mb4", scenes.random_scene(300, light_every=20), 64, 48, 4, 5, 0),
+        ("random33_80x48_mb8_third_emissive", scenes.random_scene(33, light_every=3), 80, 48, 8, 5, 0),
+        ("random2000_48x32_mb16", scenes.random_scene(2000, light_every=100), 48, 32, 16, 5, 0),
+        ("sky_hdri_40_spheres_64x48_mb8", sky, 64, 48, 8, 5, 0),
+    ]
+
+
+def renderer_record(buckets, acted, frame):
+    return {"sha256_buckets": hashlib.sha256(np.ascontiguousarray(buckets, np.float32).tobytes()).hexdigest(), "render_acted": bool(acted),
+            "sha256_frame": hashlib.sha256(np.ascontiguousarray(frame, np.float32).tobytes()).hexdigest(),
+            "sum_rgb": [float(v) for v in np.asarray(buckets).sum(axis=(0, 2), dtype=np.float64)]}
+
+
+def gen_renderer():
+    oracle_py.build()
+    out = {}
+    for name, sc, w, h, mb, n, first in renderer_cases():
+        r = oracle_py.ReferenceRenderer(sc, w, h, mb)
+        if first:
+            r.set_accumulations(first)
+        r.accumulate(n)
+        acted, frame = r.render()
+        out[name] = renderer_record(r.buckets(), acted, frame)
+        r.close()
+    json.dump(out, open(os.path.join(HERE, "golden", "renderer_kat.json"), "w"), indent=0)
+    # actual values (not digests) for the tolerance-based GPU comparison: the reference's first sample (bucket 1, linear radiance, tile
+    # order) and its converged 200-spp tonemapped frame of the default scene at 160x96, max_bounces 16
+    r = oracle_py.ReferenceRenderer(scenes.default_scene(), 160, 96, 16)
+    r.accumulate(1); first = r.buckets()[1].copy()
+    r.accumulate(199); acted, frame = r.render(); r.close()
+    assert acted
+    np.savez_compressed(os.path.join(HERE, "golden", "reference_default_160x96_mb16.npz"), first_sample=first, frame_200spp=frame)
+
+
 def gen_survey():
     H = float.fromhex
     table = {
@@ -324,5 +373,5 @@ def gen_frames():
 
 
 if __name__ == "__main__":
-    gen_rng(); gen_sampling(); gen_bvh(); gen_survey(); gen_frames()
+    gen_rng(); gen_sampling(); gen_bvh(); gen_renderer(); gen_survey(); gen_frames()
     print("golden vectors written")

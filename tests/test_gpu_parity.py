@@ -375,3 +375,37 @@ def test_c3_converged_image_at_reduced_size():
     print(f"C3 scene 480x272 16 spp: divergent pixel fraction {frac:.3e}, tonemapped RMSE {rmse:.3e}, linear RMSE {rmse_lin:.3e}")
     assert rmse < 1e-3 and frac < 5e-3
     r.close()
+
+
+# ------------------------------------------------------------------------------------------------ against the reference itself
+def test_gpu_vs_reference_renderer_fixture():
+    """north_star's correctness check, literally: the GPU against the reference's own CPU Renderer::Accumulate / Render on the same scene,
+    camera, seeds and bounce count. The reference's outputs (oracle/_ref/librefrenderer.so, built from /root/reference by
+    oracle/ref_renderer_build.sh) are committed as tests/golden/reference_default_160x96_mb16.npz by tests/gen_golden.py."""
+    ref = np.load(os.path.join(G, "reference_default_160x96_mb16.npz"))
+    sc = scenes.default_scene(); w, h, mb = 160, 96, 16
+    r = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=5)
+    r.Accumulate(1)
+    frac = divergent_fraction(r.buckets_host()[1], ref["first_sample"])
+    r.Accumulate(199); assert r.Render()
+    rmse = float(np.sqrt(np.mean((r.framebuffer[..., :3] - ref["frame_200spp"][..., :3]) ** 2)))
+    print(f"GPU vs the reference's Renderer (default scene 160x96, max_bounces 16): divergent per-sample pixel fraction {frac:.3e}, 200-spp tonemapped RMSE {rmse:.3e}")
+    assert frac < 2e-3 and rmse < 1e-3
+    r.close()
+
+
+@pytest.mark.skipif(not oracle_py.have_reference_renderer(), reason="oracle/_ref/librefrenderer.so not present")
+def test_c1_full_size_gpu_vs_reference_renderer_live():
+    """BASELINE config C1 (default scene, 1280x720, 1 spp, max_bounces 8) on the GPU and through the reference's own Renderer::Accumulate
+    run here on the host cores; then 4 more samples and Renderer::Render (median of 5 + ACES) on both."""
+    sc = scenes.default_scene(); w, h, mb = 1280, 720, 8
+    ref = oracle_py.ReferenceRenderer(sc, w, h, mb); ref.accumulate(1); ref_first = ref.buckets()[1].copy()
+    g = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=5); g.Accumulate(1)
+    frac = divergent_fraction(g.buckets_host()[1], ref_first)
+    exact = float((g.buckets_host()[1].view(np.uint32) == ref_first.view(np.uint32)).all(axis=0).mean())
+    ref.accumulate(4); acted, ref_frame = ref.render(); ref.close()
+    g.Accumulate(4); assert g.Render() and acted
+    rmse = float(np.sqrt(np.mean((g.framebuffer[..., :3] - ref_frame[..., :3]) ** 2)))
+    print(f"C1 GPU vs the reference itself: divergent pixel fraction {frac:.3e} (bit-identical pixels {exact:.4f}), 5-spp frame RMSE {rmse:.3e}")
+    assert frac < 2e-3 and rmse < 5e-3  # 5 samples are far from converged: a divergent path moves its pixel visibly; the converged bound is tested above
+    g.close()
