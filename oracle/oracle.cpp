@@ -3,12 +3,20 @@
 // CPU restatement of the reference's hot path: Renderer::Accumulate (Renderer.hpp:73-434),
 // Renderer::Render (Renderer.hpp:436-478), the BVH builder (BVH.hpp:90-206), the brute-force and
 // stream-BVH intersection routines (BVH.hpp:219-404) and the stream machinery (DataStreams.hpp).
-// The reference itself cannot be compiled here (MSVC-only C++, glm / Agner Fog VCL / PPL absent;
-// SURVEY.md §8c), so this file is the checker the CUDA path is compared with. It is pinned by
-//   * the reference's own Random.hpp/Bitmanip.hpp compiled verbatim into oracle/_ref (the only part of
-//     the reference that builds with g++), see oracle/Makefile and tests/test_oracle_rng.py;
-//   * the known-answer vectors of SURVEY.md §8c, committed under tests/golden/.
-// Everything else is "parity unpinned" by the reference (it ships no tests or golden images).
+// PARITY IS PINNED against the reference itself. The reference is MSVC-only C++ with un-vendored dependencies (glm, Agner Fog VCL,
+// PPL, Vulkan ...), but its renderer is header-only, and with stand-ins for those dependencies (oracle/ref_shim/:
+// component-wise glm/VCL definitions, a thread-pool parallel_for, an Image stub) and six token-level syntax edits made on a
+// temporary copy at build time, g++ compiles it from /root/reference (oracle/Makefile `ref`, oracle/ref_renderer_build.sh; nothing
+// is copied into this repo, outputs go to the git-ignored oracle/_ref/):
+//   * _ref/librefrenderer.so — Renderer<>::Accumulate / Render with DataStreams.hpp, BVH.hpp, Scene.hpp, Camera.hpp, Sampling.hpp,
+//     Primitives.hpp, Random.hpp ...: THE REFERENCE, runnable. This file in its slot-exact mode (ORC_SLOT_EXACT) reproduces its bucket
+//     sums and tonemapped frames bit for bit (tests/test_oracle_ref_renderer.py, tests/golden/renderer_kat.json);
+//   * _ref/librefbvh.so — the BVH constructor and the three sphere loops (bit-identical node arrays and leaf order up to 100k spheres,
+//     tests/test_oracle_ref_bvh.py); _ref/librefsampling.so — Sampling.hpp, the scalar fast math, ACES tonemapping, Camera
+//     (tests/test_oracle_ref_sampling.py); _ref/librefrng.so — Random.hpp / Bitmanip.hpp (tests/test_oracle_rng.py).
+// What that does not pin: the author's MSVC binary (its /fp mode and std::sort tie order are unknown; see the canonical choices
+// below) and the stream-BVH traversal (`USEBVH`, disabled in the reference: BVH.hpp:320-358 is restated here, checked against
+// brute force).
 //
 // Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may load this
 // library. The product never links it.
