@@ -39,3 +39,17 @@ def test_no_cpu_fallback():
     with pytest.raises(b2r.B2RError) as e:
         b2r.Renderer(scenes.default_scene(), 64, 64)
     assert e.value.code == b2r.ERR_CUDA
+
+
+def test_reference_binding_builds_and_fails_loudly_without_gpu():
+    """include/b2r_reference_binding.hpp compiles against the reference's own headers (tests/refbinding, built where /root/reference
+    exists). On a CPU-only box the drop-in must fail loudly — no CPU fallback — while the reference's own Renderer<> in the same
+    program is untouched."""
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "refbinding", "refbinding")
+    if not os.path.exists(exe):
+        pytest.skip("tests/refbinding/refbinding not present (built only where /root/reference exists)")
+    if have_gpu():
+        pytest.skip("GPU box: run by tests/test_gpu_parity.py")
+    p = subprocess.run([exe, "5"], capture_output=True, text=True, timeout=120)
+    assert p.returncode != 0 and "libb2r" in (p.stderr + p.stdout)

@@ -409,3 +409,16 @@ def test_c1_full_size_gpu_vs_reference_renderer_live():
     print(f"C1 GPU vs the reference itself: divergent pixel fraction {frac:.3e} (bit-identical pixels {exact:.4f}), 5-spp frame RMSE {rmse:.3e}")
     assert frac < 2e-3 and rmse < 5e-3  # 5 samples are far from converged: a divergent path moves its pixel visibly; the converged bound is tested above
     g.close()
+
+
+def test_reference_binding_dropin_on_the_references_own_scene():
+    """include/b2r_reference_binding.hpp — the binding a maintainer would add — compiled against the reference's own
+    headers: tests/refbinding builds ONE reference `Scene`, renders it with the reference's `Renderer<>` on the host and with
+    `b2r::ReferenceRenderer` on the GPU, through the same call sequence as the app's frame loop, and compares the framebuffers."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(__file__), "refbinding", "refbinding")
+    if not os.path.exists(exe):
+        pytest.skip("tests/refbinding/refbinding not present (built only where /root/reference exists)")
+    p = subprocess.run([exe, "200"], capture_output=True, text=True, timeout=600)
+    print(p.stdout.strip()); print(p.stderr.strip()[-2000:])
+    assert p.returncode == 0 and "REFBINDING OK" in p.stdout
