@@ -59,12 +59,14 @@ struct b2r_ctx {
 	// frame
 	float4 *d_A[2] = {nullptr, nullptr}, *d_B[2] = {nullptr, nullptr}, *d_SA = nullptr, *d_SB = nullptr, *d_fb = nullptr;
 	float *d_T[2] = {nullptr, nullptr}, *d_SL = nullptr, *d_rad = nullptr, *d_acc = nullptr;
+	uint8_t *d_ex_slot[2] = {nullptr, nullptr}, *d_ex_key = nullptr; uint16_t* d_ex_act[2] = {nullptr, nullptr}; uint32_t* d_ex_next = nullptr;  // B2R_FLAG_REFERENCE_EXACT
 	float2* d_H = nullptr;
 	uint32_t* d_counts = nullptr; size_t counts_bytes = 0;
 	unsigned long long* d_stats = nullptr;
 	BatchDev* d_batch = nullptr;
 	Params params{};
 	// launch
+	int grid_brute_first_exact = 0, grid_brute_exact = 0;
 	int grid_brute_first = 0, grid_brute = 0, grid_closest = 0, grid_shade = 0, grid_shadow = 0, grid_stream = 0;
 	cudaGraphExec_t graph_exec = nullptr; bool graph_valid = false;
 	uint64_t launches = 0;
@@ -109,6 +111,12 @@ int alloc_frame(b2r_ctx* c) {
 	if ((rc = dev_alloc(&c->d_counts, (static_cast<size_t>(mb) + 1) * 4))) return rc;
 	if (!c->d_stats) { if ((rc = dev_alloc(&c->d_stats, static_cast<size_t>(ST_COUNT)))) return rc; CU(cudaMemset(c->d_stats, 0, ST_COUNT * sizeof(unsigned long long))); }
 	if (!c->d_batch) { if ((rc = dev_alloc(&c->d_batch, static_cast<size_t>(1)))) return rc; }
+	if (c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) {
+		for (int s = 0; s < 2; s++) { if ((rc = dev_alloc(&c->d_ex_slot[s], cap))) return rc; if ((rc = dev_alloc(&c->d_ex_act[s], cap / 256))) return rc; }
+		if ((rc = dev_alloc(&c->d_ex_key, cap))) return rc;
+		if ((rc = dev_alloc(&c->d_ex_next, cap))) return rc;
+		CU(cudaMemset(c->d_ex_key, 0, cap));
+	}
 	CU(cudaMemset(c->d_rad, 0, 3 * cap * sizeof(float)));
 	CU(cudaMemset(c->d_acc, 0, static_cast<size_t>(K) * 3 * npix * sizeof(float)));
 	Params& p = c->params;
@@ -120,6 +128,8 @@ int alloc_frame(b2r_ctx* c) {
 	p.cnt.paths = c->d_counts; p.cnt.shadow = c->d_counts + (mb + 1); p.cnt.work_a = c->d_counts + 2 * (mb + 1); p.cnt.work_b = c->d_counts + 3 * (mb + 1);
 	p.cnt.stats = c->d_stats;
 	p.batch = c->d_batch; p.rad = c->d_rad; p.acc = c->d_acc;
+	for (int s = 0; s < 2; s++) { p.ex.slot[s] = c->d_ex_slot[s]; p.ex.act[s] = c->d_ex_act[s]; }
+	p.ex.key = c->d_ex_key; p.ex.next_idx = c->d_ex_next;
 	c->accumulations = 0;
 	drop_graph(c);
 	return B2R_OK;
@@ -131,8 +141,10 @@ int compute_grids(b2r_ctx* c) {
 		*out = (n < 1 ? 1 : n) * c->sm_count; return B2R_OK;
 	};
 	int rc;
-	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<true, false>), kBruteBlock, &c->grid_brute_first))) return rc;
-	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<false, false>), kBruteBlock, &c->grid_brute))) return rc;
+	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<true, false, false>), kBruteBlock, &c->grid_brute_first))) return rc;
+	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<false, false, false>), kBruteBlock, &c->grid_brute))) return rc;
+	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<true, false, true>), kBruteBlock, &c->grid_brute_first_exact))) return rc;
+	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<false, false, true>), kBruteBlock, &c->grid_brute_exact))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_closest<false>), kTravBlock, &c->grid_closest))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_shade), kBruteBlock, &c->grid_shade))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_shadow<false>), kTravBlock, &c->grid_shadow))) return rc;
@@ -160,12 +172,21 @@ int enqueue_batch(b2r_ctx* c, bool profile) {
 	CU(cudaMemsetAsync(c->d_counts, 0, c->counts_bytes, st));
 	int rc;
 	if (!c->use_bvh) {
+		const bool exact = (c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) != 0;
+		if (exact && c->params.scene.n_mat > 64) return fail(B2R_ERR_STATE, "B2R_FLAG_REFERENCE_EXACT: at most 64 materials (RendererPolicy::max_materialID, Renderer.hpp:23)");
 		for (uint32_t b = 0; b < mb; b++) {
 			rc = launch(c, KK_BRUTE, profile, [&] {
-				if (b == 0) { if (count) k_bounce_brute<true, true><<<c->grid_brute_first, kBruteBlock, 0, st>>>(p, b); else k_bounce_brute<true, false><<<c->grid_brute_first, kBruteBlock, 0, st>>>(p, b); }
-				else { if (count) k_bounce_brute<false, true><<<c->grid_brute, kBruteBlock, 0, st>>>(p, b); else k_bounce_brute<false, false><<<c->grid_brute, kBruteBlock, 0, st>>>(p, b); }
+				if (exact) {
+					if (b == 0) { if (count) k_bounce_brute<true, true, true><<<c->grid_brute_first_exact, kBruteBlock, 0, st>>>(p, b); else k_bounce_brute<true, false, true><<<c->grid_brute_first_exact, kBruteBlock, 0, st>>>(p, b); }
+					else { if (count) k_bounce_brute<false, true, true><<<c->grid_brute_exact, kBruteBlock, 0, st>>>(p, b); else k_bounce_brute<false, false, true><<<c->grid_brute_exact, kBruteBlock, 0, st>>>(p, b); }
+				} else {
+					if (b == 0) { if (count) k_bounce_brute<true, true, false><<<c->grid_brute_first, kBruteBlock, 0, st>>>(p, b); else k_bounce_brute<true, false, false><<<c->grid_brute_first, kBruteBlock, 0, st>>>(p, b); }
+					else { if (count) k_bounce_brute<false, true, false><<<c->grid_brute, kBruteBlock, 0, st>>>(p, b); else k_bounce_brute<false, false, false><<<c->grid_brute, kBruteBlock, 0, st>>>(p, b); }
+				}
 			});
 			if (rc) return rc;
+			// the reference's stream order for the next bounce (the ranking kernel's time is booked under the brute kind)
+			if (exact && b + 1 < mb) { if ((rc = launch(c, KK_BRUTE, profile, [&] { k_stream_rank<<<c->grid_stream, 256, 0, st>>>(p, b); }))) return rc; }
 		}
 	} else {
 		if ((rc = launch(c, KK_GENERATE, profile, [&] { k_generate<<<c->grid_stream, kBlock, 0, st>>>(p); }))) return rc;
@@ -204,7 +225,7 @@ int run_batch(b2r_ctx* c, const BatchArgs& args) {
 	CU(cudaGraphLaunch(c->graph_exec, c->stream));
 	const uint32_t mb = c->cfg.max_bounces;
 	const bool mis = !(c->cfg.flags & B2R_FLAG_NO_MIS);
-	c->launches += c->use_bvh ? 2 + static_cast<uint64_t>(mb) * 2 + (mis ? mb - 1 : 0) : static_cast<uint64_t>(mb) + 1;
+	c->launches += c->use_bvh ? 2 + static_cast<uint64_t>(mb) * 2 + (mis ? mb - 1 : 0) : static_cast<uint64_t>(mb) + 1 + ((c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) ? mb - 1 : 0);
 	return B2R_OK;
 }
 
@@ -271,6 +292,8 @@ void b2r_destroy(b2r_ctx* c) {
 	dev_free(&c->d_hdri); dev_free(&c->d_prim_mat); dev_free(&c->d_wide);
 	for (int s = 0; s < 2; s++) { dev_free(&c->d_A[s]); dev_free(&c->d_B[s]); dev_free(&c->d_T[s]); }
 	dev_free(&c->d_H); dev_free(&c->d_SA); dev_free(&c->d_SB); dev_free(&c->d_SL); dev_free(&c->d_rad); dev_free(&c->d_acc); dev_free(&c->d_fb);
+	for (int s = 0; s < 2; s++) { dev_free(&c->d_ex_slot[s]); dev_free(&c->d_ex_act[s]); }
+	dev_free(&c->d_ex_key); dev_free(&c->d_ex_next);
 	dev_free(&c->d_counts); dev_free(&c->d_stats); dev_free(&c->d_batch);
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
 	delete c;
@@ -317,6 +340,7 @@ int b2r_set_flags(b2r_ctx* c, uint32_t flags) {
 	int rc = ensure_device(c); if (rc) return rc;
 	CU(cudaStreamSynchronize(c->stream));
 	if ((c->cfg.flags ^ flags) & B2R_FLAG_REFERENCE_TREE) return fail(B2R_ERR_STATE, "B2R_FLAG_REFERENCE_TREE can only be chosen at b2r_create");
+	if ((c->cfg.flags ^ flags) & B2R_FLAG_REFERENCE_EXACT) return fail(B2R_ERR_STATE, "B2R_FLAG_REFERENCE_EXACT can only be chosen at b2r_create");
 	c->cfg.flags = flags; c->params.frame.flags = flags;
 	if (c->have_scene) {
 		const uint32_t n = c->params.scene.n_prims;

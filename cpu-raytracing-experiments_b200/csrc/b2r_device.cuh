@@ -95,7 +95,10 @@ __device__ __forceinline__ void block_rank2(bool fa, bool fb, uint32_t* s_a, uin
 	*rank_a = oa + __popc(ba & below); *rank_b = ob + __popc(bb & below);
 }
 
-template <bool FIRST, bool COUNT>
+// EXACT (B2R_FLAG_REFERENCE_EXACT): rays that sit in the last `active % 8` slots of their tile's stream take the reference's
+// scalar-tail sphere formula (BVH.hpp:270-286) instead of the AVX2+FMA one (:250-268), and survivors leave (material, slot) behind
+// for k_stream_rank, which computes the slots of the next bounce (the reference's stable counting sort by material).
+template <bool FIRST, bool COUNT, bool EXACT>
 __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_brute(const Params p, const uint32_t bounce) {
 	constexpr int kQ = 2 * kBruteBlock;  // hit queue: up to kBruteBlock-1 waiting + kBruteBlock new
 	__shared__ float4 s_prim[kBruteTile];
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 			// ---------------- phase 1: one ray per thread, closest hit over every sphere (ties -> lowest BVH-order index, strict <, Q6)
 			const uint32_t i = base + threadIdx.x;
 			const bool live = i < n_in;
-			float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0; uint32_t pid0 = 0;
+			float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0; uint32_t pid0 = 0; bool tail = false;
 			if (live) {
 				if (FIRST) {
 					const uint32_t sl0 = div_by(i, p.frame.npix, p.frame.npix_magic);
@@ -152,6 +155,10 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 				} else {
 					const float4 a = p.q.A[side][i], b = p.q.B[side][i];
 					ox = a.x; oy = a.y; oz = a.z; dx = a.w; dy = b.x; dz = b.y;
+					if (EXACT) {  // stream = (sample in flight, tile); in the scalar tail when slot >= active & ~7
+						const uint32_t pid_i = __float_as_uint(b.w), stream = (pid_i >> 26) * (p.frame.npix >> 8) + ((pid_i & kPixMask) >> 8);
+						tail = static_cast<uint32_t>(p.ex.slot[side][i]) >= (static_cast<uint32_t>(p.ex.act[side][stream]) & ~7u);
+					}
 				}
 			}
 			float best = FLT_MAX; int32_t prim = -1;
@@ -165,8 +172,11 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 					}
 					__syncthreads();
 				}
-				if (live) {
-#pragma unroll 3
+				if (EXACT && live && tail) {
+					for (uint32_t j = 0; j < cnt; j++) { const float4 sp = lds_f4(a_prim + j * 16u); sphere_closest_scalar_update(sp.x, sp.y, sp.z, sp.w, static_cast<int32_t>(first + j), ox, oy, oz, dx, dy, dz, &best, &prim); }
+					if (COUNT) c_sphere += cnt;
+				} else if (live) {
+				#pragma unroll 3
 					for (uint32_t j = 0; j < cnt; j++) {
 						float d; bool h;
 						if (FIRST) { const float4 q = lds_f4(a_pre + j * 16u); h = sphere_hit_prepared(SpherePre{q.x, q.y, q.z, q.w}, dx, dy, dz, &d); }
@@ -203,9 +213,10 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 			const bool shade = threadIdx.x < take;
 			queued -= take;
 			bool keep = false, want_shadow = false;
-			PathState s; ShadowRay sr; uint32_t pid = 0;
+			PathState s; ShadowRay sr; uint32_t pid = 0; uint32_t ex_slot = 0, ex_mat = 0;
 			if (shade) {
 				const uint32_t hi = s_hit_i[qi]; const float depth = s_hit_t[qi]; const int32_t hprim = s_hit_prim[qi];
+				if (EXACT) ex_slot = FIRST ? (hi & 255u) : static_cast<uint32_t>(p.ex.slot[side][hi]);  // bounce 0: hi is the path id, slot = pixel ID
 				if (FIRST) {
 					s.ox = p.frame.cam.px; s.oy = p.frame.cam.py; s.oz = p.frame.cam.pz;
 					s.dx = s_hit_d[0][FIRST ? qi : 0]; s.dy = s_hit_d[FIRST ? 1 : 0][FIRST ? qi : 0]; s.dz = s_hit_d[FIRST ? 2 : 0][FIRST ? qi : 0];
@@ -214,6 +225,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 				pid = s.pid;
 				const uint32_t acc = p.batch->acc[s.pid >> 26], seed = pixel_seed(s.pid & kPixMask, p.frame.max_bounces);
 				const Surface sf = shade_surface(sc, s, depth, hprim);
+				if (EXACT) ex_mat = static_cast<uint32_t>(sf.mat);
 				c_hits++;
 				if (last) { rad_zero(p.rad, p.frame.npix, s.pid); c_drop++; }  // survivors of the last bounce lose their radiance (Q11)
 				else {
@@ -251,7 +263,13 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 			s_queued += n_shadow;
 			if (threadIdx.x == 0) s_base = n_keep ? atomicAdd(p.cnt.paths + bounce + 1, n_keep) : 0u;
 			__syncthreads();
-			if (keep) store_path(p.q, side ^ 1, s_base + rank, s);
+			if (keep) {
+				store_path(p.q, side ^ 1, s_base + rank, s);
+				if (EXACT) {  // (stream, slot) -> material and next-queue index, for k_stream_rank
+					const uint32_t e = (pid >> 26) * p.frame.npix + ((pid & kPixMask) & ~255u) + ex_slot;
+					p.ex.key[e] = static_cast<uint8_t>(ex_mat + 1u); p.ex.next_idx[e] = s_base + rank;
+				}
+			}
 		}
 		// ---------------- phase 3: any-hit test of queued shadow rays (BVH.hpp:290-305), again a full CTA at a time
 		const bool drained = !more && queued == 0;
@@ -303,6 +321,41 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 	stat_add(p.cnt.stats, ST_SHADOW, c_shadow); stat_add(p.cnt.stats, ST_HITS, c_hits); stat_add(p.cnt.stats, ST_TERM, c_term);
 	stat_add(p.cnt.stats, ST_DROPPED, c_drop); stat_add(p.cnt.stats, ST_EVENTS, c_events);
 	if (COUNT) stat_add(p.cnt.stats, ST_SPHERE, c_sphere);
+}
+
+// B2R_FLAG_REFERENCE_EXACT, after bounce `bounce`: the reference compacts a tile's survivors in the order of its stable counting
+// sort by material (sort_rayID, DataStreams.hpp:236-253, called at Renderer.hpp:235-243; the BRDF loop appends in that order,
+// :359-404). One CTA per stream, thread = slot: rank = (survivors with a smaller material) + (same material, smaller slot).
+__global__ void __launch_bounds__(256) k_stream_rank(const Params p, const uint32_t bounce) {
+	__shared__ uint16_t s_cnt[8][64];     // survivors per (warp, material)
+	__shared__ uint16_t s_before[8][64];  // same material in the warps before
+	__shared__ uint16_t s_base[65];       // survivors with a smaller material
+	const int side = bounce & 1;
+	const uint32_t n_streams = p.batch->n_slots * (p.frame.npix >> 8), warp = threadIdx.x >> 5;
+	for (uint32_t stream = blockIdx.x; stream < n_streams; stream += gridDim.x) {
+		const uint32_t e = stream * 256u + threadIdx.x;
+		const uint32_t k = p.ex.key[e];
+		const bool alive = k != 0u;
+		if (!__syncthreads_or(alive)) { if (threadIdx.x == 0) p.ex.act[side ^ 1][stream] = 0; continue; }
+		const uint32_t m = alive ? k - 1u : 0xffffu;
+		if (alive) p.ex.key[e] = 0;
+		for (uint32_t j = threadIdx.x; j < 8u * 64u; j += 256u) (&s_cnt[0][0])[j] = 0;
+		__syncthreads();
+		const uint32_t peers = __match_any_sync(0xffffffffu, m);
+		const uint32_t rank_in_warp = __popc(peers & ((1u << lane_id()) - 1u));
+		if (alive && rank_in_warp == 0u) s_cnt[warp][m] = static_cast<uint16_t>(__popc(peers));
+		__syncthreads();
+		if (threadIdx.x < 64u) {
+			uint32_t acc = 0;
+			for (uint32_t w = 0; w < 8u; w++) { s_before[w][threadIdx.x] = static_cast<uint16_t>(acc); acc += s_cnt[w][threadIdx.x]; }
+			s_base[threadIdx.x + 1u] = static_cast<uint16_t>(acc);  // totals per material, scanned below
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) { uint32_t acc = 0; s_base[0] = 0; for (uint32_t j = 1; j <= 64u; j++) { const uint32_t c = s_base[j]; s_base[j] = static_cast<uint16_t>(acc + c); acc += c; } p.ex.act[side ^ 1][stream] = static_cast<uint16_t>(acc); }
+		__syncthreads();
+		if (alive) p.ex.slot[side ^ 1][p.ex.next_idx[e]] = static_cast<uint8_t>(s_base[m] + s_before[warp][m] + rank_in_warp);
+		__syncthreads();
+	}
 }
 
 // camera rays of a batch -> queue side 0 (Renderer.hpp:97-127)

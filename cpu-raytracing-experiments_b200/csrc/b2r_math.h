@@ -263,6 +263,20 @@ B2R_HD bool sphere_hit_prepared(const SpherePre& p, float dx, float dy, float dz
 B2R_HD bool sphere_hit_closest(float cx, float cy, float cz, float r2, float ox, float oy, float oz, float dx, float dy, float dz, float* dist_out) {
 	return sphere_hit_prepared(sphere_prepare(cx, cy, cz, r2, ox, oy, oz), dx, dy, dz, dist_out);
 }
+// The scalar tail of the same loop, BVH.hpp:270-286 (no FMA; accumulation order x, y, z): the reference runs it for the last
+// `active % 8` rays of a tile's stream. Only B2R_FLAG_REFERENCE_EXACT uses it. Updates (best, prim) exactly as the reference does.
+B2R_HD void sphere_closest_scalar_update(float cx, float cy, float cz, float r2, int32_t id, float ox, float oy, float oz, float dx, float dy, float dz, float* best, int32_t* prim) {
+	float b = 0.0f, disc = r2;
+	float t = cx - ox; b += dx * t; disc -= t * t;
+	t = cy - oy; b += dy * t; disc -= t * t;
+	t = cz - oz; b += dz * t; disc -= t * t;
+	disc += b * b;
+	if (disc < 0.0f) return;
+	disc = sqrtf(disc);
+	const float dist = (b >= disc) ? b - disc : b + disc;
+	if (dist < 0.0f || dist >= *best) return;
+	*best = dist; *prim = id;
+}
 // Any hit along [0, tfar): BVH.hpp:294-300 (glm dot products, no FMA)
 B2R_HD bool sphere_hit_any(float cx, float cy, float cz, float r2, float ox, float oy, float oz, float dx, float dy, float dz, float tfar) {
 	f3 p{cx - ox, cy - oy, cz - oz};

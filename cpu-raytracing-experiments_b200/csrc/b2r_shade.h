@@ -78,8 +78,16 @@ struct CountDev {            // zeroed at the start of every batch; index = boun
 	uint32_t* work_b;        // [mb]
 	unsigned long long* stats;  // [ST_COUNT] cumulative since reset_counters
 };
+// B2R_FLAG_REFERENCE_EXACT: the reference's per-tile stream bookkeeping. A stream = one sample of one 16x16 tile (256 slots,
+// RayStream<256>); e = stream * 256 + slot indexes `key` / `next_idx`; `slot` and `act` are double-buffered like the path queue.
+struct ExactDev {
+	uint8_t* slot[2];     // [cap] slot of queue entry i inside its stream at this bounce (bounce 0: the pixel's ID)
+	uint16_t* act[2];     // [cap / 256] active rays of each stream at this bounce (bounce 0: 256)
+	uint8_t* key;         // [cap] 1 + material of the survivor that sat in (stream, slot) this bounce, 0 = none; cleared by k_stream_rank
+	uint32_t* next_idx;   // [cap] its index in the next path queue
+};
 struct Params {
-	SceneDev scene; FrameDev frame; QueueDev q; CountDev cnt;
+	SceneDev scene; FrameDev frame; QueueDev q; CountDev cnt; ExactDev ex;
 	const BatchDev* batch;
 	float* rad;   // RAD
 	float* acc;   // ACC

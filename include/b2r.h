@@ -54,6 +54,10 @@ enum {
 	B2R_FLAG_COUNT_TESTS = 1u << 3, /* also count sphere / box tests (slower; for roofline accounting) */
 	B2R_FLAG_NO_GRAPH    = 1u << 4, /* launch kernels one by one instead of replaying a CUDA graph (profiling) */
 	B2R_FLAG_REFERENCE_TREE = 1u << 5, /* traverse the flattened REFERENCE tree (BVH.hpp:90-206 topology) instead of the tree built for traversal */
+	B2R_FLAG_REFERENCE_EXACT = 1u << 6, /* brute-force pipeline only, chosen at b2r_create: reproduce the reference's slot-dependent choice of sphere
+	                                     * formula (BVH.hpp:250-286: the last `active % 8` rays of each 16x16 tile's stream take the scalar tail;
+	                                     * stream order = stable counting sort by material, DataStreams.hpp:236-253). Results are then bit-identical
+	                                     * to the reference's own Renderer::Accumulate, at the price of one extra ranking kernel per bounce. */
 };
 
 typedef struct b2r_config {

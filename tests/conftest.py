@@ -39,6 +39,7 @@ def hostcheck():
     lib.hc_median5.restype = f; lib.hc_median5.argtypes = [C.c_void_p]
     lib.hc_median8.restype = f; lib.hc_median8.argtypes = [C.c_void_p]
     lib.hc_sphere_closest.restype = C.c_int; lib.hc_sphere_closest.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(f)]
+    lib.hc_closest_scalar.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(f), C.POINTER(C.c_int32)]
     lib.hc_sphere_any.restype = C.c_int; lib.hc_sphere_any.argtypes = [C.c_void_p, C.c_void_p, f]
     lib.hc_pcg3.argtypes = [u, C.c_void_p, C.POINTER(u), u, C.POINTER(u)]
     return lib

@@ -101,6 +101,11 @@ void hc_tonemap(float rgb[3]) { aces_tonemap(rgb, rgb + 1, rgb + 2); }
 float hc_median8(const float v[8]) { return median_of_8(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]); }
 // closest / any sphere tests: returns 1 and the distance when the candidate is valid
 int hc_sphere_closest(const float s[4], const float ray[6], float* d) { return sphere_hit_closest(s[0], s[1], s[2], s[3], ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], d) ? 1 : 0; }
+// closest hit over n spheres {c.xyz, r^2} with the scalar-tail formula (BVH.hpp:270-286), all spheres in order
+void hc_closest_scalar(const float* spheres4, uint32_t n, const float ray[6], float* best, int32_t* prim) {
+	*best = FLT_MAX; *prim = -1;
+	for (uint32_t j = 0; j < n; j++) sphere_closest_scalar_update(spheres4[4 * j], spheres4[4 * j + 1], spheres4[4 * j + 2], spheres4[4 * j + 3], static_cast<int32_t>(j), ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], best, prim);
+}
 int hc_sphere_any(const float s[4], const float ray[6], float tfar) { return sphere_hit_any(s[0], s[1], s[2], s[3], ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], tfar) ? 1 : 0; }
 
 }  // extern "C"

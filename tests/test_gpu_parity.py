@@ -422,3 +422,41 @@ def test_reference_binding_dropin_on_the_references_own_scene():
     p = subprocess.run([exe, "200"], capture_output=True, text=True, timeout=600)
     print(p.stdout.strip()); print(p.stderr.strip()[-2000:])
     assert p.returncode == 0 and "REFBINDING OK" in p.stdout
+
+
+# ------------------------------------------------------------------------------------------------ bit-exact against the reference itself
+@pytest.mark.parametrize("name,w,h,mb,n,first,sif", [("default", 160, 96, 16, 10, 0, 0), ("default", 64, 48, 8, 5, 0, 1), ("default", 96, 64, 16, 7, 60, 3),
+                                                     ("random33", 80, 48, 8, 5, 0, 0), ("random300_brute", 64, 48, 4, 5, 0, 0), ("sky", 64, 48, 8, 5, 0, 2)])
+def test_reference_exact_mode_equals_slot_exact_oracle(name, w, h, mb, n, first, sif):
+    """B2R_FLAG_REFERENCE_EXACT: the GPU reproduces the reference's slot-dependent choice of sphere formula (scalar tail for the last
+    `active % 8` rays of each tile stream, stream order = stable counting sort by material). Bit-exact against the oracle's slot-exact
+    mode, which is itself bit-exact against the reference's own Renderer (tests/test_oracle_ref_renderer.py)."""
+    sc = {"default": scenes.default_scene, "random33": lambda: scenes.random_scene(33, light_every=3), "random300_brute": lambda: scenes.random_scene(300, light_every=20),
+          "sky": lambda: scenes.bvh_test_scene(40, hdri=scenes.synthetic_hdri())}[name]()
+    flags = b2r.FLAG_REFERENCE_EXACT | b2r.FLAG_FORCE_BRUTE
+    r = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=5, flags=flags, samples_in_flight=sif)
+    o = oracle_for(sc, w, h, mb, 5, flags=oracle_py.ORC_SLOT_EXACT)
+    if first:
+        r.accumulations = first; o.set_accumulations(first)
+    r.Accumulate(n); o.accumulate(n)
+    gb, ob = r.buckets_host(), o.buckets()
+    assert gb.tobytes() == ob.tobytes(), f"{name}: {float((gb.view(np.uint32) != ob.view(np.uint32)).any(axis=(0, 1)).mean()):.3e} of pixels differ"
+    if (first + n) % 5 == 0:
+        rc, of = o.render(); assert r.Render() and rc == 0
+        assert r.framebuffer.tobytes() == of.tobytes()
+    r.close(); o.close()
+
+
+@pytest.mark.skipif(not oracle_py.have_reference_renderer(), reason="oracle/_ref/librefrenderer.so not present")
+def test_c1_full_size_reference_exact_mode_bit_identical_to_the_reference():
+    """BASELINE config C1 at full size, GPU in B2R_FLAG_REFERENCE_EXACT mode against the reference's own Renderer::Accumulate / Render
+    run live on the host cores: all five bucket planes and the tonemapped frame must be identical bit for bit."""
+    sc = scenes.default_scene(); w, h, mb = 1280, 720, 8
+    ref = oracle_py.ReferenceRenderer(sc, w, h, mb); ref.accumulate(5); rb = ref.buckets(); acted, rframe = ref.render(); ref.close()
+    g = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=5, flags=b2r.FLAG_REFERENCE_EXACT); g.Accumulate(5)
+    gb = g.buckets_host()
+    same = float((gb.view(np.uint32) == rb.view(np.uint32)).all(axis=(0, 1)).mean())
+    print(f"C1, reference-exact mode vs the reference itself: bit-identical pixels {same:.6f}")
+    assert gb.tobytes() == rb.tobytes()
+    assert g.Render() and acted and g.framebuffer.tobytes() == rframe.tobytes()
+    g.close()

@@ -68,6 +68,13 @@ def test_sphere_loops_match_reference_golden(hostcheck):
         assert hashlib.sha256(tf.tobytes()).hexdigest() == rec["sha256_tfar"] and hashlib.sha256(pid.tobytes()).hexdigest() == rec["sha256_prim"], (scene_name, kind, n)
         assert hashlib.sha256(np.asarray(occ, np.uint8).tobytes()).hexdigest() == rec["sha256_occluded"]
         assert int((pid >= 0).sum()) == rec["hits"]
+        if kind == "tail":  # the product's scalar-tail routine (B2R_FLAG_REFERENCE_EXACT) on the same rays
+            nodes, prims, ids = o.bvh()
+            sph = np.ascontiguousarray(np.concatenate([prims["position"], prims["radius_sq"][:, None]], axis=1).astype(np.float32))
+            for i in range(n):
+                best, bp = C.c_float(), C.c_int32()
+                hostcheck.hc_closest_scalar(sph.ctypes.data, len(sph), rays[i].ctypes.data, C.byref(best), C.byref(bp))
+                assert bp.value == pid[i] and (bp.value < 0 or np.float32(best.value) == tf[i])
         if kind == "simd":  # the product's closest-hit routine is the AVX2+FMA formula (DESIGN.md "Numerics"); its any-hit the shadow one
             nodes, prims, ids = o.bvh()
             sph = np.concatenate([prims["position"], prims["radius_sq"][:, None]], axis=1).astype(np.float32)
