@@ -223,6 +223,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true"); ap.add_argument("--no-profile-pass", action="store_true")
     ap.add_argument("--samples-in-flight", type=int, default=0, help="0 = library default (auto)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel (for ncu); never used for a reported number")
+    ap.add_argument("--reference-exact", action="store_true", help="brute-force workloads: B2R_FLAG_REFERENCE_EXACT (bit-identical to the reference's own renderer; one extra ranking kernel per bounce)")
     ap.add_argument("--combine", default="p2p", choices=["p2p", "nccl"], help="multi-GPU frame combine: resolve kernel reads peer buckets over NVLink (p2p) or NCCL all-reduce then resolve")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -252,9 +253,10 @@ def main():
     stream = torch.cuda.Stream(device=dev)  # a real (non-default) stream: the library launches on it and the timing events are recorded on it
     torch.cuda.set_stream(stream)
     K, spp = wl["K"], wl["spp"]
+    base_flags = b2r.FLAG_REFERENCE_EXACT if (args.reference_exact and wl["scene"] == "default") else 0
     shard = b2r_dist.shard_kwargs(rank, world, K)
     r = b2r.Renderer(ps, wl["w"], wl["h"], max_bounces=wl["mb"], buckets=K, device=local, stream=stream.cuda_stream,
-                     samples_in_flight=args.samples_in_flight, flags=b2r.FLAG_NO_GRAPH if args.no_graph else 0, **shard)
+                     samples_in_flight=args.samples_in_flight, flags=(b2r.FLAG_NO_GRAPH if args.no_graph else 0) | base_flags, **shard)
     # weak scaling: every rank renders `spp` samples of its own buckets per step => world*spp sample indices per step
     # (C5 is the strong-scaling run: the frame's spp are divided among the ranks)
     strong = bool(wl.get("strong"))
@@ -348,13 +350,13 @@ def main():
     roof = None; kernel_ms = None
     hbm_peak, peak_src, sm_max = peaks()
     if not args.no_profile_pass:
-        r.set_flags(b2r.FLAG_NO_GRAPH); r.SetCamera(ps.camera)
+        r.set_flags(b2r.FLAG_NO_GRAPH | base_flags); r.SetCamera(ps.camera)
         step(); r.sync(); r.kernel_times(reset=True); r.reset_counters()
         for _ in range(args.steps):
             step()
         r.sync()
         kt = r.kernel_times(reset=True); pc = r.counters()
-        r.set_flags(0); r.SetCamera(ps.camera)
+        r.set_flags(base_flags); r.SetCamera(ps.camera)
         kernel_ms = {k: {"ms": v[0], "launches": int(v[1])} for k, v in kt.items() if v[1]}
         total_kernel_ms = sum(v[0] for v in kt.values())
         ext, shadow, hits, events, dropped = pc["extension_rays"], pc["shadow_rays"], pc["shaded_hits"], pc["radiance_events"], pc["dropped"]
@@ -410,7 +412,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "samples_per_step_per_gpu": step_samples // world, "samples_in_flight": args.samples_in_flight,
+            "config": {"workload": wl["desc"] + (" [B2R_FLAG_REFERENCE_EXACT: reference's stream order and scalar-tail formula]" if base_flags else ""), "samples_per_step_per_gpu": step_samples // world, "samples_in_flight": args.samples_in_flight,
                        "partition": (f"sample buckets b%{world}==rank, scene+BVH replicated; " + ("resolve kernel on rank 0 reads peer bucket arrays over NVLink (CUDA IPC), 2 barriers per frame" if use_p2p else "one NCCL all-reduce of bucket sums per frame")) if world > 1 else "single GPU",
                        "l2": "no flush needed: each step streams >1 GB of path-queue records (>> 126 MB L2); RNG-unique samples every step"},
             "paths_per_s": paths_total / secs, "rays_per_step": rays_total / args.steps,

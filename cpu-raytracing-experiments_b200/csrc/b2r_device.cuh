@@ -334,6 +334,7 @@ __global__ void __launch_bounds__(256) k_stream_rank(const Params p, const uint3
 	const uint32_t n_streams = p.batch->n_slots * (p.frame.npix >> 8), warp = threadIdx.x >> 5;
 	for (uint32_t stream = blockIdx.x; stream < n_streams; stream += gridDim.x) {
 		const uint32_t e = stream * 256u + threadIdx.x;
+		if (bounce > 0u && p.ex.act[side][stream] == 0u) { if (threadIdx.x == 0) p.ex.act[side ^ 1][stream] = 0; continue; }  // stream already empty (uniform)
 		const uint32_t k = p.ex.key[e];
 		const bool alive = k != 0u;
 		if (!__syncthreads_or(alive)) { if (threadIdx.x == 0) p.ex.act[side ^ 1][stream] = 0; continue; }

@@ -460,3 +460,19 @@ def test_c1_full_size_reference_exact_mode_bit_identical_to_the_reference():
     assert gb.tobytes() == rb.tobytes()
     assert g.Render() and acted and g.framebuffer.tobytes() == rframe.tobytes()
     g.close()
+
+
+@pytest.mark.skipif(not oracle_py.have_reference_renderer(), reason="oracle/_ref/librefrenderer.so not present")
+def test_c2_size_reference_exact_mode_bit_identical_to_the_reference():
+    """BASELINE config C2's frame (1920x1080 -> 1920x1088, max_bounces 16) with the reference's own estimator (K = 5, 65 samples: the
+    reference-exact variant of SURVEY §8d) — 136M paths through the reference's Renderer on the host cores and through the GPU in
+    B2R_FLAG_REFERENCE_EXACT mode: bucket sums and the tonemapped frame identical bit for bit."""
+    sc = scenes.default_scene(); w, h, mb, n = 1920, 1088, 16, 65
+    ref = oracle_py.ReferenceRenderer(sc, w, h, mb); ref.accumulate(n); rb = ref.buckets(); acted, rframe = ref.render(); ref.close()
+    g = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=5, flags=b2r.FLAG_REFERENCE_EXACT); g.Accumulate(n)
+    gb = g.buckets_host()
+    same = float((gb.view(np.uint32) == rb.view(np.uint32)).all(axis=(0, 1)).mean())
+    print(f"C2 frame, K=5, 65 spp, reference-exact mode vs the reference itself: bit-identical pixels {same:.6f}")
+    assert gb.tobytes() == rb.tobytes()
+    assert g.Render() and acted and g.framebuffer.tobytes() == rframe.tobytes()
+    g.close()
