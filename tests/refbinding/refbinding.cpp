@@ -51,11 +51,14 @@ static void default_scene(Scene& scene, uint32_t w, uint32_t h) {  // a few sphe
 
 int main(int argc, char** argv) {
 	const uint32_t w = 320, h = 192; const uint32_t spp = argc > 1 ? static_cast<uint32_t>(atoi(argv[1])) : 200;
+	const bool exact = argc > 2 && !strcmp(argv[2], "exact");  // B2R_FLAG_REFERENCE_EXACT: every framebuffer must then be bit-identical
 	Scene scene; default_scene(scene, w, h);
 	Renderer<> cpu{scene};                                   // the reference
-	b2r::ReferenceRenderer<Scene, glm::vec4> gpu{scene};     // the drop-in, same Scene object
+	b2r::ReferencePolicy policy; if (exact) policy.flags = B2R_FLAG_REFERENCE_EXACT;
+	b2r::ReferenceRenderer<Scene, glm::vec4> gpu{scene, policy};     // the drop-in, same Scene object
 	static_assert(decltype(cpu)::RequiredTiling() == decltype(gpu)::RequiredTiling());
 	cpu.Resize(w, h); gpu.Resize(w, h);
+	bool all_identical = true;
 	auto compare = [&](const char* what) {
 		double se = 0; size_t divergent = 0, identical = 0; const size_t n = static_cast<size_t>(w) * h;
 		for (size_t i = 0; i < n; i++) {
@@ -66,6 +69,7 @@ int main(int argc, char** argv) {
 		}
 		printf("%s: accumulations %u/%u, tonemapped pixels more than 1e-4 (relative) apart %.3e, bit-identical pixels %.4f, RMSE %.3e\n", what, cpu.accumulations, gpu.accumulations,
 		       double(divergent) / n, double(identical) / n, sqrt(se / (3.0 * n)));
+		all_identical &= identical == n;
 		return sqrt(se / (3.0 * n));
 	};
 	for (uint32_t i = 0; i < 5; i++) { cpu.Accumulate(); gpu.Accumulate(); }
@@ -78,7 +82,8 @@ int main(int argc, char** argv) {
 	for (uint32_t i = 0; i < 5; i++) { cpu.Accumulate(); gpu.Accumulate(); }
 	cpu.Render(); gpu.Render();
 	const double rmse_moved = compare("after a camera move + 5 samples");
-	const bool ok = cpu.accumulations == gpu.accumulations && rmse < 1e-3 && rmse_moved < 2e-2;
+	const bool ok = cpu.accumulations == gpu.accumulations && rmse < 1e-3 && rmse_moved < 2e-2 && (!exact || all_identical);
+	if (exact) printf("reference-exact mode: every compared framebuffer bit-identical: %s\n", all_identical ? "yes" : "NO");
 	printf("%s\n", ok ? "REFBINDING OK" : "REFBINDING FAILED");
 	return ok ? 0 : 1;
 }

@@ -422,6 +422,10 @@ def test_reference_binding_dropin_on_the_references_own_scene():
     p = subprocess.run([exe, "200"], capture_output=True, text=True, timeout=600)
     print(p.stdout.strip()); print(p.stderr.strip()[-2000:])
     assert p.returncode == 0 and "REFBINDING OK" in p.stdout
+    # with B2R_FLAG_REFERENCE_EXACT the drop-in's framebuffer is the reference's, bit for bit, at every compared frame
+    p = subprocess.run([exe, "100", "exact"], capture_output=True, text=True, timeout=600)
+    print(p.stdout.strip()); print(p.stderr.strip()[-2000:])
+    assert p.returncode == 0 and "REFBINDING OK" in p.stdout and "bit-identical: yes" in p.stdout
 
 
 # ------------------------------------------------------------------------------------------------ bit-exact against the reference itself
