@@ -325,37 +325,47 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 
 // B2R_FLAG_REFERENCE_EXACT, after bounce `bounce`: the reference compacts a tile's survivors in the order of its stable counting
 // sort by material (sort_rayID, DataStreams.hpp:236-253, called at Renderer.hpp:235-243; the BRDF loop appends in that order,
-// :359-404). One CTA per stream, thread = slot: rank = (survivors with a smaller material) + (same material, smaller slot).
+// :359-404): rank = (survivors with a smaller material) + (same material, smaller slot). One WARP per stream, warp-synchronous:
+// eight rounds of 32 consecutive slots; in a round the lanes with the same material find each other with MATCH.ANY and take their
+// place after the running count of that material; a 64-bin scan then turns the per-material totals into bases.
 __global__ void __launch_bounds__(256) k_stream_rank(const Params p, const uint32_t bounce) {
-	__shared__ uint16_t s_cnt[8][64];     // survivors per (warp, material)
-	__shared__ uint16_t s_before[8][64];  // same material in the warps before
-	__shared__ uint16_t s_base[65];       // survivors with a smaller material
+	__shared__ uint16_t s_run[8][64];
 	const int side = bounce & 1;
-	const uint32_t n_streams = p.batch->n_slots * (p.frame.npix >> 8), warp = threadIdx.x >> 5;
-	for (uint32_t stream = blockIdx.x; stream < n_streams; stream += gridDim.x) {
-		const uint32_t e = stream * 256u + threadIdx.x;
-		if (bounce > 0u && p.ex.act[side][stream] == 0u) { if (threadIdx.x == 0) p.ex.act[side ^ 1][stream] = 0; continue; }  // stream already empty (uniform)
-		const uint32_t k = p.ex.key[e];
-		const bool alive = k != 0u;
-		if (!__syncthreads_or(alive)) { if (threadIdx.x == 0) p.ex.act[side ^ 1][stream] = 0; continue; }
-		const uint32_t m = alive ? k - 1u : 0xffffu;
-		if (alive) p.ex.key[e] = 0;
-		for (uint32_t j = threadIdx.x; j < 8u * 64u; j += 256u) (&s_cnt[0][0])[j] = 0;
-		__syncthreads();
-		const uint32_t peers = __match_any_sync(0xffffffffu, m);
-		const uint32_t rank_in_warp = __popc(peers & ((1u << lane_id()) - 1u));
-		if (alive && rank_in_warp == 0u) s_cnt[warp][m] = static_cast<uint16_t>(__popc(peers));
-		__syncthreads();
-		if (threadIdx.x < 64u) {
-			uint32_t acc = 0;
-			for (uint32_t w = 0; w < 8u; w++) { s_before[w][threadIdx.x] = static_cast<uint16_t>(acc); acc += s_cnt[w][threadIdx.x]; }
-			s_base[threadIdx.x + 1u] = static_cast<uint16_t>(acc);  // totals per material, scanned below
+	const uint32_t n_streams = p.batch->n_slots * (p.frame.npix >> 8), warp = threadIdx.x >> 5, lane = lane_id(), below = (1u << lane) - 1u;
+	uint16_t* run = s_run[warp];
+	for (uint32_t stream = blockIdx.x * 8u + warp; stream < n_streams; stream += gridDim.x * 8u) {
+		if (bounce > 0u && p.ex.act[side][stream] == 0u) { if (lane == 0u) p.ex.act[side ^ 1][stream] = 0; continue; }  // stream already empty (warp-uniform)
+		const uint32_t e0 = stream * 256u + lane;
+		uint32_t key[8], any = 0u;
+#pragma unroll
+		for (uint32_t r = 0; r < 8u; r++) { key[r] = p.ex.key[e0 + 32u * r]; any |= key[r]; }
+		if (!__any_sync(0xffffffffu, any != 0u)) { if (lane == 0u) p.ex.act[side ^ 1][stream] = 0; continue; }
+		run[lane] = 0; run[lane + 32u] = 0;
+		__syncwarp();
+		uint32_t within[8];
+#pragma unroll
+		for (uint32_t r = 0; r < 8u; r++) {
+			const bool alive = key[r] != 0u;
+			const uint32_t m = alive ? key[r] - 1u : 0xffffu;  // the dead lanes match each other: harmless
+			const uint32_t peers = __match_any_sync(0xffffffffu, m), rk = __popc(peers & below);
+			within[r] = alive ? run[m] + rk : 0u;
+			__syncwarp();
+			if (alive && rk == 0u) run[m] = static_cast<uint16_t>(run[m] + __popc(peers));
+			if (alive) p.ex.key[e0 + 32u * r] = 0;  // left clean for the next bounce
+			__syncwarp();
 		}
-		__syncthreads();
-		if (threadIdx.x == 0) { uint32_t acc = 0; s_base[0] = 0; for (uint32_t j = 1; j <= 64u; j++) { const uint32_t c = s_base[j]; s_base[j] = static_cast<uint16_t>(acc + c); acc += c; } p.ex.act[side ^ 1][stream] = static_cast<uint16_t>(acc); }
-		__syncthreads();
-		if (alive) p.ex.slot[side ^ 1][p.ex.next_idx[e]] = static_cast<uint8_t>(s_base[m] + s_before[warp][m] + rank_in_warp);
-		__syncthreads();
+		const uint32_t c0 = run[2u * lane], c1 = run[2u * lane + 1u];
+		uint32_t incl = c0 + c1;
+#pragma unroll
+		for (uint32_t d = 1; d < 32u; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), excl = incl - (c0 + c1);
+		__syncwarp();
+		run[2u * lane] = static_cast<uint16_t>(excl); run[2u * lane + 1u] = static_cast<uint16_t>(excl + c0);
+		__syncwarp();
+#pragma unroll
+		for (uint32_t r = 0; r < 8u; r++) if (key[r] != 0u) p.ex.slot[side ^ 1][p.ex.next_idx[e0 + 32u * r]] = static_cast<uint8_t>(run[key[r] - 1u] + within[r]);
+		if (lane == 0u) p.ex.act[side ^ 1][stream] = static_cast<uint16_t>(total);
+		__syncwarp();
 	}
 }
 
