@@ -395,6 +395,27 @@ def main():
             except Exception:
                 pass
 
+    # ---- the same workload in B2R_FLAG_REFERENCE_EXACT mode (bit-identical to the reference's own renderer), reported beside the
+    # default mode's number: brute-force workloads, N=1 only, same steps / warm-up / timing as the headline value
+    exact_line = None
+    if world == 1 and not base_flags and wl["scene"] == "default" and not args.no_profile_pass:
+        rx = b2r.Renderer(ps, wl["w"], wl["h"], max_bounces=wl["mb"], buckets=K, device=local, stream=stream.cuda_stream,
+                          samples_in_flight=args.samples_in_flight, flags=b2r.FLAG_REFERENCE_EXACT)
+        def step_x():
+            rx.ResetAccumulator(); rx.Accumulate(step_samples); assert rx.Render(to_host=False)
+        for _ in range(warm):
+            step_x()
+        torch.cuda.synchronize(dev); rx.reset_counters()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_x()
+        e1.record(stream); torch.cuda.synchronize(dev)
+        ms_x = e0.elapsed_time(e1); cx = rx.counters(); rays_x = cx["extension_rays"] + cx["shadow_rays"]
+        exact_line = {"value": rays_x / (ms_x / 1e3) / 1e6, "unit": UNIT, "ms_per_step": ms_x / args.steps,
+                      "note": "B2R_FLAG_REFERENCE_EXACT: the reference's per-tile stream order and scalar-tail sphere formula; results bit-identical to the reference's own Renderer::Accumulate/Render (tests/test_gpu_parity.py)"}
+        rx.close()
+
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample of the same workload, on the box's host
     # cores. Run as a fresh `bench.py --impl reference` process so that its threads see the same conditions as the reference arm
     # the driver launches (inside this process, after CUDA/torch start-up, the same code ran at about half the speed).
@@ -420,6 +441,8 @@ def main():
                     "includes": "upload_scene (pack + 128-B BVH flatten on host, H2D), set_camera, reset, Accumulate x spp, Render, D2H of the RGBA32F frame into pinned memory"},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "kernel_ms": kernel_ms,
         }
+        if exact_line:
+            line["reference_exact_mode"] = exact_line
         print(json.dumps(line))
     r.close()
     if world > 1:
