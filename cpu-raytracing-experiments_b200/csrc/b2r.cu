@@ -145,8 +145,8 @@ int compute_grids(b2r_ctx* c) {
 	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<false, false, false>), kBruteBlock, &c->grid_brute))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<true, false, true>), kBruteBlock, &c->grid_brute_first_exact))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<false, false, true>), kBruteBlock, &c->grid_brute_exact))) return rc;
-	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_closest<false>), kTravBlock, &c->grid_closest))) return rc;
-	if ((rc = occ(reinterpret_cast<const void*>(&k_shade), kBruteBlock, &c->grid_shade))) return rc;
+	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_closest<false, false>), kTravBlock, &c->grid_closest))) return rc;
+	if ((rc = occ(reinterpret_cast<const void*>(&k_shade<false>), kBruteBlock, &c->grid_shade))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_shadow<false>), kTravBlock, &c->grid_shadow))) return rc;
 	c->grid_stream = c->sm_count * 8;
 	return B2R_OK;
@@ -191,9 +191,15 @@ int enqueue_batch(b2r_ctx* c, bool profile) {
 	} else {
 		if ((rc = launch(c, KK_GENERATE, profile, [&] { k_generate<<<c->grid_stream, kBlock, 0, st>>>(p); }))) return rc;
 		const bool mis = !(c->cfg.flags & B2R_FLAG_NO_MIS);
+		const bool exact = (c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) != 0;
+		if (exact && c->params.scene.n_mat > 64) return fail(B2R_ERR_STATE, "B2R_FLAG_REFERENCE_EXACT: at most 64 materials (RendererPolicy::max_materialID, Renderer.hpp:23)");
 		for (uint32_t b = 0; b < mb; b++) {
-			if ((rc = launch(c, KK_CLOSEST, profile, [&] { if (count) k_intersect_closest<true><<<c->grid_closest, kTravBlock, 0, st>>>(p, b); else k_intersect_closest<false><<<c->grid_closest, kTravBlock, 0, st>>>(p, b); }))) return rc;
-			if ((rc = launch(c, KK_SHADE, profile, [&] { k_shade<<<c->grid_shade, kBruteBlock, 0, st>>>(p, b); }))) return rc;
+			if ((rc = launch(c, KK_CLOSEST, profile, [&] {
+				if (exact) { if (count) k_intersect_closest<true, true><<<c->grid_closest, kTravBlock, 0, st>>>(p, b); else k_intersect_closest<false, true><<<c->grid_closest, kTravBlock, 0, st>>>(p, b); }
+				else { if (count) k_intersect_closest<true, false><<<c->grid_closest, kTravBlock, 0, st>>>(p, b); else k_intersect_closest<false, false><<<c->grid_closest, kTravBlock, 0, st>>>(p, b); }
+			}))) return rc;
+			if ((rc = launch(c, KK_SHADE, profile, [&] { if (exact) k_shade<true><<<c->grid_shade, kBruteBlock, 0, st>>>(p, b); else k_shade<false><<<c->grid_shade, kBruteBlock, 0, st>>>(p, b); }))) return rc;
+			if (exact && b + 1 < mb) { if ((rc = launch(c, KK_SHADE, profile, [&] { k_stream_rank<<<c->grid_stream, 256, 0, st>>>(p, b); }))) return rc; }
 			if (mis && b + 1 < mb) {
 				if ((rc = launch(c, KK_SHADOW, profile, [&] { if (count) k_intersect_shadow<true><<<c->grid_shadow, kTravBlock, 0, st>>>(p, b); else k_intersect_shadow<false><<<c->grid_shadow, kTravBlock, 0, st>>>(p, b); }))) return rc;
 			}
@@ -225,7 +231,7 @@ int run_batch(b2r_ctx* c, const BatchArgs& args) {
 	CU(cudaGraphLaunch(c->graph_exec, c->stream));
 	const uint32_t mb = c->cfg.max_bounces;
 	const bool mis = !(c->cfg.flags & B2R_FLAG_NO_MIS);
-	c->launches += c->use_bvh ? 2 + static_cast<uint64_t>(mb) * 2 + (mis ? mb - 1 : 0) : static_cast<uint64_t>(mb) + 1 + ((c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) ? mb - 1 : 0);
+	c->launches += (c->use_bvh ? 2 + static_cast<uint64_t>(mb) * 2 + (mis ? mb - 1 : 0) : static_cast<uint64_t>(mb) + 1) + ((c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) ? mb - 1 : 0);
 	return B2R_OK;
 }
 

@@ -480,7 +480,7 @@ struct SmemStack {
 // closest-hit traversal of queue side (bounce & 1)
 // (63 registers without a minimum-blocks bound = 8 resident CTAs. Measured: bounding it to 8 costs 4 %; 71/79/96 registers with
 // 7/6/5 CTAs cost 3/5/16 %; 56/48 registers with 9/10 CTAs and a shorter shared-memory stack cost 5/8 %.)
-template <bool COUNT>
+template <bool COUNT, bool EXACT>
 __global__ void __launch_bounds__(kTravBlock) k_intersect_closest(const Params p, const uint32_t bounce) {
 	const uint32_t n_in = p.cnt.paths[bounce];
 	const int side = bounce & 1;
@@ -497,7 +497,12 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_closest(const Params p
 		if (got != 0xffffffffu) {
 			idx = got; active = true;
 			const float4 a = p.q.A[side][idx], b = p.q.B[side][idx];
-			t.begin(Ray{a.x, a.y, a.z, a.w, b.x, b.y});
+			bool tail = false;
+			if (EXACT && bounce > 0u) {  // B2R_FLAG_REFERENCE_EXACT: scalar-tail formula for the last `active % 8` slots of the ray's stream
+				const uint32_t pid_i = __float_as_uint(b.w), stream = (pid_i >> 26) * (p.frame.npix >> 8) + ((pid_i & kPixMask) >> 8);
+				tail = static_cast<uint32_t>(p.ex.slot[side][idx]) >= (static_cast<uint32_t>(p.ex.act[side][stream]) & ~7u);
+			}
+			t.begin(Ray{a.x, a.y, a.z, a.w, b.x, b.y}, tail);
 		}
 		uint32_t live = __ballot_sync(0xffffffffu, active);
 		if (live == 0u) break;
@@ -515,6 +520,7 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_closest(const Params p
 }
 // shade the hit records: light sample -> shadow queue, emission, BRDF sample / roulette -> next path queue.
 // Same CTA structure as the brute-force kernel: hits are collected in a shared-memory queue and shaded a full CTA at a time.
+template <bool EXACT>
 __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_shade(const Params p, const uint32_t bounce) {
 	constexpr int kQ = 2 * kBruteBlock;
 	__shared__ uint32_t s_hit_i[kQ]; __shared__ float s_hit_t[kQ]; __shared__ int32_t s_hit_prim[kQ];
@@ -552,12 +558,14 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_shade(con
 		const uint32_t qi = queued - take + threadIdx.x;
 		const bool shade = threadIdx.x < take;
 		queued -= take;
-		bool keep = false, want_shadow = false; ShadowRay sr; PathState s; uint32_t pid = 0;
+		bool keep = false, want_shadow = false; ShadowRay sr; PathState s; uint32_t pid = 0, ex_slot = 0, ex_mat = 0;
 		if (shade) {
 			const uint32_t hi = s_hit_i[qi]; const float depth = s_hit_t[qi]; const int32_t prim = s_hit_prim[qi];
 			s = load_path(p.q, side, hi); pid = s.pid;
+			if (EXACT) ex_slot = bounce == 0u ? (pid & 255u) : static_cast<uint32_t>(p.ex.slot[side][hi]);  // bounce 0: slot = pixel ID
 			const uint32_t acc = p.batch->acc[s.pid >> 26], seed = pixel_seed(s.pid & kPixMask, p.frame.max_bounces);
 			const Surface sf = shade_surface(sc, s, depth, prim);
+			if (EXACT) ex_mat = static_cast<uint32_t>(sf.mat);
 			c_hits++;
 			if (last) { rad_zero(p.rad, p.frame.npix, s.pid); c_drop++; }  // Q11
 			else {
@@ -592,7 +600,13 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_shade(con
 			p.q.SB[d] = make_float4(sr.d.y, sr.d.z, sr.tfar, __uint_as_float(pid));
 			p.q.SL[d] = sr.L.x; p.q.SL[p.q.cap + d] = sr.L.y; p.q.SL[2u * p.q.cap + d] = sr.L.z;
 		}
-		if (keep) store_path(p.q, side ^ 1, s_base + rank, s);
+		if (keep) {
+			store_path(p.q, side ^ 1, s_base + rank, s);
+			if (EXACT) {  // (stream, slot) -> material and next-queue index, for k_stream_rank
+				const uint32_t e = (pid >> 26) * p.frame.npix + ((pid & kPixMask) & ~255u) + ex_slot;
+				p.ex.key[e] = static_cast<uint8_t>(ex_mat + 1u); p.ex.next_idx[e] = s_base + rank;
+			}
+		}
 	}
 	stat_add(p.cnt.stats, ST_HITS, c_hits); stat_add(p.cnt.stats, ST_TERM, c_term);
 	stat_add(p.cnt.stats, ST_DROPPED, c_drop); stat_add(p.cnt.stats, ST_EVENTS, c_events); stat_add(p.cnt.stats, ST_SHADOW, c_inline_shadow);

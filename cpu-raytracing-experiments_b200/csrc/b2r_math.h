@@ -277,6 +277,20 @@ B2R_HD void sphere_closest_scalar_update(float cx, float cy, float cz, float r2,
 	if (dist < 0.0f || dist >= *best) return;
 	*best = dist; *prim = id;
 }
+// the same formula as a candidate test (for the BVH traversal, where spheres are not met in index order): distance if the scalar
+// tail would consider this sphere at all (discriminant >= 0 and distance >= 0); the caller applies `d < best`, ties to the lower index
+B2R_HD bool sphere_hit_closest_scalar(float cx, float cy, float cz, float r2, float ox, float oy, float oz, float dx, float dy, float dz, float* dist_out) {
+	float b = 0.0f, disc = r2;
+	float t = cx - ox; b += dx * t; disc -= t * t;
+	t = cy - oy; b += dy * t; disc -= t * t;
+	t = cz - oz; b += dz * t; disc -= t * t;
+	disc += b * b;
+	if (disc < 0.0f) return false;
+	disc = sqrtf(disc);
+	const float dist = (b >= disc) ? b - disc : b + disc;
+	*dist_out = dist;
+	return !(dist < 0.0f);
+}
 // Any hit along [0, tfar): BVH.hpp:294-300 (glm dot products, no FMA)
 B2R_HD bool sphere_hit_any(float cx, float cy, float cz, float r2, float ox, float oy, float oz, float dx, float dy, float dz, float tfar) {
 	f3 p{cx - ox, cy - oy, cz - oz};

@@ -282,8 +282,9 @@ template <bool STAGED> B2R_HD float4 node_f4(const float4* n, int i) { return ST
 template <class Stack>
 struct TravClosestT : TravBase {
 	float best; int32_t prim;
+	bool tail = false;  // B2R_FLAG_REFERENCE_EXACT: this ray sits in the scalar tail of its tile's stream (BVH.hpp:270-286)
 	Stack stack;
-	B2R_HD void begin(const Ray& r) { arm(r); best = FLT_MAX; prim = -1; stack.reset(); }
+	B2R_HD void begin(const Ray& r, bool scalar_tail = false) { arm(r); best = FLT_MAX; prim = -1; tail = scalar_tail; stack.reset(); }
 	template <bool COUNT, bool STAGED>
 	B2R_HD bool visit(const float4* n, uint32_t tn_bits, uint32_t* c_sphere, uint32_t* c_box) {
 		uint32_t key[4], link[4]; uint32_t leaves = 0u;
@@ -306,7 +307,8 @@ struct TravClosestT : TravBase {
 			leaves &= leaves - 1u;
 			const float4 sp = node_f4<STAGED>(n, 2 * k); const int32_t id = ~as_int(node_f4<STAGED>(n, 2 * k + 1).z);
 			float d; if (COUNT) (*c_sphere)++;
-			if (sphere_hit_closest(sp.x, sp.y, sp.z, sp.w, ox, oy, oz, dx, dy, dz, &d)) {
+			const bool cand = tail ? sphere_hit_closest_scalar(sp.x, sp.y, sp.z, sp.w, ox, oy, oz, dx, dy, dz, &d) : sphere_hit_closest(sp.x, sp.y, sp.z, sp.w, ox, oy, oz, dx, dy, dz, &d);
+			if (cand) {
 				if (d < best || (d == best && id < prim)) { best = d; prim = id; }
 			}
 		}

@@ -480,3 +480,33 @@ def test_c2_size_reference_exact_mode_bit_identical_to_the_reference():
     assert gb.tobytes() == rb.tobytes()
     assert g.Render() and acted and g.framebuffer.tobytes() == rframe.tobytes()
     g.close()
+
+
+@pytest.mark.parametrize("n,w,h,mb,spp", [(600, 96, 64, 8, 5), (5000, 80, 48, 16, 5)])
+def test_reference_exact_mode_bvh_pipeline_equals_slot_exact_oracle(n, w, h, mb, spp):
+    """B2R_FLAG_REFERENCE_EXACT through the flattened-BVH kernels: tail rays take the scalar formula in the leaf tests, k_shade leaves
+    (material, slot) behind, k_stream_rank orders the next bounce — against the oracle's slot-exact BRUTE-FORCE mode (the semantics the
+    reference ships). Bit-exact whenever the BVH's hit decisions equal brute force (padded boxes: a divergent fraction is tolerated and printed)."""
+    sc = scenes.random_scene(n, light_every=40)
+    r = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=5, flags=b2r.FLAG_REFERENCE_EXACT | b2r.FLAG_FORCE_BVH); r.Accumulate(spp)
+    o = oracle_for(sc, w, h, mb, 5, flags=oracle_py.ORC_SLOT_EXACT); o.accumulate(spp)
+    gb, ob = r.buckets_host(), o.buckets()
+    same = float((gb.view(np.uint32) == ob.view(np.uint32)).all(axis=(0, 1)).mean())
+    print(f"BVH pipeline, reference-exact mode, n={n}: bit-identical pixels {same:.6f}, divergent fraction {divergent_fraction(gb, ob):.3e}")
+    assert divergent_fraction(gb, ob) < 2e-3 and same > 0.998
+    r.close(); o.close()
+
+
+@pytest.mark.skipif(not oracle_py.have_reference_renderer(), reason="oracle/_ref/librefrenderer.so not present")
+def test_bvh_pipeline_reference_exact_mode_vs_the_reference_itself():
+    """2000 random spheres (the reference brute-forces them on the host cores), GPU through the BVH kernels in reference-exact mode."""
+    sc = scenes.random_scene(2000, light_every=100); w, h, mb = 96, 64, 16
+    ref = oracle_py.ReferenceRenderer(sc, w, h, mb); ref.accumulate(5); rb = ref.buckets(); acted, rframe = ref.render(); ref.close()
+    g = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=5, flags=b2r.FLAG_REFERENCE_EXACT | b2r.FLAG_FORCE_BVH); g.Accumulate(5)
+    gb = g.buckets_host()
+    same = float((gb.view(np.uint32) == rb.view(np.uint32)).all(axis=(0, 1)).mean())
+    print(f"2000 spheres, BVH kernels in reference-exact mode vs the reference itself: bit-identical pixels {same:.6f}")
+    assert same > 0.998 and divergent_fraction(gb, rb) < 2e-3
+    if same == 1.0:
+        assert g.Render() and acted and g.framebuffer.tobytes() == rframe.tobytes()
+    g.close()
