@@ -510,3 +510,19 @@ def test_bvh_pipeline_reference_exact_mode_vs_the_reference_itself():
     if same == 1.0:
         assert g.Render() and acted and g.framebuffer.tobytes() == rframe.tobytes()
     g.close()
+
+
+@pytest.mark.skipif(not oracle_py.have_reference_renderer(), reason="oracle/_ref/librefrenderer.so not present")
+def test_c3_scene_reference_exact_mode_vs_the_reference_itself():
+    """BASELINE config C3's scene (100k random spheres, 100 lights, max_bounces 16, its camera) on a 64x48 frame: the reference
+    brute-forces 100k spheres per ray on the host cores (a few seconds); the GPU walks its BVH in reference-exact mode."""
+    sc = scenes.random_scene(100000); w, h, mb = 64, 48, 16
+    ref = oracle_py.ReferenceRenderer(sc, w, h, mb); ref.accumulate(5); rb = ref.buckets(); acted, rframe = ref.render(); ref.close()
+    g = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=5, flags=b2r.FLAG_REFERENCE_EXACT); g.Accumulate(5)
+    gb = g.buckets_host()
+    same = float((gb.view(np.uint32) == rb.view(np.uint32)).all(axis=(0, 1)).mean())
+    print(f"C3 scene (100k spheres) 64x48, BVH kernels in reference-exact mode vs the reference itself: bit-identical pixels {same:.6f}, divergent fraction {divergent_fraction(gb, rb):.3e}")
+    assert same > 0.998 and divergent_fraction(gb, rb) < 2e-3
+    if same == 1.0:
+        assert g.Render() and acted and g.framebuffer.tobytes() == rframe.tobytes()
+    g.close()
