@@ -241,6 +241,19 @@ def test_error_behaviour():
         r.SetScene(ps)
     assert e.value.code == b2r.ERR_BVH
     r.close()
+    # B2R_FLAG_REFERENCE_EXACT is a create-time choice (it sizes the stream bookkeeping) and follows the reference's 64-material limit
+    r = b2r.Renderer(sc, 64, 64)
+    with pytest.raises(b2r.B2RError) as e:
+        r.set_flags(b2r.FLAG_REFERENCE_EXACT)
+    assert e.value.code == b2r.ERR_STATE
+    r.close()
+    many = scenes.random_scene(80, light_every=7)
+    many["material"] = np.repeat(many["material"], 10, axis=0)[:70].copy()  # 70 materials > RendererPolicy::max_materialID
+    r = b2r.Renderer(many, 64, 64, flags=b2r.FLAG_REFERENCE_EXACT | b2r.FLAG_FORCE_BRUTE)
+    with pytest.raises(b2r.B2RError) as e:
+        r.Accumulate(1)
+    assert e.value.code == b2r.ERR_STATE
+    r.close()
 
 
 def test_cpp_mirror_frame_loop(tmp_path):
