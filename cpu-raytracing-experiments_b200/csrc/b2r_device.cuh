@@ -333,39 +333,49 @@ __global__ void __launch_bounds__(256) k_stream_rank(const Params p, const uint3
 	const int side = bounce & 1;
 	const uint32_t n_streams = p.batch->n_slots * (p.frame.npix >> 8), warp = threadIdx.x >> 5, lane = lane_id(), below = (1u << lane) - 1u;
 	uint16_t* run = s_run[warp];
-	for (uint32_t stream = blockIdx.x * 8u + warp; stream < n_streams; stream += gridDim.x * 8u) {
-		if (bounce > 0u && p.ex.act[side][stream] == 0u) { if (lane == 0u) p.ex.act[side ^ 1][stream] = 0; continue; }  // stream already empty (warp-uniform)
-		const uint32_t e0 = stream * 256u + lane;
-		uint32_t key[8], any = 0u;
+	// a warp takes 32 consecutive streams at a time: one coalesced look at their active counts, then only the non-empty ones are ranked
+	for (uint32_t group = (blockIdx.x * 8u + warp) * 32u; group < n_streams; group += gridDim.x * 8u * 32u) {
+		const uint32_t mine = group + lane;
+		const bool has_rays = mine < n_streams && (bounce == 0u || p.ex.act[side][mine] != 0u);
+		if (mine < n_streams && !has_rays) p.ex.act[side ^ 1][mine] = 0;
+		uint32_t todo = __ballot_sync(0xffffffffu, has_rays);
+		while (todo) {
+			const uint32_t stream = group + static_cast<uint32_t>(__ffs(static_cast<int>(todo)) - 1);
+			todo &= todo - 1u;
+			const uint32_t e0 = stream * 256u + lane;
+			uint32_t key[8], any = 0u;
 #pragma unroll
-		for (uint32_t r = 0; r < 8u; r++) { key[r] = p.ex.key[e0 + 32u * r]; any |= key[r]; }
-		if (!__any_sync(0xffffffffu, any != 0u)) { if (lane == 0u) p.ex.act[side ^ 1][stream] = 0; continue; }
-		run[lane] = 0; run[lane + 32u] = 0;
-		__syncwarp();
-		uint32_t within[8];
-#pragma unroll
-		for (uint32_t r = 0; r < 8u; r++) {
-			const bool alive = key[r] != 0u;
-			const uint32_t m = alive ? key[r] - 1u : 0xffffu;  // the dead lanes match each other: harmless
-			const uint32_t peers = __match_any_sync(0xffffffffu, m), rk = __popc(peers & below);
-			within[r] = alive ? run[m] + rk : 0u;
+			for (uint32_t r = 0; r < 8u; r++) { key[r] = p.ex.key[e0 + 32u * r]; any |= key[r]; }
+			if (!__any_sync(0xffffffffu, any != 0u)) { if (lane == 0u) p.ex.act[side ^ 1][stream] = 0; continue; }
+			run[lane] = 0; run[lane + 32u] = 0;
 			__syncwarp();
-			if (alive && rk == 0u) run[m] = static_cast<uint16_t>(run[m] + __popc(peers));
-			if (alive) p.ex.key[e0 + 32u * r] = 0;  // left clean for the next bounce
+			uint32_t within[8];
+#pragma unroll
+			for (uint32_t r = 0; r < 8u; r++) {
+				const bool alive = key[r] != 0u;
+				within[r] = 0u;
+				if (!__any_sync(0xffffffffu, alive)) continue;  // nobody left in these 32 slots (late bounces: most rounds)
+				const uint32_t m = alive ? key[r] - 1u : 0xffffu;  // the dead lanes match each other: harmless
+				const uint32_t peers = __match_any_sync(0xffffffffu, m), rk = __popc(peers & below);
+				if (alive) within[r] = run[m] + rk;
+				__syncwarp();
+				if (alive && rk == 0u) run[m] = static_cast<uint16_t>(run[m] + __popc(peers));
+				if (alive) p.ex.key[e0 + 32u * r] = 0;  // left clean for the next bounce
+				__syncwarp();
+			}
+			const uint32_t c0 = run[2u * lane], c1 = run[2u * lane + 1u];
+			uint32_t incl = c0 + c1;
+#pragma unroll
+			for (uint32_t d = 1; d < 32u; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+			const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), excl = incl - (c0 + c1);
+			__syncwarp();
+			run[2u * lane] = static_cast<uint16_t>(excl); run[2u * lane + 1u] = static_cast<uint16_t>(excl + c0);
+			__syncwarp();
+#pragma unroll
+			for (uint32_t r = 0; r < 8u; r++) if (key[r] != 0u) p.ex.slot[side ^ 1][p.ex.next_idx[e0 + 32u * r]] = static_cast<uint8_t>(run[key[r] - 1u] + within[r]);
+			if (lane == 0u) p.ex.act[side ^ 1][stream] = static_cast<uint16_t>(total);
 			__syncwarp();
 		}
-		const uint32_t c0 = run[2u * lane], c1 = run[2u * lane + 1u];
-		uint32_t incl = c0 + c1;
-#pragma unroll
-		for (uint32_t d = 1; d < 32u; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), excl = incl - (c0 + c1);
-		__syncwarp();
-		run[2u * lane] = static_cast<uint16_t>(excl); run[2u * lane + 1u] = static_cast<uint16_t>(excl + c0);
-		__syncwarp();
-#pragma unroll
-		for (uint32_t r = 0; r < 8u; r++) if (key[r] != 0u) p.ex.slot[side ^ 1][p.ex.next_idx[e0 + 32u * r]] = static_cast<uint8_t>(run[key[r] - 1u] + within[r]);
-		if (lane == 0u) p.ex.act[side ^ 1][stream] = static_cast<uint16_t>(total);
-		__syncwarp();
 	}
 }
 
