@@ -268,7 +268,9 @@ def main():
 
     dbg = bool(os.environ.get("B2R_BENCH_DEBUG"))
 
-    def step(to_host_fb=None, upload=False):
+    frame_no = [0]
+
+    def step(to_host_fb=None, upload=False, async_fbs=None):
         t0 = time.perf_counter()
         if upload:
             r.SetScene(ps)  # host -> device: spheres, materials, lights, flattened BVH, camera
@@ -287,6 +289,10 @@ def main():
         elif world > 1:
             combined = b2r_dist.combine_buckets(local_buckets)  # the one collective: NCCL all-reduce of the bucket sums
             ok = r.Render(to_host=to_host_fb is not None and rank == 0, out=to_host_fb, dev_buckets=combined.data_ptr())
+        elif async_fbs is not None:
+            # progressive rendering as a user would drive it: frame N is copied out on the library's second stream into one of two pinned
+            # buffers while the samples of frame N+1 are traced (b2r_resolve_async); nothing is skipped, every frame lands on the host
+            ok = r.RenderAsync(async_fbs[frame_no[0] & 1]); frame_no[0] += 1
         else:
             ok = r.Render(to_host=to_host_fb is not None, out=to_host_fb)
         assert ok
@@ -304,6 +310,8 @@ def main():
         e0.record(stream)
         for _ in range(n):
             step(**kw)
+        if kw.get("async_fbs") is not None:
+            r.WaitFrame()  # the last frame has landed in host memory before the clock stops
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -334,10 +342,16 @@ def main():
 
     # ---- e2e: same steps through the public API with HOST buffers (scene upload + frame download each step)
     fb_host = torch.empty((wl["h"], wl["w"], 4), dtype=torch.float32, pin_memory=True).numpy()
+    e2e_kw = dict(to_host_fb=fb_host, upload=True)
+    if world == 1:  # single GPU: frames leave through b2r_resolve_async into two alternating pinned buffers (multi-GPU: the fused P2P resolve stays synchronous)
+        fb_host2 = torch.empty((wl["h"], wl["w"], 4), dtype=torch.float32, pin_memory=True).numpy()
+        e2e_kw = dict(async_fbs=[fb_host, fb_host2], upload=True)
     for _ in range(2):
-        step(to_host_fb=fb_host, upload=True)
+        step(**e2e_kw)
+    if world == 1:
+        r.WaitFrame()
     r.reset_counters()
-    ms_e2e = timed(args.steps, to_host_fb=fb_host, upload=True)
+    ms_e2e = timed(args.steps, **e2e_kw)
     c2 = r.counters(); rays_e2e = c2["extension_rays"] + c2["shadow_rays"]
     if world > 1:
         t = torch.tensor([rays_e2e], device=dev, dtype=torch.float64); dist.all_reduce(t); rays_e2e = float(t[0])
@@ -438,7 +452,8 @@ def main():
                        "l2": "no flush needed: each step streams >1 GB of path-queue records (>> 126 MB L2); RNG-unique samples every step"},
             "paths_per_s": paths_total / secs, "rays_per_step": rays_total / args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
-                    "includes": "upload_scene (pack + 128-B BVH flatten on host, H2D), set_camera, reset, Accumulate x spp, Render, D2H of the RGBA32F frame into pinned memory"},
+                    "includes": "upload_scene (pack + 128-B BVH flatten on host, H2D), set_camera, reset, Accumulate x spp, Render, D2H of the RGBA32F frame into pinned memory"
+                                + ("; frames leave through b2r_resolve_async (copy of frame N overlaps the tracing of frame N+1, two pinned buffers, last frame waited for inside the timed region)" if world == 1 else "")},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "kernel_ms": kernel_ms,
         }
         if exact_line:

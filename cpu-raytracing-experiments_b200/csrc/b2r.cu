@@ -46,6 +46,7 @@ template <typename T> void dev_free(T** p) { if (*p) { cudaFree(*p); *p = nullpt
 struct b2r_ctx {
 	b2r_config cfg{};
 	cudaStream_t stream = nullptr, own_stream = nullptr;
+	cudaStream_t copy_stream = nullptr; cudaEvent_t ev_resolved = nullptr, ev_copied = nullptr; bool copy_pending = false;  // b2r_resolve_async
 	bool have_scene = false, have_camera = false, use_bvh = false;
 	uint32_t accumulations = 0;
 	uint32_t slots = 8;
@@ -301,6 +302,7 @@ void b2r_destroy(b2r_ctx* c) {
 	for (int s = 0; s < 2; s++) { dev_free(&c->d_ex_slot[s]); dev_free(&c->d_ex_act[s]); }
 	dev_free(&c->d_ex_key); dev_free(&c->d_ex_next);
 	dev_free(&c->d_counts); dev_free(&c->d_stats); dev_free(&c->d_batch);
+	if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); cudaEventDestroy(c->ev_resolved); cudaEventDestroy(c->ev_copied); }
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
 	delete c;
 }
@@ -311,6 +313,7 @@ int b2r_resize(b2r_ctx* c, uint32_t width, uint32_t height) {
 	if (static_cast<uint64_t>(width) * height > kPixMask) return fail(B2R_ERR_ARG, "image too large");
 	int rc = ensure_device(c); if (rc) return rc;
 	CU(cudaStreamSynchronize(c->stream));
+	if (c->copy_pending) { CU(cudaEventSynchronize(c->ev_copied)); c->copy_pending = false; }
 	if (width == c->cfg.width && height == c->cfg.height) return b2r_reset(c);
 	c->cfg.width = width; c->cfg.height = height;
 	return alloc_frame(c);
@@ -444,19 +447,44 @@ int b2r_accumulate(b2r_ctx* c, uint32_t n_samples) {
 	return B2R_OK;
 }
 
-static int resolve_with(b2r_ctx* c, const BucketPtrs& bp, float* rgba_out_host, int tonemap) {
+static int resolve_with(b2r_ctx* c, const BucketPtrs& bp, float* rgba_out_host, int tonemap, bool async = false) {
 	int rc = ensure_device(c); if (rc) return rc;
 	if (c->accumulations == 0 || c->accumulations % c->cfg.buckets) return B2R_ERR_NOT_READY;  // Renderer.hpp:437
 	const float scale = c->params.frame.cam.exposure / static_cast<float>(c->accumulations / c->cfg.buckets);  // :439
 	const bool profile = (c->cfg.flags & B2R_FLAG_NO_GRAPH) != 0;
+	if (c->copy_pending) CU(cudaStreamWaitEvent(c->stream, c->ev_copied, 0));  // the previous frame is still being read out of d_fb
 	rc = launch(c, KK_RESOLVE, profile, [&] { k_resolve<<<c->grid_stream, kBlock, 0, c->stream>>>(c->params.frame, bp, c->d_fb, scale, tonemap); });
 	if (rc) return rc;
-	if (rgba_out_host) CU(cudaMemcpyAsync(rgba_out_host, c->d_fb, static_cast<size_t>(c->params.frame.npix) * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+	const size_t bytes = static_cast<size_t>(c->params.frame.npix) * sizeof(float4);
+	if (async && rgba_out_host) {
+		// the frame leaves on a second stream (copy engine) while the next samples are traced on the main one
+		if (!c->copy_stream) { CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&c->ev_resolved, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming)); }
+		CU(cudaEventRecord(c->ev_resolved, c->stream));
+		CU(cudaStreamWaitEvent(c->copy_stream, c->ev_resolved, 0));
+		CU(cudaMemcpyAsync(rgba_out_host, c->d_fb, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+		CU(cudaEventRecord(c->ev_copied, c->copy_stream));
+		c->copy_pending = true;
+		return B2R_OK;
+	}
+	if (rgba_out_host) CU(cudaMemcpyAsync(rgba_out_host, c->d_fb, bytes, cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
 	return collect_timings(c);
 }
 
 int b2r_resolve(b2r_ctx* c, float* rgba_out_host, int tonemap) { return b2r_resolve_from(c, nullptr, rgba_out_host, tonemap); }
+
+int b2r_resolve_async(b2r_ctx* c, float* rgba_out_host, int tonemap) {
+	if (!c || !rgba_out_host) return fail(B2R_ERR_ARG, "null argument");
+	BucketPtrs bp{};
+	for (uint32_t k = 0; k < c->cfg.buckets; k++) bp.k[k] = c->d_acc + static_cast<size_t>(k) * 3 * c->params.frame.npix;
+	return resolve_with(c, bp, rgba_out_host, tonemap, true);
+}
+int b2r_frame_wait(b2r_ctx* c) {
+	if (!c) return fail(B2R_ERR_ARG, "null context");
+	int rc = ensure_device(c); if (rc) return rc;
+	if (c->copy_pending) { CU(cudaEventSynchronize(c->ev_copied)); c->copy_pending = false; }
+	return B2R_OK;
+}
 
 int b2r_resolve_from(b2r_ctx* c, const void* dev_buckets, float* rgba_out_host, int tonemap) {
 	if (!c) return fail(B2R_ERR_ARG, "null context");

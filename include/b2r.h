@@ -127,6 +127,14 @@ int  b2r_accumulate(b2r_ctx* ctx, uint32_t n_samples);
  * (tonemap=0: linear), RGBA32F, row 0 = y 0. rgba_out_host: width*height*4 floats (NULL: leave it on the device).
  * Returns B2R_ERR_NOT_READY and writes nothing unless accumulations % buckets == 0. Synchronises. */
 int  b2r_resolve(b2r_ctx* ctx, float* rgba_out_host, int tonemap);
+/* Render() without the stall: the resolve kernel is enqueued on the context's stream and the frame is copied to rgba_out_host on a
+ * second stream, so the next b2r_accumulate calls overlap the copy (progressive rendering: frame N leaves while the samples of
+ * frame N+1 are traced). rgba_out_host must be page-locked for the overlap and must stay valid until b2r_frame_wait() returns;
+ * a following resolve waits (on the device) for the pending copy before it overwrites the device framebuffer.
+ * Returns B2R_ERR_NOT_READY like b2r_resolve. The reference's Render() is synchronous (Renderer.hpp:436-478); this is the same
+ * computation with the hand-over made explicit. */
+int  b2r_resolve_async(b2r_ctx* ctx, float* rgba_out_host, int tonemap);
+int  b2r_frame_wait(b2r_ctx* ctx);   /* blocks until the frame of the last b2r_resolve_async has landed in host memory */
 /* Same, reading the K bucket sums from another device array of the same layout (e.g. the NCCL-combined buckets of a
  * multi-GPU frame) instead of this context's own accumulator. dev_buckets == NULL means the context's own. */
 int  b2r_resolve_from(b2r_ctx* ctx, const void* dev_buckets, float* rgba_out_host, int tonemap);

@@ -539,3 +539,22 @@ def test_c3_scene_reference_exact_mode_vs_the_reference_itself():
     if same == 1.0:
         assert g.Render() and acted and g.framebuffer.tobytes() == rframe.tobytes()
     g.close()
+
+
+def test_async_resolve_delivers_the_same_frames():
+    """b2r_resolve_async / b2r_frame_wait: three frames rendered back to back, each copied out on the second stream while the next
+    one is traced, equal the frames of the synchronous Render() bit for bit."""
+    import torch
+    sc = scenes.default_scene(); w, h, mb, K = 320, 192, 8, 5
+    a = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=K); b = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=K)
+    pinned = [torch.empty((h, w, 4), dtype=torch.float32, pin_memory=True).numpy() for _ in range(3)]
+    sync_frames = []
+    for i in range(3):
+        a.Accumulate(K); assert a.Render(); sync_frames.append(a.framebuffer.copy())
+        b.Accumulate(K); assert b.RenderAsync(pinned[i])
+    b.WaitFrame()
+    for i in (0, 1, 2):
+        assert pinned[i].tobytes() == sync_frames[i].tobytes()
+    b.Accumulate(1)
+    assert not b.RenderAsync(pinned[1])  # accumulations % K != 0: no-op like Renderer::Render (Renderer.hpp:437)
+    a.close(); b.close()
