@@ -46,6 +46,8 @@ template <typename T> void dev_free(T** p) { if (*p) { cudaFree(*p); *p = nullpt
 struct b2r_ctx {
 	b2r_config cfg{};
 	cudaStream_t stream = nullptr, own_stream = nullptr;
+	// scene upload staging: one page-locked block reused by every b2r_upload_scene (no stream synchronisation on the upload path)
+	unsigned char* h_stage = nullptr; size_t stage_bytes = 0; cudaEvent_t ev_stage = nullptr; bool stage_busy = false;
 	cudaStream_t copy_stream = nullptr; cudaEvent_t ev_resolved = nullptr, ev_copied = nullptr; bool copy_pending = false;  // b2r_resolve_async
 	bool have_scene = false, have_camera = false, use_bvh = false;
 	uint32_t accumulations = 0;
@@ -84,7 +86,7 @@ namespace {
 int ensure_device(b2r_ctx* c) { CU(cudaSetDevice(c->cfg.device)); return B2R_OK; }
 
 void drop_graph(b2r_ctx* c) {
-	if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+	if (c->graph_exec) { if (c->stream) cudaStreamSynchronize(c->stream); cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }  // (a launch of it may still be running)
 	c->graph_valid = false;
 }
 
@@ -302,6 +304,8 @@ void b2r_destroy(b2r_ctx* c) {
 	for (int s = 0; s < 2; s++) { dev_free(&c->d_ex_slot[s]); dev_free(&c->d_ex_act[s]); }
 	dev_free(&c->d_ex_key); dev_free(&c->d_ex_next);
 	dev_free(&c->d_counts); dev_free(&c->d_stats); dev_free(&c->d_batch);
+	if (c->h_stage) cudaFreeHost(c->h_stage);
+	if (c->ev_stage) cudaEventDestroy(c->ev_stage);
 	if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); cudaEventDestroy(c->ev_resolved); cudaEventDestroy(c->ev_copied); }
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
 	delete c;
@@ -372,7 +376,9 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 	for (uint32_t i = 0; i < n_prims; i++) if (prims[i].material_ID < 0 || static_cast<uint32_t>(prims[i].material_ID) >= n_mat) return fail(B2R_ERR_ARG, "material_ID out of range");
 	for (uint32_t i = 0; i < n_lights; i++) if (light_geom_idx[i] < 0 || static_cast<uint32_t>(light_geom_idx[i]) >= n_geom) return fail(B2R_ERR_ARG, "light index out of range");
 	int rc = ensure_device(c); if (rc) return rc;
-	CU(cudaStreamSynchronize(c->stream));
+	// No stream synchronisation from here on: the copies below are ordered after the kernels already enqueued on the stream (which
+	// may still read the old scene) and before the ones enqueued next. The host side is staged in one page-locked block that is only
+	// rewritten once the previous upload's copies have completed (an event early in the previous frame, not its end).
 
 	{  // derived traversal layout, cached on the sphere array (and on which topology was asked for)
 		uint64_t key = 1469598103934665603ull ^ ((c->cfg.flags & B2R_FLAG_REFERENCE_TREE) ? 0x9e3779b97f4a7c15ull : 0ull);
@@ -389,6 +395,10 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 
 	PackedScene ps; pack_scene(prims, n_prims, materials, n_mat, light_geom_idx, n_lights, geometry, ps);
 	auto &h_prims = ps.prims, &h_alb = ps.mat_albedo, &h_em = ps.mat_emission, &h_ls = ps.light_sphere, &h_le = ps.light_emit; auto& h_pm = ps.prim_mat;
+	const bool grow = h_prims.size() > c->cap_prims || h_pm.size() > c->cap_prim_mat || h_alb.size() > c->cap_mat_albedo || h_em.size() > c->cap_mat_emission ||
+	                  h_ls.size() > c->cap_light_sphere || h_le.size() > c->cap_light_emit || c->wide_host.nodes.size() > c->cap_wide ||
+	                  (has_ambient && static_cast<size_t>(hdri_w) * hdri_h > c->cap_hdri);
+	if (grow) CU(cudaStreamSynchronize(c->stream));  // device arrays in use are about to be replaced (first upload, or a larger scene)
 	if ((rc = dev_reserve(&c->d_prims, &c->cap_prims, h_prims.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_prim_mat, &c->cap_prim_mat, h_pm.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_mat_albedo, &c->cap_mat_albedo, h_alb.size()))) return rc;
@@ -396,19 +406,31 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 	if ((rc = dev_reserve(&c->d_light_sphere, &c->cap_light_sphere, h_ls.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_light_emit, &c->cap_light_emit, h_le.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_wide, &c->cap_wide, c->wide_host.nodes.size()))) return rc;
-	CU(cudaMemcpyAsync(c->d_prims, h_prims.data(), h_prims.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->d_prim_mat, h_pm.data(), h_pm.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->d_mat_albedo, h_alb.data(), h_alb.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->d_mat_emission, h_em.data(), h_em.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->d_light_sphere, h_ls.data(), h_ls.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->d_light_emit, h_le.data(), h_le.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->d_wide, c->wide_host.nodes.data(), c->wide_host.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice, c->stream));
-	if (has_ambient) {
-		const size_t texels = static_cast<size_t>(hdri_w) * hdri_h;
-		if ((rc = dev_reserve(&c->d_hdri, &c->cap_hdri, texels))) return rc;
-		CU(cudaMemcpyAsync(c->d_hdri, hdri_rgba, texels * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+	const size_t texels = has_ambient ? static_cast<size_t>(hdri_w) * hdri_h : 0;
+	if (has_ambient && (rc = dev_reserve(&c->d_hdri, &c->cap_hdri, texels))) return rc;
+	// stage everything in one page-locked block
+	struct Part { void* dst; const void* src; size_t bytes; };
+	const Part parts[] = {
+		{c->d_prims, h_prims.data(), h_prims.size() * sizeof(float4)}, {c->d_prim_mat, h_pm.data(), h_pm.size() * sizeof(int32_t)},
+		{c->d_mat_albedo, h_alb.data(), h_alb.size() * sizeof(float4)}, {c->d_mat_emission, h_em.data(), h_em.size() * sizeof(float4)},
+		{c->d_light_sphere, h_ls.data(), h_ls.size() * sizeof(float4)}, {c->d_light_emit, h_le.data(), h_le.size() * sizeof(float4)},
+		{c->d_wide, c->wide_host.nodes.data(), c->wide_host.nodes.size() * sizeof(WideNode)}, {c->d_hdri, hdri_rgba, texels * sizeof(float4)},
+	};
+	size_t total = 0; for (const Part& q : parts) total += (q.bytes + 255) & ~static_cast<size_t>(255);
+	if (c->stage_busy) { CU(cudaEventSynchronize(c->ev_stage)); c->stage_busy = false; }
+	if (total > c->stage_bytes) {
+		if (c->h_stage) CU(cudaFreeHost(c->h_stage));
+		c->h_stage = nullptr; c->stage_bytes = 0;
+		CU(cudaMallocHost(reinterpret_cast<void**>(&c->h_stage), total)); c->stage_bytes = total;
 	}
-	CU(cudaStreamSynchronize(c->stream));  // the staging vectors above go out of scope
+	if (!c->ev_stage) CU(cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming));
+	size_t off = 0;
+	for (const Part& q : parts) {
+		if (q.bytes) { std::memcpy(c->h_stage + off, q.src, q.bytes); CU(cudaMemcpyAsync(q.dst, c->h_stage + off, q.bytes, cudaMemcpyHostToDevice, c->stream)); }
+		off += (q.bytes + 255) & ~static_cast<size_t>(255);
+	}
+	CU(cudaEventRecord(c->ev_stage, c->stream)); c->stage_busy = true;
+	const SceneDev before = c->params.scene; const bool bvh_before = c->use_bvh;
 	SceneDev& s = c->params.scene;
 	s.prims = c->d_prims; s.prim_mat = c->d_prim_mat; s.mat_albedo = c->d_mat_albedo; s.mat_emission = c->d_mat_emission;
 	s.light_sphere = c->d_light_sphere; s.light_emit = c->d_light_emit; s.wide = c->d_wide; s.hdri = has_ambient ? c->d_hdri : nullptr;
@@ -417,20 +439,22 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 	s.ambient[0] = amb[0]; s.ambient[1] = amb[1]; s.ambient[2] = amb[2]; s.has_ambient = has_ambient ? 1 : 0;
 	s.hdri_w = hdri_w; s.hdri_h = hdri_h; s.hdri_fw = static_cast<float>(hdri_w - 1); s.hdri_fh = static_cast<float>(hdri_h - 1);  // Application.cpp:230-231
 	c->use_bvh = (c->cfg.flags & B2R_FLAG_FORCE_BVH) ? true : (c->cfg.flags & B2R_FLAG_FORCE_BRUTE) ? false : n_prims > 32;
+	// the scene's pointers and scalars travel in the kernels' parameter block: the captured graph stays valid unless they changed
+	if (!c->have_scene || bvh_before != c->use_bvh || std::memcmp(&before, &s, sizeof s) != 0) drop_graph(c);
 	c->have_scene = true;
-	drop_graph(c);
 	return B2R_OK;
 }
 
 int b2r_set_camera(b2r_ctx* c, const float pos[3], const float q[4], float half_width, float half_height, float z, float exposure) {
 	if (!c || !pos || !q) return fail(B2R_ERR_ARG, "null argument");
 	int rc = ensure_device(c); if (rc) return rc;
-	CU(cudaStreamSynchronize(c->stream));
-	CameraParams& cam = c->params.frame.cam;
+	// the camera travels in the kernels' parameter block (by value: launches already enqueued keep theirs), so no synchronisation;
+	// the captured graph is only rebuilt when the camera really changed
+	CameraParams cam = c->params.frame.cam;
 	cam.px = pos[0]; cam.py = pos[1]; cam.pz = pos[2]; cam.qw = q[0]; cam.qx = q[1]; cam.qy = q[2]; cam.qz = q[3];
 	cam.half_width = half_width; cam.half_height = half_height; cam.z = z; cam.exposure = exposure;
+	if (!c->have_camera || std::memcmp(&cam, &c->params.frame.cam, sizeof cam) != 0) { c->params.frame.cam = cam; drop_graph(c); }
 	c->have_camera = true;
-	drop_graph(c);
 	return B2R_OK;
 }
 
