@@ -5,6 +5,8 @@
 #include "b2r_math.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cmath>
 #include <cstring>
 #include <numeric>
@@ -315,68 +317,109 @@ inline void tbox_grow(TBox& a, const TBox& b) { for (int k = 0; k < 3; k++) { a.
 inline float tbox_area(const TBox& b) { const float x = b.hi[0] - b.lo[0], y = b.hi[1] - b.lo[1], z = b.hi[2] - b.lo[2]; return x * y + y * z + z * x; }
 }  // namespace
 
+namespace {
+// One subtree of the traversal tree. Node indices are fixed by the subtree sizes alone — the children of a node sit next to each
+// other at `region`, followed by all descendants of the left child (2*left - 2 nodes) and then those of the right one — so
+// subtrees can be built by different threads into the pre-sized node array and the result does not depend on the schedule.
+struct TraversalBuilder {
+	static constexpr int kBins = 16;
+	const std::vector<TBox>& box; const std::vector<float>& cen; std::vector<uint32_t>& ids; std::vector<b2r_bvh_node>& nodes;
+	void set(uint32_t node, const TBox& b, uint32_t first, uint32_t count) {
+		b2r_bvh_node nd; for (int k = 0; k < 3; k++) { nd.min_bound[k] = b.lo[k]; nd.max_bound[k] = b.hi[k]; } nd.first_id = first; nd.prim_count = count; nodes[node] = nd;
+	}
+	// splits [begin, end) of node `node`; returns the split position and writes the two children at `region`
+	uint32_t split(uint32_t node, uint32_t begin, uint32_t end, uint32_t region) {
+		const uint32_t count = end - begin;
+		float clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+		for (uint32_t i = begin; i < end; i++) for (int k = 0; k < 3; k++) { const float c = cen[3 * static_cast<size_t>(ids[i]) + k]; clo[k] = fminf(clo[k], c); chi[k] = fmaxf(chi[k], c); }
+		// binned SAH per axis; the three axes of a large node are evaluated by three threads (the top of the tree is the serial part)
+		struct AxisBest { float cost = FLT_MAX; int bin = 0; };
+		AxisBest per_axis[3];
+		auto eval_axis = [&](int axis) {
+			const float ext = chi[axis] - clo[axis];
+			if (!(ext > 0.0f)) return;
+			TBox bb[kBins]; uint32_t bc[kBins];
+			for (int q = 0; q < kBins; q++) { bb[q] = tbox_empty(); bc[q] = 0; }
+			const float scale = kBins / ext;
+			for (uint32_t i = begin; i < end; i++) {
+				int q = static_cast<int>((cen[3 * static_cast<size_t>(ids[i]) + axis] - clo[axis]) * scale); if (q >= kBins) q = kBins - 1;
+				tbox_grow(bb[q], box[ids[i]]); bc[q]++;
+			}
+			float right_area[kBins]; uint32_t right_cnt[kBins];
+			TBox acc = tbox_empty(); uint32_t cnt = 0;
+			for (int q = kBins - 1; q > 0; q--) { tbox_grow(acc, bb[q]); cnt += bc[q]; right_area[q] = cnt ? tbox_area(acc) : 0.0f; right_cnt[q] = cnt; }
+			acc = tbox_empty(); cnt = 0;
+			for (int q = 0; q + 1 < kBins; q++) {
+				tbox_grow(acc, bb[q]); cnt += bc[q];
+				if (cnt == 0 || right_cnt[q + 1] == 0) continue;
+				const float cost = tbox_area(acc) * cnt + right_area[q + 1] * right_cnt[q + 1];
+				if (cost < per_axis[axis].cost) { per_axis[axis].cost = cost; per_axis[axis].bin = q; }
+			}
+		};
+		if (count >= 65536u) { std::thread t1(eval_axis, 1), t2(eval_axis, 2); eval_axis(0); t1.join(); t2.join(); }
+		else { eval_axis(0); eval_axis(1); eval_axis(2); }
+		int best_axis = -1, best_bin = 0; float best_cost = FLT_MAX;
+		for (int axis = 0; axis < 3; axis++) if (per_axis[axis].cost < best_cost) { best_cost = per_axis[axis].cost; best_axis = axis; best_bin = per_axis[axis].bin; }  // first axis wins ties, as the serial loop did
+		uint32_t mid;
+		if (best_axis < 0) mid = begin + count / 2;  // all centroids coincide: split the list in half
+		else {
+			const float scale = kBins / (chi[best_axis] - clo[best_axis]);
+			auto it = std::partition(ids.begin() + begin, ids.begin() + end, [&](uint32_t id) {
+				int q = static_cast<int>((cen[3 * static_cast<size_t>(id) + best_axis] - clo[best_axis]) * scale); if (q >= kBins) q = kBins - 1;
+				return q <= best_bin; });
+			mid = static_cast<uint32_t>(it - ids.begin());
+			if (mid == begin || mid == end) mid = begin + count / 2;
+		}
+		TBox l = tbox_empty(), r = tbox_empty();
+		for (uint32_t i = begin; i < mid; i++) tbox_grow(l, box[ids[i]]);
+		for (uint32_t i = mid; i < end; i++) tbox_grow(r, box[ids[i]]);
+		set(region, l, 0, 0); set(region + 1, r, 0, 0);
+		nodes[node].first_id = region; nodes[node].prim_count = 0;
+		return mid;
+	}
+	struct Job { uint32_t node, begin, end, region; };
+	void build(Job root, std::vector<Job>* spill, uint32_t spill_above) {
+		std::vector<Job> todo; todo.push_back(root);
+		while (!todo.empty()) {
+			const Job j = todo.back(); todo.pop_back();
+			const uint32_t count = j.end - j.begin;
+			if (count == 1) { nodes[j.node].first_id = ids[j.begin]; nodes[j.node].prim_count = 1; continue; }
+			if (spill && count <= spill_above && count > 1 && j.node != root.node) { spill->push_back(j); continue; }  // handed to the thread pool
+			const uint32_t mid = split(j.node, j.begin, j.end, j.region);
+			const uint32_t left = mid - j.begin;
+			todo.push_back({j.region, j.begin, mid, j.region + 2u});
+			todo.push_back({j.region + 1u, mid, j.end, j.region + 2u + (2u * left - 2u)});
+		}
+	}
+};
+}  // namespace
+
 void build_traversal_tree(const b2r_sphere* prims, uint32_t n, std::vector<b2r_bvh_node>& nodes) {
 	nodes.clear();
 	if (n == 0) { nodes.push_back(to_node(void_box(), 0, 0)); return; }
-	constexpr int kBins = 16;
 	std::vector<TBox> box(n); std::vector<float> cen(3 * static_cast<size_t>(n)); std::vector<uint32_t> ids(n);
 	for (uint32_t i = 0; i < n; i++) {
 		const float r = sqrtf(prims[i].radius_sq);
 		for (int k = 0; k < 3; k++) { box[i].lo[k] = prims[i].position[k] - r; box[i].hi[k] = prims[i].position[k] + r; cen[3 * static_cast<size_t>(i) + k] = prims[i].position[k]; }
 		ids[i] = i;
 	}
-	auto emit = [&](const TBox& b, uint32_t first, uint32_t count) { b2r_bvh_node nd; for (int k = 0; k < 3; k++) { nd.min_bound[k] = b.lo[k]; nd.max_bound[k] = b.hi[k]; } nd.first_id = first; nd.prim_count = count; nodes.push_back(nd); return static_cast<uint32_t>(nodes.size() - 1); };
+	nodes.resize(2 * static_cast<size_t>(n) - 1);
+	TraversalBuilder tb{box, cen, ids, nodes};
 	TBox root = tbox_empty(); for (uint32_t i = 0; i < n; i++) tbox_grow(root, box[i]);
-	emit(root, 0, 0);
-	struct Job { uint32_t node, begin, end; };
-	std::vector<Job> todo; todo.push_back({0u, 0u, n});
-	nodes.reserve(2 * static_cast<size_t>(n));
-	while (!todo.empty()) {
-		const Job j = todo.back(); todo.pop_back();
-		const uint32_t count = j.end - j.begin;
-		if (count == 1) { nodes[j.node].first_id = ids[j.begin]; nodes[j.node].prim_count = 1; continue; }
-		// centroid bounds
-		float clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-		for (uint32_t i = j.begin; i < j.end; i++) for (int k = 0; k < 3; k++) { const float c = cen[3 * static_cast<size_t>(ids[i]) + k]; clo[k] = fminf(clo[k], c); chi[k] = fmaxf(chi[k], c); }
-		int best_axis = -1, best_bin = 0; float best_cost = FLT_MAX;
-		for (int axis = 0; axis < 3; axis++) {
-			const float ext = chi[axis] - clo[axis];
-			if (!(ext > 0.0f)) continue;
-			TBox bb[kBins]; uint32_t bc[kBins];
-			for (int b = 0; b < kBins; b++) { bb[b] = tbox_empty(); bc[b] = 0; }
-			const float scale = kBins / ext;
-			for (uint32_t i = j.begin; i < j.end; i++) {
-				int b = static_cast<int>((cen[3 * static_cast<size_t>(ids[i]) + axis] - clo[axis]) * scale); if (b >= kBins) b = kBins - 1;
-				tbox_grow(bb[b], box[ids[i]]); bc[b]++;
-			}
-			float right_area[kBins]; uint32_t right_cnt[kBins];
-			TBox acc = tbox_empty(); uint32_t cnt = 0;
-			for (int b = kBins - 1; b > 0; b--) { tbox_grow(acc, bb[b]); cnt += bc[b]; right_area[b] = cnt ? tbox_area(acc) : 0.0f; right_cnt[b] = cnt; }
-			acc = tbox_empty(); cnt = 0;
-			for (int b = 0; b + 1 < kBins; b++) {
-				tbox_grow(acc, bb[b]); cnt += bc[b];
-				if (cnt == 0 || right_cnt[b + 1] == 0) continue;
-				const float cost = tbox_area(acc) * cnt + right_area[b + 1] * right_cnt[b + 1];
-				if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
-			}
-		}
-		uint32_t mid;
-		if (best_axis < 0) mid = j.begin + count / 2;  // all centroids coincide: split the list in half
-		else {
-			const float scale = kBins / (chi[best_axis] - clo[best_axis]);
-			auto it = std::partition(ids.begin() + j.begin, ids.begin() + j.end, [&](uint32_t id) {
-				int b = static_cast<int>((cen[3 * static_cast<size_t>(id) + best_axis] - clo[best_axis]) * scale); if (b >= kBins) b = kBins - 1;
-				return b <= best_bin; });
-			mid = static_cast<uint32_t>(it - ids.begin());
-			if (mid == j.begin || mid == j.end) mid = j.begin + count / 2;
-		}
-		TBox l = tbox_empty(), r = tbox_empty();
-		for (uint32_t i = j.begin; i < mid; i++) tbox_grow(l, box[ids[i]]);
-		for (uint32_t i = mid; i < j.end; i++) tbox_grow(r, box[ids[i]]);
-		const uint32_t pair = emit(l, 0, 0); emit(r, 0, 0);
-		nodes[j.node].first_id = pair; nodes[j.node].prim_count = 0;
-		todo.push_back({pair, j.begin, mid}); todo.push_back({pair + 1, mid, j.end});
-	}
+	tb.set(0, root, 0, 0);
+	const unsigned hw = std::thread::hardware_concurrency();
+	const unsigned threads = n < 20000u ? 1u : (hw ? (hw > 32u ? 32u : hw) : 1u);
+	if (threads <= 1) { tb.build({0u, 0u, n, 1u}, nullptr, 0); return; }
+	// the top of the tree on this thread until the pieces are small enough to share out, then one piece at a time per worker
+	std::vector<TraversalBuilder::Job> pieces;
+	tb.build({0u, 0u, n, 1u}, &pieces, n / (threads * 4u) + 1u);
+	std::sort(pieces.begin(), pieces.end(), [](const TraversalBuilder::Job& a, const TraversalBuilder::Job& b) { return a.end - a.begin > b.end - b.begin; });
+	std::atomic<size_t> next{0};
+	auto work = [&] { for (;;) { const size_t k = next.fetch_add(1); if (k >= pieces.size()) break; tb.build(pieces[k], nullptr, 0); } };
+	std::vector<std::thread> pool;
+	for (unsigned t = 1; t < threads; t++) pool.emplace_back(work);
+	work();
+	for (auto& t : pool) t.join();
 }
 }  // namespace b2r
 
