@@ -430,6 +430,44 @@ def main():
                       "note": "B2R_FLAG_REFERENCE_EXACT: the reference's per-tile stream order and scalar-tail sphere formula; results bit-identical to the reference's own Renderer::Accumulate/Render (tests/test_gpu_parity.py)"}
         rx.close()
 
+    # ---- scene edit (the reference rebuilds its BVH on every geometry drag, Application.cpp:508-510): every sphere of the
+    # BVH workload moves by up to a quarter of its radius; b2r_refit_scene (GPU refit of the traversal tree, topology kept) beside the
+    # full rebuild (host reference-BVH build + b2r_upload_scene: traversal-tree build, flatten, H2D). Outside the timed region; N=1 only.
+    edit_line = None
+    if rank == 0 and world == 1 and wl["scene"] != "default" and not args.no_profile_pass:
+        rs = np.random.RandomState(5)
+        geo2 = ps.geometry.copy(); rad = np.sqrt(geo2["radius_sq"])
+        geo2["position"] += (rs.uniform(-1, 1, (len(geo2), 3)) * (0.25 * rad)[:, None]).astype(np.float32)
+
+        def steps_ms(n=3):
+            step(); torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(n):
+                step()
+            b.record(stream); torch.cuda.synchronize(dev)
+            return a.elapsed_time(b) / n
+        r.sync(); t0 = time.perf_counter()
+        r.RefitScene(geo2, want_quality=False, keep_order=True); r.sync()
+        refit_ms = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+        r.RefitScene(geo2, want_quality=False); r.sync()   # as the app does it: reference BVH rebuilt on the host (new leaf order), leaves re-linked
+        refit_reordered_ms = (time.perf_counter() - t0) * 1e3
+        q = r.RefitScene(geo2, keep_order=True)
+        ms_refit = steps_ms()
+        t0 = time.perf_counter()
+        scene2 = dict(scene); scene2["geometry"] = geo2
+        ps2 = b2r.PreparedScene(scene2, wl["w"], wl["h"])
+        t1 = time.perf_counter()
+        r.SetScene(ps2); r.sync()
+        t2 = time.perf_counter()
+        ms_rebuilt = steps_ms()
+        edit_line = {"moved": "every sphere by up to 0.25 radius", "refit_ms": refit_ms, "refit_with_host_reference_bvh_rebuild_ms": refit_reordered_ms, "quality_ratio": q,
+                     "rebuild_ms": {"reference_bvh_host": (t1 - t0) * 1e3, "upload_scene": (t2 - t1) * 1e3},
+                     "ms_per_step_after_refit": ms_refit, "ms_per_step_after_rebuild": ms_rebuilt,
+                     "note": "refit = match prims to geometry + pack + H2D of the spheres and lights + k_refit_level per tree level, host wall clock incl. stream sync; leaf order kept (refit_ms) or the reference BVH rebuilt on the host first, as Application.cpp:508 does"}
+        r.SetScene(ps)
+
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample of the same workload, on the box's host
     # cores. Run as a fresh `bench.py --impl reference` process so that its threads see the same conditions as the reference arm
     # the driver launches (inside this process, after CUDA/torch start-up, the same code ran at about half the speed).
@@ -458,6 +496,8 @@ def main():
         }
         if exact_line:
             line["reference_exact_mode"] = exact_line
+        if edit_line:
+            line["scene_edit"] = edit_line
         print(json.dumps(line))
     r.close()
     if world > 1:

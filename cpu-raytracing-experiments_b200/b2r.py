@@ -32,7 +32,7 @@ COUNTER_NAMES = ["extension_rays", "shadow_rays", "shaded_hits", "terminated", "
 # every symbol include/b2r.h declares (tests/test_abi.py checks the header against this list and the library against both)
 ABI_SYMBOLS = [
     "b2r_bvh_build", "b2r_find_lights", "b2r_camera_lookat", "b2r_create", "b2r_destroy", "b2r_resize", "b2r_reset", "b2r_set_stream",
-    "b2r_sync", "b2r_upload_scene", "b2r_set_camera", "b2r_accumulate", "b2r_resolve", "b2r_resolve_async", "b2r_frame_wait", "b2r_resolve_from", "b2r_ipc_export_buckets", "b2r_ipc_open_peers", "b2r_ipc_close", "b2r_resolve_peers", "b2r_get_accumulations", "b2r_set_accumulations",
+    "b2r_sync", "b2r_upload_scene", "b2r_refit_scene", "b2r_set_camera", "b2r_accumulate", "b2r_resolve", "b2r_resolve_async", "b2r_frame_wait", "b2r_resolve_from", "b2r_ipc_export_buckets", "b2r_ipc_open_peers", "b2r_ipc_close", "b2r_resolve_peers", "b2r_get_accumulations", "b2r_set_accumulations",
     "b2r_read_buckets", "b2r_write_buckets", "b2r_device_buckets", "b2r_device_framebuffer", "b2r_read_counters", "b2r_reset_counters",
     "b2r_read_kernel_times", "b2r_set_flags", "b2r_generate_rays", "b2r_trace_closest", "b2r_trace_shadow", "b2r_read_wide_nodes",
     "b2r_write_hdr", "b2r_last_error", "b2r_abi_version",
@@ -66,6 +66,7 @@ def lib():
             "b2r_camera_lookat": [vp, vp, u32, u32, f32, f32, vp], "b2r_create": [vp, vp], "b2r_resize": [vp, u32, u32], "b2r_reset": [vp],
             "b2r_set_stream": [vp, vp], "b2r_sync": [vp],
             "b2r_upload_scene": [vp, vp, vp, u32, u32, vp, u32, vp, u32, vp, u32, vp, vp, i32, i32],
+            "b2r_refit_scene": [vp, vp, u32, vp, u32, vp, u32, vp, u32, vp],
             "b2r_set_camera": [vp, vp, vp, f32, f32, f32, f32], "b2r_accumulate": [vp, u32], "b2r_resolve": [vp, vp, C.c_int], "b2r_resolve_async": [vp, vp, C.c_int], "b2r_frame_wait": [vp], "b2r_resolve_from": [vp, vp, vp, C.c_int], "b2r_ipc_export_buckets": [vp, vp], "b2r_ipc_open_peers": [vp, vp, u32, u32], "b2r_ipc_close": [vp], "b2r_resolve_peers": [vp, vp, C.c_int],
             "b2r_get_accumulations": [vp, vp], "b2r_set_accumulations": [vp, u32], "b2r_read_buckets": [vp, vp], "b2r_write_buckets": [vp, vp],
             "b2r_device_buckets": [vp, vp, vp], "b2r_device_framebuffer": [vp, vp, vp], "b2r_read_counters": [vp, vp], "b2r_reset_counters": [vp],
@@ -172,6 +173,31 @@ class Renderer:
                                       _ptr(ps.lights), len(ps.lights), _ptr(ps.geometry), len(ps.geometry), _ptr(ps.ambient),
                                       _ptr(hd), 0 if hd is None else hd.shape[1], 0 if hd is None else hd.shape[0]))
         self.SetCamera(ps.camera)
+
+    def RefitScene(self, geometry, material=None, want_quality=True, keep_order=False):
+        """Scene edit without rebuilding the traversal tree (cf. Application.cpp:508-510): `geometry` holds the moved spheres in ORIGINAL
+        order, same count as the scene set before. As the reference does after an edit, the reference BVH is rebuilt on the host
+        (BoundingVolumeHierarchy ctor: new leaf order, Q6/Q9 depend on it) and the light list re-derived; the GPU keeps the traversal
+        tree's topology, re-links its leaves to the new order and recomputes its boxes (b2r_refit_scene). keep_order=True skips the
+        host rebuild and keeps the previous leaf order. Returns the tree-quality ratio (1.0 = as built) or None. The caller resets the
+        accumulator."""
+        import copy
+        geo = np.ascontiguousarray(geometry, dtype=_scenes.SPHERE_DTYPE)
+        if self.scene is None or len(geo) != len(self.scene.geometry):
+            raise B2RError(ERR_ARG, "RefitScene keeps the sphere count of the scene set before")
+        ps = self.scene = copy.copy(self.scene)  # the caller's PreparedScene stays as it was
+        if material is not None:
+            ps.material = np.ascontiguousarray(material, dtype=_scenes.MATERIAL_DTYPE)
+        ps.geometry = geo
+        if keep_order:
+            ps.prims = np.ascontiguousarray(geo[ps.prim_ids])
+        else:
+            ps.nodes, ps.prims, ps.prim_ids = build_bvh(geo)
+        ps.lights = find_lights(ps.geometry, ps.material)
+        q = C.c_float(0.0)
+        _check(lib().b2r_refit_scene(self._h, _ptr(ps.prims), len(ps.prims), _ptr(ps.material), len(ps.material), _ptr(ps.lights), len(ps.lights),
+                                     _ptr(ps.geometry), len(ps.geometry), C.addressof(q) if want_quality else None))
+        return q.value if want_quality else None
 
     def SetCamera(self, cam11):
         cam = np.ascontiguousarray(cam11, np.float32)

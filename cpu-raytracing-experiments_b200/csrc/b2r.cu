@@ -59,6 +59,9 @@ struct b2r_ctx {
 	WideNode* d_wide = nullptr;
 	size_t cap_prims = 0, cap_prim_mat = 0, cap_mat_albedo = 0, cap_mat_emission = 0, cap_light_sphere = 0, cap_light_emit = 0, cap_wide = 0, cap_hdri = 0;
 	WideBvh wide_host; uint64_t wide_key = 0; bool have_wide = false;
+	std::vector<uint32_t> cur_geom_of_prim;  // after a refit into a new BVH order: that order's index -> geometry index (empty: wide_host's)
+	uint32_t* d_remap = nullptr; size_t cap_remap = 0;
+	bool wide_refit = false; double* d_cost = nullptr;  // b2r_refit_scene: the device tree no longer equals wide_host
 	// frame
 	float4 *d_A[2] = {nullptr, nullptr}, *d_B[2] = {nullptr, nullptr}, *d_SA = nullptr, *d_SB = nullptr, *d_fb = nullptr;
 	float *d_T[2] = {nullptr, nullptr}, *d_SL = nullptr, *d_rad = nullptr, *d_acc = nullptr;
@@ -298,7 +301,7 @@ void b2r_destroy(b2r_ctx* c) {
 	drop_graph(c);
 	for (auto& t : c->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
 	dev_free(&c->d_prims); dev_free(&c->d_mat_albedo); dev_free(&c->d_mat_emission); dev_free(&c->d_light_sphere); dev_free(&c->d_light_emit);
-	dev_free(&c->d_hdri); dev_free(&c->d_prim_mat); dev_free(&c->d_wide);
+	dev_free(&c->d_hdri); dev_free(&c->d_prim_mat); dev_free(&c->d_wide); dev_free(&c->d_cost); dev_free(&c->d_remap);
 	for (int s = 0; s < 2; s++) { dev_free(&c->d_A[s]); dev_free(&c->d_B[s]); dev_free(&c->d_T[s]); }
 	dev_free(&c->d_H); dev_free(&c->d_SA); dev_free(&c->d_SB); dev_free(&c->d_SL); dev_free(&c->d_rad); dev_free(&c->d_acc); dev_free(&c->d_fb);
 	for (int s = 0; s < 2; s++) { dev_free(&c->d_ex_slot[s]); dev_free(&c->d_ex_act[s]); }
@@ -363,6 +366,33 @@ int b2r_set_flags(b2r_ctx* c, uint32_t flags) {
 	return B2R_OK;
 }
 
+} // extern "C"
+namespace {
+// Host arrays -> device through ONE page-locked block, without stream synchronisation: the copies are ordered after the kernels
+// already enqueued (which may still read the old scene) and before the ones enqueued next; the block is only rewritten once the
+// previous upload's copies have completed (an event early in the previous frame, not its end).
+struct UploadPart { void* dst; const void* src; size_t bytes; };
+int stage_upload(b2r_ctx* c, const UploadPart* parts, size_t n_parts) {
+	size_t total = 0; for (size_t i = 0; i < n_parts; i++) total += (parts[i].bytes + 255) & ~static_cast<size_t>(255);
+	if (c->stage_busy) { CU(cudaEventSynchronize(c->ev_stage)); c->stage_busy = false; }
+	if (total > c->stage_bytes) {
+		if (c->h_stage) CU(cudaFreeHost(c->h_stage));
+		c->h_stage = nullptr; c->stage_bytes = 0;
+		CU(cudaMallocHost(reinterpret_cast<void**>(&c->h_stage), total)); c->stage_bytes = total;
+	}
+	if (!c->ev_stage) CU(cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming));
+	size_t off = 0;
+	for (size_t i = 0; i < n_parts; i++) {
+		const UploadPart& q = parts[i];
+		if (q.bytes) { std::memcpy(c->h_stage + off, q.src, q.bytes); CU(cudaMemcpyAsync(q.dst, c->h_stage + off, q.bytes, cudaMemcpyHostToDevice, c->stream)); }
+		off += (q.bytes + 255) & ~static_cast<size_t>(255);
+	}
+	CU(cudaEventRecord(c->ev_stage, c->stream)); c->stage_busy = true;
+	return B2R_OK;
+}
+}  // namespace
+extern "C" {
+
 int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* nodes, uint32_t n_prims, uint32_t n_nodes,
                      const b2r_material* materials, uint32_t n_mat, const int32_t* light_geom_idx, uint32_t n_lights,
                      const b2r_sphere* geometry, uint32_t n_geom, const float ambient[3], const float* hdri_rgba, int32_t hdri_w, int32_t hdri_h) {
@@ -388,6 +418,7 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 			if (c->cfg.flags & B2R_FLAG_REFERENCE_TREE) flatten_bvh(nodes, n_nodes, prims, n_prims, c->wide_host);
 			else { std::vector<b2r_bvh_node> tree; build_traversal_tree(prims, n_prims, tree); flatten_bvh(tree.data(), static_cast<uint32_t>(tree.size()), prims, n_prims, c->wide_host); }
 			c->wide_key = key; c->have_wide = true;
+			match_prims_to_geometry(prims, geometry, n_prims, c->wide_host.geom_of_prim);  // which sphere each leaf stands for (b2r_refit_scene); left empty if prims is no permutation of geometry
 		}
 	}
 	if (c->wide_host.max_stack + 3u > static_cast<uint32_t>(kTraversalStack)) { c->have_wide = false; return fail(B2R_ERR_BVH, "tree needs a deeper traversal stack than kTraversalStack (3 slots of headroom for the branch-free pushes)"); }
@@ -408,28 +439,14 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 	if ((rc = dev_reserve(&c->d_wide, &c->cap_wide, c->wide_host.nodes.size()))) return rc;
 	const size_t texels = has_ambient ? static_cast<size_t>(hdri_w) * hdri_h : 0;
 	if (has_ambient && (rc = dev_reserve(&c->d_hdri, &c->cap_hdri, texels))) return rc;
-	// stage everything in one page-locked block
-	struct Part { void* dst; const void* src; size_t bytes; };
-	const Part parts[] = {
+	const UploadPart parts[] = {
 		{c->d_prims, h_prims.data(), h_prims.size() * sizeof(float4)}, {c->d_prim_mat, h_pm.data(), h_pm.size() * sizeof(int32_t)},
 		{c->d_mat_albedo, h_alb.data(), h_alb.size() * sizeof(float4)}, {c->d_mat_emission, h_em.data(), h_em.size() * sizeof(float4)},
 		{c->d_light_sphere, h_ls.data(), h_ls.size() * sizeof(float4)}, {c->d_light_emit, h_le.data(), h_le.size() * sizeof(float4)},
 		{c->d_wide, c->wide_host.nodes.data(), c->wide_host.nodes.size() * sizeof(WideNode)}, {c->d_hdri, hdri_rgba, texels * sizeof(float4)},
 	};
-	size_t total = 0; for (const Part& q : parts) total += (q.bytes + 255) & ~static_cast<size_t>(255);
-	if (c->stage_busy) { CU(cudaEventSynchronize(c->ev_stage)); c->stage_busy = false; }
-	if (total > c->stage_bytes) {
-		if (c->h_stage) CU(cudaFreeHost(c->h_stage));
-		c->h_stage = nullptr; c->stage_bytes = 0;
-		CU(cudaMallocHost(reinterpret_cast<void**>(&c->h_stage), total)); c->stage_bytes = total;
-	}
-	if (!c->ev_stage) CU(cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming));
-	size_t off = 0;
-	for (const Part& q : parts) {
-		if (q.bytes) { std::memcpy(c->h_stage + off, q.src, q.bytes); CU(cudaMemcpyAsync(q.dst, c->h_stage + off, q.bytes, cudaMemcpyHostToDevice, c->stream)); }
-		off += (q.bytes + 255) & ~static_cast<size_t>(255);
-	}
-	CU(cudaEventRecord(c->ev_stage, c->stream)); c->stage_busy = true;
+	if ((rc = stage_upload(c, parts, sizeof parts / sizeof parts[0]))) return rc;
+	c->wide_refit = false; c->cur_geom_of_prim.clear();
 	const SceneDev before = c->params.scene; const bool bvh_before = c->use_bvh;
 	SceneDev& s = c->params.scene;
 	s.prims = c->d_prims; s.prim_mat = c->d_prim_mat; s.mat_albedo = c->d_mat_albedo; s.mat_emission = c->d_mat_emission;
@@ -442,6 +459,72 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 	// the scene's pointers and scalars travel in the kernels' parameter block: the captured graph stays valid unless they changed
 	if (!c->have_scene || bvh_before != c->use_bvh || std::memcmp(&before, &s, sizeof s) != 0) drop_graph(c);
 	c->have_scene = true;
+	return B2R_OK;
+}
+
+int b2r_refit_scene(b2r_ctx* c, const b2r_sphere* prims, uint32_t n_prims, const b2r_material* materials, uint32_t n_mat,
+                    const int32_t* light_geom_idx, uint32_t n_lights, const b2r_sphere* geometry, uint32_t n_geom, float* quality_out) {
+	if (!c || !prims || !materials || !geometry || n_prims == 0 || n_mat == 0) return fail(B2R_ERR_ARG, "null or empty scene array");
+	if (!c->have_scene || !c->have_wide) return fail(B2R_ERR_STATE, "b2r_refit_scene needs the topology of an earlier b2r_upload_scene");
+	if (n_prims != c->params.scene.n_prims || n_geom != n_prims) return fail(B2R_ERR_ARG, "a refit keeps the sphere count (and BVH order) of the last b2r_upload_scene");
+	if (n_lights && !light_geom_idx) return fail(B2R_ERR_ARG, "null light list");
+	for (uint32_t i = 0; i < n_prims; i++) if (prims[i].material_ID < 0 || static_cast<uint32_t>(prims[i].material_ID) >= n_mat) return fail(B2R_ERR_ARG, "material_ID out of range");
+	for (uint32_t i = 0; i < n_lights; i++) if (light_geom_idx[i] < 0 || static_cast<uint32_t>(light_geom_idx[i]) >= n_geom) return fail(B2R_ERR_ARG, "light index out of range");
+	int rc = ensure_device(c); if (rc) return rc;
+	// The caller may have re-sorted its prims (the reference's constructor does on every rebuild, BVH.hpp:201-205): leaf links become
+	// indices into the NEW order. old index -> geometry index (known from the last upload / refit) -> new index (matched by value).
+	const std::vector<uint32_t>& old_geom = c->cur_geom_of_prim.empty() ? c->wide_host.geom_of_prim : c->cur_geom_of_prim;
+	if (old_geom.size() != n_prims) return fail(B2R_ERR_STATE, "the uploaded prims were not a permutation of geometry: no refit for this scene");
+	std::vector<uint32_t> new_geom, remap;
+	if (!match_prims_to_geometry(prims, geometry, n_prims, new_geom)) return fail(B2R_ERR_ARG, "prims_bvh_order is not a permutation of geometry");
+	bool same_order = new_geom == old_geom;
+	if (!same_order) {
+		std::vector<uint32_t> prim_of_geom(n_prims);
+		for (uint32_t i = 0; i < n_prims; i++) prim_of_geom[new_geom[i]] = i;
+		remap.resize(n_prims);
+		for (uint32_t i = 0; i < n_prims; i++) remap[i] = prim_of_geom[old_geom[i]];
+	}
+	PackedScene ps; pack_scene(prims, n_prims, materials, n_mat, light_geom_idx, n_lights, geometry, ps);
+	if ((rc = dev_reserve(&c->d_remap, &c->cap_remap, remap.size()))) return rc;
+	const bool grow = ps.mat_albedo.size() > c->cap_mat_albedo || ps.mat_emission.size() > c->cap_mat_emission ||
+	                  ps.light_sphere.size() > c->cap_light_sphere || ps.light_emit.size() > c->cap_light_emit;
+	if (grow) CU(cudaStreamSynchronize(c->stream));  // more materials or lights than before: those (small) arrays are replaced
+	if ((rc = dev_reserve(&c->d_mat_albedo, &c->cap_mat_albedo, ps.mat_albedo.size()))) return rc;
+	if ((rc = dev_reserve(&c->d_mat_emission, &c->cap_mat_emission, ps.mat_emission.size()))) return rc;
+	if ((rc = dev_reserve(&c->d_light_sphere, &c->cap_light_sphere, ps.light_sphere.size()))) return rc;
+	if ((rc = dev_reserve(&c->d_light_emit, &c->cap_light_emit, ps.light_emit.size()))) return rc;
+	if (!c->d_cost) { size_t cap = 0; if ((rc = dev_reserve(&c->d_cost, &cap, 1))) return rc; }
+	const UploadPart parts[] = {
+		{c->d_prims, ps.prims.data(), ps.prims.size() * sizeof(float4)}, {c->d_prim_mat, ps.prim_mat.data(), ps.prim_mat.size() * sizeof(int32_t)},
+		{c->d_mat_albedo, ps.mat_albedo.data(), ps.mat_albedo.size() * sizeof(float4)}, {c->d_mat_emission, ps.mat_emission.data(), ps.mat_emission.size() * sizeof(float4)},
+		{c->d_light_sphere, ps.light_sphere.data(), ps.light_sphere.size() * sizeof(float4)}, {c->d_light_emit, ps.light_emit.data(), ps.light_emit.size() * sizeof(float4)},
+		{c->d_remap, remap.data(), remap.size() * sizeof(uint32_t)},
+	};
+	if ((rc = stage_upload(c, parts, sizeof parts / sizeof parts[0]))) return rc;
+	if (!same_order) c->cur_geom_of_prim.swap(new_geom);
+	// boxes bottom-up on the device: one launch per BFS level, deepest first (stream order is the dependency)
+	const std::vector<uint32_t>& lf = c->wide_host.level_first;
+	for (size_t l = lf.size() - 1; l-- > 0;) {
+		const uint32_t first = lf[l], count = lf[l + 1] - lf[l];
+		k_refit_level<<<(count * 4u + kBlock - 1u) / kBlock, kBlock, 0, c->stream>>>(reinterpret_cast<float4*>(c->d_wide), c->d_prims, same_order ? nullptr : c->d_remap, first, count);
+		c->launches++;
+	}
+	CU(cudaGetLastError());
+	c->wide_refit = true;
+	const SceneDev before = c->params.scene;
+	SceneDev& s = c->params.scene;
+	s.mat_albedo = c->d_mat_albedo; s.mat_emission = c->d_mat_emission; s.light_sphere = c->d_light_sphere; s.light_emit = c->d_light_emit;
+	s.n_mat = n_mat; s.n_lights = n_lights; s.light_sel_pdf = 1.0f / static_cast<float>(n_lights);  // Renderer.hpp:78
+	if (std::memcmp(&before, &s, sizeof s) != 0) drop_graph(c);
+	if (quality_out) {  // optional: costs one launch and a stream synchronisation
+		CU(cudaMemsetAsync(c->d_cost, 0, sizeof(double), c->stream));
+		k_tree_cost<<<c->sm_count * 4, kBlock, 0, c->stream>>>(reinterpret_cast<const float4*>(c->d_wide), static_cast<uint32_t>(c->wide_host.nodes.size()), c->d_cost);
+		c->launches++;
+		double cost = 0.0;
+		CU(cudaMemcpyAsync(&cost, c->d_cost, sizeof cost, cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaStreamSynchronize(c->stream));
+		*quality_out = c->wide_host.cost > 0.0 ? static_cast<float>(cost / c->wide_host.cost) : 1.0f;
+	}
 	return B2R_OK;
 }
 
@@ -659,7 +742,11 @@ int b2r_read_wide_nodes(b2r_ctx* c, void* out_host, uint32_t* n_wide_nodes, uint
 	if (!c->have_scene) return fail(B2R_ERR_STATE, "upload_scene first");
 	if (n_wide_nodes) *n_wide_nodes = static_cast<uint32_t>(c->wide_host.nodes.size());
 	if (max_stack) *max_stack = c->wide_host.max_stack;
-	if (out_host) std::memcpy(out_host, c->wide_host.nodes.data(), c->wide_host.nodes.size() * sizeof(WideNode));
+	if (out_host && c->wide_refit) {  // after b2r_refit_scene the device holds the current boxes
+		int rc = ensure_device(c); if (rc) return rc;
+		CU(cudaMemcpyAsync(out_host, c->d_wide, c->wide_host.nodes.size() * sizeof(WideNode), cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaStreamSynchronize(c->stream));
+	} else if (out_host) std::memcpy(out_host, c->wide_host.nodes.data(), c->wide_host.nodes.size() * sizeof(WideNode));
 	return B2R_OK;
 }
 

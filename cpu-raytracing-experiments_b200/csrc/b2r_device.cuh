@@ -758,6 +758,25 @@ __global__ void __launch_bounds__(kBlock) k_resolve(const FrameDev frame, const 
 	}
 }
 
+// ---------------------------------------------------------------------------------------------- scene edit: refit
+// Application.cpp:508-509 rebuilds the BVH on every geometry drag. Here the traversal tree keeps its topology and only its boxes
+// are recomputed, on the GPU, from the moved spheres: one launch per BFS level, deepest first (children always sit on a deeper
+// level), four threads per 128-byte node = one per slot (refit_slot, b2r_shade.h; shared with the host twin the tests compare with).
+__global__ void __launch_bounds__(kBlock) k_refit_level(float4* __restrict__ wide, const float4* __restrict__ prims, const uint32_t* __restrict__ remap, const uint32_t first, const uint32_t count) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count * 4u) refit_slot(wide, prims, remap, first + (i >> 2), static_cast<int>(i & 3u));
+}
+// Sum of the inner-slot half areas (the quantity a refit is judged by: cost now / cost when the tree was built).
+__global__ void __launch_bounds__(kBlock) k_tree_cost(const float4* __restrict__ wide, const uint32_t n_nodes, double* __restrict__ out) {
+	double sum = 0.0;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes * 4u; i += gridDim.x * blockDim.x) {
+		const float4 a = wide[static_cast<size_t>(i) * 2u], b = wide[static_cast<size_t>(i) * 2u + 1u];
+		if (static_cast<int32_t>(bits(b.z)) >= 0) sum += static_cast<double>(slot_half_area(a, b));
+	}
+	for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+	if ((threadIdx.x & 31u) == 0u && sum != 0.0) atomicAdd(out, sum);
+}
+
 // ---------------------------------------------------------------------------------------------- taps
 __global__ void k_tap_generate(const Params p, const uint32_t acc, float* __restrict__ out) {
 	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < p.frame.npix; t += gridDim.x * blockDim.x) {

@@ -2,12 +2,13 @@
 // leaf order (BVH.hpp:90-206), the 4-wide flattening for the GPU, the light list (Scene.hpp:12-16) and the camera
 // set-up (Camera.hpp:21-32,47-50). The reference builds its BVH on one host thread as well; only the flattening is new.
 #include "b2r_host.h"
-#include "b2r_math.h"
+#include "b2r_shade.h"
 
 #include <algorithm>
 #include <atomic>
 #include <thread>
 #include <cmath>
+#include <cstddef>
 #include <cstring>
 #include <numeric>
 #include <cstdio>
@@ -157,9 +158,6 @@ bool validate_reference_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, uint32_
 }
 
 namespace {
-constexpr float kBoxPad = 4.0e-7f;  // outward padding, relative to |coordinate| + 1
-inline float pad_down(float v) { return v - (fabsf(v) + 1.0f) * kBoxPad; }
-inline float pad_up(float v) { return v + (fabsf(v) + 1.0f) * kBoxPad; }
 inline float surface(const b2r_bvh_node& n) {  // true half surface area: only used to pick which child to open
 	const float ex = n.max_bound[0] - n.min_bound[0], ey = n.max_bound[1] - n.min_bound[1], ez = n.max_bound[2] - n.min_bound[2];
 	return ex * ey + ey * ez + ez * ex;
@@ -167,8 +165,54 @@ inline float surface(const b2r_bvh_node& n) {  // true half surface area: only u
 inline float int_as_float(int32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
 }  // namespace
 
+namespace {
+double wide_cost(const WideBvh& t) {
+	double sum = 0.0;
+	for (const WideNode& w : t.nodes) for (int k = 0; k < 4; k++) {
+		int32_t link; std::memcpy(&link, &w.slot[k][6], 4);
+		if (link >= 0) { const float4* s = reinterpret_cast<const float4*>(w.slot[k]); sum += static_cast<double>(slot_half_area(s[0], s[1])); }
+	}
+	return sum;
+}
+}  // namespace
+
+void refit_wide(WideBvh& tree, const float4* prims, const uint32_t* remap) {
+	float4* wide = reinterpret_cast<float4*>(tree.nodes.data());
+	for (size_t l = tree.level_first.size() - 1; l-- > 0;)
+		for (uint32_t i = tree.level_first[l]; i < tree.level_first[l + 1]; i++) for (int k = 0; k < 4; k++) refit_slot(wide, prims, remap, i, k);
+	tree.cost = wide_cost(tree);
+}
+
+bool match_prims_to_geometry(const b2r_sphere* prims, const b2r_sphere* geometry, uint32_t n, std::vector<uint32_t>& geom_of_prim) {
+	// open-addressing table over the 20 bytes that make a sphere (bit patterns, so -0 / NaN need no special case); equal spheres are
+	// handed out first-come in probe order, which is deterministic
+	static_assert(offsetof(b2r_sphere, material_ID) == 16, "position, radius_sq, material_ID are the first 20 bytes");
+	auto hash = [](const b2r_sphere& s) {
+		uint32_t w[5]; std::memcpy(w, &s, 20);
+		uint64_t h = 0x9e3779b97f4a7c15ull;
+		for (uint32_t v : w) { h ^= v; h *= 0xff51afd7ed558ccdull; h ^= h >> 29; }
+		return h;
+	};
+	uint64_t size = 16; while (size < 2ull * n) size <<= 1;
+	const uint64_t mask = size - 1;
+	constexpr uint32_t kFree = 0xffffffffu;
+	std::vector<uint32_t> table(size, kFree);
+	for (uint32_t g = 0; g < n; g++) { uint64_t at = hash(geometry[g]) & mask; while (table[at] != kFree) at = (at + 1) & mask; table[at] = g; }
+	std::vector<uint8_t> taken(n, 0);
+	geom_of_prim.assign(n, 0u);
+	for (uint32_t i = 0; i < n; i++) {
+		uint64_t at = hash(prims[i]) & mask;
+		for (;; at = (at + 1) & mask) {
+			const uint32_t g = table[at];
+			if (g == kFree) { geom_of_prim.clear(); return false; }
+			if (!taken[g] && std::memcmp(&prims[i], &geometry[g], 20) == 0) { taken[g] = 1; geom_of_prim[i] = g; break; }
+		}
+	}
+	return true;
+}
+
 void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* prims, uint32_t n_prims, WideBvh& out) {
-	out.nodes.clear(); out.max_stack = 0; out.depth = 0; out.tn_bits = 31;
+	out.nodes.clear(); out.max_stack = 0; out.depth = 0; out.tn_bits = 31; out.level_first.assign(1, 0u); out.cost = 0.0;
 	auto set_empty = [](WideNode& w, int k) { for (int j = 0; j < 8; j++) w.slot[k][j] = 0.0f; w.slot[k][6] = int_as_float(kEmptyLink); };
 	auto set_leaf = [&](WideNode& w, int k, uint32_t prim) {
 		const b2r_sphere& s = prims[prim];
@@ -177,12 +221,12 @@ void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* 
 	};
 	if (n_prims == 0 || n_nodes == 0) {
 		WideNode w; for (int k = 0; k < 4; k++) set_empty(w, k);
-		out.nodes.push_back(w); return;
+		out.nodes.push_back(w); out.level_first.push_back(1u); return;
 	}
 	if (nodes[0].prim_count != 0) {  // single sphere: the root is a leaf
 		WideNode w; for (int k = 0; k < 4; k++) set_empty(w, k);
 		set_leaf(w, 0, nodes[0].first_id);
-		out.nodes.push_back(w); return;
+		out.nodes.push_back(w); out.level_first.push_back(1u); return;
 	}
 	// breadth-first: queue entries are binary inner nodes that become wide nodes
 	struct Pending { uint32_t bin; uint32_t level; };
@@ -191,7 +235,7 @@ void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* 
 	out.nodes.reserve(n_nodes / 2 + 1);
 	for (size_t head = 0; head < queue.size(); head++) {
 		const Pending cur = queue[head];
-		out.depth = std::max(out.depth, cur.level);
+		if (cur.level > out.depth) { out.depth = cur.level; if (cur.level > 1) out.level_first.push_back(static_cast<uint32_t>(head)); }  // first node of a new BFS level
 		uint32_t kids[4]; int nk = 2;
 		kids[0] = nodes[cur.bin].first_id; kids[1] = kids[0] + 1;
 		while (nk < 4) {  // open the inner child with the largest surface until four slots are used
@@ -229,6 +273,8 @@ void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* 
 		need[i] = worst;
 	}
 	out.max_stack = need[0];
+	out.level_first.push_back(static_cast<uint32_t>(out.nodes.size()));
+	out.cost = wide_cost(out);
 	uint32_t node_bits = 1; while ((1ull << node_bits) < out.nodes.size()) node_bits++;
 	out.tn_bits = std::min(32u - node_bits, 29u);  // >= 2 low key bits are dropped: the kernels keep the slot index there
 }

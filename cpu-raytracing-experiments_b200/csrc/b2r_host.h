@@ -24,6 +24,9 @@ struct WideBvh {
 	uint32_t max_stack = 0;        // worst-case traversal stack occupancy for this tree
 	uint32_t tn_bits = 10;         // low bits of a 32-bit stack entry that carry the entry distance (rest: node index)
 	uint32_t depth = 0;
+	std::vector<uint32_t> level_first;  // nodes of BFS level l are [level_first[l], level_first[l+1]); children always sit on a deeper level
+	double cost = 0.0;             // sum of the inner-slot half areas (what a refit is compared against)
+	std::vector<uint32_t> geom_of_prim;  // for b2r_refit_scene: geometry index of the sphere each BVH-order leaf index stands for (empty: unknown)
 };
 
 // BoundingVolumeHierarchy<Sphere> constructor (BVH.hpp:90-206), bit-identical node and leaf order.
@@ -35,6 +38,14 @@ bool validate_reference_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, uint32_
 void build_traversal_tree(const b2r_sphere* prims_bvh_order, uint32_t n, std::vector<b2r_bvh_node>& nodes);
 // Collapse the binary tree 2 -> 4 wide and inline the leaf spheres.
 void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* prims, uint32_t n_prims, WideBvh& out);
+// Host twin of the GPU refit (k_refit_level, same shared routine refit_slot): keeps the topology, takes the spheres' new positions and
+// radii from `prims` ({c.xyz, r^2} in the same BVH leaf order) and recomputes every box bottom-up. Updates `cost`. The product refits
+// on the GPU (b2r_refit_scene); this one is what tests/hostcheck compares it with.
+void refit_wide(WideBvh& tree, const float4* prims, const uint32_t* remap);
+// prims (BVH leaf order) as a permutation of geometry (original order), matched by value — the reference's BVH keeps reordered COPIES
+// of the spheres and no index map (BVH.hpp:201-205). geom_of_prim[i] = index into geometry of prims[i]; equal spheres are paired in
+// index order. Returns false when prims is not a permutation of geometry.
+bool match_prims_to_geometry(const b2r_sphere* prims, const b2r_sphere* geometry, uint32_t n, std::vector<uint32_t>& geom_of_prim);
 
 
 // Scene arrays in the packed form the kernels read (SceneDev): spheres {c.xyz, r^2} in BVH leaf order, per-material

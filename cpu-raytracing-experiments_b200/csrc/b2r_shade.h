@@ -391,4 +391,44 @@ B2R_HD bool traverse_any(const WideNode* __restrict__ wide, const Ray& r, float 
 	return t.occluded;
 }
 
+// ------------------------------------------------------------------ refit (scene edit without a rebuild, Application.cpp:508-509)
+// The box of one inner slot, recomputed from the child wide node it links to: the union of the child's inner-slot boxes (already
+// padded) and of the padded bounds c -+ sqrt(r^2) of its leaf spheres, read from `prims` (BVH leaf order). min/max are exact and the
+// padding is monotonic, so on unchanged spheres this returns exactly what flatten_bvh() stored (pad(union) == union(pad)).
+constexpr float kBoxPad = 4.0e-7f;  // outward padding, relative to |coordinate| + 1
+B2R_HD float pad_down(float v) { return v - (fabsf(v) + 1.0f) * kBoxPad; }
+B2R_HD float pad_up(float v) { return v + (fabsf(v) + 1.0f) * kBoxPad; }
+B2R_HD void refit_child_box(const float4* __restrict__ child /*the 8 float4 of the linked wide node*/, const float4* __restrict__ prims, float4* a_out, float4* b_out, int32_t link) {
+	float lx = FLT_MAX, ly = FLT_MAX, lz = FLT_MAX, hx = -FLT_MAX, hy = -FLT_MAX, hz = -FLT_MAX;
+	for (int j = 0; j < 4; j++) {
+		const float4 ca = child[2 * j], cb = child[2 * j + 1];
+		const int32_t cl = static_cast<int32_t>(bits(cb.z));
+		if (cl == kEmptyLink) continue;
+		float x0, y0, z0, x1, y1, z1;
+		if (cl < 0) {
+			const float4 s = prims[~cl]; const float r = sqrtf(s.w);
+			x0 = pad_down(s.x - r); y0 = pad_down(s.y - r); z0 = pad_down(s.z - r); x1 = pad_up(s.x + r); y1 = pad_up(s.y + r); z1 = pad_up(s.z + r);
+		} else { x0 = ca.x; y0 = ca.y; z0 = ca.z; x1 = ca.w; y1 = cb.x; z1 = cb.y; }
+		lx = sel_min(lx, x0); ly = sel_min(ly, y0); lz = sel_min(lz, z0); hx = sel_max(hx, x1); hy = sel_max(hy, y1); hz = sel_max(hz, z1);
+	}
+	*a_out = make_float4(lx, ly, lz, hx); *b_out = make_float4(hy, hz, from_bits(static_cast<uint32_t>(link)), 0.0f);
+}
+// One slot of one wide node: leaf slots take the moved sphere, inner slots the recomputed box. Levels are refit deepest first, so the
+// child node read here already carries its new leaf links. `remap` (may be null = unchanged order) maps the BVH-order index a leaf
+// held so far to the sphere's index in the new `prims` order (the reference re-sorts its prims on every rebuild, BVH.hpp:201-205, and
+// hit indices must be indices into the current order: Q6 ties, Q9).
+B2R_HD void refit_slot(float4* __restrict__ wide /*8 float4 per node*/, const float4* __restrict__ prims, const uint32_t* __restrict__ remap, uint32_t node, int k) {
+	float4* slot = wide + static_cast<size_t>(node) * 8 + 2 * k;
+	const int32_t link = static_cast<int32_t>(bits(slot[1].z));
+	if (link == kEmptyLink) return;
+	if (link < 0) {
+		const uint32_t now = remap ? remap[~link] : static_cast<uint32_t>(~link);
+		slot[0] = prims[now]; slot[1].z = from_bits(~now);
+		return;
+	}
+	float4 a, b; refit_child_box(wide + static_cast<size_t>(link) * 8, prims, &a, &b, link);
+	slot[0] = a; slot[1] = b;
+}
+B2R_HD float slot_half_area(const float4 a, const float4 b) { const float ex = a.w - a.x, ey = b.x - a.y, ez = b.y - a.z; return ex * ey + ey * ez + ez * ex; }
+
 }  // namespace b2r

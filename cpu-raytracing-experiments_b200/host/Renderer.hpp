@@ -92,6 +92,20 @@ struct Renderer {
 		                       static_cast<uint32_t>(scene.lighting_acceleration.prims.size()), reinterpret_cast<const b2r_sphere*>(scene.geometry.data()),
 		                       static_cast<uint32_t>(scene.geometry.size()), amb, scene.sky.hdri_data, scene.sky.hdri_width, scene.sky.hdri_height));
 	}
+	// geometry moved and the app has rebuilt acceleration_structure / lighting_acceleration (Application.cpp:508-509): the GPU keeps its
+	// traversal tree's topology, re-links the leaves to the rebuilt order and refits the boxes (b2r_refit_scene) instead of rebuilding;
+	// full SceneChanged() when the sphere count changed or the kept topology degraded past `rebuild_above`. Returns the quality ratio.
+	float SceneMoved(float rebuild_above = 1.5f) {
+		const auto& as = scene.acceleration_structure;
+		float quality = 1.0f;
+		const int rc = b2r_refit_scene(ctx, reinterpret_cast<const b2r_sphere*>(as.prims.data()), static_cast<uint32_t>(as.prims.size()),
+		                               reinterpret_cast<const b2r_material*>(scene.material.data()), static_cast<uint32_t>(scene.material.size()),
+		                               scene.lighting_acceleration.prims.data(), static_cast<uint32_t>(scene.lighting_acceleration.prims.size()),
+		                               reinterpret_cast<const b2r_sphere*>(scene.geometry.data()), static_cast<uint32_t>(scene.geometry.size()), &quality);
+		if (rc == B2R_ERR_ARG || rc == B2R_ERR_STATE || (rc == B2R_OK && quality > rebuild_above)) { SceneChanged(); return 1.0f; }
+		check(rc);
+		return quality;
+	}
 	void CameraChanged() {
 		const Camera& c = scene.camera;
 		const float pos[3] = {c.view.pos.x, c.view.pos.y, c.view.pos.z}, q[4] = {c.view.orient.w, c.view.orient.x, c.view.orient.y, c.view.orient.z};

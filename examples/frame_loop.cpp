@@ -58,5 +58,14 @@ int main(int argc, char** argv) {
 	double sum = 0; for (auto& p : renderer.framebuffer) sum += p.x + p.y + p.z;
 	std::printf("[%u X %u] : %.3fms : %.1ffps : %.1fMsamples/s  (mean tonemapped value %.5f after %u accumulations)\n", viewport_width, viewport_height, ms, 1000.0 / ms,
 	            viewport_width * viewport_height * 1e-3 / ms, sum / (3.0 * renderer.framebuffer.size()), renderer.accumulations);
+	// a geometry drag as the editor does it (Application.cpp:508-510): rebuild the BVH and the light list, reset — and tell the renderer the
+	// spheres only moved, so that the GPU refits its traversal tree instead of rebuilding it
+	scene.geometry[1].position.x += 0.25f; scene.geometry[1].position.y += 0.125f;
+	scene.acceleration_structure = decltype(scene.acceleration_structure){scene.geometry};
+	scene.lighting_acceleration = decltype(scene.lighting_acceleration){scene.geometry, scene.material};
+	const float quality = renderer.SceneMoved(); renderer.ResetAccumulator();
+	for (uint32_t f = 0; f < 5; f++) { renderer.Accumulate(); renderer.Render(); }
+	sum = 0; for (auto& p : renderer.framebuffer) sum += p.x + p.y + p.z;
+	std::printf("after a geometry drag: tree quality ratio %.4f, mean tonemapped value %.5f after %u accumulations\n", quality, sum / (3.0 * renderer.framebuffer.size()), renderer.accumulations);
 	return 0;
 }

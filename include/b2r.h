@@ -115,6 +115,20 @@ int  b2r_upload_scene(b2r_ctx* ctx, const b2r_sphere* prims_bvh_order, const b2r
                       uint32_t n_nodes, const b2r_material* materials, uint32_t n_mat, const int32_t* light_geom_idx,
                       uint32_t n_lights, const b2r_sphere* geometry, uint32_t n_geom, const float ambient[3],
                       const float* hdri_rgba, int32_t hdri_w, int32_t hdri_h);
+/* Scene edit without rebuilding the traversal tree. The reference rebuilds its BVH on every geometry drag (Application.cpp:508-509, then
+ * ResetAccumulator :510). Here the spheres keep their count and move / change radius or material; prims_bvh_order is either the order
+ * of the last upload or a NEW one (the reference's constructor re-sorts its prims on every rebuild, BVH.hpp:201-205, and hit indices,
+ * Q6 ties and the Q9 self-test are defined on that order) — it only has to be a permutation of `geometry`, which is how the library
+ * finds out which sphere went where (matched by value; the reference's BVH keeps no index map). The packed spheres and the light table
+ * are uploaded again; the traversal tree keeps its TOPOLOGY, its leaves are re-linked to the new order and its boxes are recomputed ON
+ * THE GPU, bottom-up, one launch per tree level (k_refit_level) — asynchronous on the context's stream, no host tree build, the captured
+ * CUDA graph stays valid. Results are those of a fresh b2r_upload_scene of the same arrays (closest hit == brute force over
+ * prims_bvh_order); only the tree's speed depends on how far the spheres moved from where it was built. quality_out (may be NULL;
+ * asking costs one more launch and a stream synchronisation) = sum of the inner boxes' surface areas now / when the tree was built:
+ * rebuild with b2r_upload_scene once it grows past ~1.5. B2R_ERR_STATE before the first upload; B2R_ERR_ARG when the count changed or
+ * prims_bvh_order is not a permutation of geometry. The caller resets the accumulator (b2r_reset) as the reference does. */
+int  b2r_refit_scene(b2r_ctx* ctx, const b2r_sphere* prims_bvh_order, uint32_t n_prims, const b2r_material* materials, uint32_t n_mat,
+                     const int32_t* light_geom_idx, uint32_t n_lights, const b2r_sphere* geometry, uint32_t n_geom, float* quality_out);
 /* Camera (Camera.hpp:61-88): view.pos, view.orient (w,x,y,z), projection.half_width/half_height/z, exp */
 int  b2r_set_camera(b2r_ctx* ctx, const float pos[3], const float orient_wxyz[4], float half_width, float half_height,
                     float z, float exposure);

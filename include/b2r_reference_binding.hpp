@@ -11,7 +11,7 @@
 // The reference's PODs are passed as they are: Sphere (32 B), Material (96 B) and BVH::Node (32 B) are layout-identical to
 // b2r_sphere / b2r_material / b2r_bvh_node (static_asserts below). Differences from the reference class:
 // the scene is snapshotted at upload, so after the app edits geometry or materials — where it already rebuilds the BVH and resets,
-// Application.cpp:508-510 — it calls SceneChanged(); camera state is re-read at every ResetAccumulator()/Resize().
+// Application.cpp:508-510 — it calls SceneChanged(), or SceneMoved() when spheres only moved (GPU refit of the traversal tree instead of a rebuild); camera state is re-read at every ResetAccumulator()/Resize().
 // tests/refbinding/ compiles this header against the reference's real headers and runs it next to the reference's own Renderer<>.
 #pragma once
 #include <cstdint>
@@ -73,6 +73,21 @@ struct ReferenceRenderer {
 		                       reinterpret_cast<const b2r_sphere*>(scene.geometry.data()), static_cast<uint32_t>(scene.geometry.size()),
 		                       ambient, scene.sky.hdri_data, scene.sky.hdri_width, scene.sky.hdri_height));
 		upload_camera();
+	}
+	// Geometry was dragged in the editor and the app has rebuilt acceleration_structure / lighting_acceleration (Application.cpp:508-509):
+	// instead of a full SceneChanged() the GPU keeps its traversal tree's topology, re-links its leaves to the rebuilt leaf order and
+	// refits its boxes (b2r_refit_scene). Falls back to SceneChanged() when the sphere count changed or the kept topology has degraded
+	// past `rebuild_above` (sum of inner-box areas relative to when the tree was built). Returns that ratio (1 after a rebuild).
+	float SceneMoved(float rebuild_above = 1.5f) {
+		const auto& bvh = scene.acceleration_structure; const auto& lights = scene.lighting_acceleration.prims;
+		float quality = 1.0f;
+		const int rc = b2r_refit_scene(ctx_, reinterpret_cast<const b2r_sphere*>(bvh.prims.data()), static_cast<uint32_t>(bvh.prims.size()),
+		                               reinterpret_cast<const b2r_material*>(scene.material.data()), static_cast<uint32_t>(scene.material.size()),
+		                               lights.data(), static_cast<uint32_t>(lights.size()),
+		                               reinterpret_cast<const b2r_sphere*>(scene.geometry.data()), static_cast<uint32_t>(scene.geometry.size()), &quality);
+		if (rc == B2R_ERR_ARG || rc == B2R_ERR_STATE || (rc == B2R_OK && quality > rebuild_above)) { SceneChanged(); return 1.0f; }  // spheres added / removed, or moved too far
+		check(rc);
+		return quality;
 	}
 	void Accumulate() { check(b2r_accumulate(ctx_, 1)); ++accumulations; }   // Renderer.hpp:73-434
 	void Render() {                                                            // Renderer.hpp:436-478: silently does nothing unless accumulations % K == 0

@@ -78,6 +78,47 @@ int hc_flatten(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* pr
 	return 0;
 }
 
+// refit tap (b2r_refit_scene's host twin): the traversal tree (reference_tree = 0) or the flattened reference tree of the spheres
+// prims_a, then refit_wide() with prims_b (same order). wide_out may be null to size; cost = sum of inner-slot half areas before / after.
+// remap (may be null): prims_b is in a new order, remap[index in prims_a] = index in prims_b of the same sphere.
+// Optionally traces rays through the refitted tree (closest hit; prim_out = index into prims_b or -1).
+int hc_refit(const b2r_sphere* prims_a, const b2r_bvh_node* nodes_a, uint32_t n_nodes, const b2r_sphere* prims_b, const uint32_t* remap, uint32_t n, void* wide_out, uint32_t* n_wide,
+             double cost[2], const float* rays, uint32_t n_rays, float* tfar_out, int32_t* prim_out) {
+	WideBvh w;
+	if (n_nodes == 0) { std::vector<b2r_bvh_node> tree; build_traversal_tree(prims_a, n, tree); flatten_bvh(tree.data(), static_cast<uint32_t>(tree.size()), prims_a, n, w); }
+	else flatten_bvh(nodes_a, n_nodes, prims_a, n, w);
+	*n_wide = static_cast<uint32_t>(w.nodes.size());
+	if (!wide_out && !n_rays) return 0;
+	cost[0] = w.cost;
+	if (prims_b) {  // null: the tree as flatten_bvh left it
+		std::vector<float4> packed(n);
+		for (uint32_t i = 0; i < n; i++) packed[i] = make_float4(prims_b[i].position[0], prims_b[i].position[1], prims_b[i].position[2], prims_b[i].radius_sq);
+		refit_wide(w, packed.data(), remap);
+	}
+	cost[1] = w.cost;
+	if (wide_out) std::memcpy(wide_out, w.nodes.data(), w.nodes.size() * sizeof(WideNode));
+	uint32_t cs = 0, cb = 0;
+	for (uint32_t i = 0; i < n_rays; i++) {
+		const float* r = rays + 6 * static_cast<size_t>(i);
+		traverse_closest<false>(w.nodes.data(), w.tn_bits, Ray{r[0], r[1], r[2], r[3], r[4], r[5]}, tfar_out + i, prim_out + i, &cs, &cb);
+	}
+	return 0;
+}
+// match_prims_to_geometry tap: geom_of_prim[n]; returns 1 when prims is a permutation of geometry
+int hc_match(const b2r_sphere* prims, const b2r_sphere* geometry, uint32_t n, uint32_t* geom_of_prim) {
+	std::vector<uint32_t> m; if (!match_prims_to_geometry(prims, geometry, n, m)) return 0;
+	std::memcpy(geom_of_prim, m.data(), n * sizeof(uint32_t)); return 1;
+}
+// brute-force closest hit over spheres in order (ties to the lowest index, BVH.hpp:265) for the same rays
+void hc_closest_brute(const b2r_sphere* prims, uint32_t n, const float* rays, uint32_t n_rays, float* tfar_out, int32_t* prim_out) {
+	for (uint32_t i = 0; i < n_rays; i++) {
+		const float* r = rays + 6 * static_cast<size_t>(i);
+		float best = FLT_MAX; int32_t prim = -1;
+		for (uint32_t j = 0; j < n; j++) { float d; if (sphere_hit_closest(prims[j].position[0], prims[j].position[1], prims[j].position[2], prims[j].radius_sq, r[0], r[1], r[2], r[3], r[4], r[5], &d) && d < best) { best = d; prim = static_cast<int32_t>(j); } }
+		tfar_out[i] = best; prim_out[i] = prim;
+	}
+}
+
 // scalar taps of csrc/b2r_math.h for function-level comparison with the oracle
 uint32_t hc_hash_2d(uint32_t x, uint32_t y) { return hash_2d(x, y); }
 uint32_t hc_hash_u32(uint32_t x) { return hash_u32(x); }

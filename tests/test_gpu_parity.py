@@ -272,6 +272,12 @@ def test_cpp_mirror_frame_loop(tmp_path):
     assert m and (int(m.group(1)), int(m.group(2)), int(m.group(4))) == (256, 144, 5)
     r = b2r.Renderer(scenes.default_scene(), 256, 144, max_bounces=16, buckets=5); r.Accumulate(5); assert r.Render()
     assert abs(float(m.group(3)) - float(r.framebuffer[..., :3].mean(dtype=np.float64))) < 1e-5
+    # the geometry drag at the end of the example (SceneMoved -> b2r_refit_scene) lands on the frame of a fresh upload of the moved scene
+    e = re.search(r"after a geometry drag: tree quality ratio ([0-9.]+), mean tonemapped value ([0-9.]+) after (\d+) accumulations", out)
+    assert e and int(e.group(3)) == 5 and float(e.group(1)) > 0.5
+    sc = scenes.default_scene(); sc["geometry"]["position"][1, 0] += np.float32(0.25); sc["geometry"]["position"][1, 1] += np.float32(0.125)
+    r.SetScene(sc); r.ResetAccumulator(); r.Accumulate(5); assert r.Render()
+    assert abs(float(e.group(2)) - float(r.framebuffer[..., :3].mean(dtype=np.float64))) < 1e-5
     r.close()
 
 
@@ -558,3 +564,97 @@ def test_async_resolve_delivers_the_same_frames():
     b.Accumulate(1)
     assert not b.RenderAsync(pinned[1])  # accumulations % K != 0: no-op like Renderer::Render (Renderer.hpp:437)
     a.close(); b.close()
+
+
+# ------------------------------------------------------------------------------------------------ scene edit: GPU refit
+def _moved_geometry(geo, rs, jitter=0.5, far=0):
+    """Every sphere moves by up to `jitter` radii and changes radius by up to 20 %; `far` of them jump anywhere in the scene."""
+    out = geo.copy(); r = np.sqrt(out["radius_sq"])
+    out["position"] += (rs.uniform(-1, 1, (len(out), 3)) * (jitter * r)[:, None]).astype(np.float32)
+    out["radius_sq"] = ((r * rs.uniform(0.8, 1.2, len(out))) ** 2).astype(np.float32)
+    if far:
+        idx = rs.choice(len(out), far, replace=False)
+        lo, hi = geo["position"].min(0), geo["position"].max(0)
+        out["position"][idx] = rs.uniform(lo, hi, (far, 3)).astype(np.float32)
+    return out
+
+
+@pytest.mark.parametrize("n,far,flags,keep", [(9, 0, 0, False), (9, 0, 0, True), (600, 20, b2r.FLAG_FORCE_BVH, False), (20000, 200, 0, False),
+                                              (20000, 0, b2r.FLAG_REFERENCE_TREE, True)])
+def test_refit_scene_equals_fresh_upload_and_oracle(n, far, flags, keep, hostcheck):
+    """b2r_refit_scene (the drop-in for the rebuild-on-drag of Application.cpp:508-510): spheres move, the app rebuilds the reference BVH
+    on the host (new leaf order; keep=True: it keeps the old one), the traversal tree keeps its topology and k_refit_level re-links its
+    leaves and recomputes its boxes on the GPU. (1) The device tree equals the host twin (same shared routine) bit for bit; (2) the frame
+    equals a fresh upload of the same arrays traced by BRUTE FORCE on the GPU, and — with the rebuilt order — the oracle's render of the
+    moved scene (within the BVH tolerance; bit-exact on the brute-force pipeline, Q9 included); (3) the captured CUDA graph survives the
+    edit; (4) the quality ratio is reported; (5) refitting back restores flatten_bvh's tree bit for bit."""
+    import ctypes as C
+    rs = np.random.RandomState(77 + n + far)
+    sc = scenes.default_scene() if n == 9 else scenes.random_scene(n, light_every=40)
+    w, h, mb = 160, 96, 8
+    r = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=2, flags=flags)
+    r.Accumulate(2)                                     # graph captured on the unedited scene
+    before_wide, _ = r.wide_nodes()
+    prims_a = r.scene.prims.copy(); nodes_a = r.scene.nodes.copy(); ids_a = r.scene.prim_ids.copy()
+    geo2 = _moved_geometry(sc["geometry"], rs, far=far)
+    q = r.RefitScene(geo2, keep_order=keep); r.ResetAccumulator(); r.reset_counters(); r.Accumulate(4)
+    got = r.buckets_host()
+    prims_b = r.scene.prims.copy(); ids_b = r.scene.prim_ids.copy()
+    assert keep == np.array_equal(ids_a, ids_b) or n == 9
+    # (1) device tree == host twin
+    wide, _ = r.wide_nodes()
+    prim_of_geom_b = np.zeros(n, np.uint32); prim_of_geom_b[ids_b] = np.arange(n, dtype=np.uint32)
+    remap = np.ascontiguousarray(prim_of_geom_b[ids_a])
+    nw = C.c_uint32(0); cost = (C.c_double * 2)(); twin = np.zeros_like(wide)
+    use_ref_tree = bool(flags & b2r.FLAG_REFERENCE_TREE)
+    hostcheck.hc_refit(C.c_void_p(prims_a.ctypes.data), C.c_void_p(nodes_a.ctypes.data) if use_ref_tree else None, len(nodes_a) if use_ref_tree else 0,
+                       C.c_void_p(prims_b.ctypes.data), C.c_void_p(remap.ctypes.data), n, C.c_void_p(twin.ctypes.data), C.byref(nw), cost, None, 0, None, None)
+    assert nw.value == len(wide) and wide.tobytes() == twin.tobytes()
+    inner = before_wide[:, :, 6].view(np.int32) >= 0
+    assert np.array_equal(inner, wide[:, :, 6].view(np.int32) >= 0) and np.array_equal(before_wide[:, :, 6].view(np.int32)[inner], wide[:, :, 6].view(np.int32)[inner])  # topology kept
+    assert abs(q - cost[1] / cost[0]) <= 1e-5 * q
+    print(f"refit n={n} far={far} keep_order={keep}: quality ratio {q:.4f}")
+    if far: assert q > 1.0
+    # (2a) fresh upload of the same arrays, brute force on the GPU
+    sc2 = scenes.Scene(name="moved", geometry=geo2, material=sc["material"], camera=sc["camera"], ambient=sc["ambient"], hdri=None)
+    ps2 = b2r.PreparedScene(sc2, w, h)
+    if keep: ps2.prims = prims_b; ps2.prim_ids = ids_b
+    else: assert all(np.array_equal(ps2.prims[k], prims_b[k]) for k in ("position", "radius_sq", "material_ID"))
+    f = b2r.Renderer(ps2, w, h, max_bounces=mb, buckets=2, flags=b2r.FLAG_FORCE_BRUTE); f.Accumulate(4)
+    fresh = f.buckets_host()
+    frac = divergent_fraction(got, fresh)
+    # (2b) the oracle on the moved scene (it rebuilds the reference BVH: the order the app gets after an edit)
+    o = oracle_for(sc2, w, h, mb, 2); o.accumulate(4)
+    frac_o = divergent_fraction(got, o.buckets())
+    print(f"refit n={n}: divergent pixel fraction vs fresh brute-force upload {frac:.3e}, vs oracle {frac_o:.3e}")
+    if n == 9:
+        assert got.tobytes() == fresh.tobytes()
+        if not keep: assert got.tobytes() == o.buckets().tobytes()
+    assert frac < 2e-3
+    if not keep:
+        assert frac_o < 2e-3
+        gc, oc = r.counters(), o.counters()
+        assert abs(gc["extension_rays"] - oc["extension_rays"]) <= 1e-3 * oc["extension_rays"]
+    # (5) back to the original spheres and order: the device tree is flatten_bvh's again, ratio 1
+    q1 = r.RefitScene(sc["geometry"], keep_order=False)
+    back, _ = r.wide_nodes()
+    assert back.tobytes() == before_wide.tobytes() and abs(q1 - 1.0) < 1e-6
+    r.close(); f.close()
+
+
+def test_refit_scene_error_behaviour():
+    sc = scenes.random_scene(300, light_every=40)
+    r = b2r.Renderer(None, 64, 48)
+    ps = b2r.PreparedScene(sc, 64, 48)
+    import ctypes as C
+    q = C.c_float(0)
+    args = lambda p: (C.c_void_p(p.prims.ctypes.data), len(p.prims), C.c_void_p(p.material.ctypes.data), len(p.material), C.c_void_p(p.lights.ctypes.data), len(p.lights),
+                      C.c_void_p(p.geometry.ctypes.data), len(p.geometry), C.byref(q))
+    assert b2r.lib().b2r_refit_scene(r._h, *args(ps)) == b2r.ERR_STATE        # no topology yet
+    r.SetScene(ps)
+    assert b2r.lib().b2r_refit_scene(r._h, *args(ps)) == b2r.OK and abs(q.value - 1.0) < 1e-6
+    other = b2r.PreparedScene(scenes.random_scene(301, light_every=40), 64, 48)
+    assert b2r.lib().b2r_refit_scene(r._h, *args(other)) == b2r.ERR_ARG        # a refit keeps the sphere count
+    bad = b2r.PreparedScene(sc, 64, 48); bad.prims = bad.prims.copy(); bad.prims["material_ID"][3] = 99
+    assert b2r.lib().b2r_refit_scene(r._h, *args(bad)) == b2r.ERR_ARG
+    r.close()

@@ -1,0 +1,153 @@
+"""Scene edit without a rebuild (b2r_refit_scene, cf. Application.cpp:508-510), CPU tier: the shared routine `refit_slot`
+(csrc/b2r_shade.h — the code k_refit_level runs per slot) through its host twin `refit_wide`, compiled by tests/hostcheck.
+
+* identity: refitting with unchanged spheres reproduces flatten_bvh's array bit for bit (pad(union) == union(pad));
+* containment: after moving spheres every inner slot's box contains every sphere below it, leaves hold the moved spheres;
+* semantics: closest hit through the refitted tree == brute force over the moved spheres in the same order (BVH.hpp:265 ties);
+* the quality ratio is 1 on identity and grows when spheres are scattered.
+The GPU tier (tests/test_gpu_parity.py::test_refit_*) checks the kernel against this twin and against a fresh upload."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import b2r
+import scenes
+
+EMPTY = -2 ** 31
+
+
+def vp(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def refit(hc, prims_a, prims_b, nodes=None, rays=None, remap=None):
+    n = len(prims_a); nw = C.c_uint32(0); cost = (C.c_double * 2)()
+    nn = 0 if nodes is None else len(nodes)
+    hc.hc_refit(vp(prims_a), vp(nodes), nn, vp(prims_b), vp(remap), n, None, C.byref(nw), cost, None, 0, None, None)
+    wide = np.zeros((nw.value, 4, 8), np.float32)
+    nr = 0 if rays is None else len(rays)
+    tfar = np.zeros(nr, np.float32); prim = np.zeros(nr, np.int32)
+    hc.hc_refit(vp(prims_a), vp(nodes), nn, vp(prims_b), vp(remap), n, vp(wide), C.byref(nw), cost, vp(rays), nr, vp(tfar), vp(prim))
+    return wide, (cost[0], cost[1]), tfar, prim
+
+
+def moved(prims, rs, jitter=0.5, far=0):
+    """Every sphere moves by up to `jitter` radii and changes radius by up to 20 %; `far` of them jump anywhere in the scene."""
+    out = prims.copy()
+    r = np.sqrt(out["radius_sq"])
+    out["position"] += (rs.uniform(-1, 1, (len(out), 3)) * (jitter * r)[:, None]).astype(np.float32)
+    out["radius_sq"] = ((r * rs.uniform(0.8, 1.2, len(out))) ** 2).astype(np.float32)
+    if far:
+        idx = rs.choice(len(out), far, replace=False)
+        lo, hi = prims["position"].min(0), prims["position"].max(0)
+        out["position"][idx] = rs.uniform(lo, hi, (far, 3)).astype(np.float32)
+    return out
+
+
+def camera_rays(n, rs, prims):
+    lo, hi = prims["position"].min(0), prims["position"].max(0)
+    o = rs.uniform(lo - 5, hi + 5, (n, 3)); t = rs.uniform(lo, hi, (n, 3)); d = t - o
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    return np.ascontiguousarray(np.concatenate([o, d], 1), np.float32)
+
+
+def check_contains(wide, prims):
+    """Returns the number of leaves; asserts that every inner slot box contains the bounds of every sphere in its subtree."""
+    seen = []
+
+    def walk(w):
+        lo = np.full(3, np.inf); hi = np.full(3, -np.inf)
+        for k in range(4):
+            link = int(wide[w, k, 6:7].view(np.int32)[0])
+            if link == EMPTY: continue
+            if link < 0:
+                pr = ~link; seen.append(pr)
+                assert np.array_equal(wide[w, k, :3], prims["position"][pr]) and wide[w, k, 3] == prims["radius_sq"][pr]
+                r = np.sqrt(prims["radius_sq"][pr]); c = prims["position"][pr]
+                lo = np.minimum(lo, c - r); hi = np.maximum(hi, c + r)
+            else:
+                clo, chi = walk(link)
+                blo, bhi = wide[w, k, 0:3], wide[w, k, 3:6]
+                assert np.all(blo <= clo) and np.all(bhi >= chi)                         # conservative
+                assert np.all(clo - blo <= (np.abs(clo) + 1) * 2e-6) and np.all(bhi - chi <= (np.abs(chi) + 1) * 2e-6)  # and tight
+                lo = np.minimum(lo, blo); hi = np.maximum(hi, bhi)
+        return lo, hi
+    walk(0)
+    assert sorted(seen) == list(range(len(prims)))
+
+
+@pytest.mark.parametrize("n", [1, 2, 9, 40, 777, 5000])
+def test_refit_identity_is_bit_exact(hostcheck, n):
+    sc = scenes.default_scene() if n == 9 else scenes.random_scene(n, light_every=5)
+    nodes, prims, _ = b2r.build_bvh(sc["geometry"])
+    base, cost, _, _ = refit(hostcheck, prims, prims)
+    # what flatten_bvh itself stores
+    if n > 1:
+        from test_hostcheck import flatten
+        ref_flat = flatten(nodes, prims)
+        ref_refit, cost_r, _, _ = refit(hostcheck, prims, prims, nodes=nodes)
+        assert ref_flat.tobytes() == ref_refit.tobytes()      # reference topology: refit(identity) == flatten, bit for bit
+        assert cost_r[0] == cost_r[1]
+    assert cost[0] == cost[1]
+    untouched, _, _, _ = refit(hostcheck, prims, None)
+    assert base.tobytes() == untouched.tobytes()              # traversal-tree topology (libb2r's default): the same identity
+    check_contains(base, prims)
+
+
+@pytest.mark.parametrize("n,far", [(9, 0), (40, 3), (777, 0), (777, 50), (5000, 100)])
+def test_refit_moved_spheres_boxes_and_closest_hit(hostcheck, n, far):
+    rs = np.random.RandomState(1000 + n + far)
+    sc = scenes.default_scene() if n == 9 else scenes.random_scene(n, light_every=5)
+    _, prims, _ = b2r.build_bvh(sc["geometry"])
+    new = moved(prims, rs, far=far)
+    rays = camera_rays(3000, rs, prims)
+    wide, cost, tfar, prim = refit(hostcheck, prims, new, rays=rays)
+    check_contains(wide, new)
+    bt = np.zeros(len(rays), np.float32); bp = np.zeros(len(rays), np.int32)
+    hostcheck.hc_closest_brute(vp(new), len(new), vp(rays), len(rays), vp(bt), vp(bp))
+    assert (bp >= 0).mean() > 0.2
+    assert np.array_equal(bp, prim) and bt.tobytes() == tfar.tobytes()
+    if far:
+        assert cost[1] > cost[0]          # scattered spheres make the kept topology worse, and the ratio says so
+    # topology untouched: same links everywhere
+    base, _, _, _ = refit(hostcheck, prims, prims)
+    assert np.array_equal(base[:, :, 6].view(np.int32), wide[:, :, 6].view(np.int32))
+
+
+@pytest.mark.parametrize("n,far", [(9, 0), (777, 50), (5000, 0)])
+def test_refit_into_a_rebuilt_bvh_order(hostcheck, n, far):
+    """The reference re-sorts its prims on every rebuild (BVH.hpp:201-205). Refit into the NEW order of the moved scene: leaf links are
+    remapped old index -> geometry index -> new index (match_prims_to_geometry pairs prims with geometry by value, as b2r_refit_scene
+    does), and the closest hit then equals brute force over the new prims array, indices included."""
+    rs = np.random.RandomState(2000 + n + far)
+    sc = scenes.default_scene() if n == 9 else scenes.random_scene(n, light_every=5)
+    geo = np.ascontiguousarray(sc["geometry"])
+    _, prims, ids = b2r.build_bvh(geo)
+    geo2 = moved(geo, rs, far=far)
+    _, prims2, ids2 = b2r.build_bvh(geo2)                 # what the app does after an edit
+    # value matching recovers the builder's own index map
+    m = np.zeros(n, np.uint32)
+    assert hostcheck.hc_match(vp(prims), vp(geo), n, vp(m)) == 1 and np.array_equal(m, ids)
+    m2 = np.zeros(n, np.uint32)
+    assert hostcheck.hc_match(vp(prims2), vp(geo2), n, vp(m2)) == 1 and np.array_equal(m2, ids2)
+    assert hostcheck.hc_match(vp(prims2), vp(geo), n, vp(m2)) == 0      # not a permutation of each other
+    prim_of_geom2 = np.zeros(n, np.uint32); prim_of_geom2[ids2] = np.arange(n, dtype=np.uint32)
+    remap = np.ascontiguousarray(prim_of_geom2[ids])
+    rays = camera_rays(3000, rs, prims)
+    wide, cost, tfar, prim = refit(hostcheck, prims, prims2, rays=rays, remap=remap)
+    check_contains(wide, prims2)
+    bt = np.zeros(len(rays), np.float32); bp = np.zeros(len(rays), np.int32)
+    hostcheck.hc_closest_brute(vp(prims2), n, vp(rays), len(rays), vp(bt), vp(bp))
+    assert np.array_equal(bp, prim) and bt.tobytes() == tfar.tobytes()
+
+
+def test_match_pairs_equal_spheres(hostcheck):
+    sc = scenes.random_scene(64, light_every=5)
+    geo = np.ascontiguousarray(sc["geometry"]); geo[10] = geo[3]; geo[40] = geo[3]      # three identical spheres
+    perm = np.random.RandomState(3).permutation(64)
+    prims = np.ascontiguousarray(geo[perm]); m = np.zeros(64, np.uint32)
+    assert hostcheck.hc_match(vp(prims), vp(geo), 64, vp(m)) == 1
+    assert sorted(m.tolist()) == list(range(64))
+    for f in ("position", "radius_sq", "material_ID"):
+        assert np.array_equal(geo[m][f], prims[f])
