@@ -476,8 +476,12 @@ int b2r_refit_scene(b2r_ctx* c, const b2r_sphere* prims, uint32_t n_prims, const
 	const std::vector<uint32_t>& old_geom = c->cur_geom_of_prim.empty() ? c->wide_host.geom_of_prim : c->cur_geom_of_prim;
 	if (old_geom.size() != n_prims) return fail(B2R_ERR_STATE, "the uploaded prims were not a permutation of geometry: no refit for this scene");
 	std::vector<uint32_t> new_geom, remap;
-	if (!match_prims_to_geometry(prims, geometry, n_prims, new_geom)) return fail(B2R_ERR_ARG, "prims_bvh_order is not a permutation of geometry");
-	bool same_order = new_geom == old_geom;
+	bool same_order = true;  // the cheap case first: the caller kept its leaf order (one sequential pass instead of a hash table)
+	for (uint32_t i = 0; i < n_prims && same_order; i++) same_order = std::memcmp(&prims[i], &geometry[old_geom[i]], 20) == 0;
+	if (!same_order) {
+		if (!match_prims_to_geometry(prims, geometry, n_prims, new_geom)) return fail(B2R_ERR_ARG, "prims_bvh_order is not a permutation of geometry");
+		same_order = new_geom == old_geom;
+	}
 	if (!same_order) {
 		std::vector<uint32_t> prim_of_geom(n_prims);
 		for (uint32_t i = 0; i < n_prims; i++) prim_of_geom[new_geom[i]] = i;
