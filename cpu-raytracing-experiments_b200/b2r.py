@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "b2r_sync", "b2r_upload_scene", "b2r_refit_scene", "b2r_set_camera", "b2r_accumulate", "b2r_resolve", "b2r_resolve_async", "b2r_frame_wait", "b2r_resolve_from", "b2r_ipc_export_buckets", "b2r_ipc_open_peers", "b2r_ipc_close", "b2r_resolve_peers", "b2r_get_accumulations", "b2r_set_accumulations",
     "b2r_read_buckets", "b2r_write_buckets", "b2r_device_buckets", "b2r_device_framebuffer", "b2r_read_counters", "b2r_reset_counters",
     "b2r_read_kernel_times", "b2r_set_flags", "b2r_generate_rays", "b2r_trace_closest", "b2r_trace_shadow", "b2r_read_wide_nodes",
-    "b2r_write_hdr", "b2r_last_error", "b2r_abi_version",
+    "b2r_write_hdr", "b2r_read_hdr", "b2r_last_error", "b2r_abi_version",
 ]
 
 
@@ -71,7 +71,7 @@ def lib():
             "b2r_get_accumulations": [vp, vp], "b2r_set_accumulations": [vp, u32], "b2r_read_buckets": [vp, vp], "b2r_write_buckets": [vp, vp],
             "b2r_device_buckets": [vp, vp, vp], "b2r_device_framebuffer": [vp, vp, vp], "b2r_read_counters": [vp, vp], "b2r_reset_counters": [vp],
             "b2r_read_kernel_times": [vp, vp, vp, C.c_int], "b2r_set_flags": [vp, u32], "b2r_generate_rays": [vp, u32, vp],
-            "b2r_write_hdr": [C.c_char_p, vp, u32, u32], "b2r_trace_closest": [vp, vp, u32, vp, vp], "b2r_trace_shadow": [vp, vp, vp, u32, vp], "b2r_read_wide_nodes": [vp, vp, vp, vp],
+            "b2r_write_hdr": [C.c_char_p, vp, u32, u32], "b2r_read_hdr": [C.c_char_p, vp, vp, vp], "b2r_trace_closest": [vp, vp, u32, vp, vp], "b2r_trace_shadow": [vp, vp, vp, u32, vp], "b2r_read_wide_nodes": [vp, vp, vp, vp],
         }
         for name, args in sig.items():
             fn = getattr(L, name); fn.argtypes = args; fn.restype = C.c_int
@@ -315,6 +315,17 @@ def write_hdr(path, rgba):
     """Image::Store (Image.cpp:71-74): Radiance .hdr of an (H, W, 4) float32 frame, vertically flipped like the reference."""
     a = np.ascontiguousarray(rgba, np.float32)
     _check(lib().b2r_write_hdr(str(path).encode(), _ptr(a), a.shape[1], a.shape[0]))
+
+
+def read_hdr(path):
+    """stbi_loadf(path, &w, &h, &channels, 4) for a Radiance .hdr, as Application.cpp:225-231 loads the sky: (H, W, 4) float32."""
+    w, h = C.c_int32(0), C.c_int32(0)
+    if lib().b2r_read_hdr(str(path).encode(), None, C.byref(w), C.byref(h)) != OK:
+        raise B2RError(ERR_ARG, f"{path}: not a Radiance .hdr stb_image would load")
+    out = np.empty((h.value, w.value, 4), np.float32)
+    if lib().b2r_read_hdr(str(path).encode(), _ptr(out), C.byref(w), C.byref(h)) != OK:
+        raise B2RError(ERR_ARG, f"{path}: corrupt or truncated .hdr")
+    return out
 
 
 def tile_to_raster(buf, width, height):

@@ -9,7 +9,9 @@
 #include <thread>
 #include <cmath>
 #include <cstddef>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 #include <numeric>
 #include <cstdio>
 
@@ -472,12 +474,13 @@ void build_traversal_tree(const b2r_sphere* prims, uint32_t n, std::vector<b2r_b
 // ---------------------------------------------------------------------------------------------- frame output
 // Image::Store (Image.cpp:71-74): stbi_flip_vertically_on_write(true); stbi_write_hdr(path, w, h, 4, rgba). The file format is
 // the published Radiance RGBE format with per-scanline run-length encoding; the mantissa/exponent split follows stb's
-// linear_to_rgbe (frexp of the largest channel, truncating conversion).
+// linear_to_rgbe (frexp of the largest channel, truncating conversion). Header as stb writes it: the EXPOSURE line follows FORMAT directly
+// and ONE empty line ends the header (stb_image's own reader — b2r_read_hdr below — takes the line after the first empty one as the resolution).
 extern "C" int b2r_write_hdr(const char* path, const float* rgba, uint32_t width, uint32_t height) {
 	if (!path || !rgba || width == 0 || height == 0) return B2R_ERR_ARG;
 	FILE* f = std::fopen(path, "wb");
 	if (!f) return B2R_ERR_ARG;
-	std::fprintf(f, "#?RADIANCE\n# Written by libb2r\nFORMAT=32-bit_rle_rgbe\n\nEXPOSURE=          1.0000000000000\n\n-Y %u +X %u\n", height, width);
+	std::fprintf(f, "#?RADIANCE\n# Written by libb2r\nFORMAT=32-bit_rle_rgbe\nEXPOSURE=          1.0000000000000\n\n-Y %u +X %u\n", height, width);
 	std::vector<unsigned char> rgbe(static_cast<size_t>(width) * 4), line;
 	for (uint32_t row = 0; row < height; row++) {
 		const float* src = rgba + static_cast<size_t>(height - 1 - row) * width * 4;  // vertical flip
@@ -510,4 +513,102 @@ extern "C" int b2r_write_hdr(const char* path, const float* rgba, uint32_t width
 	}
 	const bool ok = std::fclose(f) == 0;
 	return ok ? B2R_OK : B2R_ERR_ARG;
+}
+
+// ---------------------------------------------------------------------------------------------- sky texture input
+// The reference loads its environment map with stbi_loadf(path, &w, &h, &channels, 4) (Application.cpp:225-231; also Image.cpp:53-55).
+// stb_image.h is a third-party header the reference does not vendor (nothings/stb, no pinned version; the .hdr path has been stable
+// through v2.x). This restates its published Radiance decoder — stbi__hdr_load / stbi__hdr_convert — for req_comp = 4:
+//   header:  first line "#?RADIANCE" or "#?RGBE"; lines up to the first empty one, one of which must be "FORMAT=32-bit_rle_rgbe";
+//            then "-Y <height> +X <width>" (no other orientation is accepted);
+//   pixels:  width < 8 or >= 32768: flat RGBE quadruples. Otherwise per scanline {2, 2, width_hi, width_lo} followed by the four
+//            components one after the other, each as runs (count > 128: count-128 copies of the next byte) and literals (count bytes);
+//            a scanline that does not start with {2, 2, <0x80} switches the rest of the file to flat pixels, the four bytes read so
+//            far being pixel 0 and decoding resuming at pixel 1 of row 0 — stb's own comment: "yes, this makes no sense";
+//   value:   e == 0 -> 0, else channel = mantissa * 2^(e - 136), no half-bit offset; alpha = 1. Rows in file order (no vertical flip
+//            unless stbi_set_flip_vertically_on_load was called, which the reference never does).
+namespace {
+struct ByteReader {
+	FILE* f; bool eof = false;
+	int get8() { const int c = std::fgetc(f); if (c == EOF) { eof = true; return 0; } return c; }
+	void getn(unsigned char* dst, int n) { for (int i = 0; i < n; i++) dst[i] = static_cast<unsigned char>(get8()); }
+	// stbi__hdr_gettoken: one line without its '\n', at most 1023 characters kept, the rest of an over-long line skipped
+	std::string token() {
+		std::string s; int c = get8();
+		while (!eof && c != '\n') {
+			s.push_back(static_cast<char>(c));
+			if (s.size() == 1023) { while (!eof && get8() != '\n') {} break; }
+			c = get8();
+		}
+		return s;
+	}
+};
+inline void rgbe_to_float4(float* out, const unsigned char* in) {  // stbi__hdr_convert, req_comp 4
+	if (in[3] != 0) {
+		const float f1 = static_cast<float>(ldexp(1.0f, static_cast<int>(in[3]) - (128 + 8)));
+		out[0] = in[0] * f1; out[1] = in[1] * f1; out[2] = in[2] * f1;
+	} else out[0] = out[1] = out[2] = 0.0f;
+	out[3] = 1.0f;
+}
+}  // namespace
+
+extern "C" int b2r_read_hdr(const char* path, float* rgba_out, int32_t* width_out, int32_t* height_out) {
+	if (!path || !width_out || !height_out) return B2R_ERR_ARG;
+	FILE* f = std::fopen(path, "rb");
+	if (!f) return B2R_ERR_ARG;
+	struct Closer { FILE* f; ~Closer() { std::fclose(f); } } closer{f};
+	ByteReader in{f};
+	const std::string magic = in.token();
+	if (magic != "#?RADIANCE" && magic != "#?RGBE") return B2R_ERR_ARG;               // "not HDR"
+	bool valid = false;
+	for (;;) { const std::string t = in.token(); if (t.empty()) break; if (t == "FORMAT=32-bit_rle_rgbe") valid = true; }
+	if (!valid) return B2R_ERR_ARG;                                                      // "unsupported format"
+	const std::string res = in.token();
+	if (res.compare(0, 3, "-Y ") != 0) return B2R_ERR_ARG;                               // "unsupported data layout"
+	char* p = nullptr; const char* s = res.c_str() + 3;
+	const long height = std::strtol(s, &p, 10);
+	while (*p == ' ') ++p;
+	if (std::strncmp(p, "+X ", 3) != 0) return B2R_ERR_ARG;
+	const long width = std::strtol(p + 3, nullptr, 10);
+	if (height <= 0 || width <= 0 || height > (1 << 24) || width > (1 << 24)) return B2R_ERR_ARG;   // stb: "too large" above STBI_MAX_DIMENSIONS
+	*width_out = static_cast<int32_t>(width); *height_out = static_cast<int32_t>(height);
+	if (!rgba_out) return B2R_OK;                                                        // size query
+	const size_t W = static_cast<size_t>(width), H = static_cast<size_t>(height);
+	size_t i = 0, j = 0;
+	bool flat = width < 8 || width >= 32768;
+	if (!flat) {
+		std::vector<unsigned char> scan(W * 4);
+		for (j = 0; j < H && !flat; ++j) {
+			const int c1 = in.get8(), c2 = in.get8(); int len = in.get8();
+			if (c1 != 2 || c2 != 2 || (len & 0x80)) {
+				const unsigned char rgbe[4] = {static_cast<unsigned char>(c1), static_cast<unsigned char>(c2), static_cast<unsigned char>(len), static_cast<unsigned char>(in.get8())};
+				rgbe_to_float4(rgba_out, rgbe);
+				i = 1; j = 0; flat = true;
+				break;
+			}
+			len = (len << 8) | in.get8();
+			if (static_cast<long>(len) != width) return B2R_ERR_ARG;                     // "invalid decoded scanline length"
+			for (int k = 0; k < 4; ++k) {
+				size_t x = 0;
+				while (x < W) {
+					const size_t nleft = W - x;
+					int count = in.get8();
+					if (in.eof) return B2R_ERR_ARG;
+					if (count > 128) {
+						const unsigned char value = static_cast<unsigned char>(in.get8()); count -= 128;
+						if (count == 0 || static_cast<size_t>(count) > nleft) return B2R_ERR_ARG;  // "corrupt"
+						for (int z = 0; z < count; ++z) scan[x++ * 4 + k] = value;
+					} else {
+						if (count == 0 || static_cast<size_t>(count) > nleft) return B2R_ERR_ARG;
+						for (int z = 0; z < count; ++z) scan[x++ * 4 + k] = static_cast<unsigned char>(in.get8());
+					}
+				}
+			}
+			for (size_t x = 0; x < W; ++x) rgbe_to_float4(rgba_out + (j * W + x) * 4, scan.data() + x * 4);
+		}
+	}
+	if (flat) {
+		for (; j < H; ++j, i = 0) for (; i < W; ++i) { unsigned char rgbe[4]; in.getn(rgbe, 4); rgbe_to_float4(rgba_out + (j * W + i) * 4, rgbe); }
+	}
+	return in.eof ? B2R_ERR_ARG : B2R_OK;  // (stb does not notice a short file; a truncated environment map is reported here)
 }

@@ -23,4 +23,17 @@ struct Sky {  // Primitives.hpp:29-47: equirect HDRI (RGBA32F, nearest texel) x 
 	int32_t hdri_width = 0, hdri_height = 0, hdri_channels = 0;
 	float* hdri_data = nullptr;
 	float hdri_fwidth = 0, hdri_fheight = 0;
+	// Application.cpp:225-231: hdri_data = stbi_loadf(path, &hdri_width, &hdri_height, &hdri_channels, 4); terminate on failure;
+	// hdri_fwidth/fheight = size - 1. Here through b2r_read_hdr (the Radiance decoder of stb_image restated); returns false where the
+	// reference prints stbi_failure_reason() and terminates. The array is owned by `hdri_storage`.
+	std::vector<float> hdri_storage;
+	bool Load(const char* path) {
+		int32_t w = 0, h = 0;
+		if (b2r_read_hdr(path, nullptr, &w, &h) != B2R_OK) return false;
+		hdri_storage.assign(static_cast<size_t>(w) * h * 4, 0.0f);
+		if (b2r_read_hdr(path, hdri_storage.data(), &w, &h) != B2R_OK) return false;
+		hdri_data = hdri_storage.data(); hdri_width = w; hdri_height = h; hdri_channels = 3;
+		hdri_fwidth = static_cast<float>(w - 1); hdri_fheight = static_cast<float>(h - 1);
+		return true;
+	}
 };

@@ -192,6 +192,12 @@ int  b2r_read_wide_nodes(b2r_ctx* ctx, void* out_host, uint32_t* n_wide_nodes, u
  * RGBA32F framebuffer as a Radiance .hdr (32-bit_rle_rgbe, rows written top-down = framebuffer rows in reverse, alpha dropped). */
 int  b2r_write_hdr(const char* path, const float* rgba, uint32_t width, uint32_t height);
 
+/* The sky texture as the reference loads it: stbi_loadf(path, &w, &h, &channels, 4) (Application.cpp:225-231) — a Radiance .hdr
+ * (32-bit_rle_rgbe, "-Y h +X w") decoded to RGBA32F rows in file order, channel = mantissa * 2^(e-136), alpha 1; exactly the array
+ * b2r_upload_scene takes as hdri_rgba. rgba_out may be NULL to query the size first. B2R_ERR_ARG for a file stb_image would reject
+ * (not Radiance, other FORMAT or orientation, corrupt run lengths) and for a truncated one. */
+int  b2r_read_hdr(const char* path, float* rgba_out, int32_t* width_out, int32_t* height_out);
+
 const char* b2r_last_error(void);   /* text of the last failure on this thread */
 int  b2r_abi_version(void);
 

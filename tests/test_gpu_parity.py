@@ -340,6 +340,21 @@ def test_sky_hdri_scene(flags):
     r.close()
 
 
+def test_sky_loaded_from_a_radiance_file(tmp_path):
+    """The sky as the reference gets it (Application.cpp:225-231): an .hdr file decoded by b2r_read_hdr (stb_image's Radiance decoder
+    restated) and handed to b2r_upload_scene. RGBE keeps 8 mantissa bits, so the oracle is given the same decoded array: bit-exact."""
+    tex = scenes.synthetic_hdri(96, 48, seed=3)
+    b2r.write_hdr(tmp_path / "env.hdr", tex[::-1])      # the writer flips rows (Image.cpp:72): store it so that the file holds `tex` top-down
+    env = b2r.read_hdr(tmp_path / "env.hdr")
+    assert env.shape == tex.shape and np.all(np.abs(env[..., :3] - tex[..., :3]) <= tex[..., :3].max(axis=2, keepdims=True) / 128)
+    sc = scenes.bvh_test_scene(255, hdri=env)
+    r = b2r.Renderer(sc, 128, 80, max_bounces=8, buckets=5); r.Accumulate(5); assert r.Render()
+    o = oracle_for(sc, 128, 80, 8, 5); o.accumulate(5)
+    assert r.buckets_host().tobytes() == o.buckets().tobytes() and r.framebuffer.tobytes() == o.render()[1].tobytes()
+    assert float(r.buckets_host().max()) > 0.0
+    r.close()
+
+
 def test_c4_size_oracle_spot_tiles():
     """BASELINE configs[3] size (1M spheres, 3840x2160, max_bounces 16): one sample, 24 random tiles re-rendered by the oracle in
     stream-BVH mode. Also exercises the 22-bit node index / 13-bit distance split of the traversal stack entries."""

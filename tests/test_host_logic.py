@@ -91,3 +91,68 @@ def test_hdr_writer_roundtrip(tmp_path, w, h):
     tol = img[..., :3].max(axis=2, keepdims=True) / 128 + 1e-30
     assert np.all(np.abs(back - img[..., :3]) <= tol)
     assert np.array_equal(back[0, : w // 2], img[0, : w // 2, :3])
+
+
+# ------------------------------------------------------------------------------------------------ sky texture input (.hdr reader)
+def _hdr_file(path, w, h, body, magic=b"#?RADIANCE", fmt=b"FORMAT=32-bit_rle_rgbe", extra=b"# a comment\nEXPOSURE=1.0\n", res=None):
+    res = res if res is not None else b"-Y %d +X %d" % (h, w)
+    open(path, "wb").write(magic + b"\n" + extra + fmt + b"\n\n" + res + b"\n" + bytes(body))
+    return path
+
+
+@pytest.mark.parametrize("w,h", [(5, 3), (64, 17), (333, 9)])
+def test_hdr_reader_equals_stb_restatement(tmp_path, w, h):
+    """b2r_read_hdr = stbi_loadf(path, ..., 4) as the reference loads its sky (Application.cpp:225-231): the file written by the
+    library's own Radiance writer (flat below 8 pixels per row, RLE above) decodes to mantissa * 2^(e-136), alpha 1, rows in file
+    order — bit for bit the values of the independent Python decoder of this test file."""
+    rs = np.random.RandomState(w + 1)
+    img = np.zeros((h, w, 4), np.float32); img[..., :3] = rs.rand(h, w, 3) ** 4 * 50; img[..., 3] = 1
+    img[0, : w // 2, :3] = 0.25; img[1:, -1, :3] = 0
+    b2r.write_hdr(tmp_path / "f.hdr", img)
+    got = b2r.read_hdr(tmp_path / "f.hdr")
+    assert got.shape == (h, w, 4) and got.dtype == np.float32 and np.all(got[..., 3] == 1.0)
+    want = _read_hdr(tmp_path / "f.hdr").astype(np.float32)
+    assert got[..., :3].tobytes() == want.tobytes()
+    assert np.array_equal(got[::-1][0, : w // 2, :3], img[0, : w // 2, :3])   # the writer flips rows (Image.cpp:72), the reader does not
+
+
+def test_hdr_reader_known_answers_and_old_format(tmp_path):
+    # one RGBE quadruple by hand: (128, 64, 32 | e=129) -> 128 * 2^-7 = 1, 0.5, 0.25; e = 0 -> black whatever the mantissas
+    px = [128, 64, 32, 129, 200, 100, 50, 0, 255, 255, 255, 136 + 3, 1, 2, 3, 128]
+    got = b2r.read_hdr(_hdr_file(tmp_path / "a.hdr", 4, 1, px, magic=b"#?RGBE"))
+    assert got.tolist() == [[[1.0, 0.5, 0.25, 1.0], [0.0, 0.0, 0.0, 1.0], [2040.0, 2040.0, 2040.0, 1.0], [1 / 256, 2 / 256, 3 / 256, 1.0]]]
+    # a wide image stored WITHOUT run-length encoding (old Radiance files): the first scanline does not start with {2, 2, <0x80}, stb
+    # switches to flat pixels for the whole file ("yes, this makes no sense")
+    rs = np.random.RandomState(4); w, h = 12, 3
+    raw = rs.randint(0, 256, (h, w, 4)).astype(np.uint8); raw[..., 0] |= 128; raw[0, 0, :2] = (7, 9)
+    got = b2r.read_hdr(_hdr_file(tmp_path / "b.hdr", w, h, raw.tobytes()))
+    want = (raw[..., :3] * np.ldexp(1.0, raw[..., 3].astype(np.int32) - 136)[..., None] * (raw[..., 3:] > 0)).astype(np.float32)
+    assert got[..., :3].tobytes() == want.tobytes()
+    # hand-made RLE scanline, w = 8: R = run of 8 x 64; G = literals; B = run 3 + literals 5; E = run of 8 x 128
+    line = [2, 2, 0, 8, 128 + 8, 64, 8, 1, 2, 3, 4, 5, 6, 7, 8, 128 + 3, 9, 5, 10, 11, 12, 13, 14, 128 + 8, 128]
+    got = b2r.read_hdr(_hdr_file(tmp_path / "c.hdr", 8, 1, line))
+    assert got[0, :, 0].tolist() == [0.25] * 8 and got[0, :, 1].tolist() == [k / 256 for k in range(1, 9)]
+    assert got[0, :, 2].tolist() == [9 / 256] * 3 + [k / 256 for k in range(10, 15)]
+
+
+def test_hdr_reader_rejects_what_stb_rejects(tmp_path):
+    import ctypes as C
+    ok_line = [2, 2, 0, 8] + [128 + 8, 1] * 4
+    w, h = C.c_int32(0), C.c_int32(0)
+    def rc(path, out=None):
+        return b2r.lib().b2r_read_hdr(str(path).encode(), out, C.byref(w), C.byref(h))
+    assert rc(_hdr_file(tmp_path / "ok.hdr", 8, 1, ok_line)) == b2r.OK and (w.value, h.value) == (8, 1)
+    buf = np.zeros((1, 8, 4), np.float32); p = C.c_void_p(buf.ctypes.data)
+    assert rc(tmp_path / "ok.hdr", p) == b2r.OK
+    assert rc(tmp_path / "missing.hdr") == b2r.ERR_ARG
+    assert rc(_hdr_file(tmp_path / "m.hdr", 8, 1, ok_line, magic=b"#?RADIANC")) == b2r.ERR_ARG                 # "not HDR"
+    assert rc(_hdr_file(tmp_path / "f.hdr", 8, 1, ok_line, fmt=b"FORMAT=32-bit_rle_xyze")) == b2r.ERR_ARG      # "unsupported format"
+    assert rc(_hdr_file(tmp_path / "r.hdr", 8, 1, ok_line, res=b"+Y 1 +X 8")) == b2r.ERR_ARG                   # "unsupported data layout"
+    assert rc(_hdr_file(tmp_path / "x.hdr", 8, 1, ok_line, res=b"-Y 1 -X 8")) == b2r.ERR_ARG
+    assert rc(_hdr_file(tmp_path / "l.hdr", 8, 1, [2, 2, 0, 9] + [128 + 8, 1] * 4), p) == b2r.ERR_ARG           # "invalid decoded scanline length"
+    assert rc(_hdr_file(tmp_path / "c.hdr", 8, 1, [2, 2, 0, 8, 128 + 9, 1]), p) == b2r.ERR_ARG                  # run longer than the row: "corrupt"
+    assert rc(_hdr_file(tmp_path / "z.hdr", 8, 1, [2, 2, 0, 8, 0]), p) == b2r.ERR_ARG                           # zero count
+    two = np.zeros((2, 8, 4), np.float32)
+    assert rc(_hdr_file(tmp_path / "t.hdr", 8, 2, ok_line), C.c_void_p(two.ctypes.data)) == b2r.ERR_ARG        # second scanline missing
+    big = np.zeros((2, 3, 4), np.float32)
+    assert rc(_hdr_file(tmp_path / "s.hdr", 3, 2, [1] * 20), C.c_void_p(big.ctypes.data)) == b2r.ERR_ARG        # flat file four bytes short
