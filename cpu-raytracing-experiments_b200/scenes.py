@@ -75,6 +75,24 @@ def white_furnace():
                  ambient=(1.0, 1.0, 1.0), hdri=np.ones((1, 1, 4), np.float32))
 
 
+def brdf_test_scene(hdri=None, gradations=10):
+    """Scenes::BRDF_test, Application.cpp:123-217, in the variant the source selects (`switch (Properties::Roughness)`): a dark floor
+    sphere, one spherical light of emission 100, and a row of `gradations` unit spheres whose roughness runs 0..1 with F0 = F80 = 1 and
+    ALBEDO 0 — under the shipped Lambertian closure (BRDF 0, Renderer.hpp:70) they are black bodies: throughput drops to 0 at the first
+    hit and Russian roulette sees q = 1 (Q13). Ambient (1,1,1) over an HDRI sky; camera {0, 0, 2.8 * gradations} -> -z."""
+    mats, geo = [], []
+    mats.append(_mat(albedo=[f32(0.1)] * 3, roughness=1.0)); geo.append(_sphere((0.0, -1001.0, 0.0), f32(1000.0) * f32(1000.0), 0))
+    mats.append(_mat(emission=[100.0, 100.0, 100.0])); geo.append(_sphere((0.0, 10.0, 0.0), 5.0, 1))
+    for i in range(gradations):
+        t = f32(i) / f32(gradations - 1)
+        x = f32(i * 2 - gradations) * f32(1.25) + f32(1.0)
+        mats.append(_mat(F0=[1, 1, 1], F80=[1, 1, 1], albedo=[0, 0, 0], roughness=t))
+        geo.append(_sphere((x, f32(i) * f32(0.1), 0.0), 1.0, len(mats) - 1))
+    return Scene(name="brdf_test", geometry=np.array(geo, dtype=SPHERE_DTYPE), material=np.array(mats, dtype=MATERIAL_DTYPE),
+                 camera=dict(eye=(0.0, 0.0, float(f32(gradations) * f32(2.8))), dir=(0, 0, -1), focal_length=50.0, exposure=1.0),
+                 ambient=(1.0, 1.0, 1.0), hdri=synthetic_hdri() if hdri is None else hdri)
+
+
 # ---- the reference's PCG (Random.hpp:5-29), vectorised: state_k = A^k s0 + C (A^k - 1)/(A - 1)  (mod 2^32)
 _A = np.uint32(747796405); _C = np.uint32(2891336453)
 

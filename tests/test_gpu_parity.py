@@ -340,6 +340,21 @@ def test_sky_hdri_scene(flags):
     r.close()
 
 
+@pytest.mark.parametrize("flags", [0, b2r.FLAG_FORCE_BVH, b2r.FLAG_REFERENCE_EXACT])
+def test_brdf_test_scene(flags):
+    """Scenes::BRDF_test as shipped (Application.cpp:123-217; albedo-0 spheres under the Lambertian closure: zero throughput, roulette
+    q = 1, Q13), ambient HDRI sky: bit-exact vs the oracle in canonical mode; in reference-exact mode vs the oracle's slot-exact mode,
+    which tests/test_oracle_ref_renderer.py pins to the reference's own renderer on this scene."""
+    sc = scenes.brdf_test_scene()
+    exact = bool(flags & b2r.FLAG_REFERENCE_EXACT)
+    r = b2r.Renderer(sc, 192, 112, max_bounces=8, buckets=5, flags=flags); r.Accumulate(10); assert r.Render()
+    o = oracle_for(sc, 192, 112, 8, 5, flags=oracle_py.ORC_SLOT_EXACT if exact else 0); o.accumulate(10)
+    g, ref = r.buckets_host(), o.buckets()
+    assert g.tobytes() == ref.tobytes() and r.framebuffer.tobytes() == o.render()[1].tobytes()
+    c = r.counters(); assert c["shaded_hits"] > 0 and c["shadow_rays"] > 0 and float(g.max()) > 0.0
+    r.close()
+
+
 def test_sky_loaded_from_a_radiance_file(tmp_path):
     """The sky as the reference gets it (Application.cpp:225-231): an .hdr file decoded by b2r_read_hdr (stb_image's Radiance decoder
     restated) and handed to b2r_upload_scene. RGBE keeps 8 mantissa bits, so the oracle is given the same decoded array: bit-exact."""

@@ -48,7 +48,8 @@ def test_live_bit_exact_and_schedule_independent(threads, monkeypatch):
     """fresh cases (not in the fixture), and the reference's tile fan-out on 1 and 4 threads gives the same bits"""
     monkeypatch.setenv("REF_THREADS", threads)
     cases = [("default", scenes.default_scene(), 112, 80, 8, 15, 0), ("random900", scenes.random_scene(900, light_every=30, seed=77), 64, 64, 16, 5, 5),
-             ("sky", scenes.bvh_test_scene(64, hdri=scenes.synthetic_hdri(32, 16, seed=9)), 48, 48, 4, 10, 0)]
+             ("sky", scenes.bvh_test_scene(64, hdri=scenes.synthetic_hdri(32, 16, seed=9)), 48, 48, 4, 10, 0),
+             ("brdf_test", scenes.brdf_test_scene(hdri=scenes.synthetic_hdri(24, 12, seed=2)), 64, 48, 8, 10, 0)]  # Application.cpp:123-217: albedo-0 spheres, q = 1 roulette
     for name, sc, w, h, mb, n, first in cases:
         r = oracle_py.ReferenceRenderer(sc, w, h, mb)
         if first:
