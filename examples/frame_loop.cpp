@@ -67,5 +67,14 @@ int main(int argc, char** argv) {
 	for (uint32_t f = 0; f < 5; f++) { renderer.Accumulate(); renderer.Render(); }
 	sum = 0; for (auto& p : renderer.framebuffer) sum += p.x + p.y + p.z;
 	std::printf("after a geometry drag: tree quality ratio %.4f, mean tonemapped value %.5f after %u accumulations\n", quality, sum / (3.0 * renderer.framebuffer.size()), renderer.accumulations);
+	// an edit that adds a sphere: same two rebuild lines, same call — SceneMoved() notices that the count changed and uploads the scene anew
+	scene.material.push_back(Material{}); scene.material.back().albedo = vec3{0.2f, 0.6f, 0.3f};
+	scene.geometry.push_back(Sphere{vec3{0.125f, 0.0625f, 0.375f}, 0.0625f * 0.0625f, (int32_t)scene.material.size() - 1});
+	scene.acceleration_structure = decltype(scene.acceleration_structure){scene.geometry};
+	scene.lighting_acceleration = decltype(scene.lighting_acceleration){scene.geometry, scene.material};
+	const float quality2 = renderer.SceneMoved(); renderer.ResetAccumulator();
+	for (uint32_t f = 0; f < 5; f++) { renderer.Accumulate(); renderer.Render(); }
+	sum = 0; for (auto& p : renderer.framebuffer) sum += p.x + p.y + p.z;
+	std::printf("after adding a sphere: %zu spheres, tree quality ratio %.4f, mean tonemapped value %.5f after %u accumulations\n", scene.geometry.size(), quality2, sum / (3.0 * renderer.framebuffer.size()), renderer.accumulations);
 	return 0;
 }

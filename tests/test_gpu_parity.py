@@ -278,6 +278,14 @@ def test_cpp_mirror_frame_loop(tmp_path):
     sc = scenes.default_scene(); sc["geometry"]["position"][1, 0] += np.float32(0.25); sc["geometry"]["position"][1, 1] += np.float32(0.125)
     r.SetScene(sc); r.ResetAccumulator(); r.Accumulate(5); assert r.Render()
     assert abs(float(e.group(2)) - float(r.framebuffer[..., :3].mean(dtype=np.float64))) < 1e-5
+    # ... and the edit that adds a sphere goes through SceneMoved()'s fallback to a full upload
+    a = re.search(r"after adding a sphere: (\d+) spheres, tree quality ratio ([0-9.]+), mean tonemapped value ([0-9.]+) after (\d+) accumulations", out)
+    assert a and int(a.group(1)) == 10 and float(a.group(2)) == 1.0 and int(a.group(4)) == 5
+    mat = np.zeros(1, scenes.MATERIAL_DTYPE); mat["albedo"] = (0.2, 0.6, 0.3)
+    sph = np.zeros(1, scenes.SPHERE_DTYPE); sph["position"] = (0.125, 0.0625, 0.375); sph["radius_sq"] = np.float32(0.0625) * np.float32(0.0625); sph["material_ID"] = 9
+    sc["material"] = np.concatenate([sc["material"], mat]); sc["geometry"] = np.concatenate([sc["geometry"], sph])
+    r.SetScene(sc); r.ResetAccumulator(); r.Accumulate(5); assert r.Render()
+    assert abs(float(a.group(3)) - float(r.framebuffer[..., :3].mean(dtype=np.float64))) < 1e-5
     r.close()
 
 
