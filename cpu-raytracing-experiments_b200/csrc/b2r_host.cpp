@@ -167,7 +167,6 @@ inline float surface(const b2r_bvh_node& n) {  // true half surface area: only u
 inline float int_as_float(int32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
 }  // namespace
 
-namespace {
 double wide_cost(const WideBvh& t) {
 	double sum = 0.0;
 	for (const WideNode& w : t.nodes) for (int k = 0; k < 4; k++) {
@@ -175,14 +174,6 @@ double wide_cost(const WideBvh& t) {
 		if (link >= 0) { const float4* s = reinterpret_cast<const float4*>(w.slot[k]); sum += static_cast<double>(slot_half_area(s[0], s[1])); }
 	}
 	return sum;
-}
-}  // namespace
-
-void refit_wide(WideBvh& tree, const float4* prims, const uint32_t* remap) {
-	float4* wide = reinterpret_cast<float4*>(tree.nodes.data());
-	for (size_t l = tree.level_first.size() - 1; l-- > 0;)
-		for (uint32_t i = tree.level_first[l]; i < tree.level_first[l + 1]; i++) for (int k = 0; k < 4; k++) refit_slot(wide, prims, remap, i, k);
-	tree.cost = wide_cost(tree);
 }
 
 bool match_prims_to_geometry(const b2r_sphere* prims, const b2r_sphere* geometry, uint32_t n, std::vector<uint32_t>& geom_of_prim) {

@@ -38,10 +38,8 @@ bool validate_reference_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, uint32_
 void build_traversal_tree(const b2r_sphere* prims_bvh_order, uint32_t n, std::vector<b2r_bvh_node>& nodes);
 // Collapse the binary tree 2 -> 4 wide and inline the leaf spheres.
 void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* prims, uint32_t n_prims, WideBvh& out);
-// Host twin of the GPU refit (k_refit_level, same shared routine refit_slot): keeps the topology, takes the spheres' new positions and
-// radii from `prims` ({c.xyz, r^2} in the same BVH leaf order) and recomputes every box bottom-up. Updates `cost`. The product refits
-// on the GPU (b2r_refit_scene); this one is what tests/hostcheck compares it with.
-void refit_wide(WideBvh& tree, const float4* prims, const uint32_t* remap);
+// Sum of the inner-slot half areas of a flattened tree (WideBvh::cost; k_tree_cost computes the same sum on the device after a refit).
+double wide_cost(const WideBvh& tree);
 // prims (BVH leaf order) as a permutation of geometry (original order), matched by value — the reference's BVH keeps reordered COPIES
 // of the spheres and no index map (BVH.hpp:201-205). geom_of_prim[i] = index into geometry of prims[i]; equal spheres are paired in
 // index order. Returns false when prims is not a permutation of geometry.

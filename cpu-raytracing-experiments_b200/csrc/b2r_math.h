@@ -1,6 +1,6 @@
 // b2r_math.h — scalar device math of the path tracer (RNG, camera, tangent frames, light sampling, tonemap).
 //
-// Every function is host+device so the CUDA kernels (b2r_kernels.cu) and the host-side scene code
+// Every function is host+device so the CUDA kernels (b2r_device.cuh) and the host-side scene code
 // (b2r_host.cpp) share one definition. Arithmetic contract (DESIGN.md "Numerics"): IEEE binary32,
 // round-to-nearest, no contraction — the library is compiled with `nvcc -fmad=false` / `g++ -ffp-contract=off`,
 // and a fused multiply-add appears only where fma_rn() is written out (the closest-hit sphere test, which is

@@ -2,7 +2,8 @@
 //
 // The sm_100a kernels (b2r_device.cuh) call these from their persistent loops. They are also plain C++ so that
 // tests/hostcheck can run the very same routines on the build box (which has no GPU) and compare them bit-for-bit
-// with the oracle; nothing in libb2r.so executes them on the CPU.
+// with the oracle; nothing in libb2r.so executes them on the CPU (the one exception is bookkeeping, not rendering: slot_half_area()
+// in the flattener's tree-cost sum).
 #pragma once
 #include <vector_types.h>
 #include <vector_functions.h>

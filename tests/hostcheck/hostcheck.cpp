@@ -10,6 +10,15 @@
 
 using namespace b2r;
 
+// Host twin of the GPU refit (k_refit_level runs the same shared routine, refit_slot in csrc/b2r_shade.h, one thread per slot and one
+// launch per level): levels deepest first, children always sit on a deeper level. Lives in the test harness — libb2r refits on the GPU only.
+static void refit_wide(WideBvh& tree, const float4* prims, const uint32_t* remap) {
+	float4* wide = reinterpret_cast<float4*>(tree.nodes.data());
+	for (size_t l = tree.level_first.size() - 1; l-- > 0;)
+		for (uint32_t i = tree.level_first[l]; i < tree.level_first[l + 1]; i++) for (int k = 0; k < 4; k++) refit_slot(wide, prims, remap, i, k);
+	tree.cost = wide_cost(tree);
+}
+
 extern "C" {
 
 // One sample (`acc`) for every pixel: rad_out[3][npix] (tile order). counters: ext rays, shadow rays, hits, term, dropped.
