@@ -5,6 +5,7 @@
 #include "b2r_shade.h"
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <thread>
 #include <cmath>
@@ -366,24 +367,52 @@ struct TraversalBuilder {
 	void set(uint32_t node, const TBox& b, uint32_t first, uint32_t count) {
 		b2r_bvh_node nd; for (int k = 0; k < 3; k++) { nd.min_bound[k] = b.lo[k]; nd.max_bound[k] = b.hi[k]; } nd.first_id = first; nd.prim_count = count; nodes[node] = nd;
 	}
-	// splits [begin, end) of node `node`; returns the split position and writes the two children at `region`
-	uint32_t split(uint32_t node, uint32_t begin, uint32_t end, uint32_t region) {
+	// runs fn(chunk, b, e) over `workers` equal chunks of [begin, end), chunk 0 on the calling thread
+	template <class F> static void chunks(uint32_t begin, uint32_t end, unsigned workers, F&& fn) {
+		const uint32_t count = end - begin, step = (count + workers - 1) / workers;
+		std::vector<std::thread> pool;
+		for (unsigned w = 1; w < workers; w++) { const uint32_t b = begin + std::min(count, w * step), e = begin + std::min(count, (w + 1) * step); if (b < e) pool.emplace_back([&fn, w, b, e] { fn(w, b, e); }); }
+		fn(0u, begin, begin + std::min(count, step));
+		for (auto& t : pool) t.join();
+	}
+	struct Bins { TBox bb[3][kBins]; uint32_t bc[3][kBins]; };
+	// splits [begin, end) of node `node`; returns the split position and writes the two children at `region`. `workers` > 1: the
+	// passes over a large node (the top of the tree is the serial part of the build) are shared out in chunks; every quantity merged
+	// across chunks is a min, a max or an integer count, and the degenerate split is made on sorted ids, so the tree is a function of
+	// the SET of spheres in the node — not of their order, of the partition algorithm or of the number of threads.
+	uint32_t split(uint32_t node, uint32_t begin, uint32_t end, uint32_t region, unsigned workers) {
 		const uint32_t count = end - begin;
+		if (count < 32768u) workers = 1;
 		float clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-		for (uint32_t i = begin; i < end; i++) for (int k = 0; k < 3; k++) { const float c = cen[3 * static_cast<size_t>(ids[i]) + k]; clo[k] = fminf(clo[k], c); chi[k] = fmaxf(chi[k], c); }
-		// binned SAH per axis; the three axes of a large node are evaluated by three threads (the top of the tree is the serial part)
-		struct AxisBest { float cost = FLT_MAX; int bin = 0; };
-		AxisBest per_axis[3];
-		auto eval_axis = [&](int axis) {
-			const float ext = chi[axis] - clo[axis];
-			if (!(ext > 0.0f)) return;
-			TBox bb[kBins]; uint32_t bc[kBins];
-			for (int q = 0; q < kBins; q++) { bb[q] = tbox_empty(); bc[q] = 0; }
-			const float scale = kBins / ext;
-			for (uint32_t i = begin; i < end; i++) {
-				int q = static_cast<int>((cen[3 * static_cast<size_t>(ids[i]) + axis] - clo[axis]) * scale); if (q >= kBins) q = kBins - 1;
-				tbox_grow(bb[q], box[ids[i]]); bc[q]++;
-			}
+		{
+			std::vector<std::array<float, 6>> part(workers, std::array<float, 6>{FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX});
+			chunks(begin, end, workers, [&](unsigned w, uint32_t b, uint32_t e) {
+				std::array<float, 6> a = part[w];
+				for (uint32_t i = b; i < e; i++) for (int k = 0; k < 3; k++) { const float c = cen[3 * static_cast<size_t>(ids[i]) + k]; a[k] = fminf(a[k], c); a[3 + k] = fmaxf(a[3 + k], c); }
+				part[w] = a; });
+			for (const auto& a : part) for (int k = 0; k < 3; k++) { clo[k] = fminf(clo[k], a[k]); chi[k] = fmaxf(chi[k], a[3 + k]); }
+		}
+		// binned SAH: one pass fills the bins of all three axes
+		float scale[3]; bool usable[3];
+		for (int axis = 0; axis < 3; axis++) { const float ext = chi[axis] - clo[axis]; usable[axis] = ext > 0.0f; scale[axis] = usable[axis] ? kBins / ext : 0.0f; }
+		std::vector<Bins> bins(workers);
+		chunks(begin, end, workers, [&](unsigned w, uint32_t b, uint32_t e) {
+			Bins& bn = bins[w];
+			for (int axis = 0; axis < 3; axis++) for (int q = 0; q < kBins; q++) { bn.bb[axis][q] = tbox_empty(); bn.bc[axis][q] = 0; }
+			for (uint32_t i = b; i < e; i++) {
+				const uint32_t id = ids[i]; const TBox& bx = box[id];
+				for (int axis = 0; axis < 3; axis++) {
+					if (!usable[axis]) continue;
+					int q = static_cast<int>((cen[3 * static_cast<size_t>(id) + axis] - clo[axis]) * scale[axis]); if (q >= kBins) q = kBins - 1;
+					tbox_grow(bn.bb[axis][q], bx); bn.bc[axis][q]++;
+				}
+			} });
+		Bins& all = bins[0];
+		for (unsigned w = 1; w < workers; w++) for (int axis = 0; axis < 3; axis++) for (int q = 0; q < kBins; q++) { tbox_grow(all.bb[axis][q], bins[w].bb[axis][q]); all.bc[axis][q] += bins[w].bc[axis][q]; }
+		int best_axis = -1, best_bin = 0; float best_cost = FLT_MAX;
+		for (int axis = 0; axis < 3; axis++) {  // first axis wins ties
+			if (!usable[axis]) continue;
+			const TBox* bb = all.bb[axis]; const uint32_t* bc = all.bc[axis];
 			float right_area[kBins]; uint32_t right_cnt[kBins];
 			TBox acc = tbox_empty(); uint32_t cnt = 0;
 			for (int q = kBins - 1; q > 0; q--) { tbox_grow(acc, bb[q]); cnt += bc[q]; right_area[q] = cnt ? tbox_area(acc) : 0.0f; right_cnt[q] = cnt; }
@@ -392,39 +421,48 @@ struct TraversalBuilder {
 				tbox_grow(acc, bb[q]); cnt += bc[q];
 				if (cnt == 0 || right_cnt[q + 1] == 0) continue;
 				const float cost = tbox_area(acc) * cnt + right_area[q + 1] * right_cnt[q + 1];
-				if (cost < per_axis[axis].cost) { per_axis[axis].cost = cost; per_axis[axis].bin = q; }
+				if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = q; }
 			}
-		};
-		if (count >= 65536u) { std::thread t1(eval_axis, 1), t2(eval_axis, 2); eval_axis(0); t1.join(); t2.join(); }
-		else { eval_axis(0); eval_axis(1); eval_axis(2); }
-		int best_axis = -1, best_bin = 0; float best_cost = FLT_MAX;
-		for (int axis = 0; axis < 3; axis++) if (per_axis[axis].cost < best_cost) { best_cost = per_axis[axis].cost; best_axis = axis; best_bin = per_axis[axis].bin; }  // first axis wins ties, as the serial loop did
-		uint32_t mid;
-		if (best_axis < 0) mid = begin + count / 2;  // all centroids coincide: split the list in half
-		else {
-			const float scale = kBins / (chi[best_axis] - clo[best_axis]);
-			auto it = std::partition(ids.begin() + begin, ids.begin() + end, [&](uint32_t id) {
-				int q = static_cast<int>((cen[3 * static_cast<size_t>(id) + best_axis] - clo[best_axis]) * scale); if (q >= kBins) q = kBins - 1;
-				return q <= best_bin; });
-			mid = static_cast<uint32_t>(it - ids.begin());
-			if (mid == begin || mid == end) mid = begin + count / 2;
+		}
+		uint32_t mid = begin;
+		if (best_axis >= 0) {
+			const float sc = scale[best_axis], lo = clo[best_axis];
+			auto goes_left = [&](uint32_t id) { int q = static_cast<int>((cen[3 * static_cast<size_t>(id) + best_axis] - lo) * sc); if (q >= kBins) q = kBins - 1; return q <= best_bin; };
+			if (workers == 1) mid = static_cast<uint32_t>(std::partition(ids.begin() + begin, ids.begin() + end, goes_left) - ids.begin());
+			else {  // chunk-wise partition into a scratch copy: left parts, then right parts, in chunk order
+				std::vector<uint32_t> scratch(ids.begin() + begin, ids.begin() + end), n_left(workers, 0u), first(workers, 0u), last(workers, 0u);
+				chunks(begin, end, workers, [&](unsigned w, uint32_t b, uint32_t e) { uint32_t c = 0; for (uint32_t i = b; i < e; i++) c += goes_left(scratch[i - begin]) ? 1u : 0u; n_left[w] = c; first[w] = b; last[w] = e; });
+				uint32_t total_left = 0; for (unsigned w = 0; w < workers; w++) total_left += n_left[w];
+				std::vector<uint32_t> at_left(workers), at_right(workers);
+				uint32_t l = begin, r = begin + total_left;
+				for (unsigned w = 0; w < workers; w++) { at_left[w] = l; at_right[w] = r; l += n_left[w]; r += (last[w] - first[w]) - n_left[w]; }
+				chunks(begin, end, workers, [&](unsigned w, uint32_t b, uint32_t e) { uint32_t l2 = at_left[w], r2 = at_right[w]; for (uint32_t i = b; i < e; i++) { const uint32_t id = scratch[i - begin]; if (goes_left(id)) ids[l2++] = id; else ids[r2++] = id; } });
+				mid = begin + total_left;
+			}
 		}
 		TBox l = tbox_empty(), r = tbox_empty();
-		for (uint32_t i = begin; i < mid; i++) tbox_grow(l, box[ids[i]]);
-		for (uint32_t i = mid; i < end; i++) tbox_grow(r, box[ids[i]]);
+		if (best_axis < 0 || mid == begin || mid == end) {  // all centroids coincide: halve the list, on sorted ids so that the result does not depend on the order
+			std::sort(ids.begin() + begin, ids.begin() + end);
+			mid = begin + count / 2;
+			for (uint32_t i = begin; i < mid; i++) tbox_grow(l, box[ids[i]]);
+			for (uint32_t i = mid; i < end; i++) tbox_grow(r, box[ids[i]]);
+		} else {  // the children's boxes are the unions of the bins on either side of the split (the same min / max over the same boxes)
+			for (int q = 0; q <= best_bin; q++) tbox_grow(l, all.bb[best_axis][q]);
+			for (int q = best_bin + 1; q < kBins; q++) tbox_grow(r, all.bb[best_axis][q]);
+		}
 		set(region, l, 0, 0); set(region + 1, r, 0, 0);
 		nodes[node].first_id = region; nodes[node].prim_count = 0;
 		return mid;
 	}
 	struct Job { uint32_t node, begin, end, region; };
-	void build(Job root, std::vector<Job>* spill, uint32_t spill_above) {
+	void build(Job root, std::vector<Job>* spill, uint32_t spill_above, unsigned workers) {
 		std::vector<Job> todo; todo.push_back(root);
 		while (!todo.empty()) {
 			const Job j = todo.back(); todo.pop_back();
 			const uint32_t count = j.end - j.begin;
 			if (count == 1) { nodes[j.node].first_id = ids[j.begin]; nodes[j.node].prim_count = 1; continue; }
 			if (spill && count <= spill_above && count > 1 && j.node != root.node) { spill->push_back(j); continue; }  // handed to the thread pool
-			const uint32_t mid = split(j.node, j.begin, j.end, j.region);
+			const uint32_t mid = split(j.node, j.begin, j.end, j.region, workers);
 			const uint32_t left = mid - j.begin;
 			todo.push_back({j.region, j.begin, mid, j.region + 2u});
 			todo.push_back({j.region + 1u, mid, j.end, j.region + 2u + (2u * left - 2u)});
@@ -448,13 +486,13 @@ void build_traversal_tree(const b2r_sphere* prims, uint32_t n, std::vector<b2r_b
 	tb.set(0, root, 0, 0);
 	const unsigned hw = std::thread::hardware_concurrency();
 	const unsigned threads = n < 20000u ? 1u : (hw ? (hw > 32u ? 32u : hw) : 1u);
-	if (threads <= 1) { tb.build({0u, 0u, n, 1u}, nullptr, 0); return; }
+	if (threads <= 1) { tb.build({0u, 0u, n, 1u}, nullptr, 0, 1u); return; }
 	// the top of the tree on this thread until the pieces are small enough to share out, then one piece at a time per worker
 	std::vector<TraversalBuilder::Job> pieces;
-	tb.build({0u, 0u, n, 1u}, &pieces, n / (threads * 4u) + 1u);
+	tb.build({0u, 0u, n, 1u}, &pieces, n / (threads * 4u) + 1u, threads);
 	std::sort(pieces.begin(), pieces.end(), [](const TraversalBuilder::Job& a, const TraversalBuilder::Job& b) { return a.end - a.begin > b.end - b.begin; });
 	std::atomic<size_t> next{0};
-	auto work = [&] { for (;;) { const size_t k = next.fetch_add(1); if (k >= pieces.size()) break; tb.build(pieces[k], nullptr, 0); } };
+	auto work = [&] { for (;;) { const size_t k = next.fetch_add(1); if (k >= pieces.size()) break; tb.build(pieces[k], nullptr, 0, 1u); } };
 	std::vector<std::thread> pool;
 	for (unsigned t = 1; t < threads; t++) pool.emplace_back(work);
 	work();
