@@ -1,6 +1,7 @@
 // b2r_host.cpp — host-side scene preparation (no CUDA): the reference's SAH sweep BVH with bit-identical node and
 // leaf order (BVH.hpp:90-206), the 4-wide flattening for the GPU, the light list (Scene.hpp:12-16) and the camera
-// set-up (Camera.hpp:21-32,47-50). The reference builds its BVH on one host thread as well; only the flattening is new.
+// set-up (Camera.hpp:21-32,47-50). The reference builds its BVH on one host thread; here the same algorithm runs on all host cores with
+// the node order of the serial one (every index follows from the subtree sizes), and a second tree is built for traversal.
 #include "b2r_host.h"
 #include "b2r_shade.h"
 
@@ -47,16 +48,12 @@ inline b2r_bvh_node to_node(const Box& b, uint32_t first, uint32_t count) {
 	return n;
 }
 
-struct BuildJob { uint32_t node, begin, count; };
-
 }  // namespace
 
 void build_reference_bvh(const b2r_sphere* geometry, uint32_t n, std::vector<b2r_bvh_node>& nodes,
                          std::vector<b2r_sphere>& prims, std::vector<uint32_t>& prim_ids) {
 	nodes.clear(); prims.clear(); prim_ids.clear();
 	if (n == 0) { nodes.push_back(to_node(void_box(), 0, 0)); return; }
-	nodes.reserve(2u * static_cast<size_t>(n));
-
 	// per-primitive boxes (Sphere::bounds, Primitives.hpp:13-16) and centroids ((max+min)*0.5, BVH.hpp:55-57)
 	std::vector<Box> box(n);
 	std::vector<float> centroid[3];
@@ -71,79 +68,127 @@ void build_reference_bvh(const b2r_sphere* geometry, uint32_t n, std::vector<b2r
 	}
 	// three index lists ordered by centroid (BVH.hpp:118-122). The reference's std::ranges::sort leaves tie order
 	// implementation-defined (Q19); ties are broken by the lower original index here (== MSVC for n <= 32).
+	const unsigned hw = std::thread::hardware_concurrency();
+	const unsigned threads = n < 20000u ? 1u : (hw ? (hw > 32u ? 32u : hw) : 1u);
 	std::vector<uint32_t> order[3];
-	for (int k = 0; k < 3; k++) {
-		order[k].resize(n);
-		std::iota(order[k].begin(), order[k].end(), 0u);
-		const float* key = centroid[k].data();
-		std::stable_sort(order[k].begin(), order[k].end(), [key](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+	{
+		auto sort_axis = [&](int k) {
+			order[k].resize(n);
+			std::iota(order[k].begin(), order[k].end(), 0u);
+			const float* key = centroid[k].data();
+			std::stable_sort(order[k].begin(), order[k].end(), [key](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+		};
+		if (threads > 1) { std::thread t1(sort_axis, 1), t2(sort_axis, 2); sort_axis(0); t1.join(); t2.join(); }
+		else for (int k = 0; k < 3; k++) sort_axis(k);
 	}
 
 	Box root = void_box();
 	for (uint32_t i = 0; i < n; i++) grow(root, box[i]);  // BVH.hpp:125
-	nodes.push_back(to_node(root, 0, 0));
+	// The reference numbers its nodes in the order it creates them: a node's child pair when the node is taken off the work stack,
+	// smaller range first (BVH.hpp:190-197). A subtree over c spheres creates exactly 2c-2 nodes, so every pair's index follows from
+	// the sizes alone — pair(smaller range) = pair + 2, pair(larger range) = pair + 2 + (2*c_smaller - 2) — and disjoint subtrees can
+	// be built by different threads into the pre-sized array with the node order of the serial algorithm, bit for bit.
+	nodes.assign(2u * static_cast<size_t>(n) - 1u, to_node(void_box(), 0, 0));
+	nodes[0] = to_node(root, 0, 0);
 
-	std::vector<float> suffix_cost(n);     // accum_cost: SAH cost of the right part starting at i (BVH.hpp:154)
+	std::vector<float> suffix_cost[3];     // accum_cost: SAH cost of the right part starting at i (BVH.hpp:154); one array per axis
+	for (auto& v : suffix_cost) v.resize(n);
 	std::vector<uint8_t> goes_left(n);
-	std::vector<uint32_t> scratch(n);
-	std::vector<BuildJob> todo;
-	todo.push_back({0u, 0u, n});
-	while (!todo.empty()) {
-		const BuildJob job = todo.back(); todo.pop_back();
-		if (job.count <= 1) {  // leaf, always one sphere (BVH.hpp:133-137)
-			nodes[job.node].first_id = job.begin; nodes[job.node].prim_count = job.count;
-			continue;
-		}
-		const uint32_t begin = job.begin, end = job.begin + job.count;
-		const uint32_t pair = static_cast<uint32_t>(nodes.size());
-		nodes[job.node].first_id = pair;
-		Box here; for (int k = 0; k < 3; k++) { here.lo[k] = nodes[job.node].min_bound[k]; here.hi[k] = nodes[job.node].max_bound[k]; }
+	std::vector<uint32_t> scratch(n), scratch2(threads > 1 ? n : 0u);  // windows [begin, end) of a job: disjoint between jobs
+	struct Job { uint32_t node, begin, count, pair; };
+	auto process = [&](Job first, std::vector<Job>* spill, uint32_t spill_above) {
+		std::vector<Job> todo;
+		todo.push_back(first);
+		while (!todo.empty()) {
+			const Job job = todo.back(); todo.pop_back();
+			if (job.count <= 1) {  // leaf, always one sphere (BVH.hpp:133-137)
+				nodes[job.node].first_id = job.begin; nodes[job.node].prim_count = job.count;
+				continue;
+			}
+			if (spill && job.count <= spill_above && job.node != first.node) { spill->push_back(job); continue; }  // a piece for the thread pool
+			const uint32_t begin = job.begin, end = job.begin + job.count;
+			const uint32_t pair = job.pair;
+			nodes[job.node].first_id = pair;
+			Box here; for (int k = 0; k < 3; k++) { here.lo[k] = nodes[job.node].min_bound[k]; here.hi[k] = nodes[job.node].max_bound[k]; }
 
-		// fallback split = median on the widest axis, at the "do not split" cost area*(count-1) (BVH.hpp:144, :80-82)
-		uint32_t cut = begin + (job.count + 1) / 2; int cut_axis = widest_axis(here);
-		float cut_cost = sah_measure(here) * (static_cast<float>(job.count) - 1.0f);
-		for (int k = 0; k < 3; k++) {
-			const uint32_t* ids = order[k].data();
-			// right-to-left sweep. The reference's chunked early exit degenerates into one full sweep (Q18), and its
-			// `first_right` guard can never cut the left sweep short, so neither appears here.
-			Box acc = void_box();
-			for (uint32_t i = end - 1; i > begin; --i) {
-				grow(acc, box[ids[i]]);
-				suffix_cost[i] = sah_measure(acc) * static_cast<float>(end - i);
+			// fallback split = median on the widest axis, at the "do not split" cost area*(count-1) (BVH.hpp:144, :80-82)
+			uint32_t cut = begin + (job.count + 1) / 2; int cut_axis = widest_axis(here);
+			float cut_cost = sah_measure(here) * (static_cast<float>(job.count) - 1.0f);
+			// Per axis: right-to-left sweep (the reference's chunked early exit degenerates into one full sweep, Q18, and its `first_right`
+			// guard can never cut the left sweep short), then the left-to-right sweep (BVH.hpp:163-170), which stops once the left cost
+			// alone exceeds the bound. The reference runs the axes one after the other against a shrinking bound; the left cost never
+			// decreases along a sweep, so nothing behind a stop could have improved the bound, and the result is the first strict minimum
+			// in (axis, position) order — which is what merging three independent sweeps against the INITIAL bound gives as well.
+			struct AxisCut { float cost; uint32_t cut; bool found; };
+			const float bound0 = cut_cost;
+			auto sweep = [&](int k) {
+				const uint32_t* ids = order[k].data(); float* suffix = suffix_cost[k].data();
+				AxisCut best{bound0, 0u, false};
+				Box acc = void_box();
+				for (uint32_t i = end - 1; i > begin; --i) {
+					grow(acc, box[ids[i]]);
+					suffix[i] = sah_measure(acc) * static_cast<float>(end - i);
+				}
+				acc = void_box();
+				for (uint32_t i = begin; i + 1 < end; ++i) {
+					grow(acc, box[ids[i]]);
+					const float left = sah_measure(acc) * static_cast<float>(i + 1 - begin);
+					if (left > best.cost) break;
+					const float total = left + suffix[i + 1];
+					if (total < best.cost) { best.cost = total; best.cut = i + 1; best.found = true; }
+				}
+				return best;
+			};
+			AxisCut per_axis[3];
+			const bool wide_node = spill != nullptr && job.count >= 65536u;  // only the serial top of the tree fans out per node
+			if (wide_node) { std::thread t1([&] { per_axis[1] = sweep(1); }), t2([&] { per_axis[2] = sweep(2); }); per_axis[0] = sweep(0); t1.join(); t2.join(); }
+			else for (int k = 0; k < 3; k++) per_axis[k] = sweep(k);
+			for (int k = 0; k < 3; k++) if (per_axis[k].found && per_axis[k].cost < cut_cost) { cut = per_axis[k].cut; cut_axis = k; cut_cost = per_axis[k].cost; }
+			// keep the other two lists consistent with the chosen cut, preserving their order (BVH.hpp:173-184), and take the child boxes
+			// (BVH.hpp:109-113,188: a min / max over the spheres of each side — read here from the list that was cut, whose two sides are
+			// already in place; the reference reads list 0, the same two sets). On the serial top of the tree the three passes run side by side.
+			Box part[2] = {void_box(), void_box()};
+			{
+				const uint32_t* ids = order[cut_axis].data();
+				for (uint32_t i = begin; i < cut; ++i) goes_left[ids[i]] = 1;
+				for (uint32_t i = cut; i < end; ++i) goes_left[ids[i]] = 0;
+				auto regroup = [&](int k, uint32_t* spare) {  // spare: a window of (end - begin) entries nobody else uses
+					uint32_t* a = order[k].data();
+					uint32_t l = begin, r = 0;
+					for (uint32_t i = begin; i < end; ++i) { const uint32_t id = a[i]; if (goes_left[id]) a[l++] = id; else spare[r++] = id; }
+					std::memcpy(a + l, spare, static_cast<size_t>(r) * sizeof(uint32_t));
+				};
+				auto child_boxes = [&] {
+					for (uint32_t i = begin; i < cut; ++i) grow(part[0], box[ids[i]]);
+					for (uint32_t i = cut; i < end; ++i) grow(part[1], box[ids[i]]);
+				};
+				const int k1 = cut_axis == 0 ? 1 : 0, k2 = cut_axis == 2 ? 1 : 2;
+				if (wide_node) { std::thread t1(regroup, k1, scratch.data() + begin), t2(regroup, k2, scratch2.data() + begin); child_boxes(); t1.join(); t2.join(); }
+				else { regroup(k1, scratch.data() + begin); regroup(k2, scratch.data() + begin); child_boxes(); }
 			}
-			acc = void_box();
-			for (uint32_t i = begin; i + 1 < end; ++i) {  // left-to-right sweep (BVH.hpp:163-170)
-				grow(acc, box[ids[i]]);
-				const float left = sah_measure(acc) * static_cast<float>(i + 1 - begin);
-				if (left > cut_cost) break;
-				const float total = left + suffix_cost[i + 1];
-				if (total < cut_cost) { cut = i + 1; cut_axis = k; cut_cost = total; }
-			}
+			const uint32_t first_is_right = sah_measure(part[0]) < sah_measure(part[1]) ? 1u : 0u;
+			nodes[pair] = to_node(part[first_is_right], 0, 0);
+			nodes[pair + 1u] = to_node(part[1 - first_is_right], 0, 0);
+			const uint32_t pb[2] = {begin, cut}, pc[2] = {cut - begin, end - cut};
+			const uint32_t bigger = pc[0] < pc[1] ? 1u : 0u;  // index of the larger range
+			const uint32_t smaller = 1u - bigger;
+			const uint32_t pair_small = pair + 2u, pair_big = pair + 2u + (2u * pc[smaller] - 2u);
+			// range r lives in node pair + (r == first_is_right ? 0 : 1)
+			todo.push_back({pair + (bigger ^ first_is_right), pb[bigger], pc[bigger], pair_big});
+			todo.push_back({pair + (smaller ^ first_is_right), pb[smaller], pc[smaller], pair_small});
 		}
-		{  // keep the other two lists consistent with the chosen cut, preserving their order (BVH.hpp:173-184)
-			const uint32_t* ids = order[cut_axis].data();
-			for (uint32_t i = begin; i < cut; ++i) goes_left[ids[i]] = 1;
-			for (uint32_t i = cut; i < end; ++i) goes_left[ids[i]] = 0;
-			for (int k = 0; k < 3; k++) {
-				if (k == cut_axis) continue;
-				uint32_t* a = order[k].data();
-				uint32_t l = begin, r = 0;
-				for (uint32_t i = begin; i < end; ++i) { const uint32_t id = a[i]; if (goes_left[id]) a[l++] = id; else scratch[r++] = id; }
-				std::memcpy(a + l, scratch.data(), static_cast<size_t>(r) * sizeof(uint32_t));
-			}
-		}
-		// child boxes from list 0 (BVH.hpp:109-113,188); larger-measure child stored first, smaller range built first (:190-197)
-		Box part[2] = {void_box(), void_box()};
-		for (uint32_t i = begin; i < cut; ++i) grow(part[0], box[order[0][i]]);
-		for (uint32_t i = cut; i < end; ++i) grow(part[1], box[order[0][i]]);
-		const uint32_t first_is_right = sah_measure(part[0]) < sah_measure(part[1]) ? 1u : 0u;
-		nodes.push_back(to_node(part[first_is_right], 0, 0));
-		nodes.push_back(to_node(part[1 - first_is_right], 0, 0));
-		const uint32_t pb[2] = {begin, cut}, pc[2] = {cut - begin, end - cut};
-		const uint32_t bigger = pc[0] < pc[1] ? 1u : 0u;  // index of the larger range
-		// range r lives in node pair + (r == first_is_right ? 0 : 1)
-		todo.push_back({pair + (bigger ^ first_is_right), pb[bigger], pc[bigger]});
-		todo.push_back({pair + ((1 - bigger) ^ first_is_right), pb[1 - bigger], pc[1 - bigger]});
+	};
+	if (threads <= 1) process({0u, 0u, n, 1u}, nullptr, 0u);
+	else {
+		std::vector<Job> pieces;
+		process({0u, 0u, n, 1u}, &pieces, n / (threads * 4u) + 1u);
+		std::sort(pieces.begin(), pieces.end(), [](const Job& a, const Job& b) { return a.count > b.count; });
+		std::atomic<size_t> next{0};
+		auto work = [&] { for (;;) { const size_t k = next.fetch_add(1); if (k >= pieces.size()) break; process(pieces[k], nullptr, 0u); } };
+		std::vector<std::thread> pool;
+		for (unsigned t = 1; t < threads; t++) pool.emplace_back(work);
+		work();
+		for (auto& t : pool) t.join();
 	}
 	prims.resize(n); prim_ids.resize(n);
 	for (uint32_t i = 0; i < n; i++) { prim_ids[i] = order[0][i]; prims[i] = geometry[order[0][i]]; }  // BVH.hpp:201-205

@@ -31,6 +31,24 @@ def test_bvh_ties_are_stable():
     assert nodes.tobytes() == o.bvh()[0].tobytes() and np.array_equal(ids, o.bvh()[2])
 
 
+def test_bvh_builder_on_all_cores_equals_the_serial_algorithm():
+    """From 20 000 spheres on b2r_bvh_build fans out: the three centroid sorts and the passes over a large node run side by side, and
+    subtrees are built by a thread pool into node ranges fixed by the subtree sizes. The oracle's builder is the serial restatement of
+    BVH.hpp:90-206: same nodes, same leaf order — also with heavily tied centroids (quantised positions, equal radii), where the
+    merge of the three independent axis sweeps has to reproduce the reference's first-strict-minimum rule."""
+    rs = np.random.RandomState(8)
+    g = np.ascontiguousarray(scenes.random_scene(30000, light_every=10)["geometry"])
+    tied = g.copy(); tied["position"][:, :2] = np.floor(rs.uniform(-100, 100, (len(g), 2)) / 10).astype(np.float32); tied["radius_sq"] = 1.0
+    for geo in (g, tied):
+        nodes, prims, ids = b2r.build_bvh(geo)
+        sc = scenes.Scene(geometry=geo, material=scenes.random_scene(16)["material"], camera=scenes.default_scene()["camera"], ambient=(0, 0, 0), hdri=None)
+        o = oracle_py.Oracle(16, 16); o.set_scene(sc)
+        on, op, oi = o.bvh()
+        assert nodes.tobytes() == on.tobytes() and np.array_equal(ids, oi)
+        again = b2r.build_bvh(geo)
+        assert again[0].tobytes() == nodes.tobytes() and np.array_equal(again[2], ids)     # schedule-independent
+
+
 def test_lights_and_camera_match_oracle():
     for sc in (scenes.default_scene(), scenes.random_scene(3000)):
         o = oracle_py.Oracle(1280, 720); o.set_scene(sc)
