@@ -174,3 +174,35 @@ def test_hdr_reader_rejects_what_stb_rejects(tmp_path):
     assert rc(_hdr_file(tmp_path / "t.hdr", 8, 2, ok_line), C.c_void_p(two.ctypes.data)) == b2r.ERR_ARG        # second scanline missing
     big = np.zeros((2, 3, 4), np.float32)
     assert rc(_hdr_file(tmp_path / "s.hdr", 3, 2, [1] * 20), C.c_void_p(big.ctypes.data)) == b2r.ERR_ARG        # flat file four bytes short
+
+
+def test_hdr_reader_fuzz_against_an_independent_encoder(tmp_path):
+    """Random RGBE images encoded by a small encoder of this test (random mixture of runs of 1..127 and literal spans of 1..128, per
+    component, as the format allows — not only the run/literal choices b2r_write_hdr makes), decoded by b2r_read_hdr."""
+    rs = np.random.RandomState(31)
+    for trial in range(25):
+        w, h = int(rs.randint(8, 300)), int(rs.randint(1, 6))
+        rgbe = rs.randint(0, 256, (h, w, 4)).astype(np.uint8)
+        for y in range(h):                                            # plant long constant stretches so that runs are worth encoding
+            for c in range(4):
+                x = 0
+                while x < w:
+                    n = int(rs.randint(1, 60))
+                    if rs.rand() < 0.5: rgbe[y, x:x + n, c] = rgbe[y, x, c]
+                    x += n
+        rgbe[..., 3][rs.rand(h, w) < 0.05] = 0                        # some black pixels (e = 0)
+        body = bytearray()
+        for y in range(h):
+            body += bytes([2, 2, w >> 8, w & 255])
+            for c in range(4):
+                row = rgbe[y, :, c]; x = 0
+                while x < w:
+                    run = 1
+                    while x + run < w and run < 127 and row[x + run] == row[x]: run += 1
+                    if run >= 2 and rs.rand() < 0.8:
+                        n = int(rs.randint(1, run + 1)); body += bytes([128 + n, int(row[x])]); x += n
+                    else:
+                        n = int(rs.randint(1, min(128, w - x) + 1)); body += bytes([n]) + row[x:x + n].tobytes(); x += n
+        got = b2r.read_hdr(_hdr_file(tmp_path / f"z{trial}.hdr", w, h, body))
+        want = (rgbe[..., :3] * np.ldexp(1.0, rgbe[..., 3].astype(np.int32) - 136)[..., None] * (rgbe[..., 3:] > 0)).astype(np.float32)
+        assert got[..., :3].tobytes() == want.tobytes() and np.all(got[..., 3] == 1.0)

@@ -151,3 +151,32 @@ def test_match_pairs_equal_spheres(hostcheck):
     assert sorted(m.tolist()) == list(range(64))
     for f in ("position", "radius_sq", "material_ID"):
         assert np.array_equal(geo[m][f], prims[f])
+
+
+def test_refit_fuzz_duplicates_and_random_orders(hostcheck):
+    """Randomised: scenes with duplicated spheres, a random new leaf order, spheres moved; value matching + remap + refit must still give
+    brute-force hits over the new order (indices included, modulo which of two identical twins a tie names) and a valid tree."""
+    rs = np.random.RandomState(99)
+    for trial in range(12):
+        n = int(rs.randint(2, 400))
+        geo = np.ascontiguousarray(scenes.random_scene(max(n, 2), light_every=5, seed=1000 + trial)["geometry"])
+        for _ in range(int(rs.randint(0, 4))):                       # identical twins
+            a, b = rs.randint(0, n, 2); geo[a] = geo[b]
+        _, prims, ids = b2r.build_bvh(geo)
+        geo2 = moved(geo, rs, far=int(rs.randint(0, 3)))
+        for a in range(n):                                            # twins stay twins after the move
+            for b in range(a):
+                if all(np.array_equal(geo[a][k], geo[b][k]) for k in ("position", "radius_sq", "material_ID")): geo2[a] = geo2[b]
+        perm = rs.permutation(n).astype(np.uint32)                    # any order, not just the builder's
+        prims2 = np.ascontiguousarray(geo2[perm])
+        m_old = np.zeros(n, np.uint32); m_new = np.zeros(n, np.uint32)
+        assert hostcheck.hc_match(vp(prims), vp(geo), n, vp(m_old)) == 1 and hostcheck.hc_match(vp(prims2), vp(geo2), n, vp(m_new)) == 1
+        assert sorted(m_old.tolist()) == list(range(n)) and sorted(m_new.tolist()) == list(range(n))
+        prim_of_geom = np.zeros(n, np.uint32); prim_of_geom[m_new] = np.arange(n, dtype=np.uint32)
+        remap = np.ascontiguousarray(prim_of_geom[m_old])
+        rays = camera_rays(400, rs, prims)
+        wide, _, tfar, prim = refit(hostcheck, prims, prims2, rays=rays, remap=remap)
+        check_contains(wide, prims2)
+        bt = np.zeros(len(rays), np.float32); bp = np.zeros(len(rays), np.int32)
+        hostcheck.hc_closest_brute(vp(prims2), n, vp(rays), len(rays), vp(bt), vp(bp))
+        assert bt.tobytes() == tfar.tobytes() and np.array_equal(bp, prim)
