@@ -32,8 +32,11 @@ struct View {  // Camera.hpp:47-59
 		const b2r_host::quat b(orient.w, -orient.x, -orient.y, -orient.z);
 		b2r_host::quat p(a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
 		                 a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z, a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x);
-		const float inv = 1.0f / std::sqrt(p.w * p.w + p.x * p.x + p.y * p.y + p.z * p.z);
-		orient = b2r_host::quat(p.w * inv, -p.x * inv, -p.y * inv, -p.z * inv);
+		// glm::normalize(qua): length = sqrt(dot), glm's quaternion dot adds pairwise, (w*w + x*x) + (y*y + z*z); identity for a zero length
+		const float len = std::sqrt((p.w * p.w + p.x * p.x) + (p.y * p.y + p.z * p.z));
+		if (len <= 0.0f) { orient = b2r_host::quat(1.0f, 0.0f, 0.0f, 0.0f); return; }
+		const float inv = 1.0f / len;
+		orient = b2r_host::quat(p.w * inv, -(p.x * inv), -(p.y * inv), -(p.z * inv));
 	}
 	void Translate(b2r_host::vec3 t) {  // pos += orient * t
 		const b2r_host::vec3 q{orient.x, orient.y, orient.z};

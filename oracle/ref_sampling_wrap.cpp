@@ -42,6 +42,16 @@ void ref_generate_ray(const float eye[3], const float dir[3], uint32_t w, uint32
 	cam_out[0] = c.view.orient.w; cam_out[1] = c.view.orient.x; cam_out[2] = c.view.orient.y; cam_out[3] = c.view.orient.z;
 	cam_out[4] = c.projection.half_width; cam_out[5] = c.projection.half_height; cam_out[6] = c.projection.z;
 }
+// Camera::RotateLocal / TranslateLocal (Camera.hpp:51-56,74-79; the app's mouse / WASD handlers, Application.cpp:236-247,299): starting from
+// Camera{eye, dir}, `n_moves` x {Rotate(angles), Translate(offset)}; out7 = pos xyz, orient wxyz
+void ref_camera_move(const float eye[3], const float dir[3], const float* angles3, const float* offsets3, uint32_t n_moves, float out7[7]) {
+	View v(glm::vec3{eye[0], eye[1], eye[2]}, glm::vec3{dir[0], dir[1], dir[2]});
+	for (uint32_t i = 0; i < n_moves; i++) {
+		v.Rotate(glm::vec3{angles3[3 * i], angles3[3 * i + 1], angles3[3 * i + 2]});
+		v.Translate(glm::vec3{offsets3[3 * i], offsets3[3 * i + 1], offsets3[3 * i + 2]});
+	}
+	out7[0] = v.pos.x; out7[1] = v.pos.y; out7[2] = v.pos.z; out7[3] = v.orient.w; out7[4] = v.orient.x; out7[5] = v.orient.y; out7[6] = v.orient.z;
+}
 void ref_fast_sincos(float x, float* s, float* c) { fast_sincos(x, s, c); }
 float ref_fast_asin(float x) { return fast_asin(x); }
 float ref_fast_atan2(float y, float x) { return fast_atan2(y, x); }

@@ -65,7 +65,8 @@ inline quat operator*(quat p, quat q) {
 	            p.w * q.y + p.y * q.w + p.z * q.x - p.x * q.z, p.w * q.z + p.z * q.w + p.x * q.y - p.y * q.x);
 }
 inline quat normalize(quat q) {
-	const float len = std::sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+	// length(qua) = sqrt(dot(q, q)) with glm's quaternion dot (detail/type_quat.inl, compute_dot<qua>): tmp(w*w, x*x, y*y, z*z); (tmp.x + tmp.y) + (tmp.z + tmp.w)
+	const float len = std::sqrt((q.w * q.w + q.x * q.x) + (q.y * q.y + q.z * q.z));
 	if (len <= 0.0f) return quat(1, 0, 0, 0);
 	const float inv = 1.0f / len; return quat(q.w * inv, q.x * inv, q.y * inv, q.z * inv);
 }

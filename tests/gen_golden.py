@@ -205,6 +205,36 @@ def gen_sampling():
 
 
 # ---------------------------------------------------------------- reference BVH builder and sphere loops (oracle/_ref/librefbvh.so)
+def camera_move_inputs(seed=20261018, n=40):
+    """Camera{eye, dir} followed by a few {RotateLocal(angles), TranslateLocal(offset)} steps (the app's mouse-look and WASD handlers,
+    Application.cpp:236-247,299): small and large angles, all three axes."""
+    rs = np.random.RandomState(seed)
+    out = []
+    for i in range(n):
+        eye = rs.uniform(-5, 5, 3).astype(np.float32); d = rs.randn(3).astype(np.float32)
+        k = int(rs.randint(1, 6))
+        ang = (rs.uniform(-1, 1, (k, 3)) * (0.02 if i % 2 else 2.5)).astype(np.float32)
+        if i % 3 == 0: ang[:, 2] = 0.0                                       # the app only sends pitch and yaw
+        off = rs.uniform(-2, 2, (k, 3)).astype(np.float32)
+        out.append((eye, d, np.ascontiguousarray(ang), np.ascontiguousarray(off)))
+    return out
+
+
+def eval_camera_move(fn, moves):
+    """fn(eye, dir, angles, offsets, n, out7) -> list of hex-float strings [pos xyz, orient wxyz] per case"""
+    rows = []
+    for eye, d, ang, off in moves:
+        out = np.zeros(7, np.float32)
+        fn(C.c_void_p(eye.ctypes.data), C.c_void_p(d.ctypes.data), C.c_void_p(ang.ctypes.data), C.c_void_p(off.ctypes.data), len(ang), C.c_void_p(out.ctypes.data))
+        rows.append([float(v).hex() for v in out])
+    return rows
+
+
+def gen_camera_move():
+    json.dump({"camera_move": eval_camera_move(ref_sampling_lib().ref_camera_move, camera_move_inputs())},
+              open(os.path.join(HERE, "golden", "camera_move_kat.json"), "w"), indent=0)
+
+
 def ref_bvh_lib():
     oracle_py.build()
     ref = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "librefbvh.so"))
@@ -373,5 +403,5 @@ def gen_frames():
 
 
 if __name__ == "__main__":
-    gen_rng(); gen_sampling(); gen_bvh(); gen_renderer(); gen_survey(); gen_frames()
+    gen_rng(); gen_sampling(); gen_camera_move(); gen_bvh(); gen_renderer(); gen_survey(); gen_frames()
     print("golden vectors written")

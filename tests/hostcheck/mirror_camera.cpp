@@ -1,0 +1,14 @@
+// mirror_camera.cpp — TEST HARNESS (part of tests/hostcheck/libhostcheck.so): the C++ mirror's Camera (cpu-raytracing-experiments_b200/host/
+// Camera.hpp — what a user of the mirror moves around with the reference's RotateLocal / TranslateLocal calls) behind a C tap, so that
+// tests/test_oracle_ref_sampling.py can compare it with the reference's own Camera.hpp compiled into oracle/_ref/librefsampling.so.
+#include "Camera.hpp"
+
+extern "C" void hc_mirror_camera_move(const float eye[3], const float dir[3], const float* angles3, const float* offsets3, uint32_t n_moves, float out7[7]) {
+	Camera c({eye[0], eye[1], eye[2]}, {dir[0], dir[1], dir[2]}, 16, 16, 50.0f);
+	for (uint32_t i = 0; i < n_moves; i++) {
+		c.RotateLocal({angles3[3 * i], angles3[3 * i + 1], angles3[3 * i + 2]});      // Camera.hpp:74-76 (Application.cpp:299)
+		c.TranslateLocal({offsets3[3 * i], offsets3[3 * i + 1], offsets3[3 * i + 2]}); // Camera.hpp:77-79 (Application.cpp:236-247)
+	}
+	out7[0] = c.view.pos.x; out7[1] = c.view.pos.y; out7[2] = c.view.pos.z;
+	out7[3] = c.view.orient.w; out7[4] = c.view.orient.x; out7[5] = c.view.orient.y; out7[6] = c.view.orient.z;
+}

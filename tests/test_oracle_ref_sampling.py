@@ -89,6 +89,20 @@ def test_live_against_reference_library(hostcheck):
         assert gen_golden.eval_camera_oracle(cams) == gen_golden.eval_camera_ref(gen_golden.ref_sampling_lib(), cams)
 
 
+def test_mirror_camera_moves_like_the_references_camera(hostcheck):
+    """Camera::RotateLocal / TranslateLocal of the C++ mirror (host/Camera.hpp — the calls the app's input handlers make,
+    Application.cpp:236-247,299) against the reference's own View::Rotate / Translate (Camera.hpp:51-56, compiled verbatim): position and
+    orientation bit for bit after sequences of moves — the committed fixture everywhere, and live where oracle/_ref is present."""
+    want = json.load(open(os.path.join(G, "camera_move_kat.json")))["camera_move"]
+    got = gen_golden.eval_camera_move(hostcheck.hc_mirror_camera_move, gen_golden.camera_move_inputs())
+    assert len(got) == len(want) == 40 and got == want
+    path = os.path.join(os.path.dirname(oracle_py.__file__), "_ref", "librefsampling.so")
+    if os.path.exists(path):
+        for seed in (5, 6):
+            moves = gen_golden.camera_move_inputs(seed=seed, n=60)
+            assert gen_golden.eval_camera_move(hostcheck.hc_mirror_camera_move, moves) == gen_golden.eval_camera_move(gen_golden.ref_sampling_lib().ref_camera_move, moves)
+
+
 def test_reference_scalar_and_vec8_tonemap_agree():
     """Renderer::Render uses the Vec8f overload (Color.hpp:66-73); its scalar twin (:59-64) must give the same bits lane-wise."""
     path = os.path.join(os.path.dirname(oracle_py.__file__), "_ref", "librefsampling.so")
