@@ -223,8 +223,9 @@ double wide_cost(const WideBvh& t) {
 }
 
 bool match_prims_to_geometry(const b2r_sphere* prims, const b2r_sphere* geometry, uint32_t n, std::vector<uint32_t>& geom_of_prim) {
-	// open-addressing table over the 20 bytes that make a sphere (bit patterns, so -0 / NaN need no special case); equal spheres are
-	// handed out first-come in probe order, which is deterministic
+	// open-addressing table over the 20 bytes that make a sphere (bit patterns, so -0 / NaN need no special case): one slot per DISTINCT
+	// sphere, holding the first geometry index with that value; equal spheres hang off it as a list in index order and are handed out
+	// first in, first out — linear time however many twins a scene has
 	static_assert(offsetof(b2r_sphere, material_ID) == 16, "position, radius_sq, material_ID are the first 20 bytes");
 	auto hash = [](const b2r_sphere& s) {
 		uint32_t w[5]; std::memcpy(w, &s, 20);
@@ -234,17 +235,27 @@ bool match_prims_to_geometry(const b2r_sphere* prims, const b2r_sphere* geometry
 	};
 	uint64_t size = 16; while (size < 2ull * n) size <<= 1;
 	const uint64_t mask = size - 1;
-	constexpr uint32_t kFree = 0xffffffffu;
-	std::vector<uint32_t> table(size, kFree);
-	for (uint32_t g = 0; g < n; g++) { uint64_t at = hash(geometry[g]) & mask; while (table[at] != kFree) at = (at + 1) & mask; table[at] = g; }
-	std::vector<uint8_t> taken(n, 0);
+	constexpr uint32_t kNone = 0xffffffffu;
+	std::vector<uint32_t> table(size, kNone), next_same(n, kNone), last(n), cursor(n);
+	for (uint32_t g = 0; g < n; g++) {
+		uint64_t at = hash(geometry[g]) & mask;
+		for (;; at = (at + 1) & mask) {
+			const uint32_t rep = table[at];
+			if (rep == kNone) { table[at] = g; last[g] = g; cursor[g] = g; break; }
+			if (std::memcmp(&geometry[g], &geometry[rep], 20) == 0) { next_same[last[rep]] = g; last[rep] = g; break; }
+		}
+	}
 	geom_of_prim.assign(n, 0u);
 	for (uint32_t i = 0; i < n; i++) {
 		uint64_t at = hash(prims[i]) & mask;
 		for (;; at = (at + 1) & mask) {
-			const uint32_t g = table[at];
-			if (g == kFree) { geom_of_prim.clear(); return false; }
-			if (!taken[g] && std::memcmp(&prims[i], &geometry[g], 20) == 0) { taken[g] = 1; geom_of_prim[i] = g; break; }
+			const uint32_t rep = table[at];
+			if (rep == kNone) { geom_of_prim.clear(); return false; }              // a sphere geometry does not have
+			if (std::memcmp(&prims[i], &geometry[rep], 20) != 0) continue;
+			const uint32_t g = cursor[rep];
+			if (g == kNone) { geom_of_prim.clear(); return false; }                // more copies of it than geometry has
+			cursor[rep] = next_same[g]; geom_of_prim[i] = g;
+			break;
 		}
 	}
 	return true;

@@ -180,3 +180,23 @@ def test_refit_fuzz_duplicates_and_random_orders(hostcheck):
         bt = np.zeros(len(rays), np.float32); bp = np.zeros(len(rays), np.int32)
         hostcheck.hc_closest_brute(vp(prims2), n, vp(rays), len(rays), vp(bt), vp(bp))
         assert bt.tobytes() == tfar.tobytes() and np.array_equal(bp, prim)
+
+
+def test_match_is_linear_in_the_number_of_twins(hostcheck):
+    """50 000 copies of one sphere plus 50 000 distinct ones: pairing by value stays linear (twins are chained off one table slot and
+    handed out in index order) and rejects an array with one copy too many."""
+    import time
+    n = 100000
+    geo = np.ascontiguousarray(scenes.random_scene(n, light_every=50)["geometry"]); geo[::2] = geo[0]
+    perm = np.random.RandomState(1).permutation(n)
+    prims = np.ascontiguousarray(geo[perm]); m = np.zeros(n, np.uint32)
+    t0 = time.perf_counter()
+    assert hostcheck.hc_match(vp(prims), vp(geo), n, vp(m)) == 1
+    assert time.perf_counter() - t0 < 2.0
+    assert sorted(m.tolist()) == list(range(n))
+    for f in ("position", "radius_sq", "material_ID"):
+        assert np.array_equal(geo[m][f], prims[f])
+    twins = np.flatnonzero(perm % 2 == 0)                                  # positions in prims that hold the repeated sphere
+    assert np.array_equal(m[twins], np.arange(0, n, 2))                    # handed out first in, first out
+    prims[np.flatnonzero(perm % 2 == 1)[0]] = geo[0]                       # one twin too many, one distinct sphere missing
+    assert hostcheck.hc_match(vp(prims), vp(geo), n, vp(m)) == 0
