@@ -26,7 +26,8 @@ extern "C" {
 int hc_render_sample(const b2r_sphere* prims, const b2r_bvh_node* nodes, uint32_t n_prims, uint32_t n_nodes,
                      const b2r_material* materials, uint32_t n_mat, const int32_t* lights, uint32_t n_lights,
                      const b2r_sphere* geometry, const float cam11[11], uint32_t width, uint32_t height,
-                     uint32_t max_bounces, uint32_t flags, uint32_t acc, int use_bvh, float* rad_out, uint64_t counters[5]) {
+                     uint32_t max_bounces, uint32_t flags, uint32_t acc, int use_bvh, float* rad_out, uint64_t counters[5],
+                     const float ambient[3], const float* hdri_rgba, int32_t hdri_w, int32_t hdri_h) {  // sky (Primitives.hpp:29-47): hdri may be null when ambient is 0
 	PackedScene ps; pack_scene(prims, n_prims, materials, n_mat, lights, n_lights, geometry, ps);
 	WideBvh wide;
 	if (use_bvh == 2) { std::vector<b2r_bvh_node> tree; build_traversal_tree(prims, n_prims, tree); flatten_bvh(tree.data(), static_cast<uint32_t>(tree.size()), prims, n_prims, wide); }  // what libb2r uploads by default
@@ -35,7 +36,12 @@ int hc_render_sample(const b2r_sphere* prims, const b2r_bvh_node* nodes, uint32_
 	SceneDev sc{};
 	sc.prims = ps.prims.data(); sc.prim_mat = ps.prim_mat.data(); sc.mat_albedo = ps.mat_albedo.data(); sc.mat_emission = ps.mat_emission.data();
 	sc.light_sphere = ps.light_sphere.data(); sc.light_emit = ps.light_emit.data(); sc.wide = wide.nodes.data(); sc.hdri = nullptr;
-	sc.n_prims = n_prims; sc.n_mat = n_mat; sc.n_lights = n_lights; sc.light_sel_pdf = 1.0f / static_cast<float>(n_lights); sc.has_ambient = 0;
+	sc.n_prims = n_prims; sc.n_mat = n_mat; sc.n_lights = n_lights; sc.light_sel_pdf = 1.0f / static_cast<float>(n_lights);
+	sc.has_ambient = (ambient && hdri_rgba && sel_max(ambient[0], sel_max(ambient[1], ambient[2])) > 0.0f) ? 1 : 0;  // Renderer.hpp:79
+	if (sc.has_ambient) {
+		sc.hdri = reinterpret_cast<const float4*>(hdri_rgba); sc.ambient[0] = ambient[0]; sc.ambient[1] = ambient[1]; sc.ambient[2] = ambient[2];
+		sc.hdri_w = hdri_w; sc.hdri_h = hdri_h; sc.hdri_fw = static_cast<float>(hdri_w - 1); sc.hdri_fh = static_cast<float>(hdri_h - 1);  // Application.cpp:230-231
+	}
 	FrameDev fr{};
 	fr.cam = CameraParams{cam11[0], cam11[1], cam11[2], cam11[3], cam11[4], cam11[5], cam11[6], cam11[7], cam11[8], cam11[9], cam11[10]};
 	fr.width = width; fr.height = height; fr.h_tiles = width / 16; fr.npix = width * height; fr.h_tiles_magic = magic_for(fr.h_tiles); fr.npix_magic = magic_for(fr.npix); fr.max_bounces = max_bounces; fr.buckets = 1; fr.flags = flags;
@@ -55,7 +61,10 @@ int hc_render_sample(const b2r_sphere* prims, const b2r_bvh_node* nodes, uint32_
 				const float4 sp = sc.prims[j]; float d;
 				if (sphere_hit_closest(sp.x, sp.y, sp.z, sp.w, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, &d) && d < best) { best = d; prim = static_cast<int32_t>(j); }
 			}
-			if (prim < 0) { counters[3]++; break; }  // miss: terminated, radiance stays
+			if (prim < 0) {  // miss: terminated; with an ambient sky the miss shader adds its texel (Renderer.hpp:411-420), as the kernels do
+				if (sc.has_ambient) rad_add(rad_out, fr.npix, s.pid, shade_sky(sc, s), f3{0.0f, 0.0f, 0.0f}, true, false);
+				counters[3]++; break;
+			}
 			counters[2]++;
 			const Surface sf = shade_surface(sc, s, best, prim);
 			if (last) { rad_zero(rad_out, fr.npix, s.pid); counters[4]++; break; }

@@ -84,7 +84,8 @@ def render_hc(hostcheck, sc, w, h, mb, acc, use_bvh, flags=0):
     rad = np.zeros((3, w * h), np.float32); cnt = (C.c_uint64 * 5)()
     vp = lambda a: C.c_void_p(a.ctypes.data)
     rc = hostcheck.hc_render_sample(vp(ps.prims), vp(ps.nodes), len(ps.prims), len(ps.nodes), vp(ps.material), len(ps.material), vp(ps.lights), len(ps.lights),
-                                    vp(ps.geometry), vp(ps.camera), w, h, mb, flags, acc, use_bvh, vp(rad), cnt)
+                                    vp(ps.geometry), vp(ps.camera), w, h, mb, flags, acc, use_bvh, vp(rad), cnt,
+                                    vp(ps.ambient), None if ps.hdri is None else vp(ps.hdri), 0 if ps.hdri is None else ps.hdri.shape[1], 0 if ps.hdri is None else ps.hdri.shape[0])
     assert rc == 0
     return rad, list(cnt)
 
@@ -102,6 +103,24 @@ def test_per_sample_radiance_bit_exact(hostcheck, name, w, h, mb, use_bvh):
         assert rad.tobytes() == ref.tobytes()
         assert cnt[0] == oc["extension_rays"] and cnt[2] == oc["shaded_hits"] and cnt[3] == oc["terminated"] and cnt[4] == oc["dropped"]
         assert cnt[1] <= oc["shadow_rays"]  # the oracle also traces the (discarded) last-bounce shadow rays (Q11)
+
+
+@pytest.mark.parametrize("name,use_bvh", [("bvh_test", 0), ("bvh_test", 2), ("brdf_test", 0), ("brdf_test", 1), ("white_furnace", 0)])
+def test_sky_scenes_bit_exact(hostcheck, name, use_bvh):
+    """The reference's other three scenes as it lights them (ambient HDRI sky, Application.cpp:102-223): the product's miss shader
+    (shade_sky: fast_atan2 / fast_asin texel lookup, Q14's throughput.r typo) and the rest of the path against the oracle, bit for bit.
+    BRDF_test's albedo-0 spheres exercise zero throughput and the q = 1 roulette; the white furnace has a known answer."""
+    sc = {"bvh_test": lambda: scenes.bvh_test_scene(255), "brdf_test": scenes.brdf_test_scene, "white_furnace": scenes.white_furnace}[name]()
+    w, h, mb = 128, 80, 8
+    o = oracle_py.Oracle(w, h, max_bounces=mb, K=1); o.set_scene(sc)
+    for acc in (1, 7):
+        o.reset(); o.reset_counters(); o.set_accumulations(acc - 1); o.accumulate(1)
+        ref = o.buckets()[0]; oc = o.counters()
+        rad, cnt = render_hc(hostcheck, sc, w, h, mb, acc, use_bvh)
+        assert rad.tobytes() == ref.tobytes()
+        assert cnt[0] == oc["extension_rays"] and cnt[2] == oc["shaded_hits"] and cnt[3] == oc["terminated"] and cnt[4] == oc["dropped"]
+        if name == "white_furnace": assert np.all(rad == 1.0)
+        else: assert float(rad.max()) > 0.0
 
 
 def test_no_mis_variant(hostcheck):
