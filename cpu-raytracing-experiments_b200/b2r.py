@@ -31,7 +31,7 @@ COUNTER_NAMES = ["extension_rays", "shadow_rays", "shaded_hits", "terminated", "
 
 # every symbol include/b2r.h declares (tests/test_abi.py checks the header against this list and the library against both)
 ABI_SYMBOLS = [
-    "b2r_bvh_build", "b2r_find_lights", "b2r_camera_lookat", "b2r_create", "b2r_destroy", "b2r_resize", "b2r_reset", "b2r_set_stream",
+    "b2r_bvh_build", "b2r_bvh_build_ex", "b2r_find_lights", "b2r_camera_lookat", "b2r_create", "b2r_destroy", "b2r_resize", "b2r_reset", "b2r_set_stream",
     "b2r_sync", "b2r_upload_scene", "b2r_refit_scene", "b2r_set_camera", "b2r_accumulate", "b2r_resolve", "b2r_resolve_async", "b2r_frame_wait", "b2r_resolve_from", "b2r_ipc_export_buckets", "b2r_ipc_open_peers", "b2r_ipc_close", "b2r_resolve_peers", "b2r_get_accumulations", "b2r_set_accumulations",
     "b2r_read_buckets", "b2r_write_buckets", "b2r_device_buckets", "b2r_device_framebuffer", "b2r_read_counters", "b2r_reset_counters",
     "b2r_read_kernel_times", "b2r_set_flags", "b2r_generate_rays", "b2r_trace_closest", "b2r_trace_shadow", "b2r_read_wide_nodes",
@@ -62,7 +62,7 @@ def lib():
         L = C.CDLL(LIB_PATH)
         vp, u32, i32, f32 = C.c_void_p, C.c_uint32, C.c_int32, C.c_float
         sig = {
-            "b2r_bvh_build": [vp, u32, vp, vp, vp, vp], "b2r_find_lights": [vp, u32, vp, u32, vp, vp],
+            "b2r_bvh_build": [vp, u32, vp, vp, vp, vp], "b2r_bvh_build_ex": [vp, u32, u32, f32, vp, vp, vp, vp], "b2r_find_lights": [vp, u32, vp, u32, vp, vp],
             "b2r_camera_lookat": [vp, vp, u32, u32, f32, f32, vp], "b2r_create": [vp, vp], "b2r_resize": [vp, u32, u32], "b2r_reset": [vp],
             "b2r_set_stream": [vp, vp], "b2r_sync": [vp],
             "b2r_upload_scene": [vp, vp, vp, u32, u32, vp, u32, vp, u32, vp, u32, vp, vp, i32, i32],
@@ -91,12 +91,12 @@ def _ptr(a):
     return C.c_void_p(a.ctypes.data) if a is not None else None
 
 
-def build_bvh(geometry):
-    """BoundingVolumeHierarchy<Sphere>(geometry) — BVH.hpp:90-206. Returns (nodes, prims, prim_ids)."""
+def build_bvh(geometry, log_cluster_size=0, cost_ratio=1.0):
+    """BoundingVolumeHierarchy<Sphere>(geometry, SplitHeuristic{log_cluster_size, cost_ratio}) — BVH.hpp:70-83,90-206. Returns (nodes, prims, prim_ids)."""
     geo = np.ascontiguousarray(geometry, dtype=_scenes.SPHERE_DTYPE); n = len(geo)
     nodes = np.zeros(max(1, 2 * n - 1), _scenes.NODE_DTYPE); prims = np.zeros(n, _scenes.SPHERE_DTYPE); ids = np.zeros(n, np.uint32)
     nn = C.c_uint32(0)
-    _check(lib().b2r_bvh_build(_ptr(geo), n, _ptr(nodes), _ptr(prims), _ptr(ids), C.addressof(nn)))
+    _check(lib().b2r_bvh_build_ex(_ptr(geo), n, log_cluster_size, cost_ratio, _ptr(nodes), _ptr(prims), _ptr(ids), C.addressof(nn)))
     return nodes[:nn.value], prims, ids
 
 

@@ -51,7 +51,10 @@ inline b2r_bvh_node to_node(const Box& b, uint32_t first, uint32_t count) {
 }  // namespace
 
 void build_reference_bvh(const b2r_sphere* geometry, uint32_t n, std::vector<b2r_bvh_node>& nodes,
-                         std::vector<b2r_sphere>& prims, std::vector<uint32_t>& prim_ids) {
+                         std::vector<b2r_sphere>& prims, std::vector<uint32_t>& prim_ids, uint32_t log_cluster_size, float cost_ratio) {
+	// SplitHeuristic (BVH.hpp:70-83): prim_count(size) = (size + 2^L - 1) >> L as a float; leaf_cost = half_area * prim_count;
+	// non_split_cost = half_area * (prim_count - cost_ratio). The app always passes the defaults (L = 0, ratio 1).
+	const auto prim_count = [log_cluster_size](uint32_t size) { return static_cast<float>((static_cast<uint64_t>(size) + (1ull << log_cluster_size) - 1ull) >> log_cluster_size); };
 	nodes.clear(); prims.clear(); prim_ids.clear();
 	if (n == 0) { nodes.push_back(to_node(void_box(), 0, 0)); return; }
 	// per-primitive boxes (Sphere::bounds, Primitives.hpp:13-16) and centroids ((max+min)*0.5, BVH.hpp:55-57)
@@ -113,7 +116,7 @@ void build_reference_bvh(const b2r_sphere* geometry, uint32_t n, std::vector<b2r
 
 			// fallback split = median on the widest axis, at the "do not split" cost area*(count-1) (BVH.hpp:144, :80-82)
 			uint32_t cut = begin + (job.count + 1) / 2; int cut_axis = widest_axis(here);
-			float cut_cost = sah_measure(here) * (static_cast<float>(job.count) - 1.0f);
+			float cut_cost = sah_measure(here) * (prim_count(job.count) - cost_ratio);
 			// Per axis: right-to-left sweep (the reference's chunked early exit degenerates into one full sweep, Q18, and its `first_right`
 			// guard can never cut the left sweep short), then the left-to-right sweep (BVH.hpp:163-170), which stops once the left cost
 			// alone exceeds the bound. The reference runs the axes one after the other against a shrinking bound; the left cost never
@@ -127,12 +130,12 @@ void build_reference_bvh(const b2r_sphere* geometry, uint32_t n, std::vector<b2r
 				Box acc = void_box();
 				for (uint32_t i = end - 1; i > begin; --i) {
 					grow(acc, box[ids[i]]);
-					suffix[i] = sah_measure(acc) * static_cast<float>(end - i);
+					suffix[i] = sah_measure(acc) * prim_count(end - i);
 				}
 				acc = void_box();
 				for (uint32_t i = begin; i + 1 < end; ++i) {
 					grow(acc, box[ids[i]]);
-					const float left = sah_measure(acc) * static_cast<float>(i + 1 - begin);
+					const float left = sah_measure(acc) * prim_count(i + 1 - begin);
 					if (left > best.cost) break;
 					const float total = left + suffix[i + 1];
 					if (total < best.cost) { best.cost = total; best.cut = i + 1; best.found = true; }
@@ -360,9 +363,14 @@ extern "C" {
 
 int b2r_bvh_build(const b2r_sphere* geometry, uint32_t n, b2r_bvh_node* nodes_out, b2r_sphere* prims_out,
                   uint32_t* prim_ids_out, uint32_t* n_nodes_out) {
-	if ((n && !geometry) || !nodes_out) return B2R_ERR_ARG;
+	return b2r_bvh_build_ex(geometry, n, 0u, 1.0f, nodes_out, prims_out, prim_ids_out, n_nodes_out);
+}
+
+int b2r_bvh_build_ex(const b2r_sphere* geometry, uint32_t n, uint32_t log_cluster_size, float cost_ratio, b2r_bvh_node* nodes_out,
+                     b2r_sphere* prims_out, uint32_t* prim_ids_out, uint32_t* n_nodes_out) {
+	if ((n && !geometry) || !nodes_out || log_cluster_size > 31u) return B2R_ERR_ARG;
 	std::vector<b2r_bvh_node> nodes; std::vector<b2r_sphere> prims; std::vector<uint32_t> ids;
-	b2r::build_reference_bvh(geometry, n, nodes, prims, ids);
+	b2r::build_reference_bvh(geometry, n, nodes, prims, ids, log_cluster_size, cost_ratio);
 	std::memcpy(nodes_out, nodes.data(), nodes.size() * sizeof(b2r_bvh_node));
 	if (prims_out && n) std::memcpy(prims_out, prims.data(), prims.size() * sizeof(b2r_sphere));
 	if (prim_ids_out && n) std::memcpy(prim_ids_out, ids.data(), ids.size() * sizeof(uint32_t));

@@ -31,7 +31,7 @@ struct WideBvh {
 
 // BoundingVolumeHierarchy<Sphere> constructor (BVH.hpp:90-206), bit-identical node and leaf order.
 void build_reference_bvh(const b2r_sphere* geometry, uint32_t n, std::vector<b2r_bvh_node>& nodes,
-                         std::vector<b2r_sphere>& prims, std::vector<uint32_t>& prim_ids);
+                         std::vector<b2r_sphere>& prims, std::vector<uint32_t>& prim_ids, uint32_t log_cluster_size = 0u, float cost_ratio = 1.0f);
 // Checks the invariants the flattening relies on (children adjacent, leaf size 1, indices in range). Returns false if malformed.
 bool validate_reference_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, uint32_t n_prims);
 // A second binary tree over the same spheres (reference leaf order kept in the leaf links), built for traversal speed.

@@ -17,12 +17,20 @@ template <> struct BoundingVolumeHierarchy<Sphere> {
 	std::vector<Node> nodes;
 	std::vector<Sphere> prims;              // leaf order (BVH.hpp:201-205)
 	std::vector<uint32_t> prim_ids;         // prims[i] == geometry[prim_ids[i]]
+	struct SplitHeuristic {                 // BVH.hpp:70-83 (the arithmetic lives in b2r_bvh_build_ex)
+		size_t log_cluster_size = 0;        // log2 of the size of primitive clusters
+		float cost_ratio = 1.0f;            // cost of a ray-box test over the cost of a primitive test
+	};
 	BoundingVolumeHierarchy() {}
-	BoundingVolumeHierarchy(std::span<const Sphere> primitives) {
+	// BVH.hpp:90 has one constructor with `SplitHeuristic heuristic = SplitHeuristic{}`; in a non-template class that default argument is
+	// ill-formed (the nested struct's member initialisers are not complete yet), hence the delegating pair
+	BoundingVolumeHierarchy(std::span<const Sphere> primitives) : BoundingVolumeHierarchy(primitives, SplitHeuristic()) {}
+	BoundingVolumeHierarchy(std::span<const Sphere> primitives, SplitHeuristic heuristic) {
 		const uint32_t n = static_cast<uint32_t>(primitives.size());
 		nodes.resize(n ? 2 * n - 1 : 1); prims.resize(n); prim_ids.resize(n);
 		uint32_t n_nodes = 0;
-		b2r_bvh_build(reinterpret_cast<const b2r_sphere*>(primitives.data()), n, nodes.data(), reinterpret_cast<b2r_sphere*>(prims.data()), prim_ids.data(), &n_nodes);
+		b2r_bvh_build_ex(reinterpret_cast<const b2r_sphere*>(primitives.data()), n, static_cast<uint32_t>(heuristic.log_cluster_size), heuristic.cost_ratio,
+		                 nodes.data(), reinterpret_cast<b2r_sphere*>(prims.data()), prim_ids.data(), &n_nodes);
 		nodes.resize(n_nodes);
 	}
 	const Node& root() const { return nodes.front(); }

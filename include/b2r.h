@@ -89,6 +89,11 @@ typedef struct b2r_ctx b2r_ctx;
  * prims_out the spheres in leaf order (BVH.hpp:201-205), prim_ids_out[i] = geometry index of prims_out[i] (may be NULL). */
 int b2r_bvh_build(const b2r_sphere* geometry, uint32_t n, b2r_bvh_node* nodes_out, b2r_sphere* prims_out,
                   uint32_t* prim_ids_out, uint32_t* n_nodes_out);
+/* The same constructor with its second argument, SplitHeuristic{log_cluster_size, cost_ratio} (BVH.hpp:70-83, :90; the app always passes
+ * the defaults {0, 1.0f}, which is what b2r_bvh_build uses): leaf cost = half_area * ceil(size / 2^log_cluster_size), the cost of not
+ * splitting = half_area * (that count - cost_ratio). log_cluster_size <= 31. */
+int b2r_bvh_build_ex(const b2r_sphere* geometry, uint32_t n, uint32_t log_cluster_size, float cost_ratio, b2r_bvh_node* nodes_out,
+                     b2r_sphere* prims_out, uint32_t* prim_ids_out, uint32_t* n_nodes_out);
 /* LightingAcceleration(geometry, material) — Scene.hpp:12-16. Returns the count via n_out; out may be NULL to size. */
 int b2r_find_lights(const b2r_sphere* geometry, uint32_t n, const b2r_material* materials, uint32_t n_mat,
                     int32_t* out, uint32_t* n_out);

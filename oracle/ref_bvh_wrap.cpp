@@ -68,6 +68,14 @@ uint32_t ref_bvh_build(const void* geometry, uint32_t n, void* nodes_out, void* 
 	std::memcpy(prims_out, b.prims.data(), b.prims.size() * 32);
 	return static_cast<uint32_t>(b.nodes.size());
 }
+// the same constructor with a caller-chosen SplitHeuristic (BVH.hpp:70-83)
+uint32_t ref_bvh_build_h(const void* geometry, uint32_t n, uint32_t log_cluster_size, float cost_ratio, void* nodes_out, void* prims_out) {
+	BoundingVolumeHierarchy::SplitHeuristic h; h.log_cluster_size = log_cluster_size; h.cost_ratio = cost_ratio;
+	BoundingVolumeHierarchy b{std::span<const Sphere>(static_cast<const Sphere*>(geometry), n), h};
+	std::memcpy(nodes_out, b.nodes.data(), b.nodes.size() * 32);
+	std::memcpy(prims_out, b.prims.data(), b.prims.size() * 32);
+	return static_cast<uint32_t>(b.nodes.size());
+}
 float ref_node_half_area(const float lo[3], const float hi[3]) { BoundingVolumeHierarchy::Node nd(glm::vec3{lo[0], lo[1], lo[2]}, glm::vec3{hi[0], hi[1], hi[2]}); return nd.half_area(); }
 // rays: n x 6 floats (origin, dir), n <= 256; all spheres against all rays as the reference does (begin/end = whole ranges).
 // n rays: the first n & ~7 go through the AVX2 block, the rest through the scalar tail, exactly as in the reference.

@@ -268,6 +268,26 @@ def ref_bvh_build(ref, geo):
     return nodes[:nn].tobytes(), prims
 
 
+HEURISTICS = [(0, 1.0), (0, 0.25), (0, 4.0), (1, 1.0), (2, 0.5), (3, 2.0)]   # SplitHeuristic{log_cluster_size, cost_ratio}, BVH.hpp:70-83
+
+
+def ref_bvh_build_h(ref, geo, log_cluster_size, cost_ratio):
+    n = len(geo); nodes = np.zeros((max(2 * n - 1, 1), 32), np.uint8); prims = np.zeros(n, geo.dtype)
+    ref.ref_bvh_build_h.restype = C.c_uint32
+    nn = ref.ref_bvh_build_h(C.c_void_p(geo.ctypes.data), C.c_uint32(n), C.c_uint32(log_cluster_size), C.c_float(cost_ratio), C.c_void_p(nodes.ctypes.data), C.c_void_p(prims.ctypes.data))
+    return nodes[:nn].tobytes(), prims
+
+
+def gen_bvh_heuristics():
+    """the reference's constructor with non-default SplitHeuristic arguments -> tests/golden/bvh_heuristic_kat.json"""
+    ref = ref_bvh_lib(); out = {}
+    for name, geo in bvh_scenes():
+        if name in ("random1", "random2", "random3", "random4", "random5000"): continue
+        for L, ratio in HEURISTICS:
+            out[f"{name}|{L}|{ratio}"] = bvh_digest(*ref_bvh_build_h(ref, geo, L, ratio))
+    json.dump(out, open(os.path.join(HERE, "golden", "bvh_heuristic_kat.json"), "w"), indent=0)
+
+
 def intersect_inputs(seed=20261018):
     """seeded rays for the sphere-loop vectors, against the `default` and `random100` scenes in the reference's BVH leaf order"""
     rs = np.random.RandomState(seed); out = []
@@ -403,5 +423,5 @@ def gen_frames():
 
 
 if __name__ == "__main__":
-    gen_rng(); gen_sampling(); gen_camera_move(); gen_bvh(); gen_renderer(); gen_survey(); gen_frames()
+    gen_rng(); gen_sampling(); gen_camera_move(); gen_bvh(); gen_bvh_heuristics(); gen_renderer(); gen_survey(); gen_frames()
     print("golden vectors written")

@@ -98,3 +98,28 @@ def test_live_builder_up_to_c3_size():
         want = gen_golden.bvh_digest(*gen_golden.ref_bvh_build(ref, geo))
         assert gen_golden.bvh_digest(*oracle_build(geo)) == want, n
         assert gen_golden.bvh_digest(*product_build(geo)) == want, n
+
+
+def test_split_heuristic_argument_matches_reference_golden():
+    """BoundingVolumeHierarchy(primitives, SplitHeuristic{log_cluster_size, cost_ratio}) (BVH.hpp:70-83,:90) — the constructor's second
+    argument, which the app leaves at its default: b2r_bvh_build_ex reproduces the reference's node arrays and leaf order for other
+    values too (clustered leaf cost, cheaper / dearer "do not split" bound)."""
+    want = json.load(open(os.path.join(G, "bvh_heuristic_kat.json")))
+    geos = dict(gen_golden.bvh_scenes()); n = 0
+    for key, digest in want.items():
+        name, L, ratio = key.split("|")
+        nodes, prims, ids = b2r.build_bvh(geos[name], int(L), float(ratio))
+        assert gen_golden.bvh_digest(nodes.tobytes(), prims) == digest, key
+        n += 1
+    assert n == len(gen_golden.HEURISTICS) * 7
+    assert len({d["sha256_nodes"] for k, d in want.items() if k.startswith("random1000|")}) > 3     # the argument does change the tree
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref/librefbvh.so not present (built only where /root/reference exists)")
+def test_split_heuristic_live_on_all_cores():
+    ref = gen_golden.ref_bvh_lib()
+    geo = np.ascontiguousarray(scenes.random_scene(30000, seed=0x5EED)["geometry"])      # above the 20 000-sphere threshold of the threaded build
+    for L, ratio in ((0, 1.0), (2, 0.5), (0, 4.0)):
+        want = gen_golden.bvh_digest(*gen_golden.ref_bvh_build_h(ref, geo, L, ratio))
+        nodes, prims, ids = b2r.build_bvh(geo, L, ratio)
+        assert gen_golden.bvh_digest(nodes.tobytes(), prims) == want, (L, ratio)
