@@ -587,19 +587,26 @@ extern "C" int b2r_write_hdr(const char* path, const float* rgba, uint32_t width
 		}
 		if (width < 8 || width >= 32768) { std::fwrite(rgbe.data(), 1, rgbe.size(), f); continue; }  // flat scanline
 		line.clear(); line.push_back(2); line.push_back(2); line.push_back(static_cast<unsigned char>(width >> 8)); line.push_back(static_cast<unsigned char>(width & 255));
-		for (int c = 0; c < 4; c++) {  // each component separately: runs (128+n, value) for n >= 3 equal bytes, else literals (n, bytes...)
+		for (int c = 0; c < 4; c++) {  // each component separately, with stb_image_write's own choice of runs and literals (stbiw__write_hdr_scanline)
 			uint32_t x = 0;
+			auto at = [&](uint32_t k) { return rgbe[4 * static_cast<size_t>(k) + c]; };
 			while (x < width) {
-				uint32_t run = 1; while (x + run < width && run < 127 && rgbe[4 * (x + run) + c] == rgbe[4 * x + c]) run++;
-				if (run >= 3) { line.push_back(static_cast<unsigned char>(128 + run)); line.push_back(rgbe[4 * x + c]); x += run; continue; }
-				uint32_t lit = x, n = 0;  // literal span until the next run of >= 3
-				while (lit < width && n < 128) {
-					uint32_t r2 = 1; while (lit + r2 < width && r2 < 3 && rgbe[4 * (lit + r2) + c] == rgbe[4 * lit + c]) r2++;
-					if (r2 >= 3) break;
-					lit++; n++;
+				uint32_t r = x;  // the first position where three equal bytes start
+				while (r + 2 < width) { if (at(r) == at(r + 1) && at(r) == at(r + 2)) break; ++r; }
+				if (r + 2 >= width) r = width;
+				while (x < r) {  // literals up to there, at most 128 at a time
+					uint32_t len = r - x; if (len > 128) len = 128;
+					line.push_back(static_cast<unsigned char>(len)); for (uint32_t k = 0; k < len; k++) line.push_back(at(x + k));
+					x += len;
 				}
-				line.push_back(static_cast<unsigned char>(n)); for (uint32_t k = 0; k < n; k++) line.push_back(rgbe[4 * (x + k) + c]);
-				x += n;
+				if (r + 2 < width) {  // the run, at most 127 at a time (a remainder of one or two is still written as a run)
+					while (r < width && at(r) == at(x)) ++r;
+					while (x < r) {
+						uint32_t len = r - x; if (len > 127) len = 127;
+						line.push_back(static_cast<unsigned char>(128 + len)); line.push_back(at(x));
+						x += len;
+					}
+				}
 			}
 		}
 		std::fwrite(line.data(), 1, line.size(), f);

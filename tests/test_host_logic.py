@@ -206,3 +206,43 @@ def test_hdr_reader_fuzz_against_an_independent_encoder(tmp_path):
         got = b2r.read_hdr(_hdr_file(tmp_path / f"z{trial}.hdr", w, h, body))
         want = (rgbe[..., :3] * np.ldexp(1.0, rgbe[..., 3].astype(np.int32) - 136)[..., None] * (rgbe[..., 3:] > 0)).astype(np.float32)
         assert got[..., :3].tobytes() == want.tobytes() and np.all(got[..., 3] == 1.0)
+
+
+def test_hdr_writer_bytes_follow_stb_image_write(tmp_path):
+    """Image::Store = stbi_write_hdr (Image.cpp:71-74; stb_image_write.h is un-vendored third-party code, restated from its published
+    source): apart from the "# Written by" comment line the file is what stb writes, byte for byte — frexp-based RGBE conversion with
+    truncation, {2, 2, w_hi, w_lo} scanline headers, literals up to the first triple of equal bytes (<= 128 at a time), runs <= 127 at
+    a time with one- and two-byte remainders still written as runs. Checked against a second restatement in this test."""
+    rs = np.random.RandomState(12)
+    w, h = 300, 4
+    img = np.zeros((h, w, 4), np.float32); img[..., :3] = rs.rand(h, w, 3) ** 3 * 9; img[..., 3] = 1
+    img[0, 10:150, :] = img[0, 10, :]        # a run of 140: 127 + 13
+    img[1, 20:148, 1] = 0.5                   # a run of 128 in one component: 127 + a run of 1
+    img[2, :, :3] = 0.0                       # black row: all four components constant
+    b2r.write_hdr(tmp_path / "s.hdr", img)
+    data = open(tmp_path / "s.hdr", "rb").read()
+    head = b"#?RADIANCE\n# Written by libb2r\nFORMAT=32-bit_rle_rgbe\nEXPOSURE=          1.0000000000000\n\n-Y 4 +X 300\n"
+    assert data.startswith(head)
+    want = bytearray()
+    for row in img[::-1]:                     # stbi_flip_vertically_on_write(true)
+        rgbe = np.zeros((w, 4), np.uint8)
+        for x in range(w):
+            r, g, b = (np.float32(v) for v in row[x, :3]); m = max(r, g, b)
+            if m >= np.float32(1e-32):
+                mant, e = np.frexp(m); n = np.float32(np.float32(mant) * np.float32(256.0) / m)
+                rgbe[x] = (int(r * n), int(g * n), int(b * n), e + 128)
+        want += bytes([2, 2, w >> 8, w & 255])
+        for c in range(4):
+            comp = rgbe[:, c].tolist(); x = 0
+            while x < w:
+                r_ = x
+                while r_ + 2 < w and not (comp[r_] == comp[r_ + 1] == comp[r_ + 2]): r_ += 1
+                if r_ + 2 >= w: r_ = w
+                while x < r_:
+                    n = min(128, r_ - x); want += bytes([n] + comp[x:x + n]); x += n
+                if r_ + 2 < w:
+                    while r_ < w and comp[r_] == comp[x]: r_ += 1
+                    while x < r_:
+                        n = min(127, r_ - x); want += bytes([128 + n, comp[x]]); x += n
+    assert data[len(head):] == bytes(want)
+    assert np.array_equal(b2r.read_hdr(tmp_path / "s.hdr")[::-1][2, :, :3], np.zeros((w, 3), np.float32))
