@@ -45,6 +45,11 @@ def combine_buckets(local_buckets, group=None):
     out = local_buckets.clone()
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    if out.is_cuda:
+        # The Renderer resolves on the library's own stream (or the one given at construction), which is not ordered against
+        # torch's current stream: the reduced buckets must have landed before Render(dev_buckets=...) is enqueued.
+        import torch
+        torch.cuda.current_stream(out.device).synchronize()
     return out
 
 
