@@ -58,10 +58,12 @@ struct b2r_ctx {
 	int32_t* d_prim_mat = nullptr;
 	WideNode* d_wide = nullptr;
 	size_t cap_prims = 0, cap_prim_mat = 0, cap_mat_albedo = 0, cap_mat_emission = 0, cap_light_sphere = 0, cap_light_emit = 0, cap_wide = 0, cap_hdri = 0;
-	WideBvh wide_host; uint64_t wide_key = 0; bool have_wide = false;
+	WideBvh wide_host; uint64_t wide_key = 0; std::vector<unsigned char> wide_blob; bool have_wide = false;
 	std::vector<uint32_t> cur_geom_of_prim;  // after a refit into a new BVH order: that order's index -> geometry index (empty: wide_host's)
 	uint32_t* d_remap = nullptr; size_t cap_remap = 0;
 	bool wide_refit = false; double* d_cost = nullptr;  // b2r_refit_scene: the device tree no longer equals wide_host
+	// where ray origins may lie (leaf_half_extent, b2r_shade.h): bounds of the current spheres + camera + caller-supplied ray origins
+	OriginBox obox{}; bool obox_valid = false; float sph_lo[3] = {0, 0, 0}, sph_hi[3] = {0, 0, 0}; float cam_pos[3] = {0, 0, 0};
 	// frame
 	float4 *d_A[2] = {nullptr, nullptr}, *d_B[2] = {nullptr, nullptr}, *d_SA = nullptr, *d_SB = nullptr, *d_fb = nullptr;
 	float *d_T[2] = {nullptr, nullptr}, *d_SL = nullptr, *d_rad = nullptr, *d_acc = nullptr;
@@ -259,6 +261,33 @@ bool owns_sample(const b2r_ctx* c, uint32_t acc) {
 	return ((acc % c->cfg.buckets) % stride) == c->cfg.bucket_first;
 }
 
+
+// Boxes of the device tree for the current origin box: one k_refit_level launch per BFS level, deepest first (stream order is the
+// dependency). remap (device, may be null) re-links leaves into a new BVH order.
+int launch_refit_levels(b2r_ctx* c, const uint32_t* d_remap) {
+	const std::vector<uint32_t>& lf = c->wide_host.level_first;
+	for (size_t l = lf.size() - 1; l-- > 0;) {
+		const uint32_t first = lf[l], count = lf[l + 1] - lf[l];
+		k_refit_level<<<(count * 4u + kBlock - 1u) / kBlock, kBlock, 0, c->stream>>>(reinterpret_cast<float4*>(c->d_wide), c->d_prims, d_remap, c->obox, first, count);
+		c->launches++;
+	}
+	CU(cudaGetLastError());
+	return B2R_OK;
+}
+// Ray origins about to be used (camera position, caller-supplied rays) must lie in the origin box the leaf extents were computed for;
+// if they do not, the box grows and the device tree's boxes are recomputed for it (tens of microseconds; the box has an eighth of
+// slack on every side, so an interactive camera move does not get here every frame).
+int ensure_origin_box(b2r_ctx* c, const float* points, uint32_t n_points) {
+	if (c->obox_valid && origin_box_holds(c->obox, points, n_points)) return B2R_OK;
+	std::vector<float> extra(points, points + 3 * static_cast<size_t>(n_points));
+	if (c->have_camera) extra.insert(extra.end(), c->cam_pos, c->cam_pos + 3);
+	if (c->obox_valid) { extra.insert(extra.end(), c->obox.lo, c->obox.lo + 3); extra.insert(extra.end(), c->obox.hi, c->obox.hi + 3); }  // never shrinks between uploads
+	c->obox = origin_box_rule(c->sph_lo, c->sph_hi, extra.data(), static_cast<uint32_t>(extra.size() / 3)); c->obox_valid = true;
+	if (c->have_wide) wide_fill_boxes(c->wide_host, c->wide_host.prims.data(), c->obox);  // the host copy (and its reference cost) follows: same routine, same result
+	if (c->have_scene && c->have_wide) return launch_refit_levels(c, nullptr);
+	return B2R_OK;
+}
+
 }  // namespace
 
 // ================================================================================================ C ABI
@@ -403,23 +432,35 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 	const float amb[3] = {ambient ? ambient[0] : 0.0f, ambient ? ambient[1] : 0.0f, ambient ? ambient[2] : 0.0f};
 	const bool has_ambient = sel_max(amb[0], sel_max(amb[1], amb[2])) > 0.0f;
 	if (has_ambient && (!hdri_rgba || hdri_w <= 0 || hdri_h <= 0)) return fail(B2R_ERR_ARG, "ambient > 0 needs an HDRI (the reference terminates without one, Application.cpp:225-229)");
-	for (uint32_t i = 0; i < n_prims; i++) if (prims[i].material_ID < 0 || static_cast<uint32_t>(prims[i].material_ID) >= n_mat) return fail(B2R_ERR_ARG, "material_ID out of range");
+	for (uint32_t i = 0; i < n_prims; i++) if (prims[i].material_ID < 0 || static_cast<uint32_t>(prims[i].material_ID) >= n_mat || geometry[i].material_ID < 0 || static_cast<uint32_t>(geometry[i].material_ID) >= n_mat) return fail(B2R_ERR_ARG, "material_ID out of range");
 	for (uint32_t i = 0; i < n_lights; i++) if (light_geom_idx[i] < 0 || static_cast<uint32_t>(light_geom_idx[i]) >= n_geom) return fail(B2R_ERR_ARG, "light index out of range");
 	int rc = ensure_device(c); if (rc) return rc;
 	// No stream synchronisation from here on: the copies below are ordered after the kernels already enqueued on the stream (which
 	// may still read the old scene) and before the ones enqueued next. The host side is staged in one page-locked block that is only
 	// rewritten once the previous upload's copies have completed (an event early in the previous frame, not its end).
 
-	{  // derived traversal layout, cached on the sphere array (and on which topology was asked for)
-		uint64_t key = 1469598103934665603ull ^ ((c->cfg.flags & B2R_FLAG_REFERENCE_TREE) ? 0x9e3779b97f4a7c15ull : 0ull);
-		const uint64_t* w = reinterpret_cast<const uint64_t*>(prims);
-		for (size_t i = 0; i < static_cast<size_t>(n_prims) * (sizeof(b2r_sphere) / 8); i++) key = (key ^ w[i]) * 1099511628211ull;
-		if (!c->have_wide || key != c->wide_key) {
-			if (c->cfg.flags & B2R_FLAG_REFERENCE_TREE) flatten_bvh(nodes, n_nodes, prims, n_prims, c->wide_host);
-			else { std::vector<b2r_bvh_node> tree; build_traversal_tree(prims, n_prims, tree); flatten_bvh(tree.data(), static_cast<uint32_t>(tree.size()), prims, n_prims, c->wide_host); }
-			c->wide_key = key; c->have_wide = true;
+	{  // derived traversal layout, cached on everything it is derived from: the 20 meaningful bytes of every sphere (and, for the
+		// reference topology, the node array); a hit is confirmed by comparing the kept copies, not just the hash
+		auto fnv = [](uint64_t h, const void* data, size_t bytes) { const unsigned char* b = static_cast<const unsigned char*>(data); for (size_t i = 0; i < bytes; i++) h = (h ^ b[i]) * 1099511628211ull; return h; };
+		const bool ref_tree = (c->cfg.flags & B2R_FLAG_REFERENCE_TREE) != 0;
+		uint64_t key = 1469598103934665603ull ^ (ref_tree ? 0x9e3779b97f4a7c15ull : 0ull);
+		std::vector<unsigned char> blob(static_cast<size_t>(n_prims) * 20 + (ref_tree ? static_cast<size_t>(n_nodes) * sizeof(b2r_bvh_node) : 0));
+		for (uint32_t i = 0; i < n_prims; i++) std::memcpy(blob.data() + static_cast<size_t>(i) * 20, &prims[i], 20);
+		if (ref_tree) std::memcpy(blob.data() + static_cast<size_t>(n_prims) * 20, nodes, static_cast<size_t>(n_nodes) * sizeof(b2r_bvh_node));
+		key = fnv(key, blob.data(), blob.size());
+		const bool same_tree = c->have_wide && key == c->wide_key && blob == c->wide_blob;
+		float lo[3], hi[3]; sphere_bounds(prims, n_prims, lo, hi);
+		// the origin box is kept while it still holds the spheres and the camera; a different scene starts from a fresh one
+		const float corners[6] = {lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]};
+		if (!same_tree || !c->obox_valid || !origin_box_holds(c->obox, corners, 2) || (c->have_camera && !origin_box_holds(c->obox, c->cam_pos, 1)))
+			{ c->obox = origin_box_rule(lo, hi, c->have_camera ? c->cam_pos : nullptr, c->have_camera ? 1u : 0u); c->obox_valid = true; }
+		for (int k = 0; k < 3; k++) { c->sph_lo[k] = lo[k]; c->sph_hi[k] = hi[k]; }
+		if (!same_tree) {
+			if (ref_tree) flatten_bvh(nodes, n_nodes, prims, n_prims, c->wide_host, &c->obox);
+			else { std::vector<b2r_bvh_node> tree; build_traversal_tree(prims, n_prims, tree); flatten_bvh(tree.data(), static_cast<uint32_t>(tree.size()), prims, n_prims, c->wide_host, &c->obox); }
+			c->wide_key = key; c->wide_blob.swap(blob); c->have_wide = true;
 			match_prims_to_geometry(prims, geometry, n_prims, c->wide_host.geom_of_prim);  // which sphere each leaf stands for (b2r_refit_scene); left empty if prims is no permutation of geometry
-		}
+		} else if (std::memcmp(&c->wide_host.ob, &c->obox, sizeof(OriginBox)) != 0) wide_fill_boxes(c->wide_host, c->wide_host.prims.data(), c->obox);  // same topology, boxes for the current origin box
 	}
 	if (c->wide_host.max_stack + 3u > static_cast<uint32_t>(kTraversalStack)) { c->have_wide = false; return fail(B2R_ERR_BVH, "tree needs a deeper traversal stack than kTraversalStack (3 slots of headroom for the branch-free pushes)"); }
 	if (c->wide_host.nodes.size() >= kMaxWideNodes) { c->have_wide = false; return fail(B2R_ERR_BVH, "more than 2^22 traversal nodes (stack entries keep 22 node bits)"); }
@@ -452,7 +493,7 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 	s.prims = c->d_prims; s.prim_mat = c->d_prim_mat; s.mat_albedo = c->d_mat_albedo; s.mat_emission = c->d_mat_emission;
 	s.light_sphere = c->d_light_sphere; s.light_emit = c->d_light_emit; s.wide = c->d_wide; s.hdri = has_ambient ? c->d_hdri : nullptr;
 	s.n_prims = n_prims; s.n_mat = n_mat; s.n_lights = n_lights; s.stack_tn_bits = c->wide_host.tn_bits;
-	s.light_sel_pdf = 1.0f / static_cast<float>(n_lights);  // Renderer.hpp:78
+	s.light_sel_pdf = n_lights ? 1.0f / static_cast<float>(n_lights) : 0.0f;  // Renderer.hpp:78 (no lights: Q15, light sampling is skipped and the MIS weight of an emissive hit is 1)
 	s.ambient[0] = amb[0]; s.ambient[1] = amb[1]; s.ambient[2] = amb[2]; s.has_ambient = has_ambient ? 1 : 0;
 	s.hdri_w = hdri_w; s.hdri_h = hdri_h; s.hdri_fw = static_cast<float>(hdri_w - 1); s.hdri_fh = static_cast<float>(hdri_h - 1);  // Application.cpp:230-231
 	c->use_bvh = (c->cfg.flags & B2R_FLAG_FORCE_BVH) ? true : (c->cfg.flags & B2R_FLAG_FORCE_BRUTE) ? false : n_prims > 32;
@@ -468,7 +509,7 @@ int b2r_refit_scene(b2r_ctx* c, const b2r_sphere* prims, uint32_t n_prims, const
 	if (!c->have_scene || !c->have_wide) return fail(B2R_ERR_STATE, "b2r_refit_scene needs the topology of an earlier b2r_upload_scene");
 	if (n_prims != c->params.scene.n_prims || n_geom != n_prims) return fail(B2R_ERR_ARG, "a refit keeps the sphere count (and BVH order) of the last b2r_upload_scene");
 	if (n_lights && !light_geom_idx) return fail(B2R_ERR_ARG, "null light list");
-	for (uint32_t i = 0; i < n_prims; i++) if (prims[i].material_ID < 0 || static_cast<uint32_t>(prims[i].material_ID) >= n_mat) return fail(B2R_ERR_ARG, "material_ID out of range");
+	for (uint32_t i = 0; i < n_prims; i++) if (prims[i].material_ID < 0 || static_cast<uint32_t>(prims[i].material_ID) >= n_mat || geometry[i].material_ID < 0 || static_cast<uint32_t>(geometry[i].material_ID) >= n_mat) return fail(B2R_ERR_ARG, "material_ID out of range");
 	for (uint32_t i = 0; i < n_lights; i++) if (light_geom_idx[i] < 0 || static_cast<uint32_t>(light_geom_idx[i]) >= n_geom) return fail(B2R_ERR_ARG, "light index out of range");
 	int rc = ensure_device(c); if (rc) return rc;
 	// The caller may have re-sorted its prims (the reference's constructor does on every rebuild, BVH.hpp:201-205): leaf links become
@@ -506,19 +547,22 @@ int b2r_refit_scene(b2r_ctx* c, const b2r_sphere* prims, uint32_t n_prims, const
 	};
 	if ((rc = stage_upload(c, parts, sizeof parts / sizeof parts[0]))) return rc;
 	if (!same_order) c->cur_geom_of_prim.swap(new_geom);
-	// boxes bottom-up on the device: one launch per BFS level, deepest first (stream order is the dependency)
-	const std::vector<uint32_t>& lf = c->wide_host.level_first;
-	for (size_t l = lf.size() - 1; l-- > 0;) {
-		const uint32_t first = lf[l], count = lf[l + 1] - lf[l];
-		k_refit_level<<<(count * 4u + kBlock - 1u) / kBlock, kBlock, 0, c->stream>>>(reinterpret_cast<float4*>(c->d_wide), c->d_prims, same_order ? nullptr : c->d_remap, first, count);
-		c->launches++;
+	// boxes bottom-up on the device, for an origin box that holds the moved spheres
+	{
+		float lo[3], hi[3]; sphere_bounds(prims, n_prims, lo, hi);
+		for (int k = 0; k < 3; k++) { c->sph_lo[k] = lo[k]; c->sph_hi[k] = hi[k]; }
+		const float corners[6] = {lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]};
+		if (!c->obox_valid || !origin_box_holds(c->obox, corners, 2)) {
+			c->obox = origin_box_rule(lo, hi, c->have_camera ? c->cam_pos : nullptr, c->have_camera ? 1u : 0u); c->obox_valid = true;
+			wide_fill_boxes(c->wide_host, c->wide_host.prims.data(), c->obox);  // the as-built tree (reference cost) for the same origin box
+		}
 	}
-	CU(cudaGetLastError());
+	if ((rc = launch_refit_levels(c, same_order ? nullptr : c->d_remap))) return rc;
 	c->wide_refit = true;
 	const SceneDev before = c->params.scene;
 	SceneDev& s = c->params.scene;
 	s.mat_albedo = c->d_mat_albedo; s.mat_emission = c->d_mat_emission; s.light_sphere = c->d_light_sphere; s.light_emit = c->d_light_emit;
-	s.n_mat = n_mat; s.n_lights = n_lights; s.light_sel_pdf = 1.0f / static_cast<float>(n_lights);  // Renderer.hpp:78
+	s.n_mat = n_mat; s.n_lights = n_lights; s.light_sel_pdf = n_lights ? 1.0f / static_cast<float>(n_lights) : 0.0f;  // Renderer.hpp:78
 	if (std::memcmp(&before, &s, sizeof s) != 0) drop_graph(c);
 	if (quality_out) {  // optional: costs one launch and a stream synchronisation
 		CU(cudaMemsetAsync(c->d_cost, 0, sizeof(double), c->stream));
@@ -542,6 +586,8 @@ int b2r_set_camera(b2r_ctx* c, const float pos[3], const float q[4], float half_
 	cam.half_width = half_width; cam.half_height = half_height; cam.z = z; cam.exposure = exposure;
 	if (!c->have_camera || std::memcmp(&cam, &c->params.frame.cam, sizeof cam) != 0) { c->params.frame.cam = cam; drop_graph(c); }
 	c->have_camera = true;
+	c->cam_pos[0] = pos[0]; c->cam_pos[1] = pos[1]; c->cam_pos[2] = pos[2];
+	if (c->have_scene) return ensure_origin_box(c, c->cam_pos, 1);
 	return B2R_OK;
 }
 
@@ -717,6 +763,11 @@ static int trace_common(b2r_ctx* c, const float* rays, const float* tfar_in, uin
 	if (!c->have_scene) return fail(B2R_ERR_STATE, "upload_scene first");
 	if (n == 0) return B2R_OK;
 	int rc = ensure_device(c); if (rc) return rc;
+	if (c->use_bvh) {  // the leaf extents of the traversal tree must cover these ray origins
+		float pts[6] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+		for (uint32_t i = 0; i < n; i++) for (int k = 0; k < 3; k++) { const float v = rays[6 * static_cast<size_t>(i) + k]; if (v == v && fabsf(v) <= FLT_MAX) { pts[k] = fminf(pts[k], v); pts[3 + k] = fmaxf(pts[3 + k], v); } }
+		if (pts[0] <= pts[3] && (rc = ensure_origin_box(c, pts, 2))) return rc;
+	}
 	float *d_rays = nullptr, *d_tin = nullptr, *d_tout = nullptr; int32_t* d_prim = nullptr; uint8_t* d_occ = nullptr;
 	if ((rc = dev_alloc(&d_rays, static_cast<size_t>(n) * 6)) || (rc = dev_alloc(&d_tin, static_cast<size_t>(n))) || (rc = dev_alloc(&d_tout, static_cast<size_t>(n))) ||
 	    (rc = dev_alloc(&d_prim, static_cast<size_t>(n))) || (rc = dev_alloc(&d_occ, static_cast<size_t>(n)))) { cudaFree(d_rays); cudaFree(d_tin); cudaFree(d_tout); cudaFree(d_prim); cudaFree(d_occ); return rc; }
@@ -740,6 +791,12 @@ int b2r_trace_closest(b2r_ctx* c, const float* rays_host, uint32_t n, float* tfa
 int b2r_trace_shadow(b2r_ctx* c, const float* rays_host, const float* tfar_host, uint32_t n, uint8_t* occluded_out) {
 	if (!tfar_host || !occluded_out) return fail(B2R_ERR_ARG, "null argument");
 	return trace_common(c, rays_host, tfar_host, n, 1, nullptr, nullptr, occluded_out);
+}
+int b2r_get_origin_box(b2r_ctx* c, float out[6]) {
+	if (!c || !out) return fail(B2R_ERR_ARG, "null argument");
+	if (!c->obox_valid) return fail(B2R_ERR_STATE, "upload_scene first");
+	for (int k = 0; k < 3; k++) { out[k] = c->obox.lo[k]; out[3 + k] = c->obox.hi[k]; }
+	return B2R_OK;
 }
 int b2r_read_wide_nodes(b2r_ctx* c, void* out_host, uint32_t* n_wide_nodes, uint32_t* max_stack) {
 	if (!c) return fail(B2R_ERR_ARG, "null context");

@@ -426,13 +426,14 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 	const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
-__device__ __forceinline__ void warp_stage_nodes(const WideNode* __restrict__ wide, float4* s_rows /*[32][kNodeRowF4] of this warp*/, uint32_t my_node, uint32_t live) {
+__device__ __forceinline__ void warp_stage_nodes(const WideNode* __restrict__ wide, float4* s_rows /*[32][kNodeRowF4] of this warp*/, uint32_t my_node) {
+	// lanes without a ray pass node 0 (the root, always cached), so the copies need no predicate
 	const uint32_t lane = lane_id(), part = lane & 7u;
 #pragma unroll
 	for (uint32_t j = 0; j < 8; j++) {
 		const uint32_t owner = 4u * j + (lane >> 3);
 		const uint32_t nd = __shfl_sync(0xffffffffu, my_node, owner);
-		if ((live >> owner) & 1u) cp_async16(s_rows + owner * kNodeRowF4 + part, reinterpret_cast<const float4*>(wide + nd) + part);
+		cp_async16(s_rows + owner * kNodeRowF4 + part, reinterpret_cast<const float4*>(wide + nd) + part);
 	}
 	asm volatile("cp.async.wait_all;" ::: "memory");
 	__syncwarp();
@@ -517,7 +518,7 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_closest(const Params p
 		uint32_t live = __ballot_sync(0xffffffffu, active);
 		if (live == 0u) break;
 		do {
-			warp_stage_nodes(wide, rows, t.node, live);
+			warp_stage_nodes(wide, rows, active ? t.node : 0u);
 			if (active && !t.template step_staged<COUNT>(rows + lane_id() * kNodeRowF4, p.scene.stack_tn_bits, &c_sphere, &c_box)) {
 				p.q.H[idx] = make_float2(t.best, __int_as_float(t.prim));
 				active = false;
@@ -651,7 +652,7 @@ __global__ void __launch_bounds__(kTravBlock, 8) k_intersect_shadow(const Params
 		uint32_t live = __ballot_sync(0xffffffffu, active);
 		if (live == 0u) break;
 		do {
-			warp_stage_nodes(wide, rows, node, live);
+			warp_stage_nodes(wide, rows, active ? node : 0u);
 			if (active) {
 				uint32_t next = kNoNode, leaves = 0u;
 				sp = stack.room(sp);
@@ -660,10 +661,9 @@ __global__ void __launch_bounds__(kTravBlock, 8) k_intersect_shadow(const Params
 					const float4 a = row[2 * k], b = row[2 * k + 1];
 					const int32_t l = __float_as_int(b.z);
 					float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, tfar, &tn, &h);
-					const bool inner = l >= 0;
-					if (COUNT && inner) c_box++;
-					if (inner && h) { if (next != kNoNode) stack.put(sp++, next); next = static_cast<uint32_t>(l); }
-					leaves |= (!inner && l != kEmptyLink) ? (1u << k) : 0u;
+					if (COUNT && l != kEmptyLink) c_box++;
+					if (h && l >= 0) { if (next != kNoNode) stack.put(sp++, next); next = static_cast<uint32_t>(l); }
+					leaves |= (h && l < 0) ? (1u << k) : 0u;  // leaf slots whose (inflated) box the ray passes within [0, tfar]
 				}
 				bool occluded = false;
 				while (leaves) {
@@ -762,9 +762,9 @@ __global__ void __launch_bounds__(kBlock) k_resolve(const FrameDev frame, const 
 // Application.cpp:508-509 rebuilds the BVH on every geometry drag. Here the traversal tree keeps its topology and only its boxes
 // are recomputed, on the GPU, from the moved spheres: one launch per BFS level, deepest first (children always sit on a deeper
 // level), four threads per 128-byte node = one per slot (refit_slot, b2r_shade.h; shared with the host twin the tests compare with).
-__global__ void __launch_bounds__(kBlock) k_refit_level(float4* __restrict__ wide, const float4* __restrict__ prims, const uint32_t* __restrict__ remap, const uint32_t first, const uint32_t count) {
+__global__ void __launch_bounds__(kBlock) k_refit_level(float4* __restrict__ wide, const float4* __restrict__ prims, const uint32_t* __restrict__ remap, const OriginBox ob, const uint32_t first, const uint32_t count) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < count * 4u) refit_slot(wide, prims, remap, first + (i >> 2), static_cast<int>(i & 3u));
+	if (i < count * 4u) refit_slot(wide, prims, remap, ob, first + (i >> 2), static_cast<int>(i & 3u));
 }
 // Sum of the inner-slot half areas (the quantity a refit is judged by: cost now / cost when the tree was built).
 __global__ void __launch_bounds__(kBlock) k_tree_cost(const float4* __restrict__ wide, const uint32_t n_nodes, double* __restrict__ out) {

@@ -264,13 +264,52 @@ bool match_prims_to_geometry(const b2r_sphere* prims, const b2r_sphere* geometry
 	return true;
 }
 
-void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* prims, uint32_t n_prims, WideBvh& out) {
-	out.nodes.clear(); out.max_stack = 0; out.depth = 0; out.tn_bits = 31; out.level_first.assign(1, 0u); out.cost = 0.0;
-	auto set_empty = [](WideNode& w, int k) { for (int j = 0; j < 8; j++) w.slot[k][j] = 0.0f; w.slot[k][6] = int_as_float(kEmptyLink); };
-	auto set_leaf = [&](WideNode& w, int k, uint32_t prim) {
-		const b2r_sphere& s = prims[prim];
-		w.slot[k][0] = s.position[0]; w.slot[k][1] = s.position[1]; w.slot[k][2] = s.position[2]; w.slot[k][3] = s.radius_sq;
-		w.slot[k][4] = 0.0f; w.slot[k][5] = 0.0f; w.slot[k][6] = int_as_float(~static_cast<int32_t>(prim)); w.slot[k][7] = 0.0f;
+void sphere_bounds(const b2r_sphere* prims, uint32_t n, float lo[3], float hi[3]) {
+	for (int k = 0; k < 3; k++) { lo[k] = FLT_MAX; hi[k] = -FLT_MAX; }
+	for (uint32_t i = 0; i < n; i++) {
+		const float r = sqrtf(prims[i].radius_sq);
+		for (int k = 0; k < 3; k++) { lo[k] = fminf(lo[k], prims[i].position[k] - r); hi[k] = fmaxf(hi[k], prims[i].position[k] + r); }
+	}
+	if (n == 0) for (int k = 0; k < 3; k++) { lo[k] = 0.0f; hi[k] = 0.0f; }
+}
+OriginBox origin_box_rule(const float sphere_lo[3], const float sphere_hi[3], const float* extra, uint32_t n_extra) {
+	OriginBox ob;
+	for (int k = 0; k < 3; k++) {
+		float lo = sphere_lo[k], hi = sphere_hi[k];
+		for (uint32_t i = 0; i < n_extra; i++) { const float v = extra[3 * static_cast<size_t>(i) + k]; if (v == v) { lo = fminf(lo, v); hi = fmaxf(hi, v); } }
+		const float slack = 0.125f * (hi - lo) + 1.0f;
+		ob.lo[k] = lo - slack; ob.hi[k] = hi + slack;
+	}
+	return ob;
+}
+bool origin_box_holds(const OriginBox& ob, const float* points, uint32_t n_points) {
+	for (uint32_t i = 0; i < n_points; i++) for (int k = 0; k < 3; k++) {
+		const float v = points[3 * static_cast<size_t>(i) + k];
+		if (!(v >= ob.lo[k] && v <= ob.hi[k])) return false;
+	}
+	return true;
+}
+
+void wide_fill_boxes(WideBvh& out, const float4* packed_prims, const OriginBox& ob) {
+	float4* wide = reinterpret_cast<float4*>(out.nodes.data());
+	for (size_t l = out.level_first.size() - 1; l-- > 0;)
+		for (uint32_t i = out.level_first[l]; i < out.level_first[l + 1]; i++) for (int k = 0; k < 4; k++) refit_slot(wide, packed_prims, nullptr, ob, i, k);
+	out.ob = ob;
+	out.cost = wide_cost(out);
+}
+
+void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* prims, uint32_t n_prims, WideBvh& out, const OriginBox* ob_in) {
+	out.nodes.clear(); out.prims.clear(); out.max_stack = 0; out.depth = 0; out.tn_bits = 31; out.level_first.assign(1, 0u); out.cost = 0.0;
+	sphere_bounds(prims, n_prims, out.sphere_lo, out.sphere_hi);
+	const OriginBox ob = ob_in ? *ob_in : origin_box_rule(out.sphere_lo, out.sphere_hi, nullptr, 0);
+	out.ob = ob;
+	// topology first (links only); the boxes are filled afterwards by the refit routine, deepest level first
+	auto set_empty = [](WideNode& w, int k) { for (int j = 0; j < 8; j++) w.slot[k][j] = 0.0f; w.slot[k][4] = w.slot[k][5] = w.slot[k][7] = -1.0e30f; w.slot[k][6] = int_as_float(kEmptyLink); };
+	auto set_link = [&](WideNode& w, int k, int32_t link) { for (int j = 0; j < 8; j++) w.slot[k][j] = 0.0f; w.slot[k][6] = int_as_float(link); };
+	auto fill_boxes = [&]() {
+		out.prims.resize(n_prims);
+		for (uint32_t i = 0; i < n_prims; i++) out.prims[i] = make_float4(prims[i].position[0], prims[i].position[1], prims[i].position[2], prims[i].radius_sq);
+		wide_fill_boxes(out, out.prims.data(), ob);
 	};
 	if (n_prims == 0 || n_nodes == 0) {
 		WideNode w; for (int k = 0; k < 4; k++) set_empty(w, k);
@@ -278,8 +317,8 @@ void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* 
 	}
 	if (nodes[0].prim_count != 0) {  // single sphere: the root is a leaf
 		WideNode w; for (int k = 0; k < 4; k++) set_empty(w, k);
-		set_leaf(w, 0, nodes[0].first_id);
-		out.nodes.push_back(w); out.level_first.push_back(1u); return;
+		set_link(w, 0, ~static_cast<int32_t>(nodes[0].first_id));
+		out.nodes.push_back(w); out.level_first.push_back(1u); out.depth = 1; fill_boxes(); return;
 	}
 	// breadth-first: queue entries are binary inner nodes that become wide nodes
 	struct Pending { uint32_t bin; uint32_t level; };
@@ -298,16 +337,14 @@ void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* 
 			const uint32_t open = kids[pick];
 			kids[pick] = nodes[open].first_id; kids[nk++] = nodes[open].first_id + 1;
 		}
-		// slot order: inner children first, then leaves (lanes of a warp then mostly run the same kind of test per slot)
+		// slot order: inner children first, then leaves
 		std::stable_sort(kids, kids + nk, [&](uint32_t x, uint32_t y) { return (nodes[x].prim_count == 0) > (nodes[y].prim_count == 0); });
 		WideNode w; uint32_t n_inner = 0;
 		for (int k = 0; k < 4; k++) {
 			if (k >= nk) { set_empty(w, k); continue; }
 			const b2r_bvh_node& c = nodes[kids[k]];
-			if (c.prim_count != 0) { set_leaf(w, k, c.first_id); continue; }
-			w.slot[k][0] = pad_down(c.min_bound[0]); w.slot[k][1] = pad_down(c.min_bound[1]); w.slot[k][2] = pad_down(c.min_bound[2]);
-			w.slot[k][3] = pad_up(c.max_bound[0]); w.slot[k][4] = pad_up(c.max_bound[1]); w.slot[k][5] = pad_up(c.max_bound[2]);
-			w.slot[k][6] = int_as_float(static_cast<int32_t>(queue.size())); w.slot[k][7] = 0.0f;  // its wide index = its queue position
+			if (c.prim_count != 0) { set_link(w, k, ~static_cast<int32_t>(c.first_id)); continue; }
+			set_link(w, k, static_cast<int32_t>(queue.size()));  // its wide index = its queue position
 			queue.push_back({kids[k], cur.level + 1});
 			n_inner++;
 		}
@@ -327,7 +364,7 @@ void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* 
 	}
 	out.max_stack = need[0];
 	out.level_first.push_back(static_cast<uint32_t>(out.nodes.size()));
-	out.cost = wide_cost(out);
+	fill_boxes();
 	uint32_t node_bits = 1; while ((1ull << node_bits) < out.nodes.size()) node_bits++;
 	out.tn_bits = std::min(32u - node_bits, 29u);  // >= 2 low key bits are dropped: the kernels keep the slot index there
 }

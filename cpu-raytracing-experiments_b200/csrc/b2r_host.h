@@ -8,17 +8,20 @@
 
 namespace b2r {
 
-// 128-byte traversal node: four 32-byte child slots, each two float4.
-//   inner child : {lo.x, lo.y, lo.z, hi.x} {hi.y, hi.z, link = wide-node index (>= 0), 0}
-//   leaf child  : {c.x,  c.y,  c.z,  r^2 } {0,    0,    link = ~prim_index      (< 0),  0}   (sphere inlined: no leaf fetch)
-//   empty slot  : link = kEmptyLink
-// Child boxes are the reference's binary-node boxes (BVH.hpp:18-27) padded outward by kBoxPad so that the float slab
-// test stays conservative; the spheres are the reference's prims (BVH leaf order), bit-exact.
+// 128-byte traversal node: four 32-byte child slots, each two float4 — a box as centre + half extents in EVERY slot:
+//   inner child : {c.x, c.y, c.z, 0  } {h.x, h.y, link = wide-node index (>= 0), h.z}
+//   leaf child  : {c.x, c.y, c.z, r^2} {H,   H,   link = ~prim_index      (< 0),  H  }   (sphere inlined: no leaf fetch)
+//   empty slot  : link = kEmptyLink, h = -1e30 (its box fails every slab test)
+// A leaf's H is the half extent of a cube around the sphere that contains every ray the float sphere tests can report as a hit
+// (leaf_half_extent, b2r_shade.h); inner boxes are the padded union of their child node's slot boxes (refit_child_box), so the one
+// uniform slab pass of the traversal kernels is conservative for all four slots. The spheres are the reference's prims (BVH leaf
+// order), bit-exact.
 struct alignas(128) WideNode { float slot[4][8]; };
 static_assert(sizeof(WideNode) == 128, "one node = one 128-byte line");
 constexpr int32_t kEmptyLink = INT32_MIN;
 constexpr int kTraversalStack = 64;  // entries per thread; upload fails with B2R_ERR_BVH if a tree needs more
 
+struct OriginBox { float lo[3], hi[3]; };
 struct WideBvh {
 	std::vector<WideNode> nodes;   // nodes[0] = root, breadth-first (top of the tree is contiguous)
 	uint32_t max_stack = 0;        // worst-case traversal stack occupancy for this tree
@@ -26,6 +29,9 @@ struct WideBvh {
 	uint32_t depth = 0;
 	std::vector<uint32_t> level_first;  // nodes of BFS level l are [level_first[l], level_first[l+1]); children always sit on a deeper level
 	double cost = 0.0;             // sum of the inner-slot half areas (what a refit is compared against)
+	float sphere_lo[3] = {0, 0, 0}, sphere_hi[3] = {0, 0, 0};  // bounds of the spheres the tree was built over
+	OriginBox ob{};                // the origin box the leaf extents were computed for
+	std::vector<float4> prims;     // the spheres {c.xyz, r^2} the tree was built over (boxes can be recomputed for another origin box)
 	std::vector<uint32_t> geom_of_prim;  // for b2r_refit_scene: geometry index of the sphere each BVH-order leaf index stands for (empty: unknown)
 };
 
@@ -36,8 +42,17 @@ void build_reference_bvh(const b2r_sphere* geometry, uint32_t n, std::vector<b2r
 bool validate_reference_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, uint32_t n_prims);
 // A second binary tree over the same spheres (reference leaf order kept in the leaf links), built for traversal speed.
 void build_traversal_tree(const b2r_sphere* prims_bvh_order, uint32_t n, std::vector<b2r_bvh_node>& nodes);
-// Collapse the binary tree 2 -> 4 wide and inline the leaf spheres.
-void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* prims, uint32_t n_prims, WideBvh& out);
+// Where ray origins may lie (the leaves' inflated extents depend on how far a ray origin can be from a sphere, b2r_shade.h
+// leaf_half_extent): the bounds of all spheres, plus `extra` points (camera position, caller-supplied ray origins: [n_extra][3]), each
+// side widened by an eighth of the extent + 1 so that small moves of the camera or the spheres keep the box. Deterministic: the host
+// twin of the tests calls the same rule.
+void sphere_bounds(const b2r_sphere* prims, uint32_t n, float lo[3], float hi[3]);
+OriginBox origin_box_rule(const float sphere_lo[3], const float sphere_hi[3], const float* extra, uint32_t n_extra);
+bool origin_box_holds(const OriginBox& ob, const float* points, uint32_t n_points);
+// Collapse the binary tree 2 -> 4 wide, inline the leaf spheres and compute every slot box bottom-up (the refit routine, level by level).
+void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* prims, uint32_t n_prims, WideBvh& out, const OriginBox* ob = nullptr);
+// (Re)compute every slot box of a flattened topology for the spheres `prims` and the origin box `ob` (what flatten_bvh ends with).
+void wide_fill_boxes(WideBvh& tree, const float4* packed_prims /*{c.xyz, r^2}, BVH leaf order*/, const OriginBox& ob);
 // Sum of the inner-slot half areas of a flattened tree (WideBvh::cost; k_tree_cost computes the same sum on the device after a refit).
 double wide_cost(const WideBvh& tree);
 // prims (BVH leaf order) as a permutation of geometry (original order), matched by value — the reference's BVH keeps reordered COPIES

@@ -226,20 +226,25 @@ B2R_HD void rad_zero(float* rad, uint32_t npix, uint32_t pid) {
 // ---------------------------------------------------------------------------------------------- BVH traversal
 // Per-lane traversal of the 4-wide tree, written as a resumable state machine: *_begin() arms a ray, *_step() visits ONE node
 // and returns false when the ray is finished. The persistent kernels keep 32 such machines per warp and refill finished lanes
-// with new rays, so a warp is not held up by its longest ray. Inner slots: slab test clipped to [0, limit]; leaf slots hold
-// the sphere itself (no leaf fetch). Slots are ordered inner-first by the flattener, which keeps the lanes of a warp on the
-// same kind of test. The closest-hit machine visits children nearest first and keeps a short stack in local memory.
+// with new rays, so a warp is not held up by its longest ray.
+//
+// Slot layout (b2r_host.h): A = {c.xyz, r2}, B = {h.x, h.y, link, h.z} — a box as centre + half extents for EVERY slot. A leaf slot
+// holds the sphere itself in A (no leaf fetch) and in h the half extent of a cube that encloses every ray the float sphere tests
+// could report as a hit (leaf_half_extent below), so all four slots of a node run ONE uniform slab pass and a sphere test is only
+// paid for when the ray really passes the sphere's box within [0, best]. The centre/half form needs no per-axis min/max:
+// t_centre = c*inv - o*inv (one FMA), t_half = h*|inv| (>= 0), near = t_centre - t_half, far = t_centre + t_half.
 struct Ray { float ox, oy, oz, dx, dy, dz; };
 
+constexpr float kSlabWiden = 1.0000008f;  // the exit distance is widened by ~7 ulp: rounding of the four operations per plane never rejects a box
 B2R_HD void slab(const float4 a, const float4 b, float ix, float iy, float iz, float nx, float ny, float nz,
                  float limit, float* tnear, bool* hit) {
-	// box = {a.x,a.y,a.z | a.w,b.x,b.y}; t = plane*inv - origin*inv as one FMA (box tests never decide a result)
-	const float x0 = fma_rn(a.x, ix, nx), x1 = fma_rn(a.w, ix, nx);
-	const float y0 = fma_rn(a.y, iy, ny), y1 = fma_rn(b.x, iy, ny);
-	const float z0 = fma_rn(a.z, iz, nz), z1 = fma_rn(b.y, iz, nz);
-	const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
-	const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), limit));
-	*tnear = t0; *hit = t0 <= t1 * 1.0000004f;
+	// box tests never decide a result (they are conservative), so FMA is used freely; a NaN (0 * inf on an axis the ray is parallel
+	// to) drops out of fminf / fmaxf, which leaves that axis unconstrained
+	const float cx = fma_rn(a.x, ix, nx), cy = fma_rn(a.y, iy, ny), cz = fma_rn(a.z, iz, nz);
+	const float hx = b.x * fabsf(ix), hy = b.y * fabsf(iy), hz = b.w * fabsf(iz);
+	const float t0 = fmaxf(fmaxf(fmaxf(cx - hx, cy - hy), cz - hz), 0.0f);
+	const float t1 = fminf(fminf(fminf(cx + hx, cy + hy), cz + hz), limit);
+	*tnear = t0; *hit = t0 <= t1 * kSlabWiden;
 }
 #define B2R_CSWAP(ka, la, kb, lb) { const bool sw = kb < ka; const uint32_t tk = sw ? kb : ka, tl = sw ? lb : la; kb = sw ? ka : kb; lb = sw ? la : lb; ka = tk; la = tl; }
 
@@ -274,12 +279,19 @@ struct TravBase {
 };
 // node access: STAGED = the node's eight float4 were copied to shared memory by the warp (kernels); otherwise read-only LDG
 template <bool STAGED> B2R_HD float4 node_f4(const float4* n, int i) { return STAGED ? n[i] : ldg4(n + i); }
+B2R_HD int first_bit(uint32_t m) {
+#if defined(__CUDA_ARCH__)
+	return __ffs(static_cast<int>(m)) - 1;
+#else
+	return __builtin_ctz(m);
+#endif
+}
 
 // Closest hit == brute force over all spheres (BVH.hpp:311-318): a candidate replaces the best when d < best, or d == best with
-// a lower sphere index (the brute-force loop keeps the first of equal distances, BVH.hpp:265); a node is culled only when its
-// entry distance is beyond the best. Inner slots are slab-tested in one uniform pass; leaf slots are only marked there and
-// their spheres tested in a second, compact loop, so a few lanes with leaves do not drag the whole warp through four
-// sphere tests.
+// a lower sphere index (the brute-force loop keeps the first of equal distances, BVH.hpp:265); a node or a leaf is culled only
+// when its box is entered beyond the best distance. All four slots are slab-tested in one uniform pass; the leaf slots that passed
+// are sphere-tested right away from the staged row (they can only shorten `best`), then the inner slots that passed are ordered by
+// entry distance and re-checked against the possibly shorter `best` before they are pushed.
 template <class Stack>
 struct TravClosestT : TravBase {
 	float best; int32_t prim;
@@ -294,17 +306,12 @@ struct TravClosestT : TravBase {
 			const float4 a = node_f4<STAGED>(n, 2 * k), b = node_f4<STAGED>(n, 2 * k + 1);
 			const int32_t l = as_int(b.z);
 			float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, best, &tn, &h);
-			const bool inner = l >= 0;
-			if (COUNT && inner) (*c_box)++;
-			key[k] = (inner && h) ? bits(tn) : 0xffffffffu; link[k] = static_cast<uint32_t>(l);
-			leaves |= (!inner && l != kEmptyLink) ? (1u << k) : 0u;
+			if (COUNT && l != kEmptyLink) (*c_box)++;
+			key[k] = (h && l >= 0) ? bits(tn) : 0xffffffffu; link[k] = static_cast<uint32_t>(l);
+			leaves |= (h && l < 0) ? (1u << k) : 0u;  // an empty slot's box (h = -1e30) is never hit
 		}
 		while (leaves) {
-#if defined(__CUDA_ARCH__)
-			const int k = __ffs(static_cast<int>(leaves)) - 1;
-#else
-			const int k = __builtin_ctz(leaves);
-#endif
+			const int k = first_bit(leaves);
 			leaves &= leaves - 1u;
 			const float4 sp = node_f4<STAGED>(n, 2 * k); const int32_t id = ~as_int(node_f4<STAGED>(n, 2 * k + 1).z);
 			float d; if (COUNT) (*c_sphere)++;
@@ -318,10 +325,11 @@ struct TravClosestT : TravBase {
 		B2R_CSWAP(key[0], link[0], key[2], link[2]); B2R_CSWAP(key[1], link[1], key[3], link[3]);
 		B2R_CSWAP(key[1], link[1], key[2], link[2]);
 		sp = stack.room(sp);
-		if (key[3] != 0xffffffffu) stack.put(sp++, pack_entry(link[3], key[3], tn_bits));
-		if (key[2] != 0xffffffffu) stack.put(sp++, pack_entry(link[2], key[2], tn_bits));
-		if (key[1] != 0xffffffffu) stack.put(sp++, pack_entry(link[1], key[1], tn_bits));
-		if (key[0] != 0xffffffffu && from_bits(key[0]) <= best) { node = link[0]; return true; }
+		// a miss key is a NaN pattern, so one ordered compare says "hit and still within the best distance"
+		if (from_bits(key[3]) <= best) stack.put(sp++, pack_entry(link[3], key[3], tn_bits));
+		if (from_bits(key[2]) <= best) stack.put(sp++, pack_entry(link[2], key[2], tn_bits));
+		if (from_bits(key[1]) <= best) stack.put(sp++, pack_entry(link[1], key[1], tn_bits));
+		if (from_bits(key[0]) <= best) { node = link[0]; return true; }
 		for (;;) {
 			while (sp > 0) {
 				const uint32_t e = stack.get(--sp);
@@ -350,17 +358,12 @@ struct TravAnyT : TravBase {
 			const float4 a = node_f4<STAGED>(n, 2 * k), b = node_f4<STAGED>(n, 2 * k + 1);
 			const int32_t l = as_int(b.z);
 			float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, tfar, &tn, &h);
-			const bool inner = l >= 0;
-			if (COUNT && inner) (*c_box)++;
-			if (inner && h) { if (next != 0xffffffffu) stack.put(sp++, next); next = static_cast<uint32_t>(l); }
-			leaves |= (!inner && l != kEmptyLink) ? (1u << k) : 0u;
+			if (COUNT && l != kEmptyLink) (*c_box)++;
+			if (h && l >= 0) { if (next != 0xffffffffu) stack.put(sp++, next); next = static_cast<uint32_t>(l); }
+			leaves |= (h && l < 0) ? (1u << k) : 0u;
 		}
 		while (leaves) {
-#if defined(__CUDA_ARCH__)
-			const int k = __ffs(static_cast<int>(leaves)) - 1;
-#else
-			const int k = __builtin_ctz(leaves);
-#endif
+			const int k = first_bit(leaves);
 			leaves &= leaves - 1u;
 			const float4 sp = node_f4<STAGED>(n, 2 * k);
 			if (COUNT) (*c_sphere)++;
@@ -392,44 +395,56 @@ B2R_HD bool traverse_any(const WideNode* __restrict__ wide, const Ray& r, float 
 	return t.occluded;
 }
 
-// ------------------------------------------------------------------ refit (scene edit without a rebuild, Application.cpp:508-509)
-// The box of one inner slot, recomputed from the child wide node it links to: the union of the child's inner-slot boxes (already
-// padded) and of the padded bounds c -+ sqrt(r^2) of its leaf spheres, read from `prims` (BVH leaf order). min/max are exact and the
-// padding is monotonic, so on unchanged spheres this returns exactly what flatten_bvh() stored (pad(union) == union(pad)).
-constexpr float kBoxPad = 4.0e-7f;  // outward padding, relative to |coordinate| + 1
-B2R_HD float pad_down(float v) { return v - (fabsf(v) + 1.0f) * kBoxPad; }
-B2R_HD float pad_up(float v) { return v + (fabsf(v) + 1.0f) * kBoxPad; }
-B2R_HD void refit_child_box(const float4* __restrict__ child /*the 8 float4 of the linked wide node*/, const float4* __restrict__ prims, float4* a_out, float4* b_out, int32_t link) {
+// ------------------------------------------------------------------ slot boxes: build and refit (scene edit, Application.cpp:508-509)
+// Leaf half extent. The closest hit is DEFINED as what the float sphere tests report (== the reference's brute force), and those tests
+// are noisy: with t = c - o the discriminant b^2 - |t|^2 + r^2 cancels at the magnitude |t|^2, so a ray that passes the sphere at
+// perpendicular distance p is reported as a hit whenever p^2 <= r^2 + E with E <= kHitNoise * |t|^2. Bound: the FMA form (BVH.hpp:252-260)
+// makes 3 roundings of b (each <= u|t|, u = 2^-24) -> 2|b| * 3u|t| <= 6u|t|^2, 3 roundings of r^2 - |t|^2 -> 3u|t|^2, |d|^2 = 1 +- 4u
+// -> 4u b^2; the dot-product form of the any-hit test (BVH.hpp:294-300) makes 5 + 1 + 5 + 2 roundings -> <= 18u|t|^2; the box test sees
+// c and o separately, not t = fl(c - o): a shift of <= sqrt(3) u|t| -> < 4u|t|^2. 22u = 1.31e-6; kHitNoise rounds that up. A cube of half
+// extent H = sqrt(r^2 + kHitNoise * D^2) around c therefore contains every ray either test can report, for every ray origin within
+// distance D of c; D is taken over the scene's origin box (all sphere bounds, the camera, caller-supplied ray origins; b2r_host.h).
+constexpr float kHitNoise = 1.5e-6f;
+constexpr float kBoxPad = 4.0e-7f;  // outward padding, relative to |centre| + half extent + 1: covers the roundings of c -+ h below
+B2R_HD float leaf_half_extent(const float4 s /*{c.xyz, r^2}*/, const OriginBox& ob) {
+	const float ex = sel_max(fabsf(s.x - ob.lo[0]), fabsf(ob.hi[0] - s.x)), ey = sel_max(fabsf(s.y - ob.lo[1]), fabsf(ob.hi[1] - s.y)), ez = sel_max(fabsf(s.z - ob.lo[2]), fabsf(ob.hi[2] - s.z));
+	const float far2 = (ex * ex + ey * ey + ez * ez) * 1.0001f;
+	const float h = sqrtf(s.w + kHitNoise * far2);
+	return h + (sel_max(fabsf(s.x), sel_max(fabsf(s.y), fabsf(s.z))) + h + 1.0f) * kBoxPad;
+}
+// The box of one inner slot, recomputed from the child wide node it links to: centre and half extents of the union of the child's
+// slot boxes c -+ h (leaf slots included — their h is the inflated sphere extent), padded. The same routine fills the tree when it is
+// built (flatten_bvh runs it level by level on the host), so a refit with unchanged spheres reproduces the built tree bit for bit.
+B2R_HD void refit_child_box(const float4* __restrict__ child /*the 8 float4 of the linked wide node*/, float4* a_out, float4* b_out, int32_t link) {
 	float lx = FLT_MAX, ly = FLT_MAX, lz = FLT_MAX, hx = -FLT_MAX, hy = -FLT_MAX, hz = -FLT_MAX;
 	for (int j = 0; j < 4; j++) {
 		const float4 ca = child[2 * j], cb = child[2 * j + 1];
-		const int32_t cl = static_cast<int32_t>(bits(cb.z));
-		if (cl == kEmptyLink) continue;
-		float x0, y0, z0, x1, y1, z1;
-		if (cl < 0) {
-			const float4 s = prims[~cl]; const float r = sqrtf(s.w);
-			x0 = pad_down(s.x - r); y0 = pad_down(s.y - r); z0 = pad_down(s.z - r); x1 = pad_up(s.x + r); y1 = pad_up(s.y + r); z1 = pad_up(s.z + r);
-		} else { x0 = ca.x; y0 = ca.y; z0 = ca.z; x1 = ca.w; y1 = cb.x; z1 = cb.y; }
-		lx = sel_min(lx, x0); ly = sel_min(ly, y0); lz = sel_min(lz, z0); hx = sel_max(hx, x1); hy = sel_max(hy, y1); hz = sel_max(hz, z1);
+		if (static_cast<int32_t>(bits(cb.z)) == kEmptyLink) continue;
+		lx = sel_min(lx, ca.x - cb.x); ly = sel_min(ly, ca.y - cb.y); lz = sel_min(lz, ca.z - cb.w);
+		hx = sel_max(hx, ca.x + cb.x); hy = sel_max(hy, ca.y + cb.y); hz = sel_max(hz, ca.z + cb.w);
 	}
-	*a_out = make_float4(lx, ly, lz, hx); *b_out = make_float4(hy, hz, from_bits(static_cast<uint32_t>(link)), 0.0f);
+	const float cx = 0.5f * (lx + hx), cy = 0.5f * (ly + hy), cz = 0.5f * (lz + hz);
+	float ex = sel_max(hx - cx, cx - lx), ey = sel_max(hy - cy, cy - ly), ez = sel_max(hz - cz, cz - lz);
+	ex += (fabsf(cx) + ex + 1.0f) * kBoxPad; ey += (fabsf(cy) + ey + 1.0f) * kBoxPad; ez += (fabsf(cz) + ez + 1.0f) * kBoxPad;
+	*a_out = make_float4(cx, cy, cz, 0.0f); *b_out = make_float4(ex, ey, from_bits(static_cast<uint32_t>(link)), ez);
 }
-// One slot of one wide node: leaf slots take the moved sphere, inner slots the recomputed box. Levels are refit deepest first, so the
-// child node read here already carries its new leaf links. `remap` (may be null = unchanged order) maps the BVH-order index a leaf
+// One slot of one wide node: leaf slots take the (moved) sphere and its inflated extent, inner slots the recomputed box. Levels are
+// processed deepest first, so the child node read here is already final. `remap` (may be null = unchanged order) maps the BVH-order index a leaf
 // held so far to the sphere's index in the new `prims` order (the reference re-sorts its prims on every rebuild, BVH.hpp:201-205, and
 // hit indices must be indices into the current order: Q6 ties, Q9).
-B2R_HD void refit_slot(float4* __restrict__ wide /*8 float4 per node*/, const float4* __restrict__ prims, const uint32_t* __restrict__ remap, uint32_t node, int k) {
+B2R_HD void refit_slot(float4* __restrict__ wide /*8 float4 per node*/, const float4* __restrict__ prims, const uint32_t* __restrict__ remap, const OriginBox& ob, uint32_t node, int k) {
 	float4* slot = wide + static_cast<size_t>(node) * 8 + 2 * k;
 	const int32_t link = static_cast<int32_t>(bits(slot[1].z));
 	if (link == kEmptyLink) return;
 	if (link < 0) {
 		const uint32_t now = remap ? remap[~link] : static_cast<uint32_t>(~link);
-		slot[0] = prims[now]; slot[1].z = from_bits(~now);
+		const float4 s = prims[now]; const float h = leaf_half_extent(s, ob);
+		slot[0] = s; slot[1] = make_float4(h, h, from_bits(~now), h);
 		return;
 	}
-	float4 a, b; refit_child_box(wide + static_cast<size_t>(link) * 8, prims, &a, &b, link);
+	float4 a, b; refit_child_box(wide + static_cast<size_t>(link) * 8, &a, &b, link);
 	slot[0] = a; slot[1] = b;
 }
-B2R_HD float slot_half_area(const float4 a, const float4 b) { const float ex = a.w - a.x, ey = b.x - a.y, ez = b.y - a.z; return ex * ey + ey * ez + ez * ex; }
+B2R_HD float slot_half_area(const float4 /*a*/, const float4 b) { return 4.0f * (b.x * b.y + b.y * b.w + b.w * b.x); }
 
 }  // namespace b2r

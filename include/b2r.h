@@ -54,7 +54,7 @@ enum {
 	B2R_FLAG_COUNT_TESTS = 1u << 3, /* also count sphere / box tests (slower; for roofline accounting) */
 	B2R_FLAG_NO_GRAPH    = 1u << 4, /* launch kernels one by one instead of replaying a CUDA graph (profiling) */
 	B2R_FLAG_REFERENCE_TREE = 1u << 5, /* traverse the flattened REFERENCE tree (BVH.hpp:90-206 topology) instead of the tree built for traversal */
-	B2R_FLAG_REFERENCE_EXACT = 1u << 6, /* brute-force pipeline only, chosen at b2r_create: reproduce the reference's slot-dependent choice of sphere
+	B2R_FLAG_REFERENCE_EXACT = 1u << 6, /* both pipelines, chosen at b2r_create: reproduce the reference's slot-dependent choice of sphere
 	                                     * formula (BVH.hpp:250-286: the last `active % 8` rays of each 16x16 tile's stream take the scalar tail;
 	                                     * stream order = stable counting sort by material, DataStreams.hpp:236-253). Results are then bit-identical
 	                                     * to the reference's own Renderer::Accumulate, at the price of one extra ranking kernel per bounce. */
@@ -192,6 +192,9 @@ int  b2r_trace_closest(b2r_ctx* ctx, const float* rays_host, uint32_t n, float* 
 int  b2r_trace_shadow(b2r_ctx* ctx, const float* rays_host, const float* tfar_host, uint32_t n, uint8_t* occluded_out);
 /* the flattened 128-byte node array (for the layout round-trip test): out may be NULL to size */
 int  b2r_read_wide_nodes(b2r_ctx* ctx, void* out_host, uint32_t* n_wide_nodes, uint32_t* max_stack);
+/* the box ray origins are assumed to lie in ({lo.xyz, hi.xyz}: sphere bounds, camera, origins passed to b2r_trace_*): the leaf slots of the
+ * traversal tree are sized for it, so a host twin of the tree needs the same box (tests) */
+int  b2r_get_origin_box(b2r_ctx* ctx, float lo_hi_out[6]);
 
 /* Image::Store (Image.cpp:71-74 -> stbi_write_hdr with vertical flip, called on F5, Application.cpp:254-257): writes the
  * RGBA32F framebuffer as a Radiance .hdr (32-bit_rle_rgbe, rows written top-down = framebuffer rows in reverse, alpha dropped). */

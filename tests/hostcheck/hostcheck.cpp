@@ -12,11 +12,22 @@ using namespace b2r;
 
 // Host twin of the GPU refit (k_refit_level runs the same shared routine, refit_slot in csrc/b2r_shade.h, one thread per slot and one
 // launch per level): levels deepest first, children always sit on a deeper level. Lives in the test harness — libb2r refits on the GPU only.
-static void refit_wide(WideBvh& tree, const float4* prims, const uint32_t* remap) {
+static void refit_wide(WideBvh& tree, const float4* prims, const uint32_t* remap, const OriginBox& ob) {
 	float4* wide = reinterpret_cast<float4*>(tree.nodes.data());
 	for (size_t l = tree.level_first.size() - 1; l-- > 0;)
-		for (uint32_t i = tree.level_first[l]; i < tree.level_first[l + 1]; i++) for (int k = 0; k < 4; k++) refit_slot(wide, prims, remap, i, k);
+		for (uint32_t i = tree.level_first[l]; i < tree.level_first[l + 1]; i++) for (int k = 0; k < 4; k++) refit_slot(wide, prims, remap, ob, i, k);
 	tree.cost = wide_cost(tree);
+}
+// the origin box of a test: `box6` ({lo.xyz, hi.xyz}, e.g. b2r_get_origin_box of the context under test) when given, else the library's
+// rule over the spheres plus the given points (camera position, ray origins)
+static OriginBox origin_box_of(const b2r_sphere* prims, uint32_t n, const float* box6, const float* points, uint32_t n_points) {
+	if (box6) { OriginBox ob; for (int k = 0; k < 3; k++) { ob.lo[k] = box6[k]; ob.hi[k] = box6[3 + k]; } return ob; }
+	float lo[3], hi[3]; sphere_bounds(prims, n, lo, hi);
+	return origin_box_rule(lo, hi, points, n_points);
+}
+static void ray_origin_bounds(const float* rays, uint32_t n, float out[6]) {
+	for (int k = 0; k < 3; k++) { out[k] = FLT_MAX; out[3 + k] = -FLT_MAX; }
+	for (uint32_t i = 0; i < n; i++) for (int k = 0; k < 3; k++) { out[k] = fminf(out[k], rays[6 * static_cast<size_t>(i) + k]); out[3 + k] = fmaxf(out[3 + k], rays[6 * static_cast<size_t>(i) + k]); }
 }
 
 extern "C" {
@@ -30,8 +41,9 @@ int hc_render_sample(const b2r_sphere* prims, const b2r_bvh_node* nodes, uint32_
                      const float ambient[3], const float* hdri_rgba, int32_t hdri_w, int32_t hdri_h) {  // sky (Primitives.hpp:29-47): hdri may be null when ambient is 0
 	PackedScene ps; pack_scene(prims, n_prims, materials, n_mat, lights, n_lights, geometry, ps);
 	WideBvh wide;
-	if (use_bvh == 2) { std::vector<b2r_bvh_node> tree; build_traversal_tree(prims, n_prims, tree); flatten_bvh(tree.data(), static_cast<uint32_t>(tree.size()), prims, n_prims, wide); }  // what libb2r uploads by default
-	else flatten_bvh(nodes, n_nodes, prims, n_prims, wide);  // B2R_FLAG_REFERENCE_TREE
+	const OriginBox ob = origin_box_of(prims, n_prims, nullptr, cam11, 1);  // spheres + camera position
+	if (use_bvh == 2) { std::vector<b2r_bvh_node> tree; build_traversal_tree(prims, n_prims, tree); flatten_bvh(tree.data(), static_cast<uint32_t>(tree.size()), prims, n_prims, wide, &ob); }  // what libb2r uploads by default
+	else flatten_bvh(nodes, n_nodes, prims, n_prims, wide, &ob);  // B2R_FLAG_REFERENCE_TREE
 	if (wide.max_stack + 3u > static_cast<uint32_t>(kTraversalStack)) return B2R_ERR_BVH;
 	SceneDev sc{};
 	sc.prims = ps.prims.data(); sc.prim_mat = ps.prim_mat.data(); sc.mat_albedo = ps.mat_albedo.data(); sc.mat_emission = ps.mat_emission.data();
@@ -89,8 +101,9 @@ int hc_render_sample(const b2r_sphere* prims, const b2r_bvh_node* nodes, uint32_
 }
 
 // flatten_bvh tap: out may be null to size
-int hc_flatten(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* prims, uint32_t n_prims, void* out, uint32_t* n_wide, uint32_t* max_stack) {
-	WideBvh w; flatten_bvh(nodes, n_nodes, prims, n_prims, w);
+int hc_flatten(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* prims, uint32_t n_prims, void* out, uint32_t* n_wide, uint32_t* max_stack, const float* box6) {
+	const OriginBox ob = origin_box_of(prims, n_prims, box6, nullptr, 0);
+	WideBvh w; flatten_bvh(nodes, n_nodes, prims, n_prims, w, &ob);
 	*n_wide = static_cast<uint32_t>(w.nodes.size()); *max_stack = w.max_stack;
 	if (out) std::memcpy(out, w.nodes.data(), w.nodes.size() * sizeof(WideNode));
 	return 0;
@@ -100,18 +113,22 @@ int hc_flatten(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* pr
 // prims_a, then refit_wide() with prims_b (same order). wide_out may be null to size; cost = sum of inner-slot half areas before / after.
 // remap (may be null): prims_b is in a new order, remap[index in prims_a] = index in prims_b of the same sphere.
 // Optionally traces rays through the refitted tree (closest hit; prim_out = index into prims_b or -1).
+// box6 (may be null): the origin box to size the leaves for (both the build and the refit); default: the library's rule over the spheres
+// of the final tree plus the origins of `rays`.
 int hc_refit(const b2r_sphere* prims_a, const b2r_bvh_node* nodes_a, uint32_t n_nodes, const b2r_sphere* prims_b, const uint32_t* remap, uint32_t n, void* wide_out, uint32_t* n_wide,
-             double cost[2], const float* rays, uint32_t n_rays, float* tfar_out, int32_t* prim_out) {
+             double cost[2], const float* rays, uint32_t n_rays, float* tfar_out, int32_t* prim_out, const float* box6) {
 	WideBvh w;
-	if (n_nodes == 0) { std::vector<b2r_bvh_node> tree; build_traversal_tree(prims_a, n, tree); flatten_bvh(tree.data(), static_cast<uint32_t>(tree.size()), prims_a, n, w); }
-	else flatten_bvh(nodes_a, n_nodes, prims_a, n, w);
+	float ro[6]; if (n_rays) ray_origin_bounds(rays, n_rays, ro);
+	const OriginBox ob_a = origin_box_of(prims_a, n, box6, n_rays ? ro : nullptr, n_rays ? 2u : 0u);
+	if (n_nodes == 0) { std::vector<b2r_bvh_node> tree; build_traversal_tree(prims_a, n, tree); flatten_bvh(tree.data(), static_cast<uint32_t>(tree.size()), prims_a, n, w, &ob_a); }
+	else flatten_bvh(nodes_a, n_nodes, prims_a, n, w, &ob_a);
 	*n_wide = static_cast<uint32_t>(w.nodes.size());
 	if (!wide_out && !n_rays) return 0;
 	cost[0] = w.cost;
 	if (prims_b) {  // null: the tree as flatten_bvh left it
 		std::vector<float4> packed(n);
 		for (uint32_t i = 0; i < n; i++) packed[i] = make_float4(prims_b[i].position[0], prims_b[i].position[1], prims_b[i].position[2], prims_b[i].radius_sq);
-		refit_wide(w, packed.data(), remap);
+		refit_wide(w, packed.data(), remap, origin_box_of(prims_b, n, box6, n_rays ? ro : nullptr, n_rays ? 2u : 0u));
 	}
 	cost[1] = w.cost;
 	if (wide_out) std::memcpy(wide_out, w.nodes.data(), w.nodes.size() * sizeof(WideNode));
@@ -173,8 +190,10 @@ int hc_sphere_any(const float s[4], const float ray[6], float tfar) { return sph
 extern "C" int hc_trace_stats(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* prims, uint32_t n_prims, const float* rays, uint32_t n,
                               uint32_t* steps, uint32_t* boxes, uint32_t* spheres, int32_t* prim_out) {
 	WideBvh w;
-	if (n_nodes == 0) { std::vector<b2r_bvh_node> tn; build_traversal_tree(prims, n_prims, tn); flatten_bvh(tn.data(), static_cast<uint32_t>(tn.size()), prims, n_prims, w); }
-	else flatten_bvh(nodes, n_nodes, prims, n_prims, w);
+	float ro[6]; ray_origin_bounds(rays, n, ro);
+	const OriginBox ob = origin_box_of(prims, n_prims, nullptr, ro, 2);
+	if (n_nodes == 0) { std::vector<b2r_bvh_node> tn; build_traversal_tree(prims, n_prims, tn); flatten_bvh(tn.data(), static_cast<uint32_t>(tn.size()), prims, n_prims, w, &ob); }
+	else flatten_bvh(nodes, n_nodes, prims, n_prims, w, &ob);
 	for (uint32_t i = 0; i < n; i++) {
 		const float* r = rays + 6 * static_cast<size_t>(i);
 		TravClosest t; t.begin(Ray{r[0], r[1], r[2], r[3], r[4], r[5]});
@@ -188,7 +207,9 @@ extern "C" int hc_trace_stats(const b2r_bvh_node* nodes, uint32_t n_nodes, const
 // histogram of visited wide-node indices below `top` (BFS order: the first nodes are the top of the tree): tuning aid
 extern "C" int hc_trace_top_share(const b2r_sphere* prims, uint32_t n_prims, const float* rays, uint32_t n, uint32_t top, uint64_t* visits_top, uint64_t* visits_all) {
 	std::vector<b2r_bvh_node> tn; build_traversal_tree(prims, n_prims, tn);
-	WideBvh w; flatten_bvh(tn.data(), static_cast<uint32_t>(tn.size()), prims, n_prims, w);
+	float ro[6]; ray_origin_bounds(rays, n, ro);
+	const OriginBox ob = origin_box_of(prims, n_prims, nullptr, ro, 2);
+	WideBvh w; flatten_bvh(tn.data(), static_cast<uint32_t>(tn.size()), prims, n_prims, w, &ob);
 	uint64_t a = 0, b = 0;
 	for (uint32_t i = 0; i < n; i++) {
 		const float* r = rays + 6 * static_cast<size_t>(i);

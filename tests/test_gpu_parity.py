@@ -640,13 +640,14 @@ def test_refit_scene_equals_fresh_upload_and_oracle(n, far, flags, keep, hostche
     prims_b = r.scene.prims.copy(); ids_b = r.scene.prim_ids.copy()
     assert keep == np.array_equal(ids_a, ids_b) or n == 9
     # (1) device tree == host twin
-    wide, _ = r.wide_nodes()
+    wide, _ = r.wide_nodes(); obox = r.origin_box()   # the host twin sizes its leaves for the same origin box
     prim_of_geom_b = np.zeros(n, np.uint32); prim_of_geom_b[ids_b] = np.arange(n, dtype=np.uint32)
     remap = np.ascontiguousarray(prim_of_geom_b[ids_a])
     nw = C.c_uint32(0); cost = (C.c_double * 2)(); twin = np.zeros_like(wide)
     use_ref_tree = bool(flags & b2r.FLAG_REFERENCE_TREE)
     hostcheck.hc_refit(C.c_void_p(prims_a.ctypes.data), C.c_void_p(nodes_a.ctypes.data) if use_ref_tree else None, len(nodes_a) if use_ref_tree else 0,
-                       C.c_void_p(prims_b.ctypes.data), C.c_void_p(remap.ctypes.data), n, C.c_void_p(twin.ctypes.data), C.byref(nw), cost, None, 0, None, None)
+                       C.c_void_p(prims_b.ctypes.data), C.c_void_p(remap.ctypes.data), n, C.c_void_p(twin.ctypes.data), C.byref(nw), cost, None, 0, None, None,
+                       C.c_void_p(obox.ctypes.data))
     assert nw.value == len(wide) and wide.tobytes() == twin.tobytes()
     inner = before_wide[:, :, 6].view(np.int32) >= 0
     assert np.array_equal(inner, wide[:, :, 6].view(np.int32) >= 0) and np.array_equal(before_wide[:, :, 6].view(np.int32)[inner], wide[:, :, 6].view(np.int32)[inner])  # topology kept

@@ -139,31 +139,36 @@ def test_flatten_roundtrip():
         # flatten through the host check harness' twin: use the library's own export via a context-free path
         wide = flatten(nodes, prims)
         leaves = {}
+        def box_of(w, k):  # slot layout {c.xyz, r2}{h.x, h.y, link, h.z}: box = c -+ h
+            c = wide[w, k, 0:3].astype(np.float64); h = wide[w, k, [4, 5, 7]].astype(np.float64)
+            return c - h, c + h
         def walk(w, box):
             for k in range(4):
                 link = int(wide[w, k, 6:7].view(np.int32)[0])
                 if link == -2 ** 31: continue
+                lo, hi = box_of(w, k)
+                if box is not None: assert np.all(lo >= box[0] - 1e-3) and np.all(hi <= box[1] + 1e-3)
                 if link < 0:
                     pr = ~link; assert pr not in leaves; leaves[pr] = wide[w, k, :4].copy()
-                    if box is not None:
-                        c, r = prims["position"][pr], np.sqrt(prims["radius_sq"][pr])
-                        assert np.all(c - r >= box[0] - 1e-3) and np.all(c + r <= box[1] + 1e-3)
+                    c, r = prims["position"][pr].astype(np.float64), np.sqrt(float(prims["radius_sq"][pr]))
+                    assert np.all(lo <= c - r) and np.all(hi >= c + r)   # the leaf's cube holds the sphere (and the hit-noise margin)
                 else:
-                    lo, hi = wide[w, k, 0:3], wide[w, k, 3:6]
-                    if box is not None: assert np.all(lo >= box[0] - 1e-3) and np.all(hi <= box[1] + 1e-3)
                     walk(link, (lo, hi))
         walk(0, None)
         assert sorted(leaves) == list(range(n))
         for pr, s in leaves.items():
             assert np.array_equal(s[:3], prims["position"][pr]) and s[3] == prims["radius_sq"][pr]
-        # every wide inner slot is one of the reference's inner-node boxes, padded outward by <= ~1e-6 relative
+        # every wide inner slot contains one of the reference's inner-node boxes and exceeds it by no more than the leaves' hit-noise
+        # margin (H - r <= sqrt(kHitNoise) * origin-box diagonal) plus padding
         inner = nodes[nodes["prim_count"] == 0]
+        r_all = np.sqrt(prims["radius_sq"].astype(np.float64))[:, None]; c_all = prims["position"].astype(np.float64)
+        ext = (c_all + r_all).max(0) - (c_all - r_all).min(0)
+        margin = np.sqrt(1.5e-6) * np.linalg.norm(1.25 * ext + 2.0) * 1.001 + 1e-4
         for w in range(len(wide)):
             for k in range(4):
                 if int(wide[w, k, 6:7].view(np.int32)[0]) < 0: continue
-                lo, hi = wide[w, k, 0:3], wide[w, k, 3:6]
-                tol = (np.abs(inner["min_bound"]) + np.abs(inner["max_bound"]) + 1) * 1e-6
-                ok = np.all((inner["min_bound"] - lo >= 0) & (inner["min_bound"] - lo <= tol) & (hi - inner["max_bound"] >= 0) & (hi - inner["max_bound"] <= tol), axis=1)
+                lo, hi = box_of(w, k)
+                ok = np.all((inner["min_bound"] - lo >= 0) & (inner["min_bound"] - lo <= margin) & (hi - inner["max_bound"] >= 0) & (hi - inner["max_bound"] <= margin), axis=1)
                 assert ok.any()
 
 
@@ -172,8 +177,8 @@ def flatten(nodes, prims):
     from conftest import ROOT
     hc = C.CDLL(os.path.join(ROOT, "tests", "hostcheck", "libhostcheck.so"))
     n = C.c_uint32(0); ms = C.c_uint32(0)
-    hc.hc_flatten(C.c_void_p(nodes.ctypes.data), len(nodes), C.c_void_p(prims.ctypes.data), len(prims), None, C.byref(n), C.byref(ms))
+    hc.hc_flatten(C.c_void_p(nodes.ctypes.data), len(nodes), C.c_void_p(prims.ctypes.data), len(prims), None, C.byref(n), C.byref(ms), None)
     out = np.zeros((n.value, 4, 8), np.float32)
-    hc.hc_flatten(C.c_void_p(nodes.ctypes.data), len(nodes), C.c_void_p(prims.ctypes.data), len(prims), C.c_void_p(out.ctypes.data), C.byref(n), C.byref(ms))
+    hc.hc_flatten(C.c_void_p(nodes.ctypes.data), len(nodes), C.c_void_p(prims.ctypes.data), len(prims), C.c_void_p(out.ctypes.data), C.byref(n), C.byref(ms), None)
     assert ms.value <= 64
     return out

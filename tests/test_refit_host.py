@@ -1,7 +1,7 @@
 """Scene edit without a rebuild (b2r_refit_scene, cf. Application.cpp:508-510), CPU tier: the shared routine `refit_slot`
 (csrc/b2r_shade.h — the code k_refit_level runs per slot) through its host twin `refit_wide`, compiled by tests/hostcheck.
 
-* identity: refitting with unchanged spheres reproduces flatten_bvh's array bit for bit (pad(union) == union(pad));
+* identity: refitting with unchanged spheres reproduces flatten_bvh's array bit for bit (flatten_bvh fills its boxes with the same routine);
 * containment: after moving spheres every inner slot's box contains every sphere below it, leaves hold the moved spheres;
 * semantics: closest hit through the refitted tree == brute force over the moved spheres in the same order (BVH.hpp:265 ties);
 * the quality ratio is 1 on identity and grows when spheres are scattered.
@@ -24,11 +24,11 @@ def vp(a):
 def refit(hc, prims_a, prims_b, nodes=None, rays=None, remap=None):
     n = len(prims_a); nw = C.c_uint32(0); cost = (C.c_double * 2)()
     nn = 0 if nodes is None else len(nodes)
-    hc.hc_refit(vp(prims_a), vp(nodes), nn, vp(prims_b), vp(remap), n, None, C.byref(nw), cost, None, 0, None, None)
+    hc.hc_refit(vp(prims_a), vp(nodes), nn, vp(prims_b), vp(remap), n, None, C.byref(nw), cost, None, 0, None, None, None)
     wide = np.zeros((nw.value, 4, 8), np.float32)
     nr = 0 if rays is None else len(rays)
     tfar = np.zeros(nr, np.float32); prim = np.zeros(nr, np.int32)
-    hc.hc_refit(vp(prims_a), vp(nodes), nn, vp(prims_b), vp(remap), n, vp(wide), C.byref(nw), cost, vp(rays), nr, vp(tfar), vp(prim))
+    hc.hc_refit(vp(prims_a), vp(nodes), nn, vp(prims_b), vp(remap), n, vp(wide), C.byref(nw), cost, vp(rays), nr, vp(tfar), vp(prim), None)
     return wide, (cost[0], cost[1]), tfar, prim
 
 
@@ -52,26 +52,42 @@ def camera_rays(n, rs, prims):
     return np.ascontiguousarray(np.concatenate([o, d], 1), np.float32)
 
 
-def check_contains(wide, prims):
-    """Returns the number of leaves; asserts that every inner slot box contains the bounds of every sphere in its subtree."""
+def origin_box(prims, points=None):
+    """The library's rule (origin_box_rule, csrc/b2r_host.cpp): sphere bounds + points, an eighth of the extent + 1 of slack per side."""
+    r = np.sqrt(prims["radius_sq"].astype(np.float64))[:, None]; c = prims["position"].astype(np.float64)
+    lo, hi = (c - r).min(0), (c + r).max(0)
+    if points is not None and len(points):
+        lo = np.minimum(lo, np.asarray(points, np.float64).min(0)); hi = np.maximum(hi, np.asarray(points, np.float64).max(0))
+    slack = 0.125 * (hi - lo) + 1.0
+    return lo - slack, hi + slack
+
+
+def check_contains(wide, prims, points=None):
+    """Slot layout {c.xyz, r2}{h.x, h.y, link, h.z}. Asserts: every leaf slot holds its sphere and a cube extent H that covers
+    sqrt(r^2 + kHitNoise * D^2) for the farthest origin-box corner D (and is no looser than that plus the padding); every inner slot box
+    contains the union of its child node's slot boxes and is tight around it; every sphere appears exactly once."""
     seen = []
+    olo, ohi = origin_box(prims, points)
 
     def walk(w):
         lo = np.full(3, np.inf); hi = np.full(3, -np.inf)
         for k in range(4):
             link = int(wide[w, k, 6:7].view(np.int32)[0])
             if link == EMPTY: continue
+            c = wide[w, k, 0:3].astype(np.float64); h = wide[w, k, [4, 5, 7]].astype(np.float64)
             if link < 0:
                 pr = ~link; seen.append(pr)
                 assert np.array_equal(wide[w, k, :3], prims["position"][pr]) and wide[w, k, 3] == prims["radius_sq"][pr]
-                r = np.sqrt(prims["radius_sq"][pr]); c = prims["position"][pr]
-                lo = np.minimum(lo, c - r); hi = np.maximum(hi, c + r)
+                assert h[0] == h[1] == h[2]
+                far2 = (np.maximum(np.abs(c - olo), np.abs(ohi - c)) ** 2).sum()
+                need = np.sqrt(float(prims["radius_sq"][pr]) + 1.5e-6 * far2)
+                assert h[0] >= need * (1 - 1e-6) and h[0] <= need * (1 + 2e-4) + (np.abs(c).max() + need + 1) * 1e-6
             else:
                 clo, chi = walk(link)
-                blo, bhi = wide[w, k, 0:3], wide[w, k, 3:6]
+                blo, bhi = c - h, c + h
                 assert np.all(blo <= clo) and np.all(bhi >= chi)                         # conservative
-                assert np.all(clo - blo <= (np.abs(clo) + 1) * 2e-6) and np.all(bhi - chi <= (np.abs(chi) + 1) * 2e-6)  # and tight
-                lo = np.minimum(lo, blo); hi = np.maximum(hi, bhi)
+                assert np.all(clo - blo <= (np.abs(c) + h + 1) * 3e-6) and np.all(bhi - chi <= (np.abs(c) + h + 1) * 3e-6)  # and tight
+            lo = np.minimum(lo, c - h); hi = np.maximum(hi, c + h)
         return lo, hi
     walk(0)
     assert sorted(seen) == list(range(len(prims)))
@@ -103,7 +119,7 @@ def test_refit_moved_spheres_boxes_and_closest_hit(hostcheck, n, far):
     new = moved(prims, rs, far=far)
     rays = camera_rays(3000, rs, prims)
     wide, cost, tfar, prim = refit(hostcheck, prims, new, rays=rays)
-    check_contains(wide, new)
+    check_contains(wide, new, rays[:, :3])
     bt = np.zeros(len(rays), np.float32); bp = np.zeros(len(rays), np.int32)
     hostcheck.hc_closest_brute(vp(new), len(new), vp(rays), len(rays), vp(bt), vp(bp))
     assert (bp >= 0).mean() > 0.2
@@ -136,7 +152,7 @@ def test_refit_into_a_rebuilt_bvh_order(hostcheck, n, far):
     remap = np.ascontiguousarray(prim_of_geom2[ids])
     rays = camera_rays(3000, rs, prims)
     wide, cost, tfar, prim = refit(hostcheck, prims, prims2, rays=rays, remap=remap)
-    check_contains(wide, prims2)
+    check_contains(wide, prims2, rays[:, :3])
     bt = np.zeros(len(rays), np.float32); bp = np.zeros(len(rays), np.int32)
     hostcheck.hc_closest_brute(vp(prims2), n, vp(rays), len(rays), vp(bt), vp(bp))
     assert np.array_equal(bp, prim) and bt.tobytes() == tfar.tobytes()
@@ -176,7 +192,7 @@ def test_refit_fuzz_duplicates_and_random_orders(hostcheck):
         remap = np.ascontiguousarray(prim_of_geom[m_old])
         rays = camera_rays(400, rs, prims)
         wide, _, tfar, prim = refit(hostcheck, prims, prims2, rays=rays, remap=remap)
-        check_contains(wide, prims2)
+        check_contains(wide, prims2, rays[:, :3])
         bt = np.zeros(len(rays), np.float32); bp = np.zeros(len(rays), np.int32)
         hostcheck.hc_closest_brute(vp(prims2), n, vp(rays), len(rays), vp(bt), vp(bp))
         assert bt.tobytes() == tfar.tobytes() and np.array_equal(bp, prim)
