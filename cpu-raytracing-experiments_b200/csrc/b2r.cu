@@ -153,7 +153,7 @@ int compute_grids(b2r_ctx* c) {
 	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<false, false, false>), kBruteBlock, &c->grid_brute))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<true, false, true>), kBruteBlock, &c->grid_brute_first_exact))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<false, false, true>), kBruteBlock, &c->grid_brute_exact))) return rc;
-	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_closest<false, false>), kTravBlock, &c->grid_closest))) return rc;
+	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_closest<false, false, 16u>), kTravBlock, &c->grid_closest))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_shade<false>), kBruteBlock, &c->grid_shade))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_shadow<false>), kTravBlock, &c->grid_shadow))) return rc;
 	c->grid_stream = c->sm_count * 8;
@@ -203,8 +203,12 @@ int enqueue_batch(b2r_ctx* c, bool profile) {
 		if (exact && c->params.scene.n_mat > 64) return fail(B2R_ERR_STATE, "B2R_FLAG_REFERENCE_EXACT: at most 64 materials (RendererPolicy::max_materialID, Renderer.hpp:23)");
 		for (uint32_t b = 0; b < mb; b++) {
 			if ((rc = launch(c, KK_CLOSEST, profile, [&] {
-				if (exact) { if (count) k_intersect_closest<true, true><<<c->grid_closest, kTravBlock, 0, st>>>(p, b); else k_intersect_closest<false, true><<<c->grid_closest, kTravBlock, 0, st>>>(p, b); }
-				else { if (count) k_intersect_closest<true, false><<<c->grid_closest, kTravBlock, 0, st>>>(p, b); else k_intersect_closest<false, false><<<c->grid_closest, kTravBlock, 0, st>>>(p, b); }
+				// stack entries split 16/16 (up to 65536 wide nodes: C3) get immediate shifts; other sizes read the split from the scene
+				const bool tn16 = c->params.scene.stack_tn_bits == 16u;
+#define B2R_CLOSEST(COUNT, EXACT) do { if (tn16) k_intersect_closest<COUNT, EXACT, 16u><<<c->grid_closest, kTravBlock, 0, st>>>(p, b); else k_intersect_closest<COUNT, EXACT, 0u><<<c->grid_closest, kTravBlock, 0, st>>>(p, b); } while (0)
+				if (exact) { if (count) B2R_CLOSEST(true, true); else B2R_CLOSEST(false, true); }
+				else { if (count) B2R_CLOSEST(true, false); else B2R_CLOSEST(false, false); }
+#undef B2R_CLOSEST
 			}))) return rc;
 			if ((rc = launch(c, KK_SHADE, profile, [&] { if (exact) k_shade<true><<<c->grid_shade, kBruteBlock, 0, st>>>(p, b); else k_shade<false><<<c->grid_shade, kBruteBlock, 0, st>>>(p, b); }))) return rc;
 			if (exact && b + 1 < mb) { if ((rc = launch(c, KK_SHADE, profile, [&] { k_stream_rank<<<c->grid_stream, 256, 0, st>>>(p, b); }))) return rc; }

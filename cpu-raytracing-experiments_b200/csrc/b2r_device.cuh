@@ -449,31 +449,31 @@ __device__ __forceinline__ void warp_stage_nodes(const WideNode* __restrict__ wi
 constexpr int kSmemStack = B2R_SMEM_STACK, kEvict = 8;
 constexpr uint32_t kNoNode = 0xffffffffu;
 static_assert(kSmemStack >= kEvict + 3 && kTraversalStack % kEvict == 0, "stack geometry");
-__device__ __forceinline__ void stack_st(uint32_t sm, int i, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(sm + static_cast<uint32_t>(i) * (kTravBlock * 4u)), "r"(v)); }
-__device__ __forceinline__ uint32_t stack_ld(uint32_t sm, int i) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sm + static_cast<uint32_t>(i) * (kTravBlock * 4u))); return v; }
+constexpr uint32_t kStackStride = kTravBlock * 4u;  // bytes between consecutive entries of one thread
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v)); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 // the rare paths are real calls that see only the backing array, so the per-ray state stays in registers
-__device__ __noinline__ int stack_evict(uint32_t sm, uint32_t* backing, int sp) {
-	for (int j = 0; j < kEvict; j++) backing[j] = stack_ld(sm, j);
-	for (int j = kEvict; j < sp; j++) stack_st(sm, j - kEvict, stack_ld(sm, j));
-	return sp - kEvict;
+__device__ __noinline__ void stack_evict(uint32_t base, uint32_t top, uint32_t* backing) {
+	for (int j = 0; j < kEvict; j++) backing[j] = lds_u32(base + j * kStackStride);
+	for (uint32_t a = base + kEvict * kStackStride; a < top; a += kStackStride) sts_u32(a - kEvict * kStackStride, lds_u32(a));
 }
-__device__ __noinline__ void stack_restore(uint32_t sm, const uint32_t* backing) { for (int j = 0; j < kEvict; j++) stack_st(sm, j, backing[j]); }
+__device__ __noinline__ void stack_restore(uint32_t base, const uint32_t* backing) { for (int j = 0; j < kEvict; j++) sts_u32(base + j * kStackStride, backing[j]); }
 struct SmemStack {
-	uint32_t sm;       // 32-bit shared-window address of s_stack[0][threadIdx.x]: every access is one LD/ST.shared with an IMAD'd offset
-	int spilled;       // entries in the backing store
-	uint32_t* backing; // [kTraversalStack] in local memory, declared by the kernel
-	__device__ __forceinline__ void bind(const uint32_t* slot0, uint32_t* local_backing) { sm = static_cast<uint32_t>(__cvta_generic_to_shared(slot0)); backing = local_backing; spilled = 0; }
-	__device__ __forceinline__ void reset() { spilled = 0; }
-	__device__ __forceinline__ void put(int i, uint32_t v) { stack_st(sm, i, v); }
-	__device__ __forceinline__ uint32_t get(int i) const { return stack_ld(sm, i); }
-	__device__ __forceinline__ int room(int sp) {
-		if (sp > kSmemStack - 3) { sp = stack_evict(sm, backing + spilled, sp); spilled += kEvict; }
-		return sp;
+	uint32_t base, top;  // 32-bit shared-window addresses: s_stack[0][threadIdx.x] and the next free entry; a push or pop is one ST/LD.shared and one add
+	int spilled;         // entries in the backing store
+	uint32_t* backing;   // [kTraversalStack] in local memory, declared by the kernel
+	__device__ __forceinline__ void bind(const uint32_t* slot0, uint32_t* local_backing) { base = top = static_cast<uint32_t>(__cvta_generic_to_shared(slot0)); backing = local_backing; spilled = 0; }
+	__device__ __forceinline__ void reset() { top = base; spilled = 0; }
+	__device__ __forceinline__ void push(uint32_t v) { sts_u32(top, v); top += kStackStride; }
+	__device__ __forceinline__ uint32_t pop() { top -= kStackStride; return lds_u32(top); }
+	__device__ __forceinline__ bool empty() const { return top == base; }
+	__device__ __forceinline__ void room() {
+		if (top > base + (kSmemStack - 3) * kStackStride) { stack_evict(base, top, backing + spilled); spilled += kEvict; top -= kEvict * kStackStride; }
 	}
-	__device__ __forceinline__ int refill() {
-		if (spilled == 0) return 0;
-		spilled -= kEvict; stack_restore(sm, backing + spilled);
-		return kEvict;
+	__device__ __forceinline__ bool refill() {
+		if (spilled == 0) return false;
+		spilled -= kEvict; stack_restore(base, backing + spilled); top = base + kEvict * kStackStride;
+		return true;
 	}
 };
 // The traversal kernels run 32 per-lane walks per warp (b2r_shade.h describes the tree and the per-lane state machines). One
@@ -491,7 +491,7 @@ struct SmemStack {
 // closest-hit traversal of queue side (bounce & 1)
 // (63 registers without a minimum-blocks bound = 8 resident CTAs. Measured: bounding it to 8 costs 4 %; 71/79/96 registers with
 // 7/6/5 CTAs cost 3/5/16 %; 56/48 registers with 9/10 CTAs and a shorter shared-memory stack cost 5/8 %.)
-template <bool COUNT, bool EXACT>
+template <bool COUNT, bool EXACT, uint32_t TNB>
 __global__ void __launch_bounds__(kTravBlock) k_intersect_closest(const Params p, const uint32_t bounce) {
 	const uint32_t n_in = p.cnt.paths[bounce];
 	const int side = bounce & 1;
@@ -500,10 +500,12 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_closest(const Params p
 	__shared__ __align__(128) float4 s_nodes[kTravBlock / 32][32 * kNodeRowF4];
 	__shared__ uint32_t s_stack[kSmemStack][kTravBlock];
 	float4* rows = s_nodes[threadIdx.x >> 5];
-	WarpPool pool; TravClosestT<SmemStack> t; bool active = false; uint32_t idx = 0;
+	WarpPool pool; TravClosestT<SmemStack> t; bool active = false, unsent = false; uint32_t idx = 0;
 	uint32_t backing[kTraversalStack];
 	t.node = 0u; t.stack.bind(&s_stack[0][threadIdx.x], backing);
 	for (;;) {
+		// rays that finished since the last refill hand their hit records over together (one dense store instead of one per finish)
+		if (unsent) { p.q.H[idx] = make_float2(t.best, __int_as_float(t.prim)); unsent = false; }
 		const uint32_t got = pool.take(!active, p.cnt.work_a + bounce, n_in);
 		if (got != 0xffffffffu) {
 			idx = got; active = true;
@@ -519,10 +521,7 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_closest(const Params p
 		if (live == 0u) break;
 		do {
 			warp_stage_nodes(wide, rows, active ? t.node : 0u);
-			if (active && !t.template step_staged<COUNT>(rows + lane_id() * kNodeRowF4, p.scene.stack_tn_bits, &c_sphere, &c_box)) {
-				p.q.H[idx] = make_float2(t.best, __int_as_float(t.prim));
-				active = false;
-			}
+			if (active && !t.template step_staged<COUNT, TNB>(rows + lane_id() * kNodeRowF4, p.scene.stack_tn_bits, &c_sphere, &c_box)) { active = false; unsent = true; }
 			live = __ballot_sync(0xffffffffu, active);
 		} while (live != 0u && (pool.dry || __popc(live) >= kRefillBelow));
 	}
@@ -637,9 +636,14 @@ __global__ void __launch_bounds__(kTravBlock, 8) k_intersect_shadow(const Params
 	uint32_t backing[kTraversalStack];
 	SmemStack stack; stack.bind(&s_stack[0][threadIdx.x], backing);
 	WarpPool pool;
-	float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, ix = 0, iy = 0, iz = 0, nx = 0, ny = 0, nz = 0, tfar = 0;
-	uint32_t node = 0u, idx = 0, pid = 0; int sp = 0; bool active = false;
+	float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, ix = 0, iy = 0, iz = 0, nx = 0, ny = 0, nz = 0, ax = 0, ay = 0, az = 0, tfar = 0;
+	uint32_t node = 0u, idx = 0, pid = 0; bool active = false, lit = false;
 	for (;;) {
+		// light samples found unoccluded since the last refill are added together (dense loads and reductions)
+		if (lit) {
+			const f3 L{p.q.SL[idx], p.q.SL[p.q.cap + idx], p.q.SL[2u * p.q.cap + idx]};
+			rad_add(p.rad, p.frame.npix, pid, L, f3{0.0f, 0.0f, 0.0f}, true, false); c_events++; lit = false;
+		}
 		const uint32_t got = pool.take(!active, p.cnt.work_b + bounce, n_in);
 		if (got != 0xffffffffu) {
 			idx = got; active = true;
@@ -647,7 +651,8 @@ __global__ void __launch_bounds__(kTravBlock, 8) k_intersect_shadow(const Params
 			ox = a.x; oy = a.y; oz = a.z; dx = a.w; dy = b.x; dz = b.y; tfar = b.z; pid = __float_as_uint(b.w);
 			ix = 1.0f / dx; iy = 1.0f / dy; iz = 1.0f / dz;
 			nx = -(ox * ix); ny = -(oy * iy); nz = -(oz * iz);
-			node = 0u; sp = 0; stack.reset();
+			ax = fabsf(ix); ay = fabsf(iy); az = fabsf(iz);
+			node = 0u; stack.reset();
 		}
 		uint32_t live = __ballot_sync(0xffffffffu, active);
 		if (live == 0u) break;
@@ -655,14 +660,14 @@ __global__ void __launch_bounds__(kTravBlock, 8) k_intersect_shadow(const Params
 			warp_stage_nodes(wide, rows, active ? node : 0u);
 			if (active) {
 				uint32_t next = kNoNode, leaves = 0u;
-				sp = stack.room(sp);
+				stack.room();
 #pragma unroll
 				for (int k = 0; k < 4; k++) {
 					const float4 a = row[2 * k], b = row[2 * k + 1];
 					const int32_t l = __float_as_int(b.z);
-					float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, tfar, &tn, &h);
+					float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, ax, ay, az, tfar, &tn, &h);
 					if (COUNT && l != kEmptyLink) c_box++;
-					if (h && l >= 0) { if (next != kNoNode) stack.put(sp++, next); next = static_cast<uint32_t>(l); }
+					if (h && l >= 0) { if (next != kNoNode) stack.push(next); next = static_cast<uint32_t>(l); }
 					leaves |= (h && l < 0) ? (1u << k) : 0u;  // leaf slots whose (inflated) box the ray passes within [0, tfar]
 				}
 				bool occluded = false;
@@ -675,13 +680,9 @@ __global__ void __launch_bounds__(kTravBlock, 8) k_intersect_shadow(const Params
 				}
 				if (occluded) active = false;  // the light sample is dropped
 				else {
-					if (next == kNoNode) { if (sp == 0) sp = stack.refill(); if (sp > 0) next = stack.get(--sp); }
+					if (next == kNoNode && (!stack.empty() || stack.refill())) next = stack.pop();
 					node = next;
-					if (next == kNoNode) {  // walked the whole tree without an occluder
-						const f3 L{p.q.SL[idx], p.q.SL[p.q.cap + idx], p.q.SL[2u * p.q.cap + idx]};
-						rad_add(p.rad, p.frame.npix, pid, L, f3{0.0f, 0.0f, 0.0f}, true, false); c_events++;
-						active = false;
-					}
+					if (next == kNoNode) { active = false; lit = true; }  // walked the whole tree without an occluder
 				}
 			}
 			live = __ballot_sync(0xffffffffu, active);

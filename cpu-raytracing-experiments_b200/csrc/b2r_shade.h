@@ -236,14 +236,13 @@ B2R_HD void rad_zero(float* rad, uint32_t npix, uint32_t pid) {
 struct Ray { float ox, oy, oz, dx, dy, dz; };
 
 constexpr float kSlabWiden = 1.0000008f;  // the exit distance is widened by ~7 ulp: rounding of the four operations per plane never rejects a box
-B2R_HD void slab(const float4 a, const float4 b, float ix, float iy, float iz, float nx, float ny, float nz,
+B2R_HD void slab(const float4 a, const float4 b, float ix, float iy, float iz, float nx, float ny, float nz, float ax, float ay, float az,
                  float limit, float* tnear, bool* hit) {
 	// box tests never decide a result (they are conservative), so FMA is used freely; a NaN (0 * inf on an axis the ray is parallel
-	// to) drops out of fminf / fmaxf, which leaves that axis unconstrained
+	// to) drops out of fminf / fmaxf, which leaves that axis unconstrained. (ax, ay, az) = |1/d|.
 	const float cx = fma_rn(a.x, ix, nx), cy = fma_rn(a.y, iy, ny), cz = fma_rn(a.z, iz, nz);
-	const float hx = b.x * fabsf(ix), hy = b.y * fabsf(iy), hz = b.w * fabsf(iz);
-	const float t0 = fmaxf(fmaxf(fmaxf(cx - hx, cy - hy), cz - hz), 0.0f);
-	const float t1 = fminf(fminf(fminf(cx + hx, cy + hy), cz + hz), limit);
+	const float t0 = fmaxf(fmaxf(fmaxf(fma_rn(-b.x, ax, cx), fma_rn(-b.y, ay, cy)), fma_rn(-b.w, az, cz)), 0.0f);
+	const float t1 = fminf(fminf(fminf(fma_rn(b.x, ax, cx), fma_rn(b.y, ay, cy)), fma_rn(b.w, az, cz)), limit);
 	*tnear = t0; *hit = t0 <= t1 * kSlabWiden;
 }
 #define B2R_CSWAP(ka, la, kb, lb) { const bool sw = kb < ka; const uint32_t tk = sw ? kb : ka, tl = sw ? lb : la; kb = sw ? ka : kb; lb = sw ? la : lb; ka = tk; la = tl; }
@@ -255,12 +254,13 @@ B2R_HD void slab(const float4 a, const float4 b, float ix, float iy, float iz, f
 // local memory made the stack the largest L1/L2 client of the first version — more sectors than the nodes themselves).
 constexpr uint32_t kMaxWideNodes = 1u << 22;  // leaves >= 10 bits for the distance
 struct ArrayStack {
-	uint32_t e[kTraversalStack];
-	B2R_HD void put(int i, uint32_t v) { e[i] = v; }
-	B2R_HD uint32_t get(int i) const { return e[i]; }
-	B2R_HD int room(int sp) { return sp; }   // called before the (up to three) pushes of a node visit
-	B2R_HD int refill() { return 0; }        // called when the stack has run empty: entries brought back from a backing store
-	B2R_HD void reset() {}
+	uint32_t e[kTraversalStack]; int sp;
+	B2R_HD void reset() { sp = 0; }
+	B2R_HD void push(uint32_t v) { e[sp++] = v; }
+	B2R_HD uint32_t pop() { return e[--sp]; }
+	B2R_HD bool empty() const { return sp == 0; }
+	B2R_HD void room() {}                    // called before the (up to three) pushes of a node visit
+	B2R_HD bool refill() { return false; }   // called when the stack has run empty: entries brought back from a backing store
 };
 B2R_HD uint32_t pack_entry(uint32_t node, uint32_t tnear_bits, uint32_t tn_bits) { return (node << tn_bits) | (tnear_bits >> (31u - tn_bits)); }
 B2R_HD float entry_tnear(uint32_t e, uint32_t tn_bits) { return from_bits((e & ((1u << tn_bits) - 1u)) << (31u - tn_bits)); }
@@ -269,12 +269,14 @@ B2R_HD uint32_t entry_node(uint32_t e, uint32_t tn_bits) { return e >> tn_bits; 
 struct TravBase {
 	float ox, oy, oz, dx, dy, dz;   // ray
 	float ix, iy, iz, nx, ny, nz;   // 1/d and -o/d
-	uint32_t node; int sp;
+	float ax, ay, az;               // |1/d|
+	uint32_t node;
 	B2R_HD void arm(const Ray& r) {
 		ox = r.ox; oy = r.oy; oz = r.oz; dx = r.dx; dy = r.dy; dz = r.dz;
 		ix = 1.0f / r.dx; iy = 1.0f / r.dy; iz = 1.0f / r.dz;
 		nx = -(r.ox * ix); ny = -(r.oy * iy); nz = -(r.oz * iz);
-		node = 0u; sp = 0;
+		ax = fabsf(ix); ay = fabsf(iy); az = fabsf(iz);
+		node = 0u;
 	}
 };
 // node access: STAGED = the node's eight float4 were copied to shared memory by the warp (kernels); otherwise read-only LDG
@@ -298,14 +300,15 @@ struct TravClosestT : TravBase {
 	bool tail = false;  // B2R_FLAG_REFERENCE_EXACT: this ray sits in the scalar tail of its tile's stream (BVH.hpp:270-286)
 	Stack stack;
 	B2R_HD void begin(const Ray& r, bool scalar_tail = false) { arm(r); best = FLT_MAX; prim = -1; tail = scalar_tail; stack.reset(); }
-	template <bool COUNT, bool STAGED>
-	B2R_HD bool visit(const float4* n, uint32_t tn_bits, uint32_t* c_sphere, uint32_t* c_box) {
+	template <bool COUNT, bool STAGED, uint32_t TNB = 0u>  // TNB != 0: the stack-entry split is a compile-time constant (immediate shifts)
+	B2R_HD bool visit(const float4* n, uint32_t tn_bits_rt, uint32_t* c_sphere, uint32_t* c_box) {
+		const uint32_t tn_bits = TNB ? TNB : tn_bits_rt;
 		uint32_t key[4], link[4]; uint32_t leaves = 0u;
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
 			const float4 a = node_f4<STAGED>(n, 2 * k), b = node_f4<STAGED>(n, 2 * k + 1);
 			const int32_t l = as_int(b.z);
-			float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, best, &tn, &h);
+			float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, ax, ay, az, best, &tn, &h);
 			if (COUNT && l != kEmptyLink) (*c_box)++;
 			key[k] = (h && l >= 0) ? bits(tn) : 0xffffffffu; link[k] = static_cast<uint32_t>(l);
 			leaves |= (h && l < 0) ? (1u << k) : 0u;  // an empty slot's box (h = -1e30) is never hit
@@ -324,32 +327,31 @@ struct TravClosestT : TravBase {
 		B2R_CSWAP(key[0], link[0], key[1], link[1]); B2R_CSWAP(key[2], link[2], key[3], link[3]);
 		B2R_CSWAP(key[0], link[0], key[2], link[2]); B2R_CSWAP(key[1], link[1], key[3], link[3]);
 		B2R_CSWAP(key[1], link[1], key[2], link[2]);
-		sp = stack.room(sp);
+		stack.room();
 		// a miss key is a NaN pattern, so one ordered compare says "hit and still within the best distance"
-		if (from_bits(key[3]) <= best) stack.put(sp++, pack_entry(link[3], key[3], tn_bits));
-		if (from_bits(key[2]) <= best) stack.put(sp++, pack_entry(link[2], key[2], tn_bits));
-		if (from_bits(key[1]) <= best) stack.put(sp++, pack_entry(link[1], key[1], tn_bits));
+		if (from_bits(key[3]) <= best) stack.push(pack_entry(link[3], key[3], tn_bits));
+		if (from_bits(key[2]) <= best) stack.push(pack_entry(link[2], key[2], tn_bits));
+		if (from_bits(key[1]) <= best) stack.push(pack_entry(link[1], key[1], tn_bits));
 		if (from_bits(key[0]) <= best) { node = link[0]; return true; }
 		for (;;) {
-			while (sp > 0) {
-				const uint32_t e = stack.get(--sp);
+			while (!stack.empty()) {
+				const uint32_t e = stack.pop();
 				if (entry_tnear(e, tn_bits) <= best) { node = entry_node(e, tn_bits); return true; }
 			}
-			sp = stack.refill();
-			if (sp == 0) return false;
+			if (!stack.refill()) return false;
 		}
 	}
 	template <bool COUNT>
 	B2R_HD bool step(const WideNode* __restrict__ wide, uint32_t tn_bits, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, false>(reinterpret_cast<const float4*>(wide + node), tn_bits, c_sphere, c_box); }
-	template <bool COUNT>
-	B2R_HD bool step_staged(const float4* n, uint32_t tn_bits, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, true>(n, tn_bits, c_sphere, c_box); }
+	template <bool COUNT, uint32_t TNB = 0u>
+	B2R_HD bool step_staged(const float4* n, uint32_t tn_bits, uint32_t* c_sphere, uint32_t* c_box) { return visit<COUNT, true, TNB>(n, tn_bits, c_sphere, c_box); }
 };
 // Any hit along [0, tfar) — Traverse_shadow semantics (BVH.hpp:290-305): an order-independent boolean.
 template <class Stack>
 struct TravAnyT : TravBase {
 	float tfar; bool occluded;
 	Stack stack;
-	B2R_HD void begin(const Ray& r, float limit) { arm(r); tfar = limit; occluded = false; }
+	B2R_HD void begin(const Ray& r, float limit) { arm(r); tfar = limit; occluded = false; stack.reset(); }
 	template <bool COUNT, bool STAGED>
 	B2R_HD bool visit(const float4* n, uint32_t* c_sphere, uint32_t* c_box) {
 		uint32_t next = 0xffffffffu, leaves = 0u;
@@ -357,9 +359,9 @@ struct TravAnyT : TravBase {
 		for (int k = 0; k < 4; k++) {
 			const float4 a = node_f4<STAGED>(n, 2 * k), b = node_f4<STAGED>(n, 2 * k + 1);
 			const int32_t l = as_int(b.z);
-			float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, tfar, &tn, &h);
+			float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, ax, ay, az, tfar, &tn, &h);
 			if (COUNT && l != kEmptyLink) (*c_box)++;
-			if (h && l >= 0) { if (next != 0xffffffffu) stack.put(sp++, next); next = static_cast<uint32_t>(l); }
+			if (h && l >= 0) { if (next != 0xffffffffu) stack.push(next); next = static_cast<uint32_t>(l); }
 			leaves |= (h && l < 0) ? (1u << k) : 0u;
 		}
 		while (leaves) {
@@ -370,8 +372,8 @@ struct TravAnyT : TravBase {
 			if (sphere_hit_any(sp.x, sp.y, sp.z, sp.w, ox, oy, oz, dx, dy, dz, tfar)) { occluded = true; return false; }
 		}
 		if (next != 0xffffffffu) { node = next; return true; }
-		if (sp == 0) return false;
-		node = stack.get(--sp);
+		if (stack.empty()) return false;
+		node = stack.pop();
 		return true;
 	}
 	template <bool COUNT>
