@@ -1,20 +1,30 @@
 #!/usr/bin/env python
 """bench.py — throughput of the hot path (Renderer::Accumulate x spp + Renderer::Render) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c5] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 One STEP = one frame of the workload: ResetAccumulator, Accumulate() for the workload's sample count, Render().
-Default workload = BASELINE.json configs[1] (C2): Scenes::Default, 1920x1080 (rendered 1920x1088), 64 spp,
-median-of-means with 8 buckets, max_bounces 16, MIS on. `value` is Mrays/s (extension + shadow rays actually traced, counted on
-the device) with the scene resident in HBM; `e2e` is the same through the public API with host buffers (scene upload from host,
-frame download to pinned host memory every step). Prints ONE JSON line on rank 0.
+Default workload = the north-star configuration, BASELINE.json configs[2] (C3): random 100k-sphere BVH scene, 1920x1080 (rendered
+1920x1088), 16 spp, median-of-means with 8 buckets, max_bounces 16, light sampling + MIS. `value` is Mrays/s (extension +
+shadow rays actually traced, counted on the device) with the scene resident in HBM; `e2e` is the same through the public API with host
+buffers (scene upload from host, frame download to pinned host memory every step). Prints ONE JSON line on rank 0, which also carries
 
---impl reference times the reference's CPU path. The reference itself cannot be built here (MSVC-only C++, glm/VCL/PPL absent,
-SURVEY §8c), so this arm runs the oracle port (oracle/liboracle_fast.so, all host threads) on a bounded sample of the same
+  * `parity_checked` / `parity`: before anything is timed the frame the N ranks produce together (buckets split over the ranks, slabs
+    resolved over NVLink into rank 0's framebuffer) is compared byte for byte with the frame ONE GPU renders from the same samples, and
+    with the digest committed under tests/golden/bench_digests.json when there is one; a mismatch aborts the run;
+  * `strong`: the same scene at 128 spp per frame SPLIT over the ranks by bucket (strong scaling), beside the weak-scaling `value`,
+    with the single-GPU time of the same frame measured in the same run (rank 0) and the resulting efficiency;
+  * `e2e_dropin`: the reference's own call pattern — Accumulate() once + Render() per application frame, synchronous copy to host;
+  * `c2` (N=1): the brute-force configuration BASELINE.json quotes second (default 9-sphere scene, 64 spp) as a secondary record with
+    its own reference-kind CPU baseline.
+
+--impl reference times the reference's CPU path on the host cores: the reference's own Renderer<>::Accumulate (oracle/_ref/librefrenderer.so,
+compiled from /root/reference by oracle/ref_renderer_build.sh; brute force over every sphere, as shipped) on a bounded sample of the same
 workload. It is the ONE place besides cpu_baseline where bench.py executes oracle/ code, as the thing being measured on the CPU.
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -36,7 +46,9 @@ WORKLOADS = {
     # C5: progressive convergence run; the frame's 1024 samples are SPLIT over the ranks by bucket (strong scaling)
     "c5": dict(desc="C5 progressive 3840x2160 1024spp on the C3 100k-sphere scene, K=8 buckets split over the GPUs, max_bounces=16", scene="random100000", w=3840, h=2160, spp=1024, mb=16, K=8, strong=True),
 }
+STRONG_SPP = 128   # the `strong` record: this many samples per frame, split over the ranks by bucket
 METRIC, UNIT = "Mrays/s", "Mrays/s"
+DIGESTS = os.path.join(ROOT, "tests", "golden", "bench_digests.json")
 
 
 def make_scene(name):
@@ -130,29 +142,37 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
-# bounded CPU samples: full frames for the 9-sphere scene; a fixed random subset of 16x16 tiles for the BVH scenes (every tile is an
-# independent unit of the reference's parallel_for, Renderer.hpp:75-84), sized for roughly 5-20 s of host time
+# ------------------------------------------------------------------------------------------------ the CPU arm
+# Bounded samples. The 9-sphere scene: a few spp of the full frame. The BVH scenes: the reference brute-forces every ray against every
+# sphere (USEBVH false, BVH.hpp:307), so its sample is one spp of a REDUCED frame (same scene, camera, bounce count; the frame size only
+# sets how many camera rays there are) — roughly 1-5 s on the box's host cores.
+CPU_REF_FRAME = {"c3": (256, 144), "c4": (128, 80), "c5": (256, 144)}
 CPU_TILE_SAMPLE = {"c3": 1024, "c4": 384, "c5": 1024}
 
 
-def cpu_reference_run(wl, scene, samples, first_sample=0):
+def cpu_reference_run(wl, scene, samples, first_sample=0, frame=None):
     """Times THE REFERENCE ITSELF — Renderer<>::Accumulate from /root/reference's Renderer.hpp, compiled into oracle/_ref/librefrenderer.so
     by oracle/ref_renderer_build.sh (brute force, as shipped: USEBVH false) — on all host threads. Rays are not counted by the reference;
-    they are counted by the oracle's slot-exact mode on the same samples (bit-identical paths, tests/test_oracle_ref_renderer.py), untimed."""
+    they are counted by the oracle on the same samples, untimed (slot-exact mode on the 9-sphere scene: bit-identical paths,
+    tests/test_oracle_ref_renderer.py; its BVH mode on the large scenes, where brute-force counting would double the run: same paths up
+    to grazing hits, ray counts within 1e-3)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py
     threads = os.cpu_count() or 1
-    r = oracle_py.ReferenceRenderer(scene, wl["w"], wl["h"], wl["mb"])
+    w, h = frame or (wl["w"], wl["h"])
+    r = oracle_py.ReferenceRenderer(scene, w, h, wl["mb"])
     r.set_accumulations(first_sample)
     t0 = time.perf_counter()
     r.accumulate(samples)
     dt = time.perf_counter() - t0
     r.close()
-    o = oracle_py.Oracle(wl["w"], wl["h"], max_bounces=wl["mb"], K=5, flags=oracle_py.ORC_SLOT_EXACT, fast=True)
+    bvh = wl["scene"] != "default"
+    o = oracle_py.Oracle(w, h, max_bounces=wl["mb"], K=5, flags=oracle_py.ORC_BVH if bvh else oracle_py.ORC_SLOT_EXACT, fast=True)
     o.set_scene(scene); o.set_accumulations(first_sample); o.reset_counters(); o.accumulate(samples, threads=threads)
     c = o.counters(); rays = c["extension_rays"] + c["shadow_rays"]; o.close()
-    return dict(seconds=dt, rays=rays, paths=wl["w"] * wl["h"] * samples, threads=threads, what=f"{samples} spp of the {wl['w']}x{wl['h']} frame",
-                mode="the reference's own Renderer::Accumulate (Renderer.hpp, g++ -O2 -mavx2 -mfma, brute force as shipped), tiles over all host threads",
+    what = f"{samples} spp of the {w}x{h} frame" + (f" (reduced from {wl['w']}x{wl['h']}: the reference tests every ray against all {len(scene['geometry'])} spheres)" if frame else "")
+    return dict(seconds=dt, rays=rays, paths=w * h * samples, threads=threads, what=what,
+                mode="the reference's own Renderer::Accumulate (Renderer.hpp, g++ -O2 -mavx2 -mfma, brute force as shipped, PPL stand-in spawning its threads per parallel_for), tiles over all host threads",
                 kind="reference")
 
 
@@ -178,7 +198,7 @@ def cpu_oracle_run(wl, scene, samples, fast=True, workload_name=None):
     c = o.counters(); rays = c["extension_rays"] + c["shadow_rays"]
     o.close()
     what = f"{samples} spp of {n_tiles} of the {n_tiles_all} 16x16 tiles of the {wl['w']}x{wl['h']} frame" if n_tiles < n_tiles_all else f"{samples} spp of the {wl['w']}x{wl['h']} frame"
-    return dict(seconds=dt, rays=rays, paths=n_tiles * 256 * samples, threads=threads, what=what,
+    return dict(seconds=dt, rays=rays, paths=n_tiles * 256 * samples, threads=threads, what=what, kind="port",
                 mode="stream-BVH (BVH.hpp:320-358 restated)" if bvh else "brute force (as shipped, USEBVH false)")
 
 
@@ -187,266 +207,393 @@ def run_reference(args, wl, rank):
     if rank != 0:
         return
     scene = make_scene(wl["scene"])
-    per_step = 4 if wl["scene"] == "default" else 1  # a few spp of the workload's frame per step: a bounded sample (~0.1-20 s on the host cores)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py
-    # The reference itself when it is runnable for this workload: it ships brute force only (USEBVH false), so the 9-sphere
-    # configurations; max_bounces must be one of the instantiated template values. The BVH workloads keep the oracle port
-    # (stream-BVH restatement): brute force over 1e5-1e6 spheres is ~1e11-1e12 sphere tests per bounce pass.
-    use_ref = wl["scene"] == "default" and oracle_py.have_reference_renderer() and wl["mb"] in oracle_py.REF_MAX_BOUNCES
-    run = (lambda k: cpu_reference_run(wl, scene, per_step, first_sample=k * per_step)) if use_ref else (lambda k: cpu_oracle_run(wl, scene, per_step, workload_name=args.workload))
+    bvh = wl["scene"] != "default"
+    per_step = 1 if bvh else 4
+    # the reference itself whenever it is runnable here (oracle/_ref travels with the repo; max_bounces must be one of the instantiated
+    # template values); otherwise the oracle port
+    use_ref = oracle_py.have_reference_renderer() and wl["mb"] in oracle_py.REF_MAX_BOUNCES and not args.cpu_port
+    frame = CPU_REF_FRAME.get(args.workload) if bvh else None
+    run = (lambda k: cpu_reference_run(wl, scene, per_step, first_sample=k * per_step, frame=frame)) if use_ref else (lambda k: cpu_oracle_run(wl, scene, per_step, workload_name=args.workload))
     for k in range(args.warmup):
         run(k)
     secs, rays, paths = 0.0, 0, 0
-    threads = mode = None
+    threads = mode = what = None
     for k in range(args.steps):
-        r = run(k); secs += r["seconds"]; rays += r["rays"]; paths += r["paths"]; threads, mode = r["threads"], r["mode"]; what = r["what"]
+        r = run(k); secs += r["seconds"]; rays += r["rays"]; paths += r["paths"]; threads, mode, what = r["threads"], r["mode"], r["what"]
     v = rays / secs / 1e6
     kind = "reference" if use_ref else "port"
     sample = f"{what} per step ({paths // args.steps} paths), {args.steps} steps; " + (mode if use_ref else f"oracle port -O3 -march=native, {mode}")
+    extra = None
+    if use_ref and bvh and not args.no_port_line:  # beside it: what a CPU does with the (disabled) stream-BVH branch of the reference, restated by the oracle
+        p = cpu_oracle_run(wl, scene, 1, workload_name=args.workload)
+        extra = {"value": p["rays"] / p["seconds"] / 1e6, "unit": UNIT, "kind": "port", "sample": f"{p['what']}; oracle port -O3 -march=native, {p['mode']} — the branch the reference compiles out (USEBVH false)"}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["desc"]}, "paths_per_s": paths / secs,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "cpu_stream_bvh_port": extra,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": ("oracle/_ref/librefrenderer.so: the reference's Renderer.hpp and the headers it includes, compiled from /root/reference by oracle/ref_renderer_build.sh "
-                 "(stand-ins for ppl.h / Image.h / glm / VCL, six token-level syntax edits)") if use_ref else
-                "the reference ships brute force only; for BVH workloads (or without oracle/_ref) the oracle port is timed",
+                 "(stand-ins for ppl.h / Image.h / glm / VCL, six token-level syntax edits; -O2, and the PPL stand-in starts its threads per parallel_for call: a few per cent against the CPU arm)") if use_ref else
+                "oracle port (oracle/_ref absent, or --cpu-port)",
     }))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1); ap.add_argument("--steps", type=int, default=20); ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"]); ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--no-cpu-baseline", action="store_true"); ap.add_argument("--no-profile-pass", action="store_true")
-    ap.add_argument("--samples-in-flight", type=int, default=0, help="0 = library default (auto)")
-    ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel (for ncu); never used for a reported number")
-    ap.add_argument("--reference-exact", action="store_true", help="brute-force workloads: B2R_FLAG_REFERENCE_EXACT (bit-identical to the reference's own renderer; one extra ranking kernel per bounce)")
-    ap.add_argument("--combine", default="p2p", choices=["p2p", "nccl"], help="multi-GPU frame combine: resolve kernel reads peer buckets over NVLink (p2p) or NCCL all-reduce then resolve")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 0)
-    wl = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, wl, rank); return
+# ------------------------------------------------------------------------------------------------ the GPU arm
+def sha(a):
+    return hashlib.sha256(a.tobytes()).hexdigest()
 
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    import __graft_entry__ as entry
-    if rank == 0:
-        entry.build()
-    if world > 1:
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-        dist.barrier()
-    import b2r, b2r_dist
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: libb2r has no CPU fallback")
-    dev = torch.device(f"cuda:{local}"); torch.cuda.set_device(dev)
-    warm = max(args.warmup, 3)
 
-    scene = make_scene(wl["scene"])
-    ps = b2r.PreparedScene(scene, wl["w"], wl["h"])  # host BVH build + light list: scene (re)build, outside the hot path
-    stream = torch.cuda.Stream(device=dev)  # a real (non-default) stream: the library launches on it and the timing events are recorded on it
-    torch.cuda.set_stream(stream)
-    K, spp = wl["K"], wl["spp"]
-    base_flags = b2r.FLAG_REFERENCE_EXACT if (args.reference_exact and wl["scene"] == "default") else 0
-    shard = b2r_dist.shard_kwargs(rank, world, K)
-    r = b2r.Renderer(ps, wl["w"], wl["h"], max_bounces=wl["mb"], buckets=K, device=local, stream=stream.cuda_stream,
-                     samples_in_flight=args.samples_in_flight, flags=(b2r.FLAG_NO_GRAPH if args.no_graph else 0) | base_flags, **shard)
-    # weak scaling: every rank renders `spp` samples of its own buckets per step => world*spp sample indices per step
-    # (C5 is the strong-scaling run: the frame's spp are divided among the ranks)
-    strong = bool(wl.get("strong"))
-    step_samples = spp if strong else spp * world
-    local_buckets = b2r_dist.buckets_tensor(r, dev)
-    use_p2p = world > 1 and args.combine == "p2p"
-    if use_p2p:
-        b2r_dist.open_peers(r)
+class Bench:
+    """One workload on this rank's GPU; every rank of the job builds the same object (SPMD)."""
 
-    dbg = bool(os.environ.get("B2R_BENCH_DEBUG"))
+    def __init__(self, args, name, rank, world, local, stream, dev):
+        import b2r, b2r_dist
+        self.b2r, self.dist_mod = b2r, b2r_dist
+        self.args, self.name, self.wl, self.rank, self.world, self.local, self.stream, self.dev = args, name, WORKLOADS[name], rank, world, local, stream, dev
+        wl = self.wl
+        self.scene = make_scene(wl["scene"])
+        self.ps = b2r.PreparedScene(self.scene, wl["w"], wl["h"])  # host BVH build + light list: scene (re)build, outside the hot path (SURVEY §3.4)
+        self.K, self.spp = wl["K"], wl["spp"]
+        self.base_flags = b2r.FLAG_REFERENCE_EXACT if (args.reference_exact and wl["scene"] == "default") else 0
+        self.strong = bool(wl.get("strong"))
+        self.step_samples = self.spp if self.strong else self.spp * world   # weak scaling: every rank renders `spp` samples of its own buckets per step
+        self.r = self.renderer(sharded=True, flags=(b2r.FLAG_NO_GRAPH if args.no_graph else 0) | self.base_flags)
+        self.use_team = world > 1 and args.combine == "team"
+        self.use_p2p = world > 1 and args.combine == "p2p"
+        if self.use_team:
+            b2r_dist.open_team(self.r)
+        elif self.use_p2p:
+            b2r_dist.open_peers(self.r)
+        self.local_buckets = b2r_dist.buckets_tensor(self.r, dev) if (world > 1 and args.combine == "nccl") else None
+        self.frame_no = 0
 
-    frame_no = [0]
+    def renderer(self, sharded, flags=0, samples_in_flight=None):
+        wl = self.wl
+        shard = self.dist_mod.shard_kwargs(self.rank, self.world, self.K) if sharded else dict(bucket_first=0, bucket_stride=0)
+        return self.b2r.Renderer(self.ps, wl["w"], wl["h"], max_bounces=wl["mb"], buckets=self.K, device=self.local, stream=self.stream.cuda_stream,
+                                 samples_in_flight=self.args.samples_in_flight if samples_in_flight is None else samples_in_flight, flags=flags, **shard)
 
-    def step(to_host_fb=None, upload=False, async_fbs=None):
-        t0 = time.perf_counter()
-        if upload:
-            r.SetScene(ps)  # host -> device: spheres, materials, lights, flattened BVH, camera
-        t1 = time.perf_counter()
-        r.ResetAccumulator()
-        r.Accumulate(step_samples)
-        if dbg:
-            r.sync(); print(f"[dbg] upload {t1 - t0:.4f}s accumulate {time.perf_counter() - t1:.4f}s", file=sys.stderr)
-        t2 = time.perf_counter()
-        if use_p2p:
-            # fused combine: rank 0's resolve kernel pulls every bucket from its owner over NVLink. The two barriers order it after
-            # every rank's last bounce and before any rank's next ResetAccumulator.
-            r.sync(); dist.barrier()
-            ok = r.RenderPeers(to_host=to_host_fb is not None, out=to_host_fb) if rank == 0 else True
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
             dist.barrier()
-        elif world > 1:
-            combined = b2r_dist.combine_buckets(local_buckets)  # the one collective: NCCL all-reduce of the bucket sums
-            ok = r.Render(to_host=to_host_fb is not None and rank == 0, out=to_host_fb, dev_buckets=combined.data_ptr())
+        torch.cuda.synchronize(self.dev)
+
+    def step(self, samples=None, to_host_fb=None, upload=False, async_fbs=None):
+        """One frame. Multi-GPU (team mode): nothing here waits for another rank on the host — the ranks hand the frame over through flags
+        in peer memory, and with async_fbs rank 0's D2H copy of frame N overlaps the tracing of frame N+1 exactly as on one GPU."""
+        import torch.distributed as dist
+        r = self.r
+        if upload:
+            r.SetScene(self.ps)  # host -> device: spheres, materials, lights, flattened BVH, camera
+        r.ResetAccumulator()
+        r.Accumulate(self.step_samples if samples is None else samples)
+        if self.use_team:
+            if async_fbs is not None:
+                ok = r.RenderTeam(out=async_fbs[self.frame_no & 1], use_async=True); self.frame_no += 1
+            else:
+                ok = r.RenderTeam(to_host=to_host_fb is not None, out=to_host_fb)
+        elif self.use_p2p:  # round-1 path, kept for comparison: rank 0 resolves everything, two host barriers per frame
+            r.sync(); dist.barrier()
+            ok = r.RenderPeers(to_host=to_host_fb is not None, out=to_host_fb) if self.rank == 0 else True
+            dist.barrier()
+        elif self.world > 1:
+            r.sync()
+            combined = self.dist_mod.combine_buckets(self.local_buckets)  # NCCL all-reduce of the bucket sums, then every rank resolves
+            ok = r.Render(to_host=to_host_fb is not None and self.rank == 0, out=to_host_fb, dev_buckets=combined.data_ptr())
         elif async_fbs is not None:
             # progressive rendering as a user would drive it: frame N is copied out on the library's second stream into one of two pinned
             # buffers while the samples of frame N+1 are traced (b2r_resolve_async); nothing is skipped, every frame lands on the host
-            ok = r.RenderAsync(async_fbs[frame_no[0] & 1]); frame_no[0] += 1
+            ok = r.RenderAsync(async_fbs[self.frame_no & 1]); self.frame_no += 1
         else:
             ok = r.Render(to_host=to_host_fb is not None, out=to_host_fb)
         assert ok
-        if dbg:
-            print(f"[dbg] render {time.perf_counter() - t2:.4f}s total {time.perf_counter() - t0:.4f}s", file=sys.stderr)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def timed(n, **kw):
-        barrier()
+    def timed(self, n, **kw):
+        """n steps between two barriers, timed with CUDA events on the launching stream; max over ranks."""
+        import torch
+        import torch.distributed as dist
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
+        e0.record(self.stream)
         for _ in range(n):
-            step(**kw)
-        if kw.get("async_fbs") is not None:
-            r.WaitFrame()  # the last frame has landed in host memory before the clock stops
-        e1.record(stream)
-        barrier()
+            self.step(**kw)
+        if kw.get("async_fbs") is not None and (self.world == 1 or self.rank == 0):
+            self.r.WaitFrame()  # the last frame has landed in host memory before the clock stops
+        e1.record(self.stream)
+        self.barrier()
         ms = e0.elapsed_time(e1)
-        if dbg:
-            print(f"[dbg] timed region {ms:.2f} ms for {n} steps", file=sys.stderr)
-        if world > 1:
-            t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
         return ms
 
+    def rays(self, cnt):
+        import torch
+        import torch.distributed as dist
+        v = [cnt["extension_rays"] + cnt["shadow_rays"], cnt["launches"]]
+        if self.world > 1:
+            t = torch.tensor(v, device=self.dev, dtype=torch.float64); dist.all_reduce(t); v = [float(t[0]), float(t[1])]
+        return float(v[0]), int(v[1])
+
+    # ---- parity: the frame the job produces == the frame one GPU renders from the same samples (== the committed digest, if any)
+    def parity(self, samples, tag):
+        import numpy as np
+        import torch
+        wl = self.wl
+        fb = np.zeros((wl["h"], wl["w"], 4), np.float32)
+        self.step(samples=samples, to_host_fb=fb)
+        self.barrier()
+        out = None
+        if self.rank == 0:
+            # one GPU, no bucket split, a different batching (4 samples in flight, launched kernel by kernel instead of a replayed graph)
+            single = self.renderer(sharded=False, flags=self.b2r.FLAG_NO_GRAPH | self.base_flags, samples_in_flight=4)
+            single.Accumulate(samples); assert single.Render()
+            ref = single.framebuffer.copy(); single.close()
+            same = fb.tobytes() == ref.tobytes()
+            key = f"{self.name}:{samples}spp" + (":exact" if self.base_flags else "")
+            golden = json.load(open(DIGESTS)).get(key) if os.path.exists(DIGESTS) else None
+            out = {"frame_sha256": sha(fb), "single_gpu_frame_sha256": sha(ref), "identical": bool(same), "samples_per_frame": samples, "what": tag,
+                   "against": "one GPU rendering the same sample indices without the bucket split, 4 samples in flight, kernel-by-kernel launches",
+                   "committed_digest": golden, "matches_committed_digest": (golden == sha(fb)) if golden else None, "digest_key": key}
+            if not same:
+                bad = float((fb != ref).any(axis=2).mean())
+                raise SystemExit(f"bench.py: PARITY FAILURE ({tag}): the {self.world}-GPU frame differs from the single-GPU frame in {bad:.3e} of the pixels")
+        self.barrier()
+        if self.use_team and self.r.team_error():
+            raise SystemExit("bench.py: a team hand-shake timed out")
+        return out
+
+    def close(self):
+        if self.use_team:
+            self.barrier(); self.r.team_close()
+        self.r.close()
+
+
+def roofline(b, kt, pc, steps, hbm_peak, peak_src, sm_max):
+    """Per-kernel roofline rows from the kernel-by-kernel pass (CUDA event pair around every launch) and the device counters of the same
+    steps. Algorithmic bytes / flops: DESIGN.md §5. The top-level keys describe the dominant kernel; `kernels` lists every kernel of the step."""
+    wl, world, ps = b.wl, b.world, b.ps
+    total_kernel_ms = sum(v[0] for v in kt.values())
+    ext, shadow, hits, events, dropped = pc["extension_rays"], pc["shadow_rays"], pc["shaded_hits"], pc["radiance_events"], pc["dropped"]
+    box, sph = pc.get("box_tests", 0), pc.get("sphere_tests", 0)
+    npix = wl["w"] * wl["h"]
+    primaries = npix * (b.step_samples // world) * steps
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    rows = {}
+
+    def row(kind, name, alg_bytes, flops=None, note=None):
+        ms, n = kt[kind]
+        if not n:
+            return
+        ach = alg_bytes / (ms / 1e3) / 1e9
+        rows[name] = {"ms_per_step": ms / steps, "launches_per_step": n / steps, "avg_launch_ms": ms / n, "share_of_step": ms / total_kernel_ms if total_kernel_ms else None,
+                      "algorithmic_bytes_per_launch": alg_bytes / n, "hbm_achieved_gbs": ach, "hbm_frac": ach / hbm_peak}
+        if flops is not None:
+            rows[name]["fp32_achieved_tflops"] = flops / (ms / 1e3) / 1e12; rows[name]["fp32_frac"] = flops / (ms / 1e3) / 1e12 / fp32_peak
+        if note:
+            rows[name]["note"] = note
+    if kt["bounce_brute"][1]:
+        n_prims = len(ps.prims)
+        row("bounce_brute", "k_bounce_brute", 88.0 * (ext - primaries) + 12.0 * primaries + 24.0 * events + 12.0 * dropped,
+            20.0 * n_prims * (ext + shadow) + 250.0 * hits, "44 B path record read + 44 B written per non-primary ray, 12 B radiance entry per primary path, 24 B per contribution; 20 flop per sphere test (shadow tests at their upper bound), 250 per shaded hit")
+        dom = "k_bounce_brute"
+    else:
+        # COUNT_TESTS counters of the same steps split between the two traversal kernels in proportion to their rays (the counters are not
+        # kept per kernel): 25 flop per slab test, 20 per sphere test (SURVEY §8d)
+        fl = 25.0 * box + 20.0 * sph
+        share_c = ext / max(ext + shadow, 1)
+        row("generate", "k_generate", 56.0 * primaries, None, "44 B path record + 12 B radiance entry written per primary path")
+        row("intersect_closest", "k_intersect_closest", 40.0 * ext, fl * share_c if box else None, "32 B ray read + 8 B hit record written per extension ray; nodes (128 B per visit) are L2-resident and not counted")
+        row("shade", "k_shade", (8.0 + 44.0) * ext + 44.0 * (ext - primaries) + 44.0 * shadow + 24.0 * (events - 0), 250.0 * hits, "hit record + path record read per ray, path record written per continuing path, 44 B per shadow ray queued, 24 B per radiance contribution; 250 flop per shaded hit")
+        row("intersect_shadow", "k_intersect_shadow", 32.0 * shadow + 12.0 * shadow, fl * (1 - share_c) if box else None, "32 B ray read per shadow ray + its 12 B light sample when unoccluded (upper bound)")
+        dom = "k_intersect_closest"
+    s_gpu = b.step_samples // world
+    slots = b.args.samples_in_flight or min(64, max(4, (128 << 20) // npix))   # the library's default batch width (alloc_frame)
+    n_batches = -(-s_gpu // slots); k_touched = min(wl["K"] // world if world > 1 else wl["K"], min(s_gpu, slots))
+    row("accumulate", "k_accumulate", float(npix) * (12.0 * s_gpu + 24.0 * k_touched * n_batches) * steps, None, "12 B radiance read per (sample, pixel) + 24 B bucket read-modify-write per pixel, bucket and batch")
+    row("resolve", "k_resolve", (12.0 * wl["K"] + 16.0) * npix * steps / world, None, "K bucket sums read + RGBA32F written per pixel (a rank resolves its slab)")
+    d = rows[dom]
+    out = {"bound": "hbm", "kernel": dom, "achieved": d["hbm_achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": d["hbm_frac"], "traffic": None,
+           "peak_source": peak_src, "avg_launch_ms": d["avg_launch_ms"], "launches": int(kt["bounce_brute" if dom == "k_bounce_brute" else "intersect_closest"][1]),
+           "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"], "kernel_share_of_step": d["share_of_step"],
+           "timing": "CUDA event pair around every launch, non-graph pass of the same steps on the launching stream",
+           "note": "the traversal and brute-force kernels are bound by instruction issue and the L1/shared-memory data pipe, not by HBM: `fp32`, `issue` and `l1` say how close they are to those; `frac` is the HBM fraction the contract asks for",
+           "fp32_peak_tflops": fp32_peak, "kernels": rows}
+    if "fp32_achieved_tflops" in d:
+        out["fp32"] = {"achieved_tflops": d["fp32_achieved_tflops"], "peak_tflops": fp32_peak, "frac": d["fp32_frac"],
+                       "note": "accounting flops: 25 per slab test, 20 per sphere test (device counters, B2R_FLAG_COUNT_TESTS pass), 250 per shaded hit"}
+    if box:
+        out["tests_per_ray"] = {"box": box / max(ext + shadow, 1), "sphere": sph / max(ext + shadow, 1)}
+    # ncu-derived figures of the same workload (static, from the committed capture): DRAM traffic over ALL launches of the kernel in
+    # one frame, issue-slot and L1 data-pipe utilisation, active lanes per instruction
+    for fn in ("r02_traffic.json", "r01_traffic.json"):
+        p = os.path.join(ROOT, "profiles", fn)
+        if os.path.exists(p):
+            try:
+                tr = json.load(open(p)).get(b.name, {}).get(dom)
+                if tr:
+                    out["traffic"] = tr["dram_bytes_per_launch"]; out["traffic_source"] = tr.get("source")
+                    for k_src, k_dst in (("issue_slots_busy_pct", "issue"), ("l1_data_pipe_pct", "l1"), ("active_lanes_per_instruction", "active_lanes")):
+                        if tr.get(k_src) is not None:
+                            out[k_dst] = {"value": tr[k_src], "source": tr.get("source")}
+                    break
+            except Exception:
+                pass
+    return out
+
+
+def run_workload(args, name, rank, world, local, stream, dev, secondary=False):
+    import numpy as np
+    import torch
+    b = Bench(args, name, rank, world, local, stream, dev)
+    b2r, wl, r = b.b2r, b.wl, b.r
+    warm = max(args.warmup, 3)
+    steps = args.steps
+
+    # ---- parity first: nothing is timed on a renderer whose frame is wrong
+    par = b.parity(b.step_samples, f"{name}: {b.step_samples} spp per frame over {world} GPU(s)") if not args.no_parity else None
+
     for _ in range(warm):
-        step()
-    barrier()
+        b.step()
+    b.barrier()
     r.reset_counters()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    ms_total = timed(args.steps)
+    ms_total = b.timed(steps)
     clk = clocks.stop() if rank == 0 else None
-    cnt = r.counters()
-    rays_local = cnt["extension_rays"] + cnt["shadow_rays"]
-    if world > 1:
-        t = torch.tensor([rays_local, cnt["launches"]], device=dev, dtype=torch.float64); dist.all_reduce(t); rays_total, launches = float(t[0]), int(t[1])
-    else:
-        rays_total, launches = float(rays_local), cnt["launches"]
+    rays_total, launches = b.rays(r.counters())
     secs = ms_total / 1e3
     value = rays_total / secs / 1e6
-    paths_total = wl["w"] * wl["h"] * step_samples * args.steps
+    paths_total = wl["w"] * wl["h"] * b.step_samples * steps
 
-    # ---- e2e: same steps through the public API with HOST buffers (scene upload + frame download each step)
+    # ---- e2e: same steps through the public API with HOST buffers (scene upload + frame download each step); frames leave asynchronously
+    # into two alternating pinned buffers (on one GPU: b2r_resolve_async; team mode: rank 0's copy stream), the last one is waited for
     fb_host = torch.empty((wl["h"], wl["w"], 4), dtype=torch.float32, pin_memory=True).numpy()
-    e2e_kw = dict(to_host_fb=fb_host, upload=True)
-    if world == 1:  # single GPU: frames leave through b2r_resolve_async into two alternating pinned buffers (multi-GPU: the fused P2P resolve stays synchronous)
-        fb_host2 = torch.empty((wl["h"], wl["w"], 4), dtype=torch.float32, pin_memory=True).numpy()
-        e2e_kw = dict(async_fbs=[fb_host, fb_host2], upload=True)
+    fb_host2 = torch.empty((wl["h"], wl["w"], 4), dtype=torch.float32, pin_memory=True).numpy()
+    e2e_kw = dict(async_fbs=[fb_host, fb_host2], upload=True) if (world == 1 or b.use_team) else dict(to_host_fb=fb_host, upload=True)
     for _ in range(2):
-        step(**e2e_kw)
-    if world == 1:
+        b.step(**e2e_kw)
+    if "async_fbs" in e2e_kw and (world == 1 or rank == 0):
         r.WaitFrame()
     r.reset_counters()
-    ms_e2e = timed(args.steps, **e2e_kw)
-    c2 = r.counters(); rays_e2e = c2["extension_rays"] + c2["shadow_rays"]
-    if world > 1:
-        t = torch.tensor([rays_e2e], device=dev, dtype=torch.float64); dist.all_reduce(t); rays_e2e = float(t[0])
+    ms_e2e = b.timed(steps, **e2e_kw)
+    rays_e2e, _ = b.rays(r.counters())
     wide, _ms = r.wide_nodes()
-    h2d = len(ps.prims) * 20 + len(ps.material) * 32 + max(1, len(ps.lights)) * 32 + wide.shape[0] * 128 + 44
+    h2d = len(b.ps.prims) * 20 + len(b.ps.material) * 32 + max(1, len(b.ps.lights)) * 32 + wide.shape[0] * 128 + 44
     d2h = wl["w"] * wl["h"] * 16 if rank == 0 else 0
     e2e_value = rays_e2e / (ms_e2e / 1e3) / 1e6
 
-    # ---- per-kernel pass: the same K steps launched kernel by kernel with an event pair around every launch (roofline)
+    # ---- the drop-in's own call pattern (Application.cpp:373-382 through include/b2r_reference_binding.hpp): one Accumulate() per
+    # application frame, Render() every frame — a no-op unless accumulations % K == 0, else a synchronous resolve + copy into pageable
+    # host memory. N=1 only (the reference's loop knows nothing about ranks).
+    dropin = None
+    if world == 1 and not args.no_dropin:
+        frames = 8 * wl["K"]
+        page_fb = np.zeros((wl["h"], wl["w"], 4), np.float32)
+        def app_frames(n):
+            r.ResetAccumulator()
+            for _ in range(n):
+                r.Accumulate(1); r.Render(out=page_fb)
+        app_frames(wl["K"]); torch.cuda.synchronize(dev); r.reset_counters()
+        t0 = time.perf_counter(); app_frames(frames); torch.cuda.synchronize(dev); dt = time.perf_counter() - t0
+        cd = r.counters(); rd = cd["extension_rays"] + cd["shadow_rays"]
+        dropin = {"value": rd / dt / 1e6, "unit": UNIT, "ms_per_app_frame": 1e3 * dt / frames, "app_frames": frames, "resolves": frames // wl["K"],
+                  "pattern": "per application frame: Accumulate() (1 sample, one wavefront batch) + Render() (resolve + synchronous D2H into pageable memory when accumulations % K == 0), host wall clock",
+                  "vs_batched_value": (rd / dt / 1e6) / value}
+
+    # ---- per-kernel pass: the same steps launched kernel by kernel with an event pair around every launch (roofline), test counters on
     roof = None; kernel_ms = None
     hbm_peak, peak_src, sm_max = peaks()
     if not args.no_profile_pass:
-        r.set_flags(b2r.FLAG_NO_GRAPH | base_flags); r.SetCamera(ps.camera)
-        step(); r.sync(); r.kernel_times(reset=True); r.reset_counters()
-        for _ in range(args.steps):
-            step()
+        r.set_flags(b2r.FLAG_NO_GRAPH | b.base_flags); r.SetCamera(b.ps.camera)
+        b.step(); r.sync(); r.kernel_times(reset=True); r.reset_counters()
+        for _ in range(steps):
+            b.step()
         r.sync()
         kt = r.kernel_times(reset=True); pc = r.counters()
-        r.set_flags(base_flags); r.SetCamera(ps.camera)
+        if b.r.scene is not None and wl["scene"] != "default":  # sphere / box test counts of the same steps (their own pass: counting costs time)
+            r.set_flags(b2r.FLAG_NO_GRAPH | b2r.FLAG_COUNT_TESTS | b.base_flags); r.SetCamera(b.ps.camera); r.reset_counters()
+            for _ in range(steps):
+                b.step()
+            r.sync(); cc = r.counters(); pc["box_tests"], pc["sphere_tests"] = cc["box_tests"], cc["sphere_tests"]; r.kernel_times(reset=True)
+        r.set_flags(b.base_flags); r.SetCamera(b.ps.camera)
         kernel_ms = {k: {"ms": v[0], "launches": int(v[1])} for k, v in kt.items() if v[1]}
-        total_kernel_ms = sum(v[0] for v in kt.values())
-        ext, shadow, hits, events, dropped = pc["extension_rays"], pc["shadow_rays"], pc["shaded_hits"], pc["radiance_events"], pc["dropped"]
-        primaries = wl["w"] * wl["h"] * (step_samples // world) * args.steps
-        if kt["bounce_brute"][1]:
-            # DESIGN.md "Algorithmic bytes": 44 B path record read per non-primary ray + 44 B written per continuing path (= every
-            # non-primary ray was written once) + 12 B radiance entry started per primary path + 24 B radiance read-modify-write
-            # per contribution + 12 B per dropped path
-            name, ms, n = "k_bounce_brute", kt["bounce_brute"][0], kt["bounce_brute"][1]
-            alg = 88.0 * (ext - primaries) + 12.0 * primaries + 24.0 * events + 12.0 * dropped
-        else:
-            # dominant kernel of the BVH pipeline = closest-hit traversal: 32 B ray read + 8 B hit written per extension ray from HBM;
-            # node/sphere fetches are L2-resident and reported separately through the box/sphere counters
-            name, ms, n = "k_intersect_closest", kt["intersect_closest"][0], kt["intersect_closest"][1]
-            alg = 40.0 * ext
-        achieved = alg / (ms / 1e3) / 1e9
-        roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                "peak_source": peak_src, "avg_launch_ms": ms / n, "launches": int(n), "algorithmic_bytes_per_launch": alg / n,
-                "kernel_share_of_step": ms / total_kernel_ms if total_kernel_ms else None,
-                "timing": "CUDA event pair around every launch, non-graph pass of the same steps on the launching stream"}
-        # FP32 view (never tensor cores): 20 flop per sphere test (BVH.hpp:251-265), ~250 per shaded hit
-        if kt["bounce_brute"][1]:
-            n_prims = len(ps.prims)
-            flops = 20.0 * n_prims * (ext + shadow) + 250.0 * hits  # shadow: upper bound (any-hit exits early)
-            fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
-            roof["fp32"] = {"achieved_tflops": flops / (ms / 1e3) / 1e12, "peak_tflops": fp32_peak, "frac": flops / (ms / 1e3) / 1e12 / fp32_peak,
-                            "note": "accounting flops (20/sphere test, 250/shaded hit); shadow tests counted at their upper bound"}
-        ncu = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(ncu):
-            try:
-                tr = json.load(open(ncu)).get(args.workload, {}).get(name)
-                if tr:
-                    roof["traffic"] = tr["dram_bytes_per_launch"]; roof["traffic_source"] = tr.get("source")
-                    if tr.get("issue_slots_busy_pct") is not None:  # the binding resource of these kernels (ncu, not live): instruction issue
-                        roof["issue"] = {"slots_busy_pct": tr["issue_slots_busy_pct"], "source": "ncu smsp__issue_active, same capture as traffic"}
-            except Exception:
-                pass
+        roof = roofline(b, kt, pc, steps, hbm_peak, peak_src, sm_max)
 
-    # ---- the same workload in B2R_FLAG_REFERENCE_EXACT mode (bit-identical to the reference's own renderer), reported beside the
-    # default mode's number: brute-force workloads, N=1 only, same steps / warm-up / timing as the headline value
+    # ---- strong scaling beside the weak `value`: STRONG_SPP samples per frame split over the ranks by bucket
+    strong = None
+    if not b.strong and not secondary and not args.no_strong and wl["scene"] != "default":
+        sp = b.parity(STRONG_SPP, f"{name} scene, {STRONG_SPP} spp per frame split over {world} GPU(s) by bucket") if not args.no_parity else None
+        k = max(3, steps // 4)
+        for _ in range(2):
+            b.step(samples=STRONG_SPP)
+        b.barrier(); r.reset_counters()
+        ms_s = b.timed(k, samples=STRONG_SPP)
+        rays_s, _ = b.rays(r.counters())
+        single_ms = None
+        if world > 1:
+            if rank == 0:  # the same frame on ONE GPU, in the same run (the other ranks wait at the barrier)
+                one = b.renderer(sharded=False, flags=b.base_flags)
+                def f1():
+                    one.ResetAccumulator(); one.Accumulate(STRONG_SPP); assert one.Render(to_host=False)
+                f1(); torch.cuda.synchronize(dev)
+                a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for _ in range(k):
+                    f1()
+                c.record(stream); torch.cuda.synchronize(dev)
+                single_ms = a.elapsed_time(c) / k; one.close()
+            b.barrier()
+        else:
+            single_ms = ms_s / k
+        strong = {"workload": f"{wl['desc'].split(' 16spp')[0]} {STRONG_SPP}spp per frame, buckets split over the GPUs (strong scaling)", "steps": k, "ms_per_step": ms_s / k,
+                  "value": rays_s / (ms_s / 1e3) / 1e6, "unit": UNIT, "single_gpu_ms_per_step": single_ms,
+                  "speedup_vs_one_gpu": (single_ms / (ms_s / k)) if single_ms else None, "efficiency": (single_ms / (ms_s / k) / world) if single_ms else None,
+                  "parity": sp, "parity_checked": bool(sp and sp["identical"]) if rank == 0 else None}
+
+    # ---- the same workload in B2R_FLAG_REFERENCE_EXACT mode (bit-identical to the reference's own renderer), beside the default mode's
+    # number: brute-force workloads, N=1 only
     exact_line = None
-    if world == 1 and not base_flags and wl["scene"] == "default" and not args.no_profile_pass:
-        rx = b2r.Renderer(ps, wl["w"], wl["h"], max_bounces=wl["mb"], buckets=K, device=local, stream=stream.cuda_stream,
-                          samples_in_flight=args.samples_in_flight, flags=b2r.FLAG_REFERENCE_EXACT)
+    if world == 1 and not b.base_flags and wl["scene"] == "default" and not args.no_profile_pass:
+        rx = b.renderer(sharded=False, flags=b2r.FLAG_REFERENCE_EXACT)
         def step_x():
-            rx.ResetAccumulator(); rx.Accumulate(step_samples); assert rx.Render(to_host=False)
+            rx.ResetAccumulator(); rx.Accumulate(b.step_samples); assert rx.Render(to_host=False)
         for _ in range(warm):
             step_x()
         torch.cuda.synchronize(dev); rx.reset_counters()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(args.steps):
+        for _ in range(steps):
             step_x()
         e1.record(stream); torch.cuda.synchronize(dev)
         ms_x = e0.elapsed_time(e1); cx = rx.counters(); rays_x = cx["extension_rays"] + cx["shadow_rays"]
-        exact_line = {"value": rays_x / (ms_x / 1e3) / 1e6, "unit": UNIT, "ms_per_step": ms_x / args.steps,
+        exact_line = {"value": rays_x / (ms_x / 1e3) / 1e6, "unit": UNIT, "ms_per_step": ms_x / steps,
                       "note": "B2R_FLAG_REFERENCE_EXACT: the reference's per-tile stream order and scalar-tail sphere formula; results bit-identical to the reference's own Renderer::Accumulate/Render (tests/test_gpu_parity.py)"}
         rx.close()
 
     # ---- scene edit (SURVEY §8f-2; the reference rebuilds its BVH on every geometry drag, Application.cpp:508-510): every sphere of the
     # BVH workload moves by up to a quarter of its radius; b2r_refit_scene (GPU refit of the traversal tree, topology kept) beside the
-    # full rebuild (host reference-BVH build + b2r_upload_scene: traversal-tree build, flatten, H2D). Outside the timed region; N=1 only.
+    # full rebuild. Outside the timed region; N=1 only.
     edit_line = None
-    if rank == 0 and world == 1 and wl["scene"] != "default" and not args.no_profile_pass:
+    if rank == 0 and world == 1 and wl["scene"] != "default" and not args.no_profile_pass and not secondary:
         rs = np.random.RandomState(5)
-        geo2 = ps.geometry.copy(); rad = np.sqrt(geo2["radius_sq"])
+        geo2 = b.ps.geometry.copy(); rad = np.sqrt(geo2["radius_sq"])
         geo2["position"] += (rs.uniform(-1, 1, (len(geo2), 3)) * (0.25 * rad)[:, None]).astype(np.float32)
 
         def steps_ms(n=3):
-            step(); torch.cuda.synchronize(dev)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b.step(); torch.cuda.synchronize(dev)
+            a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
             for _ in range(n):
-                step()
-            b.record(stream); torch.cuda.synchronize(dev)
-            return a.elapsed_time(b) / n
+                b.step()
+            c.record(stream); torch.cuda.synchronize(dev)
+            return a.elapsed_time(c) / n
         r.sync(); t0 = time.perf_counter()
         r.RefitScene(geo2, want_quality=False, keep_order=True); r.sync()
         refit_ms = (time.perf_counter() - t0) * 1e3
@@ -456,7 +603,7 @@ def main():
         q = r.RefitScene(geo2, keep_order=True)
         ms_refit = steps_ms()
         t0 = time.perf_counter()
-        scene2 = dict(scene); scene2["geometry"] = geo2
+        scene2 = dict(b.scene); scene2["geometry"] = geo2
         ps2 = b2r.PreparedScene(scene2, wl["w"], wl["h"])
         t1 = time.perf_counter()
         r.SetScene(ps2); r.sync()
@@ -466,40 +613,98 @@ def main():
                      "rebuild_ms": {"reference_bvh_host": (t1 - t0) * 1e3, "upload_scene": (t2 - t1) * 1e3},
                      "ms_per_step_after_refit": ms_refit, "ms_per_step_after_rebuild": ms_rebuilt,
                      "note": "refit = match prims to geometry + pack + H2D of the spheres and lights + k_refit_level per tree level, host wall clock incl. stream sync; leaf order kept (refit_ms) or the reference BVH rebuilt on the host first, as Application.cpp:508 does"}
-        r.SetScene(ps)
+        r.SetScene(b.ps)
 
-    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample of the same workload, on the box's host
-    # cores. Run as a fresh `bench.py --impl reference` process so that its threads see the same conditions as the reference arm
-    # the driver launches (inside this process, after CUDA/torch start-up, the same code ran at about half the speed).
+    # ---- CPU baseline beside it (rank 0, N=1 only): a fresh `bench.py --impl reference` process, so that its threads see the same
+    # conditions as the reference arm the driver launches (inside this process, after CUDA/torch start-up, the same code ran at about half the speed)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload, "--steps", "2", "--warmup", "1"],
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", name, "--steps", "2", "--warmup", "1"],
                                  capture_output=True, text=True, timeout=900).stdout.strip().splitlines()[-1]
             ref = json.loads(out)
             cpu = dict(ref["cpu_baseline"]); cpu["paths_per_s"] = ref.get("paths_per_s")
+            if ref.get("cpu_stream_bvh_port"):
+                cpu["stream_bvh_port"] = ref["cpu_stream_bvh_port"]
         except Exception as e:  # never let the baseline leg break the GPU line
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
 
+    line = None
     if rank == 0:
+        if b.use_team:
+            part = f"sample buckets b%{world}==rank, scene+BVH replicated; team mode: every rank resolves its slab of tiles reading the bucket sums from their owners over NVLink (CUDA IPC) and stores it into rank 0's framebuffer; hand-shakes are release/acquire flags in peer memory (no host barrier per frame)"
+        elif b.use_p2p:
+            part = f"sample buckets b%{world}==rank; resolve kernel on rank 0 reads peer bucket arrays over NVLink (CUDA IPC), 2 host barriers per frame"
+        elif world > 1:
+            part = f"sample buckets b%{world}==rank; one NCCL all-reduce of bucket sums per frame"
+        else:
+            part = "single GPU"
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"] + (" [B2R_FLAG_REFERENCE_EXACT: reference's stream order and scalar-tail formula]" if base_flags else ""), "samples_per_step_per_gpu": step_samples // world, "samples_in_flight": args.samples_in_flight,
-                       "partition": (f"sample buckets b%{world}==rank, scene+BVH replicated; " + ("resolve kernel on rank 0 reads peer bucket arrays over NVLink (CUDA IPC), 2 barriers per frame" if use_p2p else "one NCCL all-reduce of bucket sums per frame")) if world > 1 else "single GPU",
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_total / steps,
+            "higher_is_better": True, "scaling": "strong" if b.strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"] + (" [B2R_FLAG_REFERENCE_EXACT: reference's stream order and scalar-tail formula]" if b.base_flags else ""), "samples_per_step_per_gpu": b.step_samples // world, "samples_in_flight": args.samples_in_flight,
+                       "partition": part,
                        "l2": "no flush needed: each step streams >1 GB of path-queue records (>> 126 MB L2); RNG-unique samples every step"},
-            "paths_per_s": paths_total / secs, "rays_per_step": rays_total / args.steps,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
+            "paths_per_s": paths_total / secs, "rays_per_step": rays_total / steps,
+            "parity_checked": bool(par and par["identical"]), "parity": par,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / steps,
                     "includes": "upload_scene (pack + 128-B BVH flatten on host, H2D), set_camera, reset, Accumulate x spp, Render, D2H of the RGBA32F frame into pinned memory"
-                                + ("; frames leave through b2r_resolve_async (copy of frame N overlaps the tracing of frame N+1, two pinned buffers, last frame waited for inside the timed region)" if world == 1 else "")},
+                                + ("; frames leave asynchronously (copy of frame N overlaps the tracing of frame N+1, two pinned buffers, last frame waited for inside the timed region)" if "async_fbs" in e2e_kw else "")},
+            "e2e_dropin": dropin, "strong": strong,
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "kernel_ms": kernel_ms,
         }
         if exact_line:
             line["reference_exact_mode"] = exact_line
         if edit_line:
             line["scene_edit"] = edit_line
+    b.close()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1); ap.add_argument("--steps", type=int, default=20); ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"]); ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true"); ap.add_argument("--no-profile-pass", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the frame-hash check (ncu runs only; a reported number always carries it)")
+    ap.add_argument("--no-strong", action="store_true"); ap.add_argument("--no-dropin", action="store_true"); ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--cpu-port", action="store_true", help="--impl reference: time the oracle port instead of the reference itself")
+    ap.add_argument("--no-port-line", action="store_true")
+    ap.add_argument("--samples-in-flight", type=int, default=0, help="0 = library default (auto)")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel (for ncu); never used for a reported number")
+    ap.add_argument("--reference-exact", action="store_true", help="brute-force workloads: B2R_FLAG_REFERENCE_EXACT (bit-identical to the reference's own renderer; one extra ranking kernel per bounce)")
+    ap.add_argument("--combine", default="team", choices=["team", "p2p", "nccl"], help="multi-GPU frame combine: team = sliced resolve over NVLink with device-side hand-shakes (default); p2p = rank 0 resolves, host barriers (round 1); nccl = all-reduce then resolve")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, wl, rank); return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keeps NCCL's version banner off stdout: rank 0 prints ONE line
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        dist.barrier()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libb2r has no CPU fallback")
+    dev = torch.device(f"cuda:{local}"); torch.cuda.set_device(dev)
+    stream = torch.cuda.Stream(device=dev)  # a real (non-default) stream: the library launches on it and the timing events are recorded on it
+    torch.cuda.set_stream(stream)
+
+    line = run_workload(args, args.workload, rank, world, local, stream, dev)
+    # secondary record: BASELINE.json configs[1] (C2, the brute-force configuration the reference itself can run at full size), N=1
+    if world == 1 and args.workload == "c3" and not args.no_secondary and not args.no_graph:
+        c2 = run_workload(args, "c2", rank, world, local, stream, dev, secondary=True)
+        if rank == 0:
+            line["c2"] = {k: c2[k] for k in ("value", "unit", "ms_per_step", "config", "paths_per_s", "parity_checked", "parity", "e2e", "e2e_dropin", "roofline", "cpu_baseline", "kernel_ms", "reference_exact_mode") if k in c2}
+    if rank == 0:
         print(json.dumps(line))
-    r.close()
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 

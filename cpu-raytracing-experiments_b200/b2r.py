@@ -32,7 +32,7 @@ COUNTER_NAMES = ["extension_rays", "shadow_rays", "shaded_hits", "terminated", "
 # every symbol include/b2r.h declares (tests/test_abi.py checks the header against this list and the library against both)
 ABI_SYMBOLS = [
     "b2r_bvh_build", "b2r_bvh_build_ex", "b2r_find_lights", "b2r_camera_lookat", "b2r_create", "b2r_destroy", "b2r_resize", "b2r_reset", "b2r_set_stream",
-    "b2r_sync", "b2r_upload_scene", "b2r_refit_scene", "b2r_set_camera", "b2r_accumulate", "b2r_resolve", "b2r_resolve_async", "b2r_frame_wait", "b2r_resolve_from", "b2r_ipc_export_buckets", "b2r_ipc_open_peers", "b2r_ipc_close", "b2r_resolve_peers", "b2r_get_accumulations", "b2r_set_accumulations",
+    "b2r_sync", "b2r_upload_scene", "b2r_refit_scene", "b2r_set_camera", "b2r_accumulate", "b2r_resolve", "b2r_resolve_async", "b2r_frame_wait", "b2r_resolve_from", "b2r_ipc_export_buckets", "b2r_ipc_open_peers", "b2r_ipc_close", "b2r_resolve_peers", "b2r_team_export", "b2r_team_open", "b2r_team_resolve", "b2r_team_error", "b2r_team_close", "b2r_get_accumulations", "b2r_set_accumulations",
     "b2r_read_buckets", "b2r_write_buckets", "b2r_device_buckets", "b2r_device_framebuffer", "b2r_read_counters", "b2r_reset_counters",
     "b2r_read_kernel_times", "b2r_set_flags", "b2r_generate_rays", "b2r_trace_closest", "b2r_trace_shadow", "b2r_read_wide_nodes", "b2r_get_origin_box",
     "b2r_write_hdr", "b2r_read_hdr", "b2r_last_error", "b2r_abi_version",
@@ -67,7 +67,7 @@ def lib():
             "b2r_set_stream": [vp, vp], "b2r_sync": [vp],
             "b2r_upload_scene": [vp, vp, vp, u32, u32, vp, u32, vp, u32, vp, u32, vp, vp, i32, i32],
             "b2r_refit_scene": [vp, vp, u32, vp, u32, vp, u32, vp, u32, vp],
-            "b2r_set_camera": [vp, vp, vp, f32, f32, f32, f32], "b2r_accumulate": [vp, u32], "b2r_resolve": [vp, vp, C.c_int], "b2r_resolve_async": [vp, vp, C.c_int], "b2r_frame_wait": [vp], "b2r_resolve_from": [vp, vp, vp, C.c_int], "b2r_ipc_export_buckets": [vp, vp], "b2r_ipc_open_peers": [vp, vp, u32, u32], "b2r_ipc_close": [vp], "b2r_resolve_peers": [vp, vp, C.c_int],
+            "b2r_set_camera": [vp, vp, vp, f32, f32, f32, f32], "b2r_accumulate": [vp, u32], "b2r_resolve": [vp, vp, C.c_int], "b2r_resolve_async": [vp, vp, C.c_int], "b2r_frame_wait": [vp], "b2r_resolve_from": [vp, vp, vp, C.c_int], "b2r_ipc_export_buckets": [vp, vp], "b2r_ipc_open_peers": [vp, vp, u32, u32], "b2r_ipc_close": [vp], "b2r_resolve_peers": [vp, vp, C.c_int], "b2r_team_export": [vp, vp], "b2r_team_open": [vp, vp, u32, u32], "b2r_team_resolve": [vp, vp, C.c_int, C.c_int], "b2r_team_error": [vp, vp], "b2r_team_close": [vp],
             "b2r_get_accumulations": [vp, vp], "b2r_set_accumulations": [vp, u32], "b2r_read_buckets": [vp, vp], "b2r_write_buckets": [vp, vp],
             "b2r_device_buckets": [vp, vp, vp], "b2r_device_framebuffer": [vp, vp, vp], "b2r_read_counters": [vp, vp], "b2r_reset_counters": [vp],
             "b2r_read_kernel_times": [vp, vp, vp, C.c_int], "b2r_set_flags": [vp, u32], "b2r_generate_rays": [vp, u32, vp],
@@ -259,6 +259,27 @@ class Renderer:
         """Render() reading every bucket from its owner GPU over NVLink (after ipc_open_peers and a barrier)."""
         dst = (self.framebuffer if out is None else out) if to_host else None
         return _check(lib().b2r_resolve_peers(self._h, _ptr(dst), 1 if tonemap else 0)) == OK
+
+    # -- team mode: multi-GPU frame without host barriers (see b2r_dist.open_team)
+    def team_export(self):
+        h = (C.c_ubyte * 192)(); _check(lib().b2r_team_export(self._h, h)); return bytes(h)
+
+    def team_open(self, handles, my_rank):
+        blob = b"".join(handles); buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        _check(lib().b2r_team_open(self._h, buf, len(handles), my_rank))
+
+    def team_close(self):
+        _check(lib().b2r_team_close(self._h))
+
+    def RenderTeam(self, tonemap=True, out=None, to_host=True, use_async=False):
+        """Render() of a multi-GPU frame, called by every rank: this rank resolves its slab of tiles (buckets read from their owners over
+        NVLink) into rank 0's framebuffer; rank 0 copies the frame to `out` / self.framebuffer (use_async: on its copy stream, WaitFrame()
+        to join). No host synchronisation between ranks."""
+        dst = (self.framebuffer if out is None else out) if to_host else None
+        return _check(lib().b2r_team_resolve(self._h, _ptr(dst), 1 if tonemap else 0, 1 if use_async else 0)) == OK
+
+    def team_error(self):
+        v = C.c_uint32(0); _check(lib().b2r_team_error(self._h, C.byref(v))); return v.value
 
     def GetFrame(self):
         return self.framebuffer  # Renderer.hpp:68 returns the Vulkan Image; here: the host RGBA32F array

@@ -68,3 +68,22 @@ def open_peers(renderer, group=None):
         handles = [mine]
     renderer.ipc_open_peers(handles, rank)
     return world
+
+
+def open_team(renderer, group=None):
+    """Team mode (b2r_team_*): exchange the three CUDA IPC handles of every rank once (bucket array, framebuffer, hand-shake flags),
+    map the peers', and barrier ONCE so that nobody signals into a block that is not mapped yet. After this Renderer.RenderTeam() needs no
+    host-side synchronisation between ranks: the ranks hand frames over through release/acquire flags in peer memory."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    mine = renderer.team_export()
+    handles = [None] * world
+    if world > 1:
+        dist.all_gather_object(handles, mine, group=group)
+    else:
+        handles = [mine]
+    renderer.team_open(handles, rank)
+    if world > 1:
+        dist.barrier(group=group)
+    return world

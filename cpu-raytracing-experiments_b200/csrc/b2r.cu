@@ -84,6 +84,8 @@ struct b2r_ctx {
 	double kernel_ms[8] = {0}; uint64_t kernel_launches[8] = {0};
 	// peers' bucket arrays mapped through CUDA IPC (multi-GPU fused resolve)
 	std::vector<void*> peer_acc; uint32_t my_rank = 0;
+	// team mode (b2r_team_*): peers' bucket arrays, rank 0's framebuffer and every rank's TeamSync block, mapped through CUDA IPC
+	TeamSync* d_team = nullptr; std::vector<void*> team_acc, team_sync; void* team_fb0 = nullptr; uint32_t team_rank = 0, team_frame = 0; bool team_wait_done = false;
 };
 
 namespace {
@@ -297,6 +299,7 @@ int ensure_origin_box(b2r_ctx* c, const float* points, uint32_t n_points) {
 // ================================================================================================ C ABI
 extern "C" {
 
+static int team_before_bucket_write(b2r_ctx* c);
 const char* b2r_last_error(void) { return g_error.c_str(); }
 int b2r_abi_version(void) { return B2R_ABI_VERSION; }
 
@@ -331,6 +334,7 @@ void b2r_destroy(b2r_ctx* c) {
 	cudaSetDevice(c->cfg.device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	for (size_t r = 0; r < c->peer_acc.size(); r++) if (c->peer_acc[r] && r != c->my_rank) cudaIpcCloseMemHandle(c->peer_acc[r]);
+	b2r_team_close(c); if (c->d_team) { cudaFree(c->d_team); c->d_team = nullptr; }
 	drop_graph(c);
 	for (auto& t : c->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
 	dev_free(&c->d_prims); dev_free(&c->d_mat_albedo); dev_free(&c->d_mat_emission); dev_free(&c->d_light_sphere); dev_free(&c->d_light_emit);
@@ -355,6 +359,7 @@ int b2r_resize(b2r_ctx* c, uint32_t width, uint32_t height) {
 	CU(cudaStreamSynchronize(c->stream));
 	if (c->copy_pending) { CU(cudaEventSynchronize(c->ev_copied)); c->copy_pending = false; }
 	if (width == c->cfg.width && height == c->cfg.height) return b2r_reset(c);
+	if (!c->peer_acc.empty() || !c->team_acc.empty()) return fail(B2R_ERR_STATE, "the bucket array / framebuffer are exported to peers (CUDA IPC): b2r_ipc_close / b2r_team_close on every rank before a resize, then export again");
 	c->cfg.width = width; c->cfg.height = height;
 	return alloc_frame(c);
 }
@@ -363,6 +368,7 @@ int b2r_reset(b2r_ctx* c) {
 	if (!c) return fail(B2R_ERR_ARG, "null context");
 	int rc = ensure_device(c); if (rc) return rc;
 	c->accumulations = 0;
+	if ((rc = team_before_bucket_write(c))) return rc;
 	const size_t npix = static_cast<size_t>(c->cfg.width) * c->cfg.height;
 	CU(cudaMemsetAsync(c->d_acc, 0, static_cast<size_t>(c->cfg.buckets) * 3 * npix * sizeof(float), c->stream));
 	return B2R_OK;
@@ -599,6 +605,7 @@ int b2r_accumulate(b2r_ctx* c, uint32_t n_samples) {
 	if (!c) return fail(B2R_ERR_ARG, "null context");
 	if (!c->have_scene || !c->have_camera) return fail(B2R_ERR_STATE, "upload_scene and set_camera must precede accumulate");
 	int rc = ensure_device(c); if (rc) return rc;
+	if ((rc = team_before_bucket_write(c))) return rc;
 	BatchArgs args; args.n = 0;
 	for (uint32_t s = 0; s < n_samples; s++) {
 		const uint32_t acc = ++c->accumulations;  // pre-increment: the first sample has index 1 (Renderer.hpp:74, Q1)
@@ -614,7 +621,7 @@ static int resolve_with(b2r_ctx* c, const BucketPtrs& bp, float* rgba_out_host, 
 	const float scale = c->params.frame.cam.exposure / static_cast<float>(c->accumulations / c->cfg.buckets);  // :439
 	const bool profile = (c->cfg.flags & B2R_FLAG_NO_GRAPH) != 0;
 	if (c->copy_pending) CU(cudaStreamWaitEvent(c->stream, c->ev_copied, 0));  // the previous frame is still being read out of d_fb
-	rc = launch(c, KK_RESOLVE, profile, [&] { k_resolve<<<c->grid_stream, kBlock, 0, c->stream>>>(c->params.frame, bp, c->d_fb, scale, tonemap); });
+	rc = launch(c, KK_RESOLVE, profile, [&] { k_resolve<<<c->grid_stream, kBlock, 0, c->stream>>>(c->params.frame, bp, c->d_fb, scale, tonemap, 0u, c->params.frame.npix); });
 	if (rc) return rc;
 	const size_t bytes = static_cast<size_t>(c->params.frame.npix) * sizeof(float4);
 	if (async && rgba_out_host) {
@@ -692,6 +699,117 @@ int b2r_resolve_peers(b2r_ctx* c, float* rgba_out_host, int tonemap) {
 	for (uint32_t k = 0; k < c->cfg.buckets; k++)  // bucket k lives on rank k % G (b2r_config.bucket_first/stride)
 		bp.k[k] = static_cast<const float*>(c->peer_acc[k % G]) + static_cast<size_t>(k) * 3 * c->params.frame.npix;
 	return resolve_with(c, bp, rgba_out_host, tonemap);
+}
+
+
+// ---- team mode: the multi-GPU frame without host barriers ----------------------------------------------------------------------
+int b2r_team_close(b2r_ctx* c) {
+	if (!c) return fail(B2R_ERR_ARG, "null context");
+	int rc = ensure_device(c); if (rc) return rc;
+	CU(cudaStreamSynchronize(c->stream));
+	if (c->copy_stream) CU(cudaStreamSynchronize(c->copy_stream));
+	for (size_t r = 0; r < c->team_acc.size(); r++) if (r != c->team_rank) { if (c->team_acc[r]) cudaIpcCloseMemHandle(c->team_acc[r]); if (c->team_sync[r]) cudaIpcCloseMemHandle(c->team_sync[r]); }
+	if (c->team_fb0 && c->team_rank != 0) cudaIpcCloseMemHandle(c->team_fb0);
+	c->team_acc.clear(); c->team_sync.clear(); c->team_fb0 = nullptr; c->team_frame = 0; c->team_wait_done = false;
+	return B2R_OK;
+}
+int b2r_team_export(b2r_ctx* c, unsigned char handles_out[192]) {
+	if (!c || !handles_out) return fail(B2R_ERR_ARG, "null argument");
+	int rc = ensure_device(c); if (rc) return rc;
+	if (!c->d_team) { CU(cudaMalloc(reinterpret_cast<void**>(&c->d_team), sizeof(TeamSync))); }
+	CU(cudaMemsetAsync(c->d_team, 0, sizeof(TeamSync), c->stream)); CU(cudaStreamSynchronize(c->stream));
+	cudaIpcMemHandle_t h;
+	CU(cudaIpcGetMemHandle(&h, c->d_acc)); std::memcpy(handles_out, &h, 64);
+	CU(cudaIpcGetMemHandle(&h, c->d_fb)); std::memcpy(handles_out + 64, &h, 64);
+	CU(cudaIpcGetMemHandle(&h, c->d_team)); std::memcpy(handles_out + 128, &h, 64);
+	return B2R_OK;
+}
+int b2r_team_open(b2r_ctx* c, const unsigned char* all_handles, uint32_t n_ranks, uint32_t my_rank) {
+	if (!c || !all_handles || n_ranks == 0 || my_rank >= n_ranks || n_ranks > static_cast<uint32_t>(kTeamMax)) return fail(B2R_ERR_ARG, "bad team (1..16 ranks)");
+	if (c->cfg.buckets % n_ranks) return fail(B2R_ERR_ARG, "bucket count must be a multiple of the number of ranks");
+	if (!c->d_team) return fail(B2R_ERR_STATE, "b2r_team_export first");
+	int rc = b2r_team_close(c); if (rc) return rc;
+	c->team_acc.assign(n_ranks, nullptr); c->team_sync.assign(n_ranks, nullptr); c->team_rank = my_rank;
+	auto open = [&](void** out, const unsigned char* handle) -> int {
+		cudaIpcMemHandle_t h; std::memcpy(&h, handle, 64);
+		cudaError_t e = cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess);
+		if (e != cudaSuccess) { *out = nullptr; return fail(B2R_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
+		return B2R_OK;
+	};
+	for (uint32_t r = 0; r < n_ranks; r++) {
+		const unsigned char* hs = all_handles + 192 * static_cast<size_t>(r);
+		if (r == my_rank) { c->team_acc[r] = c->d_acc; c->team_sync[r] = c->d_team; continue; }
+		if ((rc = open(&c->team_acc[r], hs)) || (rc = open(&c->team_sync[r], hs + 128))) { b2r_team_close(c); return rc; }
+	}
+	if (my_rank == 0) c->team_fb0 = c->d_fb;
+	else if ((rc = open(&c->team_fb0, all_handles + 64))) { b2r_team_close(c); return rc; }
+	return B2R_OK;
+}
+static int team_signal(b2r_ctx* c, cudaStream_t st, int field, uint32_t frame) {
+	TeamPeers peers{}; const uint32_t n = static_cast<uint32_t>(c->team_sync.size());
+	for (uint32_t r = 0; r < n; r++) peers.sync[r] = static_cast<TeamSync*>(c->team_sync[r]);
+	k_team_signal<<<1, 32, 0, st>>>(peers, n, c->team_rank, field, frame);
+	CU(cudaGetLastError()); c->launches++;
+	return B2R_OK;
+}
+static int team_wait(b2r_ctx* c, int field, uint32_t frame) {
+	k_team_wait<<<1, 32, 0, c->stream>>>(c->d_team, static_cast<uint32_t>(c->team_sync.size()), field, frame);
+	CU(cudaGetLastError()); c->launches++;
+	return B2R_OK;
+}
+// peers may still be reading this rank's buckets for the last resolved frame: anything that writes them waits (on the device) first
+static int team_before_bucket_write(b2r_ctx* c) {
+	if (c->team_acc.empty() || !c->team_wait_done) return B2R_OK;
+	c->team_wait_done = false;
+	return team_wait(c, TEAM_DONE, c->team_frame);
+}
+int b2r_team_resolve(b2r_ctx* c, float* rgba_out_host, int tonemap, int async) {
+	if (!c) return fail(B2R_ERR_ARG, "null context");
+	if (c->team_acc.empty()) return fail(B2R_ERR_STATE, "b2r_team_open first");
+	int rc = ensure_device(c); if (rc) return rc;
+	if (c->accumulations == 0 || c->accumulations % c->cfg.buckets) return B2R_ERR_NOT_READY;  // Renderer.hpp:437 (every rank counts every sample, so all ranks agree)
+	const uint32_t G = static_cast<uint32_t>(c->team_acc.size()), f = ++c->team_frame;
+	const float scale = c->params.frame.cam.exposure / static_cast<float>(c->accumulations / c->cfg.buckets);  // :439
+	const bool profile = (c->cfg.flags & B2R_FLAG_NO_GRAPH) != 0;
+	if ((rc = team_signal(c, c->stream, TEAM_READY, f))) return rc;   // my buckets of frame f are final (stream order: after my last accumulate)
+	if ((rc = team_wait(c, TEAM_READY, f))) return rc;                // ... and so are everybody's
+	if (f > 1 && (rc = team_wait(c, TEAM_COPIED, f - 1))) return rc;  // rank 0 has read frame f-1 out of its framebuffer
+	BucketPtrs bp{};
+	for (uint32_t k = 0; k < c->cfg.buckets; k++) bp.k[k] = static_cast<const float*>(c->team_acc[k % G]) + static_cast<size_t>(k) * 3 * c->params.frame.npix;  // bucket k lives on rank k % G
+	// rank g resolves the g-th slab of 16x16 tiles (tile order) and writes it into rank 0's framebuffer
+	const uint32_t n_tiles = c->params.frame.npix >> 8;
+	const uint32_t t0 = static_cast<uint32_t>(static_cast<uint64_t>(n_tiles) * c->team_rank / G) << 8, t1 = static_cast<uint32_t>(static_cast<uint64_t>(n_tiles) * (c->team_rank + 1) / G) << 8;
+	rc = launch(c, KK_RESOLVE, profile, [&] { k_resolve<<<c->grid_stream, kBlock, 0, c->stream>>>(c->params.frame, bp, static_cast<float4*>(c->team_fb0), scale, tonemap, t0, t1); });
+	if (rc) return rc;
+	if ((rc = team_signal(c, c->stream, TEAM_DONE, f))) return rc;
+	c->team_wait_done = true;
+	if (c->team_rank != 0) return B2R_OK;
+	if ((rc = team_wait(c, TEAM_DONE, f))) return rc;  // every slab has landed in my framebuffer
+	c->team_wait_done = false;
+	const size_t bytes = static_cast<size_t>(c->params.frame.npix) * sizeof(float4);
+	if (rgba_out_host && async) {
+		if (!c->copy_stream) { CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&c->ev_resolved, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming)); }
+		CU(cudaEventRecord(c->ev_resolved, c->stream));
+		CU(cudaStreamWaitEvent(c->copy_stream, c->ev_resolved, 0));
+		CU(cudaMemcpyAsync(rgba_out_host, c->d_fb, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+		if ((rc = team_signal(c, c->copy_stream, TEAM_COPIED, f))) return rc;
+		CU(cudaEventRecord(c->ev_copied, c->copy_stream));
+		c->copy_pending = true;
+		return B2R_OK;
+	}
+	if (rgba_out_host) CU(cudaMemcpyAsync(rgba_out_host, c->d_fb, bytes, cudaMemcpyDeviceToHost, c->stream));
+	if ((rc = team_signal(c, c->stream, TEAM_COPIED, f))) return rc;
+	if (rgba_out_host) { CU(cudaStreamSynchronize(c->stream)); return collect_timings(c); }
+	return B2R_OK;
+}
+int b2r_team_error(b2r_ctx* c, uint32_t* out) {
+	if (!c || !out) return fail(B2R_ERR_ARG, "null argument");
+	*out = 0;
+	if (!c->d_team) return B2R_OK;
+	int rc = ensure_device(c); if (rc) return rc;
+	CU(cudaMemcpyAsync(out, &c->d_team->error, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return B2R_OK;
 }
 
 int b2r_get_accumulations(b2r_ctx* c, uint32_t* out) { if (!c || !out) return fail(B2R_ERR_ARG, "null argument"); *out = c->accumulations; return B2R_OK; }

@@ -747,15 +747,52 @@ __device__ __forceinline__ float median_buckets_at(const BucketPtrs& bp, uint32_
 // Renderer::Render, Renderer.hpp:436-478: one thread per pixel (tile order in, raster RGBA out). With peer pointers this one
 // kernel is the whole multi-GPU combine: the median network pulls each bucket from its owner over NVLink (coalesced 128-byte
 // peer loads) — no all-reduce, no staging copy.
-__global__ void __launch_bounds__(kBlock) k_resolve(const FrameDev frame, const __grid_constant__ BucketPtrs bp, float4* __restrict__ fb, const float scale, const int tonemap) {
+__global__ void __launch_bounds__(kBlock) k_resolve(const FrameDev frame, const __grid_constant__ BucketPtrs bp, float4* __restrict__ fb, const float scale, const int tonemap,
+                                                    const uint32_t t_begin, const uint32_t t_end) {
 	const uint32_t npix = frame.npix, K = frame.buckets;
-	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < npix; t += gridDim.x * blockDim.x) {
+	for (uint32_t t = t_begin + blockIdx.x * blockDim.x + threadIdx.x; t < t_end; t += gridDim.x * blockDim.x) {
 		float r = scale * median_buckets_at(bp, K, t);
 		float g = scale * median_buckets_at(bp, K, npix + t);
 		float b = scale * median_buckets_at(bp, K, 2u * npix + t);
 		if (tonemap) aces_tonemap(&r, &g, &b);
 		int32_t x, y; pixel_xy(t, frame, &x, &y);
 		fb[static_cast<size_t>(y) * frame.width + x] = make_float4(r, g, b, 1.0f);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------- multi-GPU team: device-side hand-shakes
+// One TeamSync block per rank, in its own HBM, mapped by every peer (CUDA IPC). A rank announces an event by storing the frame number
+// into ITS entry of every peer's block (release, system scope, over NVLink); a rank waits by spinning on its own block (acquire, local
+// HBM). Frame numbers only grow, so nothing is ever reset. Every signal is enqueued on the signalling rank's stream before anything
+// that rank waits for, so the waits cannot deadlock; they still give up after kTeamSpinLimit cycles and flag an error instead of hanging
+// the GPU if a peer died.
+constexpr int kTeamMax = 16;
+struct TeamSync {
+	uint32_t ready[kTeamMax];   // ready[r]  = last frame whose buckets rank r has finished accumulating
+	uint32_t done[kTeamMax];    // done[r]   = last frame rank r has finished resolving (its reads of peer buckets and its slab writes are complete)
+	uint32_t copied;            // last frame rank 0 has copied out of its framebuffer (the framebuffer may be overwritten)
+	uint32_t error;             // non-zero: a wait timed out
+};
+struct TeamPeers { TeamSync* sync[kTeamMax]; };
+enum TeamField { TEAM_READY = 0, TEAM_DONE = 1, TEAM_COPIED = 2 };
+constexpr long long kTeamSpinLimit = 8000000000ll;  // ~4 s at 1.9 GHz
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__global__ void k_team_signal(const __grid_constant__ TeamPeers peers, const uint32_t n_ranks, const uint32_t my_rank, const int field, const uint32_t frame) {
+	const uint32_t r = threadIdx.x;
+	if (r >= n_ranks) return;
+	__threadfence_system();  // everything this rank wrote before (stream order) is visible system-wide before the flag is
+	TeamSync* s = peers.sync[r];
+	st_release_sys(field == TEAM_READY ? &s->ready[my_rank] : field == TEAM_DONE ? &s->done[my_rank] : &s->copied, frame);
+}
+__global__ void k_team_wait(TeamSync* mine, const uint32_t n_ranks, const int field, const uint32_t frame) {
+	const uint32_t r = threadIdx.x;
+	if (r >= (field == TEAM_COPIED ? 1u : n_ranks)) return;
+	const uint32_t* flag = field == TEAM_READY ? &mine->ready[r] : field == TEAM_DONE ? &mine->done[r] : &mine->copied;
+	const long long t0 = clock64();
+	while (static_cast<int32_t>(ld_acquire_sys(flag) - frame) < 0) {
+		if (clock64() - t0 > kTeamSpinLimit) { atomicExch(&mine->error, 1u + static_cast<uint32_t>(field)); break; }
+		__nanosleep(200);
 	}
 }
 

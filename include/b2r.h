@@ -174,6 +174,21 @@ int  b2r_ipc_export_buckets(b2r_ctx* ctx, unsigned char handle_out[64]);
 int  b2r_ipc_open_peers(b2r_ctx* ctx, const unsigned char* peer_handles, uint32_t n_peers, uint32_t my_rank);
 int  b2r_ipc_close(b2r_ctx* ctx);
 int  b2r_resolve_peers(b2r_ctx* ctx, float* rgba_out_host, int tonemap);
+/* Team mode — the multi-GPU frame without host barriers. Every rank exports three handles (its bucket array, its framebuffer, a small
+ * block of hand-shake flags), the ranks exchange them once (any transport) and open each other's; after that a frame needs no host
+ * synchronisation between ranks at all. b2r_team_resolve, called by EVERY rank once its samples are enqueued: rank g waits on the device
+ * until every rank's buckets of this frame are final, resolves the g-th slab of 16x16 tiles — median of the K bucket sums read straight
+ * from their owners' HBM over NVLink (bucket k lives on rank k % n_ranks), exposure scale, ACES — and stores it into RANK 0's framebuffer
+ * over NVLink; rank 0 then copies the frame to rgba_out_host (async != 0: on its copy stream, page-locked buffer, b2r_frame_wait to join;
+ * NULL: the frame stays on the device). The hand-shakes are release/acquire flags in peer-mapped memory written and polled by tiny
+ * kernels in stream order (a wait gives up after ~4 s and raises b2r_team_error instead of hanging the GPU); b2r_reset / b2r_accumulate
+ * of the next frame wait the same way until the peers have finished reading this rank's buckets. The resolved frame is bit-identical to a
+ * single-GPU render of the same samples. The resized framebuffer / bucket array must not be exported: b2r_resize fails while a team is open. */
+int  b2r_team_export(b2r_ctx* ctx, unsigned char handles_out[192]);
+int  b2r_team_open(b2r_ctx* ctx, const unsigned char* all_handles /* n_ranks x 192 bytes, rank order */, uint32_t n_ranks, uint32_t my_rank);
+int  b2r_team_resolve(b2r_ctx* ctx, float* rgba_out_host, int tonemap, int async);
+int  b2r_team_error(b2r_ctx* ctx, uint32_t* error_out);   /* 0 = no hand-shake has timed out (synchronises the stream) */
+int  b2r_team_close(b2r_ctx* ctx);
 /* counters since the last reset: [0] extension rays, [1] shadow rays, [2] shaded hits, [3] terminated paths,
  * [4] dropped at max_bounces (Q11), [5] sphere tests, [6] box tests (5,6 only with B2R_FLAG_COUNT_TESTS), [7] kernel launches,
  * [8] radiance contributions written (light samples, emissive hits, sky), [9] reserved */

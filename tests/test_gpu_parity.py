@@ -697,3 +697,30 @@ def test_refit_scene_error_behaviour():
     bad = b2r.PreparedScene(sc, 64, 48); bad.prims = bad.prims.copy(); bad.prims["material_ID"][3] = 99
     assert b2r.lib().b2r_refit_scene(r._h, *args(bad)) == b2r.ERR_ARG
     r.close()
+
+
+def test_team_mode_on_one_gpu_equals_plain_render():
+    """b2r_team_* with a team of one: the same hand-shake kernels, slab resolve and copy paths as on N GPUs (the 2-GPU case is
+    tests/test_multigpu_gpu.py), frames bit-identical to Render(); a resize while the team is open is refused."""
+    import torch
+    sc = scenes.default_scene()
+    w, h = 256, 144
+    a = b2r.Renderer(sc, w, h, max_bounces=8, buckets=8); b = b2r.Renderer(sc, w, h, max_bounces=8, buckets=8)
+    b.team_open([b.team_export()], 0)
+    pinned = torch.empty((h, w, 4), dtype=torch.float32, pin_memory=True).numpy()
+    for k, n in enumerate((8, 16, 8)):
+        a.ResetAccumulator(); a.Accumulate(n); assert a.Render()
+        b.ResetAccumulator(); b.Accumulate(n)
+        if k == 1:
+            assert b.RenderTeam(out=pinned, use_async=True); b.WaitFrame(); got = pinned
+        else:
+            assert b.RenderTeam(); got = b.framebuffer
+        assert got.tobytes() == a.framebuffer.tobytes()
+    a.Accumulate(8); assert a.Render(); b.Accumulate(8); assert b.RenderTeam()      # progressive, no reset in between
+    assert b.framebuffer.tobytes() == a.framebuffer.tobytes()
+    b.Accumulate(3); assert not b.RenderTeam()                                      # accumulations % K != 0: no-op like Renderer::Render
+    assert b.team_error() == 0
+    with pytest.raises(b2r.B2RError):
+        b.Resize(128, 64)
+    b.team_close(); b.Resize(128, 64)
+    a.close(); b.close()

@@ -1,6 +1,6 @@
-"""Two-GPU test (-m gpu, skipped on a single-GPU box): two processes, NCCL, sample buckets split between them. Both frame
-combines — NCCL all-reduce then resolve, and the fused resolve that reads the peer's buckets over NVLink — must reproduce the
-single-GPU frame bit-for-bit."""
+"""Two-GPU test (-m gpu, skipped on a single-GPU box): two processes, NCCL, sample buckets split between them. All three frame
+combines — NCCL all-reduce then resolve, rank 0's resolve reading the peer's buckets over NVLink, and team mode (every rank resolves its
+slab into rank 0's framebuffer, device-side hand-shakes, no host barrier per frame) — must reproduce the single-GPU frame bit-for-bit."""
 import os
 import socket
 
@@ -32,7 +32,31 @@ def _worker(rank, world, port, out_dir):
     b = np.zeros((H, W, 4), np.float32); assert r.RenderPeers(out=b)
     dist.barrier()
     np.save(os.path.join(out_dir, f"nccl{rank}.npy"), a); np.save(os.path.join(out_dir, f"p2p{rank}.npy"), b)
-    r.ipc_close(); r.close()
+    r.ipc_close()
+    # team mode: every rank resolves its slab into rank 0's framebuffer; no host barrier between the frames. Three frames back to back
+    # (reset, more samples each time) so that the "peers have read my buckets" and "rank 0 has copied the frame" hand-shakes are exercised;
+    # the last one leaves through rank 0's copy stream.
+    b2r_dist.open_team(r)
+    frames = []
+    for k, n in enumerate((SAMPLES, 2 * SAMPLES, SAMPLES)):
+        r.ResetAccumulator(); r.Accumulate(n)
+        f = np.zeros((H, W, 4), np.float32)
+        if k == 2:
+            import torch as _t
+            pinned = _t.empty((H, W, 4), dtype=_t.float32, pin_memory=True).numpy()
+            assert r.RenderTeam(out=pinned, use_async=True)
+            if rank == 0:
+                r.WaitFrame(); f = pinned.copy()
+        else:
+            assert r.RenderTeam(out=f)
+        frames.append(f)
+    # progressive: samples keep accumulating across resolves without a reset (the next Accumulate waits for the peers' reads on the device)
+    r.Accumulate(SAMPLES); g = np.zeros((H, W, 4), np.float32); assert r.RenderTeam(out=g); frames.append(g)
+    assert r.team_error() == 0
+    if rank == 0:
+        np.save(os.path.join(out_dir, "team.npy"), np.stack(frames))
+    dist.barrier()
+    r.team_close(); r.close()
     dist.destroy_process_group()
 
 
@@ -46,4 +70,10 @@ def test_two_gpu_frame_equals_single_gpu(tmp_path):
     single = b2r.Renderer(scenes.default_scene(), W, H, max_bounces=MB, buckets=K); single.Accumulate(SAMPLES); assert single.Render()
     for name in ("nccl0", "nccl1", "p2p0", "p2p1"):
         assert np.load(tmp_path / f"{name}.npy").tobytes() == single.framebuffer.tobytes(), name
+    team = np.load(tmp_path / "team.npy")
+    assert team[0].tobytes() == single.framebuffer.tobytes() and team[2].tobytes() == single.framebuffer.tobytes()
+    single.ResetAccumulator(); single.Accumulate(2 * SAMPLES); assert single.Render()
+    assert team[1].tobytes() == single.framebuffer.tobytes()
+    single.ResetAccumulator(); single.Accumulate(SAMPLES); single.Accumulate(SAMPLES); assert single.Render()
+    assert team[3].tobytes() == single.framebuffer.tobytes()
     single.close()
