@@ -24,14 +24,14 @@ except ImportError:  # imported as a top-level module from the package directory
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B2R_LIB_PATH", os.path.join(_HERE, "libb2r.so"))  # override: kernel A/B experiments only
 
-FLAG_FORCE_BRUTE, FLAG_FORCE_BVH, FLAG_NO_MIS, FLAG_COUNT_TESTS, FLAG_NO_GRAPH, FLAG_REFERENCE_TREE, FLAG_REFERENCE_EXACT = 1, 2, 4, 8, 16, 32, 64
+FLAG_FORCE_BRUTE, FLAG_FORCE_BVH, FLAG_NO_MIS, FLAG_COUNT_TESTS, FLAG_NO_GRAPH, FLAG_REFERENCE_TREE, FLAG_REFERENCE_EXACT, FLAG_NO_SPECULATION = 1, 2, 4, 8, 16, 32, 64, 128
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NO_LIGHTS, ERR_BVH, NOT_READY = 0, -1, -2, -3, -4, -5, 1
 KERNEL_KINDS = ["generate", "bounce_brute", "intersect_closest", "shade", "intersect_shadow", "accumulate", "resolve"]
 COUNTER_NAMES = ["extension_rays", "shadow_rays", "shaded_hits", "terminated", "dropped", "sphere_tests", "box_tests", "launches", "radiance_events", "reserved"]
 
 # every symbol include/b2r.h declares (tests/test_abi.py checks the header against this list and the library against both)
 ABI_SYMBOLS = [
-    "b2r_bvh_build", "b2r_bvh_build_ex", "b2r_find_lights", "b2r_camera_lookat", "b2r_create", "b2r_destroy", "b2r_resize", "b2r_reset", "b2r_set_stream",
+    "b2r_bvh_build", "b2r_bvh_build_ex", "b2r_find_lights", "b2r_camera_lookat", "b2r_camera_ray", "b2r_create", "b2r_destroy", "b2r_resize", "b2r_reset", "b2r_set_stream",
     "b2r_sync", "b2r_upload_scene", "b2r_refit_scene", "b2r_set_camera", "b2r_accumulate", "b2r_resolve", "b2r_resolve_async", "b2r_frame_wait", "b2r_resolve_from", "b2r_ipc_export_buckets", "b2r_ipc_open_peers", "b2r_ipc_close", "b2r_resolve_peers", "b2r_team_export", "b2r_team_open", "b2r_team_resolve", "b2r_team_error", "b2r_team_close", "b2r_get_accumulations", "b2r_set_accumulations",
     "b2r_read_buckets", "b2r_write_buckets", "b2r_device_buckets", "b2r_device_framebuffer", "b2r_read_counters", "b2r_reset_counters",
     "b2r_read_kernel_times", "b2r_set_flags", "b2r_generate_rays", "b2r_trace_closest", "b2r_trace_shadow", "b2r_read_wide_nodes", "b2r_get_origin_box",
@@ -63,7 +63,7 @@ def lib():
         vp, u32, i32, f32 = C.c_void_p, C.c_uint32, C.c_int32, C.c_float
         sig = {
             "b2r_bvh_build": [vp, u32, vp, vp, vp, vp], "b2r_bvh_build_ex": [vp, u32, u32, f32, vp, vp, vp, vp], "b2r_find_lights": [vp, u32, vp, u32, vp, vp],
-            "b2r_camera_lookat": [vp, vp, u32, u32, f32, f32, vp], "b2r_create": [vp, vp], "b2r_resize": [vp, u32, u32], "b2r_reset": [vp],
+            "b2r_camera_lookat": [vp, vp, u32, u32, f32, f32, vp], "b2r_camera_ray": [vp, vp, f32, f32, f32, i32, i32, vp, vp, vp], "b2r_create": [vp, vp], "b2r_resize": [vp, u32, u32], "b2r_reset": [vp],
             "b2r_set_stream": [vp, vp], "b2r_sync": [vp],
             "b2r_upload_scene": [vp, vp, vp, u32, u32, vp, u32, vp, u32, vp, u32, vp, vp, i32, i32],
             "b2r_refit_scene": [vp, vp, u32, vp, u32, vp, u32, vp, u32, vp],

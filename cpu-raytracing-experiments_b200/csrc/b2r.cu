@@ -17,9 +17,9 @@ int fail(int code, const std::string& what) { g_error = what; return code; }
 
 enum KernelKind { KK_GENERATE = 0, KK_BRUTE, KK_CLOSEST, KK_SHADE, KK_SHADOW, KK_ACCUMULATE, KK_RESOLVE, KK_COUNT };
 
-struct BatchArgs { uint32_t n; uint32_t acc[kMaxSlots]; };
+struct BatchArgs { uint32_t n; uint32_t acc[kMaxSlots]; unsigned long long fold = ~0ull; };
 __global__ void k_set_batch(BatchDev* dst, const BatchArgs a) {
-	if (threadIdx.x == 0) dst->n_slots = a.n;
+	if (threadIdx.x == 0) { dst->n_slots = a.n; dst->fold = a.fold; }
 	if (threadIdx.x < a.n) dst->acc[threadIdx.x] = a.acc[threadIdx.x];
 }
 
@@ -85,14 +85,20 @@ struct b2r_ctx {
 	// peers' bucket arrays mapped through CUDA IPC (multi-GPU fused resolve)
 	std::vector<void*> peer_acc; uint32_t my_rank = 0;
 	// team mode (b2r_team_*): peers' bucket arrays, rank 0's framebuffer and every rank's TeamSync block, mapped through CUDA IPC
+	// samples traced ahead of the caller: an application that calls Accumulate() once per frame (Application.cpp:379) gets wavefront
+	// batches of 2, 4, ... kSpecMax samples as long as nothing invalidates them; the extra samples wait in RAD and are folded by later calls
+	uint32_t spec_width = 1, spec_first = 0, spec_count = 0, spec_used = 0; BatchArgs spec_args;
 	TeamSync* d_team = nullptr; std::vector<void*> team_acc, team_sync; void* team_fb0 = nullptr; uint32_t team_rank = 0, team_frame = 0; bool team_wait_done = false;
 };
 
 namespace {
 
 int ensure_device(b2r_ctx* c) { CU(cudaSetDevice(c->cfg.device)); return B2R_OK; }
+constexpr uint32_t kSpecMax = 16;
+void drop_speculation(b2r_ctx* c) { c->spec_count = 0; c->spec_used = 0; c->spec_width = 1; }  // scene, camera, sample index or buckets changed under the samples traced ahead
 
 void drop_graph(b2r_ctx* c) {
+	drop_speculation(c);  // everything that invalidates the captured graph (camera, scene pointers, flags, frame size) invalidates them too
 	if (c->graph_exec) { if (c->stream) cudaStreamSynchronize(c->stream); cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }  // (a launch of it may still be running)
 	c->graph_valid = false;
 }
@@ -367,7 +373,7 @@ int b2r_resize(b2r_ctx* c, uint32_t width, uint32_t height) {
 int b2r_reset(b2r_ctx* c) {
 	if (!c) return fail(B2R_ERR_ARG, "null context");
 	int rc = ensure_device(c); if (rc) return rc;
-	c->accumulations = 0;
+	c->accumulations = 0; drop_speculation(c);
 	if ((rc = team_before_bucket_write(c))) return rc;
 	const size_t npix = static_cast<size_t>(c->cfg.width) * c->cfg.height;
 	CU(cudaMemsetAsync(c->d_acc, 0, static_cast<size_t>(c->cfg.buckets) * 3 * npix * sizeof(float), c->stream));
@@ -497,7 +503,7 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 		{c->d_wide, c->wide_host.nodes.data(), c->wide_host.nodes.size() * sizeof(WideNode)}, {c->d_hdri, hdri_rgba, texels * sizeof(float4)},
 	};
 	if ((rc = stage_upload(c, parts, sizeof parts / sizeof parts[0]))) return rc;
-	c->wide_refit = false; c->cur_geom_of_prim.clear();
+	c->wide_refit = false; c->cur_geom_of_prim.clear(); drop_speculation(c);
 	const SceneDev before = c->params.scene; const bool bvh_before = c->use_bvh;
 	SceneDev& s = c->params.scene;
 	s.prims = c->d_prims; s.prim_mat = c->d_prim_mat; s.mat_albedo = c->d_mat_albedo; s.mat_emission = c->d_mat_emission;
@@ -568,7 +574,7 @@ int b2r_refit_scene(b2r_ctx* c, const b2r_sphere* prims, uint32_t n_prims, const
 		}
 	}
 	if ((rc = launch_refit_levels(c, same_order ? nullptr : c->d_remap))) return rc;
-	c->wide_refit = true;
+	c->wide_refit = true; drop_speculation(c);
 	const SceneDev before = c->params.scene;
 	SceneDev& s = c->params.scene;
 	s.mat_albedo = c->d_mat_albedo; s.mat_emission = c->d_mat_emission; s.light_sphere = c->d_light_sphere; s.light_emit = c->d_light_emit;
@@ -606,12 +612,36 @@ int b2r_accumulate(b2r_ctx* c, uint32_t n_samples) {
 	if (!c->have_scene || !c->have_camera) return fail(B2R_ERR_STATE, "upload_scene and set_camera must precede accumulate");
 	int rc = ensure_device(c); if (rc) return rc;
 	if ((rc = team_before_bucket_write(c))) return rc;
+	const bool speculate = c->cfg.bucket_stride <= 1 && !(c->cfg.flags & (B2R_FLAG_NO_SPECULATION | B2R_FLAG_NO_GRAPH));
 	BatchArgs args; args.n = 0;
 	for (uint32_t s = 0; s < n_samples; s++) {
 		const uint32_t acc = ++c->accumulations;  // pre-increment: the first sample has index 1 (Renderer.hpp:74, Q1)
-		if (owns_sample(c, acc)) args.acc[args.n++] = acc;
+		if (c->spec_used < c->spec_count && acc == c->spec_first + c->spec_used) {
+			// traced ahead by an earlier call: fold it (samples are folded in index order: earlier samples of this call go first)
+			if (args.n) { if ((rc = run_batch(c, args))) return rc; args.n = 0; }
+			BatchArgs f = c->spec_args; f.fold = 1ull << c->spec_used;
+			k_set_batch<<<1, kMaxSlots, 0, c->stream>>>(c->d_batch, f);
+			k_accumulate<<<c->grid_stream, kBlock, 0, c->stream>>>(c->params);
+			CU(cudaGetLastError()); c->launches += 1;
+			if (++c->spec_used == c->spec_count) { c->spec_count = 0; c->spec_used = 0; c->spec_width = c->spec_width * 2u > kSpecMax ? kSpecMax : c->spec_width * 2u; }
+			continue;
+		}
+		if (c->spec_count) drop_speculation(c);  // the caller jumped elsewhere
+		if (!owns_sample(c, acc)) continue;
+		if (speculate && n_samples == 1) {
+			// the reference's frame loop: one Accumulate() per application frame. Trace spec_width samples now, fold the first.
+			const uint32_t w = c->spec_width < c->slots ? c->spec_width : c->slots;
+			args.n = w; for (uint32_t i = 0; i < w; i++) args.acc[i] = acc + i;
+			args.fold = 1ull;
+			if ((rc = run_batch(c, args))) return rc;
+			if (w > 1) { c->spec_args = args; c->spec_first = acc; c->spec_count = w; c->spec_used = 1; }
+			else c->spec_width = 2;
+			return B2R_OK;
+		}
+		args.acc[args.n++] = acc;
 		if (args.n == c->slots || (s + 1 == n_samples && args.n)) { if ((rc = run_batch(c, args))) return rc; args.n = 0; }
 	}
+	if (args.n) { if ((rc = run_batch(c, args))) return rc; }
 	return B2R_OK;
 }
 
@@ -813,7 +843,7 @@ int b2r_team_error(b2r_ctx* c, uint32_t* out) {
 }
 
 int b2r_get_accumulations(b2r_ctx* c, uint32_t* out) { if (!c || !out) return fail(B2R_ERR_ARG, "null argument"); *out = c->accumulations; return B2R_OK; }
-int b2r_set_accumulations(b2r_ctx* c, uint32_t acc) { if (!c) return fail(B2R_ERR_ARG, "null context"); c->accumulations = acc; return B2R_OK; }
+int b2r_set_accumulations(b2r_ctx* c, uint32_t acc) { if (!c) return fail(B2R_ERR_ARG, "null context"); c->accumulations = acc; drop_speculation(c); return B2R_OK; }
 
 int b2r_read_buckets(b2r_ctx* c, float* out_host) {
 	if (!c || !out_host) return fail(B2R_ERR_ARG, "null argument");
@@ -825,6 +855,7 @@ int b2r_read_buckets(b2r_ctx* c, float* out_host) {
 int b2r_write_buckets(b2r_ctx* c, const float* in_host) {
 	if (!c || !in_host) return fail(B2R_ERR_ARG, "null argument");
 	int rc = ensure_device(c); if (rc) return rc;
+	drop_speculation(c);
 	CU(cudaMemcpyAsync(c->d_acc, in_host, static_cast<size_t>(c->cfg.buckets) * 3 * c->params.frame.npix * sizeof(float), cudaMemcpyHostToDevice, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
 	return B2R_OK;

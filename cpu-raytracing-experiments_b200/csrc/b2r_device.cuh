@@ -703,7 +703,8 @@ __global__ void __launch_bounds__(kBlock) k_accumulate(const Params p) {
 	const uint32_t npix4 = p.frame.npix / 4u, n = 3u * npix4, slots = p.batch->n_slots, K = p.frame.buckets;
 	if (threadIdx.x == 0) {
 		uint32_t m = 0;
-		for (uint32_t k = 0; k < K; k++) { s_first[k] = m; for (uint32_t s = 0; s < slots; s++) if (p.batch->acc[s] % K == k) s_order[m++] = s; }
+		const unsigned long long fold = p.batch->fold;
+		for (uint32_t k = 0; k < K; k++) { s_first[k] = m; for (uint32_t s = 0; s < slots; s++) if (((fold >> s) & 1ull) && p.batch->acc[s] % K == k) s_order[m++] = s; }
 		s_first[K] = m;
 	}
 	__syncthreads();

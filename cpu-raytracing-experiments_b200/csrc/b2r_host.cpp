@@ -198,14 +198,27 @@ void build_reference_bvh(const b2r_sphere* geometry, uint32_t n, std::vector<b2r
 }
 
 bool validate_reference_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, uint32_t n_prims) {
+	// What flatten_bvh and the reference's own builder rely on (BVH.hpp:90-206): 2n-1 nodes; an inner node's two children are adjacent
+	// and were allocated AFTER it (first_id > own index: no cycles); leaves hold one sphere; every node but the root is some inner
+	// node's child exactly once and every sphere sits in exactly one leaf (no shared or orphaned subtrees, no sphere rendered twice).
 	if (n_nodes == 0) return false;
 	if (n_prims == 0) return n_nodes == 1;
 	if (n_nodes != 2 * n_prims - 1) return false;
+	std::vector<unsigned char> node_seen(n_nodes, 0), prim_seen(n_prims, 0);
 	for (uint32_t i = 0; i < n_nodes; i++) {
-		if (nodes[i].prim_count == 0) { if (nodes[i].first_id == 0 || static_cast<uint64_t>(nodes[i].first_id) + 1 >= n_nodes) return false; }
-		else if (nodes[i].prim_count != 1 || nodes[i].first_id >= n_prims) return false;
+		if (nodes[i].prim_count == 0) {
+			const uint64_t first = nodes[i].first_id;
+			if (first <= i || first + 1 >= n_nodes) return false;
+			if (node_seen[first] || node_seen[first + 1]) return false;
+			node_seen[first] = node_seen[first + 1] = 1;
+		} else {
+			if (nodes[i].prim_count != 1 || nodes[i].first_id >= n_prims || prim_seen[nodes[i].first_id]) return false;
+			prim_seen[nodes[i].first_id] = 1;
+		}
 	}
-	return true;
+	if (node_seen[0]) return false;
+	for (uint32_t i = 1; i < n_nodes; i++) if (!node_seen[i]) return false;
+	return true;  // n_prims leaves each with a distinct sphere follows from the counts: (n-1) inner nodes claim 2(n-1) children, the rest are leaves
 }
 
 namespace {
@@ -426,6 +439,15 @@ int b2r_find_lights(const b2r_sphere* geometry, uint32_t n, const b2r_material* 
 		if (e[0] * e[0] + e[1] * e[1] + e[2] * e[2] > 0.0f) { if (out) out[count] = static_cast<int32_t>(i); count++; }
 	}
 	*n_out = count;
+	return B2R_OK;
+}
+
+int b2r_camera_ray(const float pos[3], const float q[4], float half_width, float half_height, float z, int32_t x, int32_t y, const float samples[2], float origin_out[3], float dir_out[3]) {
+	if (!pos || !q || !samples || !origin_out || !dir_out) return B2R_ERR_ARG;
+	const b2r::CameraParams cam{pos[0], pos[1], pos[2], q[0], q[1], q[2], q[3], half_width, half_height, z, 1.0f};
+	const b2r::f3 d = b2r::camera_dir(cam, x, y, samples[0], samples[1]);  // the routine the kernels run per pixel (b2r_math.h)
+	origin_out[0] = pos[0]; origin_out[1] = pos[1]; origin_out[2] = pos[2];
+	dir_out[0] = d.x; dir_out[1] = d.y; dir_out[2] = d.z;
 	return B2R_OK;
 }
 

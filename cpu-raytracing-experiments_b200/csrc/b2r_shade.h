@@ -65,6 +65,7 @@ B2R_HD uint32_t magic_for(uint32_t d) { return d <= 1u ? 0xffffffffu : static_ca
 struct BatchDev {  // one wavefront batch: n_slots samples traced together
 	uint32_t n_slots;
 	uint32_t acc[kMaxSlots];  // sample index (the reference's `accumulations` value, Q1) of each slot
+	unsigned long long fold;  // slots k_accumulate folds into the buckets now (the others were traced ahead of the caller's Accumulate() calls)
 };
 struct QueueDev {
 	float4* A[2]; float4* B[2]; float* T[2];

@@ -58,4 +58,15 @@ struct Camera {  // Camera.hpp:61-88
 	View view;
 	Projection projection;
 	float exp;
+
+	struct Ray { b2r_host::vec3 origin, dir; };
+	// Camera.hpp:80-88: the ray through pixel (x, y) with sub-pixel position samples[0..1]; computed by libb2r's camera routine (the one the
+	// kernels run per pixel), so `const auto [orig, dir] = scene.camera.generate_ray(x, y, no_pixel_jitter)` (Application.cpp:288) compiles
+	// unchanged and gives the renderer's own ray bit for bit.
+	Ray generate_ray(int32_t x, int32_t y, const float* samples) const noexcept {
+		const float p[3] = {view.pos.x, view.pos.y, view.pos.z}, q[4] = {view.orient.w, view.orient.x, view.orient.y, view.orient.z};
+		float o[3], d[3];
+		b2r_camera_ray(p, q, projection.half_width, projection.half_height, projection.z, x, y, samples, o, d);
+		return {view.pos, {d[0], d[1], d[2]}};
+	}
 };

@@ -44,14 +44,12 @@ int main(int argc, char** argv) {
 		auto depth_ray = std::make_unique<RayStream<8>>();
 		depth_ray->hit.matID[0] = -1; depth_ray->hit.primID[0] = -1; depth_ray->hit.tfar[0] = FLT_MAX;
 		auto* raygen_buffer = depth_ray->path.input;
-		const float q[4] = {scene.camera.view.orient.w, scene.camera.view.orient.x, scene.camera.view.orient.y, scene.camera.view.orient.z};
-		(void)q;
-		float ray[6] = {scene.camera.view.pos.x, scene.camera.view.pos.y, scene.camera.view.pos.z, 0.1f, -0.4f, -1.0f};
-		const float inv = 1.0f / std::sqrt(ray[3] * ray[3] + ray[4] * ray[4] + ray[5] * ray[5]);
-		raygen_buffer->p.x[0] = ray[0]; raygen_buffer->p.y[0] = ray[1]; raygen_buffer->p.z[0] = ray[2];
-		raygen_buffer->dir.x[0] = ray[3] * inv; raygen_buffer->dir.y[0] = ray[4] * inv; raygen_buffer->dir.z[0] = ray[5] * inv;
+		static constexpr float no_pixel_jitter[2]{0.5f, 0.5f};
+		const auto [orig, dir] = scene.camera.generate_ray(static_cast<int32_t>(viewport_width / 2), static_cast<int32_t>(viewport_height / 2), no_pixel_jitter);  // Application.cpp:287-288
+		raygen_buffer->dir.x[0] = dir.x; raygen_buffer->dir.y[0] = dir.y; raygen_buffer->dir.z[0] = dir.z;
+		raygen_buffer->p.x[0] = orig.x; raygen_buffer->p.y[0] = orig.y; raygen_buffer->p.z[0] = orig.z;
 		scene.acceleration_structure.Traverse<8>(*depth_ray->path.input, depth_ray->hit, 1);
-		float t2; int32_t p2; const float r6[6] = {ray[0], ray[1], ray[2], ray[3] * inv, ray[4] * inv, ray[5] * inv};
+		float t2; int32_t p2; const float r6[6] = {orig.x, orig.y, orig.z, dir.x, dir.y, dir.z};
 		renderer.Traverse(r6, 1, &t2, &p2);
 		std::printf("focus pick: prim %d mat %d depth %.6f (renderer path: prim %d depth %.6f)\n", depth_ray->hit.primID[0], depth_ray->hit.matID[0], depth_ray->hit.tfar[0], p2, t2);
 	}

@@ -58,6 +58,8 @@ enum {
 	                                     * formula (BVH.hpp:250-286: the last `active % 8` rays of each 16x16 tile's stream take the scalar tail;
 	                                     * stream order = stable counting sort by material, DataStreams.hpp:236-253). Results are then bit-identical
 	                                     * to the reference's own Renderer::Accumulate, at the price of one extra ranking kernel per bounce. */
+	B2R_FLAG_NO_SPECULATION = 1u << 7, /* b2r_accumulate(ctx, 1) traces exactly one sample (default: a caller that asks for one sample per frame gets
+	                                    * batches of 2, 4, ... 16 samples traced ahead while nothing changes; results are identical either way) */
 };
 
 typedef struct b2r_config {
@@ -101,6 +103,13 @@ int b2r_find_lights(const b2r_sphere* geometry, uint32_t n, const b2r_material* 
  * half_width, half_height, z, exposure: the exact arguments of b2r_set_camera. */
 int b2r_camera_lookat(const float eye[3], const float dir[3], uint32_t width, uint32_t height, float focal_length_mm,
                       float exposure, float out11[11]);
+
+/* Camera::generate_ray (Camera.hpp:80-88) for ONE pixel, on the host: view.pos and normalize(view.orient * {x + samples[0] - half_width,
+ * y + samples[1] - half_height, z}) with glm's scalar arithmetic — the call the app's focus picking makes (Application.cpp:288) before it
+ * hands the ray to BoundingVolumeHierarchy::Traverse (b2r_trace_closest). The renderer's own camera rays are generated on the GPU by the
+ * same routine (b2r_generate_rays); this entry is for host code that needs a single ray. */
+int b2r_camera_ray(const float pos[3], const float orient_wxyz[4], float half_width, float half_height, float z,
+                   int32_t x, int32_t y, const float samples[2], float origin_out[3], float dir_out[3]);
 
 /* ---- renderer life cycle (Renderer<Policy>, Renderer.hpp:28-68) -------------------------------------- */
 int  b2r_create(b2r_ctx** out, const b2r_config* cfg);             /* Renderer(const Scene&) + Resize, :51-63 */

@@ -139,6 +139,8 @@ int hc_refit(const b2r_sphere* prims_a, const b2r_bvh_node* nodes_a, uint32_t n_
 	}
 	return 0;
 }
+// validate_reference_bvh tap (what b2r_upload_scene checks before it flattens a caller's node array)
+int hc_validate(const b2r_bvh_node* nodes, uint32_t n_nodes, uint32_t n_prims) { return validate_reference_bvh(nodes, n_nodes, n_prims) ? 1 : 0; }
 // match_prims_to_geometry tap: geom_of_prim[n]; returns 1 when prims is a permutation of geometry
 int hc_match(const b2r_sphere* prims, const b2r_sphere* geometry, uint32_t n, uint32_t* geom_of_prim) {
 	std::vector<uint32_t> m; if (!match_prims_to_geometry(prims, geometry, n, m)) return 0;

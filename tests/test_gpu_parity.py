@@ -724,3 +724,36 @@ def test_team_mode_on_one_gpu_equals_plain_render():
         b.Resize(128, 64)
     b.team_close(); b.Resize(128, 64)
     a.close(); b.close()
+
+
+def test_samples_traced_ahead_are_invisible_to_the_caller():
+    """The drop-in's call pattern is one Accumulate() per application frame (Application.cpp:379). The library traces 2, 4, ... 16 samples
+    ahead while nothing changes and folds them on the later calls. Bucket sums after every single call must be exactly those of a renderer
+    that traces one sample per call (B2R_FLAG_NO_SPECULATION) and of one Accumulate(n) — including across a camera change, a reset, a
+    jump of the sample index and a mixed Accumulate(1) / Accumulate(n) sequence, on both pipelines."""
+    for sc, flags in ((scenes.default_scene(), 0), (scenes.random_scene(700, light_every=30), b2r.FLAG_FORCE_BVH)):
+        w, h, K = 128, 80, 4
+        a = b2r.Renderer(sc, w, h, max_bounces=6, buckets=K, flags=flags)
+        b = b2r.Renderer(sc, w, h, max_bounces=6, buckets=K, flags=flags | b2r.FLAG_NO_SPECULATION)
+        def both(fn):
+            fn(a); fn(b)
+        for i in range(21):                                   # 1, then batches of 2, 4, 8, 16 traced ahead
+            both(lambda r: r.Accumulate(1))
+            if i in (0, 1, 2, 5, 6, 13, 14, 20):
+                assert a.buckets_host().tobytes() == b.buckets_host().tobytes(), i
+        c = b2r.Renderer(sc, w, h, max_bounces=6, buckets=K, flags=flags); c.Accumulate(21)
+        assert a.buckets_host().tobytes() == c.buckets_host().tobytes()
+        cam2 = a.scene.camera.copy(); cam2[0] += 0.05                    # camera moves while samples traced ahead are pending: they are dropped
+        both(lambda r: (r.SetCamera(cam2), r.ResetAccumulator()))
+        for i in range(5):
+            both(lambda r: r.Accumulate(1))
+        assert a.buckets_host().tobytes() == b.buckets_host().tobytes()
+        both(lambda r: r.Accumulate(6)); both(lambda r: r.Accumulate(1)); both(lambda r: r.Accumulate(1))   # mixed: pending samples are consumed in order
+        assert a.buckets_host().tobytes() == b.buckets_host().tobytes()
+        for r in (a, b): r.accumulations = 100                          # jump of the sample index (resume): pending samples no longer match
+        for i in range(3):
+            both(lambda r: r.Accumulate(1))
+        assert a.buckets_host().tobytes() == b.buckets_host().tobytes() and a.accumulations == 103
+        assert a.Render() == b.Render()
+        assert a.framebuffer.tobytes() == b.framebuffer.tobytes()
+        a.close(); b.close(); c.close()

@@ -246,3 +246,28 @@ def test_hdr_writer_bytes_follow_stb_image_write(tmp_path):
                         n = min(127, r_ - x); want += bytes([128 + n, comp[x]]); x += n
     assert data[len(head):] == bytes(want)
     assert np.array_equal(b2r.read_hdr(tmp_path / "s.hdr")[::-1][2, :, :3], np.zeros((w, 3), np.float32))
+
+
+def test_node_array_validation_rejects_malformed_trees(hostcheck):
+    """b2r_upload_scene flattens a CALLER's node array (B2R_FLAG_REFERENCE_TREE): validate_reference_bvh must refuse anything the
+    breadth-first flattening would loop on or render wrongly — cycles, shared children, a sphere in two leaves, a missing sphere."""
+    def ok(nodes, n):
+        a = np.ascontiguousarray(nodes)
+        return hostcheck.hc_validate(C.c_void_p(a.ctypes.data), len(a), n) == 1
+    for n in (1, 2, 9, 300):
+        sc = scenes.default_scene() if n == 9 else scenes.random_scene(n, light_every=10)
+        nodes, prims, _ = b2r.build_bvh(sc["geometry"])
+        assert ok(nodes, n)                                             # the reference builder's own output
+        if n < 3: continue
+        inner = np.flatnonzero(nodes["prim_count"] == 0); leaves = np.flatnonzero(nodes["prim_count"] != 0)
+        bad = nodes.copy(); bad["first_id"][inner[-1]] = 0              # child pair before its parent: a cycle through the root
+        assert not ok(bad, n)
+        bad = nodes.copy(); bad["first_id"][inner[1]] = nodes["first_id"][inner[0]]   # two parents share one child pair
+        assert not ok(bad, n)
+        bad = nodes.copy(); bad["first_id"][leaves[0]] = nodes["first_id"][leaves[1]]  # one sphere in two leaves (another one in none)
+        assert not ok(bad, n)
+        bad = nodes.copy(); bad["prim_count"][leaves[0]] = 2            # multi-sphere leaf
+        assert not ok(bad, n)
+        bad = nodes.copy(); bad["first_id"][inner[0]] = len(nodes) - 1  # second child out of range
+        assert not ok(bad, n)
+        assert not ok(nodes[:-1], n) and not ok(nodes, n + 1)

@@ -114,3 +114,16 @@ def test_reference_scalar_and_vec8_tonemap_agree():
         a = np.ascontiguousarray(rgb).copy(); lib.ref_tonemap_scalar(a.ctypes.data)
         r, g, b = (np.full(8, rgb[i], np.float32) for i in range(3)); lib.ref_tonemap_vec8(r.ctypes.data, g.ctypes.data, b.ctypes.data)
         assert a.tobytes() == np.array([r[3], g[3], b[3]], np.float32).tobytes()
+
+
+def test_mirror_camera_generate_ray_matches_the_references(hostcheck):
+    """Camera::generate_ray of the C++ mirror (host/Camera.hpp -> b2r_camera_ray -> the kernels' camera_dir) against the reference's own
+    Camera.hpp:80-88 — the committed fixture everywhere, the compiled reference live where it exists. The app calls it for focus picking
+    (Application.cpp:288), so the mirror has to offer it with the same signature."""
+    class _Lib:  # eval_camera_ref only needs an object with a ref_generate_ray attribute
+        ref_generate_ray = hostcheck.hc_mirror_generate_ray
+    want = json.load(open(os.path.join(G, "sampling_kat.json")))["camera"]
+    assert gen_golden.eval_camera_ref(_Lib, gen_golden.camera_inputs()) == want
+    if os.path.exists(os.path.join(os.path.dirname(oracle_py.__file__), "_ref", "librefsampling.so")):
+        cams = gen_golden.camera_inputs(seed=99, n=40)
+        assert gen_golden.eval_camera_ref(_Lib, cams) == gen_golden.eval_camera_ref(gen_golden.ref_sampling_lib(), cams)
