@@ -33,7 +33,7 @@ COUNTER_NAMES = ["extension_rays", "shadow_rays", "shaded_hits", "terminated", "
 ABI_SYMBOLS = [
     "b2r_bvh_build", "b2r_bvh_build_ex", "b2r_find_lights", "b2r_camera_lookat", "b2r_camera_ray", "b2r_create", "b2r_destroy", "b2r_resize", "b2r_reset", "b2r_set_stream",
     "b2r_sync", "b2r_upload_scene", "b2r_refit_scene", "b2r_set_camera", "b2r_accumulate", "b2r_resolve", "b2r_resolve_async", "b2r_frame_wait", "b2r_resolve_from", "b2r_ipc_export_buckets", "b2r_ipc_open_peers", "b2r_ipc_close", "b2r_resolve_peers", "b2r_team_export", "b2r_team_open", "b2r_team_resolve", "b2r_team_error", "b2r_team_close", "b2r_get_accumulations", "b2r_set_accumulations",
-    "b2r_read_buckets", "b2r_write_buckets", "b2r_device_buckets", "b2r_device_framebuffer", "b2r_read_counters", "b2r_reset_counters",
+    "b2r_read_buckets", "b2r_write_buckets", "b2r_save_checkpoint", "b2r_load_checkpoint", "b2r_device_buckets", "b2r_device_framebuffer", "b2r_read_counters", "b2r_reset_counters",
     "b2r_read_kernel_times", "b2r_set_flags", "b2r_generate_rays", "b2r_trace_closest", "b2r_trace_shadow", "b2r_read_wide_nodes", "b2r_get_origin_box",
     "b2r_write_hdr", "b2r_read_hdr", "b2r_last_error", "b2r_abi_version",
 ]
@@ -71,7 +71,7 @@ def lib():
             "b2r_get_accumulations": [vp, vp], "b2r_set_accumulations": [vp, u32], "b2r_read_buckets": [vp, vp], "b2r_write_buckets": [vp, vp],
             "b2r_device_buckets": [vp, vp, vp], "b2r_device_framebuffer": [vp, vp, vp], "b2r_read_counters": [vp, vp], "b2r_reset_counters": [vp],
             "b2r_read_kernel_times": [vp, vp, vp, C.c_int], "b2r_set_flags": [vp, u32], "b2r_generate_rays": [vp, u32, vp],
-            "b2r_write_hdr": [C.c_char_p, vp, u32, u32], "b2r_read_hdr": [C.c_char_p, vp, vp, vp], "b2r_trace_closest": [vp, vp, u32, vp, vp], "b2r_trace_shadow": [vp, vp, vp, u32, vp], "b2r_read_wide_nodes": [vp, vp, vp, vp], "b2r_get_origin_box": [vp, vp],
+            "b2r_save_checkpoint": [vp, C.c_char_p], "b2r_load_checkpoint": [vp, C.c_char_p], "b2r_write_hdr": [C.c_char_p, vp, u32, u32], "b2r_read_hdr": [C.c_char_p, vp, vp, vp], "b2r_trace_closest": [vp, vp, u32, vp, vp], "b2r_trace_shadow": [vp, vp, vp, u32, vp], "b2r_read_wide_nodes": [vp, vp, vp, vp], "b2r_get_origin_box": [vp, vp],
         }
         for name, args in sig.items():
             fn = getattr(L, name); fn.argtypes = args; fn.restype = C.c_int
@@ -293,6 +293,14 @@ class Renderer:
 
     def write_buckets(self, arr):
         a = np.ascontiguousarray(arr, np.float32); _check(lib().b2r_write_buckets(self._h, _ptr(a)))
+
+    def SaveCheckpoint(self, path):
+        """Bucket sums + sample counter as one file (b2r_save_checkpoint); LoadCheckpoint on a renderer of the same configuration resumes the
+        same image bit for bit."""
+        _check(lib().b2r_save_checkpoint(self._h, str(path).encode()))
+
+    def LoadCheckpoint(self, path):
+        _check(lib().b2r_load_checkpoint(self._h, str(path).encode()))
 
     def device_buckets(self):
         p = C.c_void_p(None); n = C.c_size_t(0); _check(lib().b2r_device_buckets(self._h, C.byref(p), C.byref(n))); return p.value, n.value

@@ -61,6 +61,7 @@ struct b2r_ctx {
 	WideBvh wide_host; uint64_t wide_key = 0; std::vector<unsigned char> wide_blob; bool have_wide = false;
 	std::vector<uint32_t> cur_geom_of_prim;  // after a refit into a new BVH order: that order's index -> geometry index (empty: wide_host's)
 	uint32_t* d_remap = nullptr; size_t cap_remap = 0;
+	uint8_t* d_trace = nullptr; size_t cap_trace = 0;  // b2r_trace_* staging (rays in, results out)
 	bool wide_refit = false; double* d_cost = nullptr;  // b2r_refit_scene: the device tree no longer equals wide_host
 	// where ray origins may lie (leaf_half_extent, b2r_shade.h): bounds of the current spheres + camera + caller-supplied ray origins
 	OriginBox obox{}; bool obox_valid = false; float sph_lo[3] = {0, 0, 0}, sph_hi[3] = {0, 0, 0}; float cam_pos[3] = {0, 0, 0};
@@ -344,7 +345,7 @@ void b2r_destroy(b2r_ctx* c) {
 	drop_graph(c);
 	for (auto& t : c->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
 	dev_free(&c->d_prims); dev_free(&c->d_mat_albedo); dev_free(&c->d_mat_emission); dev_free(&c->d_light_sphere); dev_free(&c->d_light_emit);
-	dev_free(&c->d_hdri); dev_free(&c->d_prim_mat); dev_free(&c->d_wide); dev_free(&c->d_cost); dev_free(&c->d_remap);
+	dev_free(&c->d_hdri); dev_free(&c->d_prim_mat); dev_free(&c->d_wide); dev_free(&c->d_cost); dev_free(&c->d_remap); dev_free(&c->d_trace);
 	for (int s = 0; s < 2; s++) { dev_free(&c->d_A[s]); dev_free(&c->d_B[s]); dev_free(&c->d_T[s]); }
 	dev_free(&c->d_H); dev_free(&c->d_SA); dev_free(&c->d_SB); dev_free(&c->d_SL); dev_free(&c->d_rad); dev_free(&c->d_acc); dev_free(&c->d_fb);
 	for (int s = 0; s < 2; s++) { dev_free(&c->d_ex_slot[s]); dev_free(&c->d_ex_act[s]); }
@@ -860,6 +861,49 @@ int b2r_write_buckets(b2r_ctx* c, const float* in_host) {
 	CU(cudaStreamSynchronize(c->stream));
 	return B2R_OK;
 }
+
+// ---- bucket checkpoint file (SURVEY §5 "checkpoint / resume"; the reference's only dump is the tonemapped frame, Image.cpp:71-74) --------
+// Layout: 64-byte header {magic "B2RBUCK1", width, height, buckets, max_bounces, accumulations, flags that change the result, payload FNV-1a 64}
+// then the [buckets][3][width*height] float32 bucket sums in tile order — exactly b2r_read_buckets' array. A progressive render resumes
+// bit-identically because the RNG streams are a pure function of (sample index, pixel, bounce) (Q2-Q3).
+namespace {
+struct CheckpointHeader { char magic[8]; uint32_t width, height, buckets, max_bounces, accumulations, result_flags; uint64_t payload_hash; uint64_t payload_bytes; uint32_t reserved[4]; };
+static_assert(sizeof(CheckpointHeader) == 64, "checkpoint header");
+constexpr uint32_t kResultFlags = B2R_FLAG_NO_MIS | B2R_FLAG_REFERENCE_EXACT;  // flags that change which image is being accumulated
+uint64_t fnv1a64(const void* data, size_t bytes) { const unsigned char* b = static_cast<const unsigned char*>(data); uint64_t h = 1469598103934665603ull; for (size_t i = 0; i < bytes; i++) h = (h ^ b[i]) * 1099511628211ull; return h; }
+}  // namespace
+int b2r_save_checkpoint(b2r_ctx* c, const char* path) {
+	if (!c || !path) return fail(B2R_ERR_ARG, "null argument");
+	const size_t n = static_cast<size_t>(c->cfg.buckets) * 3 * c->params.frame.npix;
+	std::vector<float> host(n);
+	int rc = b2r_read_buckets(c, host.data()); if (rc) return rc;
+	CheckpointHeader h{}; std::memcpy(h.magic, "B2RBUCK1", 8);
+	h.width = c->cfg.width; h.height = c->cfg.height; h.buckets = c->cfg.buckets; h.max_bounces = c->cfg.max_bounces; h.accumulations = c->accumulations;
+	h.result_flags = c->cfg.flags & kResultFlags; h.payload_bytes = n * sizeof(float); h.payload_hash = fnv1a64(host.data(), n * sizeof(float));
+	FILE* f = std::fopen(path, "wb");
+	if (!f) return fail(B2R_ERR_ARG, std::string("cannot open ") + path + " for writing");
+	const bool ok = std::fwrite(&h, sizeof h, 1, f) == 1 && std::fwrite(host.data(), sizeof(float), n, f) == n;
+	if (std::fclose(f) != 0 || !ok) return fail(B2R_ERR_ARG, std::string("short write to ") + path);
+	return B2R_OK;
+}
+int b2r_load_checkpoint(b2r_ctx* c, const char* path) {
+	if (!c || !path) return fail(B2R_ERR_ARG, "null argument");
+	FILE* f = std::fopen(path, "rb");
+	if (!f) return fail(B2R_ERR_ARG, std::string("cannot open ") + path);
+	CheckpointHeader h{};
+	const size_t n = static_cast<size_t>(c->cfg.buckets) * 3 * c->params.frame.npix;
+	std::vector<float> host(n);
+	bool ok = std::fread(&h, sizeof h, 1, f) == 1 && std::memcmp(h.magic, "B2RBUCK1", 8) == 0;
+	const bool same = ok && h.width == c->cfg.width && h.height == c->cfg.height && h.buckets == c->cfg.buckets && h.max_bounces == c->cfg.max_bounces &&
+	                  h.result_flags == (c->cfg.flags & kResultFlags) && h.payload_bytes == n * sizeof(float);
+	if (same) ok = std::fread(host.data(), sizeof(float), n, f) == n && std::fgetc(f) == EOF && fnv1a64(host.data(), n * sizeof(float)) == h.payload_hash;
+	std::fclose(f);
+	if (!ok) return fail(B2R_ERR_ARG, std::string(path) + ": not a bucket checkpoint, truncated, or its payload hash does not match");
+	if (!same) return fail(B2R_ERR_STATE, std::string(path) + ": written for another frame size, bucket count, bounce limit (the pixel seeds depend on width and max_bounces, Q2) or MIS / reference-exact mode");
+	int rc = b2r_write_buckets(c, host.data()); if (rc) return rc;
+	return b2r_set_accumulations(c, h.accumulations);
+}
+
 int b2r_device_buckets(b2r_ctx* c, void** dev_ptr, size_t* bytes) {
 	if (!c || !dev_ptr || !bytes) return fail(B2R_ERR_ARG, "null argument");
 	*dev_ptr = c->d_acc; *bytes = static_cast<size_t>(c->cfg.buckets) * 3 * c->params.frame.npix * sizeof(float);
@@ -921,9 +965,11 @@ static int trace_common(b2r_ctx* c, const float* rays, const float* tfar_in, uin
 		for (uint32_t i = 0; i < n; i++) for (int k = 0; k < 3; k++) { const float v = rays[6 * static_cast<size_t>(i) + k]; if (v == v && fabsf(v) <= FLT_MAX) { pts[k] = fminf(pts[k], v); pts[3 + k] = fmaxf(pts[3 + k], v); } }
 		if (pts[0] <= pts[3] && (rc = ensure_origin_box(c, pts, 2))) return rc;
 	}
-	float *d_rays = nullptr, *d_tin = nullptr, *d_tout = nullptr; int32_t* d_prim = nullptr; uint8_t* d_occ = nullptr;
-	if ((rc = dev_alloc(&d_rays, static_cast<size_t>(n) * 6)) || (rc = dev_alloc(&d_tin, static_cast<size_t>(n))) || (rc = dev_alloc(&d_tout, static_cast<size_t>(n))) ||
-	    (rc = dev_alloc(&d_prim, static_cast<size_t>(n))) || (rc = dev_alloc(&d_occ, static_cast<size_t>(n)))) { cudaFree(d_rays); cudaFree(d_tin); cudaFree(d_tout); cudaFree(d_prim); cudaFree(d_occ); return rc; }
+	// one grow-only device block per context, carved into the five arrays (focus picking calls this per mouse click, Application.cpp:282-298)
+	const size_t n6 = (static_cast<size_t>(n) * 6 * sizeof(float) + 255) & ~static_cast<size_t>(255), n4 = (static_cast<size_t>(n) * 4 + 255) & ~static_cast<size_t>(255), n1 = (static_cast<size_t>(n) + 255) & ~static_cast<size_t>(255);
+	if ((rc = dev_reserve(&c->d_trace, &c->cap_trace, n6 + 3 * n4 + n1))) return rc;
+	float* d_rays = reinterpret_cast<float*>(c->d_trace); float* d_tin = reinterpret_cast<float*>(c->d_trace + n6); float* d_tout = reinterpret_cast<float*>(c->d_trace + n6 + n4);
+	int32_t* d_prim = reinterpret_cast<int32_t*>(c->d_trace + n6 + 2 * n4); uint8_t* d_occ = c->d_trace + n6 + 3 * n4;
 	cudaError_t e = cudaMemcpyAsync(d_rays, rays, static_cast<size_t>(n) * 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream);
 	if (e == cudaSuccess && shadow) e = cudaMemcpyAsync(d_tin, tfar_in, static_cast<size_t>(n) * sizeof(float), cudaMemcpyHostToDevice, c->stream);
 	if (e == cudaSuccess) {
@@ -933,7 +979,6 @@ static int trace_common(b2r_ctx* c, const float* rays, const float* tfar_in, uin
 	if (e == cudaSuccess && !shadow) { e = cudaMemcpyAsync(tfar_out, d_tout, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost, c->stream); if (e == cudaSuccess) e = cudaMemcpyAsync(prim_out, d_prim, static_cast<size_t>(n) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream); }
 	if (e == cudaSuccess && shadow) e = cudaMemcpyAsync(occ_out, d_occ, static_cast<size_t>(n), cudaMemcpyDeviceToHost, c->stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-	cudaFree(d_rays); cudaFree(d_tin); cudaFree(d_tout); cudaFree(d_prim); cudaFree(d_occ);
 	if (e != cudaSuccess) return fail(B2R_ERR_CUDA, cudaGetErrorString(e));
 	return B2R_OK;
 }

@@ -395,6 +395,15 @@ __global__ void __launch_bounds__(kBlock) k_generate(const Params p) {
 constexpr uint32_t kTravChunk = 128, kRefillBelow = B2R_REFILL_BELOW;
 struct WarpPool {
 	uint32_t next = 0, end = 0; bool dry = false;  // warp-uniform
+	// Guided chunks: a warp claims 128 rays while plenty are left and fewer (down to 32 = one ray per lane) as the queue runs out, about
+	// half of an even share of what is left. The end of every launch — and the whole of a thin late-bounce launch — is then spread over
+	// all resident warps instead of a few warps walking 128 rays each, four rounds in a row, while the rest of the GPU idles.
+	__device__ __forceinline__ uint32_t chunk_for(const uint32_t* cursor, uint32_t n_in) const {
+		const uint32_t at = *reinterpret_cast<const volatile uint32_t*>(cursor);
+		const uint32_t left = n_in > at ? n_in - at : 0u, warps = gridDim.x * (blockDim.x >> 5);
+		const uint32_t share = left / (2u * warps);
+		return share >= kTravChunk ? kTravChunk : share <= 32u ? 32u : (share & ~31u);
+	}
 	// hands ray indices to the lanes flagged `idle`; returns the lane's index or 0xffffffff
 	__device__ __forceinline__ uint32_t take(bool idle, uint32_t* cursor, uint32_t n_in) {
 		const uint32_t mask = __ballot_sync(0xffffffffu, idle);
@@ -402,11 +411,11 @@ struct WarpPool {
 		uint32_t want = __popc(mask), given = 0;
 		while (want > given && !dry) {
 			if (next >= end) {
-				uint32_t b = 0;
-				if (lane_id() == 0) b = atomicAdd(cursor, kTravChunk);
-				b = __shfl_sync(0xffffffffu, b, 0);
+				uint32_t b = 0, chunk = 0;
+				if (lane_id() == 0) { chunk = chunk_for(cursor, n_in); b = atomicAdd(cursor, chunk); }
+				b = __shfl_sync(0xffffffffu, b, 0); chunk = __shfl_sync(0xffffffffu, chunk, 0);
 				if (b >= n_in) { dry = true; break; }
-				next = b; end = min(b + kTravChunk, n_in);
+				next = b; end = min(b + chunk, n_in);
 			}
 			const uint32_t n = min(want - given, end - next);
 			const uint32_t rank = __popc(mask & ((1u << lane_id()) - 1u));

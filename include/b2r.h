@@ -172,6 +172,13 @@ int  b2r_get_accumulations(b2r_ctx* ctx, uint32_t* out);
 int  b2r_set_accumulations(b2r_ctx* ctx, uint32_t acc);            /* resume / jump to a sample index (RNG is stateless, Q2-Q3) */
 int  b2r_read_buckets(b2r_ctx* ctx, float* out_host);               /* [buckets][3][width*height], pixels in tile order t = tile*256+ID */
 int  b2r_write_buckets(b2r_ctx* ctx, const float* in_host);         /* checkpoint restore */
+/* Checkpoint / resume of a progressive render as ONE file: a 64-byte header (magic, frame size, bucket count, bounce limit, accumulations,
+ * the flags that change the image, payload size and hash) followed by the bucket sums exactly as b2r_read_buckets returns them. Loading
+ * checks all of it (B2R_ERR_ARG: not a checkpoint / truncated / corrupt; B2R_ERR_STATE: written for another configuration) and then
+ * restores the buckets and the sample counter, so that further b2r_accumulate calls continue the SAME image bit for bit (the RNG is a pure
+ * function of sample index, pixel and bounce, Q2-Q3). The reference has no such file: its only dump is the tonemapped frame (Image.cpp:71-74). */
+int  b2r_save_checkpoint(b2r_ctx* ctx, const char* path);
+int  b2r_load_checkpoint(b2r_ctx* ctx, const char* path);
 int  b2r_device_buckets(b2r_ctx* ctx, void** dev_ptr, size_t* bytes); /* device address of the same array (NCCL / P2P combine) */
 int  b2r_device_framebuffer(b2r_ctx* ctx, void** dev_ptr, size_t* bytes);
 /* Multi-GPU resolve over peer memory (NVLink P2P), the fused alternative to combine-then-resolve: every process exports its

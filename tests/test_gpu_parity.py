@@ -757,3 +757,31 @@ def test_samples_traced_ahead_are_invisible_to_the_caller():
         assert a.Render() == b.Render()
         assert a.framebuffer.tobytes() == b.framebuffer.tobytes()
         a.close(); b.close(); c.close()
+
+
+def test_bucket_checkpoint_file_resumes_bit_identically(tmp_path):
+    """b2r_save_checkpoint / b2r_load_checkpoint: 11 samples, save, a NEW renderer loads the file and goes on for 13 samples — bucket sums and
+    frame equal 24 straight samples bit for bit (RNG streams are a function of the sample index, Q2-Q3); the file is refused for another
+    configuration, when truncated and when a payload byte is flipped."""
+    sc = scenes.random_scene(500, light_every=25)
+    w, h, K, mb = 160, 96, 8, 6
+    a = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=K); a.Accumulate(11)
+    path = tmp_path / "run.b2rk"; a.SaveCheckpoint(path); a.close()
+    assert path.stat().st_size == 64 + K * 3 * w * h * 4
+    b = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=K); b.LoadCheckpoint(path)
+    assert b.accumulations == 11
+    b.Accumulate(13); assert b.Render()
+    c = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=K); c.Accumulate(24); assert c.Render()
+    assert b.buckets_host().tobytes() == c.buckets_host().tobytes() and b.framebuffer.tobytes() == c.framebuffer.tobytes()
+    for kw in (dict(max_bounces=mb + 1, buckets=K), dict(max_bounces=mb, buckets=K - 1), dict(max_bounces=mb, buckets=K, flags=b2r.FLAG_NO_MIS)):
+        d = b2r.Renderer(sc, w, h, **kw)
+        with pytest.raises(b2r.B2RError) as e: d.LoadCheckpoint(path)
+        assert e.value.code == b2r.ERR_STATE
+        d.close()
+    raw = bytearray(path.read_bytes())
+    (tmp_path / "short.b2rk").write_bytes(raw[:-4]); raw[1000] ^= 1; (tmp_path / "flipped.b2rk").write_bytes(raw); (tmp_path / "junk.b2rk").write_bytes(b"not a checkpoint" * 8)
+    for name in ("short.b2rk", "flipped.b2rk", "junk.b2rk", "missing.b2rk"):
+        with pytest.raises(b2r.B2RError) as e: b.LoadCheckpoint(tmp_path / name)
+        assert e.value.code == b2r.ERR_ARG
+    assert b.buckets_host().tobytes() == c.buckets_host().tobytes()   # a refused file leaves the renderer untouched
+    b.close(); c.close()
