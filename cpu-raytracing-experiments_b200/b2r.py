@@ -26,7 +26,7 @@ LIB_PATH = os.environ.get("B2R_LIB_PATH", os.path.join(_HERE, "libb2r.so"))  # o
 
 FLAG_FORCE_BRUTE, FLAG_FORCE_BVH, FLAG_NO_MIS, FLAG_COUNT_TESTS, FLAG_NO_GRAPH, FLAG_REFERENCE_TREE, FLAG_REFERENCE_EXACT, FLAG_NO_SPECULATION = 1, 2, 4, 8, 16, 32, 64, 128
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NO_LIGHTS, ERR_BVH, NOT_READY = 0, -1, -2, -3, -4, -5, 1
-KERNEL_KINDS = ["generate", "bounce_brute", "intersect_closest", "shade", "intersect_shadow", "accumulate", "resolve"]
+KERNEL_KINDS = ["generate", "bounce_brute", "intersect_closest", "shade", "intersect_shadow", "accumulate", "resolve", "finish_paths"]
 COUNTER_NAMES = ["extension_rays", "shadow_rays", "shaded_hits", "terminated", "dropped", "sphere_tests", "box_tests", "launches", "radiance_events", "reserved"]
 
 # every symbol include/b2r.h declares (tests/test_abi.py checks the header against this list and the library against both)
