@@ -16,7 +16,7 @@ thread_local std::string g_error;
 int fail(int code, const std::string& what) { g_error = what; return code; }
 #define CU(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail(B2R_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
 
-enum KernelKind { KK_GENERATE = 0, KK_BRUTE, KK_CLOSEST, KK_SHADE, KK_SHADOW, KK_ACCUMULATE, KK_RESOLVE, KK_FINISH, KK_COUNT };
+enum KernelKind { KK_GENERATE = 0, KK_BRUTE, KK_CLOSEST, KK_SHADE, KK_SHADOW, KK_ACCUMULATE, KK_RESOLVE, KK_COUNT };
 
 struct BatchArgs { uint32_t n; uint32_t acc[kMaxSlots]; unsigned long long fold = ~0ull; };
 __global__ void k_set_batch(BatchDev* dst, const BatchArgs a) {
@@ -77,7 +77,7 @@ struct b2r_ctx {
 	Params params{};
 	// launch
 	int grid_brute_first_exact = 0, grid_brute_exact = 0;
-	int grid_brute_first = 0, grid_brute = 0, grid_closest = 0, grid_shade = 0, grid_shadow = 0, grid_stream = 0, grid_finish = 0;
+	int grid_brute_first = 0, grid_brute = 0, grid_closest = 0, grid_shade = 0, grid_shadow = 0, grid_stream = 0;
 	cudaGraphExec_t graph_exec = nullptr; bool graph_valid = false;
 	uint64_t launches = 0;
 	// profiling (B2R_FLAG_NO_GRAPH): events around every launch
@@ -97,9 +97,6 @@ namespace {
 
 int ensure_device(b2r_ctx* c) { CU(cudaSetDevice(c->cfg.device)); return B2R_OK; }
 constexpr uint32_t kSpecMax = 16;
-constexpr uint32_t kFinishBelow = 0u;  // k_finish_paths is OFF by default: measured on C3 (thresholds 30k ... 12M paths) it is never faster than the per-bounce launches it
-                                     // replaces — a late bounce lasts as long as its longest ray either way, and a warp that waits for all 32 lanes per phase does
-                                     // 2.5x the warp-steps (27.2 ms per frame at every threshold <= 250k, 28.2 at 1.5M, 37.1 at 12M). B2R_FINISH_BELOW=<paths> turns it on.
 void drop_speculation(b2r_ctx* c) { c->spec_count = 0; c->spec_used = 0; c->spec_width = 1; }  // scene, camera, sample index or buckets changed under the samples traced ahead
 
 void drop_graph(b2r_ctx* c) {
@@ -144,11 +141,6 @@ int alloc_frame(b2r_ctx* c) {
 	p.frame.width = w; p.frame.height = h; p.frame.h_tiles = w / 16; p.frame.npix = npix;
 	p.frame.h_tiles_magic = magic_for(w / 16); p.frame.npix_magic = magic_for(npix);
 	p.frame.max_bounces = mb; p.frame.buckets = K; p.frame.flags = c->cfg.flags;
-	{  // k_finish_paths: default threshold, overridable for experiments; the reference-exact mode keeps one launch per bounce (its stream ranking is a per-bounce step)
-		const char* e = std::getenv("B2R_FINISH_BELOW"); const char* f = std::getenv("B2R_FINISH_FIRST");
-		p.frame.finish_below = (c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) ? 0u : e ? static_cast<uint32_t>(std::strtoul(e, nullptr, 10)) : kFinishBelow;
-		p.frame.finish_first = f ? static_cast<uint32_t>(std::strtoul(f, nullptr, 10)) : 2u;
-	}
 	for (int s = 0; s < 2; s++) { p.q.A[s] = c->d_A[s]; p.q.B[s] = c->d_B[s]; p.q.T[s] = c->d_T[s]; }
 	p.q.H = c->d_H; p.q.SA = c->d_SA; p.q.SB = c->d_SB; p.q.SL = c->d_SL; p.q.cap = static_cast<uint32_t>(cap);
 	p.cnt.paths = c->d_counts; p.cnt.shadow = c->d_counts + (mb + 1); p.cnt.work_a = c->d_counts + 2 * (mb + 1); p.cnt.work_b = c->d_counts + 3 * (mb + 1);
@@ -174,7 +166,6 @@ int compute_grids(b2r_ctx* c) {
 	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_closest<false, false, 16u>), kTravBlock, &c->grid_closest))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_shade<false>), kBruteBlock, &c->grid_shade))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_shadow<false>), kTravBlock, &c->grid_shadow))) return rc;
-	if ((rc = occ(reinterpret_cast<const void*>(&k_finish_paths<false, 16u>), kTravBlock, &c->grid_finish))) return rc;
 	c->grid_stream = c->sm_count * 8;
 	return B2R_OK;
 }
@@ -221,13 +212,6 @@ int enqueue_batch(b2r_ctx* c, bool profile) {
 		const bool exact = (c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) != 0;
 		if (exact && c->params.scene.n_mat > 64) return fail(B2R_ERR_STATE, "B2R_FLAG_REFERENCE_EXACT: at most 64 materials (RendererPolicy::max_materialID, Renderer.hpp:23)");
 		for (uint32_t b = 0; b < mb; b++) {
-			if (p.frame.finish_below && b >= p.frame.finish_first && b + 1 < mb) {  // takes the remaining paths over once few enough are left (a no-op launch otherwise)
-				if ((rc = launch(c, KK_FINISH, profile, [&] {
-					const bool tn16f = c->params.scene.stack_tn_bits == 16u;
-					if (count) { if (tn16f) k_finish_paths<true, 16u><<<c->grid_finish, kTravBlock, 0, st>>>(p, b); else k_finish_paths<true, 0u><<<c->grid_finish, kTravBlock, 0, st>>>(p, b); }
-					else { if (tn16f) k_finish_paths<false, 16u><<<c->grid_finish, kTravBlock, 0, st>>>(p, b); else k_finish_paths<false, 0u><<<c->grid_finish, kTravBlock, 0, st>>>(p, b); }
-				}))) return rc;
-			}
 			if ((rc = launch(c, KK_CLOSEST, profile, [&] {
 				// stack entries split 16/16 (up to 65536 wide nodes: C3) get immediate shifts; other sizes read the split from the scene
 				const bool tn16 = c->params.scene.stack_tn_bits == 16u;
@@ -269,8 +253,7 @@ int run_batch(b2r_ctx* c, const BatchArgs& args) {
 	CU(cudaGraphLaunch(c->graph_exec, c->stream));
 	const uint32_t mb = c->cfg.max_bounces;
 	const bool mis = !(c->cfg.flags & B2R_FLAG_NO_MIS);
-	const uint64_t finish_launches = (c->use_bvh && c->params.frame.finish_below && mb > c->params.frame.finish_first + 1u) ? mb - 1u - c->params.frame.finish_first : 0u;
-	c->launches += (c->use_bvh ? 2 + static_cast<uint64_t>(mb) * 2 + (mis ? mb - 1 : 0) + finish_launches : static_cast<uint64_t>(mb) + 1) + ((c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) ? mb - 1 : 0);
+	c->launches += (c->use_bvh ? 2 + static_cast<uint64_t>(mb) * 2 + (mis ? mb - 1 : 0) : static_cast<uint64_t>(mb) + 1) + ((c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) ? mb - 1 : 0);
 	return B2R_OK;
 }
 
@@ -941,6 +924,16 @@ int b2r_read_counters(b2r_ctx* c, uint64_t out[10]) {
 	CU(cudaStreamSynchronize(c->stream));
 	out[0] = h[ST_EXT]; out[1] = h[ST_SHADOW]; out[2] = h[ST_HITS]; out[3] = h[ST_TERM]; out[4] = h[ST_DROPPED]; out[5] = h[ST_SPHERE]; out[6] = h[ST_BOX];
 	out[7] = c->launches; out[8] = h[ST_EVENTS]; out[9] = 0;
+	return collect_timings(c);
+}
+int b2r_read_bounce_counts(b2r_ctx* c, uint32_t* paths_out, uint32_t* shadow_out, uint32_t n) {
+	if (!c || !paths_out || !shadow_out) return fail(B2R_ERR_ARG, "null argument");
+	int rc = ensure_device(c); if (rc) return rc;
+	const uint32_t mb = c->cfg.max_bounces;
+	std::vector<uint32_t> h((static_cast<size_t>(mb) + 1) * 4);
+	CU(cudaMemcpyAsync(h.data(), c->d_counts, c->counts_bytes, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	for (uint32_t b = 0; b < n; b++) { paths_out[b] = b <= mb ? h[b] : 0u; shadow_out[b] = b < mb ? h[mb + 1 + b] : 0u; }
 	return collect_timings(c);
 }
 int b2r_reset_counters(b2r_ctx* c) {

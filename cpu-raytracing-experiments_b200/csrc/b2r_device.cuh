@@ -497,20 +497,12 @@ struct SmemStack {
 // network (the compiler already emits VIMNMX), 5 % slower; refill thresholds 16/20/28 and 12/20 stack entries in shared memory —
 // flat; full-sweep SAH and a cost-optimal 2->4 collapse of the traversal tree — 12.3 instead of 12.4 node visits per ray.
 
-// Late bounces carry a few per cent of the rays but cost a launch each (closest, shade, shadow), and a launch lasts at least as long as
-// its longest ray. Once fewer than frame.finish_below paths enter a bounce (first checked at frame.finish_first), k_finish_paths traces
-// those paths to their end in ONE launch and the per-bounce kernels of the remaining bounces return at once: the path counts only fall,
-// so "paths[bounce] < finish_below" says the same thing in every kernel (an untouched count of a later bounce reads 0).
-__device__ __forceinline__ bool finished_elsewhere(const Params& p, uint32_t bounce, uint32_t n_in) {
-	return p.frame.finish_below != 0u && bounce >= p.frame.finish_first && n_in < p.frame.finish_below;
-}
 // closest-hit traversal of queue side (bounce & 1)
 // (63 registers without a minimum-blocks bound = 8 resident CTAs. Measured: bounding it to 8 costs 4 %; 71/79/96 registers with
 // 7/6/5 CTAs cost 3/5/16 %; 56/48 registers with 9/10 CTAs and a shorter shared-memory stack cost 5/8 %.)
 template <bool COUNT, bool EXACT, uint32_t TNB>
 __global__ void __launch_bounds__(kTravBlock) k_intersect_closest(const Params p, const uint32_t bounce) {
 	const uint32_t n_in = p.cnt.paths[bounce];
-	if (finished_elsewhere(p, bounce, n_in)) return;
 	const int side = bounce & 1;
 	const WideNode* __restrict__ wide = p.scene.wide;
 	uint32_t c_sphere = 0, c_box = 0;
@@ -554,7 +546,6 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_shade(con
 	__shared__ uint32_t s_cnt_a[kBruteWarps], s_cnt_b[kBruteWarps], s_cnt_c[kBruteWarps], s_base, s_sbase;
 	const SceneDev& sc = p.scene;
 	const uint32_t n_in = p.cnt.paths[bounce];
-	if (finished_elsewhere(p, bounce, n_in)) return;
 	const int side = bounce & 1;
 	const bool mis = !(p.frame.flags & B2R_FLAG_NO_MIS);
 	const bool last = bounce + 1 >= p.frame.max_bounces;
@@ -645,7 +636,6 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_shade(con
 template <bool COUNT>
 __global__ void __launch_bounds__(kTravBlock, 8) k_intersect_shadow(const Params p, const uint32_t bounce) {
 	const uint32_t n_in = p.cnt.shadow[bounce];
-	if (n_in == 0u) return;
 	const WideNode* __restrict__ wide = p.scene.wide;
 	uint32_t c_sphere = 0, c_box = 0, c_events = 0;
 	__shared__ __align__(128) float4 s_nodes[kTravBlock / 32][32 * kNodeRowF4];
@@ -712,112 +702,6 @@ __global__ void __launch_bounds__(kTravBlock, 8) k_intersect_shadow(const Params
 	if (COUNT) { stat_add(p.cnt.stats, ST_SPHERE, c_sphere); stat_add(p.cnt.stats, ST_BOX, c_box); }
 }
 
-
-// The rest of every path that enters bounce `bounce0`, in one launch (see finished_elsewhere): a warp keeps 32 paths and takes them
-// through closest-hit traversal, shading and the shadow ray's any-hit traversal bounce after bounce; lanes whose path has ended pick up
-// the next waiting path. The same routines as the per-bounce kernels (TravClosestT::visit, shade_*, the any-hit walk), the same RNG
-// streams (a function of sample, pixel and bounce) and the same order of the radiance additions of a path (light sample, then emission),
-// so every path ends with the same bits as in the per-bounce pipeline.
-template <bool COUNT, uint32_t TNB>
-__global__ void __launch_bounds__(kTravBlock) k_finish_paths(const Params p, const uint32_t bounce0) {
-	const uint32_t n_in = p.cnt.paths[bounce0];
-	if (n_in == 0u || !finished_elsewhere(p, bounce0, n_in)) return;
-	if (bounce0 > p.frame.finish_first && p.cnt.paths[bounce0 - 1u] < p.frame.finish_below) return;  // an earlier launch of this kernel took them
-	const SceneDev& sc = p.scene;
-	const WideNode* __restrict__ wide = sc.wide;
-	const int side = bounce0 & 1;
-	const bool mis = !(p.frame.flags & B2R_FLAG_NO_MIS);
-	const uint32_t mb = p.frame.max_bounces;
-	uint32_t c_sphere = 0, c_box = 0, c_ext = 0, c_shadow = 0, c_hits = 0, c_term = 0, c_drop = 0, c_events = 0;
-	__shared__ __align__(128) float4 s_nodes[kTravBlock / 32][32 * kNodeRowF4];
-	__shared__ uint32_t s_stack[kSmemStack][kTravBlock];
-	float4* rows = s_nodes[threadIdx.x >> 5];
-	const float4* row = rows + lane_id() * kNodeRowF4;
-	uint32_t backing[kTraversalStack];
-	WarpPool pool; TravClosestT<SmemStack> t; t.node = 0u; t.stack.bind(&s_stack[0][threadIdx.x], backing);
-	PathState s; uint32_t bounce = 0; bool alive = false;
-	for (;;) {
-		const uint32_t got = pool.take(!alive, p.cnt.work_a + bounce0, n_in);
-		if (got != 0xffffffffu) { s = load_path(p.q, side, got); bounce = bounce0; alive = true; }
-		if (!__any_sync(0xffffffffu, alive)) break;
-		// ---- closest hit of every live lane
-		bool active = alive;
-		if (alive) { t.begin(Ray{s.ox, s.oy, s.oz, s.dx, s.dy, s.dz}, false); c_ext++; }
-		while (__any_sync(0xffffffffu, active)) {
-			warp_stage_nodes(wide, rows, active ? t.node : 0u);
-			if (active && !t.template step_staged<COUNT, TNB>(row, sc.stack_tn_bits, &c_sphere, &c_box)) active = false;
-		}
-		// ---- shade
-		bool want_shadow = false, has_emit = false, keep = false; ShadowRay sr{}; f3 emit{0.0f, 0.0f, 0.0f}; const uint32_t pid = s.pid;
-		if (alive) {
-			if (t.prim < 0) {  // miss shader (Renderer.hpp:408-420)
-				c_term++;
-				if (sc.has_ambient) { rad_add(p.rad, p.frame.npix, pid, shade_sky(sc, s), f3{0.0f, 0.0f, 0.0f}, true, false); c_events++; }
-			} else {
-				const uint32_t acc = p.batch->acc[pid >> 26], seed = pixel_seed(pid & kPixMask, mb);
-				const Surface sf = shade_surface(sc, s, t.best, t.prim);
-				c_hits++;
-				if (bounce + 1u >= mb) { rad_zero(p.rad, p.frame.npix, pid); c_drop++; }  // Q11
-				else {
-					if (mis) want_shadow = shade_light_sample(sc, sf, s, t.prim, acc, seed, bounce, &sr);
-					if (sf.emissive) { emit = shade_emission(sc, sf, s, t.best, bounce, mis); has_emit = true; }
-					keep = shade_continue(sf, &s, acc, seed, bounce);
-					if (!keep) c_term++;
-				}
-			}
-		}
-		// ---- the shadow ray of this bounce: any-hit walk (BVH.hpp:290-305)
-		bool lit = false;
-		if (__any_sync(0xffffffffu, want_shadow)) {
-			float ix = 0, iy = 0, iz = 0, nx = 0, ny = 0, nz = 0, ax = 0, ay = 0, az = 0; uint32_t node = 0u;
-			active = want_shadow;
-			if (want_shadow) {
-				c_shadow++;
-				ix = 1.0f / sr.d.x; iy = 1.0f / sr.d.y; iz = 1.0f / sr.d.z;
-				nx = -(sr.o.x * ix); ny = -(sr.o.y * iy); nz = -(sr.o.z * iz);
-				ax = fabsf(ix); ay = fabsf(iy); az = fabsf(iz);
-				t.stack.reset();
-			}
-			while (__any_sync(0xffffffffu, active)) {
-				warp_stage_nodes(wide, rows, active ? node : 0u);
-				if (active) {
-					uint32_t next = kNoNode, leaves = 0u;
-					t.stack.room();
-#pragma unroll
-					for (int k = 0; k < 4; k++) {
-						const float4 a = row[2 * k], b = row[2 * k + 1];
-						const int32_t l = __float_as_int(b.z);
-						float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, ax, ay, az, sr.tfar, &tn, &h);
-						if (COUNT && l != kEmptyLink) c_box++;
-						if (h && l >= 0) { if (next != kNoNode) t.stack.push(next); next = static_cast<uint32_t>(l); }
-						leaves |= (h && l < 0) ? (1u << k) : 0u;
-					}
-					bool occluded = false;
-					while (leaves) {
-						const uint32_t k = static_cast<uint32_t>(__ffs(static_cast<int>(leaves)) - 1);
-						leaves &= leaves - 1u;
-						const float4 s4 = row[2u * k];
-						if (COUNT) c_sphere++;
-						if (sphere_hit_any(s4.x, s4.y, s4.z, s4.w, sr.o.x, sr.o.y, sr.o.z, sr.d.x, sr.d.y, sr.d.z, sr.tfar)) { occluded = true; break; }
-					}
-					if (occluded) active = false;
-					else {
-						if (next == kNoNode && (!t.stack.empty() || t.stack.refill())) next = t.stack.pop();
-						node = next;
-						if (next == kNoNode) { active = false; lit = true; }
-					}
-				}
-			}
-		}
-		// light sample first, then emission (Renderer.hpp:304-353); one radiance event per emissive hit, as the per-bounce kernels count them
-		if (has_emit) { rad_add(p.rad, p.frame.npix, pid, sr.L, emit, lit, true); c_events++; }
-		else if (lit) { rad_add(p.rad, p.frame.npix, pid, sr.L, f3{0.0f, 0.0f, 0.0f}, true, false); c_events++; }
-		alive = keep; bounce++;
-	}
-	stat_add(p.cnt.stats, ST_EXT, c_ext); stat_add(p.cnt.stats, ST_SHADOW, c_shadow); stat_add(p.cnt.stats, ST_HITS, c_hits); stat_add(p.cnt.stats, ST_TERM, c_term);
-	stat_add(p.cnt.stats, ST_DROPPED, c_drop); stat_add(p.cnt.stats, ST_EVENTS, c_events);
-	if (COUNT) { stat_add(p.cnt.stats, ST_SPHERE, c_sphere); stat_add(p.cnt.stats, ST_BOX, c_box); }
-}
 
 // ---------------------------------------------------------------------------------------------- accumulate + resolve
 // Fold the batch's per-sample radiance into its median-of-means bucket, in sample order (Renderer.hpp:424-430 adds one

@@ -210,8 +210,11 @@ int  b2r_team_close(b2r_ctx* ctx);
  * [8] radiance contributions written (light samples, emissive hits, sky), [9] reserved */
 int  b2r_read_counters(b2r_ctx* ctx, uint64_t out[10]);
 int  b2r_reset_counters(b2r_ctx* ctx);
+/* rays of the LAST wavefront batch per bounce: paths_out[b] = extension rays entering bounce b, shadow_out[b] = shadow rays queued at bounce b
+ * (n entries each; what the per-launch roofline rows divide by). Synchronises. */
+int  b2r_read_bounce_counts(b2r_ctx* ctx, uint32_t* paths_out, uint32_t* shadow_out, uint32_t n);
 /* per-kernel device time (ms) and launch counts accumulated while B2R_FLAG_NO_GRAPH profiling is on:
- * index 0 generate, 1 bounce_brute, 2 intersect_closest, 3 shade, 4 intersect_shadow, 5 accumulate, 6 resolve, 7 finish_paths */
+ * index 0 generate, 1 bounce_brute, 2 intersect_closest, 3 shade, 4 intersect_shadow, 5 accumulate, 6 resolve */
 int  b2r_read_kernel_times(b2r_ctx* ctx, double ms_out[8], uint64_t launches_out[8], int reset);
 int  b2r_set_flags(b2r_ctx* ctx, uint32_t flags);
 
