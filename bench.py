@@ -429,21 +429,28 @@ def roofline(b, kt, pc, steps, hbm_peak, peak_src, sm_max):
                        "note": "accounting flops: 25 per slab test, 20 per sphere test (device counters, B2R_FLAG_COUNT_TESTS pass), 250 per shaded hit"}
     if box:
         out["tests_per_ray"] = {"box": box / max(ext + shadow, 1), "sphere": sph / max(ext + shadow, 1)}
-    # ncu-derived figures of the same workload (static, from the committed capture): DRAM traffic over ALL launches of the kernel in
-    # one frame, issue-slot and L1 data-pipe utilisation, active lanes per instruction
+    # ncu-derived figures of the same workload (static, from the committed capture profiles/r02_*): DRAM traffic per launch averaged over
+    # ALL launches of the kernel in one step (the same population the algorithmic bytes per launch are averaged over), duration-weighted
+    # issue-slot and L1 data-pipe utilisation, active lanes per instruction
     for fn in ("r02_traffic.json", "r01_traffic.json"):
-        p = os.path.join(ROOT, "profiles", fn)
-        if os.path.exists(p):
-            try:
-                tr = json.load(open(p)).get(b.name, {}).get(dom)
-                if tr:
-                    out["traffic"] = tr["dram_bytes_per_launch"]; out["traffic_source"] = tr.get("source")
-                    for k_src, k_dst in (("issue_slots_busy_pct", "issue"), ("l1_data_pipe_pct", "l1"), ("active_lanes_per_instruction", "active_lanes")):
-                        if tr.get(k_src) is not None:
-                            out[k_dst] = {"value": tr[k_src], "source": tr.get("source")}
-                    break
-            except Exception:
-                pass
+        pth = os.path.join(ROOT, "profiles", fn)
+        if not os.path.exists(pth):
+            continue
+        try:
+            allk = json.load(open(pth)).get(b.name, {})
+        except Exception:
+            continue
+        for kname, tr in allk.items():
+            if kname in rows:
+                rows[kname]["ncu"] = {k: tr[k] for k in ("dram_bytes_per_launch", "issue_slots_busy_pct", "l1_data_pipe_pct", "active_lanes_per_instruction", "achieved_occupancy_pct", "launches") if k in tr}
+                rows[kname]["traffic_over_algorithmic"] = tr["dram_bytes_per_launch"] / rows[kname]["algorithmic_bytes_per_launch"] if rows[kname]["algorithmic_bytes_per_launch"] else None
+        tr = allk.get(dom)
+        if tr:
+            out["traffic"] = tr["dram_bytes_per_launch"]; out["traffic_source"] = tr.get("source")
+            for k_src, k_dst in (("issue_slots_busy_pct", "issue"), ("l1_data_pipe_pct", "l1"), ("active_lanes_per_instruction", "active_lanes")):
+                if tr.get(k_src) is not None:
+                    out[k_dst] = {"value": tr[k_src], "source": "ncu, same capture as traffic"}
+            break
     return out
 
 
