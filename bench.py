@@ -441,7 +441,7 @@ def roofline(b, kt, pc, steps, hbm_peak, peak_src, sm_max):
         except Exception:
             continue
         for kname, tr in allk.items():
-            if kname in rows:
+            if kname in rows and world == 1:
                 rows[kname]["ncu"] = {k: tr[k] for k in ("dram_bytes_per_launch", "issue_slots_busy_pct", "l1_data_pipe_pct", "active_lanes_per_instruction", "achieved_occupancy_pct", "launches") if k in tr}
                 rows[kname]["traffic_over_algorithmic"] = tr["dram_bytes_per_launch"] / rows[kname]["algorithmic_bytes_per_launch"] if rows[kname]["algorithmic_bytes_per_launch"] else None
         tr = allk.get(dom)
@@ -620,6 +620,13 @@ def run_workload(args, name, rank, world, local, stream, dev, secondary=False):
                      "rebuild_ms": {"reference_bvh_host": (t1 - t0) * 1e3, "upload_scene": (t2 - t1) * 1e3},
                      "ms_per_step_after_refit": ms_refit, "ms_per_step_after_rebuild": ms_rebuilt,
                      "note": "refit = match prims to geometry + pack + H2D of the spheres and lights + k_refit_level per tree level, host wall clock incl. stream sync; leaf order kept (refit_ms) or the reference BVH rebuilt on the host first, as Application.cpp:508 does"}
+        # an edit that adds or removes spheres cannot keep the topology: the tree built ON THE GPU (B2R_FLAG_GPU_TREE) beside the host's SAH build
+        r.set_flags(b2r.FLAG_GPU_TREE | b.base_flags); r.SetCamera(b.ps.camera); r.SetScene(ps2); r.sync()   # first use: allocations, CUB scratch
+        t3 = time.perf_counter(); r.SetScene(ps2); r.sync(); t4 = time.perf_counter()
+        ms_gpu_tree = steps_ms()
+        edit_line["gpu_tree"] = {"upload_scene_ms": (t4 - t3) * 1e3, "ms_per_step": ms_gpu_tree,
+                                 "note": "b2r_upload_scene with B2R_FLAG_GPU_TREE: pack + H2D on the host side, Morton keys + radix sort + implicit 4-ary links + refit passes on the device, host wall clock incl. stream sync; the balanced Morton tree needs more node visits than the SAH tree (ms_per_step), so it is the instant tree after an edit, replaced by a default upload when the host build is done"}
+        r.set_flags(b.base_flags); r.SetCamera(b.ps.camera)
         r.SetScene(b.ps)
 
     # ---- CPU baseline beside it (rank 0, N=1 only): a fresh `bench.py --impl reference` process, so that its threads see the same

@@ -2,6 +2,8 @@
 // b2r_device.cuh; there is no CPU rendering path in this library.
 #include "b2r_device.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -60,6 +62,10 @@ struct b2r_ctx {
 	WideNode* d_wide = nullptr;
 	size_t cap_prims = 0, cap_prim_mat = 0, cap_mat_albedo = 0, cap_mat_emission = 0, cap_light_sphere = 0, cap_light_emit = 0, cap_wide = 0, cap_hdri = 0;
 	WideBvh wide_host; uint64_t wide_key = 0; std::vector<unsigned char> wide_blob; bool have_wide = false;
+	uint32_t n_wide = 0;  // wide nodes of the current tree
+	// B2R_FLAG_GPU_TREE: the tree was built on the device (no host copy of its nodes); sort scratch; the arrays a later refit needs to match
+	bool gpu_tree = false; uint32_t *d_mkey[2] = {nullptr, nullptr}, *d_midx[2] = {nullptr, nullptr}; size_t cap_mkey = 0; uint8_t* d_sort_tmp = nullptr; size_t cap_sort_tmp = 0;
+	std::vector<b2r_sphere> lazy_prims, lazy_geom; double* d_cost_base = nullptr;
 	std::vector<uint32_t> cur_geom_of_prim;  // after a refit into a new BVH order: that order's index -> geometry index (empty: wide_host's)
 	uint32_t* d_remap = nullptr; size_t cap_remap = 0;
 	uint8_t* d_trace = nullptr; size_t cap_trace = 0;  // b2r_trace_* staging (rays in, results out)
@@ -297,7 +303,7 @@ int ensure_origin_box(b2r_ctx* c, const float* points, uint32_t n_points) {
 	if (c->have_camera) extra.insert(extra.end(), c->cam_pos, c->cam_pos + 3);
 	if (c->obox_valid) { extra.insert(extra.end(), c->obox.lo, c->obox.lo + 3); extra.insert(extra.end(), c->obox.hi, c->obox.hi + 3); }  // never shrinks between uploads
 	c->obox = origin_box_rule(c->sph_lo, c->sph_hi, extra.data(), static_cast<uint32_t>(extra.size() / 3)); c->obox_valid = true;
-	if (c->have_wide) wide_fill_boxes(c->wide_host, c->wide_host.prims.data(), c->obox);  // the host copy (and its reference cost) follows: same routine, same result
+	if (c->have_wide && !c->gpu_tree) wide_fill_boxes(c->wide_host, c->wide_host.prims.data(), c->obox);  // the host copy (and its reference cost) follows: same routine, same result
 	if (c->have_scene && c->have_wide) return launch_refit_levels(c, nullptr);
 	return B2R_OK;
 }
@@ -346,7 +352,8 @@ void b2r_destroy(b2r_ctx* c) {
 	drop_graph(c);
 	for (auto& t : c->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
 	dev_free(&c->d_prims); dev_free(&c->d_mat_albedo); dev_free(&c->d_mat_emission); dev_free(&c->d_light_sphere); dev_free(&c->d_light_emit);
-	dev_free(&c->d_hdri); dev_free(&c->d_prim_mat); dev_free(&c->d_wide); dev_free(&c->d_cost); dev_free(&c->d_remap); dev_free(&c->d_trace);
+	dev_free(&c->d_hdri); dev_free(&c->d_prim_mat); dev_free(&c->d_wide); dev_free(&c->d_cost); dev_free(&c->d_remap); dev_free(&c->d_trace); dev_free(&c->d_cost_base); dev_free(&c->d_sort_tmp);
+	for (int k = 0; k < 2; k++) { dev_free(&c->d_mkey[k]); dev_free(&c->d_midx[k]); }
 	for (int s = 0; s < 2; s++) { dev_free(&c->d_A[s]); dev_free(&c->d_B[s]); dev_free(&c->d_T[s]); }
 	dev_free(&c->d_H); dev_free(&c->d_SA); dev_free(&c->d_SB); dev_free(&c->d_SL); dev_free(&c->d_rad); dev_free(&c->d_acc); dev_free(&c->d_fb);
 	for (int s = 0; s < 2; s++) { dev_free(&c->d_ex_slot[s]); dev_free(&c->d_ex_act[s]); }
@@ -457,36 +464,56 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 	// may still read the old scene) and before the ones enqueued next. The host side is staged in one page-locked block that is only
 	// rewritten once the previous upload's copies have completed (an event early in the previous frame, not its end).
 
-	{  // derived traversal layout, cached on everything it is derived from: the 20 meaningful bytes of every sphere (and, for the
-		// reference topology, the node array); a hit is confirmed by comparing the kept copies, not just the hash
-		auto fnv = [](uint64_t h, const void* data, size_t bytes) { const unsigned char* b = static_cast<const unsigned char*>(data); for (size_t i = 0; i < bytes; i++) h = (h ^ b[i]) * 1099511628211ull; return h; };
-		const bool ref_tree = (c->cfg.flags & B2R_FLAG_REFERENCE_TREE) != 0;
-		uint64_t key = 1469598103934665603ull ^ (ref_tree ? 0x9e3779b97f4a7c15ull : 0ull);
-		std::vector<unsigned char> blob(static_cast<size_t>(n_prims) * 20 + (ref_tree ? static_cast<size_t>(n_nodes) * sizeof(b2r_bvh_node) : 0));
-		for (uint32_t i = 0; i < n_prims; i++) std::memcpy(blob.data() + static_cast<size_t>(i) * 20, &prims[i], 20);
-		if (ref_tree) std::memcpy(blob.data() + static_cast<size_t>(n_prims) * 20, nodes, static_cast<size_t>(n_nodes) * sizeof(b2r_bvh_node));
-		key = fnv(key, blob.data(), blob.size());
-		const bool same_tree = c->have_wide && key == c->wide_key && blob == c->wide_blob;
+	const bool gpu_tree = (c->cfg.flags & B2R_FLAG_GPU_TREE) && !(c->cfg.flags & B2R_FLAG_REFERENCE_TREE);
+	if (gpu_tree) {
+		// the tree is built on the device below (after the spheres have been copied): only its shape is worked out here
 		float lo[3], hi[3]; sphere_bounds(prims, n_prims, lo, hi);
-		// the origin box is kept while it still holds the spheres and the camera; a different scene starts from a fresh one
 		const float corners[6] = {lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]};
-		if (!same_tree || !c->obox_valid || !origin_box_holds(c->obox, corners, 2) || (c->have_camera && !origin_box_holds(c->obox, c->cam_pos, 1)))
+		if (!c->obox_valid || !origin_box_holds(c->obox, corners, 2) || (c->have_camera && !origin_box_holds(c->obox, c->cam_pos, 1)))
 			{ c->obox = origin_box_rule(lo, hi, c->have_camera ? c->cam_pos : nullptr, c->have_camera ? 1u : 0u); c->obox_valid = true; }
-		for (int k = 0; k < 3; k++) { c->sph_lo[k] = lo[k]; c->sph_hi[k] = hi[k]; }
-		if (!same_tree) {
-			if (ref_tree) flatten_bvh(nodes, n_nodes, prims, n_prims, c->wide_host, &c->obox);
-			else { std::vector<b2r_bvh_node> tree; build_traversal_tree(prims, n_prims, tree); flatten_bvh(tree.data(), static_cast<uint32_t>(tree.size()), prims, n_prims, c->wide_host, &c->obox); }
-			c->wide_key = key; c->wide_blob.swap(blob); c->have_wide = true;
-			match_prims_to_geometry(prims, geometry, n_prims, c->wide_host.geom_of_prim);  // which sphere each leaf stands for (b2r_refit_scene); left empty if prims is no permutation of geometry
-		} else if (std::memcmp(&c->wide_host.ob, &c->obox, sizeof(OriginBox)) != 0) wide_fill_boxes(c->wide_host, c->wide_host.prims.data(), c->obox);  // same topology, boxes for the current origin box
+		for (int k = 0; k < 3; k++) { c->sph_lo[k] = lo[k]; c->sph_hi[k] = hi[k]; c->wide_host.sphere_lo[k] = lo[k]; c->wide_host.sphere_hi[k] = hi[k]; }
+		WideBvh& w = c->wide_host;
+		w.nodes.clear(); w.prims.clear(); w.geom_of_prim.clear(); w.cost = 0.0; w.ob = c->obox;
+		packed_levels(n_prims, w.level_first);
+		w.depth = static_cast<uint32_t>(w.level_first.size()) - 1u; w.max_stack = 3u * w.depth;
+		c->n_wide = w.level_first.back();
+		uint32_t node_bits = 1; while ((1ull << node_bits) < c->n_wide) node_bits++;
+		w.tn_bits = 32u - node_bits < 29u ? 32u - node_bits : 29u;
+		c->wide_key = 0; c->wide_blob.clear(); c->have_wide = true; c->gpu_tree = true;
+		c->lazy_prims.assign(prims, prims + n_prims); c->lazy_geom.assign(geometry, geometry + n_geom);  // matched by value only if a refit ever asks
+	} else {
+	{  // derived traversal layout, cached on everything it is derived from: the 20 meaningful bytes of every sphere (and, for the
+			// reference topology, the node array); a hit is confirmed by comparing the kept copies, not just the hash
+			auto fnv = [](uint64_t h, const void* data, size_t bytes) { const unsigned char* b = static_cast<const unsigned char*>(data); for (size_t i = 0; i < bytes; i++) h = (h ^ b[i]) * 1099511628211ull; return h; };
+			const bool ref_tree = (c->cfg.flags & B2R_FLAG_REFERENCE_TREE) != 0;
+			uint64_t key = 1469598103934665603ull ^ (ref_tree ? 0x9e3779b97f4a7c15ull : 0ull);
+			std::vector<unsigned char> blob(static_cast<size_t>(n_prims) * 20 + (ref_tree ? static_cast<size_t>(n_nodes) * sizeof(b2r_bvh_node) : 0));
+			for (uint32_t i = 0; i < n_prims; i++) std::memcpy(blob.data() + static_cast<size_t>(i) * 20, &prims[i], 20);
+			if (ref_tree) std::memcpy(blob.data() + static_cast<size_t>(n_prims) * 20, nodes, static_cast<size_t>(n_nodes) * sizeof(b2r_bvh_node));
+			key = fnv(key, blob.data(), blob.size());
+			const bool same_tree = c->have_wide && key == c->wide_key && blob == c->wide_blob;
+			float lo[3], hi[3]; sphere_bounds(prims, n_prims, lo, hi);
+			// the origin box is kept while it still holds the spheres and the camera; a different scene starts from a fresh one
+			const float corners[6] = {lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]};
+			if (!same_tree || !c->obox_valid || !origin_box_holds(c->obox, corners, 2) || (c->have_camera && !origin_box_holds(c->obox, c->cam_pos, 1)))
+				{ c->obox = origin_box_rule(lo, hi, c->have_camera ? c->cam_pos : nullptr, c->have_camera ? 1u : 0u); c->obox_valid = true; }
+			for (int k = 0; k < 3; k++) { c->sph_lo[k] = lo[k]; c->sph_hi[k] = hi[k]; }
+			if (!same_tree) {
+				if (ref_tree) flatten_bvh(nodes, n_nodes, prims, n_prims, c->wide_host, &c->obox);
+				else { std::vector<b2r_bvh_node> tree; build_traversal_tree(prims, n_prims, tree); flatten_bvh(tree.data(), static_cast<uint32_t>(tree.size()), prims, n_prims, c->wide_host, &c->obox); }
+				c->wide_key = key; c->wide_blob.swap(blob); c->have_wide = true;
+				match_prims_to_geometry(prims, geometry, n_prims, c->wide_host.geom_of_prim);  // which sphere each leaf stands for (b2r_refit_scene); left empty if prims is no permutation of geometry
+			} else if (std::memcmp(&c->wide_host.ob, &c->obox, sizeof(OriginBox)) != 0) wide_fill_boxes(c->wide_host, c->wide_host.prims.data(), c->obox);  // same topology, boxes for the current origin box
+		}
+		c->gpu_tree = false; c->n_wide = static_cast<uint32_t>(c->wide_host.nodes.size());
 	}
 	if (c->wide_host.max_stack + 3u > static_cast<uint32_t>(kTraversalStack)) { c->have_wide = false; return fail(B2R_ERR_BVH, "tree needs a deeper traversal stack than kTraversalStack (3 slots of headroom for the branch-free pushes)"); }
-	if (c->wide_host.nodes.size() >= kMaxWideNodes) { c->have_wide = false; return fail(B2R_ERR_BVH, "more than 2^22 traversal nodes (stack entries keep 22 node bits)"); }
+	if (c->n_wide >= kMaxWideNodes) { c->have_wide = false; return fail(B2R_ERR_BVH, "more than 2^22 traversal nodes (stack entries keep 22 node bits)"); }
 
 	PackedScene ps; pack_scene(prims, n_prims, materials, n_mat, light_geom_idx, n_lights, geometry, ps);
 	auto &h_prims = ps.prims, &h_alb = ps.mat_albedo, &h_em = ps.mat_emission, &h_ls = ps.light_sphere, &h_le = ps.light_emit; auto& h_pm = ps.prim_mat;
 	const bool grow = h_prims.size() > c->cap_prims || h_pm.size() > c->cap_prim_mat || h_alb.size() > c->cap_mat_albedo || h_em.size() > c->cap_mat_emission ||
-	                  h_ls.size() > c->cap_light_sphere || h_le.size() > c->cap_light_emit || c->wide_host.nodes.size() > c->cap_wide ||
+	                  h_ls.size() > c->cap_light_sphere || h_le.size() > c->cap_light_emit || c->n_wide > c->cap_wide ||
 	                  (has_ambient && static_cast<size_t>(hdri_w) * hdri_h > c->cap_hdri);
 	if (grow) CU(cudaStreamSynchronize(c->stream));  // device arrays in use are about to be replaced (first upload, or a larger scene)
 	if ((rc = dev_reserve(&c->d_prims, &c->cap_prims, h_prims.size()))) return rc;
@@ -495,17 +522,37 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 	if ((rc = dev_reserve(&c->d_mat_emission, &c->cap_mat_emission, h_em.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_light_sphere, &c->cap_light_sphere, h_ls.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_light_emit, &c->cap_light_emit, h_le.size()))) return rc;
-	if ((rc = dev_reserve(&c->d_wide, &c->cap_wide, c->wide_host.nodes.size()))) return rc;
+	if ((rc = dev_reserve(&c->d_wide, &c->cap_wide, static_cast<size_t>(c->n_wide)))) return rc;
 	const size_t texels = has_ambient ? static_cast<size_t>(hdri_w) * hdri_h : 0;
 	if (has_ambient && (rc = dev_reserve(&c->d_hdri, &c->cap_hdri, texels))) return rc;
 	const UploadPart parts[] = {
 		{c->d_prims, h_prims.data(), h_prims.size() * sizeof(float4)}, {c->d_prim_mat, h_pm.data(), h_pm.size() * sizeof(int32_t)},
 		{c->d_mat_albedo, h_alb.data(), h_alb.size() * sizeof(float4)}, {c->d_mat_emission, h_em.data(), h_em.size() * sizeof(float4)},
 		{c->d_light_sphere, h_ls.data(), h_ls.size() * sizeof(float4)}, {c->d_light_emit, h_le.data(), h_le.size() * sizeof(float4)},
-		{c->d_wide, c->wide_host.nodes.data(), c->wide_host.nodes.size() * sizeof(WideNode)}, {c->d_hdri, hdri_rgba, texels * sizeof(float4)},
+		{c->d_wide, c->wide_host.nodes.data(), gpu_tree ? 0 : c->wide_host.nodes.size() * sizeof(WideNode)}, {c->d_hdri, hdri_rgba, texels * sizeof(float4)},
 	};
 	if ((rc = stage_upload(c, parts, sizeof parts / sizeof parts[0]))) return rc;
 	c->wide_refit = false; c->cur_geom_of_prim.clear(); drop_speculation(c);
+	if (gpu_tree) {  // Morton keys -> stable radix sort -> implicit 4-ary links -> boxes, all on the stream behind the copies above
+		if (n_prims > c->cap_mkey) { for (int k = 0; k < 2; k++) { size_t cap = 0; if ((rc = dev_reserve(&c->d_mkey[k], &cap, n_prims)) || (cap = 0, rc = dev_reserve(&c->d_midx[k], &cap, n_prims))) return rc; } c->cap_mkey = n_prims; }
+		float scale[3]; morton_scale(c->sph_lo, c->sph_hi, scale);
+		k_morton_keys<<<(n_prims + kBlock - 1u) / kBlock, kBlock, 0, c->stream>>>(c->d_prims, n_prims, c->sph_lo[0], c->sph_lo[1], c->sph_lo[2], scale[0], scale[1], scale[2], c->d_mkey[0], c->d_midx[0]);
+		size_t tmp = 0;
+		CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_mkey[0], c->d_mkey[1], c->d_midx[0], c->d_midx[1], static_cast<int>(n_prims), 0, 30, c->stream));
+		if ((rc = dev_reserve(&c->d_sort_tmp, &c->cap_sort_tmp, tmp))) return rc;
+		CU(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, tmp, c->d_mkey[0], c->d_mkey[1], c->d_midx[0], c->d_midx[1], static_cast<int>(n_prims), 0, 30, c->stream));
+		PackedLevels lv{}; lv.levels = c->wide_host.depth;
+		if (lv.levels + 1u > sizeof lv.first / sizeof lv.first[0]) return fail(B2R_ERR_BVH, "packed tree deeper than 23 levels");
+		for (uint32_t l = 0; l <= lv.levels; l++) lv.first[l] = c->wide_host.level_first[l];
+		k_packed_links<<<(c->n_wide * 4u + kBlock - 1u) / kBlock, kBlock, 0, c->stream>>>(reinterpret_cast<float4*>(c->d_wide), lv, n_prims, c->d_midx[1]);
+		CU(cudaGetLastError()); c->launches += 3;
+		if ((rc = launch_refit_levels(c, nullptr))) return rc;
+		if (!c->d_cost_base) { size_t cap = 0; if ((rc = dev_reserve(&c->d_cost_base, &cap, 1))) return rc; }
+		CU(cudaMemsetAsync(c->d_cost_base, 0, sizeof(double), c->stream));
+		k_tree_cost<<<c->sm_count * 4, kBlock, 0, c->stream>>>(reinterpret_cast<const float4*>(c->d_wide), c->n_wide, c->d_cost_base);  // what a later refit's quality ratio is measured against
+		c->launches++;
+		c->wide_refit = true;  // the device holds the only copy of this tree
+	}
 	const SceneDev before = c->params.scene; const bool bvh_before = c->use_bvh;
 	SceneDev& s = c->params.scene;
 	s.prims = c->d_prims; s.prim_mat = c->d_prim_mat; s.mat_albedo = c->d_mat_albedo; s.mat_emission = c->d_mat_emission;
@@ -532,6 +579,8 @@ int b2r_refit_scene(b2r_ctx* c, const b2r_sphere* prims, uint32_t n_prims, const
 	int rc = ensure_device(c); if (rc) return rc;
 	// The caller may have re-sorted its prims (the reference's constructor does on every rebuild, BVH.hpp:201-205): leaf links become
 	// indices into the NEW order. old index -> geometry index (known from the last upload / refit) -> new index (matched by value).
+	if (c->gpu_tree && c->wide_host.geom_of_prim.empty() && c->lazy_prims.size() == n_prims)  // a device-built tree: which sphere each leaf stands for is worked out on the first refit
+		match_prims_to_geometry(c->lazy_prims.data(), c->lazy_geom.data(), n_prims, c->wide_host.geom_of_prim);
 	const std::vector<uint32_t>& old_geom = c->cur_geom_of_prim.empty() ? c->wide_host.geom_of_prim : c->cur_geom_of_prim;
 	if (old_geom.size() != n_prims) return fail(B2R_ERR_STATE, "the uploaded prims were not a permutation of geometry: no refit for this scene");
 	std::vector<uint32_t> new_geom, remap;
@@ -572,7 +621,7 @@ int b2r_refit_scene(b2r_ctx* c, const b2r_sphere* prims, uint32_t n_prims, const
 		const float corners[6] = {lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]};
 		if (!c->obox_valid || !origin_box_holds(c->obox, corners, 2)) {
 			c->obox = origin_box_rule(lo, hi, c->have_camera ? c->cam_pos : nullptr, c->have_camera ? 1u : 0u); c->obox_valid = true;
-			wide_fill_boxes(c->wide_host, c->wide_host.prims.data(), c->obox);  // the as-built tree (reference cost) for the same origin box
+			if (!c->gpu_tree) wide_fill_boxes(c->wide_host, c->wide_host.prims.data(), c->obox);  // the as-built tree (reference cost) for the same origin box
 		}
 	}
 	if ((rc = launch_refit_levels(c, same_order ? nullptr : c->d_remap))) return rc;
@@ -584,12 +633,13 @@ int b2r_refit_scene(b2r_ctx* c, const b2r_sphere* prims, uint32_t n_prims, const
 	if (std::memcmp(&before, &s, sizeof s) != 0) drop_graph(c);
 	if (quality_out) {  // optional: costs one launch and a stream synchronisation
 		CU(cudaMemsetAsync(c->d_cost, 0, sizeof(double), c->stream));
-		k_tree_cost<<<c->sm_count * 4, kBlock, 0, c->stream>>>(reinterpret_cast<const float4*>(c->d_wide), static_cast<uint32_t>(c->wide_host.nodes.size()), c->d_cost);
+		k_tree_cost<<<c->sm_count * 4, kBlock, 0, c->stream>>>(reinterpret_cast<const float4*>(c->d_wide), c->n_wide, c->d_cost);
 		c->launches++;
-		double cost = 0.0;
+		double cost = 0.0, base = c->wide_host.cost;
 		CU(cudaMemcpyAsync(&cost, c->d_cost, sizeof cost, cudaMemcpyDeviceToHost, c->stream));
+		if (c->gpu_tree && c->d_cost_base) CU(cudaMemcpyAsync(&base, c->d_cost_base, sizeof base, cudaMemcpyDeviceToHost, c->stream));
 		CU(cudaStreamSynchronize(c->stream));
-		*quality_out = c->wide_host.cost > 0.0 ? static_cast<float>(cost / c->wide_host.cost) : 1.0f;
+		*quality_out = base > 0.0 ? static_cast<float>(cost / base) : 1.0f;
 	}
 	return B2R_OK;
 }
@@ -1010,11 +1060,11 @@ int b2r_get_origin_box(b2r_ctx* c, float out[6]) {
 int b2r_read_wide_nodes(b2r_ctx* c, void* out_host, uint32_t* n_wide_nodes, uint32_t* max_stack) {
 	if (!c) return fail(B2R_ERR_ARG, "null context");
 	if (!c->have_scene) return fail(B2R_ERR_STATE, "upload_scene first");
-	if (n_wide_nodes) *n_wide_nodes = static_cast<uint32_t>(c->wide_host.nodes.size());
+	if (n_wide_nodes) *n_wide_nodes = c->n_wide;
 	if (max_stack) *max_stack = c->wide_host.max_stack;
 	if (out_host && c->wide_refit) {  // after b2r_refit_scene the device holds the current boxes
 		int rc = ensure_device(c); if (rc) return rc;
-		CU(cudaMemcpyAsync(out_host, c->d_wide, c->wide_host.nodes.size() * sizeof(WideNode), cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaMemcpyAsync(out_host, c->d_wide, static_cast<size_t>(c->n_wide) * sizeof(WideNode), cudaMemcpyDeviceToHost, c->stream));
 		CU(cudaStreamSynchronize(c->stream));
 	} else if (out_host) std::memcpy(out_host, c->wide_host.nodes.data(), c->wide_host.nodes.size() * sizeof(WideNode));
 	return B2R_OK;

@@ -815,6 +815,33 @@ __global__ void __launch_bounds__(kBlock) k_refit_level(float4* __restrict__ wid
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < count * 4u) refit_slot(wide, prims, remap, ob, first + (i >> 2), static_cast<int>(i & 3u));
 }
+// ---------------------------------------------------------------------------------------------- GPU tree build (B2R_FLAG_GPU_TREE)
+// The traversal tree built on the device for edits that add or remove spheres (the reference rebuilds its BVH on every edit,
+// Application.cpp:508-509): 30-bit Morton keys of the sphere centres, a stable radix sort (CUB), then an implicit, perfectly balanced
+// 4-ary topology over the sorted order — four spheres to a bottom node, four nodes to a parent — whose links follow from the sphere count
+// alone (k_packed_links), and the boxes from the same k_refit_level passes a scene edit uses. Results do not depend on the tree; its
+// quality does: on C3's overlapping spheres it needs ~3.5x the node visits of the host's SAH tree, so it is the instant tree
+// after an edit, not the default. Host twin: build_packed_tree (b2r_host.cpp); the tests compare the two bit for bit.
+struct PackedLevels { uint32_t first[24]; uint32_t levels; };   // level_first of packed_levels(): root level first
+__global__ void __launch_bounds__(kBlock) k_morton_keys(const float4* __restrict__ prims, const uint32_t n, const float lo0, const float lo1, const float lo2,
+                                                        const float s0, const float s1, const float s2, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float lo[3] = {lo0, lo1, lo2}, scale[3] = {s0, s1, s2};
+	const float4 p = prims[i];
+	keys[i] = morton_key(p.x, p.y, p.z, lo, scale); idx[i] = i;
+}
+__global__ void __launch_bounds__(kBlock) k_packed_links(float4* __restrict__ wide, const __grid_constant__ PackedLevels lv, const uint32_t n, const uint32_t* __restrict__ order) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, node = t >> 2, k = t & 3u;
+	if (node >= lv.first[lv.levels]) return;
+	uint32_t l = 0; while (node >= lv.first[l + 1]) l++;
+	const bool bottom = l + 1 == lv.levels;
+	const uint32_t i = node - lv.first[l], c = 4u * i + k;
+	const uint32_t child_count = bottom ? n : lv.first[l + 2] - lv.first[l + 1];
+	float4* slot = wide + static_cast<size_t>(node) * 8 + 2 * k;
+	if (c >= child_count) { slot[0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); slot[1] = make_float4(-1.0e30f, -1.0e30f, __int_as_float(kEmptyLink), -1.0e30f); }
+	else { slot[0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); slot[1] = make_float4(0.0f, 0.0f, __int_as_float(bottom ? ~static_cast<int32_t>(order[c]) : static_cast<int32_t>(lv.first[l + 1] + c)), 0.0f); }
+}
 // Sum of the inner-slot half areas (the quantity a refit is judged by: cost now / cost when the tree was built).
 __global__ void __launch_bounds__(kBlock) k_tree_cost(const float4* __restrict__ wide, const uint32_t n_nodes, double* __restrict__ out) {
 	double sum = 0.0;

@@ -382,6 +382,49 @@ void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* 
 	out.tn_bits = std::min(32u - node_bits, 29u);  // >= 2 low key bits are dropped: the kernels keep the slot index there
 }
 
+void morton_keys(const b2r_sphere* prims, uint32_t n, const float lo[3], const float hi[3], std::vector<uint32_t>& keys) {
+	float scale[3]; morton_scale(lo, hi, scale);
+	keys.resize(n);
+	for (uint32_t i = 0; i < n; i++) keys[i] = morton_key(prims[i].position[0], prims[i].position[1], prims[i].position[2], lo, scale);
+}
+void packed_levels(uint32_t n, std::vector<uint32_t>& level_first) {
+	std::vector<uint32_t> sizes;  // bottom level first
+	uint32_t m = (n + 3u) / 4u; if (m == 0u) m = 1u;
+	sizes.push_back(m);
+	while (m > 1u) { m = (m + 3u) / 4u; sizes.push_back(m); }
+	level_first.assign(1, 0u);
+	for (size_t l = sizes.size(); l-- > 0;) level_first.push_back(level_first.back() + sizes[l]);
+}
+void build_packed_tree(const b2r_sphere* prims, uint32_t n, WideBvh& out, const OriginBox* ob_in) {
+	out.nodes.clear(); out.prims.clear(); out.geom_of_prim.clear(); out.cost = 0.0;
+	sphere_bounds(prims, n, out.sphere_lo, out.sphere_hi);
+	const OriginBox ob = ob_in ? *ob_in : origin_box_rule(out.sphere_lo, out.sphere_hi, nullptr, 0);
+	std::vector<uint32_t> keys; morton_keys(prims, n, out.sphere_lo, out.sphere_hi, keys);
+	std::vector<uint32_t> order(n); std::iota(order.begin(), order.end(), 0u);
+	std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });  // == a stable radix sort by key
+	packed_levels(n, out.level_first);
+	const uint32_t levels = static_cast<uint32_t>(out.level_first.size()) - 1u;
+	out.depth = levels; out.max_stack = 3u * levels;
+	out.nodes.resize(out.level_first.back());
+	for (uint32_t l = 0; l < levels; l++) {
+		const uint32_t first = out.level_first[l], count = out.level_first[l + 1] - first;
+		const bool bottom = l + 1 == levels;
+		const uint32_t child_first = bottom ? 0u : out.level_first[l + 1], child_count = bottom ? n : out.level_first[l + 2] - out.level_first[l + 1];
+		for (uint32_t i = 0; i < count; i++) for (int k = 0; k < 4; k++) {
+			WideNode& w = out.nodes[first + i];
+			for (int j = 0; j < 8; j++) w.slot[k][j] = 0.0f;
+			const uint32_t c = 4u * i + static_cast<uint32_t>(k);
+			if (c >= child_count) { w.slot[k][4] = w.slot[k][5] = w.slot[k][7] = -1.0e30f; w.slot[k][6] = int_as_float(kEmptyLink); }
+			else w.slot[k][6] = int_as_float(bottom ? ~static_cast<int32_t>(order[c]) : static_cast<int32_t>(child_first + c));
+		}
+	}
+	out.prims.resize(n);
+	for (uint32_t i = 0; i < n; i++) out.prims[i] = make_float4(prims[i].position[0], prims[i].position[1], prims[i].position[2], prims[i].radius_sq);
+	wide_fill_boxes(out, out.prims.data(), ob);
+	uint32_t node_bits = 1; while ((1ull << node_bits) < out.nodes.size()) node_bits++;
+	out.tn_bits = std::min(32u - node_bits, 29u);
+}
+
 void pack_scene(const b2r_sphere* prims, uint32_t n_prims, const b2r_material* materials, uint32_t n_mat,
                 const int32_t* light_geom_idx, uint32_t n_lights, const b2r_sphere* geometry, PackedScene& out) {
 	auto f4 = [](float x, float y, float z, float w) { float4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; };

@@ -51,6 +51,14 @@ OriginBox origin_box_rule(const float sphere_lo[3], const float sphere_hi[3], co
 bool origin_box_holds(const OriginBox& ob, const float* points, uint32_t n_points);
 // Collapse the binary tree 2 -> 4 wide, inline the leaf spheres and compute every slot box bottom-up (the refit routine, level by level).
 void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* prims, uint32_t n_prims, WideBvh& out, const OriginBox* ob = nullptr);
+// The traversal tree the GPU can build by itself (b2r_upload_scene with B2R_FLAG_GPU_TREE; k_morton_keys / k_packed_links in
+// b2r_device.cuh): spheres sorted by the 30-bit Morton code of their centre (stable), packed four to a bottom node, nodes packed four to
+// a parent, level by level up to the root — an implicit, perfectly balanced 4-ary topology whose links follow from the sphere count
+// alone; the boxes are then filled by the refit routine. This is its host twin (tests compare the device tree with it bit for bit).
+void morton_keys(const b2r_sphere* prims, uint32_t n, const float lo[3], const float hi[3], std::vector<uint32_t>& keys);
+void build_packed_tree(const b2r_sphere* prims, uint32_t n, WideBvh& out, const OriginBox* ob = nullptr);
+// level sizes of the packed tree for n spheres, root level first (level_first has one more entry than there are levels)
+void packed_levels(uint32_t n, std::vector<uint32_t>& level_first);
 // (Re)compute every slot box of a flattened topology for the spheres `prims` and the origin box `ob` (what flatten_bvh ends with).
 void wide_fill_boxes(WideBvh& tree, const float4* packed_prims /*{c.xyz, r^2}, BVH leaf order*/, const OriginBox& ob);
 // Sum of the inner-slot half areas of a flattened tree (WideBvh::cost; k_tree_cost computes the same sum on the device after a refit).

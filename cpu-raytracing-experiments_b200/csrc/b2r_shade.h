@@ -448,6 +448,14 @@ B2R_HD void refit_slot(float4* __restrict__ wide /*8 float4 per node*/, const fl
 	float4 a, b; refit_child_box(wide + static_cast<size_t>(link) * 8, &a, &b, link);
 	slot[0] = a; slot[1] = b;
 }
+// 30-bit Morton code of a sphere centre inside the sphere bounds [lo, hi] (10 bits per axis); shared by the GPU tree build and its host twin
+B2R_HD uint32_t morton_spread10(uint32_t v) { v &= 1023u; v = (v | (v << 16)) & 0x030000ffu; v = (v | (v << 8)) & 0x0300f00fu; v = (v | (v << 4)) & 0x030c30c3u; v = (v | (v << 2)) & 0x09249249u; return v; }
+B2R_HD uint32_t morton_key(float cx, float cy, float cz, const float lo[3], const float scale[3]) {
+	const float fx = (cx - lo[0]) * scale[0], fy = (cy - lo[1]) * scale[1], fz = (cz - lo[2]) * scale[2];
+	const uint32_t qx = static_cast<uint32_t>(sel_min(sel_max(fx, 0.0f), 1023.0f)), qy = static_cast<uint32_t>(sel_min(sel_max(fy, 0.0f), 1023.0f)), qz = static_cast<uint32_t>(sel_min(sel_max(fz, 0.0f), 1023.0f));
+	return (morton_spread10(qx) << 2) | (morton_spread10(qy) << 1) | morton_spread10(qz);
+}
+B2R_HD void morton_scale(const float lo[3], const float hi[3], float scale[3]) { for (int k = 0; k < 3; k++) { const float e = hi[k] - lo[k]; scale[k] = e > 0.0f ? 1024.0f / e : 0.0f; } }
 B2R_HD float slot_half_area(const float4 /*a*/, const float4 b) { return 4.0f * (b.x * b.y + b.y * b.w + b.w * b.x); }
 
 }  // namespace b2r

@@ -58,6 +58,9 @@ enum {
 	                                     * formula (BVH.hpp:250-286: the last `active % 8` rays of each 16x16 tile's stream take the scalar tail;
 	                                     * stream order = stable counting sort by material, DataStreams.hpp:236-253). Results are then bit-identical
 	                                     * to the reference's own Renderer::Accumulate, at the price of one extra ranking kernel per bounce. */
+	B2R_FLAG_GPU_TREE = 1u << 8,       /* b2r_upload_scene builds the traversal tree ON THE GPU (Morton keys, radix sort, implicit balanced 4-ary topology, refit passes):
+	                                    * milliseconds instead of the host's SAH build, for edits that add or remove spheres; same results, ~3.5x the node visits
+	                                    * of the SAH tree on C3's overlapping spheres. May be toggled with b2r_set_flags between uploads. */
 	B2R_FLAG_NO_SPECULATION = 1u << 7, /* b2r_accumulate(ctx, 1) traces exactly one sample (default: a caller that asks for one sample per frame gets
 	                                    * batches of 2, 4, ... 16 samples traced ahead while nothing changes; results are identical either way) */
 };

@@ -139,6 +139,14 @@ int hc_refit(const b2r_sphere* prims_a, const b2r_bvh_node* nodes_a, uint32_t n_
 	}
 	return 0;
 }
+// build_packed_tree tap: the host twin of the tree b2r_upload_scene builds on the GPU with B2R_FLAG_GPU_TREE. out may be null to size.
+int hc_packed_tree(const b2r_sphere* prims, uint32_t n, const float* box6, void* out, uint32_t* n_wide, uint32_t* max_stack) {
+	const OriginBox ob = origin_box_of(prims, n, box6, nullptr, 0);
+	WideBvh w; build_packed_tree(prims, n, w, &ob);
+	*n_wide = static_cast<uint32_t>(w.nodes.size()); *max_stack = w.max_stack;
+	if (out) std::memcpy(out, w.nodes.data(), w.nodes.size() * sizeof(WideNode));
+	return 0;
+}
 // validate_reference_bvh tap (what b2r_upload_scene checks before it flattens a caller's node array)
 int hc_validate(const b2r_bvh_node* nodes, uint32_t n_nodes, uint32_t n_prims) { return validate_reference_bvh(nodes, n_nodes, n_prims) ? 1 : 0; }
 // match_prims_to_geometry tap: geom_of_prim[n]; returns 1 when prims is a permutation of geometry
@@ -194,7 +202,8 @@ extern "C" int hc_trace_stats(const b2r_bvh_node* nodes, uint32_t n_nodes, const
 	WideBvh w;
 	float ro[6]; ray_origin_bounds(rays, n, ro);
 	const OriginBox ob = origin_box_of(prims, n_prims, nullptr, ro, 2);
-	if (n_nodes == 0) { std::vector<b2r_bvh_node> tn; build_traversal_tree(prims, n_prims, tn); flatten_bvh(tn.data(), static_cast<uint32_t>(tn.size()), prims, n_prims, w, &ob); }
+	if (n_nodes == 0xffffffffu) build_packed_tree(prims, n_prims, w, &ob);   // the Morton-packed tree the GPU builds by itself
+	else if (n_nodes == 0) { std::vector<b2r_bvh_node> tn; build_traversal_tree(prims, n_prims, tn); flatten_bvh(tn.data(), static_cast<uint32_t>(tn.size()), prims, n_prims, w, &ob); }
 	else flatten_bvh(nodes, n_nodes, prims, n_prims, w, &ob);
 	for (uint32_t i = 0; i < n; i++) {
 		const float* r = rays + 6 * static_cast<size_t>(i);

@@ -791,3 +791,36 @@ def test_bucket_checkpoint_file_resumes_bit_identically(tmp_path):
         assert e.value.code == b2r.ERR_ARG
     assert b.buckets_host().tobytes() == c.buckets_host().tobytes()   # a refused file leaves the renderer untouched
     b.close(); c.close()
+
+
+@pytest.mark.parametrize("n", [5, 700, 20000])
+def test_gpu_built_tree_equals_host_twin_and_brute_force(n, hostcheck):
+    """B2R_FLAG_GPU_TREE: b2r_upload_scene builds the traversal tree on the device (Morton keys, CUB radix sort, implicit 4-ary links, refit
+    passes). (1) The device tree equals the host twin build_packed_tree bit for bit; (2) the frame equals brute force on the GPU and the
+    default SAH tree's; (3) a scene edit refits the device-built tree (leaf matching done lazily) and still equals brute force; (4) switching
+    the flag off again uploads the SAH tree."""
+    import ctypes as C
+    sc = scenes.random_scene(n, light_every=20)
+    w, h, mb = 160, 96, 8
+    r = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=2, flags=b2r.FLAG_FORCE_BVH | b2r.FLAG_GPU_TREE); r.Accumulate(4)
+    wide, ms = r.wide_nodes(); obox = r.origin_box()
+    nw = C.c_uint32(0); m2 = C.c_uint32(0); twin = np.zeros_like(wide)
+    prims = np.ascontiguousarray(r.scene.prims)
+    hostcheck.hc_packed_tree(C.c_void_p(prims.ctypes.data), n, C.c_void_p(obox.ctypes.data), C.c_void_p(twin.ctypes.data), C.byref(nw), C.byref(m2))
+    assert nw.value == len(wide) and m2.value == ms and wide.tobytes() == twin.tobytes()
+    got = r.buckets_host()
+    b = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=2, flags=b2r.FLAG_FORCE_BRUTE); b.Accumulate(4)
+    s = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=2, flags=b2r.FLAG_FORCE_BVH); s.Accumulate(4)
+    assert got.tobytes() == b.buckets_host().tobytes() == s.buckets_host().tobytes()
+    # (3) edit
+    rs = np.random.RandomState(n)
+    geo2 = _moved_geometry(sc["geometry"], rs, far=min(3, n // 2))
+    q = r.RefitScene(geo2); r.ResetAccumulator(); r.Accumulate(4)
+    sc2 = scenes.Scene(name="moved", geometry=geo2, material=sc["material"], camera=sc["camera"], ambient=sc["ambient"], hdri=None)
+    b.SetScene(sc2); b.ResetAccumulator(); b.Accumulate(4)
+    assert r.buckets_host().tobytes() == b.buckets_host().tobytes() and q > 0.0   # (the ratio can fall below 1: moved spheres may shrink the boxes)
+    # (4) flag off: the next upload builds the SAH tree on the host again
+    r.set_flags(b2r.FLAG_FORCE_BVH); r.SetScene(sc); r.ResetAccumulator(); r.Accumulate(4)
+    wide2, _ = r.wide_nodes(); s_wide, _ = s.wide_nodes()
+    assert r.buckets_host().tobytes() == got.tobytes() and wide2.shape == s_wide.shape
+    r.close(); b.close(); s.close()

@@ -216,3 +216,24 @@ def test_match_is_linear_in_the_number_of_twins(hostcheck):
     assert np.array_equal(m[twins], np.arange(0, n, 2))                    # handed out first in, first out
     prims[np.flatnonzero(perm % 2 == 1)[0]] = geo[0]                       # one twin too many, one distinct sphere missing
     assert hostcheck.hc_match(vp(prims), vp(geo), n, vp(m)) == 0
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 17, 300, 5000])
+def test_packed_morton_tree_host_twin(hostcheck, n):
+    """The tree b2r_upload_scene builds on the GPU with B2R_FLAG_GPU_TREE, through its host twin (build_packed_tree): every sphere in exactly
+    one leaf, boxes conservative and tight (check_contains), and the closest hit through it equals brute force, indices included."""
+    rs = np.random.RandomState(n)
+    sc = scenes.random_scene(max(n, 2), light_every=5)
+    _, prims, _ = b2r.build_bvh(sc["geometry"][:n])
+    nw = C.c_uint32(0); ms = C.c_uint32(0)
+    hostcheck.hc_packed_tree(vp(prims), n, None, None, C.byref(nw), C.byref(ms))
+    wide = np.zeros((nw.value, 4, 8), np.float32)
+    hostcheck.hc_packed_tree(vp(prims), n, None, vp(wide), C.byref(nw), C.byref(ms))
+    assert ms.value + 3 <= 64
+    check_contains(wide, prims)
+    rays = camera_rays(2000, rs, prims) if n > 1 else np.ascontiguousarray(np.concatenate([prims["position"][[0] * 50] + rs.uniform(3, 9, (50, 3)), -np.ones((50, 3)) / np.sqrt(3)], 1), np.float32)
+    m = len(rays); st = np.zeros(m, np.uint32); bx = np.zeros(m, np.uint32); sp = np.zeros(m, np.uint32); pr = np.zeros(m, np.int32)
+    hostcheck.hc_trace_stats(None, 0xffffffff, vp(prims), n, vp(rays), m, vp(st), vp(bx), vp(sp), vp(pr))
+    bt = np.zeros(m, np.float32); bp = np.zeros(m, np.int32)
+    hostcheck.hc_closest_brute(vp(prims), n, vp(rays), m, vp(bt), vp(bp))
+    assert np.array_equal(bp, pr)
