@@ -20,9 +20,9 @@ int fail(int code, const std::string& what) { g_error = what; return code; }
 
 enum KernelKind { KK_GENERATE = 0, KK_BRUTE, KK_CLOSEST, KK_SHADE, KK_SHADOW, KK_ACCUMULATE, KK_RESOLVE, KK_COUNT };
 
-struct BatchArgs { uint32_t n; uint32_t acc[kMaxSlots]; unsigned long long fold = ~0ull; };
+struct BatchArgs { uint32_t n; uint32_t acc[kMaxSlots]; unsigned long long fold = ~0ull; CameraParams cam; };
 __global__ void k_set_batch(BatchDev* dst, const BatchArgs a) {
-	if (threadIdx.x == 0) { dst->n_slots = a.n; dst->fold = a.fold; }
+	if (threadIdx.x == 0) { dst->n_slots = a.n; dst->fold = a.fold; dst->cam = a.cam; }
 	if (threadIdx.x < a.n) dst->acc[threadIdx.x] = a.acc[threadIdx.x];
 }
 
@@ -236,8 +236,9 @@ int enqueue_batch(b2r_ctx* c, bool profile) {
 	return launch(c, KK_ACCUMULATE, profile, [&] { k_accumulate<<<c->grid_stream, kBlock, 0, st>>>(p); });
 }
 
-int run_batch(b2r_ctx* c, const BatchArgs& args) {
+int run_batch(b2r_ctx* c, BatchArgs& args) {
 	const bool no_graph = (c->cfg.flags & B2R_FLAG_NO_GRAPH) != 0;
+	args.cam = c->params.frame.cam;  // the camera travels with the batch descriptor: a camera move leaves the captured graph alone
 	k_set_batch<<<1, kMaxSlots, 0, c->stream>>>(c->d_batch, args);
 	CU(cudaGetLastError());
 	if (no_graph) return enqueue_batch(c, true);
@@ -647,12 +648,12 @@ int b2r_refit_scene(b2r_ctx* c, const b2r_sphere* prims, uint32_t n_prims, const
 int b2r_set_camera(b2r_ctx* c, const float pos[3], const float q[4], float half_width, float half_height, float z, float exposure) {
 	if (!c || !pos || !q) return fail(B2R_ERR_ARG, "null argument");
 	int rc = ensure_device(c); if (rc) return rc;
-	// the camera travels in the kernels' parameter block (by value: launches already enqueued keep theirs), so no synchronisation;
-	// the captured graph is only rebuilt when the camera really changed
+	// the camera travels with every batch's descriptor (k_set_batch, stream-ordered: batches already enqueued keep theirs), so a camera
+	// move needs no synchronisation and leaves the captured batch graph alone
 	CameraParams cam = c->params.frame.cam;
 	cam.px = pos[0]; cam.py = pos[1]; cam.pz = pos[2]; cam.qw = q[0]; cam.qx = q[1]; cam.qy = q[2]; cam.qz = q[3];
 	cam.half_width = half_width; cam.half_height = half_height; cam.z = z; cam.exposure = exposure;
-	if (!c->have_camera || std::memcmp(&cam, &c->params.frame.cam, sizeof cam) != 0) { c->params.frame.cam = cam; drop_graph(c); }
+	if (!c->have_camera || std::memcmp(&cam, &c->params.frame.cam, sizeof cam) != 0) { c->params.frame.cam = cam; drop_speculation(c); }  // samples traced ahead saw the old camera
 	c->have_camera = true;
 	c->cam_pos[0] = pos[0]; c->cam_pos[1] = pos[1]; c->cam_pos[2] = pos[2];
 	if (c->have_scene) return ensure_origin_box(c, c->cam_pos, 1);

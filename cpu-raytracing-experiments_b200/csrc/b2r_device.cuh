@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 	if (n_tiles == 1) {
 		for (uint32_t j = threadIdx.x; j < sc.n_prims; j += blockDim.x) {
 			const float4 sp = sc.prims[j]; s_prim[j] = sp; s_prim_mat[j] = sc.prim_mat[j];
-			if (FIRST) { const SpherePre q = sphere_prepare(sp.x, sp.y, sp.z, sp.w, p.frame.cam.px, p.frame.cam.py, p.frame.cam.pz); s_pre[j] = make_float4(q.tx, q.ty, q.tz, q.disc0); }
+			if (FIRST) { const SpherePre q = sphere_prepare(sp.x, sp.y, sp.z, sp.w, p.batch->cam.px, p.batch->cam.py, p.batch->cam.pz); s_pre[j] = make_float4(q.tx, q.ty, q.tz, q.disc0); }
 		}
 		sc.prim_mat = s_prim_mat; sc.prims = s_prim;
 	}
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 			if (live) {
 				if (FIRST) {
 					const uint32_t sl0 = div_by(i, p.frame.npix, p.frame.npix_magic);
-					const PathState s0 = primary_path(p.frame, p.batch->acc[sl0], sl0, i - sl0 * p.frame.npix);
+					const PathState s0 = primary_path(p.frame, p.batch->cam, p.batch->acc[sl0], sl0, i - sl0 * p.frame.npix);
 					ox = s0.ox; oy = s0.oy; oz = s0.oz; dx = s0.dx; dy = s0.dy; dz = s0.dz;
 					pid0 = s0.pid; rad_zero(p.rad, p.frame.npix, s0.pid);  // a path's radiance starts at 0 here (coalesced stores); contributions are added after a CTA barrier
 				} else {
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 					__syncthreads();
 					for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
 						const float4 sp = p.scene.prims[first + j]; s_prim[j] = sp;
-						if (FIRST) { const SpherePre q = sphere_prepare(sp.x, sp.y, sp.z, sp.w, p.frame.cam.px, p.frame.cam.py, p.frame.cam.pz); s_pre[j] = make_float4(q.tx, q.ty, q.tz, q.disc0); }
+						if (FIRST) { const SpherePre q = sphere_prepare(sp.x, sp.y, sp.z, sp.w, p.batch->cam.px, p.batch->cam.py, p.batch->cam.pz); s_pre[j] = make_float4(q.tx, q.ty, q.tz, q.disc0); }
 					}
 					__syncthreads();
 				}
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 				c_term++;
 				if (sc.has_ambient) {
 					const uint32_t slm = FIRST ? div_by(i, p.frame.npix, p.frame.npix_magic) : 0u;
-					const PathState sm = FIRST ? primary_path(p.frame, p.batch->acc[slm], slm, i - slm * p.frame.npix) : load_path(p.q, side, i);
+					const PathState sm = FIRST ? primary_path(p.frame, p.batch->cam, p.batch->acc[slm], slm, i - slm * p.frame.npix) : load_path(p.q, side, i);
 					rad_add(p.rad, p.frame.npix, sm.pid, shade_sky(sc, sm), f3{0.0f, 0.0f, 0.0f}, true, false); c_events++;
 				}
 			}
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 				const uint32_t hi = s_hit_i[qi]; const float depth = s_hit_t[qi]; const int32_t hprim = s_hit_prim[qi];
 				if (EXACT) ex_slot = FIRST ? (hi & 255u) : static_cast<uint32_t>(p.ex.slot[side][hi]);  // bounce 0: hi is the path id, slot = pixel ID
 				if (FIRST) {
-					s.ox = p.frame.cam.px; s.oy = p.frame.cam.py; s.oz = p.frame.cam.pz;
+					s.ox = p.batch->cam.px; s.oy = p.batch->cam.py; s.oz = p.batch->cam.pz;
 					s.dx = s_hit_d[0][FIRST ? qi : 0]; s.dy = s_hit_d[FIRST ? 1 : 0][FIRST ? qi : 0]; s.dz = s_hit_d[FIRST ? 2 : 0][FIRST ? qi : 0];
 					s.tr = s.tg = s.tb = 1.0f; s.pdf = 0.0f; s.pid = hi;
 				} else s = load_path(p.q, side, hi);
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(256) k_stream_rank(const Params p, const uint3
 __global__ void __launch_bounds__(kBlock) k_generate(const Params p) {
 	const uint32_t n = p.batch->n_slots * p.frame.npix;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-		{ const uint32_t sl = div_by(i, p.frame.npix, p.frame.npix_magic); const PathState s = primary_path(p.frame, p.batch->acc[sl], sl, i - sl * p.frame.npix); store_path(p.q, 0, i, s); rad_zero(p.rad, p.frame.npix, s.pid); }
+		{ const uint32_t sl = div_by(i, p.frame.npix, p.frame.npix_magic); const PathState s = primary_path(p.frame, p.batch->cam, p.batch->acc[sl], sl, i - sl * p.frame.npix); store_path(p.q, 0, i, s); rad_zero(p.rad, p.frame.npix, s.pid); }
 	if (blockIdx.x == 0 && threadIdx.x == 0) p.cnt.paths[0] = n;
 }
 // Work distribution of the traversal kernels: every warp owns a pool of ray indices claimed kTravChunk at a time from the

@@ -65,6 +65,8 @@ B2R_HD uint32_t magic_for(uint32_t d) { return d <= 1u ? 0xffffffffu : static_ca
 struct BatchDev {  // one wavefront batch: n_slots samples traced together
 	uint32_t n_slots;
 	uint32_t acc[kMaxSlots];  // sample index (the reference's `accumulations` value, Q1) of each slot
+	CameraParams cam;         // the camera this batch is traced with: it travels with the batch descriptor (written by k_set_batch in front of every batch),
+	                          // not with the kernels' parameter block, so a camera move neither re-captures the batch graph nor waits for the stream
 	unsigned long long fold;  // slots k_accumulate folds into the buckets now (the others were traced ahead of the caller's Accumulate() calls)
 };
 struct QueueDev {
@@ -107,13 +109,13 @@ B2R_HD void pixel_xy(uint32_t t, const FrameDev& fr, int32_t* x, int32_t* y) {
 struct PathState { float ox, oy, oz, dx, dy, dz, tr, tg, tb, pdf; uint32_t pid; };
 
 // primary ray of (slot, pixel t): Renderer.hpp:97-127
-B2R_HD PathState primary_path(const FrameDev& fr, uint32_t acc, uint32_t slot, uint32_t t) {
+B2R_HD PathState primary_path(const FrameDev& fr, const CameraParams& cam, uint32_t acc, uint32_t slot, uint32_t t) {
 	Pcg rng{hash_2d(acc, pixel_seed(t, fr.max_bounces))};
 	const float s0 = rng.next_unit(), s1 = rng.next_unit();
 	int32_t x, y; pixel_xy(t, fr, &x, &y);
-	const f3 d = camera_dir(fr.cam, x, y, s0, s1);
+	const f3 d = camera_dir(cam, x, y, s0, s1);
 	PathState s;
-	s.ox = fr.cam.px; s.oy = fr.cam.py; s.oz = fr.cam.pz; s.dx = d.x; s.dy = d.y; s.dz = d.z;
+	s.ox = cam.px; s.oy = cam.py; s.oz = cam.pz; s.dx = d.x; s.dy = d.y; s.dz = d.z;
 	s.tr = s.tg = s.tb = 1.0f; s.pdf = 0.0f; s.pid = (slot << 26) | t;
 	return s;
 }

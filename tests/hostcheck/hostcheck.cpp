@@ -62,7 +62,7 @@ int hc_render_sample(const b2r_sphere* prims, const b2r_bvh_node* nodes, uint32_
 	for (int k = 0; k < 5; k++) counters[k] = 0;
 	uint32_t cs = 0, cb = 0;
 	for (uint32_t t = 0; t < fr.npix; t++) {
-		PathState s = primary_path(fr, acc, 0, t);
+		PathState s = primary_path(fr, fr.cam, acc, 0, t);
 		const uint32_t seed = pixel_seed(t, max_bounces);
 		for (uint32_t bounce = 0; bounce < max_bounces; bounce++) {
 			counters[0]++;
