@@ -1,11 +1,17 @@
-"""Multi-GPU plumbing: one process per GPU, sample buckets partitioned over the ranks, ONE collective per resolved frame.
+"""Multi-GPU plumbing: one process per GPU, sample buckets partitioned over the ranks.
 
 Partition (BASELINE north_star): scene + BVH replicated; rank g of G owns the median-of-means buckets
 {b : b % G == g} and renders exactly the sample indices acc with acc % K in that set (RNG streams are a pure function of
 (acc, pixel, bounce), Renderer.hpp:117,255,362, so no rank needs another's state). Nothing is exchanged while rendering.
-At resolve every bucket buffer has a single owner and is zero elsewhere, so the combine is one all-reduce (sum) of the
-[K][3][npix] array over NCCL/NVLink (gloo on CPU for the tests) — adding zeros is exact, the result is bit-identical to a
-single-GPU render of the same samples.
+
+The frame is put together by TEAM MODE (open_team + Renderer.RenderTeam, b2r_team_* in include/b2r.h): every rank resolves its slab of
+tiles, pulling each bucket's sums from its owner's HBM over NVLink, into rank 0's framebuffer; the ranks hand frames over through
+release/acquire flags in peer-mapped memory, so there is no host barrier and no NCCL call per frame. torch.distributed / NCCL carries
+the one-time exchange of CUDA IPC handles (and, in bench.py, the barriers around the timed region and the max-over-ranks of the time).
+Two older combines are kept and tested: open_peers + RenderPeers (rank 0 resolves everything from peer memory between two barriers the
+caller provides) and combine_buckets (out-of-place NCCL all-reduce of the owner-only [K][3][npix] bucket arrays — every bucket has one
+owner and is zero elsewhere, so adding is exact — then Render(dev_buckets=...); gloo on CPU for the tests). All three give a frame that
+is bit-identical to a single-GPU render of the same samples.
 """
 import numpy as np
 
