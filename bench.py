@@ -503,6 +503,7 @@ def run_workload(args, name, rank, world, local, stream, dev, secondary=False):
     if world == 1 and not args.no_dropin:
         frames = 8 * wl["K"]
         page_fb = np.zeros((wl["h"], wl["w"], 4), np.float32)
+        b2r.host_register(page_fb)   # as the C++ faces do with their framebuffer vector after Resize (b2r_host_register)
         def app_frames(n):
             r.ResetAccumulator()
             for _ in range(n):
@@ -510,8 +511,9 @@ def run_workload(args, name, rank, world, local, stream, dev, secondary=False):
         app_frames(wl["K"]); torch.cuda.synchronize(dev); r.reset_counters()
         t0 = time.perf_counter(); app_frames(frames); torch.cuda.synchronize(dev); dt = time.perf_counter() - t0
         cd = r.counters(); rd = cd["extension_rays"] + cd["shadow_rays"]
+        b2r.host_unregister(page_fb)
         dropin = {"value": rd / dt / 1e6, "unit": UNIT, "ms_per_app_frame": 1e3 * dt / frames, "app_frames": frames, "resolves": frames // wl["K"],
-                  "pattern": "per application frame: Accumulate() (1 sample, one wavefront batch) + Render() (resolve + synchronous D2H into pageable memory when accumulations % K == 0), host wall clock",
+                  "pattern": "per application frame: Accumulate() (1 sample, one wavefront batch) + Render() (resolve + synchronous D2H into the caller's frame buffer, page-locked once with b2r_host_register as the C++ faces do, when accumulations % K == 0), host wall clock",
                   "vs_batched_value": (rd / dt / 1e6) / value}
 
     # ---- per-kernel pass: the same steps launched kernel by kernel with an event pair around every launch (roofline), test counters on

@@ -83,7 +83,7 @@ struct b2r_ctx {
 	Params params{};
 	// launch
 	int grid_brute_first_exact = 0, grid_brute_exact = 0;
-	int grid_brute_first = 0, grid_brute = 0, grid_closest = 0, grid_shade = 0, grid_shadow = 0, grid_stream = 0;
+	int grid_brute_first = 0, grid_brute = 0, grid_closest = 0, grid_shade = 0, grid_shadow = 0, grid_stream = 0, grid_packet = 0; bool packet_primary = true;
 	cudaGraphExec_t graph_exec = nullptr; bool graph_valid = false;
 	uint64_t launches = 0;
 	// profiling (B2R_FLAG_NO_GRAPH): events around every launch
@@ -172,6 +172,8 @@ int compute_grids(b2r_ctx* c) {
 	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_closest<false, false, 16u>), kTravBlock, &c->grid_closest))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_shade<false>), kBruteBlock, &c->grid_shade))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_shadow<false>), kTravBlock, &c->grid_shadow))) return rc;
+	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_packet<false>), kTravBlock, &c->grid_packet))) return rc;
+	c->packet_primary = std::getenv("B2R_NO_PACKET") == nullptr;  // A/B switch for measurements: per-lane walks for the camera rays too
 	c->grid_stream = c->sm_count * 8;
 	return B2R_OK;
 }
@@ -218,6 +220,9 @@ int enqueue_batch(b2r_ctx* c, bool profile) {
 		const bool exact = (c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) != 0;
 		if (exact && c->params.scene.n_mat > 64) return fail(B2R_ERR_STATE, "B2R_FLAG_REFERENCE_EXACT: at most 64 materials (RendererPolicy::max_materialID, Renderer.hpp:23)");
 		for (uint32_t b = 0; b < mb; b++) {
+			if (b == 0 && c->packet_primary) {  // camera rays: one walk per warp (k_intersect_packet)
+				if ((rc = launch(c, KK_CLOSEST, profile, [&] { if (count) k_intersect_packet<true><<<c->grid_packet, kTravBlock, 0, st>>>(p, b); else k_intersect_packet<false><<<c->grid_packet, kTravBlock, 0, st>>>(p, b); }))) return rc;
+			} else
 			if ((rc = launch(c, KK_CLOSEST, profile, [&] {
 				// stack entries split 16/16 (up to 65536 wide nodes: C3) get immediate shifts; other sizes read the split from the scene
 				const bool tn16 = c->params.scene.stack_tn_bits == 16u;
@@ -895,6 +900,19 @@ int b2r_team_error(b2r_ctx* c, uint32_t* out) {
 	return B2R_OK;
 }
 
+int b2r_host_register(void* ptr, size_t bytes) {
+	if (!ptr || !bytes) return fail(B2R_ERR_ARG, "null argument");
+	cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+	if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return B2R_OK; }
+	if (e != cudaSuccess) return fail(B2R_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+	return B2R_OK;
+}
+int b2r_host_unregister(void* ptr) {
+	if (!ptr) return fail(B2R_ERR_ARG, "null argument");
+	cudaError_t e = cudaHostUnregister(ptr);
+	if (e != cudaSuccess) { cudaGetLastError(); return fail(B2R_ERR_CUDA, std::string("cudaHostUnregister: ") + cudaGetErrorString(e)); }
+	return B2R_OK;
+}
 int b2r_get_accumulations(b2r_ctx* c, uint32_t* out) { if (!c || !out) return fail(B2R_ERR_ARG, "null argument"); *out = c->accumulations; return B2R_OK; }
 int b2r_set_accumulations(b2r_ctx* c, uint32_t acc) { if (!c) return fail(B2R_ERR_ARG, "null context"); c->accumulations = acc; drop_speculation(c); return B2R_OK; }
 

@@ -497,6 +497,81 @@ struct SmemStack {
 // network (the compiler already emits VIMNMX), 5 % slower; refill thresholds 16/20/28 and 12/20 stack entries in shared memory —
 // flat; full-sweep SAH and a cost-optimal 2->4 collapse of the traversal tree — 12.3 instead of 12.4 node visits per ray.
 
+// ---- bounce 0: packet traversal ------------------------------------------------------------------------------------------------
+// Camera rays are coherent: the 32 consecutive tile-order pixels of a warp (two rows of 16 in one 16x16 tile) walk almost the same
+// nodes — measured on C3, ONE walk for the whole warp visits 14.9 nodes per 32 rays where 32 per-lane walks take 14.0 warp-steps. So for
+// primary rays the warp walks the tree as a packet: the node is fetched once for the warp (eight broadcast LDG.128: 8 L1 wavefronts
+// instead of the ~90 of the staged per-lane fetch), every lane slab-tests the four slots with its own ray, a slot is taken when ANY lane
+// passes it within its own best distance (the link is warp-uniform, so leaf / inner is a uniform branch: the sphere test of a leaf slot
+// runs once per slot, predicated on the lanes that passed its box), inner slots are ordered by the packet's minimum entry distance
+// (REDUX.MIN), and there is ONE stack per warp in shared memory with no per-lane loops at all. Each lane still keeps its own closest
+// hit, and a lane only tests spheres whose box its own ray passes, so every lane's result is exactly what its own walk would give.
+constexpr int kPacketStack = 64;
+template <bool COUNT>
+__global__ void __launch_bounds__(kTravBlock) k_intersect_packet(const Params p, const uint32_t bounce) {
+	const uint32_t n_in = p.cnt.paths[bounce];   // a multiple of 256: whole tiles of whole samples
+	const int side = bounce & 1;
+	const float4* __restrict__ wide4 = reinterpret_cast<const float4*>(p.scene.wide);
+	__shared__ uint2 s_pstack[kTravBlock / 32][kPacketStack];
+	uint2* stack = s_pstack[threadIdx.x >> 5];
+	uint32_t c_sphere = 0, c_box = 0;
+	uint32_t next = 0, end = 0;
+	for (;;) {
+		if (next >= end) {  // four packets per claim
+			uint32_t b = 0;
+			if (lane_id() == 0) b = atomicAdd(p.cnt.work_a + bounce, 128u);
+			b = __shfl_sync(0xffffffffu, b, 0);
+			if (b >= n_in) break;
+			next = b; end = min(b + 128u, n_in);
+		}
+		const uint32_t idx = next + lane_id(); next += 32u;
+		const float4 ra = p.q.A[side][idx], rb = p.q.B[side][idx];
+		const float ox = ra.x, oy = ra.y, oz = ra.z, dx = ra.w, dy = rb.x, dz = rb.y;
+		const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
+		const float nx = -(ox * ix), ny = -(oy * iy), nz = -(oz * iz), ax = fabsf(ix), ay = fabsf(iy), az = fabsf(iz);
+		float best = FLT_MAX; int32_t prim = -1;
+		uint32_t node = 0u, sp = 0u;
+		for (;;) {
+			const float4* nd = wide4 + static_cast<size_t>(node) * 8u;
+			uint32_t key[4], link[4];
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				const float4 a = ldg4(nd + 2 * k), b = ldg4(nd + 2 * k + 1);   // same address in every lane: one broadcast
+				const int32_t l = __float_as_int(b.z);                          // warp-uniform
+				key[k] = 0xffffffffu; link[k] = static_cast<uint32_t>(l);
+				if (l == kEmptyLink) continue;
+				float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, ax, ay, az, best, &tn, &h);
+				if (COUNT) c_box++;
+				if (!__any_sync(0xffffffffu, h)) continue;
+				if (l < 0) {  // leaf slot: the lanes whose ray passes its box test the sphere
+					if (h) {
+						float d; if (COUNT) c_sphere++;
+						if (sphere_hit_closest(a.x, a.y, a.z, a.w, ox, oy, oz, dx, dy, dz, &d) && (d < best || (d == best && ~l < prim))) { best = d; prim = ~l; }
+					}
+				} else key[k] = __reduce_min_sync(0xffffffffu, h ? __float_as_uint(tn) : 0xffffffffu);  // the packet's entry distance
+			}
+			const uint32_t far_best = __reduce_max_sync(0xffffffffu, __float_as_uint(best));  // a node is dead once it lies behind EVERY lane's hit
+			B2R_CSWAP(key[0], link[0], key[1], link[1]); B2R_CSWAP(key[2], link[2], key[3], link[3]);
+			B2R_CSWAP(key[0], link[0], key[2], link[2]); B2R_CSWAP(key[1], link[1], key[3], link[3]);
+			B2R_CSWAP(key[1], link[1], key[2], link[2]);
+			if (key[3] <= far_best) { if (lane_id() == 0) stack[sp] = make_uint2(link[3], key[3]); sp++; }   // (a miss key is 0xffffffff > any distance)
+			if (key[2] <= far_best) { if (lane_id() == 0) stack[sp] = make_uint2(link[2], key[2]); sp++; }
+			if (key[1] <= far_best) { if (lane_id() == 0) stack[sp] = make_uint2(link[1], key[1]); sp++; }
+			__syncwarp();
+			if (key[0] <= far_best) { node = link[0]; continue; }
+			bool found = false;
+			while (sp > 0u) {
+				const uint2 e = stack[--sp];
+				if (e.y <= far_best) { node = e.x; found = true; break; }
+			}
+			if (!found) break;
+		}
+		p.q.H[idx] = make_float2(best, __int_as_float(prim));
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.cnt.stats + ST_EXT, static_cast<unsigned long long>(n_in));
+	if (COUNT) { stat_add(p.cnt.stats, ST_SPHERE, c_sphere); stat_add(p.cnt.stats, ST_BOX, c_box); }
+}
+
 // closest-hit traversal of queue side (bounce & 1)
 // (63 registers without a minimum-blocks bound = 8 resident CTAs. Measured: bounding it to 8 costs 4 %; 71/79/96 registers with
 // 7/6/5 CTAs cost 3/5/16 %; 56/48 registers with 9/10 CTAs and a shorter shared-memory stack cost 5/8 %.)

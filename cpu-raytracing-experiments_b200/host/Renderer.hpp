@@ -62,13 +62,15 @@ struct Renderer {
 	uint32_t h_tiles = 0, v_tiles = 0;
 
 	explicit Renderer(const Scene& scene, RendererPolicy policy = {}) : Policy(policy), scene(scene) {}
-	~Renderer() { if (ctx) b2r_destroy(ctx); }
+	~Renderer() { if (!framebuffer.empty()) b2r_host_unregister(framebuffer.data()); if (ctx) b2r_destroy(ctx); }
 	Renderer(const Renderer&) = delete;
 	Renderer& operator=(const Renderer&) = delete;
 
 	void Resize(uint32_t new_width, uint32_t new_height) {  // Renderer.hpp:53-63
 		height = new_height; width = new_width;
+		if (!framebuffer.empty()) b2r_host_unregister(framebuffer.data());
 		framebuffer.resize(static_cast<size_t>(width) * height);
+		b2r_host_register(framebuffer.data(), framebuffer.size() * sizeof(framebuffer[0]));  // Render() copies into it at DMA speed (best effort)
 		h_tiles = width / TileRoot; v_tiles = height / TileRoot;
 		if (!ctx) {
 			b2r_config cfg{}; cfg.width = width; cfg.height = height; cfg.max_bounces = static_cast<uint32_t>(Policy.max_bounces);

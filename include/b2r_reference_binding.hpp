@@ -38,13 +38,15 @@ struct ReferenceRenderer {
 	uint32_t width = 0, height = 0, accumulations = 0, h_tiles = 0, v_tiles = 0;
 
 	explicit ReferenceRenderer(const SceneT& s, ReferencePolicy p = {}) : scene(s), policy(p) { static_assert(sizeof(Vec4T) == 16, "framebuffer texel = 4 floats"); }
-	~ReferenceRenderer() { if (ctx_) b2r_destroy(ctx_); }
+	~ReferenceRenderer() { if (!framebuffer.empty()) b2r_host_unregister(framebuffer.data()); if (ctx_) b2r_destroy(ctx_); }
 	ReferenceRenderer(const ReferenceRenderer&) = delete;
 	ReferenceRenderer& operator=(const ReferenceRenderer&) = delete;
 
 	void Resize(uint32_t new_width, uint32_t new_height) {                   // Renderer.hpp:53-63
 		width = new_width; height = new_height; h_tiles = width / TileRoot; v_tiles = height / TileRoot;
+		if (!framebuffer.empty()) b2r_host_unregister(framebuffer.data());
 		framebuffer.resize(static_cast<size_t>(width) * height);
+		b2r_host_register(framebuffer.data(), framebuffer.size() * sizeof(framebuffer[0]));  // Render() then copies into it at DMA speed (best effort: failure is ignored)
 		if (!ctx_) {
 			b2r_config cfg{}; cfg.width = width; cfg.height = height; cfg.max_bounces = policy.max_bounces; cfg.buckets = policy.buckets;
 			cfg.flags = policy.flags; cfg.device = policy.device;

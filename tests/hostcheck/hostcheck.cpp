@@ -5,6 +5,7 @@
 // flow below mirrors one path through k_bounce_brute / k_intersect_closest + k_shade + k_intersect_shadow
 // (csrc/b2r_device.cuh); the GPU tier (-m gpu) then checks the kernels themselves through the C ABI.
 #include "b2r_shade.h"
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -230,4 +231,49 @@ extern "C" int hc_trace_top_share(const b2r_sphere* prims, uint32_t n_prims, con
 	}
 	*visits_top = a; *visits_all = b;
 	return 0;
+}
+
+// packet traversal statistics (tuning aid): `n` rays in packets of 32 consecutive rays walk the traversal tree TOGETHER — a node is visited
+// when any ray of the packet passes its box within its own best distance; children nearest-first by the packet's minimum entry distance.
+// Returns the node visits per packet and checks every ray's closest hit against its own single-ray walk (returns the number of mismatches).
+extern "C" int hc_packet_stats(const b2r_sphere* prims, uint32_t n_prims, const float* rays, uint32_t n, uint32_t* visits_per_packet, uint32_t* sphere_tests_per_packet) {
+	float ro[6]; ray_origin_bounds(rays, n, ro);
+	const OriginBox ob = origin_box_of(prims, n_prims, nullptr, ro, 2);
+	std::vector<b2r_bvh_node> tn; build_traversal_tree(prims, n_prims, tn);
+	WideBvh w; flatten_bvh(tn.data(), static_cast<uint32_t>(tn.size()), prims, n_prims, w, &ob);
+	const float4* wide = reinterpret_cast<const float4*>(w.nodes.data());
+	int bad = 0;
+	for (uint32_t p0 = 0; p0 < n; p0 += 32) {
+		const uint32_t m = std::min(32u, n - p0);
+		TravClosest t[32]; float best[32]; int32_t prim[32];
+		for (uint32_t i = 0; i < m; i++) { const float* r = rays + 6 * static_cast<size_t>(p0 + i); t[i].begin(Ray{r[0], r[1], r[2], r[3], r[4], r[5]}); best[i] = FLT_MAX; prim[i] = -1; }
+		struct E { uint32_t node; float tn; }; std::vector<E> stack; stack.push_back({0u, 0.0f});
+		uint32_t visits = 0, stests = 0;
+		while (!stack.empty()) {
+			const E e = stack.back(); stack.pop_back();
+			float wmax = 0.0f; for (uint32_t i = 0; i < m; i++) wmax = std::max(wmax, best[i]);
+			if (e.tn > wmax) continue;
+			visits++;
+			const float4* nd = wide + static_cast<size_t>(e.node) * 8;
+			E kids[4]; int nk = 0;
+			for (int k = 0; k < 4; k++) {
+				const float4 a = nd[2 * k], b = nd[2 * k + 1]; const int32_t l = as_int(b.z);
+				if (l == kEmptyLink) continue;
+				float tmin = FLT_MAX; bool any = false;
+				for (uint32_t i = 0; i < m; i++) {
+					float tnr; bool h; slab(a, b, t[i].ix, t[i].iy, t[i].iz, t[i].nx, t[i].ny, t[i].nz, t[i].ax, t[i].ay, t[i].az, best[i], &tnr, &h);
+					if (!h) continue;
+					any = true; tmin = std::min(tmin, tnr);
+					if (l < 0) { float d; stests++; if (sphere_hit_closest(a.x, a.y, a.z, a.w, t[i].ox, t[i].oy, t[i].oz, t[i].dx, t[i].dy, t[i].dz, &d) && (d < best[i] || (d == best[i] && ~l < prim[i]))) { best[i] = d; prim[i] = ~l; } }
+				}
+				if (any && l >= 0) kids[nk++] = {static_cast<uint32_t>(l), tmin};
+			}
+			std::sort(kids, kids + nk, [](const E& x, const E& y) { return x.tn > y.tn; });  // farthest first onto the stack
+			for (int k = 0; k < nk; k++) stack.push_back(kids[k]);
+		}
+		visits_per_packet[p0 / 32] = visits; sphere_tests_per_packet[p0 / 32] = stests;
+		for (uint32_t i = 0; i < m; i++) { uint32_t cs = 0, cb = 0; float b1; int32_t p1; const float* r = rays + 6 * static_cast<size_t>(p0 + i);
+			traverse_closest<false>(w.nodes.data(), w.tn_bits, Ray{r[0], r[1], r[2], r[3], r[4], r[5]}, &b1, &p1, &cs, &cb); if (p1 != prim[i] || bits(b1) != bits(best[i])) bad++; }
+	}
+	return bad;
 }
