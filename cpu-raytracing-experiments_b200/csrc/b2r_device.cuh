@@ -533,16 +533,18 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_packet(const Params p,
 		uint32_t node = 0u, sp = 0u;
 		for (;;) {
 			const float4* nd = wide4 + static_cast<size_t>(node) * 8u;
+			float4 na[4], nb[4];
+#pragma unroll
+			for (int k = 0; k < 4; k++) { na[k] = ldg4(nd + 2 * k); nb[k] = ldg4(nd + 2 * k + 1); }   // the whole node up front: eight broadcast loads in flight (every lane reads the same address)
 			uint32_t key[4], link[4];
 #pragma unroll
 			for (int k = 0; k < 4; k++) {
-				const float4 a = ldg4(nd + 2 * k), b = ldg4(nd + 2 * k + 1);   // same address in every lane: one broadcast
+				const float4 a = na[k], b = nb[k];
 				const int32_t l = __float_as_int(b.z);                          // warp-uniform
 				key[k] = 0xffffffffu; link[k] = static_cast<uint32_t>(l);
-				if (l == kEmptyLink) continue;
-				float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, ax, ay, az, best, &tn, &h);
-				if (COUNT) c_box++;
-				if (!__any_sync(0xffffffffu, h)) continue;
+				float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, ax, ay, az, best, &tn, &h);  // an empty slot's box (h = -1e30) is never hit
+				if (COUNT && l != kEmptyLink) c_box++;
+				if (__ballot_sync(0xffffffffu, h) == 0u) continue;
 				if (l < 0) {  // leaf slot: the lanes whose ray passes its box test the sphere
 					if (h) {
 						float d; if (COUNT) c_sphere++;
