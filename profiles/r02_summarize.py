@@ -49,10 +49,19 @@ for d in launch.values():
 print()
 print(f"{'kernel (all launches)':22s} {'n':>3s} {'total us':>9s} {'share':>6s} {'MB/launch':>10s} {'issue %':>8s} {'L1 pipe %':>9s} {'lanes':>6s} {'occ %':>6s} {'fma %':>6s} {'alu %':>6s}")
 out = {}
+if "k_intersect_packet" in tot and "k_intersect_closest" in tot:
+    # bench.py books the bounce-0 packet launch with the closest-hit traversal (one KK_CLOSEST launch per bounce): the JSON row
+    # "k_intersect_closest" is the sum over all 16 closest-hit launches of the step, the packet kernel is listed on its own as well
+    m = collections.defaultdict(float)
+    for src in ("k_intersect_packet", "k_intersect_closest"):
+        for q, v in tot[src].items():
+            m[q] += v
+    tot["k_intersect_closest (16 launches incl. the bounce-0 packet launch)"] = m
 for k, a in tot.items():
     w = lambda q: a[q] / a["t"]
-    print(f"{k:22s} {int(a['n']):3d} {a['t']:9.1f} {100 * a['t'] / T:5.1f}% {a['bytes'] / a['n'] / 1e6:10.2f} {w('issue'):8.1f} {w('l1'):9.1f} {a['tinst'] / a['inst']:6.2f} {w('occ'):6.1f} {w('fma'):6.1f} {w('alu'):6.1f}")
-    out[k] = {"launches": int(a["n"]), "dram_bytes_per_launch": a["bytes"] / a["n"], "device_us_per_step": a["t"], "issue_slots_busy_pct": w("issue"), "l1_data_pipe_pct": w("l1"),
+    print(f"{k[:22]:22s} {int(a['n']):3d} {a['t']:9.1f} {100 * a['t'] / T:5.1f}% {a['bytes'] / a['n'] / 1e6:10.2f} {w('issue'):8.1f} {w('l1'):9.1f} {a['tinst'] / a['inst']:6.2f} {w('occ'):6.1f} {w('fma'):6.1f} {w('alu'):6.1f}")
+    jk = "k_intersect_closest" if k.startswith("k_intersect_closest (") else ("k_intersect_closest_per_lane" if k == "k_intersect_closest" and "k_intersect_packet" in tot else k)
+    out[jk] = {"launches": int(a["n"]), "dram_bytes_per_launch": a["bytes"] / a["n"], "device_us_per_step": a["t"], "issue_slots_busy_pct": w("issue"), "l1_data_pipe_pct": w("l1"),
               "active_lanes_per_instruction": a["tinst"] / a["inst"], "achieved_occupancy_pct": w("occ"),
               "source": f"profiles/r02_{workload}_metrics.txt: ncu --metrics (dram__bytes_read/write.sum, smsp__issue_active, l1tex__data_pipe_lsu_wavefronts, smsp__thread_inst_executed_per_inst_executed) --clock-control none over ALL {int(a['n'])} launches of the kernel in one {workload.upper()} step; percentages duration-weighted"}
 dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "r02_traffic.json")
