@@ -703,7 +703,7 @@ def main():
     if rank == 0:
         entry.build()
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keeps NCCL's version banner off stdout: rank 0 prints ONE line
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.devnull)  # NCCL's version banner goes there instead of stdout: rank 0 prints ONE line
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
         dist.barrier()
