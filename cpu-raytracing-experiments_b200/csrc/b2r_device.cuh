@@ -65,6 +65,9 @@ __device__ __forceinline__ void store_path(const QueueDev& q, int side, uint32_t
 #ifndef B2R_BRUTE_MIN_BLOCKS
 #define B2R_BRUTE_MIN_BLOCKS 7      // resident CTAs per SM the register allocation is bounded for
 #endif
+#ifndef B2R_SHADE_MIN_BLOCKS
+#define B2R_SHADE_MIN_BLOCKS 7      // k_shade: resident CTAs per SM the register allocation is bounded for
+#endif
 constexpr int kBruteBlock = 128;       // threads per CTA
 constexpr int kBruteWarps = kBruteBlock / 32;
 constexpr int kSmemTable = 64;         // materials / lights kept in shared memory when they fit
@@ -617,7 +620,7 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_closest(const Params p
 // shade the hit records: light sample -> shadow queue, emission, BRDF sample / roulette -> next path queue.
 // Same CTA structure as the brute-force kernel: hits are collected in a shared-memory queue and shaded a full CTA at a time.
 template <bool EXACT>
-__global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_shade(const Params p, const uint32_t bounce) {
+__global__ void __launch_bounds__(kBruteBlock, B2R_SHADE_MIN_BLOCKS) k_shade(const Params p, const uint32_t bounce) {
 	constexpr int kQ = 2 * kBruteBlock;
 	__shared__ uint32_t s_hit_i[kQ]; __shared__ float s_hit_t[kQ]; __shared__ int32_t s_hit_prim[kQ];
 	__shared__ uint32_t s_cnt_a[kBruteWarps], s_cnt_b[kBruteWarps], s_cnt_c[kBruteWarps], s_base, s_sbase;

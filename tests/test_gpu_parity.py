@@ -824,3 +824,27 @@ def test_gpu_built_tree_equals_host_twin_and_brute_force(n, hostcheck):
     wide2, _ = r.wide_nodes(); s_wide, _ = s.wide_nodes()
     assert r.buckets_host().tobytes() == got.tobytes() and wide2.shape == s_wide.shape
     r.close(); b.close(); s.close()
+
+
+def test_packet_traversal_of_camera_rays_equals_per_lane_walks():
+    """k_intersect_packet walks the tree once per warp for the camera rays (bounce 0). Every lane's closest hit must be what its own walk
+    gives: same bucket sums, bit for bit, as a context created with the per-lane kernel at bounce 0 (B2R_NO_PACKET, read at b2r_create),
+    on a scene with many small spheres (lanes of one packet hit different spheres and miss), a wide-angle camera (divergent packets), a
+    deep tree of nested spheres (the warp stack), and in reference-exact mode."""
+    cases = [(scenes.random_scene(3000, light_every=25), 160, 96, 0), (scenes.random_scene(20000, light_every=40), 320, 192, b2r.FLAG_REFERENCE_EXACT)]
+    wide = scenes.random_scene(3000, light_every=25); wide["camera"] = dict(wide["camera"]); wide["camera"]["focal_length"] = 6.0; cases.append((wide, 160, 96, 0))
+    nested = scenes.Scene(scenes.default_scene()); n = 300
+    geo = np.zeros(n, scenes.SPHERE_DTYPE); geo["radius_sq"] = (np.linspace(0.01, 1.2, n) ** 2).astype(np.float32); geo["position"][:, 0] = 0.3; geo["material_ID"] = np.arange(n) % 9
+    nested["geometry"] = geo; cases.append((nested, 160, 96, b2r.FLAG_FORCE_BVH))
+    for sc, w, h, flags in cases:
+        a = b2r.Renderer(sc, w, h, max_bounces=6, buckets=2, flags=flags | b2r.FLAG_FORCE_BVH); a.Accumulate(4)
+        os.environ["B2R_NO_PACKET"] = "1"
+        try:
+            b = b2r.Renderer(sc, w, h, max_bounces=6, buckets=2, flags=flags | b2r.FLAG_FORCE_BVH)
+        finally:
+            del os.environ["B2R_NO_PACKET"]
+        b.Accumulate(4)
+        assert a.buckets_host().tobytes() == b.buckets_host().tobytes()
+        ca, cb = a.counters(), b.counters()
+        assert ca["extension_rays"] == cb["extension_rays"] and ca["shadow_rays"] == cb["shadow_rays"] and ca["shaded_hits"] == cb["shaded_hits"]
+        a.close(); b.close()
