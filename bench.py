@@ -703,10 +703,16 @@ def main():
     if rank == 0:
         entry.build()
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", os.devnull)  # NCCL's version banner goes there instead of stdout: rank 0 prints ONE line
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-        dist.barrier()
+        # NCCL prints its version banner to stdout when the first communicator is created: file descriptor 1 points at /dev/null until
+        # that has happened, so that rank 0's stdout carries ONE line
+        sys.stdout.flush(); keep = os.dup(1); null = os.open(os.devnull, os.O_WRONLY); os.dup2(null, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+            dist.barrier()
+            t = torch.zeros(1, device=f"cuda:{local}"); dist.all_reduce(t); torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(keep, 1); os.close(keep); os.close(null)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libb2r has no CPU fallback")
     dev = torch.device(f"cuda:{local}"); torch.cuda.set_device(dev)

@@ -98,6 +98,15 @@ __device__ __forceinline__ void block_rank2(bool fa, bool fb, uint32_t* s_a, uin
 	*rank_a = oa + __popc(ba & below); *rank_b = ob + __popc(bb & below);
 }
 
+// The late bounces of the brute-force pipeline are thin (C2: bounces >= 5 carry 3 % of the instructions of a batch but 10 % of its time, at
+// 20-45 % issue utilisation: each launch stages the scene, fills and drains its shared-memory queues for a handful of rays per CTA). Once
+// fewer than frame.finish_below paths enter a bounce (first checked at frame.finish_first), k_brute_finish traces those paths to their end in
+// ONE launch and the per-bounce kernels of the remaining bounces return at once: the path counts only fall, so "paths[bounce] <
+// finish_below" says the same thing in every kernel (an untouched count of a later bounce reads 0).
+__device__ __forceinline__ bool finished_elsewhere(const Params& p, uint32_t bounce, uint32_t n_in) {
+	return p.frame.finish_below != 0u && bounce >= p.frame.finish_first && bounce + 1u < p.frame.max_bounces && n_in < p.frame.finish_below;  // (the last bounce is never handed over: nothing is left to finish)
+}
+
 // EXACT (B2R_FLAG_REFERENCE_EXACT): rays that sit in the last `active % 8` slots of their tile's stream take the reference's
 // scalar-tail sphere formula (BVH.hpp:270-286) instead of the AVX2+FMA one (:250-268), and survivors leave (material, slot) behind
 // for k_stream_rank, which computes the slots of the next bounce (the reference's stable counting sort by material).
@@ -120,6 +129,7 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 	const bool last = bounce + 1 >= p.frame.max_bounces;
 	uint32_t c_shadow = 0, c_hits = 0, c_term = 0, c_drop = 0, c_events = 0, c_sphere = 0;
 	if (blockIdx.x * kBruteBlock >= n_in) return;  // thin late bounces: CTAs without a first chunk leave before staging anything
+	if (!FIRST && !EXACT && finished_elsewhere(p, bounce, n_in)) return;  // k_brute_finish has taken the rest of the batch
 
 	// stage the scene tables once per CTA (persistent: amortised over the whole launch)
 	if (n_tiles == 1) {
@@ -322,6 +332,113 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_bounce_br
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.cnt.stats + ST_EXT, static_cast<unsigned long long>(n_in));
 	stat_add(p.cnt.stats, ST_SHADOW, c_shadow); stat_add(p.cnt.stats, ST_HITS, c_hits); stat_add(p.cnt.stats, ST_TERM, c_term);
+	stat_add(p.cnt.stats, ST_DROPPED, c_drop); stat_add(p.cnt.stats, ST_EVENTS, c_events);
+	if (COUNT) stat_add(p.cnt.stats, ST_SPHERE, c_sphere);
+}
+
+
+// The rest of every path that enters bounce `bounce0` of the brute-force pipeline, in one launch (see finished_elsewhere). One path per
+// lane; both sphere loops are warp-uniform (every lane walks all the spheres of the shared-memory copy), so the only divergence is paths
+// ending, and a lane whose path has ended picks up the next waiting path. Same routines, same RNG streams (a function of sample, pixel and
+// bounce), same order of a path's radiance additions (light sample, then emission) as k_bounce_brute: every path ends with the same bits.
+template <bool COUNT>
+__global__ void __launch_bounds__(kBruteBlock, B2R_BRUTE_MIN_BLOCKS) k_brute_finish(const Params p, const uint32_t bounce0) {
+	__shared__ float4 s_prim[kBruteTile];
+	__shared__ int32_t s_prim_mat[kBruteTile];
+	__shared__ float4 s_table[4][kSmemTable];
+	SceneDev sc = p.scene;
+	const uint32_t n_in = p.cnt.paths[bounce0];
+	if (n_in == 0u || !finished_elsewhere(p, bounce0, n_in)) return;
+	if (bounce0 > p.frame.finish_first && p.cnt.paths[bounce0 - 1u] < p.frame.finish_below) return;  // an earlier launch of this kernel took them
+	if (blockIdx.x * kBruteBlock >= n_in) return;
+	const int side = bounce0 & 1;
+	const bool mis = !(p.frame.flags & B2R_FLAG_NO_MIS);
+	const uint32_t mb = p.frame.max_bounces, n_prims = sc.n_prims;
+	for (uint32_t j = threadIdx.x; j < n_prims; j += blockDim.x) { s_prim[j] = sc.prims[j]; s_prim_mat[j] = sc.prim_mat[j]; }  // (launched only when the scene fits one tile)
+	sc.prim_mat = s_prim_mat; sc.prims = s_prim;
+	if (sc.n_mat <= kSmemTable) {
+		for (uint32_t j = threadIdx.x; j < sc.n_mat; j += blockDim.x) { s_table[0][j] = sc.mat_albedo[j]; s_table[1][j] = sc.mat_emission[j]; }
+		sc.mat_albedo = s_table[0]; sc.mat_emission = s_table[1];
+	}
+	if (sc.n_lights <= kSmemTable) {
+		for (uint32_t j = threadIdx.x; j < sc.n_lights; j += blockDim.x) { s_table[2][j] = sc.light_sphere[j]; s_table[3][j] = sc.light_emit[j]; }
+		sc.light_sphere = s_table[2]; sc.light_emit = s_table[3];
+	}
+	__syncthreads();
+	const uint32_t a_prim = smem_addr(s_prim);
+	uint32_t c_ext = 0, c_shadow = 0, c_hits = 0, c_term = 0, c_drop = 0, c_events = 0, c_sphere = 0;
+	uint32_t next = 0, end = 0; bool dry = false;  // warp-uniform: 32 paths per claim
+	PathState s; uint32_t bounce = 0; bool alive = false;
+	for (;;) {
+		// lanes without a path take the next waiting ones
+		const uint32_t idle = __ballot_sync(0xffffffffu, !alive);
+		if (idle && !dry) {
+			uint32_t want = __popc(idle), given = 0, mine = 0xffffffffu;
+			while (want > given && !dry) {
+				if (next >= end) {
+					uint32_t b = 0;
+					if (lane_id() == 0) b = atomicAdd(p.cnt.work_a + bounce0, 32u);
+					b = __shfl_sync(0xffffffffu, b, 0);
+					if (b >= n_in) { dry = true; break; }
+					next = b; end = min(b + 32u, n_in);
+				}
+				const uint32_t n = min(want - given, end - next), rank = __popc(idle & ((1u << lane_id()) - 1u));
+				if (!alive && rank >= given && rank < given + n) mine = next + (rank - given);
+				next += n; given += n;
+			}
+			if (mine != 0xffffffffu) { s = load_path(p.q, side, mine); bounce = bounce0; alive = true; }
+		}
+		if (!__any_sync(0xffffffffu, alive)) break;
+		// closest hit over every sphere (ties -> lowest BVH-order index, strict <, Q6)
+		float best = FLT_MAX; int32_t prim = -1;
+		if (alive) {
+			c_ext++;
+			for (uint32_t j = 0; j < n_prims; j++) {
+				const float4 sp = lds_f4(a_prim + j * 16u); float d;
+				if (sphere_hit_closest(sp.x, sp.y, sp.z, sp.w, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, &d) && d < best) { best = d; prim = static_cast<int32_t>(j); }
+			}
+			if (COUNT) c_sphere += n_prims;
+		}
+		bool want_shadow = false, has_emit = false, keep = false; ShadowRay sr{}; f3 emit{0.0f, 0.0f, 0.0f}; const uint32_t pid = s.pid;
+		if (alive) {
+			if (prim < 0) {  // miss shader (Renderer.hpp:408-420)
+				c_term++;
+				if (sc.has_ambient) { rad_add(p.rad, p.frame.npix, pid, shade_sky(sc, s), f3{0.0f, 0.0f, 0.0f}, true, false); c_events++; }
+			} else {
+				const uint32_t acc = p.batch->acc[pid >> 26], seed = pixel_seed(pid & kPixMask, mb);
+				const Surface sf = shade_surface(sc, s, best, prim);
+				c_hits++;
+				if (bounce + 1u >= mb) { rad_zero(p.rad, p.frame.npix, pid); c_drop++; }  // Q11
+				else {
+					if (mis) want_shadow = shade_light_sample(sc, sf, s, prim, acc, seed, bounce, &sr);
+					if (sf.emissive) { emit = shade_emission(sc, sf, s, best, bounce, mis); has_emit = true; }
+					keep = shade_continue(sf, &s, acc, seed, bounce);
+					if (!keep) c_term++;
+				}
+			}
+		}
+		// any-hit test of this bounce's shadow ray (BVH.hpp:290-305), three spheres per early-out vote
+		bool occluded = !want_shadow;
+		if (__any_sync(0xffffffffu, want_shadow)) {
+			if (want_shadow) { c_shadow++; if (COUNT) c_sphere += n_prims; }
+			for (uint32_t j0 = 0; j0 < n_prims; j0 += 3u) {
+#pragma unroll
+				for (uint32_t u = 0; u < 3u; u++) {
+					if (j0 + u < n_prims) {
+						const float4 sp = lds_f4(a_prim + (j0 + u) * 16u);
+						if (!occluded && sphere_hit_any(sp.x, sp.y, sp.z, sp.w, sr.o.x, sr.o.y, sr.o.z, sr.d.x, sr.d.y, sr.d.z, sr.tfar)) occluded = true;
+					}
+				}
+				if (__all_sync(0xffffffffu, occluded)) break;
+			}
+		}
+		const bool lit = want_shadow && !occluded;
+		// light sample first, then emission (Renderer.hpp:304-353); one radiance event per emissive hit, as k_bounce_brute counts them
+		if (has_emit) { rad_add(p.rad, p.frame.npix, pid, sr.L, emit, lit, true); c_events++; }
+		else if (lit) { rad_add(p.rad, p.frame.npix, pid, sr.L, f3{0.0f, 0.0f, 0.0f}, true, false); c_events++; }
+		alive = keep; bounce++;
+	}
+	stat_add(p.cnt.stats, ST_EXT, c_ext); stat_add(p.cnt.stats, ST_SHADOW, c_shadow); stat_add(p.cnt.stats, ST_HITS, c_hits); stat_add(p.cnt.stats, ST_TERM, c_term);
 	stat_add(p.cnt.stats, ST_DROPPED, c_drop); stat_add(p.cnt.stats, ST_EVENTS, c_events);
 	if (COUNT) stat_add(p.cnt.stats, ST_SPHERE, c_sphere);
 }

@@ -50,6 +50,7 @@ struct FrameDev {
 	uint32_t width, height, h_tiles, npix;
 	uint32_t max_bounces, buckets, flags;
 	uint32_t h_tiles_magic, npix_magic;  // floor(2^32 / d) for div_by()
+	uint32_t finish_below, finish_first;  // brute-force pipeline: once fewer than finish_below paths enter a bounce >= finish_first, k_brute_finish traces them to their end in one launch (0 = never)
 };
 // x / d for a launch-constant divisor without the ~20-instruction integer division: q = mulhi(x, floor(2^32/d)) is q or q-1.
 B2R_HD uint32_t div_by(uint32_t x, uint32_t d, uint32_t magic) {
