@@ -865,7 +865,7 @@ __global__ void __launch_bounds__(kTravBlock, 8) k_intersect_shadow(const Params
 		do {
 			warp_stage_nodes(wide, rows, active ? node : 0u);
 			if (active) {
-				uint32_t next = kNoNode, leaves = 0u;
+				uint32_t next = kNoNode, leaves = 0u; float next_tn = FLT_MAX;
 				stack.room();
 #pragma unroll
 				for (int k = 0; k < 4; k++) {
@@ -873,7 +873,14 @@ __global__ void __launch_bounds__(kTravBlock, 8) k_intersect_shadow(const Params
 					const int32_t l = __float_as_int(b.z);
 					float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, ax, ay, az, tfar, &tn, &h);
 					if (COUNT && l != kEmptyLink) c_box++;
-					if (h && l >= 0) { if (next != kNoNode) stack.push(next); next = static_cast<uint32_t>(l); }
+					if (h && l >= 0) {
+						// the NEAREST hit child is visited next, the others are pushed: the result is an order-independent boolean, but in a
+						// dense scene the occluder is usually close to the origin (C3: every shadow ray is occluded; 12.4 -> 10.2 node visits per ray)
+						const bool nearer = tn < next_tn;
+						const uint32_t later = nearer ? next : static_cast<uint32_t>(l);
+						if (later != kNoNode) stack.push(later);
+						if (nearer) { next = static_cast<uint32_t>(l); next_tn = tn; }
+					}
 					leaves |= (h && l < 0) ? (1u << k) : 0u;  // leaf slots whose (inflated) box the ray passes within [0, tfar]
 				}
 				bool occluded = false;

@@ -358,14 +358,19 @@ struct TravAnyT : TravBase {
 	B2R_HD void begin(const Ray& r, float limit) { arm(r); tfar = limit; occluded = false; stack.reset(); }
 	template <bool COUNT, bool STAGED>
 	B2R_HD bool visit(const float4* n, uint32_t* c_sphere, uint32_t* c_box) {
-		uint32_t next = 0xffffffffu, leaves = 0u;
+		uint32_t next = 0xffffffffu, leaves = 0u; float next_tn = FLT_MAX;
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
 			const float4 a = node_f4<STAGED>(n, 2 * k), b = node_f4<STAGED>(n, 2 * k + 1);
 			const int32_t l = as_int(b.z);
 			float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, ax, ay, az, tfar, &tn, &h);
 			if (COUNT && l != kEmptyLink) (*c_box)++;
-			if (h && l >= 0) { if (next != 0xffffffffu) stack.push(next); next = static_cast<uint32_t>(l); }
+			if (h && l >= 0) {  // nearest hit child next, the others pushed (as k_intersect_shadow does)
+				const bool nearer = tn < next_tn;
+				const uint32_t later = nearer ? next : static_cast<uint32_t>(l);
+				if (later != 0xffffffffu) stack.push(later);
+				if (nearer) { next = static_cast<uint32_t>(l); next_tn = tn; }
+			}
 			leaves |= (h && l < 0) ? (1u << k) : 0u;
 		}
 		while (leaves) {

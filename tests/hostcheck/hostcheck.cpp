@@ -6,6 +6,7 @@
 // (csrc/b2r_device.cuh); the GPU tier (-m gpu) then checks the kernels themselves through the C ABI.
 #include "b2r_shade.h"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -274,6 +275,46 @@ extern "C" int hc_packet_stats(const b2r_sphere* prims, uint32_t n_prims, const 
 		visits_per_packet[p0 / 32] = visits; sphere_tests_per_packet[p0 / 32] = stests;
 		for (uint32_t i = 0; i < m; i++) { uint32_t cs = 0, cb = 0; float b1; int32_t p1; const float* r = rays + 6 * static_cast<size_t>(p0 + i);
 			traverse_closest<false>(w.nodes.data(), w.tn_bits, Ray{r[0], r[1], r[2], r[3], r[4], r[5]}, &b1, &p1, &cs, &cb); if (p1 != prim[i] || bits(b1) != bits(best[i])) bad++; }
+	}
+	return bad;
+}
+
+// any-hit traversal statistics (tuning aid): node visits per shadow ray with the kernels' order (first hit slot first) and with the nearest
+// hit child first; occluded_out from the kernels' order; returns the number of rays on which the two policies disagree (must be 0)
+extern "C" int hc_anyhit_stats(const b2r_sphere* prims, uint32_t n_prims, const float* rays, const float* tfar, uint32_t n, uint32_t* steps_slot_order, uint32_t* steps_nearest, uint8_t* occluded_out) {
+	float ro[6]; ray_origin_bounds(rays, n, ro);
+	const OriginBox ob = origin_box_of(prims, n_prims, nullptr, ro, 2);
+	std::vector<b2r_bvh_node> tn; build_traversal_tree(prims, n_prims, tn);
+	WideBvh w; flatten_bvh(tn.data(), static_cast<uint32_t>(tn.size()), prims, n_prims, w, &ob);
+	const float4* wide = reinterpret_cast<const float4*>(w.nodes.data());
+	int bad = 0;
+	for (uint32_t i = 0; i < n; i++) {
+		const float* r = rays + 6 * static_cast<size_t>(i);
+		TravBase t; t.arm(Ray{r[0], r[1], r[2], r[3], r[4], r[5]});
+		bool occ[2] = {false, false}; uint32_t st[2] = {0, 0};
+		for (int policy = 0; policy < 2; policy++) {
+			const int mode = policy == 0 ? 0 : (std::getenv("HC_ANYHIT_MODE") ? std::atoi(std::getenv("HC_ANYHIT_MODE")) : 1);
+			std::vector<uint32_t> stack; uint32_t node = 0; bool have = true;
+			while (have && !occ[policy]) {
+				st[policy]++;
+				const float4* nd = wide + static_cast<size_t>(node) * 8;
+				uint32_t hit[4]; float htn[4]; int nh = 0;
+				for (int k = 0; k < 4 && !occ[policy]; k++) {
+					const float4 a = nd[2 * k], b = nd[2 * k + 1]; const int32_t l = as_int(b.z);
+					float tnr; bool h; slab(a, b, t.ix, t.iy, t.iz, t.nx, t.ny, t.nz, t.ax, t.ay, t.az, tfar[i], &tnr, &h);
+					if (!h) continue;
+					if (l < 0) { if (sphere_hit_any(a.x, a.y, a.z, a.w, t.ox, t.oy, t.oz, t.dx, t.dy, t.dz, tfar[i])) occ[policy] = true; }
+					else { hit[nh] = static_cast<uint32_t>(l); htn[nh] = tnr; nh++; }
+				}
+				if (occ[policy]) break;
+				if (mode == 1 && nh > 1) { int m = 0; for (int k = 1; k < nh; k++) if (htn[k] < htn[m]) m = k; std::swap(hit[0], hit[m]); std::swap(htn[0], htn[m]); }
+				if (mode == 2 && nh > 1) { for (int a2 = 0; a2 < nh; a2++) for (int b2 = a2 + 1; b2 < nh; b2++) if (htn[b2] < htn[a2]) { std::swap(hit[a2], hit[b2]); std::swap(htn[a2], htn[b2]); } }
+				for (int k = nh - 1; k >= 1; k--) stack.push_back(hit[k]);
+				if (nh) node = hit[0]; else if (!stack.empty()) { node = stack.back(); stack.pop_back(); } else have = false;
+			}
+		}
+		if (occ[0] != occ[1]) bad++;
+		steps_slot_order[i] = st[0]; steps_nearest[i] = st[1]; occluded_out[i] = occ[0] ? 1 : 0;
 	}
 	return bad;
 }
