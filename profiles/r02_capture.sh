@@ -16,7 +16,7 @@ timeout 900 ncu --metrics $M --clock-control none -k regex:"k_intersect_packet|k
 # (3) full sections + source for a mid-path bounce (bounce 4: closest, shade, shadow) of the same step, and for the packet kernel (bounce 0)
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_intersect_closest|k_intersect_shadow|k_shade" -s 150 -c 3 -o gpurun_out/r02_c3_bounce4 -f $C3 > gpurun_out/r02_c3_ncu3.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_intersect_packet" -s 3 -c 1 -o gpurun_out/r02_c3_packet -f $C3 > gpurun_out/r02_c3_ncu4.log 2>&1
-# (4) C2: the 16 k_bounce_brute launches of one step + accumulate + resolve
+# (4) C2: one step = k_set_batch, 16 k_bounce_brute + 13 k_brute_finish launches (12 of them return at once), k_accumulate, k_resolve = 32 launches
 timeout 300 $C2 > gpurun_out/r02_c2_plain.log 2>&1 || exit 1
-timeout 900 ncu --metrics $M --clock-control none -s 54 -c 18 --csv --log-file gpurun_out/r02_c2_metrics.csv $C2 > gpurun_out/r02_c2_ncu.log 2>&1
+timeout 900 ncu --metrics $M --clock-control none -s 96 -c 32 --csv --log-file gpurun_out/r02_c2_metrics.csv $C2 > gpurun_out/r02_c2_ncu.log 2>&1
 echo captured

@@ -49,18 +49,23 @@ for d in launch.values():
 print()
 print(f"{'kernel (all launches)':22s} {'n':>3s} {'total us':>9s} {'share':>6s} {'MB/launch':>10s} {'issue %':>8s} {'L1 pipe %':>9s} {'lanes':>6s} {'occ %':>6s} {'fma %':>6s} {'alu %':>6s}")
 out = {}
-if "k_intersect_packet" in tot and "k_intersect_closest" in tot:
-    # bench.py books the bounce-0 packet launch with the closest-hit traversal (one KK_CLOSEST launch per bounce): the JSON row
-    # "k_intersect_closest" is the sum over all 16 closest-hit launches of the step, the packet kernel is listed on its own as well
-    m = collections.defaultdict(float)
-    for src in ("k_intersect_packet", "k_intersect_closest"):
-        for q, v in tot[src].items():
-            m[q] += v
-    tot["k_intersect_closest (16 launches incl. the bounce-0 packet launch)"] = m
+# bench.py books the bounce-0 packet launch with the closest-hit traversal (one KK_CLOSEST launch per bounce) and the k_brute_finish
+# launches with the brute-force bounce kernel (KK_BRUTE): the JSON rows "k_intersect_closest" / "k_bounce_brute" are the sums over all
+# those launches of the step (the same population bench.py averages its algorithmic bytes over); the parts are listed on their own as well
+MERGE = {"k_intersect_closest": ("k_intersect_packet", "k_intersect_closest_per_lane"), "k_bounce_brute": ("k_brute_finish", "k_bounce_brute_per_bounce")}
+renamed = {}
+for main, (extra, alone) in MERGE.items():
+    if main in tot and extra in tot:
+        m = collections.defaultdict(float)
+        for src in (extra, main):
+            for q, v in tot[src].items():
+                m[q] += v
+        tot[f"{main} (all {int(m['n'])} launches incl. {extra})"] = m
+        renamed[main] = alone
 for k, a in tot.items():
     w = lambda q: a[q] / a["t"]
     print(f"{k[:22]:22s} {int(a['n']):3d} {a['t']:9.1f} {100 * a['t'] / T:5.1f}% {a['bytes'] / a['n'] / 1e6:10.2f} {w('issue'):8.1f} {w('l1'):9.1f} {a['tinst'] / a['inst']:6.2f} {w('occ'):6.1f} {w('fma'):6.1f} {w('alu'):6.1f}")
-    jk = "k_intersect_closest" if k.startswith("k_intersect_closest (") else ("k_intersect_closest_per_lane" if k == "k_intersect_closest" and "k_intersect_packet" in tot else k)
+    jk = k.split(" (")[0] if " (all " in k else renamed.get(k, k)
     out[jk] = {"launches": int(a["n"]), "dram_bytes_per_launch": a["bytes"] / a["n"], "device_us_per_step": a["t"], "issue_slots_busy_pct": w("issue"), "l1_data_pipe_pct": w("l1"),
               "active_lanes_per_instruction": a["tinst"] / a["inst"], "achieved_occupancy_pct": w("occ"),
               "source": f"profiles/r02_{workload}_metrics.txt: ncu --metrics (dram__bytes_read/write.sum, smsp__issue_active, l1tex__data_pipe_lsu_wavefronts, smsp__thread_inst_executed_per_inst_executed) --clock-control none over ALL {int(a['n'])} launches of the kernel in one {workload.upper()} step; percentages duration-weighted"}
