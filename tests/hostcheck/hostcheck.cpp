@@ -318,3 +318,44 @@ extern "C" int hc_anyhit_stats(const b2r_sphere* prims, uint32_t n_prims, const 
 	}
 	return bad;
 }
+
+// closest-hit traversal statistics for push-order policies (tuning aid): mode 0 = the kernels' order (all hit children sorted by entry
+// distance), 1 = nearest child next, the others pushed in slot order, 2 = nearest next, the others pushed farthest-slot-first by a single
+// compare of the two remaining... Returns mismatching rays against mode 0 (must be 0); steps_out[mode][ray].
+extern "C" int hc_closest_order_stats(const b2r_sphere* prims, uint32_t n_prims, const float* rays, uint32_t n, uint32_t* steps0, uint32_t* steps1) {
+	float ro[6]; ray_origin_bounds(rays, n, ro);
+	const OriginBox ob = origin_box_of(prims, n_prims, nullptr, ro, 2);
+	std::vector<b2r_bvh_node> tn; build_traversal_tree(prims, n_prims, tn);
+	WideBvh w; flatten_bvh(tn.data(), static_cast<uint32_t>(tn.size()), prims, n_prims, w, &ob);
+	const float4* wide = reinterpret_cast<const float4*>(w.nodes.data());
+	int bad = 0;
+	for (uint32_t i = 0; i < n; i++) {
+		const float* r = rays + 6 * static_cast<size_t>(i);
+		TravBase t; t.arm(Ray{r[0], r[1], r[2], r[3], r[4], r[5]});
+		float bestm[2]; int32_t primm[2];
+		for (int mode = 0; mode < 2; mode++) {
+			struct E { uint32_t node; float tn; }; std::vector<E> stack; float best = FLT_MAX; int32_t prim = -1; uint32_t node = 0, st = 0; bool have = true;
+			while (have) {
+				st++;
+				const float4* nd = wide + static_cast<size_t>(node) * 8;
+				E kids[4]; int nk = 0;
+				for (int k = 0; k < 4; k++) {
+					const float4 a = nd[2 * k], b = nd[2 * k + 1]; const int32_t l = as_int(b.z);
+					float tnr; bool h; slab(a, b, t.ix, t.iy, t.iz, t.nx, t.ny, t.nz, t.ax, t.ay, t.az, best, &tnr, &h);
+					if (!h) continue;
+					if (l < 0) { float d; if (sphere_hit_closest(a.x, a.y, a.z, a.w, t.ox, t.oy, t.oz, t.dx, t.dy, t.dz, &d) && (d < best || (d == best && ~l < prim))) { best = d; prim = ~l; } }
+					else kids[nk++] = {static_cast<uint32_t>(l), tnr};
+				}
+				if (mode == 0) std::stable_sort(kids, kids + nk, [](const E& x, const E& y) { return x.tn < y.tn; });
+				else if (nk > 1) { int m = 0; for (int k = 1; k < nk; k++) if (kids[k].tn < kids[m].tn) m = k; std::swap(kids[0], kids[m]); }
+				for (int k = nk - 1; k >= 1; k--) if (kids[k].tn <= best) stack.push_back(kids[k]);
+				have = false;
+				if (nk && kids[0].tn <= best) { node = kids[0].node; have = true; }
+				else while (!stack.empty()) { const E e = stack.back(); stack.pop_back(); if (e.tn <= best) { node = e.node; have = true; break; } }
+			}
+			bestm[mode] = best; primm[mode] = prim; (mode == 0 ? steps0 : steps1)[i] = st;
+		}
+		if (primm[0] != primm[1] || bits(bestm[0]) != bits(bestm[1])) bad++;
+	}
+	return bad;
+}
