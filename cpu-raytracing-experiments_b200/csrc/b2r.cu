@@ -229,7 +229,7 @@ int enqueue_batch(b2r_ctx* c, bool profile) {
 			if (exact && b + 1 < mb) { if ((rc = launch(c, KK_BRUTE, profile, [&] { k_stream_rank<<<c->grid_stream, 256, 0, st>>>(p, b); }))) return rc; }
 		}
 	} else {
-		if ((rc = launch(c, KK_GENERATE, profile, [&] { k_generate<<<c->grid_stream, kBlock, 0, st>>>(p); }))) return rc;
+		if (!c->packet_primary) { if ((rc = launch(c, KK_GENERATE, profile, [&] { k_generate<<<c->grid_stream, kBlock, 0, st>>>(p); }))) return rc; }  // (the packet kernel generates the camera rays itself)
 		const bool mis = !(c->cfg.flags & B2R_FLAG_NO_MIS);
 		const bool exact = (c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) != 0;
 		if (exact && c->params.scene.n_mat > 64) return fail(B2R_ERR_STATE, "B2R_FLAG_REFERENCE_EXACT: at most 64 materials (RendererPolicy::max_materialID, Renderer.hpp:23)");
@@ -279,7 +279,7 @@ int run_batch(b2r_ctx* c, BatchArgs& args) {
 	CU(cudaGraphLaunch(c->graph_exec, c->stream));
 	const uint32_t mb = c->cfg.max_bounces;
 	const bool mis = !(c->cfg.flags & B2R_FLAG_NO_MIS);
-	c->launches += (c->use_bvh ? 2 + static_cast<uint64_t>(mb) * 2 + (mis ? mb - 1 : 0) : static_cast<uint64_t>(mb) + 1 + ((c->params.frame.finish_below && !(c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) && c->params.scene.n_prims <= static_cast<uint32_t>(kBruteTile) && mb > c->params.frame.finish_first + 1u) ? mb - 1u - c->params.frame.finish_first : 0u)) + ((c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) ? mb - 1 : 0);
+	c->launches += (c->use_bvh ? (c->packet_primary ? 1 : 2) + static_cast<uint64_t>(mb) * 2 + (mis ? mb - 1 : 0) : static_cast<uint64_t>(mb) + 1 + ((c->params.frame.finish_below && !(c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) && c->params.scene.n_prims <= static_cast<uint32_t>(kBruteTile) && mb > c->params.frame.finish_first + 1u) ? mb - 1u - c->params.frame.finish_first : 0u)) + ((c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) ? mb - 1 : 0);
 	return B2R_OK;
 }
 

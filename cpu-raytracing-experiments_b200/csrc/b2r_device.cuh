@@ -629,8 +629,10 @@ struct SmemStack {
 constexpr int kPacketStack = 64;
 template <bool COUNT>
 __global__ void __launch_bounds__(kTravBlock) k_intersect_packet(const Params p, const uint32_t bounce) {
-	const uint32_t n_in = p.cnt.paths[bounce];   // a multiple of 256: whole tiles of whole samples
-	const int side = bounce & 1;
+	// The camera rays are GENERATED here (Renderer.hpp:97-127: hash_2d -> PCG -> Camera::generate_ray, in registers) and their path
+	// records and zeroed radiance entries written behind the walk (plain coalesced stores that nobody waits for) for k_shade to read:
+	// there is no separate ray-generation launch and no read-back of 32 B per ray in front of the traversal.
+	const uint32_t n_in = p.batch->n_slots * p.frame.npix;   // a multiple of 256: whole tiles of whole samples
 	const float4* __restrict__ wide4 = reinterpret_cast<const float4*>(p.scene.wide);
 	__shared__ uint2 s_pstack[kTravBlock / 32][kPacketStack];
 	uint2* stack = s_pstack[threadIdx.x >> 5];
@@ -645,8 +647,10 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_packet(const Params p,
 			next = b; end = min(b + 128u, n_in);
 		}
 		const uint32_t idx = next + lane_id(); next += 32u;
-		const float4 ra = p.q.A[side][idx], rb = p.q.B[side][idx];
-		const float ox = ra.x, oy = ra.y, oz = ra.z, dx = ra.w, dy = rb.x, dz = rb.y;
+		const uint32_t sl = div_by(idx, p.frame.npix, p.frame.npix_magic);
+		const PathState s0 = primary_path(p.frame, p.batch->cam, p.batch->acc[sl], sl, idx - sl * p.frame.npix);
+		store_path(p.q, 0, idx, s0); rad_zero(p.rad, p.frame.npix, s0.pid);
+		const float ox = s0.ox, oy = s0.oy, oz = s0.oz, dx = s0.dx, dy = s0.dy, dz = s0.dz;
 		const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
 		const float nx = -(ox * ix), ny = -(oy * iy), nz = -(oz * iz), ax = fabsf(ix), ay = fabsf(iy), az = fabsf(iz);
 		float best = FLT_MAX; int32_t prim = -1;
@@ -690,7 +694,7 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_packet(const Params p,
 		}
 		p.q.H[idx] = make_float2(best, __int_as_float(prim));
 	}
-	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.cnt.stats + ST_EXT, static_cast<unsigned long long>(n_in));
+	if (blockIdx.x == 0 && threadIdx.x == 0) { p.cnt.paths[0] = n_in; atomicAdd(p.cnt.stats + ST_EXT, static_cast<unsigned long long>(n_in)); }
 	if (COUNT) { stat_add(p.cnt.stats, ST_SPHERE, c_sphere); stat_add(p.cnt.stats, ST_BOX, c_box); }
 }
 
