@@ -20,10 +20,21 @@ int fail(int code, const std::string& what) { g_error = what; return code; }
 
 enum KernelKind { KK_GENERATE = 0, KK_BRUTE, KK_CLOSEST, KK_SHADE, KK_SHADOW, KK_ACCUMULATE, KK_RESOLVE, KK_COUNT };
 
-struct BatchArgs { uint32_t n; uint32_t acc[kMaxSlots]; unsigned long long fold = ~0ull; CameraParams cam; };
+struct BatchArgs {
+	uint32_t n; uint32_t acc[kMaxSlots]; unsigned long long fold = ~0ull; CameraParams cam;
+	uint32_t n_a = 0, off_b = 0;  // twin lanes (run_batch): slots [0, n_a) are lane A's samples, slots [off_b, n) lane B's, the slots between hold nothing
+	uint32_t slot_of(uint32_t i) const { return n_a == 0u || i < n_a ? i : off_b + (i - n_a); }  // slot of the i-th sample of the batch
+};
+// dst[0] describes the whole batch (k_accumulate), dst[1] / dst[2] the two lanes' halves (slot numbers local to the lane)
 __global__ void k_set_batch(BatchDev* dst, const BatchArgs a) {
-	if (threadIdx.x == 0) { dst->n_slots = a.n; dst->fold = a.fold; dst->cam = a.cam; }
-	if (threadIdx.x < a.n) dst->acc[threadIdx.x] = a.acc[threadIdx.x];
+	if (threadIdx.x == 0) {
+		dst[0].n_slots = a.n; dst[0].fold = a.fold; dst[0].cam = a.cam;
+		dst[1].n_slots = a.n_a; dst[1].fold = 0ull; dst[1].cam = a.cam;
+		dst[2].n_slots = a.n_a ? a.n - a.off_b : 0u; dst[2].fold = 0ull; dst[2].cam = a.cam;
+	}
+	if (threadIdx.x < a.n) dst[0].acc[threadIdx.x] = a.acc[threadIdx.x];
+	if (threadIdx.x < a.n_a) dst[1].acc[threadIdx.x] = a.acc[threadIdx.x];
+	if (a.n_a && a.off_b + threadIdx.x < a.n) dst[2].acc[threadIdx.x] = a.acc[a.off_b + threadIdx.x];
 }
 
 template <typename T> int dev_alloc(T** p, size_t count) {
@@ -76,7 +87,8 @@ struct b2r_ctx {
 	float4 *d_A[2] = {nullptr, nullptr}, *d_B[2] = {nullptr, nullptr}, *d_SA = nullptr, *d_SB = nullptr, *d_fb = nullptr;
 	float *d_T[2] = {nullptr, nullptr}, *d_SL = nullptr, *d_rad = nullptr, *d_acc = nullptr;
 	uint8_t *d_ex_slot[2] = {nullptr, nullptr}, *d_ex_key = nullptr; uint16_t* d_ex_act[2] = {nullptr, nullptr}; uint32_t* d_ex_next = nullptr;  // B2R_FLAG_REFERENCE_EXACT
-	float2* d_H = nullptr;
+	float2* d_H = nullptr; uint32_t* d_SS = nullptr;
+	uint32_t *d_parent = nullptr, *d_leaf_node = nullptr; size_t cap_parent = 0, cap_leaf_node = 0;  // k_link_tables
 	uint32_t* d_counts = nullptr; size_t counts_bytes = 0;
 	unsigned long long* d_stats = nullptr;
 	BatchDev* d_batch = nullptr;
@@ -85,6 +97,11 @@ struct b2r_ctx {
 	int grid_brute_first_exact = 0, grid_brute_exact = 0;
 	int grid_brute_first = 0, grid_brute = 0, grid_closest = 0, grid_shade = 0, grid_shadow = 0, grid_stream = 0, grid_packet = 0, grid_brute_finish = 0; bool packet_primary = true;
 	cudaGraphExec_t graph_exec = nullptr; bool graph_valid = false;
+	// twin lanes: a batch of two or more samples is traced as two independent half batches on two streams (own queues, counters and batch
+	// descriptors) inside one graph, so that the drained end of every launch of one half is filled by the other half's kernels
+	cudaGraphExec_t twin_exec = nullptr; bool twin_valid = false, twin_enabled = true;
+	cudaStream_t lane_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+	uint64_t graph_launches = 0, twin_launches = 0;  // kernels one replay of each graph launches (counted while capturing)
 	uint64_t launches = 0;
 	// profiling (B2R_FLAG_NO_GRAPH): events around every launch
 	struct Timed { int kind; cudaEvent_t a, b; };
@@ -95,7 +112,7 @@ struct b2r_ctx {
 	// team mode (b2r_team_*): peers' bucket arrays, rank 0's framebuffer and every rank's TeamSync block, mapped through CUDA IPC
 	// samples traced ahead of the caller: an application that calls Accumulate() once per frame (Application.cpp:379) gets wavefront
 	// batches of 2, 4, ... kSpecMax samples as long as nothing invalidates them; the extra samples wait in RAD and are folded by later calls
-	uint32_t spec_width = 1, spec_first = 0, spec_count = 0, spec_used = 0; BatchArgs spec_args;
+	uint32_t spec_width = 1, spec_first = 0, spec_count = 0, spec_used = 0; BatchArgs spec_args;  // (spec_args in the slot layout run_batch gave it)
 	TeamSync* d_team = nullptr; std::vector<void*> team_acc, team_sync; void* team_fb0 = nullptr; uint32_t team_rank = 0, team_frame = 0; bool team_wait_done = false;
 };
 
@@ -109,8 +126,10 @@ void drop_speculation(b2r_ctx* c) { c->spec_count = 0; c->spec_used = 0; c->spec
 
 void drop_graph(b2r_ctx* c) {
 	drop_speculation(c);  // everything that invalidates the captured graph (camera, scene pointers, flags, frame size) invalidates them too
-	if (c->graph_exec) { if (c->stream) cudaStreamSynchronize(c->stream); cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }  // (a launch of it may still be running)
-	c->graph_valid = false;
+	if (c->graph_exec || c->twin_exec) { if (c->stream) cudaStreamSynchronize(c->stream); }  // (a launch of it may still be running)
+	if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+	if (c->twin_exec) { cudaGraphExecDestroy(c->twin_exec); c->twin_exec = nullptr; }
+	c->graph_valid = false; c->twin_valid = false;
 }
 
 int alloc_frame(b2r_ctx* c) {
@@ -130,13 +149,15 @@ int alloc_frame(b2r_ctx* c) {
 	if ((rc = dev_alloc(&c->d_SA, cap))) return rc;
 	if ((rc = dev_alloc(&c->d_SB, cap))) return rc;
 	if ((rc = dev_alloc(&c->d_SL, 3 * cap))) return rc;
+	if ((rc = dev_alloc(&c->d_SS, cap))) return rc;
 	if ((rc = dev_alloc(&c->d_rad, 3 * cap))) return rc;
 	if ((rc = dev_alloc(&c->d_acc, static_cast<size_t>(K) * 3 * npix))) return rc;
 	if ((rc = dev_alloc(&c->d_fb, static_cast<size_t>(npix)))) return rc;
 	c->counts_bytes = (static_cast<size_t>(mb) + 1) * 4 * sizeof(uint32_t);
-	if ((rc = dev_alloc(&c->d_counts, (static_cast<size_t>(mb) + 1) * 4))) return rc;
+	if ((rc = dev_alloc(&c->d_counts, (static_cast<size_t>(mb) + 1) * 4 * 2))) return rc;  // second block: lane B of a twin batch
+	CU(cudaMemset(c->d_counts, 0, 2 * c->counts_bytes));
 	if (!c->d_stats) { if ((rc = dev_alloc(&c->d_stats, static_cast<size_t>(ST_COUNT)))) return rc; CU(cudaMemset(c->d_stats, 0, ST_COUNT * sizeof(unsigned long long))); }
-	if (!c->d_batch) { if ((rc = dev_alloc(&c->d_batch, static_cast<size_t>(1)))) return rc; }
+	if (!c->d_batch) { if ((rc = dev_alloc(&c->d_batch, static_cast<size_t>(3)))) return rc; }  // whole batch, lane A, lane B
 	if (c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) {
 		for (int s = 0; s < 2; s++) { if ((rc = dev_alloc(&c->d_ex_slot[s], cap))) return rc; if ((rc = dev_alloc(&c->d_ex_act[s], cap / 256))) return rc; }
 		if ((rc = dev_alloc(&c->d_ex_key, cap))) return rc;
@@ -155,7 +176,7 @@ int alloc_frame(b2r_ctx* c) {
 		p.frame.finish_first = f ? static_cast<uint32_t>(std::strtoul(f, nullptr, 10)) : 2u;
 	}
 	for (int s = 0; s < 2; s++) { p.q.A[s] = c->d_A[s]; p.q.B[s] = c->d_B[s]; p.q.T[s] = c->d_T[s]; }
-	p.q.H = c->d_H; p.q.SA = c->d_SA; p.q.SB = c->d_SB; p.q.SL = c->d_SL; p.q.cap = static_cast<uint32_t>(cap);
+	p.q.H = c->d_H; p.q.SA = c->d_SA; p.q.SB = c->d_SB; p.q.SL = c->d_SL; p.q.SS = c->d_SS; p.q.cap = static_cast<uint32_t>(cap);
 	p.cnt.paths = c->d_counts; p.cnt.shadow = c->d_counts + (mb + 1); p.cnt.work_a = c->d_counts + 2 * (mb + 1); p.cnt.work_b = c->d_counts + 3 * (mb + 1);
 	p.cnt.stats = c->d_stats;
 	p.batch = c->d_batch; p.rad = c->d_rad; p.acc = c->d_acc;
@@ -182,6 +203,7 @@ int compute_grids(b2r_ctx* c) {
 	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_packet<false>), kTravBlock, &c->grid_packet))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_brute_finish<false>), kBruteBlock, &c->grid_brute_finish))) return rc;
 	c->packet_primary = std::getenv("B2R_NO_PACKET") == nullptr;  // A/B switch for measurements: per-lane walks for the camera rays too
+	c->twin_enabled = std::getenv("B2R_NO_TWIN") == nullptr;      // A/B switch for measurements: every batch as one lane
 	c->grid_stream = c->sm_count * 8;
 	return B2R_OK;
 }
@@ -197,19 +219,17 @@ template <typename F> int launch(b2r_ctx* c, int kind, bool profile, F&& f) {
 	return B2R_OK;
 }
 
-// Enqueue one wavefront batch (everything after k_set_batch): counters reset, max_bounces rounds, fold into buckets.
-int enqueue_batch(b2r_ctx* c, bool profile) {
-	const Params& p = c->params;
+// The max_bounces rounds of one batch — or of one lane's half of it — on stream st; p carries that batch's queues, counters and descriptor.
+int enqueue_rounds(b2r_ctx* c, const Params& p_in, cudaStream_t st, bool profile) {
+	const Params& p = p_in;
 	const bool count = (c->cfg.flags & B2R_FLAG_COUNT_TESTS) != 0;
 	const uint32_t mb = c->cfg.max_bounces;
-	cudaStream_t st = c->stream;
-	CU(cudaMemsetAsync(c->d_counts, 0, c->counts_bytes, st));
 	int rc;
 	if (!c->use_bvh) {
 		const bool exact = (c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) != 0;
 		if (exact && c->params.scene.n_mat > 64) return fail(B2R_ERR_STATE, "B2R_FLAG_REFERENCE_EXACT: at most 64 materials (RendererPolicy::max_materialID, Renderer.hpp:23)");
 		const bool finish = !exact && c->params.frame.finish_below != 0u && c->params.scene.n_prims <= static_cast<uint32_t>(kBruteTile);
-		Params p = c->params;  // (shadows the reference above) the hand-over threshold only reaches the kernels when k_brute_finish is launched too
+		Params p = p_in;  // (shadows the reference above) the hand-over threshold only reaches the kernels when k_brute_finish is launched too
 		if (!finish) p.frame.finish_below = 0u;
 		for (uint32_t b = 0; b < mb; b++) {
 			if (finish && b >= p.frame.finish_first && b + 1 < mb) {  // takes the remaining paths over once few enough are left (a no-op launch otherwise)
@@ -252,34 +272,82 @@ int enqueue_batch(b2r_ctx* c, bool profile) {
 			}
 		}
 	}
-	return launch(c, KK_ACCUMULATE, profile, [&] { k_accumulate<<<c->grid_stream, kBlock, 0, st>>>(p); });
+	return B2R_OK;
 }
 
+// Lane `which` (0 = A, 1 = B) of a twin batch: its own part of every queue array (A the first ceil(slots/2) samples' worth, B the rest),
+// its own counter block and batch descriptor, and its own part of RAD — lane B's local slot s is slot ceil(slots/2) + s of the whole
+// batch, which is how k_accumulate (whole-batch descriptor) finds it.
+Params lane_params(const b2r_ctx* c, int which) {
+	Params p = c->params;
+	const size_t npix = p.frame.npix, cap_a = static_cast<size_t>((c->slots + 1u) / 2u) * npix, cap_b = static_cast<size_t>(c->slots / 2u) * npix;
+	const size_t off = which ? cap_a : 0, cap = which ? cap_b : cap_a;
+	for (int s = 0; s < 2; s++) { p.q.A[s] += off; p.q.B[s] += off; p.q.T[s] += 3 * off; }
+	p.q.H += off; p.q.SA += off; p.q.SB += off; p.q.SL += 3 * off; p.q.SS += off; p.q.cap = static_cast<uint32_t>(cap);
+	const uint32_t block = (c->cfg.max_bounces + 1u) * 4u;
+	p.cnt.paths += which * block; p.cnt.shadow += which * block; p.cnt.work_a += which * block; p.cnt.work_b += which * block;
+	p.batch = c->d_batch + 1 + which;
+	p.rad += 3 * off;
+	return p;
+}
+
+// Enqueue one wavefront batch (everything after k_set_batch): counters reset, max_bounces rounds, fold into buckets.
+int enqueue_batch(b2r_ctx* c, bool profile, bool twin) {
+	cudaStream_t st = c->stream;
+	CU(cudaMemsetAsync(c->d_counts, 0, 2 * c->counts_bytes, st));
+	int rc;
+	if (!twin) { if ((rc = enqueue_rounds(c, c->params, st, profile))) return rc; }
+	else {
+		// fork: lane B's rounds on the second stream, lane A's on the main one; join before the fold (which adds in sample order over both)
+		CU(cudaEventRecord(c->ev_fork, st)); CU(cudaStreamWaitEvent(c->lane_stream, c->ev_fork, 0));
+		if ((rc = enqueue_rounds(c, lane_params(c, 0), st, false))) return rc;
+		if ((rc = enqueue_rounds(c, lane_params(c, 1), c->lane_stream, false))) return rc;
+		CU(cudaEventRecord(c->ev_join, c->lane_stream)); CU(cudaStreamWaitEvent(st, c->ev_join, 0));
+	}
+	return launch(c, KK_ACCUMULATE, profile, [&] { k_accumulate<<<c->grid_stream, kBlock, 0, st>>>(c->params); });
+}
+
+// One wavefront batch of args.n samples (args.acc[0..n) in sample order). Two or more samples are traced as twin lanes: run_batch moves
+// the second half of the samples to the slots lane B owns and leaves args in that layout (the caller may keep it: samples traced ahead).
 int run_batch(b2r_ctx* c, BatchArgs& args) {
 	const bool no_graph = (c->cfg.flags & B2R_FLAG_NO_GRAPH) != 0;
+	const bool twin = c->twin_enabled && !no_graph && args.n >= 2u && c->slots >= 2u && !(c->cfg.flags & B2R_FLAG_REFERENCE_EXACT);
+	if (twin) {
+		const uint32_t n = args.n, n_a = (n + 1u) / 2u, off_b = (c->slots + 1u) / 2u;
+		unsigned long long fold = 0ull;
+		for (uint32_t i = n; i-- > n_a;) { args.acc[off_b + (i - n_a)] = args.acc[i]; }   // (highest first: the ranges may overlap)
+		for (uint32_t i = 0; i < n; i++) if ((args.fold >> i) & 1ull) fold |= 1ull << (i < n_a ? i : off_b + (i - n_a));
+		for (uint32_t s = n_a; s < off_b; s++) args.acc[s] = 0u;
+		args.n_a = n_a; args.off_b = off_b; args.n = off_b + (n - n_a); args.fold = fold;
+	} else { args.n_a = 0; args.off_b = 0; if (args.n < 64u) args.fold &= (1ull << args.n) - 1ull; }
 	args.cam = c->params.frame.cam;  // the camera travels with the batch descriptor: a camera move leaves the captured graph alone
 	k_set_batch<<<1, kMaxSlots, 0, c->stream>>>(c->d_batch, args);
 	CU(cudaGetLastError());
-	if (no_graph) return enqueue_batch(c, true);
-	if (!c->graph_valid) {
-		drop_graph(c);
+	if (no_graph) return enqueue_batch(c, true, false);
+	cudaGraphExec_t& exec = twin ? c->twin_exec : c->graph_exec;
+	bool& valid = twin ? c->twin_valid : c->graph_valid;
+	uint64_t& per_replay = twin ? c->twin_launches : c->graph_launches;
+	if (!valid) {
+		if (exec) { CU(cudaStreamSynchronize(c->stream)); cudaGraphExecDestroy(exec); exec = nullptr; }
+		if (twin && !c->lane_stream) {
+			CU(cudaStreamCreateWithFlags(&c->lane_stream, cudaStreamNonBlocking));
+			CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+		}
 		cudaGraph_t graph = nullptr;
 		const uint64_t before = c->launches;
 		CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-		int rc = enqueue_batch(c, false);
+		int rc = enqueue_batch(c, false, twin);
 		cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
-		c->launches = before;
+		per_replay = c->launches - before; c->launches = before;
 		if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
 		if (e != cudaSuccess) return fail(B2R_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-		e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+		e = cudaGraphInstantiate(&exec, graph, 0);
 		cudaGraphDestroy(graph);
 		if (e != cudaSuccess) return fail(B2R_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
-		c->graph_valid = true;
+		valid = true;
 	}
-	CU(cudaGraphLaunch(c->graph_exec, c->stream));
-	const uint32_t mb = c->cfg.max_bounces;
-	const bool mis = !(c->cfg.flags & B2R_FLAG_NO_MIS);
-	c->launches += (c->use_bvh ? (c->packet_primary ? 1 : 2) + static_cast<uint64_t>(mb) * 2 + (mis ? mb - 1 : 0) : static_cast<uint64_t>(mb) + 1 + ((c->params.frame.finish_below && !(c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) && c->params.scene.n_prims <= static_cast<uint32_t>(kBruteTile) && mb > c->params.frame.finish_first + 1u) ? mb - 1u - c->params.frame.finish_first : 0u)) + ((c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) ? mb - 1 : 0);
+	CU(cudaGraphLaunch(exec, c->stream));
+	c->launches += per_replay;
 	return B2R_OK;
 }
 
@@ -312,6 +380,12 @@ int launch_refit_levels(b2r_ctx* c, const uint32_t* d_remap) {
 		c->launches++;
 	}
 	CU(cudaGetLastError());
+	return B2R_OK;
+}
+// parent[] / leaf_node[] of the device tree (where k_intersect_shadow starts and how it climbs), read off the tree itself
+int launch_link_tables(b2r_ctx* c) {
+	k_link_tables<<<(c->n_wide * 4u + kBlock - 1u) / kBlock, kBlock, 0, c->stream>>>(reinterpret_cast<const float4*>(c->d_wide), c->n_wide, c->d_parent, c->d_leaf_node);
+	CU(cudaGetLastError()); c->launches++;
 	return B2R_OK;
 }
 // Ray origins about to be used (camera position, caller-supplied rays) must lie in the origin box the leaf extents were computed for;
@@ -375,13 +449,14 @@ void b2r_destroy(b2r_ctx* c) {
 	dev_free(&c->d_hdri); dev_free(&c->d_prim_mat); dev_free(&c->d_wide); dev_free(&c->d_cost); dev_free(&c->d_remap); dev_free(&c->d_trace); dev_free(&c->d_cost_base); dev_free(&c->d_sort_tmp);
 	for (int k = 0; k < 2; k++) { dev_free(&c->d_mkey[k]); dev_free(&c->d_midx[k]); }
 	for (int s = 0; s < 2; s++) { dev_free(&c->d_A[s]); dev_free(&c->d_B[s]); dev_free(&c->d_T[s]); }
-	dev_free(&c->d_H); dev_free(&c->d_SA); dev_free(&c->d_SB); dev_free(&c->d_SL); dev_free(&c->d_rad); dev_free(&c->d_acc); dev_free(&c->d_fb);
+	dev_free(&c->d_H); dev_free(&c->d_SA); dev_free(&c->d_SB); dev_free(&c->d_SL); dev_free(&c->d_SS); dev_free(&c->d_parent); dev_free(&c->d_leaf_node); dev_free(&c->d_rad); dev_free(&c->d_acc); dev_free(&c->d_fb);
 	for (int s = 0; s < 2; s++) { dev_free(&c->d_ex_slot[s]); dev_free(&c->d_ex_act[s]); }
 	dev_free(&c->d_ex_key); dev_free(&c->d_ex_next);
 	dev_free(&c->d_counts); dev_free(&c->d_stats); dev_free(&c->d_batch);
 	if (c->h_stage) cudaFreeHost(c->h_stage);
 	if (c->ev_stage) cudaEventDestroy(c->ev_stage);
 	if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); cudaEventDestroy(c->ev_resolved); cudaEventDestroy(c->ev_copied); }
+	if (c->lane_stream) { cudaStreamDestroy(c->lane_stream); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
 	delete c;
 }
@@ -533,7 +608,7 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 	PackedScene ps; pack_scene(prims, n_prims, materials, n_mat, light_geom_idx, n_lights, geometry, ps);
 	auto &h_prims = ps.prims, &h_alb = ps.mat_albedo, &h_em = ps.mat_emission, &h_ls = ps.light_sphere, &h_le = ps.light_emit; auto& h_pm = ps.prim_mat;
 	const bool grow = h_prims.size() > c->cap_prims || h_pm.size() > c->cap_prim_mat || h_alb.size() > c->cap_mat_albedo || h_em.size() > c->cap_mat_emission ||
-	                  h_ls.size() > c->cap_light_sphere || h_le.size() > c->cap_light_emit || c->n_wide > c->cap_wide ||
+	                  h_ls.size() > c->cap_light_sphere || h_le.size() > c->cap_light_emit || c->n_wide > c->cap_wide || c->n_wide > c->cap_parent || n_prims > c->cap_leaf_node ||
 	                  (has_ambient && static_cast<size_t>(hdri_w) * hdri_h > c->cap_hdri);
 	if (grow) CU(cudaStreamSynchronize(c->stream));  // device arrays in use are about to be replaced (first upload, or a larger scene)
 	if ((rc = dev_reserve(&c->d_prims, &c->cap_prims, h_prims.size()))) return rc;
@@ -543,6 +618,8 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 	if ((rc = dev_reserve(&c->d_light_sphere, &c->cap_light_sphere, h_ls.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_light_emit, &c->cap_light_emit, h_le.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_wide, &c->cap_wide, static_cast<size_t>(c->n_wide)))) return rc;
+	if ((rc = dev_reserve(&c->d_parent, &c->cap_parent, static_cast<size_t>(c->n_wide)))) return rc;
+	if ((rc = dev_reserve(&c->d_leaf_node, &c->cap_leaf_node, static_cast<size_t>(n_prims)))) return rc;
 	const size_t texels = has_ambient ? static_cast<size_t>(hdri_w) * hdri_h : 0;
 	if (has_ambient && (rc = dev_reserve(&c->d_hdri, &c->cap_hdri, texels))) return rc;
 	const UploadPart parts[] = {
@@ -573,10 +650,12 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 		c->launches++;
 		c->wide_refit = true;  // the device holds the only copy of this tree
 	}
+	if ((rc = launch_link_tables(c))) return rc;
 	const SceneDev before = c->params.scene; const bool bvh_before = c->use_bvh;
 	SceneDev& s = c->params.scene;
 	s.prims = c->d_prims; s.prim_mat = c->d_prim_mat; s.mat_albedo = c->d_mat_albedo; s.mat_emission = c->d_mat_emission;
 	s.light_sphere = c->d_light_sphere; s.light_emit = c->d_light_emit; s.wide = c->d_wide; s.hdri = has_ambient ? c->d_hdri : nullptr;
+	s.parent = c->d_parent; s.leaf_node = c->d_leaf_node;
 	s.n_prims = n_prims; s.n_mat = n_mat; s.n_lights = n_lights; s.stack_tn_bits = c->wide_host.tn_bits;
 	s.light_sel_pdf = n_lights ? 1.0f / static_cast<float>(n_lights) : 0.0f;  // Renderer.hpp:78 (no lights: Q15, light sampling is skipped and the MIS weight of an emissive hit is 1)
 	s.ambient[0] = amb[0]; s.ambient[1] = amb[1]; s.ambient[2] = amb[2]; s.has_ambient = has_ambient ? 1 : 0;
@@ -645,6 +724,7 @@ int b2r_refit_scene(b2r_ctx* c, const b2r_sphere* prims, uint32_t n_prims, const
 		}
 	}
 	if ((rc = launch_refit_levels(c, same_order ? nullptr : c->d_remap))) return rc;
+	if (!same_order && (rc = launch_link_tables(c))) return rc;  // leaves were re-linked into the new BVH order
 	c->wide_refit = true; drop_speculation(c);
 	const SceneDev before = c->params.scene;
 	SceneDev& s = c->params.scene;
@@ -691,7 +771,7 @@ int b2r_accumulate(b2r_ctx* c, uint32_t n_samples) {
 		if (c->spec_used < c->spec_count && acc == c->spec_first + c->spec_used) {
 			// traced ahead by an earlier call: fold it (samples are folded in index order: earlier samples of this call go first)
 			if (args.n) { if ((rc = run_batch(c, args))) return rc; args.n = 0; }
-			BatchArgs f = c->spec_args; f.fold = 1ull << c->spec_used;
+			BatchArgs f = c->spec_args; f.fold = 1ull << f.slot_of(c->spec_used);
 			k_set_batch<<<1, kMaxSlots, 0, c->stream>>>(c->d_batch, f);
 			k_accumulate<<<c->grid_stream, kBlock, 0, c->stream>>>(c->params);
 			CU(cudaGetLastError()); c->launches += 1;
@@ -1013,10 +1093,11 @@ int b2r_read_bounce_counts(b2r_ctx* c, uint32_t* paths_out, uint32_t* shadow_out
 	if (!c || !paths_out || !shadow_out) return fail(B2R_ERR_ARG, "null argument");
 	int rc = ensure_device(c); if (rc) return rc;
 	const uint32_t mb = c->cfg.max_bounces;
-	std::vector<uint32_t> h((static_cast<size_t>(mb) + 1) * 4);
-	CU(cudaMemcpyAsync(h.data(), c->d_counts, c->counts_bytes, cudaMemcpyDeviceToHost, c->stream));
+	const size_t block = (static_cast<size_t>(mb) + 1) * 4;
+	std::vector<uint32_t> h(block * 2);  // the last batch's counters: one block per lane (lane B's stays zero when the batch ran as one lane)
+	CU(cudaMemcpyAsync(h.data(), c->d_counts, 2 * c->counts_bytes, cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
-	for (uint32_t b = 0; b < n; b++) { paths_out[b] = b <= mb ? h[b] : 0u; shadow_out[b] = b < mb ? h[mb + 1 + b] : 0u; }
+	for (uint32_t b = 0; b < n; b++) { paths_out[b] = b <= mb ? h[b] + h[block + b] : 0u; shadow_out[b] = b < mb ? h[mb + 1 + b] + h[block + mb + 1 + b] : 0u; }
 	return collect_timings(c);
 }
 int b2r_reset_counters(b2r_ctx* c) {

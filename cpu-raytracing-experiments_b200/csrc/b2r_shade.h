@@ -38,6 +38,8 @@ struct SceneDev {
 	const float4* light_sphere; // [n_lights] scene.geometry[light] {c.xyz, r^2}   (Renderer.hpp:261-262)
 	const float4* light_emit;   // [n_lights] {emission.rgb of its material, as_float(light_primID)}
 	const WideNode* wide;       // flattened BVH
+	const uint32_t* parent;     // [n_wide] the wide node that links to node i (the root's entry is 0)      } written by k_link_tables from the device tree itself;
+	const uint32_t* leaf_node;  // [n_prims] the wide node that holds sphere i (BVH order) in a leaf slot       } k_intersect_shadow starts its walks there
 	const float4* hdri;         // equirect RGBA32F or null
 	uint32_t n_prims, n_mat, n_lights;
 	uint32_t stack_tn_bits;     // traversal stack entry split (WideBvh::tn_bits)
@@ -74,6 +76,7 @@ struct QueueDev {
 	float4* A[2]; float4* B[2]; float* T[2];
 	float2* H;
 	float4* SA; float4* SB; float* SL;
+	uint32_t* SS;            // [cap] the wide node a shadow ray's walk starts at (the node holding the sphere it leaves from)
 	uint32_t cap;
 };
 struct CountDev {            // zeroed at the start of every batch; index = bounce

@@ -319,6 +319,60 @@ extern "C" int hc_anyhit_stats(const b2r_sphere* prims, uint32_t n_prims, const 
 	return bad;
 }
 
+// any-hit traversal started BELOW the root (tuning aid): a shadow ray leaves a point on sphere `origin_prim`, and in a dense scene its
+// occluder is usually a neighbour, so the walk starts at the ancestor `height` levels above the node that holds the origin sphere's leaf
+// slot and only falls back to the root (skipping the subtree already searched) when that subtree holds no occluder. The result is the same
+// order-independent boolean. steps_root = visits of the walk from the root (nearest hit child first), steps_local = visits of the two-phase walk.
+extern "C" int hc_anyhit_local_stats(const b2r_sphere* prims, uint32_t n_prims, const float* rays, const float* tfar, const int32_t* origin_prim, uint32_t n, uint32_t height,
+                                     uint32_t* steps_root, uint32_t* steps_local, uint8_t* found_local) {
+	float ro[6]; ray_origin_bounds(rays, n, ro);
+	const OriginBox ob = origin_box_of(prims, n_prims, nullptr, ro, 2);
+	std::vector<b2r_bvh_node> tn; build_traversal_tree(prims, n_prims, tn);
+	WideBvh w; flatten_bvh(tn.data(), static_cast<uint32_t>(tn.size()), prims, n_prims, w, &ob);
+	const float4* wide = reinterpret_cast<const float4*>(w.nodes.data());
+	const uint32_t nn = static_cast<uint32_t>(w.nodes.size());
+	std::vector<uint32_t> parent(nn, 0u), leaf_node(n_prims, 0u);
+	for (uint32_t nd = 0; nd < nn; nd++) for (int k = 0; k < 4; k++) { const int32_t l = as_int(wide[static_cast<size_t>(nd) * 8 + 2 * k + 1].z); if (l == kEmptyLink) continue; if (l < 0) leaf_node[~l] = nd; else parent[l] = nd; }
+	int bad = 0;
+	for (uint32_t i = 0; i < n; i++) {
+		const float* r = rays + 6 * static_cast<size_t>(i);
+		TravBase t; t.arm(Ray{r[0], r[1], r[2], r[3], r[4], r[5]});
+		uint32_t start = leaf_node[origin_prim[i]]; for (uint32_t h = 0; h < height; h++) start = parent[start];
+		auto walk = [&](uint32_t from, uint32_t skip, uint32_t* steps) {
+			std::vector<uint32_t> stack; uint32_t node = from; bool have = true, occ = false;
+			while (have && !occ) {
+				(*steps)++;
+				const float4* nd = wide + static_cast<size_t>(node) * 8;
+				uint32_t hit[4]; float htn[4]; int nh = 0;
+				for (int k = 0; k < 4 && !occ; k++) {
+					const float4 a = nd[2 * k], b = nd[2 * k + 1]; const int32_t l = as_int(b.z);
+					float tnr; bool h; slab(a, b, t.ix, t.iy, t.iz, t.nx, t.ny, t.nz, t.ax, t.ay, t.az, tfar[i], &tnr, &h);
+					if (!h) continue;
+					if (l < 0) { if (sphere_hit_any(a.x, a.y, a.z, a.w, t.ox, t.oy, t.oz, t.dx, t.dy, t.dz, tfar[i])) occ = true; }
+					else if (static_cast<uint32_t>(l) != skip) { hit[nh] = static_cast<uint32_t>(l); htn[nh] = tnr; nh++; }
+				}
+				if (occ) break;
+				if (nh > 1) { int m = 0; for (int k = 1; k < nh; k++) if (htn[k] < htn[m]) m = k; std::swap(hit[0], hit[m]); std::swap(htn[0], htn[m]); }
+				for (int k = nh - 1; k >= 1; k--) stack.push_back(hit[k]);
+				if (nh) node = hit[0]; else if (!stack.empty()) { node = stack.back(); stack.pop_back(); } else have = false;
+			}
+			return occ;
+		};
+		uint32_t sr = 0, sl = 0;
+		const bool occ_root = walk(0u, 0xffffffffu, &sr);
+		bool occ_local = walk(start, 0xffffffffu, &sl);
+		found_local[i] = occ_local ? 1 : 0;
+		if (std::getenv("HC_CLIMB")) {  // instead of restarting at the root: climb one level at a time, searching the siblings not yet searched
+			uint32_t cur = start;
+			while (!occ_local && cur != 0u) { const uint32_t up = parent[cur]; occ_local = walk(up, cur, &sl); cur = up; }
+		} else
+		if (!occ_local && start != 0u) occ_local = walk(0u, start, &sl);
+		if (occ_root != occ_local) bad++;
+		steps_root[i] = sr; steps_local[i] = sl;
+	}
+	return bad;
+}
+
 // closest-hit traversal statistics for push-order policies (tuning aid): mode 0 = the kernels' order (all hit children sorted by entry
 // distance), 1 = nearest child next, the others pushed in slot order, 2 = nearest next, the others pushed farthest-slot-first by a single
 // compare of the two remaining... Returns mismatching rays against mode 0 (must be 0); steps_out[mode][ray].
