@@ -68,10 +68,10 @@ struct b2r_ctx {
 	uint32_t slots = 8;
 	int sm_count = 0;
 	// scene
-	float4 *d_prims = nullptr, *d_mat_albedo = nullptr, *d_mat_emission = nullptr, *d_light_sphere = nullptr, *d_light_emit = nullptr, *d_hdri = nullptr;
+	float4 *d_prims = nullptr, *d_mat_albedo = nullptr, *d_mat_emission = nullptr, *d_mat_f0 = nullptr, *d_light_sphere = nullptr, *d_light_emit = nullptr, *d_hdri = nullptr;
 	int32_t* d_prim_mat = nullptr;
 	WideNode* d_wide = nullptr;
-	size_t cap_prims = 0, cap_prim_mat = 0, cap_mat_albedo = 0, cap_mat_emission = 0, cap_light_sphere = 0, cap_light_emit = 0, cap_wide = 0, cap_hdri = 0;
+	size_t cap_prims = 0, cap_prim_mat = 0, cap_mat_albedo = 0, cap_mat_emission = 0, cap_mat_f0 = 0, cap_light_sphere = 0, cap_light_emit = 0, cap_wide = 0, cap_hdri = 0;
 	WideBvh wide_host; uint64_t wide_key = 0; std::vector<unsigned char> wide_blob; bool have_wide = false;
 	uint32_t n_wide = 0;  // wide nodes of the current tree
 	// B2R_FLAG_GPU_TREE: the tree was built on the device (no host copy of its nodes); sort scratch; the arrays a later refit needs to match
@@ -95,6 +95,7 @@ struct b2r_ctx {
 	Params params{};
 	// launch
 	int grid_brute_first_exact = 0, grid_brute_exact = 0;
+	int grid_brute_first_ggx = 0, grid_brute_ggx = 0, grid_brute_finish_ggx = 0, grid_shade_ggx = 0;
 	int grid_brute_first = 0, grid_brute = 0, grid_closest = 0, grid_shade = 0, grid_shadow = 0, grid_stream = 0, grid_packet = 0, grid_brute_finish = 0; bool packet_primary = true;
 	cudaGraphExec_t graph_exec = nullptr; bool graph_valid = false;
 	// twin lanes: a batch of two or more samples is traced as two independent half batches on two streams (own queues, counters and batch
@@ -202,6 +203,10 @@ int compute_grids(b2r_ctx* c) {
 	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_shadow<false>), kTravBlock, &c->grid_shadow))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_packet<false>), kTravBlock, &c->grid_packet))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_brute_finish<false>), kBruteBlock, &c->grid_brute_finish))) return rc;
+	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<true, false, false, true>), kBruteBlock, &c->grid_brute_first_ggx))) return rc;
+	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<false, false, false, true>), kBruteBlock, &c->grid_brute_ggx))) return rc;
+	if ((rc = occ(reinterpret_cast<const void*>(&k_brute_finish<false, true>), kBruteBlock, &c->grid_brute_finish_ggx))) return rc;
+	if ((rc = occ(reinterpret_cast<const void*>(&k_shade<false, true>), kBruteBlock, &c->grid_shade_ggx))) return rc;
 	c->packet_primary = std::getenv("B2R_NO_PACKET") == nullptr;  // A/B switch for measurements: per-lane walks for the camera rays too
 	c->twin_enabled = std::getenv("B2R_NO_TWIN") == nullptr;      // A/B switch for measurements: every batch as one lane
 	c->grid_stream = c->sm_count * 8;
@@ -228,15 +233,19 @@ int enqueue_rounds(b2r_ctx* c, const Params& p_in, cudaStream_t st, bool profile
 	if (!c->use_bvh) {
 		const bool exact = (c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) != 0;
 		if (exact && c->params.scene.n_mat > 64) return fail(B2R_ERR_STATE, "B2R_FLAG_REFERENCE_EXACT: at most 64 materials (RendererPolicy::max_materialID, Renderer.hpp:23)");
+		const bool ggx = (c->cfg.flags & B2R_FLAG_GGX) != 0;  // the GGX closure's kernels are built without the sphere-test counters
 		const bool finish = !exact && c->params.frame.finish_below != 0u && c->params.scene.n_prims <= static_cast<uint32_t>(kBruteTile);
 		Params p = p_in;  // (shadows the reference above) the hand-over threshold only reaches the kernels when k_brute_finish is launched too
 		if (!finish) p.frame.finish_below = 0u;
 		for (uint32_t b = 0; b < mb; b++) {
 			if (finish && b >= p.frame.finish_first && b + 1 < mb) {  // takes the remaining paths over once few enough are left (a no-op launch otherwise)
-				if ((rc = launch(c, KK_BRUTE, profile, [&] { if (count) k_brute_finish<true><<<c->grid_brute_finish, kBruteBlock, 0, st>>>(p, b); else k_brute_finish<false><<<c->grid_brute_finish, kBruteBlock, 0, st>>>(p, b); }))) return rc;
+				if ((rc = launch(c, KK_BRUTE, profile, [&] { if (ggx) k_brute_finish<false, true><<<c->grid_brute_finish_ggx, kBruteBlock, 0, st>>>(p, b); else if (count) k_brute_finish<true><<<c->grid_brute_finish, kBruteBlock, 0, st>>>(p, b); else k_brute_finish<false><<<c->grid_brute_finish, kBruteBlock, 0, st>>>(p, b); }))) return rc;
 			}
 			rc = launch(c, KK_BRUTE, profile, [&] {
-				if (exact) {
+				if (ggx) {
+					if (b == 0) k_bounce_brute<true, false, false, true><<<c->grid_brute_first_ggx, kBruteBlock, 0, st>>>(p, b);
+					else k_bounce_brute<false, false, false, true><<<c->grid_brute_ggx, kBruteBlock, 0, st>>>(p, b);
+				} else if (exact) {
 					if (b == 0) { if (count) k_bounce_brute<true, true, true><<<c->grid_brute_first_exact, kBruteBlock, 0, st>>>(p, b); else k_bounce_brute<true, false, true><<<c->grid_brute_first_exact, kBruteBlock, 0, st>>>(p, b); }
 					else { if (count) k_bounce_brute<false, true, true><<<c->grid_brute_exact, kBruteBlock, 0, st>>>(p, b); else k_bounce_brute<false, false, true><<<c->grid_brute_exact, kBruteBlock, 0, st>>>(p, b); }
 				} else {
@@ -265,7 +274,7 @@ int enqueue_rounds(b2r_ctx* c, const Params& p_in, cudaStream_t st, bool profile
 				else { if (count) B2R_CLOSEST(true, false); else B2R_CLOSEST(false, false); }
 #undef B2R_CLOSEST
 			}))) return rc;
-			if ((rc = launch(c, KK_SHADE, profile, [&] { if (exact) k_shade<true><<<c->grid_shade, kBruteBlock, 0, st>>>(p, b); else k_shade<false><<<c->grid_shade, kBruteBlock, 0, st>>>(p, b); }))) return rc;
+			if ((rc = launch(c, KK_SHADE, profile, [&] { if (c->cfg.flags & B2R_FLAG_GGX) k_shade<false, true><<<c->grid_shade_ggx, kBruteBlock, 0, st>>>(p, b); else if (exact) k_shade<true><<<c->grid_shade, kBruteBlock, 0, st>>>(p, b); else k_shade<false><<<c->grid_shade, kBruteBlock, 0, st>>>(p, b); }))) return rc;
 			if (exact && b + 1 < mb) { if ((rc = launch(c, KK_SHADE, profile, [&] { k_stream_rank<<<c->grid_stream, 256, 0, st>>>(p, b); }))) return rc; }
 			if (mis && b + 1 < mb) {
 				if ((rc = launch(c, KK_SHADOW, profile, [&] { if (count) k_intersect_shadow<true><<<c->grid_shadow, kTravBlock, 0, st>>>(p, b); else k_intersect_shadow<false><<<c->grid_shadow, kTravBlock, 0, st>>>(p, b); }))) return rc;
@@ -420,6 +429,7 @@ int b2r_create(b2r_ctx** out, const b2r_config* cfg) {
 	if (cfg->max_bounces < 1 || cfg->max_bounces > 1024) return fail(B2R_ERR_ARG, "max_bounces must be in 1..1024");
 	if (cfg->bucket_stride > 1 && cfg->bucket_first >= cfg->bucket_stride) return fail(B2R_ERR_ARG, "bucket_first must be < bucket_stride");
 	if (cfg->samples_in_flight > static_cast<uint32_t>(kMaxSlots)) return fail(B2R_ERR_ARG, "samples_in_flight must be <= 64");
+	if ((cfg->flags & B2R_FLAG_GGX) && (cfg->flags & B2R_FLAG_REFERENCE_EXACT)) return fail(B2R_ERR_ARG, "B2R_FLAG_GGX cannot be combined with B2R_FLAG_REFERENCE_EXACT");
 	int n_dev = 0;
 	cudaError_t e = cudaGetDeviceCount(&n_dev);
 	if (e != cudaSuccess || n_dev == 0) return fail(B2R_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libb2r has no CPU fallback)");
@@ -445,7 +455,7 @@ void b2r_destroy(b2r_ctx* c) {
 	b2r_team_close(c); if (c->d_team) { cudaFree(c->d_team); c->d_team = nullptr; }
 	drop_graph(c);
 	for (auto& t : c->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
-	dev_free(&c->d_prims); dev_free(&c->d_mat_albedo); dev_free(&c->d_mat_emission); dev_free(&c->d_light_sphere); dev_free(&c->d_light_emit);
+	dev_free(&c->d_prims); dev_free(&c->d_mat_albedo); dev_free(&c->d_mat_emission); dev_free(&c->d_mat_f0); dev_free(&c->d_light_sphere); dev_free(&c->d_light_emit);
 	dev_free(&c->d_hdri); dev_free(&c->d_prim_mat); dev_free(&c->d_wide); dev_free(&c->d_cost); dev_free(&c->d_remap); dev_free(&c->d_trace); dev_free(&c->d_cost_base); dev_free(&c->d_sort_tmp);
 	for (int k = 0; k < 2; k++) { dev_free(&c->d_mkey[k]); dev_free(&c->d_midx[k]); }
 	for (int s = 0; s < 2; s++) { dev_free(&c->d_A[s]); dev_free(&c->d_B[s]); dev_free(&c->d_T[s]); }
@@ -506,6 +516,7 @@ int b2r_set_flags(b2r_ctx* c, uint32_t flags) {
 	CU(cudaStreamSynchronize(c->stream));
 	if ((c->cfg.flags ^ flags) & B2R_FLAG_REFERENCE_TREE) return fail(B2R_ERR_STATE, "B2R_FLAG_REFERENCE_TREE can only be chosen at b2r_create");
 	if ((c->cfg.flags ^ flags) & B2R_FLAG_REFERENCE_EXACT) return fail(B2R_ERR_STATE, "B2R_FLAG_REFERENCE_EXACT can only be chosen at b2r_create");
+	if ((flags & B2R_FLAG_GGX) && (flags & B2R_FLAG_REFERENCE_EXACT)) return fail(B2R_ERR_ARG, "B2R_FLAG_GGX cannot be combined with B2R_FLAG_REFERENCE_EXACT");
 	c->cfg.flags = flags; c->params.frame.flags = flags;
 	if (c->have_scene) {
 		const uint32_t n = c->params.scene.n_prims;
@@ -606,8 +617,8 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 	if (c->n_wide >= kMaxWideNodes) { c->have_wide = false; return fail(B2R_ERR_BVH, "more than 2^22 traversal nodes (stack entries keep 22 node bits)"); }
 
 	PackedScene ps; pack_scene(prims, n_prims, materials, n_mat, light_geom_idx, n_lights, geometry, ps);
-	auto &h_prims = ps.prims, &h_alb = ps.mat_albedo, &h_em = ps.mat_emission, &h_ls = ps.light_sphere, &h_le = ps.light_emit; auto& h_pm = ps.prim_mat;
-	const bool grow = h_prims.size() > c->cap_prims || h_pm.size() > c->cap_prim_mat || h_alb.size() > c->cap_mat_albedo || h_em.size() > c->cap_mat_emission ||
+	auto &h_prims = ps.prims, &h_alb = ps.mat_albedo, &h_em = ps.mat_emission, &h_f0 = ps.mat_f0, &h_ls = ps.light_sphere, &h_le = ps.light_emit; auto& h_pm = ps.prim_mat;
+	const bool grow = h_prims.size() > c->cap_prims || h_pm.size() > c->cap_prim_mat || h_alb.size() > c->cap_mat_albedo || h_em.size() > c->cap_mat_emission || h_f0.size() > c->cap_mat_f0 ||
 	                  h_ls.size() > c->cap_light_sphere || h_le.size() > c->cap_light_emit || c->n_wide > c->cap_wide || c->n_wide > c->cap_parent || n_prims > c->cap_leaf_node ||
 	                  (has_ambient && static_cast<size_t>(hdri_w) * hdri_h > c->cap_hdri);
 	if (grow) CU(cudaStreamSynchronize(c->stream));  // device arrays in use are about to be replaced (first upload, or a larger scene)
@@ -615,6 +626,7 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 	if ((rc = dev_reserve(&c->d_prim_mat, &c->cap_prim_mat, h_pm.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_mat_albedo, &c->cap_mat_albedo, h_alb.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_mat_emission, &c->cap_mat_emission, h_em.size()))) return rc;
+	if ((rc = dev_reserve(&c->d_mat_f0, &c->cap_mat_f0, h_f0.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_light_sphere, &c->cap_light_sphere, h_ls.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_light_emit, &c->cap_light_emit, h_le.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_wide, &c->cap_wide, static_cast<size_t>(c->n_wide)))) return rc;
@@ -624,7 +636,7 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 	if (has_ambient && (rc = dev_reserve(&c->d_hdri, &c->cap_hdri, texels))) return rc;
 	const UploadPart parts[] = {
 		{c->d_prims, h_prims.data(), h_prims.size() * sizeof(float4)}, {c->d_prim_mat, h_pm.data(), h_pm.size() * sizeof(int32_t)},
-		{c->d_mat_albedo, h_alb.data(), h_alb.size() * sizeof(float4)}, {c->d_mat_emission, h_em.data(), h_em.size() * sizeof(float4)},
+		{c->d_mat_albedo, h_alb.data(), h_alb.size() * sizeof(float4)}, {c->d_mat_emission, h_em.data(), h_em.size() * sizeof(float4)}, {c->d_mat_f0, h_f0.data(), h_f0.size() * sizeof(float4)},
 		{c->d_light_sphere, h_ls.data(), h_ls.size() * sizeof(float4)}, {c->d_light_emit, h_le.data(), h_le.size() * sizeof(float4)},
 		{c->d_wide, c->wide_host.nodes.data(), gpu_tree ? 0 : c->wide_host.nodes.size() * sizeof(WideNode)}, {c->d_hdri, hdri_rgba, texels * sizeof(float4)},
 	};
@@ -653,7 +665,7 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 	if ((rc = launch_link_tables(c))) return rc;
 	const SceneDev before = c->params.scene; const bool bvh_before = c->use_bvh;
 	SceneDev& s = c->params.scene;
-	s.prims = c->d_prims; s.prim_mat = c->d_prim_mat; s.mat_albedo = c->d_mat_albedo; s.mat_emission = c->d_mat_emission;
+	s.prims = c->d_prims; s.prim_mat = c->d_prim_mat; s.mat_albedo = c->d_mat_albedo; s.mat_emission = c->d_mat_emission; s.mat_f0 = c->d_mat_f0;
 	s.light_sphere = c->d_light_sphere; s.light_emit = c->d_light_emit; s.wide = c->d_wide; s.hdri = has_ambient ? c->d_hdri : nullptr;
 	s.parent = c->d_parent; s.leaf_node = c->d_leaf_node;
 	s.n_prims = n_prims; s.n_mat = n_mat; s.n_lights = n_lights; s.stack_tn_bits = c->wide_host.tn_bits;
@@ -697,17 +709,18 @@ int b2r_refit_scene(b2r_ctx* c, const b2r_sphere* prims, uint32_t n_prims, const
 	}
 	PackedScene ps; pack_scene(prims, n_prims, materials, n_mat, light_geom_idx, n_lights, geometry, ps);
 	if ((rc = dev_reserve(&c->d_remap, &c->cap_remap, remap.size()))) return rc;
-	const bool grow = ps.mat_albedo.size() > c->cap_mat_albedo || ps.mat_emission.size() > c->cap_mat_emission ||
+	const bool grow = ps.mat_albedo.size() > c->cap_mat_albedo || ps.mat_emission.size() > c->cap_mat_emission || ps.mat_f0.size() > c->cap_mat_f0 ||
 	                  ps.light_sphere.size() > c->cap_light_sphere || ps.light_emit.size() > c->cap_light_emit;
 	if (grow) CU(cudaStreamSynchronize(c->stream));  // more materials or lights than before: those (small) arrays are replaced
 	if ((rc = dev_reserve(&c->d_mat_albedo, &c->cap_mat_albedo, ps.mat_albedo.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_mat_emission, &c->cap_mat_emission, ps.mat_emission.size()))) return rc;
+	if ((rc = dev_reserve(&c->d_mat_f0, &c->cap_mat_f0, ps.mat_f0.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_light_sphere, &c->cap_light_sphere, ps.light_sphere.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_light_emit, &c->cap_light_emit, ps.light_emit.size()))) return rc;
 	if (!c->d_cost) { size_t cap = 0; if ((rc = dev_reserve(&c->d_cost, &cap, 1))) return rc; }
 	const UploadPart parts[] = {
 		{c->d_prims, ps.prims.data(), ps.prims.size() * sizeof(float4)}, {c->d_prim_mat, ps.prim_mat.data(), ps.prim_mat.size() * sizeof(int32_t)},
-		{c->d_mat_albedo, ps.mat_albedo.data(), ps.mat_albedo.size() * sizeof(float4)}, {c->d_mat_emission, ps.mat_emission.data(), ps.mat_emission.size() * sizeof(float4)},
+		{c->d_mat_albedo, ps.mat_albedo.data(), ps.mat_albedo.size() * sizeof(float4)}, {c->d_mat_emission, ps.mat_emission.data(), ps.mat_emission.size() * sizeof(float4)}, {c->d_mat_f0, ps.mat_f0.data(), ps.mat_f0.size() * sizeof(float4)},
 		{c->d_light_sphere, ps.light_sphere.data(), ps.light_sphere.size() * sizeof(float4)}, {c->d_light_emit, ps.light_emit.data(), ps.light_emit.size() * sizeof(float4)},
 		{c->d_remap, remap.data(), remap.size() * sizeof(uint32_t)},
 	};
@@ -728,7 +741,7 @@ int b2r_refit_scene(b2r_ctx* c, const b2r_sphere* prims, uint32_t n_prims, const
 	c->wide_refit = true; drop_speculation(c);
 	const SceneDev before = c->params.scene;
 	SceneDev& s = c->params.scene;
-	s.mat_albedo = c->d_mat_albedo; s.mat_emission = c->d_mat_emission; s.light_sphere = c->d_light_sphere; s.light_emit = c->d_light_emit;
+	s.mat_albedo = c->d_mat_albedo; s.mat_emission = c->d_mat_emission; s.mat_f0 = c->d_mat_f0; s.light_sphere = c->d_light_sphere; s.light_emit = c->d_light_emit;
 	s.n_mat = n_mat; s.n_lights = n_lights; s.light_sel_pdf = n_lights ? 1.0f / static_cast<float>(n_lights) : 0.0f;  // Renderer.hpp:78
 	if (std::memcmp(&before, &s, sizeof s) != 0) drop_graph(c);
 	if (quality_out) {  // optional: costs one launch and a stream synchronisation

@@ -433,12 +433,13 @@ void pack_scene(const b2r_sphere* prims, uint32_t n_prims, const b2r_material* m
 		out.prims[i] = f4(prims[i].position[0], prims[i].position[1], prims[i].position[2], prims[i].radius_sq);
 		out.prim_mat[i] = prims[i].material_ID;
 	}
-	out.mat_albedo.resize(n_mat); out.mat_emission.resize(n_mat);
+	out.mat_albedo.resize(n_mat); out.mat_emission.resize(n_mat); out.mat_f0.resize(n_mat);
 	for (uint32_t i = 0; i < n_mat; i++) {
 		const float* e = materials[i].emission;
 		const bool emissive = sel_max(e[0], sel_max(e[1], e[2])) > FLT_EPSILON;  // is_emissive, Renderer.hpp:201
 		out.mat_albedo[i] = f4(materials[i].albedo[0], materials[i].albedo[1], materials[i].albedo[2], emissive ? 1.0f : 0.0f);
 		out.mat_emission[i] = f4(e[0], e[1], e[2], 0.0f);
+		out.mat_f0[i] = f4(materials[i].F0[0], materials[i].F0[1], materials[i].F0[2], materials[i].roughness);  // Closure<GGX>, Renderer.hpp:210-211
 	}
 	out.light_sphere.resize(n_lights ? n_lights : 1, f4(0, 0, 0, 0)); out.light_emit.resize(n_lights ? n_lights : 1, f4(0, 0, 0, 0));
 	for (uint32_t i = 0; i < n_lights; i++) {  // NEE reads the light from scene.geometry, original order (Renderer.hpp:261-262,277)

@@ -233,6 +233,59 @@ B2R_HD f3 sample_sphere_cone(f3 wc, float sin2_max, float center_dist, float r2,
 	f3 bx, by; branchless_onb(wc, &bx, &by);
 	return {bx.x * l.x + by.x * l.y + wc.x * l.z, bx.y * l.x + by.y * l.y + wc.y * l.z, bx.z * l.x + by.z * l.y + wc.z * l.z};
 }
+// ---- GGX closure (the reference's `#define BRDF 1` build: Closure<ClosureType::GGX>, DataStreams.hpp:184-219; Sampling.hpp:102-104,249-309)
+B2R_HD float lerp_glm(float a, float b, float t) { return a * (1.0f - t) + b * t; }  // glm::mix(x, y, a) = x * (1 - a) + y * a
+B2R_HD f3 ggx_visible_normal(f3 v_local, float alpha, float u0, float u1) {  // distribution_visible_normals, Sampling.hpp:253-270
+	const f3 V = unit3(f3{alpha * v_local.x, alpha * v_local.y, v_local.z});
+	float sn, cs; sincos_poly(u1 * B2R_TWO_PI, &sn, &cs);  // disk(u, v) = polar_to_cartesian(v, sqrt(u)), :85-91,102-104
+	const float rho = sqrtf(u0);
+	const float sx = rho * cs; float sy = rho * sn;
+	const float t = 1.0f - sx * sx;
+	sy = lerp_glm(sqrtf(t), sy, V.z * 0.5f + 0.5f);
+	f3 X, Y; branchless_onb(V, &X, &Y);
+	const float hz = sqrtf(sel_max(0.0f, t - sy * sy));
+	const f3 H{(X.x * sx + Y.x * sy) + V.x * hz, (X.y * sx + Y.y * sy) + V.y * hz, (X.z * sx + Y.z * sy) + V.z * hz};
+	return unit3(f3{alpha * H.x, alpha * H.y, sel_max(0.0f, H.z)});
+}
+B2R_HD f3 ggx_fresnel(f3 f0, float h_dot_v) {  // Fresnel, Sampling.hpp:272-275
+	float c = 1.0f - h_dot_v; c = c < 0.0f ? 0.0f : (1.0f < c ? 1.0f : c);  // std::clamp
+	float a = c * c; a *= a; a = c * a;  // pow5
+	return f3{f0.x * (1.0f - a) + 1.0f * a, f0.y * (1.0f - a) + 1.0f * a, f0.z * (1.0f - a) + 1.0f * a};
+}
+B2R_HD float ggx_ndf(float alpha2, float n_dot_h2) { const float t = (1.0f + (alpha2 - 1.0f) * n_dot_h2); return alpha2 / (B2R_PI * t * t); }  // GGX_D, :278-281
+B2R_HD float ggx_g2_lagarde(float alpha2, float n_dot_l, float n_dot_v) {  // Smith_G2_Height_Correlated_GGX_Lagarde, :287-291
+	const float a = n_dot_v * sqrtf(alpha2 + n_dot_l * (n_dot_l - alpha2 * n_dot_l));
+	const float b = n_dot_l * sqrtf(alpha2 + n_dot_v * (n_dot_v - alpha2 * n_dot_v));
+	return 0.5f / (a + b);
+}
+B2R_HD f3 ggx_microfacet_brdf(f3 f0, float alpha, float n_dot_v, float n_dot_l, float n_dot_h, float h_dot_v) {  // microfacet_brdf, :293-296
+	const float alpha2 = alpha * alpha;
+	return scale3(ggx_fresnel(f0, h_dot_v), n_dot_l * ggx_ndf(sel_max(0.00001f, alpha2), n_dot_h * n_dot_h) * ggx_g2_lagarde(alpha2, n_dot_l, n_dot_v));
+}
+B2R_HD float ggx_g1(float alpha2, float n_dot_s2) { return 2.0f / (1.0f + sqrtf(((alpha2 * (1.0f - n_dot_s2)) + n_dot_s2) / n_dot_s2)); }  // G1_GGX, :297-299
+B2R_HD f3 ggx_vndf_estimator(f3 f0, float alpha, float n_dot_v, float n_dot_l, float h_dot_v) {  // vndf_estimator, :301-309
+	const float alpha2 = alpha * alpha;
+	const float g1v = ggx_g1(alpha2, n_dot_v * n_dot_v), g1l = ggx_g1(alpha2, n_dot_l * n_dot_l);
+	return scale3(ggx_fresnel(f0, h_dot_v), g1l / (g1v + g1l - g1v * g1l));
+}
+B2R_HD f3 ggx_eval(f3 f0, float alpha, f3 l_local, f3 v_local) {  // Closure<GGX>::eval, DataStreams.hpp:189-195
+	const float n_dot_l = sel_max(0.0f, l_local.z), n_dot_v = sel_max(0.0f, v_local.z);
+	const f3 hn = unit3(f3{l_local.x + v_local.x, l_local.y + v_local.y, l_local.z + v_local.z});
+	return ggx_microfacet_brdf(f0, alpha, n_dot_v, n_dot_l, sel_max(0.0f, hn.z), sel_max(0.0f, dot3(hn, v_local)));
+}
+B2R_HD void ggx_sample(f3 f0, float alpha, f3 v_local, float u0, float u1, f3* dir, f3* estimator) {  // Closure<GGX>::sample, DataStreams.hpp:199-218
+	const float n_dot_v = sel_max(0.0f, v_local.z);
+	float h_dot_v;
+	if (alpha == 0.0f) { *dir = f3{-v_local.x, -v_local.y, v_local.z}; h_dot_v = n_dot_v; }
+	else {
+		const f3 h = ggx_visible_normal(v_local, alpha, u0, u1);
+		h_dot_v = dot3(h, v_local);
+		const float k = 2.0f * h_dot_v;
+		*dir = f3{k * h.x - v_local.x, k * h.y - v_local.y, k * h.z - v_local.z};
+		h_dot_v = sel_max(0.0f, h_dot_v);
+	}
+	*estimator = ggx_vndf_estimator(f0, alpha, n_dot_v, sel_max(0.0f, dir->z), h_dot_v);
+}
 B2R_HD float power_heuristic(float f, float g) { float f2 = f * f; return f2 / sel_max(1e-6f, f2 + g * g); }  // Sampling.hpp:241-244
 B2R_HD float power_heuristic_over_f(float f, float g) { return f / sel_max(1e-6f, f * f + g * g); }         // Sampling.hpp:245-247
 

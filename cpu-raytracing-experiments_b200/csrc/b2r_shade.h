@@ -35,6 +35,7 @@ struct SceneDev {
 	const int32_t* prim_mat;    // [n_prims] material_ID
 	const float4* mat_albedo;   // [n_mat] {albedo.rgb, emissive ? 1 : 0}  (max(emission) > FLT_EPSILON, Renderer.hpp:201)
 	const float4* mat_emission; // [n_mat] {emission.rgb, 0}
+	const float4* mat_f0;       // [n_mat] {F0.rgb, roughness}: read by the GGX closure only (B2R_FLAG_GGX)
 	const float4* light_sphere; // [n_lights] scene.geometry[light] {c.xyz, r^2}   (Renderer.hpp:261-262)
 	const float4* light_emit;   // [n_lights] {emission.rgb of its material, as_float(light_primID)}
 	const WideNode* wide;       // flattened BVH
@@ -126,10 +127,13 @@ B2R_HD PathState primary_path(const FrameDev& fr, const CameraParams& cam, uint3
 
 
 // ---------------------------------------------------------------------------------------------- shading
-struct Surface { f3 P; TangentQuat T; float n_dot_v; f3 albedo; bool emissive; int32_t mat; float r2; };
+struct Surface { f3 P; TangentQuat T; float n_dot_v; f3 albedo; bool emissive; int32_t mat; float r2; f3 v_local; float alpha; };  // GGX: albedo holds F0; v_local / alpha are only set (and read) by the GGX closure
 struct ShadowRay { f3 o, d; float tfar; f3 L; };
 
-// closest-hit shader, Renderer.hpp:169-214
+// closest-hit shader, Renderer.hpp:169-214. GGX = the reference's `#define BRDF 1` build (Renderer.hpp:70,207-213): the closure takes F0 and
+// alpha = roughness^2 + (1 - roughness^2) * gloss_decay_table[bounce]; the reference never declares that table, it is all zeros here as in
+// oracle/ref_renderer_build.sh's build of the reference itself.
+template <bool GGX = false>
 B2R_HD Surface shade_surface(const SceneDev& sc, const PathState& s, float depth, int32_t prim) {
 	const float4 sp = ld4(sc.prims + prim);
 	const f3 D{s.dx, s.dy, s.dz};
@@ -138,14 +142,21 @@ B2R_HD Surface shade_surface(const SceneDev& sc, const PathState& s, float depth
 	if (dot3(N, D) >= 0.0f) N = f3{-N.x, -N.y, -N.z};  // backface
 	Surface sf;
 	sf.T = tangent_frame(N);
-	sf.n_dot_v = frame_to_local(sf.T, f3{-D.x, -D.y, -D.z}).z;
+	const f3 vl = frame_to_local(sf.T, f3{-D.x, -D.y, -D.z});
+	sf.n_dot_v = vl.z;
 	sf.P = f3{hp.x + N.x * 1e-4f, hp.y + N.y * 1e-4f, hp.z + N.z * 1e-4f};
 	sf.mat = sc.prim_mat[prim];
 	const float4 al = ld4(sc.mat_albedo + sf.mat);
 	sf.albedo = f3{al.x, al.y, al.z}; sf.emissive = al.w != 0.0f; sf.r2 = sp.w;
+	if (GGX) {
+		const float4 fr = ld4(sc.mat_f0 + sf.mat);
+		float alpha = fr.w; alpha *= alpha;
+		sf.albedo = f3{fr.x, fr.y, fr.z}; sf.alpha = alpha + (1.0f - alpha) * 0.0f; sf.v_local = vl;  // Renderer.hpp:210-212
+	}
 	return sf;
 }
 // next-event estimation, Renderer.hpp:249-298. Returns false when no shadow ray is produced.
+template <bool GGX = false>
 B2R_HD bool shade_light_sample(const SceneDev& sc, const Surface& sf, const PathState& s, int32_t hit_prim,
                                                    uint32_t acc, uint32_t seed, uint32_t bounce, ShadowRay* out) {
 	if (sc.n_lights == 0u) return false;  // undefined in the reference (Q15); defined here as "no light sampling"
@@ -167,10 +178,13 @@ B2R_HD bool shade_light_sample(const SceneDev& sc, const Surface& sf, const Path
 	const f3 ll = frame_to_local(sf.T, L);
 	if (ll.z < 0.0f) return false;
 	f3 rad{le.x * s.tr, le.y * s.tg, le.z * s.tb};
-	const float f = B2R_INV_PI * sel_max(0.0f, ll.z);  // Closure<Lambertian>::eval, DataStreams.hpp:169-172
-	rad = f3{rad.x * (sf.albedo.x * f), rad.y * (sf.albedo.y * f), rad.z * (sf.albedo.z * f)};
+	if (GGX) { const f3 e = ggx_eval(sf.albedo, sf.alpha, ll, sf.v_local); rad = f3{rad.x * e.x, rad.y * e.y, rad.z * e.z}; }  // Closure<GGX>::eval, DataStreams.hpp:189-195
+	else {
+		const float f = B2R_INV_PI * sel_max(0.0f, ll.z);  // Closure<Lambertian>::eval, DataStreams.hpp:169-172
+		rad = f3{rad.x * (sf.albedo.x * f), rad.y * (sf.albedo.y * f), rad.z * (sf.albedo.z * f)};
+	}
 	lpdf *= sc.light_sel_pdf;
-	const float bpdf = B2R_INV_PI * sel_max(0.0f, ll.z);
+	const float bpdf = GGX ? 0.0f : B2R_INV_PI * sel_max(0.0f, ll.z);  // Closure<GGX>::pdf is `return 0.0f; //TODO` in the reference (:196-198)
 	const float w = power_heuristic_over_f(lpdf, bpdf);
 	rad = scale3(rad, w);
 	if (sel_max(sel_max(rad.x, rad.y), rad.z) <= 0.0f) return false;
@@ -187,18 +201,21 @@ B2R_HD f3 shade_emission(const SceneDev& sc, const Surface& sf, const PathState&
 	return f3{(s.tr * w) * em.x, (s.tg * w) * em.y, (s.tb * w) * em.z};
 }
 // BRDF sampling + Russian roulette, Renderer.hpp:359-403. Returns false when the path is terminated by roulette.
+template <bool GGX = false>
 B2R_HD bool shade_continue(const Surface& sf, PathState* s, uint32_t acc, uint32_t seed, uint32_t bounce) {
 	Pcg rng{hash_2d(acc, seed + bounce * 2u + 1u)};
 	const float u0 = rng.next_unit(), u1 = rng.next_unit();
-	const f3 dl = cosine_hemisphere(u0, u1);
-	f3 thr{s->tr * sf.albedo.x, s->tg * sf.albedo.y, s->tb * sf.albedo.z};
+	f3 dl, est = sf.albedo;
+	if (GGX) ggx_sample(sf.albedo, sf.alpha, sf.v_local, u0, u1, &dl, &est);  // Closure<GGX>::sample, DataStreams.hpp:199-218
+	else dl = cosine_hemisphere(u0, u1);
+	f3 thr{s->tr * est.x, s->tg * est.y, s->tb * est.z};
 	const float q = 1.0f - sel_max(thr.x, sel_max(thr.y, thr.z));
 	if (rng.next_unit() < q) return false;
 	thr = scale3(thr, 1.0f / sel_max(FLT_EPSILON, 1.0f - q));
 	const f3 dw = frame_to_world(sf.T, dl);
 	s->ox = sf.P.x; s->oy = sf.P.y; s->oz = sf.P.z; s->dx = dw.x; s->dy = dw.y; s->dz = dw.z;
 	s->tr = thr.x; s->tg = thr.y; s->tb = thr.z;
-	s->pdf = B2R_INV_PI * sel_max(0.0f, dw.z);  // pdf of the world-space direction (Q10)
+	s->pdf = GGX ? 0.0f : B2R_INV_PI * sel_max(0.0f, dw.z);  // pdf of the world-space direction (Q10); Closure<GGX>::pdf returns 0
 	return true;
 }
 // miss shader with ambient sky, Renderer.hpp:411-420 + Sky::operator(), Primitives.hpp:35-46

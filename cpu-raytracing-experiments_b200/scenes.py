@@ -143,6 +143,18 @@ def random_scene(n, light_every=1000, seed=0x04D15A07, emission=20.0):
                  ambient=(0.0, 0.0, 0.0), hdri=None)
 
 
+def ggx_random_scene(n, light_every=20, seed=0x66780001):
+    """random_scene(n) with materials the GGX closure (the reference's `#define BRDF 1` build, DataStreams.hpp:184-219) has something to do
+    with: F0 ~ U(0.3, 1) per channel, roughness ~ U(0.05, 1) — and exactly 0 for material 0, the closure's mirror branch (alpha == 0)."""
+    sc = random_scene(n, light_every=light_every)
+    u = pcg_unit_floats(_hash_u32(seed), 8 * 4).reshape(8, 4)
+    for i in range(8):
+        sc["material"][i]["F0"] = f32(0.3) + u[i, :3] * f32(0.7)
+        sc["material"][i]["roughness"] = f32(0.0) if i == 0 else f32(0.05) + u[i, 3] * f32(0.95)
+    sc["name"] = f"ggx_random{n}"
+    return sc
+
+
 def synthetic_hdri(width=64, height=32, seed=0x5EED):
     """Deterministic equirect RGBA32F test texture (the reference loads env.hdr from disk, Application.cpp:225): values in [0.1, 4)."""
     u = pcg_unit_floats(_hash_u32(seed), width * height * 4).reshape(height, width, 4)

@@ -61,6 +61,9 @@ enum {
 	B2R_FLAG_GPU_TREE = 1u << 8,       /* b2r_upload_scene builds the traversal tree ON THE GPU (Morton keys, radix sort, implicit balanced 4-ary topology, refit passes):
 	                                    * milliseconds instead of the host's SAH build, for edits that add or remove spheres; same results, ~3.5x the node visits
 	                                    * of the SAH tree on C3's overlapping spheres. May be toggled with b2r_set_flags between uploads. */
+	B2R_FLAG_GGX = 1u << 9,            /* the reference's `#define BRDF 1` build (Renderer.hpp:70,207-213): Closure<GGX> (DataStreams.hpp:184-219) from the materials'
+	                                    * F0 and roughness instead of the Lambertian closure; gloss_decay_table (never declared by the reference) is all zeros and
+	                                    * Closure<GGX>::pdf returns 0 as it does there. Not combinable with B2R_FLAG_REFERENCE_EXACT. */
 	B2R_FLAG_NO_SPECULATION = 1u << 7, /* b2r_accumulate(ctx, 1) traces exactly one sample (default: a caller that asks for one sample per frame gets
 	                                    * batches of 2, 4, ... 16 samples traced ahead while nothing changes; results are identical either way) */
 };

@@ -61,6 +61,10 @@ enum Flags : uint32_t {
 	ORC_BVH = 1u,         // USEBVH true: stream-BVH traversal of BVH.hpp:320-358 / 368-403 (reference ships false)
 	ORC_SLOT_EXACT = 2u,  // closest-hit: SIMD blocks of 8 + scalar tail exactly as BVH.hpp:250-286 (default: FMA formula everywhere)
 	ORC_NO_MIS = 4u,      // this repo's "MIS off" definition: no NEE, radiance += throughput*emission
+	ORC_GGX = 8u,         // the reference's `#define BRDF 1` build (Renderer.hpp:70,207-213): Closure<GGX> (DataStreams.hpp:184-219) with F0 and
+	                      // alpha = roughness^2 + (1 - roughness^2) * gloss_decay_table[bounce]. The reference never declares gloss_decay_table (BRDF 1
+	                      // does not compile as shipped); oracle/ref_renderer_build.sh supplies an all-zero table ("no decay") and so does this port.
+	                      // Closure<GGX>::pdf is `return 0.0f; //TODO` in the reference and is restated as that.
 };
 
 // ---------------------------------------------------------------- BVH node helpers (BVH.hpp:28-67)
@@ -203,7 +207,8 @@ struct ShadowStream {
 struct ShaderData {
 	float Px[kTileSize], Py[kTileSize], Pz[kTileSize], Vx[kTileSize], Vy[kTileSize], Vz[kTileSize];
 	float Tx[kTileSize], Ty[kTileSize], Tz[kTileSize], Tw[kTileSize];
-	float albedo[kTileSize][3];  // Closure<LambertianDiffuse>::albedo (DataStreams.hpp:165-167)
+	float albedo[kTileSize][3];  // Closure<LambertianDiffuse>::albedo (DataStreams.hpp:165-167); ORC_GGX: Closure<GGX>::F0 (:186)
+	float alpha[kTileSize];      // ORC_GGX: Closure<GGX>::alpha (:187)
 	uint8_t is_emissive[kTileSize];
 };
 
@@ -406,6 +411,7 @@ static void accumulate_tile(Ctx& c, uint32_t LaunchIndex, TileScratch& S) {
 	const bool has_ambient = smax(c.ambient[0], smax(c.ambient[1], c.ambient[2])) > 0.0f;      // :79
 	const uint32_t bucket_index = accumulations % c.K;                                         // :82 (Q1)
 	const bool mis = !(c.flags & ORC_NO_MIS);
+	const bool ggx = (c.flags & ORC_GGX) != 0;
 	float* out_r = c.accumulator.data() + (static_cast<size_t>(LaunchIndex) * c.K + bucket_index) * 3 * kTileSize;  // :84
 	float* out_g = out_r + kTileSize; float* out_b = out_g + kTileSize;
 	const int32_t tile_x = kTileRoot * static_cast<int32_t>(LaunchIndex % c.h_tiles);          // :85-88
@@ -456,7 +462,12 @@ static void accumulate_tile(Ctx& c, uint32_t LaunchIndex, TileScratch& S) {
 			S.sd.Tx[ID] = T.x; S.sd.Ty[ID] = T.y; S.sd.Tz[ID] = T.z; S.sd.Tw[ID] = T.w;
 			const Material& m = c.material[mat_ID];
 			if (smax(m.emission[0], smax(m.emission[1], m.emission[2])) > FLT_EPSILON) S.sd.is_emissive[ID] = 1;  // :201-203
-			S.sd.albedo[ID][0] = m.albedo[0]; S.sd.albedo[ID][1] = m.albedo[1]; S.sd.albedo[ID][2] = m.albedo[2];  // :208
+			if (!ggx) { S.sd.albedo[ID][0] = m.albedo[0]; S.sd.albedo[ID][1] = m.albedo[1]; S.sd.albedo[ID][2] = m.albedo[2]; }  // :208
+			else {  // :210-212 with gloss_decay_table == 0
+				S.sd.albedo[ID][0] = m.F0[0]; S.sd.albedo[ID][1] = m.F0[1]; S.sd.albedo[ID][2] = m.F0[2];
+				float alpha = m.roughness; alpha *= alpha;
+				S.sd.alpha[ID] = alpha + (1.0f - alpha) * 0.0f;
+			}
 		}
 
 		size_t miss_count;  // sort_rayID, DataStreams.hpp:221-253 (call Renderer.hpp:235-241)
@@ -498,13 +509,13 @@ static void accumulate_tile(Ctx& c, uint32_t LaunchIndex, TileScratch& S) {
 				if (Llocal.z < 0.0f) continue;
 				const Material& lm = c.material[light_prim.material_ID];
 				V3 radiance = V3{lm.emission[0], lm.emission[1], lm.emission[2]} * V3{in->tr[ID], in->tg[ID], in->tb[ID]};  // :277
-				{  // Closure<Lambertian>::eval, DataStreams.hpp:169-172
+				if (!ggx) {  // Closure<Lambertian>::eval, DataStreams.hpp:169-172
 					float NdotL = smax(0.0f, Llocal.z);
 					float f = kOneOverPi * NdotL;
 					radiance = radiance * V3{S.sd.albedo[ID][0] * f, S.sd.albedo[ID][1] * f, S.sd.albedo[ID][2] * f};
-				}
+				} else radiance = radiance * ggx_eval(V3{S.sd.albedo[ID][0], S.sd.albedo[ID][1], S.sd.albedo[ID][2]}, S.sd.alpha[ID], Llocal, V3{S.sd.Vx[ID], S.sd.Vy[ID], S.sd.Vz[ID]});  // :189-195
 				light_pdf *= light_selection_pdf;
-				float brdf_pdf = kOneOverPi * smax(0.0f, Llocal.z);  // DataStreams.hpp:173-176
+				float brdf_pdf = ggx ? 0.0f : kOneOverPi * smax(0.0f, Llocal.z);  // DataStreams.hpp:173-176; GGX :196-198 (`return 0.0f; //TODO`)
 				radiance = radiance * powerHeuristic_over_f(light_pdf, brdf_pdf);
 				if (smax(smax(radiance.x, radiance.y), radiance.z) <= 0.0f) continue;
 				S.shadow.dx[shadow_index] = L.x; S.shadow.dy[shadow_index] = L.y; S.shadow.dz[shadow_index] = L.z;
@@ -559,9 +570,11 @@ static void accumulate_tile(Ctx& c, uint32_t LaunchIndex, TileScratch& S) {
 				const int32_t ID = static_cast<int32_t>(S.RayID[miss_count + i]);
 				uint32_t rng_state = hash_2d(accumulations, S.seed[in->pixelID[ID]] + static_cast<uint32_t>(bounce) * 2 + 1);  // :362
 				const float brdf_samples[2] = {rand_unit_float(&rng_state), rand_unit_float(&rng_state)};
-				V3 sdir = hemisphere(brdf_samples[0], brdf_samples[1]);  // DataStreams.hpp:177-181
+				V3 sdir, estimator;
+				if (!ggx) { sdir = hemisphere(brdf_samples[0], brdf_samples[1]); estimator = V3{S.sd.albedo[ID][0], S.sd.albedo[ID][1], S.sd.albedo[ID][2]}; }  // DataStreams.hpp:177-181
+				else ggx_sample(V3{S.sd.albedo[ID][0], S.sd.albedo[ID][1], S.sd.albedo[ID][2]}, S.sd.alpha[ID], V3{S.sd.Vx[ID], S.sd.Vy[ID], S.sd.Vz[ID]}, brdf_samples[0], brdf_samples[1], &sdir, &estimator);  // :199-218
 				V3 throughput{in->tr[ID], in->tg[ID], in->tb[ID]};
-				throughput = throughput * V3{S.sd.albedo[ID][0], S.sd.albedo[ID][1], S.sd.albedo[ID][2]};
+				throughput = throughput * estimator;
 				{  // Russian roulette :377-384 (Q13)
 					float q = 1.0f - smax(throughput.x, smax(throughput.y, throughput.z));
 					if (rand_unit_float(&rng_state) < q) { S.termination[ID] = 1; continue; }
@@ -574,7 +587,7 @@ static void accumulate_tile(Ctx& c, uint32_t LaunchIndex, TileScratch& S) {
 				out->tr[output_index] = throughput.x; out->tg[output_index] = throughput.y; out->tb[output_index] = throughput.z;
 				out->rr[output_index] = in->rr[ID]; out->rg[output_index] = in->rg[ID]; out->rb[output_index] = in->rb[ID];
 				out->pixelID[output_index] = in->pixelID[ID];
-				out->pdf[output_index] = kOneOverPi * smax(0.0f, sdir.z);  // :401 — pdf of the WORLD-space dir (Q10)
+				out->pdf[output_index] = ggx ? 0.0f : kOneOverPi * smax(0.0f, sdir.z);  // :401 — pdf of the WORLD-space dir (Q10); GGX: 0 (:196-198)
 				output_index++;
 			}
 		} else {
@@ -807,6 +820,11 @@ void orc_sample_direction_to_sphere(const float Wc[3], float s2, float cd, float
 }
 float orc_sphere_pdf(float r2, float d2) { return spherePdf(r2, d2); }
 float orc_power_heuristic(float f, float g) { return powerHeuristic(f, g); }
+void orc_distribution_visible_normals(const float v[3], float alpha, float u0, float u1, float out[3]) { V3 h = distribution_visible_normals(V3{v[0], v[1], v[2]}, alpha, u0, u1); out[0] = h.x; out[1] = h.y; out[2] = h.z; }
+void orc_microfacet_brdf(const float f0[3], float alpha, float ndv, float ndl, float ndh, float hdv, float out[3]) { V3 r = microfacet_brdf(V3{f0[0], f0[1], f0[2]}, alpha, ndv, ndl, ndh, hdv); out[0] = r.x; out[1] = r.y; out[2] = r.z; }
+void orc_vndf_estimator(const float f0[3], float alpha, float ndv, float ndl, float hdv, float out[3]) { V3 r = vndf_estimator(V3{f0[0], f0[1], f0[2]}, alpha, ndv, ndl, hdv); out[0] = r.x; out[1] = r.y; out[2] = r.z; }
+void orc_ggx_eval(const float f0[3], float alpha, const float l[3], const float v[3], float out[3]) { V3 r = ggx_eval(V3{f0[0], f0[1], f0[2]}, alpha, V3{l[0], l[1], l[2]}, V3{v[0], v[1], v[2]}); out[0] = r.x; out[1] = r.y; out[2] = r.z; }
+void orc_ggx_sample(const float f0[3], float alpha, const float v[3], float u0, float u1, float out[6]) { V3 d, e; ggx_sample(V3{f0[0], f0[1], f0[2]}, alpha, V3{v[0], v[1], v[2]}, u0, u1, &d, &e); out[0] = d.x; out[1] = d.y; out[2] = d.z; out[3] = e.x; out[4] = e.y; out[5] = e.z; }
 float orc_power_heuristic_over_f(float f, float g) { return powerHeuristic_over_f(f, g); }
 void orc_tonemap(float rgb[3]) { tonemapping(rgb[0], rgb[1], rgb[2]); }
 void orc_quat_look_at(const float dir[3], float out_wxyz[4]) { Quat q = quat_look_at(normalize(V3{dir[0], dir[1], dir[2]}), V3{0, 1, 0}); out_wxyz[0] = q.w; out_wxyz[1] = q.x; out_wxyz[2] = q.y; out_wxyz[3] = q.z; }

@@ -214,6 +214,73 @@ static inline V3 sample_direction_to_sphere(V3 Wc, float sinThetaMax2, float cen
 	        wcX.y * Ll.x + wcY.y * Ll.y + Wc.y * Ll.z,
 	        wcX.z * Ll.x + wcY.z * Ll.y + Wc.z * Ll.z};
 }
+// ---- GGX (the reference's `#define BRDF 1` build: Closure<ClosureType::GGX>, DataStreams.hpp:184-219) — Sampling.hpp:102-104,249-309
+static inline float gmix(float a, float b, float t) { return a * (1.0f - t) + b * t; }  // [glm] mix(x, y, a) = x * (1 - a) + y * a
+static inline void disk(float t, float s, float* x, float* y) {  // :102-104 via polar_to_cartesian :85-91
+	float cos_phi, sin_phi; fast_sincos(s * kTwoPi, &sin_phi, &cos_phi);
+	const float rho = std::sqrt(t);
+	*x = rho * cos_phi; *y = rho * sin_phi;
+}
+static inline V3 distribution_visible_normals(V3 Vlocal, float alpha, float u, float v) {  // :253-270
+	V3 V = normalize(V3{alpha * Vlocal.x, alpha * Vlocal.y, Vlocal.z});
+	float sx, sy; disk(u, v, &sx, &sy);
+	const float t = 1.0f - sx * sx;
+	sy = gmix(std::sqrt(t), sy, V.z * 0.5f + 0.5f);
+	V3 X, Y; orthonormal_basis(V, &X, &Y);
+	V3 H = X * sx + Y * sy + V * std::sqrt(smax(0.0f, t - sy * sy));
+	return normalize(V3{alpha * H.x, alpha * H.y, smax(0.0f, H.z)});
+}
+static inline float pow5(float x) { float t = x * x; t *= t; return x * t; }  // :272
+static inline V3 Fresnel(V3 F0, float HdotV) {  // :273-275: glm::mix(F0, Spectrum{1}, pow5(clamp(1 - HdotV, 0, 1)))
+	float c = 1.0f - HdotV; c = c < 0.0f ? 0.0f : (1.0f < c ? 1.0f : c);  // std::clamp(v, lo, hi) = v < lo ? lo : hi < v ? hi : v
+	const float a = pow5(c);
+	return V3{F0.x * (1.0f - a) + 1.0f * a, F0.y * (1.0f - a) + 1.0f * a, F0.z * (1.0f - a) + 1.0f * a};
+}
+static inline float GGX_D(float alpha2, float NdotH2) {  // :278-281
+	float temp = (1.0f + (alpha2 - 1.0f) * NdotH2);
+	return alpha2 / (kPi * temp * temp);
+}
+static inline float Smith_G2_Height_Correlated_GGX_Lagarde(float alpha2, float NdotL, float NdotV) {  // :287-291
+	float a = NdotV * std::sqrt(alpha2 + NdotL * (NdotL - alpha2 * NdotL));
+	float b = NdotL * std::sqrt(alpha2 + NdotV * (NdotV - alpha2 * NdotV));
+	return 0.5f / (a + b);
+}
+static inline V3 microfacet_brdf(V3 F0, float alpha, float NdotV, float NdotL, float NdotH, float HdotV) {  // :293-296
+	const float alpha2 = alpha * alpha;
+	return Fresnel(F0, HdotV) * (NdotL * GGX_D(smax(0.00001f, alpha2), NdotH * NdotH) * Smith_G2_Height_Correlated_GGX_Lagarde(alpha2, NdotL, NdotV));
+}
+static inline float G1_GGX(float alpha2, float NdotS2) { return 2.0f / (1.0f + std::sqrt(((alpha2 * (1.0f - NdotS2)) + NdotS2) / NdotS2)); }  // :297-299
+static inline float Smith_G2_Over_G1_Height_Correlated(float alpha2, float NdotL, float NdotV) {  // :301-305
+	float G1V = G1_GGX(alpha2, NdotV * NdotV);
+	float G1L = G1_GGX(alpha2, NdotL * NdotL);
+	return G1L / (G1V + G1L - G1V * G1L);
+}
+static inline V3 vndf_estimator(V3 F0, float alpha, float NdotV, float NdotL, float HdotV) {  // :307-309
+	return Fresnel(F0, HdotV) * Smith_G2_Over_G1_Height_Correlated(alpha * alpha, NdotL, NdotV);
+}
+// Closure<GGX>::eval, DataStreams.hpp:189-195
+static inline V3 ggx_eval(V3 F0, float alpha, V3 Llocal, V3 Vlocal) {
+	float NdotL = smax(0.0f, Llocal.z);
+	float NdotV = smax(0.0f, Vlocal.z);
+	V3 Hn = normalize(Llocal + Vlocal);
+	float NdotH = smax(0.0f, Hn.z);
+	float HdotV = smax(0.0f, dot(Hn, Vlocal));
+	return microfacet_brdf(F0, alpha, NdotV, NdotL, NdotH, HdotV);
+}
+// Closure<GGX>::sample, DataStreams.hpp:199-218: direction (local frame) and estimator
+static inline void ggx_sample(V3 F0, float alpha, V3 Vlocal, float u0, float u1, V3* dir, V3* estimator) {
+	float NdotV = smax(0.0f, Vlocal.z);
+	float HdotV;
+	if (alpha == 0.0f) { *dir = V3{-Vlocal.x, -Vlocal.y, Vlocal.z}; HdotV = NdotV; }
+	else {
+		V3 Hlocal = distribution_visible_normals(Vlocal, alpha, u0, u1);
+		HdotV = dot(Hlocal, Vlocal);
+		*dir = Hlocal * (2.0f * HdotV) - Vlocal;   // (2.0f * HdotV) * Hlocal - Vlocal
+		HdotV = smax(0.0f, HdotV);
+	}
+	float NdotL = smax(0.0f, dir->z);
+	*estimator = vndf_estimator(F0, alpha, NdotV, NdotL, HdotV);
+}
 static inline float powerHeuristic(float f, float g) { float f2 = f * f; return f2 / smax(1e-6f, f2 + g * g); }  // :241-244
 static inline float powerHeuristic_over_f(float f, float g) { return f / smax(1e-6f, f * f + g * g); }  // :245-247
 

@@ -9,7 +9,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-ORC_BVH, ORC_SLOT_EXACT, ORC_NO_MIS = 1, 2, 4
+ORC_BVH, ORC_SLOT_EXACT, ORC_NO_MIS, ORC_GGX = 1, 2, 4, 8
 
 _f = C.c_float; _u = C.c_uint32; _i = C.c_int32; _p = C.c_void_p
 _fp = C.POINTER(C.c_float); _up = C.POINTER(C.c_uint32)
@@ -185,39 +185,39 @@ def tile_to_raster(buf_tileorder, width, height):
 
 # ---------------------------------------------------------------------------------------------- the reference itself
 REF_RENDERER_PATH = os.path.join(_HERE, "_ref", "librefrenderer.so")
+REF_RENDERER_GGX_PATH = os.path.join(_HERE, "_ref", "librefrenderer_ggx.so")  # the same sources with `#define BRDF 1` (ref_renderer_build.sh)
 REF_MAX_BOUNCES = (1, 2, 4, 8, 16)  # Renderer<>'s max_bounces is a template argument: the values instantiated by ref_renderer_wrap.cpp
 ORC_SLOT_EXACT = 2  # oracle flag: closest-hit SIMD blocks of 8 + scalar tail by stream slot, exactly as BVH.hpp:250-286
 
 
-def have_reference_renderer():
-    return os.path.exists(REF_RENDERER_PATH)
+def have_reference_renderer(ggx=False):
+    return os.path.exists(REF_RENDERER_GGX_PATH if ggx else REF_RENDERER_PATH)
 
 
-_ref_renderer = None
+_ref_renderer = {}
 
 
-def _ref_renderer_lib():
-    global _ref_renderer
-    if _ref_renderer is None:
-        L = C.CDLL(REF_RENDERER_PATH)
+def _ref_renderer_lib(ggx=False):
+    if ggx not in _ref_renderer:
+        L = C.CDLL(REF_RENDERER_GGX_PATH if ggx else REF_RENDERER_PATH)
         L.ref_renderer_create.restype = _p
         L.ref_renderer_create.argtypes = [_p, _u, _p, _u, _p, _p, _f, _f, _p, _p, _i, _i, _u, _u, _u]
         L.ref_renderer_destroy.argtypes = [_p]; L.ref_renderer_accumulate.argtypes = [_p, _u]; L.ref_renderer_set_accumulations.argtypes = [_p, _u]
         L.ref_renderer_accumulations.restype = _u; L.ref_renderer_accumulations.argtypes = [_p]
         L.ref_renderer_read_buckets.argtypes = [_p, _p]; L.ref_renderer_render.restype = C.c_int; L.ref_renderer_render.argtypes = [_p, _p, _u]
         L.ref_renderer_light_count.restype = _u; L.ref_renderer_light_count.argtypes = [_p]
-        _ref_renderer = L
-    return _ref_renderer
+        _ref_renderer[ggx] = L
+    return _ref_renderer[ggx]
 
 
 class ReferenceRenderer:
     """The reference's OWN Renderer<> (Renderer.hpp) compiled from /root/reference by oracle/ref_renderer_build.sh — same calls as
     Oracle: accumulate(n), buckets() -> [5][3][npix] (tile order), render() -> (acted, RGBA32F raster frame). K is fixed at 5."""
 
-    def __init__(self, scene, width, height, max_bounces=16):
+    def __init__(self, scene, width, height, max_bounces=16, ggx=False):
         if max_bounces not in REF_MAX_BOUNCES:
             raise ValueError(f"max_bounces must be one of {REF_MAX_BOUNCES} (template instantiations)")
-        self.L = _ref_renderer_lib(); self.w, self.h = width, height
+        self.L = _ref_renderer_lib(ggx); self.w, self.h = width, height
         sd = _scene_dtypes()
         self._geo = np.ascontiguousarray(scene["geometry"], dtype=sd[0]); self._mat = np.ascontiguousarray(scene["material"], dtype=sd[1])
         cam = scene["camera"]; eye = farr(*cam["eye"]); d = farr(*cam["dir"]); amb = farr(*scene["ambient"])

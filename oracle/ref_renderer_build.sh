@@ -20,3 +20,13 @@ sed -e 's/typename const /const typename /g' "$REF/DataStreams.hpp" > "$T/DataSt
 g++ -std=c++23 -fPIC -shared -O2 -mavx2 -mfma -mbmi -mbmi2 -mlzcnt -ffp-contract=off -Wno-attributes -fpermissive -w -pthread -Wl,-Bsymbolic \
     '-D__assume(x)=' -D__vectorcall= -I "$T" -I "$HERE/ref_shim" "$HERE/ref_renderer_wrap.cpp" -o "$OUT"
 echo "built $OUT from $REF/Renderer.hpp and the files it includes"
+# The reference's GGX build (`#define BRDF 1`, Renderer.hpp:70): the same sources with that one token changed. As shipped it does not
+# compile — Renderer.hpp:212 reads `gloss_decay_table[bounce]`, which no file of the reference declares — so the table is supplied here:
+# all zeros ("gloss is not reduced on later bounces"), the one input of this build that is not the reference's.
+OUT_GGX=$HERE/_ref/librefrenderer_ggx.so
+rm "$T/Renderer.hpp"; sed -e 's/^#define BRDF 0/#define BRDF 1/' "$REF/Renderer.hpp" > "$T/Renderer.hpp"
+grep -q '^#define BRDF 1' "$T/Renderer.hpp"
+echo 'static constexpr float gloss_decay_table[1025] = {};' > "$T/gloss_decay_table.h"
+g++ -std=c++23 -fPIC -shared -O2 -mavx2 -mfma -mbmi -mbmi2 -mlzcnt -ffp-contract=off -Wno-attributes -fpermissive -w -pthread -Wl,-Bsymbolic \
+    '-D__assume(x)=' -D__vectorcall= -include "$T/gloss_decay_table.h" -I "$T" -I "$HERE/ref_shim" "$HERE/ref_renderer_wrap.cpp" -o "$OUT_GGX"
+echo "built $OUT_GGX: the same with #define BRDF 1 and an all-zero gloss_decay_table"

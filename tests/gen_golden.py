@@ -16,6 +16,8 @@
 * renderer_kat.json — outputs of the reference's OWN Renderer<>::Accumulate / Render (Renderer.hpp and everything it includes, compiled into
                     oracle/_ref/librefrenderer.so by oracle/ref_renderer_build.sh): digests of the five bucket-sum planes and of the
                     tonemapped RGBA32F frame for small renders of the default, random, white-furnace and sky/HDRI scenes.
+* renderer_ggx_kat.json — the same from the reference's GGX build (`#define BRDF 1`, Renderer.hpp:70; oracle/_ref/librefrenderer_ggx.so, with the
+                    all-zero gloss_decay_table that build has to supply).
 * survey_kat.json — the known-answer table of SURVEY.md §8c (derived from the same reference file), transcribed.
 * oracle_frames.json — outputs of the ORACLE (not the reference, which cannot be built: SURVEY §8c) on small inputs: bucket-sum
                     checksums, counters, BVH order. They pin the oracle against accidental change and give the GPU tests a
@@ -348,6 +350,31 @@ def renderer_record(buckets, acted, frame):
             "sum_rgb": [float(v) for v in np.asarray(buckets).sum(axis=(0, 2), dtype=np.float64)]}
 
 
+def renderer_ggx_cases():
+    """the same for the reference's GGX build (`#define BRDF 1`, oracle/_ref/librefrenderer_ggx.so; gloss_decay_table all zeros)"""
+    return [
+        ("ggx_default_64x48_mb8", scenes.default_scene(), 64, 48, 8, 5, 0),          # roughness 0.05 .. 1, F0 0.03 .. 0.94
+        ("ggx_default_96x64_mb16_from_acc60", scenes.default_scene(), 96, 64, 16, 5, 60),
+        ("ggx_random300_64x48_mb4", scenes.ggx_random_scene(300), 64, 48, 4, 5, 0),  # one mirror material (alpha == 0)
+        ("ggx_random2000_48x32_mb16", scenes.ggx_random_scene(2000, light_every=100), 48, 32, 16, 5, 0),
+        ("ggx_brdf_test_64x48_mb8", scenes.brdf_test_scene(hdri=scenes.synthetic_hdri(24, 12, seed=2)), 64, 48, 8, 5, 0),  # Application.cpp:123-217: the scene made for this closure
+    ]
+
+
+def gen_renderer_ggx():
+    oracle_py.build()
+    out = {}
+    for name, sc, w, h, mb, n, first in renderer_ggx_cases():
+        r = oracle_py.ReferenceRenderer(sc, w, h, mb, ggx=True)
+        if first:
+            r.set_accumulations(first)
+        r.accumulate(n)
+        acted, frame = r.render()
+        out[name] = renderer_record(r.buckets(), acted, frame)
+        r.close()
+    json.dump(out, open(os.path.join(HERE, "golden", "renderer_ggx_kat.json"), "w"), indent=0)
+
+
 def gen_renderer():
     oracle_py.build()
     out = {}
@@ -423,5 +450,5 @@ def gen_frames():
 
 
 if __name__ == "__main__":
-    gen_rng(); gen_sampling(); gen_camera_move(); gen_bvh(); gen_bvh_heuristics(); gen_renderer(); gen_survey(); gen_frames()
+    gen_rng(); gen_sampling(); gen_camera_move(); gen_bvh(); gen_bvh_heuristics(); gen_renderer(); gen_renderer_ggx(); gen_survey(); gen_frames()
     print("golden vectors written")

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 using namespace b2r;
@@ -48,7 +49,7 @@ int hc_render_sample(const b2r_sphere* prims, const b2r_bvh_node* nodes, uint32_
 	else flatten_bvh(nodes, n_nodes, prims, n_prims, wide, &ob);  // B2R_FLAG_REFERENCE_TREE
 	if (wide.max_stack + 3u > static_cast<uint32_t>(kTraversalStack)) return B2R_ERR_BVH;
 	SceneDev sc{};
-	sc.prims = ps.prims.data(); sc.prim_mat = ps.prim_mat.data(); sc.mat_albedo = ps.mat_albedo.data(); sc.mat_emission = ps.mat_emission.data();
+	sc.prims = ps.prims.data(); sc.prim_mat = ps.prim_mat.data(); sc.mat_albedo = ps.mat_albedo.data(); sc.mat_emission = ps.mat_emission.data(); sc.mat_f0 = ps.mat_f0.data();
 	sc.light_sphere = ps.light_sphere.data(); sc.light_emit = ps.light_emit.data(); sc.wide = wide.nodes.data(); sc.hdri = nullptr;
 	sc.n_prims = n_prims; sc.n_mat = n_mat; sc.n_lights = n_lights; sc.light_sel_pdf = 1.0f / static_cast<float>(n_lights);
 	sc.has_ambient = (ambient && hdri_rgba && sel_max(ambient[0], sel_max(ambient[1], ambient[2])) > 0.0f) ? 1 : 0;  // Renderer.hpp:79
@@ -63,6 +64,8 @@ int hc_render_sample(const b2r_sphere* prims, const b2r_bvh_node* nodes, uint32_
 	std::memset(rad_out, 0, sizeof(float) * 3 * fr.npix);
 	for (int k = 0; k < 5; k++) counters[k] = 0;
 	uint32_t cs = 0, cb = 0;
+	auto trace_all = [&](auto ggx_tag) {  // B2R_FLAG_GGX: the same loop with the GGX closure's shading routines (k_shade<EXACT, GGX> / k_bounce_brute<..., GGX>)
+	constexpr bool GGX = decltype(ggx_tag)::value;
 	for (uint32_t t = 0; t < fr.npix; t++) {
 		PathState s = primary_path(fr, fr.cam, acc, 0, t);
 		const uint32_t seed = pixel_seed(t, max_bounces);
@@ -80,9 +83,9 @@ int hc_render_sample(const b2r_sphere* prims, const b2r_bvh_node* nodes, uint32_
 				counters[3]++; break;
 			}
 			counters[2]++;
-			const Surface sf = shade_surface(sc, s, best, prim);
+			const Surface sf = shade_surface<GGX>(sc, s, best, prim);
 			if (last) { rad_zero(rad_out, fr.npix, s.pid); counters[4]++; break; }
-			ShadowRay sr; bool want_shadow = mis && shade_light_sample(sc, sf, s, prim, acc, seed, bounce, &sr);
+			ShadowRay sr; bool want_shadow = mis && shade_light_sample<GGX>(sc, sf, s, prim, acc, seed, bounce, &sr);
 			f3 e{0, 0, 0};
 			if (sf.emissive) e = shade_emission(sc, sf, s, best, bounce, mis);
 			if (want_shadow) {
@@ -96,9 +99,11 @@ int hc_render_sample(const b2r_sphere* prims, const b2r_bvh_node* nodes, uint32_
 				if (occ) want_shadow = false;
 			}
 			if (want_shadow || sf.emissive) rad_add(rad_out, fr.npix, s.pid, sr.L, e, want_shadow, sf.emissive);
-			if (!shade_continue(sf, &s, acc, seed, bounce)) { counters[3]++; break; }
+			if (!shade_continue<GGX>(sf, &s, acc, seed, bounce)) { counters[3]++; break; }
 		}
 	}
+	};
+	if (flags & B2R_FLAG_GGX) trace_all(std::true_type{}); else trace_all(std::false_type{});
 	return 0;
 }
 
@@ -369,6 +374,50 @@ extern "C" int hc_anyhit_local_stats(const b2r_sphere* prims, uint32_t n_prims, 
 		if (!occ_local && start != 0u) occ_local = walk(0u, start, &sl);
 		if (occ_root != occ_local) bad++;
 		steps_root[i] = sr; steps_local[i] = sl;
+	}
+	return bad;
+}
+
+// closest-hit walk started at the node that holds the origin sphere and climbing to the root (tuning aid), against the walk from the root:
+// node visits, pushes and pops (culled ones included) per ray. out[6 * i + {0,1,2}] = root walk, {3,4,5} = climbing walk. Returns mismatches.
+extern "C" int hc_closest_climb_stats(const b2r_sphere* prims, uint32_t n_prims, const float* rays, const int32_t* origin_prim, uint32_t n, uint32_t* out) {
+	float ro[6]; ray_origin_bounds(rays, n, ro);
+	const OriginBox ob = origin_box_of(prims, n_prims, nullptr, ro, 2);
+	std::vector<b2r_bvh_node> tn; build_traversal_tree(prims, n_prims, tn);
+	WideBvh w; flatten_bvh(tn.data(), static_cast<uint32_t>(tn.size()), prims, n_prims, w, &ob);
+	const float4* wide = reinterpret_cast<const float4*>(w.nodes.data());
+	const uint32_t nn = static_cast<uint32_t>(w.nodes.size());
+	std::vector<uint32_t> parent(nn, 0u), leaf_node(n_prims, 0u);
+	for (uint32_t nd = 0; nd < nn; nd++) for (int k = 0; k < 4; k++) { const int32_t l = as_int(wide[static_cast<size_t>(nd) * 8 + 2 * k + 1].z); if (l == kEmptyLink) continue; if (l < 0) leaf_node[~l] = nd; else parent[l] = nd; }
+	int bad = 0;
+	for (uint32_t i = 0; i < n; i++) {
+		const float* r = rays + 6 * static_cast<size_t>(i);
+		TravBase t; t.arm(Ray{r[0], r[1], r[2], r[3], r[4], r[5]});
+		float bestm[2]; int32_t primm[2];
+		for (int mode = 0; mode < 2; mode++) {
+			struct E { uint32_t node; float tn; }; std::vector<E> stack; float best = FLT_MAX; int32_t prim = -1; uint32_t st = 0, pushes = 0, pops = 0; bool have = true;
+			uint32_t root = mode == 0 ? 0u : leaf_node[origin_prim[i]], skip = 0xffffffffu, node = root;
+			while (have) {
+				st++;
+				const float4* nd = wide + static_cast<size_t>(node) * 8;
+				E kids[4]; int nk = 0;
+				for (int k = 0; k < 4; k++) {
+					const float4 a = nd[2 * k], b = nd[2 * k + 1]; const int32_t l = as_int(b.z);
+					float tnr; bool h; slab(a, b, t.ix, t.iy, t.iz, t.nx, t.ny, t.nz, t.ax, t.ay, t.az, best, &tnr, &h);
+					if (!h) continue;
+					if (l < 0) { float d; if (sphere_hit_closest(a.x, a.y, a.z, a.w, t.ox, t.oy, t.oz, t.dx, t.dy, t.dz, &d) && (d < best || (d == best && ~l < prim))) { best = d; prim = ~l; } }
+					else if (static_cast<uint32_t>(l) != skip) kids[nk++] = {static_cast<uint32_t>(l), tnr};
+				}
+				std::stable_sort(kids, kids + nk, [](const E& x, const E& y) { return x.tn < y.tn; });
+				for (int k = nk - 1; k >= 1; k--) if (kids[k].tn <= best) { stack.push_back(kids[k]); pushes++; }
+				have = false;
+				if (nk && kids[0].tn <= best) { node = kids[0].node; have = true; }
+				else while (!stack.empty()) { const E e = stack.back(); stack.pop_back(); pops++; if (e.tn <= best) { node = e.node; have = true; break; } }
+				if (!have && root != 0u) { skip = root; root = parent[root]; node = root; have = true; }
+			}
+			bestm[mode] = best; primm[mode] = prim; out[6 * static_cast<size_t>(i) + 3 * mode] = st; out[6 * static_cast<size_t>(i) + 3 * mode + 1] = pushes; out[6 * static_cast<size_t>(i) + 3 * mode + 2] = pops;
+		}
+		if (primm[0] != primm[1] || bits(bestm[0]) != bits(bestm[1])) bad++;
 	}
 	return bad;
 }

@@ -123,6 +123,24 @@ def test_sky_scenes_bit_exact(hostcheck, name, use_bvh):
         else: assert float(rad.max()) > 0.0
 
 
+@pytest.mark.parametrize("name,use_bvh", [("default", 0), ("default", 2), ("ggx_random", 0), ("ggx_random", 2), ("brdf_test", 1)])
+def test_ggx_closure_bit_exact(hostcheck, name, use_bvh):
+    """B2R_FLAG_GGX: the product's GGX shading routines (b2r_math.h ggx_*, shade_*<true>) against the oracle's ORC_GGX mode — which is pinned to
+    the reference's own `#define BRDF 1` build (tests/test_oracle_ref_renderer.py) — bit for bit, mirror branch (alpha == 0) included."""
+    sc = {"default": scenes.default_scene, "ggx_random": lambda: scenes.ggx_random_scene(1500, light_every=40), "brdf_test": scenes.brdf_test_scene}[name]()
+    w, h, mb = 128, 80, 8
+    o = oracle_py.Oracle(w, h, max_bounces=mb, K=1, flags=oracle_py.ORC_GGX); o.set_scene(sc)
+    lam = oracle_py.Oracle(w, h, max_bounces=mb, K=1); lam.set_scene(sc); lam.accumulate(1)
+    for acc in (1, 9):
+        o.reset(); o.reset_counters(); o.set_accumulations(acc - 1); o.accumulate(1)
+        ref = o.buckets()[0]; oc = o.counters()
+        rad, cnt = render_hc(hostcheck, sc, w, h, mb, acc, use_bvh, flags=b2r.FLAG_GGX)
+        assert rad.tobytes() == ref.tobytes()
+        assert cnt[0] == oc["extension_rays"] and cnt[2] == oc["shaded_hits"] and cnt[3] == oc["terminated"] and cnt[4] == oc["dropped"]
+        assert np.isfinite(rad).all() and float(rad.max()) > 0.0
+        if acc == 1: assert rad.tobytes() != lam.buckets()[0].tobytes()
+
+
 def test_no_mis_variant(hostcheck):
     sc = scenes.default_scene()
     o = oracle_py.Oracle(160, 96, max_bounces=8, K=1, flags=oracle_py.ORC_NO_MIS); o.set_scene(sc); o.accumulate(1)

@@ -73,3 +73,36 @@ def test_canonical_mode_within_north_star_tolerance_of_reference():
     rmse = float(np.sqrt(np.mean((frame[..., :3] - rframe[..., :3]) ** 2)))
     print(f"canonical oracle vs reference renderer: divergent per-sample pixel fraction {divergent:.3e}, converged (200 spp) tonemapped RMSE {rmse:.3e}")
     assert racted and acted and divergent < 2e-3 and rmse < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------- GGX closure (the reference's `#define BRDF 1` build)
+live_ggx = pytest.mark.skipif(not oracle_py.have_reference_renderer(ggx=True), reason="oracle/_ref/librefrenderer_ggx.so not present (built only where /root/reference exists)")
+
+
+def test_oracle_ggx_mode_reproduces_the_references_brdf1_build_golden():
+    """ORC_GGX restates Closure<GGX> (DataStreams.hpp:184-219) and Sampling.hpp:249-309; the fixture holds what the reference's own
+    Renderer<> computes when built with `#define BRDF 1` (and the all-zero gloss_decay_table that build needs to compile at all)."""
+    want = json.load(open(os.path.join(G, "renderer_ggx_kat.json")))
+    for name, sc, w, h, mb, n, first in gen_golden.renderer_ggx_cases():
+        b, acted, frame = oracle_run(sc, w, h, mb, n, first, oracle_py.ORC_SLOT_EXACT | oracle_py.ORC_GGX)
+        got = gen_golden.renderer_record(b, acted, frame)
+        assert got["sha256_buckets"] == want[name]["sha256_buckets"], f"{name}: bucket sums differ from the reference's BRDF 1 build"
+        assert got["render_acted"] == want[name]["render_acted"] and got["sha256_frame"] == want[name]["sha256_frame"], name
+        assert np.isfinite(b).all()
+
+
+@live_ggx
+def test_live_ggx_bit_exact():
+    cases = [("default", scenes.default_scene(), 112, 80, 8, 10, 0), ("ggx_random900", scenes.ggx_random_scene(900, light_every=30), 64, 64, 16, 5, 5),
+             ("brdf_test", scenes.brdf_test_scene(hdri=scenes.synthetic_hdri(24, 12, seed=2)), 64, 48, 4, 10, 0)]
+    for name, sc, w, h, mb, n, first in cases:
+        r = oracle_py.ReferenceRenderer(sc, w, h, mb, ggx=True)
+        if first:
+            r.set_accumulations(first)
+        r.accumulate(n); rb = r.buckets(); racted, rframe = r.render(); r.close()
+        b, acted, frame = oracle_run(sc, w, h, mb, n, first, oracle_py.ORC_SLOT_EXACT | oracle_py.ORC_GGX)
+        assert rb.tobytes() == b.tobytes(), name
+        assert racted == acted and rframe.tobytes() == frame.tobytes(), name
+        # and it is a different image from the Lambertian build's (the closure is really in use)
+        lb, _, _ = oracle_run(sc, w, h, mb, n, first, oracle_py.ORC_SLOT_EXACT)
+        assert lb.tobytes() != b.tobytes(), name
