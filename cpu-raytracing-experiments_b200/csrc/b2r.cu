@@ -102,6 +102,7 @@ struct b2r_ctx {
 	// descriptors) inside one graph, so that the drained end of every launch of one half is filled by the other half's kernels
 	cudaGraphExec_t twin_exec = nullptr; bool twin_valid = false, twin_enabled = true;
 	cudaStream_t lane_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+	float lane_grid_frac = 1.0f;
 	uint64_t graph_launches = 0, twin_launches = 0;  // kernels one replay of each graph launches (counted while capturing)
 	uint64_t launches = 0;
 	// profiling (B2R_FLAG_NO_GRAPH): events around every launch
@@ -209,6 +210,7 @@ int compute_grids(b2r_ctx* c) {
 	if ((rc = occ(reinterpret_cast<const void*>(&k_shade<false, true>), kBruteBlock, &c->grid_shade_ggx))) return rc;
 	c->packet_primary = std::getenv("B2R_NO_PACKET") == nullptr;  // A/B switch for measurements: per-lane walks for the camera rays too
 	c->twin_enabled = std::getenv("B2R_NO_TWIN") == nullptr;      // A/B switch for measurements: every batch as one lane
+	if (const char* e = std::getenv("B2R_LANE_GRID")) { c->lane_grid_frac = static_cast<float>(std::atof(e)); if (!(c->lane_grid_frac > 0.0f && c->lane_grid_frac <= 1.0f)) c->lane_grid_frac = 1.0f; }
 	c->grid_stream = c->sm_count * 8;
 	return B2R_OK;
 }
@@ -225,8 +227,11 @@ template <typename F> int launch(b2r_ctx* c, int kind, bool profile, F&& f) {
 }
 
 // The max_bounces rounds of one batch — or of one lane's half of it — on stream st; p carries that batch's queues, counters and descriptor.
-int enqueue_rounds(b2r_ctx* c, const Params& p_in, cudaStream_t st, bool profile) {
+int enqueue_rounds(b2r_ctx* c, const Params& p_in, cudaStream_t st, bool profile, float grid_frac = 1.0f) {
 	const Params& p = p_in;
+	// (measurement tap, B2R_LANE_GRID: the lanes of a twin batch may be given a fraction of the resident-CTA grid each, so that the two lanes'
+	// kernels sit on every SM side by side instead of taking turns)
+	auto G = [&](int g) { const int per_sm = g / c->sm_count; int k = static_cast<int>(per_sm * grid_frac + 0.5f); if (k < 1) k = 1; return k * c->sm_count; };
 	const bool count = (c->cfg.flags & B2R_FLAG_COUNT_TESTS) != 0;
 	const uint32_t mb = c->cfg.max_bounces;
 	int rc;
@@ -264,20 +269,20 @@ int enqueue_rounds(b2r_ctx* c, const Params& p_in, cudaStream_t st, bool profile
 		if (exact && c->params.scene.n_mat > 64) return fail(B2R_ERR_STATE, "B2R_FLAG_REFERENCE_EXACT: at most 64 materials (RendererPolicy::max_materialID, Renderer.hpp:23)");
 		for (uint32_t b = 0; b < mb; b++) {
 			if (b == 0 && c->packet_primary) {  // camera rays: one walk per warp (k_intersect_packet)
-				if ((rc = launch(c, KK_CLOSEST, profile, [&] { if (count) k_intersect_packet<true><<<c->grid_packet, kTravBlock, 0, st>>>(p, b); else k_intersect_packet<false><<<c->grid_packet, kTravBlock, 0, st>>>(p, b); }))) return rc;
+				if ((rc = launch(c, KK_CLOSEST, profile, [&] { if (count) k_intersect_packet<true><<<G(c->grid_packet), kTravBlock, 0, st>>>(p, b); else k_intersect_packet<false><<<G(c->grid_packet), kTravBlock, 0, st>>>(p, b); }))) return rc;
 			} else
 			if ((rc = launch(c, KK_CLOSEST, profile, [&] {
 				// stack entries split 16/16 (up to 65536 wide nodes: C3) get immediate shifts; other sizes read the split from the scene
 				const bool tn16 = c->params.scene.stack_tn_bits == 16u;
-#define B2R_CLOSEST(COUNT, EXACT) do { if (tn16) k_intersect_closest<COUNT, EXACT, 16u><<<c->grid_closest, kTravBlock, 0, st>>>(p, b); else k_intersect_closest<COUNT, EXACT, 0u><<<c->grid_closest, kTravBlock, 0, st>>>(p, b); } while (0)
+#define B2R_CLOSEST(COUNT, EXACT) do { if (tn16) k_intersect_closest<COUNT, EXACT, 16u><<<G(c->grid_closest), kTravBlock, 0, st>>>(p, b); else k_intersect_closest<COUNT, EXACT, 0u><<<G(c->grid_closest), kTravBlock, 0, st>>>(p, b); } while (0)
 				if (exact) { if (count) B2R_CLOSEST(true, true); else B2R_CLOSEST(false, true); }
 				else { if (count) B2R_CLOSEST(true, false); else B2R_CLOSEST(false, false); }
 #undef B2R_CLOSEST
 			}))) return rc;
-			if ((rc = launch(c, KK_SHADE, profile, [&] { if (c->cfg.flags & B2R_FLAG_GGX) k_shade<false, true><<<c->grid_shade_ggx, kBruteBlock, 0, st>>>(p, b); else if (exact) k_shade<true><<<c->grid_shade, kBruteBlock, 0, st>>>(p, b); else k_shade<false><<<c->grid_shade, kBruteBlock, 0, st>>>(p, b); }))) return rc;
+			if ((rc = launch(c, KK_SHADE, profile, [&] { if (c->cfg.flags & B2R_FLAG_GGX) k_shade<false, true><<<G(c->grid_shade_ggx), kBruteBlock, 0, st>>>(p, b); else if (exact) k_shade<true><<<G(c->grid_shade), kBruteBlock, 0, st>>>(p, b); else k_shade<false><<<G(c->grid_shade), kBruteBlock, 0, st>>>(p, b); }))) return rc;
 			if (exact && b + 1 < mb) { if ((rc = launch(c, KK_SHADE, profile, [&] { k_stream_rank<<<c->grid_stream, 256, 0, st>>>(p, b); }))) return rc; }
 			if (mis && b + 1 < mb) {
-				if ((rc = launch(c, KK_SHADOW, profile, [&] { if (count) k_intersect_shadow<true><<<c->grid_shadow, kTravBlock, 0, st>>>(p, b); else k_intersect_shadow<false><<<c->grid_shadow, kTravBlock, 0, st>>>(p, b); }))) return rc;
+				if ((rc = launch(c, KK_SHADOW, profile, [&] { if (count) k_intersect_shadow<true><<<G(c->grid_shadow), kTravBlock, 0, st>>>(p, b); else k_intersect_shadow<false><<<G(c->grid_shadow), kTravBlock, 0, st>>>(p, b); }))) return rc;
 			}
 		}
 	}
@@ -309,8 +314,8 @@ int enqueue_batch(b2r_ctx* c, bool profile, bool twin) {
 	else {
 		// fork: lane B's rounds on the second stream, lane A's on the main one; join before the fold (which adds in sample order over both)
 		CU(cudaEventRecord(c->ev_fork, st)); CU(cudaStreamWaitEvent(c->lane_stream, c->ev_fork, 0));
-		if ((rc = enqueue_rounds(c, lane_params(c, 0), st, false))) return rc;
-		if ((rc = enqueue_rounds(c, lane_params(c, 1), c->lane_stream, false))) return rc;
+		if ((rc = enqueue_rounds(c, lane_params(c, 0), st, false, c->lane_grid_frac))) return rc;
+		if ((rc = enqueue_rounds(c, lane_params(c, 1), c->lane_stream, false, c->lane_grid_frac))) return rc;
 		CU(cudaEventRecord(c->ev_join, c->lane_stream)); CU(cudaStreamWaitEvent(st, c->ev_join, 0));
 	}
 	return launch(c, KK_ACCUMULATE, profile, [&] { k_accumulate<<<c->grid_stream, kBlock, 0, st>>>(c->params); });

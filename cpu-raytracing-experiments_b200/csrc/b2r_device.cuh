@@ -40,6 +40,7 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 	float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
 	return v;
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ PathState load_path(const QueueDev& q, int side, uint32_t i) {
 	const float4 a = q.A[side][i], b = q.B[side][i];
 	PathState s; s.ox = a.x; s.oy = a.y; s.oz = a.z; s.dx = a.w; s.dy = b.x; s.dz = b.y; s.pdf = b.z; s.pid = __float_as_uint(b.w);
@@ -761,6 +762,15 @@ __global__ void __launch_bounds__(kBruteBlock, B2R_SHADE_MIN_BLOCKS) k_shade(con
 			float depth = FLT_MAX; int32_t prim = -1;
 			if (live) { const float2 h = p.q.H[i]; depth = h.x; prim = __float_as_int(h.y); }
 			const bool is_hit = live && prim >= 0;
+#ifndef B2R_NO_SHADE_PREFETCH
+			// what the shading phase will read for this hit — its path record (44 B over five planes), its sphere and material id — is asked for
+			// now, before the hits are compacted behind two barriers: the shading phase's dependent round trips then hit in L1
+			if (is_hit) {
+				prefetch_l1(p.q.A[side] + i); prefetch_l1(p.q.B[side] + i); prefetch_l1(p.q.T[side] + i); prefetch_l1(p.q.T[side] + p.q.cap + i); prefetch_l1(p.q.T[side] + 2u * p.q.cap + i);
+				prefetch_l1(sc.prims + prim); prefetch_l1(sc.prim_mat + prim); prefetch_l1(sc.leaf_node + prim);
+			}
+			if (base + gridDim.x * kBruteBlock + threadIdx.x < n_in) prefetch_l1(p.q.H + base + gridDim.x * kBruteBlock + threadIdx.x);  // the next chunk's hit records
+#endif
 			if (live && !is_hit) {  // miss shader (Renderer.hpp:408-420)
 				c_term++;
 				if (sc.has_ambient) { const PathState sm = load_path(p.q, side, i); rad_add(p.rad, p.frame.npix, sm.pid, shade_sky(sc, sm), f3{0.0f, 0.0f, 0.0f}, true, false); c_events++; }
