@@ -10,7 +10,7 @@ M="gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__issue
 # 15 x k_intersect_shadow, k_accumulate, k_resolve = 50 launches; 3 warm-up steps precede it
 timeout 300 $C3 > gpurun_out/r02_c3_plain.log 2>&1 || exit 1
 # (1) every launch of one C3 step with its device time
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 50 --csv --log-file gpurun_out/r02_c3_launches.csv $C3 > gpurun_out/r02_c3_ncu1.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_set_batch|k_intersect_packet|k_intersect_closest|k_intersect_shadow|k_shade|k_accumulate|k_resolve" -s 150 -c 50 --csv --log-file gpurun_out/r02_c3_launches.csv $C3 > gpurun_out/r02_c3_ncu1.log 2>&1
 # (2) DRAM bytes, issue / L1 utilisation, active lanes of EVERY traversal and shading launch of the same step (the roofline's population)
 timeout 900 ncu --metrics $M --clock-control none -k regex:"k_intersect_packet|k_intersect_closest|k_intersect_shadow|k_shade|k_accumulate|k_resolve" -s 147 -c 49 --csv --log-file gpurun_out/r02_c3_metrics.csv $C3 > gpurun_out/r02_c3_ncu2.log 2>&1
 # (3) full sections + source for a mid-path bounce (bounce 4: closest, shade, shadow) of the same step, and for the packet kernel (bounce 0)
