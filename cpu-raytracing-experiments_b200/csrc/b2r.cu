@@ -202,7 +202,7 @@ int compute_grids(b2r_ctx* c) {
 	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_closest<false, false, 16u>), kTravBlock, &c->grid_closest))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_shade<false>), kBruteBlock, &c->grid_shade))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_shadow<false>), kTravBlock, &c->grid_shadow))) return rc;
-	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_packet<false>), kTravBlock, &c->grid_packet))) return rc;
+	if ((rc = occ(reinterpret_cast<const void*>(&k_intersect_packet<false, B2R_PACKET_RPL>), kTravBlock, &c->grid_packet))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_brute_finish<false>), kBruteBlock, &c->grid_brute_finish))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<true, false, false, true>), kBruteBlock, &c->grid_brute_first_ggx))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_bounce_brute<false, false, false, true>), kBruteBlock, &c->grid_brute_ggx))) return rc;
@@ -269,7 +269,7 @@ int enqueue_rounds(b2r_ctx* c, const Params& p_in, cudaStream_t st, bool profile
 		if (exact && c->params.scene.n_mat > 64) return fail(B2R_ERR_STATE, "B2R_FLAG_REFERENCE_EXACT: at most 64 materials (RendererPolicy::max_materialID, Renderer.hpp:23)");
 		for (uint32_t b = 0; b < mb; b++) {
 			if (b == 0 && c->packet_primary) {  // camera rays: one walk per warp (k_intersect_packet)
-				if ((rc = launch(c, KK_CLOSEST, profile, [&] { if (count) k_intersect_packet<true><<<G(c->grid_packet), kTravBlock, 0, st>>>(p, b); else k_intersect_packet<false><<<G(c->grid_packet), kTravBlock, 0, st>>>(p, b); }))) return rc;
+				if ((rc = launch(c, KK_CLOSEST, profile, [&] { if (count) k_intersect_packet<true, B2R_PACKET_RPL><<<G(c->grid_packet), kTravBlock, 0, st>>>(p, b); else k_intersect_packet<false, B2R_PACKET_RPL><<<G(c->grid_packet), kTravBlock, 0, st>>>(p, b); }))) return rc;
 			} else
 			if ((rc = launch(c, KK_CLOSEST, profile, [&] {
 				// stack entries split 16/16 (up to 65536 wide nodes: C3) get immediate shifts; other sizes read the split from the scene

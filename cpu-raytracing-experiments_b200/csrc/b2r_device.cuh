@@ -628,7 +628,14 @@ struct SmemStack {
 // (REDUX.MIN), and there is ONE stack per warp in shared memory with no per-lane loops at all. Each lane still keeps its own closest
 // hit, and a lane only tests spheres whose box its own ray passes, so every lane's result is exactly what its own walk would give.
 constexpr int kPacketStack = 64;
-template <bool COUNT>
+// RPL rays per lane: a packet is 32 * RPL consecutive tile-order pixels (RPL = 4: eight rows of 16 = half a 16x16 tile, of one sample). The node
+// fetch, the link tests, the ordering network and the stack work are paid once per packet; the slab and sphere tests once per ray (all camera
+// rays share the origin, so a ray costs 14 registers). Measured on C3 / C4 (frame time, A/B in one run, frames bit-identical): RPL 1 22.40 ms,
+// 2 21.81 (80 registers), 4 21.65 / 197.8 (101 registers), 8 22.72 / 206.3 (162 registers: too few warps left).
+#ifndef B2R_PACKET_RPL
+#define B2R_PACKET_RPL 4
+#endif
+template <bool COUNT, int RPL = 1>
 __global__ void __launch_bounds__(kTravBlock) k_intersect_packet(const Params p, const uint32_t bounce) {
 	// The camera rays are GENERATED here (Renderer.hpp:97-127: hash_2d -> PCG -> Camera::generate_ray, in registers) and their path
 	// records and zeroed radiance entries written behind the walk (plain coalesced stores that nobody waits for) for k_shade to read:
@@ -639,22 +646,28 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_packet(const Params p,
 	uint2* stack = s_pstack[threadIdx.x >> 5];
 	uint32_t c_sphere = 0, c_box = 0;
 	uint32_t next = 0, end = 0;
+	constexpr uint32_t kClaim = 128u * RPL;  // four packets per claim
 	for (;;) {
-		if (next >= end) {  // four packets per claim
+		if (next >= end) {
 			uint32_t b = 0;
-			if (lane_id() == 0) b = atomicAdd(p.cnt.work_a + bounce, 128u);
+			if (lane_id() == 0) b = atomicAdd(p.cnt.work_a + bounce, kClaim);
 			b = __shfl_sync(0xffffffffu, b, 0);
 			if (b >= n_in) break;
-			next = b; end = min(b + 128u, n_in);
+			next = b; end = min(b + kClaim, n_in);
 		}
-		const uint32_t idx = next + lane_id(); next += 32u;
-		const uint32_t sl = div_by(idx, p.frame.npix, p.frame.npix_magic);
-		const PathState s0 = primary_path(p.frame, p.batch->cam, p.batch->acc[sl], sl, idx - sl * p.frame.npix);
-		store_path(p.q, 0, idx, s0); rad_zero(p.rad, p.frame.npix, s0.pid);
-		const float ox = s0.ox, oy = s0.oy, oz = s0.oz, dx = s0.dx, dy = s0.dy, dz = s0.dz;
-		const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
-		const float nx = -(ox * ix), ny = -(oy * iy), nz = -(oz * iz), ax = fabsf(ix), ay = fabsf(iy), az = fabsf(iz);
-		float best = FLT_MAX; int32_t prim = -1;
+		const uint32_t idx0 = next + lane_id(); next += 32u * RPL;
+		float ox = 0, oy = 0, oz = 0, dx[RPL], dy[RPL], dz[RPL], ix[RPL], iy[RPL], iz[RPL], nx[RPL], ny[RPL], nz[RPL], ax[RPL], ay[RPL], az[RPL], best[RPL]; int32_t prim[RPL];
+#pragma unroll
+		for (int r = 0; r < RPL; r++) {
+			const uint32_t idx = idx0 + 32u * r;
+			const uint32_t sl = div_by(idx, p.frame.npix, p.frame.npix_magic);
+			const PathState s0 = primary_path(p.frame, p.batch->cam, p.batch->acc[sl], sl, idx - sl * p.frame.npix);
+			store_path(p.q, 0, idx, s0); rad_zero(p.rad, p.frame.npix, s0.pid);
+			ox = s0.ox; oy = s0.oy; oz = s0.oz; dx[r] = s0.dx; dy[r] = s0.dy; dz[r] = s0.dz;   // (all camera rays leave the same point)
+			ix[r] = 1.0f / dx[r]; iy[r] = 1.0f / dy[r]; iz[r] = 1.0f / dz[r];
+			nx[r] = -(ox * ix[r]); ny[r] = -(oy * iy[r]); nz[r] = -(oz * iz[r]); ax[r] = fabsf(ix[r]); ay[r] = fabsf(iy[r]); az[r] = fabsf(iz[r]);
+			best[r] = FLT_MAX; prim[r] = -1;
+		}
 		uint32_t node = 0u, sp = 0u;
 		for (;;) {
 			const float4* nd = wide4 + static_cast<size_t>(node) * 8u;
@@ -667,17 +680,26 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_packet(const Params p,
 				const float4 a = na[k], b = nb[k];
 				const int32_t l = __float_as_int(b.z);                          // warp-uniform
 				key[k] = 0xffffffffu; link[k] = static_cast<uint32_t>(l);
-				float tn; bool h; slab(a, b, ix, iy, iz, nx, ny, nz, ax, ay, az, best, &tn, &h);  // an empty slot's box (h = -1e30) is never hit
-				if (COUNT && l != kEmptyLink) c_box++;
-				if (__ballot_sync(0xffffffffu, h) == 0u) continue;
-				if (l < 0) {  // leaf slot: the lanes whose ray passes its box test the sphere
-					if (h) {
+				float tn[RPL]; bool h[RPL]; bool any = false; uint32_t tmin = 0xffffffffu;
+#pragma unroll
+				for (int r = 0; r < RPL; r++) {
+					slab(a, b, ix[r], iy[r], iz[r], nx[r], ny[r], nz[r], ax[r], ay[r], az[r], best[r], &tn[r], &h[r]);  // an empty slot's box (h = -1e30) is never hit
+					any = any || h[r]; tmin = min(tmin, h[r] ? __float_as_uint(tn[r]) : 0xffffffffu);
+				}
+				if (COUNT && l != kEmptyLink) c_box += RPL;
+				if (__ballot_sync(0xffffffffu, any) == 0u) continue;
+				if (l < 0) {  // leaf slot: the rays that pass its box test the sphere
+#pragma unroll
+					for (int r = 0; r < RPL; r++) if (h[r]) {
 						float d; if (COUNT) c_sphere++;
-						if (sphere_hit_closest(a.x, a.y, a.z, a.w, ox, oy, oz, dx, dy, dz, &d) && (d < best || (d == best && ~l < prim))) { best = d; prim = ~l; }
+						if (sphere_hit_closest(a.x, a.y, a.z, a.w, ox, oy, oz, dx[r], dy[r], dz[r], &d) && (d < best[r] || (d == best[r] && ~l < prim[r]))) { best[r] = d; prim[r] = ~l; }
 					}
-				} else key[k] = __reduce_min_sync(0xffffffffu, h ? __float_as_uint(tn) : 0xffffffffu);  // the packet's entry distance
+				} else key[k] = __reduce_min_sync(0xffffffffu, tmin);  // the packet's entry distance
 			}
-			const uint32_t far_best = __reduce_max_sync(0xffffffffu, __float_as_uint(best));  // a node is dead once it lies behind EVERY lane's hit
+			float fb = best[0];
+#pragma unroll
+			for (int r = 1; r < RPL; r++) fb = fmaxf(fb, best[r]);
+			const uint32_t far_best = __reduce_max_sync(0xffffffffu, __float_as_uint(fb));  // a node is dead once it lies behind EVERY ray's hit
 			B2R_CSWAP(key[0], link[0], key[1], link[1]); B2R_CSWAP(key[2], link[2], key[3], link[3]);
 			B2R_CSWAP(key[0], link[0], key[2], link[2]); B2R_CSWAP(key[1], link[1], key[3], link[3]);
 			B2R_CSWAP(key[1], link[1], key[2], link[2]);
@@ -693,7 +715,8 @@ __global__ void __launch_bounds__(kTravBlock) k_intersect_packet(const Params p,
 			}
 			if (!found) break;
 		}
-		p.q.H[idx] = make_float2(best, __int_as_float(prim));
+#pragma unroll
+		for (int r = 0; r < RPL; r++) p.q.H[idx0 + 32u * r] = make_float2(best[r], __int_as_float(prim[r]));
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) { p.cnt.paths[0] = n_in; atomicAdd(p.cnt.stats + ST_EXT, static_cast<unsigned long long>(n_in)); }
 	if (COUNT) { stat_add(p.cnt.stats, ST_SPHERE, c_sphere); stat_add(p.cnt.stats, ST_BOX, c_box); }
