@@ -20,21 +20,27 @@ int fail(int code, const std::string& what) { g_error = what; return code; }
 
 enum KernelKind { KK_GENERATE = 0, KK_BRUTE, KK_CLOSEST, KK_SHADE, KK_SHADOW, KK_ACCUMULATE, KK_RESOLVE, KK_COUNT };
 
+constexpr uint32_t kMaxLanes = 4;
 struct BatchArgs {
 	uint32_t n; uint32_t acc[kMaxSlots]; unsigned long long fold = ~0ull; CameraParams cam;
-	uint32_t n_a = 0, off_b = 0;  // twin lanes (run_batch): slots [0, n_a) are lane A's samples, slots [off_b, n) lane B's, the slots between hold nothing
-	uint32_t slot_of(uint32_t i) const { return n_a == 0u || i < n_a ? i : off_b + (i - n_a); }  // slot of the i-th sample of the batch
-};
-// dst[0] describes the whole batch (k_accumulate), dst[1] / dst[2] the two lanes' halves (slot numbers local to the lane)
-__global__ void k_set_batch(BatchDev* dst, const BatchArgs a) {
-	if (threadIdx.x == 0) {
-		dst[0].n_slots = a.n; dst[0].fold = a.fold; dst[0].cam = a.cam;
-		dst[1].n_slots = a.n_a; dst[1].fold = 0ull; dst[1].cam = a.cam;
-		dst[2].n_slots = a.n_a ? a.n - a.off_b : 0u; dst[2].fold = 0ull; dst[2].cam = a.cam;
+	// lanes (run_batch): lane j holds n_lane[j] consecutive samples of the batch in slots [j * lane_slots, j * lane_slots + n_lane[j]); the slots
+	// between the lanes hold nothing. lanes == 0: one lane, slots 0..n-1.
+	uint32_t lanes = 0, lane_slots = 0, n_lane[kMaxLanes] = {0, 0, 0, 0};
+	uint32_t slot_of(uint32_t i) const {  // slot of the i-th sample of the batch
+		if (lanes == 0u) return i;
+		uint32_t j = 0; while (j + 1u < lanes && i >= n_lane[j]) { i -= n_lane[j]; j++; }
+		return j * lane_slots + i;
 	}
+};
+// dst[0] describes the whole batch (k_accumulate), dst[1 + j] lane j's part of it (slot numbers local to the lane)
+__global__ void k_set_batch(BatchDev* dst, const BatchArgs a) {
+	if (threadIdx.x == 0) { dst[0].n_slots = a.n; dst[0].fold = a.fold; dst[0].cam = a.cam; }
 	if (threadIdx.x < a.n) dst[0].acc[threadIdx.x] = a.acc[threadIdx.x];
-	if (threadIdx.x < a.n_a) dst[1].acc[threadIdx.x] = a.acc[threadIdx.x];
-	if (a.n_a && a.off_b + threadIdx.x < a.n) dst[2].acc[threadIdx.x] = a.acc[a.off_b + threadIdx.x];
+	for (uint32_t j = 0; j < kMaxLanes; j++) {
+		const uint32_t nj = j < a.lanes ? a.n_lane[j] : 0u;
+		if (threadIdx.x == 0) { dst[1 + j].n_slots = nj; dst[1 + j].fold = 0ull; dst[1 + j].cam = a.cam; }
+		if (threadIdx.x < nj) dst[1 + j].acc[threadIdx.x] = a.acc[j * a.lane_slots + threadIdx.x];
+	}
 }
 
 template <typename T> int dev_alloc(T** p, size_t count) {
@@ -100,10 +106,11 @@ struct b2r_ctx {
 	cudaGraphExec_t graph_exec = nullptr; bool graph_valid = false;
 	// twin lanes: a batch of two or more samples is traced as two independent half batches on two streams (own queues, counters and batch
 	// descriptors) inside one graph, so that the drained end of every launch of one half is filled by the other half's kernels
-	cudaGraphExec_t twin_exec = nullptr; bool twin_valid = false, twin_enabled = true;
-	cudaStream_t lane_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+	cudaGraphExec_t lane_exec[kMaxLanes + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr}; bool lane_valid[kMaxLanes + 1] = {false, false, false, false, false};  // index = lanes (2, 4)
+	uint32_t lanes_max = 2;
+	cudaStream_t lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
 	float lane_grid_frac = 1.0f;
-	uint64_t graph_launches = 0, twin_launches = 0;  // kernels one replay of each graph launches (counted while capturing)
+	uint64_t graph_launches = 0, lane_launches[kMaxLanes + 1] = {0, 0, 0, 0, 0};  // kernels one replay of each graph launches (counted while capturing)
 	uint64_t launches = 0;
 	// profiling (B2R_FLAG_NO_GRAPH): events around every launch
 	struct Timed { int kind; cudaEvent_t a, b; };
@@ -128,10 +135,10 @@ void drop_speculation(b2r_ctx* c) { c->spec_count = 0; c->spec_used = 0; c->spec
 
 void drop_graph(b2r_ctx* c) {
 	drop_speculation(c);  // everything that invalidates the captured graph (camera, scene pointers, flags, frame size) invalidates them too
-	if (c->graph_exec || c->twin_exec) { if (c->stream) cudaStreamSynchronize(c->stream); }  // (a launch of it may still be running)
+	if (c->stream) cudaStreamSynchronize(c->stream);  // (a launch of a graph may still be running)
 	if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
-	if (c->twin_exec) { cudaGraphExecDestroy(c->twin_exec); c->twin_exec = nullptr; }
-	c->graph_valid = false; c->twin_valid = false;
+	for (uint32_t l = 0; l <= kMaxLanes; l++) { if (c->lane_exec[l]) { cudaGraphExecDestroy(c->lane_exec[l]); c->lane_exec[l] = nullptr; } c->lane_valid[l] = false; }
+	c->graph_valid = false;
 }
 
 int alloc_frame(b2r_ctx* c) {
@@ -156,10 +163,10 @@ int alloc_frame(b2r_ctx* c) {
 	if ((rc = dev_alloc(&c->d_acc, static_cast<size_t>(K) * 3 * npix))) return rc;
 	if ((rc = dev_alloc(&c->d_fb, static_cast<size_t>(npix)))) return rc;
 	c->counts_bytes = (static_cast<size_t>(mb) + 1) * 4 * sizeof(uint32_t);
-	if ((rc = dev_alloc(&c->d_counts, (static_cast<size_t>(mb) + 1) * 4 * 2))) return rc;  // second block: lane B of a twin batch
-	CU(cudaMemset(c->d_counts, 0, 2 * c->counts_bytes));
+	if ((rc = dev_alloc(&c->d_counts, (static_cast<size_t>(mb) + 1) * 4 * kMaxLanes))) return rc;  // one block per lane
+	CU(cudaMemset(c->d_counts, 0, kMaxLanes * c->counts_bytes));
 	if (!c->d_stats) { if ((rc = dev_alloc(&c->d_stats, static_cast<size_t>(ST_COUNT)))) return rc; CU(cudaMemset(c->d_stats, 0, ST_COUNT * sizeof(unsigned long long))); }
-	if (!c->d_batch) { if ((rc = dev_alloc(&c->d_batch, static_cast<size_t>(3)))) return rc; }  // whole batch, lane A, lane B
+	if (!c->d_batch) { if ((rc = dev_alloc(&c->d_batch, static_cast<size_t>(1 + kMaxLanes)))) return rc; }  // whole batch + one per lane
 	if (c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) {
 		for (int s = 0; s < 2; s++) { if ((rc = dev_alloc(&c->d_ex_slot[s], cap))) return rc; if ((rc = dev_alloc(&c->d_ex_act[s], cap / 256))) return rc; }
 		if ((rc = dev_alloc(&c->d_ex_key, cap))) return rc;
@@ -209,7 +216,8 @@ int compute_grids(b2r_ctx* c) {
 	if ((rc = occ(reinterpret_cast<const void*>(&k_brute_finish<false, true>), kBruteBlock, &c->grid_brute_finish_ggx))) return rc;
 	if ((rc = occ(reinterpret_cast<const void*>(&k_shade<false, true>), kBruteBlock, &c->grid_shade_ggx))) return rc;
 	c->packet_primary = std::getenv("B2R_NO_PACKET") == nullptr;  // A/B switch for measurements: per-lane walks for the camera rays too
-	c->twin_enabled = std::getenv("B2R_NO_TWIN") == nullptr;      // A/B switch for measurements: every batch as one lane
+	c->lanes_max = std::getenv("B2R_NO_TWIN") ? 1u : 2u;          // A/B switches for measurements: every batch as one lane / B2R_LANES = 1, 2 or 4
+	if (const char* e = std::getenv("B2R_LANES")) { const int v = std::atoi(e); if (v == 1 || v == 2 || v == 4) c->lanes_max = static_cast<uint32_t>(v); }
 	if (const char* e = std::getenv("B2R_LANE_GRID")) { c->lane_grid_frac = static_cast<float>(std::atof(e)); if (!(c->lane_grid_frac > 0.0f && c->lane_grid_frac <= 1.0f)) c->lane_grid_frac = 1.0f; }
 	c->grid_stream = c->sm_count * 8;
 	return B2R_OK;
@@ -289,13 +297,14 @@ int enqueue_rounds(b2r_ctx* c, const Params& p_in, cudaStream_t st, bool profile
 	return B2R_OK;
 }
 
-// Lane `which` (0 = A, 1 = B) of a twin batch: its own part of every queue array (A the first ceil(slots/2) samples' worth, B the rest),
-// its own counter block and batch descriptor, and its own part of RAD — lane B's local slot s is slot ceil(slots/2) + s of the whole
-// batch, which is how k_accumulate (whole-batch descriptor) finds it.
-Params lane_params(const b2r_ctx* c, int which) {
+// Lane `which` of a batch traced as `lanes` lanes: its own part of every queue array (lane_slots = ceil(slots / lanes) samples' worth, the last
+// lane what is left), its own counter block and batch descriptor, and its own part of RAD — lane j's local slot s is slot j * lane_slots + s
+// of the whole batch, which is how k_accumulate (whole-batch descriptor) finds it.
+uint32_t lane_slots_of(const b2r_ctx* c, uint32_t lanes) { return (c->slots + lanes - 1u) / lanes; }
+Params lane_params(const b2r_ctx* c, uint32_t which, uint32_t lanes) {
 	Params p = c->params;
-	const size_t npix = p.frame.npix, cap_a = static_cast<size_t>((c->slots + 1u) / 2u) * npix, cap_b = static_cast<size_t>(c->slots / 2u) * npix;
-	const size_t off = which ? cap_a : 0, cap = which ? cap_b : cap_a;
+	const uint32_t ls = lane_slots_of(c, lanes), first = which * ls, mine = first >= c->slots ? 0u : (c->slots - first < ls ? c->slots - first : ls);
+	const size_t npix = p.frame.npix, off = static_cast<size_t>(first) * npix, cap = static_cast<size_t>(mine) * npix;
 	for (int s = 0; s < 2; s++) { p.q.A[s] += off; p.q.B[s] += off; p.q.T[s] += 3 * off; }
 	p.q.H += off; p.q.SA += off; p.q.SB += off; p.q.SL += 3 * off; p.q.SS += off; p.q.cap = static_cast<uint32_t>(cap);
 	const uint32_t block = (c->cfg.max_bounces + 1u) * 4u;
@@ -306,51 +315,59 @@ Params lane_params(const b2r_ctx* c, int which) {
 }
 
 // Enqueue one wavefront batch (everything after k_set_batch): counters reset, max_bounces rounds, fold into buckets.
-int enqueue_batch(b2r_ctx* c, bool profile, bool twin) {
+int enqueue_batch(b2r_ctx* c, bool profile, uint32_t lanes) {
 	cudaStream_t st = c->stream;
-	CU(cudaMemsetAsync(c->d_counts, 0, 2 * c->counts_bytes, st));
+	CU(cudaMemsetAsync(c->d_counts, 0, kMaxLanes * c->counts_bytes, st));
 	int rc;
-	if (!twin) { if ((rc = enqueue_rounds(c, c->params, st, profile))) return rc; }
+	if (lanes <= 1u) { if ((rc = enqueue_rounds(c, c->params, st, profile))) return rc; }
 	else {
-		// fork: lane B's rounds on the second stream, lane A's on the main one; join before the fold (which adds in sample order over both)
-		CU(cudaEventRecord(c->ev_fork, st)); CU(cudaStreamWaitEvent(c->lane_stream, c->ev_fork, 0));
-		if ((rc = enqueue_rounds(c, lane_params(c, 0), st, false, c->lane_grid_frac))) return rc;
-		if ((rc = enqueue_rounds(c, lane_params(c, 1), c->lane_stream, false, c->lane_grid_frac))) return rc;
-		CU(cudaEventRecord(c->ev_join, c->lane_stream)); CU(cudaStreamWaitEvent(st, c->ev_join, 0));
+		// fork: lane 0's rounds on the main stream, the others' on their own; join before the fold (which adds in sample order over all lanes)
+		CU(cudaEventRecord(c->ev_fork, st));
+		for (uint32_t j = 1; j < lanes; j++) CU(cudaStreamWaitEvent(c->lane_stream[j], c->ev_fork, 0));
+		for (uint32_t j = 0; j < lanes; j++) if ((rc = enqueue_rounds(c, lane_params(c, j, lanes), j ? c->lane_stream[j] : st, false, c->lane_grid_frac))) return rc;
+		for (uint32_t j = 1; j < lanes; j++) { CU(cudaEventRecord(c->ev_join[j], c->lane_stream[j])); CU(cudaStreamWaitEvent(st, c->ev_join[j], 0)); }
 	}
 	return launch(c, KK_ACCUMULATE, profile, [&] { k_accumulate<<<c->grid_stream, kBlock, 0, st>>>(c->params); });
 }
 
-// One wavefront batch of args.n samples (args.acc[0..n) in sample order). Two or more samples are traced as twin lanes: run_batch moves
-// the second half of the samples to the slots lane B owns and leaves args in that layout (the caller may keep it: samples traced ahead).
+// One wavefront batch of args.n samples (args.acc[0..n) in sample order). Two or more samples are traced as lanes: run_batch moves every
+// lane's samples to the slots that lane owns and leaves args in that layout (the caller may keep it: samples traced ahead).
 int run_batch(b2r_ctx* c, BatchArgs& args) {
 	const bool no_graph = (c->cfg.flags & B2R_FLAG_NO_GRAPH) != 0;
-	const bool twin = c->twin_enabled && !no_graph && args.n >= 2u && c->slots >= 2u && !(c->cfg.flags & B2R_FLAG_REFERENCE_EXACT);
-	if (twin) {
-		const uint32_t n = args.n, n_a = (n + 1u) / 2u, off_b = (c->slots + 1u) / 2u;
-		unsigned long long fold = 0ull;
-		for (uint32_t i = n; i-- > n_a;) { args.acc[off_b + (i - n_a)] = args.acc[i]; }   // (highest first: the ranges may overlap)
-		for (uint32_t i = 0; i < n; i++) if ((args.fold >> i) & 1ull) fold |= 1ull << (i < n_a ? i : off_b + (i - n_a));
-		for (uint32_t s = n_a; s < off_b; s++) args.acc[s] = 0u;
-		args.n_a = n_a; args.off_b = off_b; args.n = off_b + (n - n_a); args.fold = fold;
-	} else { args.n_a = 0; args.off_b = 0; if (args.n < 64u) args.fold &= (1ull << args.n) - 1ull; }
+	uint32_t lanes = 1;
+	if (!no_graph && !(c->cfg.flags & B2R_FLAG_REFERENCE_EXACT)) {
+		if (c->lanes_max >= 4u && args.n >= 4u && c->slots % 4u == 0u) lanes = 4;
+		else if (c->lanes_max >= 2u && args.n >= 2u && c->slots >= 2u) lanes = 2;
+	}
+	if (lanes > 1u) {
+		const uint32_t n = args.n, ls = lane_slots_of(c, lanes);
+		uint32_t acc[kMaxSlots]; for (uint32_t i = 0; i < n; i++) acc[i] = args.acc[i];
+		unsigned long long fold = 0ull; uint32_t i = 0, span = 0;
+		for (uint32_t s = 0; s < static_cast<uint32_t>(kMaxSlots); s++) args.acc[s] = 0u;
+		for (uint32_t j = 0; j < lanes; j++) {
+			const uint32_t nj = n / lanes + (j < n % lanes ? 1u : 0u);   // the first lanes take the remainder: never more than ceil(n / lanes) <= lane_slots
+			args.n_lane[j] = nj;
+			for (uint32_t k = 0; k < nj; k++, i++) { const uint32_t slot = j * ls + k; args.acc[slot] = acc[i]; if ((args.fold >> i) & 1ull) fold |= 1ull << slot; if (slot + 1u > span) span = slot + 1u; }
+		}
+		args.lanes = lanes; args.lane_slots = ls; args.n = span; args.fold = fold;
+	} else { args.lanes = 0; args.lane_slots = 0; if (args.n < 64u) args.fold &= (1ull << args.n) - 1ull; }
 	args.cam = c->params.frame.cam;  // the camera travels with the batch descriptor: a camera move leaves the captured graph alone
 	k_set_batch<<<1, kMaxSlots, 0, c->stream>>>(c->d_batch, args);
 	CU(cudaGetLastError());
-	if (no_graph) return enqueue_batch(c, true, false);
-	cudaGraphExec_t& exec = twin ? c->twin_exec : c->graph_exec;
-	bool& valid = twin ? c->twin_valid : c->graph_valid;
-	uint64_t& per_replay = twin ? c->twin_launches : c->graph_launches;
+	if (no_graph) return enqueue_batch(c, true, 1);
+	cudaGraphExec_t& exec = lanes > 1u ? c->lane_exec[lanes] : c->graph_exec;
+	bool& valid = lanes > 1u ? c->lane_valid[lanes] : c->graph_valid;
+	uint64_t& per_replay = lanes > 1u ? c->lane_launches[lanes] : c->graph_launches;
 	if (!valid) {
 		if (exec) { CU(cudaStreamSynchronize(c->stream)); cudaGraphExecDestroy(exec); exec = nullptr; }
-		if (twin && !c->lane_stream) {
-			CU(cudaStreamCreateWithFlags(&c->lane_stream, cudaStreamNonBlocking));
-			CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+		if (lanes > 1u && !c->ev_fork) CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+		for (uint32_t j = 1; j < lanes; j++) if (!c->lane_stream[j]) {
+			CU(cudaStreamCreateWithFlags(&c->lane_stream[j], cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&c->ev_join[j], cudaEventDisableTiming));
 		}
 		cudaGraph_t graph = nullptr;
 		const uint64_t before = c->launches;
 		CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-		int rc = enqueue_batch(c, false, twin);
+		int rc = enqueue_batch(c, false, lanes);
 		cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
 		per_replay = c->launches - before; c->launches = before;
 		if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -471,7 +488,8 @@ void b2r_destroy(b2r_ctx* c) {
 	if (c->h_stage) cudaFreeHost(c->h_stage);
 	if (c->ev_stage) cudaEventDestroy(c->ev_stage);
 	if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); cudaEventDestroy(c->ev_resolved); cudaEventDestroy(c->ev_copied); }
-	if (c->lane_stream) { cudaStreamDestroy(c->lane_stream); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
+	for (uint32_t j = 1; j < kMaxLanes; j++) if (c->lane_stream[j]) { cudaStreamDestroy(c->lane_stream[j]); cudaEventDestroy(c->ev_join[j]); }
+	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
 	delete c;
 }
@@ -1112,10 +1130,13 @@ int b2r_read_bounce_counts(b2r_ctx* c, uint32_t* paths_out, uint32_t* shadow_out
 	int rc = ensure_device(c); if (rc) return rc;
 	const uint32_t mb = c->cfg.max_bounces;
 	const size_t block = (static_cast<size_t>(mb) + 1) * 4;
-	std::vector<uint32_t> h(block * 2);  // the last batch's counters: one block per lane (lane B's stays zero when the batch ran as one lane)
-	CU(cudaMemcpyAsync(h.data(), c->d_counts, 2 * c->counts_bytes, cudaMemcpyDeviceToHost, c->stream));
+	std::vector<uint32_t> h(block * kMaxLanes);  // the last batch's counters: one block per lane (unused lanes' blocks stay zero)
+	CU(cudaMemcpyAsync(h.data(), c->d_counts, kMaxLanes * c->counts_bytes, cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
-	for (uint32_t b = 0; b < n; b++) { paths_out[b] = b <= mb ? h[b] + h[block + b] : 0u; shadow_out[b] = b < mb ? h[mb + 1 + b] + h[block + mb + 1 + b] : 0u; }
+	for (uint32_t b = 0; b < n; b++) {
+		paths_out[b] = 0u; shadow_out[b] = 0u;
+		for (uint32_t j = 0; j < kMaxLanes; j++) { if (b <= mb) paths_out[b] += h[j * block + b]; if (b < mb) shadow_out[b] += h[j * block + mb + 1 + b]; }
+	}
 	return collect_timings(c);
 }
 int b2r_reset_counters(b2r_ctx* c) {
