@@ -310,8 +310,12 @@ class Bench:
             # progressive rendering as a user would drive it: frame N is copied out on the library's second stream into one of two pinned
             # buffers while the samples of frame N+1 are traced (b2r_resolve_async); nothing is skipped, every frame lands on the host
             ok = r.RenderAsync(async_fbs[self.frame_no & 1]); self.frame_no += 1
+        elif to_host_fb is None:
+            # the device-timed pass: the frame is resolved into the device framebuffer and the next frame is enqueued behind it without a host
+            # wait (b2r_resolve_device) — frames are pipelined on the device exactly as the multi-GPU team path and the e2e path already are
+            ok = r.RenderDevice()
         else:
-            ok = r.Render(to_host=to_host_fb is not None, out=to_host_fb)
+            ok = r.Render(to_host=True, out=to_host_fb)
         assert ok
 
     def timed(self, n, **kw):
@@ -550,7 +554,7 @@ def run_workload(args, name, rank, world, local, stream, dev, secondary=False):
             if rank == 0:  # the same frame on ONE GPU, in the same run (the other ranks wait at the barrier)
                 one = b.renderer(sharded=False, flags=b.base_flags)
                 def f1():
-                    one.ResetAccumulator(); one.Accumulate(STRONG_SPP); assert one.Render(to_host=False)
+                    one.ResetAccumulator(); one.Accumulate(STRONG_SPP); assert one.RenderDevice()
                 f1(); torch.cuda.synchronize(dev)
                 a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(stream)
@@ -572,7 +576,7 @@ def run_workload(args, name, rank, world, local, stream, dev, secondary=False):
     if world == 1 and not b.base_flags and wl["scene"] == "default" and not args.no_profile_pass:
         rx = b.renderer(sharded=False, flags=b2r.FLAG_REFERENCE_EXACT)
         def step_x():
-            rx.ResetAccumulator(); rx.Accumulate(b.step_samples); assert rx.Render(to_host=False)
+            rx.ResetAccumulator(); rx.Accumulate(b.step_samples); assert rx.RenderDevice()
         for _ in range(warm):
             step_x()
         torch.cuda.synchronize(dev); rx.reset_counters()
@@ -660,7 +664,8 @@ def run_workload(args, name, rank, world, local, stream, dev, secondary=False):
             "higher_is_better": True, "scaling": "strong" if b.strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"] + (" [B2R_FLAG_REFERENCE_EXACT: reference's stream order and scalar-tail formula]" if b.base_flags else ""), "samples_per_step_per_gpu": b.step_samples // world, "samples_in_flight": args.samples_in_flight,
                        "partition": part,
-                       "l2": "no flush needed: each step streams >1 GB of path-queue records (>> 126 MB L2); RNG-unique samples every step"},
+                       "l2": "no flush needed: each step streams >1 GB of path-queue records (>> 126 MB L2); RNG-unique samples every step",
+                       "frames": "enqueued back to back: every step resets, traces, folds and resolves its frame into the device framebuffer; no host wait inside the timed region, so the device pipelines consecutive frames (the e2e figure copies every frame to the host)"},
             "paths_per_s": paths_total / secs, "rays_per_step": rays_total / steps,
             "parity_checked": bool(par and par["identical"]), "parity": par,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / steps,

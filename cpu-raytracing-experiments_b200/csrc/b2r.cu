@@ -107,10 +107,23 @@ struct b2r_ctx {
 	// twin lanes: a batch of two or more samples is traced as two independent half batches on two streams (own queues, counters and batch
 	// descriptors) inside one graph, so that the drained end of every launch of one half is filled by the other half's kernels
 	cudaGraphExec_t lane_exec[kMaxLanes + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr}; bool lane_valid[kMaxLanes + 1] = {false, false, false, false, false};  // index = lanes (2, 4)
-	uint32_t lanes_max = 2;
+	bool idle = true;  // nothing of this context is running on the device (set by sync_main, cleared by run_batch)
+	uint32_t lanes_max = 2; bool lanes_forced = false;  // B2R_LANES given: no per-batch choice
 	cudaStream_t lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
 	float lane_grid_frac = 1.0f;
 	uint64_t graph_launches = 0, lane_launches[kMaxLanes + 1] = {0, 0, 0, 0, 0};  // kernels one replay of each graph launches (counted while capturing)
+	// sides: consecutive batches alternate between two halves of the queue memory and are TRACED on two library-owned streams, so that the thin
+	// late bounces of one batch (and its fold and the frame's resolve) run under the first, fat bounces of the next; only k_accumulate stays on
+	// the caller's stream, behind an event, so buckets are still folded in sample order and everything the caller enqueues later (reset,
+	// resolve, a scene upload) is ordered behind all tracing enqueued so far
+	struct Side {
+		cudaStream_t stream = nullptr, lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+		cudaEvent_t ev_traced = nullptr, ev_folded = nullptr, ev_sync = nullptr, ev_fork = nullptr, ev_join[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+		bool folded_valid = false; uint64_t epoch = ~0ull;
+		cudaGraphExec_t exec[kMaxLanes + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr}; bool valid[kMaxLanes + 1] = {false, false, false, false, false}; uint64_t launches[kMaxLanes + 1] = {0, 0, 0, 0, 0};
+	} side[2];
+	uint32_t sides = 2, next_side = 0, last_side = 0, spec_side = 0, counts_first = 0;  // counts_first: first counter block of the last batch
+	uint64_t scene_epoch = 0;  // bumped by everything the side streams must not run ahead of (scene copies, refits, counter resets)
 	uint64_t launches = 0;
 	// profiling (B2R_FLAG_NO_GRAPH): events around every launch
 	struct Timed { int kind; cudaEvent_t a, b; };
@@ -128,6 +141,9 @@ struct b2r_ctx {
 namespace {
 
 int ensure_device(b2r_ctx* c) { CU(cudaSetDevice(c->cfg.device)); return B2R_OK; }
+// every wait for the caller's stream goes through here: afterwards the device is idle (all tracing enqueued so far precedes that stream's
+// position), which run_batch takes into account when it shapes the next batch
+cudaError_t sync_main(b2r_ctx* c) { c->idle = true; return cudaStreamSynchronize(c->stream); }
 constexpr uint32_t kSpecMax = 16;
 constexpr uint32_t kFinishBelow = 12000000u;  // paths entering a bounce below which k_brute_finish takes the rest of a brute-force batch. Measured on C2 (134 M paths
                                               // per batch): 13.72 ms per frame without it, 13.41 at 8 M, 13.34 at 12-16 M, 13.48 at 25 M; B2R_FINISH_BELOW overrides (0 = off)
@@ -135,9 +151,13 @@ void drop_speculation(b2r_ctx* c) { c->spec_count = 0; c->spec_used = 0; c->spec
 
 void drop_graph(b2r_ctx* c) {
 	drop_speculation(c);  // everything that invalidates the captured graph (camera, scene pointers, flags, frame size) invalidates them too
-	if (c->stream) cudaStreamSynchronize(c->stream);  // (a launch of a graph may still be running)
+	if (c->stream) sync_main(c);  // (a launch of a graph may still be running)
 	if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
 	for (uint32_t l = 0; l <= kMaxLanes; l++) { if (c->lane_exec[l]) { cudaGraphExecDestroy(c->lane_exec[l]); c->lane_exec[l] = nullptr; } c->lane_valid[l] = false; }
+	for (auto& S : c->side) {
+		if (S.stream) cudaStreamSynchronize(S.stream);
+		for (uint32_t l = 0; l <= kMaxLanes; l++) { if (S.exec[l]) { cudaGraphExecDestroy(S.exec[l]); S.exec[l] = nullptr; } S.valid[l] = false; }
+	}
 	c->graph_valid = false;
 }
 
@@ -163,10 +183,10 @@ int alloc_frame(b2r_ctx* c) {
 	if ((rc = dev_alloc(&c->d_acc, static_cast<size_t>(K) * 3 * npix))) return rc;
 	if ((rc = dev_alloc(&c->d_fb, static_cast<size_t>(npix)))) return rc;
 	c->counts_bytes = (static_cast<size_t>(mb) + 1) * 4 * sizeof(uint32_t);
-	if ((rc = dev_alloc(&c->d_counts, (static_cast<size_t>(mb) + 1) * 4 * kMaxLanes))) return rc;  // one block per lane
-	CU(cudaMemset(c->d_counts, 0, kMaxLanes * c->counts_bytes));
+	if ((rc = dev_alloc(&c->d_counts, (static_cast<size_t>(mb) + 1) * 4 * kMaxLanes * 2))) return rc;  // one block per lane and side
+	CU(cudaMemset(c->d_counts, 0, 2 * kMaxLanes * c->counts_bytes));
 	if (!c->d_stats) { if ((rc = dev_alloc(&c->d_stats, static_cast<size_t>(ST_COUNT)))) return rc; CU(cudaMemset(c->d_stats, 0, ST_COUNT * sizeof(unsigned long long))); }
-	if (!c->d_batch) { if ((rc = dev_alloc(&c->d_batch, static_cast<size_t>(1 + kMaxLanes)))) return rc; }  // whole batch + one per lane
+	if (!c->d_batch) { if ((rc = dev_alloc(&c->d_batch, static_cast<size_t>(2 * (1 + kMaxLanes))))) return rc; }  // per side: whole batch + one per lane
 	if (c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) {
 		for (int s = 0; s < 2; s++) { if ((rc = dev_alloc(&c->d_ex_slot[s], cap))) return rc; if ((rc = dev_alloc(&c->d_ex_act[s], cap / 256))) return rc; }
 		if ((rc = dev_alloc(&c->d_ex_key, cap))) return rc;
@@ -217,7 +237,8 @@ int compute_grids(b2r_ctx* c) {
 	if ((rc = occ(reinterpret_cast<const void*>(&k_shade<false, true>), kBruteBlock, &c->grid_shade_ggx))) return rc;
 	c->packet_primary = std::getenv("B2R_NO_PACKET") == nullptr;  // A/B switch for measurements: per-lane walks for the camera rays too
 	c->lanes_max = std::getenv("B2R_NO_TWIN") ? 1u : 2u;          // A/B switches for measurements: every batch as one lane / B2R_LANES = 1, 2 or 4
-	if (const char* e = std::getenv("B2R_LANES")) { const int v = std::atoi(e); if (v == 1 || v == 2 || v == 4) c->lanes_max = static_cast<uint32_t>(v); }
+	if (const char* e = std::getenv("B2R_SIDES")) { c->sides = std::atoi(e) == 1 ? 1u : 2u; }   // A/B switch: 1 = every batch on the caller's stream, one after the other
+	if (const char* e = std::getenv("B2R_LANES")) { const int v = std::atoi(e); if (v == 1 || v == 2 || v == 4) { c->lanes_max = static_cast<uint32_t>(v); c->lanes_forced = true; } }
 	if (const char* e = std::getenv("B2R_LANE_GRID")) { c->lane_grid_frac = static_cast<float>(std::atof(e)); if (!(c->lane_grid_frac > 0.0f && c->lane_grid_frac <= 1.0f)) c->lane_grid_frac = 1.0f; }
 	c->grid_stream = c->sm_count * 8;
 	return B2R_OK;
@@ -300,18 +321,43 @@ int enqueue_rounds(b2r_ctx* c, const Params& p_in, cudaStream_t st, bool profile
 // Lane `which` of a batch traced as `lanes` lanes: its own part of every queue array (lane_slots = ceil(slots / lanes) samples' worth, the last
 // lane what is left), its own counter block and batch descriptor, and its own part of RAD — lane j's local slot s is slot j * lane_slots + s
 // of the whole batch, which is how k_accumulate (whole-batch descriptor) finds it.
-uint32_t lane_slots_of(const b2r_ctx* c, uint32_t lanes) { return (c->slots + lanes - 1u) / lanes; }
-Params lane_params(const b2r_ctx* c, uint32_t which, uint32_t lanes) {
+// (BVH pipeline only: a side holds half of the samples in flight, and the brute-force pipeline — C2: one 64-sample batch per frame — loses more to
+// the smaller batches than the overlap gives back: 13.16 -> 13.09 ms per frame device-resident, but e2e 29.0 -> 28.1 Grays/s)
+bool use_sides(const b2r_ctx* c) { return c->sides == 2u && c->use_bvh && !(c->cfg.flags & (B2R_FLAG_NO_GRAPH | B2R_FLAG_REFERENCE_EXACT)) && c->slots >= 2u && c->slots % 2u == 0u; }
+uint32_t batch_cap(const b2r_ctx* c) { return use_sides(c) ? c->slots / 2u : c->slots; }   // samples one batch can hold
+uint32_t lane_slots_of(const b2r_ctx* c, uint32_t lanes) { return (batch_cap(c) + lanes - 1u) / lanes; }
+// (side = 0 with sides off: the batch owns all the queue memory)
+Params lane_params(const b2r_ctx* c, uint32_t which, uint32_t lanes, uint32_t side = 0) {
 	Params p = c->params;
-	const uint32_t ls = lane_slots_of(c, lanes), first = which * ls, mine = first >= c->slots ? 0u : (c->slots - first < ls ? c->slots - first : ls);
-	const size_t npix = p.frame.npix, off = static_cast<size_t>(first) * npix, cap = static_cast<size_t>(mine) * npix;
+	const uint32_t cap_slots = batch_cap(c), ls = lane_slots_of(c, lanes), rel = which * ls, mine = rel >= cap_slots ? 0u : (cap_slots - rel < ls ? cap_slots - rel : ls);
+	const size_t npix = p.frame.npix, off = static_cast<size_t>(side * cap_slots + rel) * npix, cap = static_cast<size_t>(mine) * npix;
 	for (int s = 0; s < 2; s++) { p.q.A[s] += off; p.q.B[s] += off; p.q.T[s] += 3 * off; }
 	p.q.H += off; p.q.SA += off; p.q.SB += off; p.q.SL += 3 * off; p.q.SS += off; p.q.cap = static_cast<uint32_t>(cap);
-	const uint32_t block = (c->cfg.max_bounces + 1u) * 4u;
-	p.cnt.paths += which * block; p.cnt.shadow += which * block; p.cnt.work_a += which * block; p.cnt.work_b += which * block;
-	p.batch = c->d_batch + 1 + which;
+	const uint32_t block = (c->cfg.max_bounces + 1u) * 4u, blk = side * kMaxLanes + which;
+	p.cnt.paths += blk * block; p.cnt.shadow += blk * block; p.cnt.work_a += blk * block; p.cnt.work_b += blk * block;
+	p.batch = c->d_batch + side * (1u + kMaxLanes) + 1u + which;
 	p.rad += 3 * off;
 	return p;
+}
+// what k_accumulate sees of a side: that side's whole-batch descriptor and its part of RAD
+Params side_params(const b2r_ctx* c, uint32_t side) {
+	Params p = c->params;
+	p.batch = c->d_batch + side * (1u + kMaxLanes);
+	p.rad += 3 * static_cast<size_t>(side * batch_cap(c)) * p.frame.npix;
+	return p;
+}
+// The tracing of one batch on a side's streams: counters reset, max_bounces rounds per lane (fork / join), no fold.
+int enqueue_trace(b2r_ctx* c, uint32_t sidx, uint32_t lanes) {
+	b2r_ctx::Side& S = c->side[sidx];
+	cudaStream_t st = S.stream;
+	CU(cudaMemsetAsync(c->d_counts + static_cast<size_t>(sidx) * kMaxLanes * (c->counts_bytes / sizeof(uint32_t)), 0, kMaxLanes * c->counts_bytes, st));
+	int rc;
+	if (lanes <= 1u) { Params p = lane_params(c, 0, 1, sidx); p.batch = c->d_batch + sidx * (1u + kMaxLanes); return enqueue_rounds(c, p, st, false); }  // one lane: the whole-batch descriptor is the lane's
+	CU(cudaEventRecord(S.ev_fork, st));
+	for (uint32_t j = 1; j < lanes; j++) CU(cudaStreamWaitEvent(S.lane_stream[j], S.ev_fork, 0));
+	for (uint32_t j = 0; j < lanes; j++) if ((rc = enqueue_rounds(c, lane_params(c, j, lanes, sidx), j ? S.lane_stream[j] : st, false, c->lane_grid_frac))) return rc;
+	for (uint32_t j = 1; j < lanes; j++) { CU(cudaEventRecord(S.ev_join[j], S.lane_stream[j])); CU(cudaStreamWaitEvent(st, S.ev_join[j], 0)); }
+	return B2R_OK;
 }
 
 // Enqueue one wavefront batch (everything after k_set_batch): counters reset, max_bounces rounds, fold into buckets.
@@ -336,9 +382,15 @@ int run_batch(b2r_ctx* c, BatchArgs& args) {
 	const bool no_graph = (c->cfg.flags & B2R_FLAG_NO_GRAPH) != 0;
 	uint32_t lanes = 1;
 	if (!no_graph && !(c->cfg.flags & B2R_FLAG_REFERENCE_EXACT)) {
-		if (c->lanes_max >= 4u && args.n >= 4u && c->slots % 4u == 0u) lanes = 4;
-		else if (c->lanes_max >= 2u && args.n >= 2u && c->slots >= 2u) lanes = 2;
+		if (c->lanes_max >= 4u && args.n >= 4u && batch_cap(c) % 4u == 0u) lanes = 4;
+		else if (c->lanes_max >= 2u && args.n >= 2u && batch_cap(c) >= 2u) lanes = 2;
+		// With sides a batch normally runs under the previous one (the other side's), and then ONE lane of full-size launches is the better
+		// shape (C3, frames enqueued back to back: 20.7 ms per frame against 21.4 with two lanes per side). A batch that has nothing to run
+		// under — the caller has waited for the device since the last batch, or this side must first wait for a scene upload or refit on the
+		// caller's stream — overlaps nothing but itself, and keeps its lanes.
+		if (use_sides(c) && !c->lanes_forced && !c->idle && c->side[c->next_side].epoch == c->scene_epoch) lanes = 1;
 	}
+	c->idle = false;
 	if (lanes > 1u) {
 		const uint32_t n = args.n, ls = lane_slots_of(c, lanes);
 		uint32_t acc[kMaxSlots]; for (uint32_t i = 0; i < n; i++) acc[i] = args.acc[i];
@@ -352,6 +404,47 @@ int run_batch(b2r_ctx* c, BatchArgs& args) {
 		args.lanes = lanes; args.lane_slots = ls; args.n = span; args.fold = fold;
 	} else { args.lanes = 0; args.lane_slots = 0; if (args.n < 64u) args.fold &= (1ull << args.n) - 1ull; }
 	args.cam = c->params.frame.cam;  // the camera travels with the batch descriptor: a camera move leaves the captured graph alone
+	if (use_sides(c)) {
+		const uint32_t sidx = c->next_side; c->next_side ^= 1u;
+		b2r_ctx::Side& S = c->side[sidx];
+		if (!S.stream) {
+			CU(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+			for (cudaEvent_t* e : {&S.ev_traced, &S.ev_folded, &S.ev_sync, &S.ev_fork}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+		}
+		for (uint32_t j = 1; j < lanes; j++) if (!S.lane_stream[j]) { CU(cudaStreamCreateWithFlags(&S.lane_stream[j], cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&S.ev_join[j], cudaEventDisableTiming)); }
+		// the side must not run ahead of scene copies / refits enqueued on the caller's stream since it last looked, nor overwrite its part of
+		// RAD before the previous batch it traced has been folded
+		if (S.epoch != c->scene_epoch) { CU(cudaEventRecord(S.ev_sync, c->stream)); CU(cudaStreamWaitEvent(S.stream, S.ev_sync, 0)); S.epoch = c->scene_epoch; }
+		if (S.folded_valid) CU(cudaStreamWaitEvent(S.stream, S.ev_folded, 0));
+		k_set_batch<<<1, kMaxSlots, 0, S.stream>>>(c->d_batch + sidx * (1u + kMaxLanes), args);
+		CU(cudaGetLastError());
+		if (!S.valid[lanes]) {
+			if (S.exec[lanes]) { CU(cudaStreamSynchronize(S.stream)); cudaGraphExecDestroy(S.exec[lanes]); S.exec[lanes] = nullptr; }
+			cudaGraph_t graph = nullptr;
+			const uint64_t before = c->launches;
+			CU(cudaStreamBeginCapture(S.stream, cudaStreamCaptureModeThreadLocal));
+			int rc = enqueue_trace(c, sidx, lanes);
+			cudaError_t e = cudaStreamEndCapture(S.stream, &graph);
+			S.launches[lanes] = c->launches - before; c->launches = before;
+			if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+			if (e != cudaSuccess) return fail(B2R_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+			e = cudaGraphInstantiate(&S.exec[lanes], graph, 0);
+			cudaGraphDestroy(graph);
+			if (e != cudaSuccess) return fail(B2R_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+			S.valid[lanes] = true;
+		}
+		CU(cudaGraphLaunch(S.exec[lanes], S.stream));
+		CU(cudaEventRecord(S.ev_traced, S.stream));
+		// the fold stays on the caller's stream: buckets are added to in sample order, behind whatever the caller enqueued before (reset)
+		CU(cudaStreamWaitEvent(c->stream, S.ev_traced, 0));
+		k_accumulate<<<c->grid_stream, kBlock, 0, c->stream>>>(side_params(c, sidx));
+		CU(cudaGetLastError());
+		CU(cudaEventRecord(S.ev_folded, c->stream)); S.folded_valid = true;
+		c->launches += S.launches[lanes] + 1u;
+		c->last_side = sidx; c->counts_first = sidx * kMaxLanes;
+		return B2R_OK;
+	}
+	c->counts_first = 0;
 	k_set_batch<<<1, kMaxSlots, 0, c->stream>>>(c->d_batch, args);
 	CU(cudaGetLastError());
 	if (no_graph) return enqueue_batch(c, true, 1);
@@ -359,7 +452,7 @@ int run_batch(b2r_ctx* c, BatchArgs& args) {
 	bool& valid = lanes > 1u ? c->lane_valid[lanes] : c->graph_valid;
 	uint64_t& per_replay = lanes > 1u ? c->lane_launches[lanes] : c->graph_launches;
 	if (!valid) {
-		if (exec) { CU(cudaStreamSynchronize(c->stream)); cudaGraphExecDestroy(exec); exec = nullptr; }
+		if (exec) { CU(sync_main(c)); cudaGraphExecDestroy(exec); exec = nullptr; }
 		if (lanes > 1u && !c->ev_fork) CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
 		for (uint32_t j = 1; j < lanes; j++) if (!c->lane_stream[j]) {
 			CU(cudaStreamCreateWithFlags(&c->lane_stream[j], cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&c->ev_join[j], cudaEventDisableTiming));
@@ -384,7 +477,7 @@ int run_batch(b2r_ctx* c, BatchArgs& args) {
 
 int collect_timings(b2r_ctx* c) {
 	if (c->timed.empty()) return B2R_OK;
-	CU(cudaStreamSynchronize(c->stream));
+	CU(sync_main(c));
 	for (auto& t : c->timed) {
 		float ms = 0.0f; CU(cudaEventElapsedTime(&ms, t.a, t.b));
 		c->kernel_ms[t.kind] += ms; c->kernel_launches[t.kind]++;
@@ -404,6 +497,7 @@ bool owns_sample(const b2r_ctx* c, uint32_t acc) {
 // Boxes of the device tree for the current origin box: one k_refit_level launch per BFS level, deepest first (stream order is the
 // dependency). remap (device, may be null) re-links leaves into a new BVH order.
 int launch_refit_levels(b2r_ctx* c, const uint32_t* d_remap) {
+	c->scene_epoch++;
 	const std::vector<uint32_t>& lf = c->wide_host.level_first;
 	for (size_t l = lf.size() - 1; l-- > 0;) {
 		const uint32_t first = lf[l], count = lf[l + 1] - lf[l];
@@ -415,6 +509,7 @@ int launch_refit_levels(b2r_ctx* c, const uint32_t* d_remap) {
 }
 // parent[] / leaf_node[] of the device tree (where k_intersect_shadow starts and how it climbs), read off the tree itself
 int launch_link_tables(b2r_ctx* c) {
+	c->scene_epoch++;
 	k_link_tables<<<(c->n_wide * 4u + kBlock - 1u) / kBlock, kBlock, 0, c->stream>>>(reinterpret_cast<const float4*>(c->d_wide), c->n_wide, c->d_parent, c->d_leaf_node);
 	CU(cudaGetLastError()); c->launches++;
 	return B2R_OK;
@@ -472,7 +567,7 @@ int b2r_create(b2r_ctx** out, const b2r_config* cfg) {
 void b2r_destroy(b2r_ctx* c) {
 	if (!c) return;
 	cudaSetDevice(c->cfg.device);
-	if (c->stream) cudaStreamSynchronize(c->stream);
+	if (c->stream) sync_main(c);
 	for (size_t r = 0; r < c->peer_acc.size(); r++) if (c->peer_acc[r] && r != c->my_rank) cudaIpcCloseMemHandle(c->peer_acc[r]);
 	b2r_team_close(c); if (c->d_team) { cudaFree(c->d_team); c->d_team = nullptr; }
 	drop_graph(c);
@@ -488,6 +583,10 @@ void b2r_destroy(b2r_ctx* c) {
 	if (c->h_stage) cudaFreeHost(c->h_stage);
 	if (c->ev_stage) cudaEventDestroy(c->ev_stage);
 	if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); cudaEventDestroy(c->ev_resolved); cudaEventDestroy(c->ev_copied); }
+	for (auto& S : c->side) {
+		for (uint32_t j = 1; j < kMaxLanes; j++) if (S.lane_stream[j]) { cudaStreamDestroy(S.lane_stream[j]); cudaEventDestroy(S.ev_join[j]); }
+		if (S.stream) { cudaStreamDestroy(S.stream); cudaEventDestroy(S.ev_traced); cudaEventDestroy(S.ev_folded); cudaEventDestroy(S.ev_sync); cudaEventDestroy(S.ev_fork); }
+	}
 	for (uint32_t j = 1; j < kMaxLanes; j++) if (c->lane_stream[j]) { cudaStreamDestroy(c->lane_stream[j]); cudaEventDestroy(c->ev_join[j]); }
 	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -499,7 +598,7 @@ int b2r_resize(b2r_ctx* c, uint32_t width, uint32_t height) {
 	if (width == 0 || height == 0 || width % 16 || height % 16) return fail(B2R_ERR_ARG, "width/height must be non-zero multiples of 16");
 	if (static_cast<uint64_t>(width) * height > kPixMask) return fail(B2R_ERR_ARG, "image too large");
 	int rc = ensure_device(c); if (rc) return rc;
-	CU(cudaStreamSynchronize(c->stream));
+	CU(sync_main(c));
 	if (c->copy_pending) { CU(cudaEventSynchronize(c->ev_copied)); c->copy_pending = false; }
 	if (width == c->cfg.width && height == c->cfg.height) return b2r_reset(c);
 	if (!c->peer_acc.empty() || !c->team_acc.empty()) return fail(B2R_ERR_STATE, "the bucket array / framebuffer are exported to peers (CUDA IPC): b2r_ipc_close / b2r_team_close on every rank before a resize, then export again");
@@ -520,7 +619,7 @@ int b2r_reset(b2r_ctx* c) {
 int b2r_set_stream(b2r_ctx* c, void* cuda_stream) {
 	if (!c) return fail(B2R_ERR_ARG, "null context");
 	int rc = ensure_device(c); if (rc) return rc;
-	CU(cudaStreamSynchronize(c->stream));
+	CU(sync_main(c));
 	c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
 	drop_graph(c);
 	return B2R_OK;
@@ -529,14 +628,14 @@ int b2r_set_stream(b2r_ctx* c, void* cuda_stream) {
 int b2r_sync(b2r_ctx* c) {
 	if (!c) return fail(B2R_ERR_ARG, "null context");
 	int rc = ensure_device(c); if (rc) return rc;
-	CU(cudaStreamSynchronize(c->stream));
+	CU(sync_main(c));
 	return collect_timings(c);
 }
 
 int b2r_set_flags(b2r_ctx* c, uint32_t flags) {
 	if (!c) return fail(B2R_ERR_ARG, "null context");
 	int rc = ensure_device(c); if (rc) return rc;
-	CU(cudaStreamSynchronize(c->stream));
+	CU(sync_main(c));
 	if ((c->cfg.flags ^ flags) & B2R_FLAG_REFERENCE_TREE) return fail(B2R_ERR_STATE, "B2R_FLAG_REFERENCE_TREE can only be chosen at b2r_create");
 	if ((c->cfg.flags ^ flags) & B2R_FLAG_REFERENCE_EXACT) return fail(B2R_ERR_STATE, "B2R_FLAG_REFERENCE_EXACT can only be chosen at b2r_create");
 	if ((flags & B2R_FLAG_GGX) && (flags & B2R_FLAG_REFERENCE_EXACT)) return fail(B2R_ERR_ARG, "B2R_FLAG_GGX cannot be combined with B2R_FLAG_REFERENCE_EXACT");
@@ -571,6 +670,7 @@ int stage_upload(b2r_ctx* c, const UploadPart* parts, size_t n_parts) {
 		off += (q.bytes + 255) & ~static_cast<size_t>(255);
 	}
 	CU(cudaEventRecord(c->ev_stage, c->stream)); c->stage_busy = true;
+	c->scene_epoch++;  // the side streams may not trace the next batch before these copies have landed
 	return B2R_OK;
 }
 }  // namespace
@@ -644,7 +744,7 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 	const bool grow = h_prims.size() > c->cap_prims || h_pm.size() > c->cap_prim_mat || h_alb.size() > c->cap_mat_albedo || h_em.size() > c->cap_mat_emission || h_f0.size() > c->cap_mat_f0 ||
 	                  h_ls.size() > c->cap_light_sphere || h_le.size() > c->cap_light_emit || c->n_wide > c->cap_wide || c->n_wide > c->cap_parent || n_prims > c->cap_leaf_node ||
 	                  (has_ambient && static_cast<size_t>(hdri_w) * hdri_h > c->cap_hdri);
-	if (grow) CU(cudaStreamSynchronize(c->stream));  // device arrays in use are about to be replaced (first upload, or a larger scene)
+	if (grow) CU(sync_main(c));  // device arrays in use are about to be replaced (first upload, or a larger scene)
 	if ((rc = dev_reserve(&c->d_prims, &c->cap_prims, h_prims.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_prim_mat, &c->cap_prim_mat, h_pm.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_mat_albedo, &c->cap_mat_albedo, h_alb.size()))) return rc;
@@ -734,7 +834,7 @@ int b2r_refit_scene(b2r_ctx* c, const b2r_sphere* prims, uint32_t n_prims, const
 	if ((rc = dev_reserve(&c->d_remap, &c->cap_remap, remap.size()))) return rc;
 	const bool grow = ps.mat_albedo.size() > c->cap_mat_albedo || ps.mat_emission.size() > c->cap_mat_emission || ps.mat_f0.size() > c->cap_mat_f0 ||
 	                  ps.light_sphere.size() > c->cap_light_sphere || ps.light_emit.size() > c->cap_light_emit;
-	if (grow) CU(cudaStreamSynchronize(c->stream));  // more materials or lights than before: those (small) arrays are replaced
+	if (grow) CU(sync_main(c));  // more materials or lights than before: those (small) arrays are replaced
 	if ((rc = dev_reserve(&c->d_mat_albedo, &c->cap_mat_albedo, ps.mat_albedo.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_mat_emission, &c->cap_mat_emission, ps.mat_emission.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_mat_f0, &c->cap_mat_f0, ps.mat_f0.size()))) return rc;
@@ -774,7 +874,7 @@ int b2r_refit_scene(b2r_ctx* c, const b2r_sphere* prims, uint32_t n_prims, const
 		double cost = 0.0, base = c->wide_host.cost;
 		CU(cudaMemcpyAsync(&cost, c->d_cost, sizeof cost, cudaMemcpyDeviceToHost, c->stream));
 		if (c->gpu_tree && c->d_cost_base) CU(cudaMemcpyAsync(&base, c->d_cost_base, sizeof base, cudaMemcpyDeviceToHost, c->stream));
-		CU(cudaStreamSynchronize(c->stream));
+		CU(sync_main(c));
 		*quality_out = base > 0.0 ? static_cast<float>(cost / base) : 1.0f;
 	}
 	return B2R_OK;
@@ -808,8 +908,15 @@ int b2r_accumulate(b2r_ctx* c, uint32_t n_samples) {
 			// traced ahead by an earlier call: fold it (samples are folded in index order: earlier samples of this call go first)
 			if (args.n) { if ((rc = run_batch(c, args))) return rc; args.n = 0; }
 			BatchArgs f = c->spec_args; f.fold = 1ull << f.slot_of(c->spec_used);
-			k_set_batch<<<1, kMaxSlots, 0, c->stream>>>(c->d_batch, f);
-			k_accumulate<<<c->grid_stream, kBlock, 0, c->stream>>>(c->params);
+			if (use_sides(c)) {  // the samples wait in the side's part of RAD that traced them; that side is not reused before this fold has run
+				b2r_ctx::Side& S = c->side[c->spec_side];
+				k_set_batch<<<1, kMaxSlots, 0, c->stream>>>(c->d_batch + c->spec_side * (1u + kMaxLanes), f);
+				k_accumulate<<<c->grid_stream, kBlock, 0, c->stream>>>(side_params(c, c->spec_side));
+				CU(cudaEventRecord(S.ev_folded, c->stream)); S.folded_valid = true;
+			} else {
+				k_set_batch<<<1, kMaxSlots, 0, c->stream>>>(c->d_batch, f);
+				k_accumulate<<<c->grid_stream, kBlock, 0, c->stream>>>(c->params);
+			}
 			CU(cudaGetLastError()); c->launches += 1;
 			if (++c->spec_used == c->spec_count) { c->spec_count = 0; c->spec_used = 0; c->spec_width = c->spec_width * 2u > kSpecMax ? kSpecMax : c->spec_width * 2u; }
 			continue;
@@ -818,22 +925,22 @@ int b2r_accumulate(b2r_ctx* c, uint32_t n_samples) {
 		if (!owns_sample(c, acc)) continue;
 		if (speculate && n_samples == 1) {
 			// the reference's frame loop: one Accumulate() per application frame. Trace spec_width samples now, fold the first.
-			const uint32_t w = c->spec_width < c->slots ? c->spec_width : c->slots;
+			const uint32_t w = c->spec_width < batch_cap(c) ? c->spec_width : batch_cap(c);
 			args.n = w; for (uint32_t i = 0; i < w; i++) args.acc[i] = acc + i;
 			args.fold = 1ull;
 			if ((rc = run_batch(c, args))) return rc;
-			if (w > 1) { c->spec_args = args; c->spec_first = acc; c->spec_count = w; c->spec_used = 1; }
+			if (w > 1) { c->spec_args = args; c->spec_first = acc; c->spec_count = w; c->spec_used = 1; c->spec_side = c->last_side; }
 			else c->spec_width = 2;
 			return B2R_OK;
 		}
 		args.acc[args.n++] = acc;
-		if (args.n == c->slots || (s + 1 == n_samples && args.n)) { if ((rc = run_batch(c, args))) return rc; args.n = 0; }
+		if (args.n == batch_cap(c) || (s + 1 == n_samples && args.n)) { if ((rc = run_batch(c, args))) return rc; args.n = 0; }
 	}
 	if (args.n) { if ((rc = run_batch(c, args))) return rc; }
 	return B2R_OK;
 }
 
-static int resolve_with(b2r_ctx* c, const BucketPtrs& bp, float* rgba_out_host, int tonemap, bool async = false) {
+static int resolve_with(b2r_ctx* c, const BucketPtrs& bp, float* rgba_out_host, int tonemap, bool async = false, bool enqueue_only = false) {
 	int rc = ensure_device(c); if (rc) return rc;
 	if (c->accumulations == 0 || c->accumulations % c->cfg.buckets) return B2R_ERR_NOT_READY;  // Renderer.hpp:437
 	const float scale = c->params.frame.cam.exposure / static_cast<float>(c->accumulations / c->cfg.buckets);  // :439
@@ -852,8 +959,9 @@ static int resolve_with(b2r_ctx* c, const BucketPtrs& bp, float* rgba_out_host, 
 		c->copy_pending = true;
 		return B2R_OK;
 	}
+	if (enqueue_only) return B2R_OK;  // b2r_resolve_device: the frame stays in the device framebuffer and nobody waits
 	if (rgba_out_host) CU(cudaMemcpyAsync(rgba_out_host, c->d_fb, bytes, cudaMemcpyDeviceToHost, c->stream));
-	CU(cudaStreamSynchronize(c->stream));
+	CU(sync_main(c));
 	return collect_timings(c);
 }
 
@@ -864,6 +972,12 @@ int b2r_resolve_async(b2r_ctx* c, float* rgba_out_host, int tonemap) {
 	BucketPtrs bp{};
 	for (uint32_t k = 0; k < c->cfg.buckets; k++) bp.k[k] = c->d_acc + static_cast<size_t>(k) * 3 * c->params.frame.npix;
 	return resolve_with(c, bp, rgba_out_host, tonemap, true);
+}
+int b2r_resolve_device(b2r_ctx* c, int tonemap) {
+	if (!c) return fail(B2R_ERR_ARG, "null context");
+	BucketPtrs bp{};
+	for (uint32_t k = 0; k < c->cfg.buckets; k++) bp.k[k] = c->d_acc + static_cast<size_t>(k) * 3 * c->params.frame.npix;
+	return resolve_with(c, bp, nullptr, tonemap, false, true);
 }
 int b2r_frame_wait(b2r_ctx* c) {
 	if (!c) return fail(B2R_ERR_ARG, "null context");
@@ -891,7 +1005,7 @@ int b2r_ipc_export_buckets(b2r_ctx* c, unsigned char handle_out[64]) {
 int b2r_ipc_close(b2r_ctx* c) {
 	if (!c) return fail(B2R_ERR_ARG, "null context");
 	int rc = ensure_device(c); if (rc) return rc;
-	CU(cudaStreamSynchronize(c->stream));
+	CU(sync_main(c));
 	for (size_t r = 0; r < c->peer_acc.size(); r++) if (c->peer_acc[r] && r != c->my_rank) cudaIpcCloseMemHandle(c->peer_acc[r]);
 	c->peer_acc.clear();
 	return B2R_OK;
@@ -924,7 +1038,7 @@ int b2r_resolve_peers(b2r_ctx* c, float* rgba_out_host, int tonemap) {
 int b2r_team_close(b2r_ctx* c) {
 	if (!c) return fail(B2R_ERR_ARG, "null context");
 	int rc = ensure_device(c); if (rc) return rc;
-	CU(cudaStreamSynchronize(c->stream));
+	CU(sync_main(c));
 	if (c->copy_stream) CU(cudaStreamSynchronize(c->copy_stream));
 	for (size_t r = 0; r < c->team_acc.size(); r++) if (r != c->team_rank) { if (c->team_acc[r]) cudaIpcCloseMemHandle(c->team_acc[r]); if (c->team_sync[r]) cudaIpcCloseMemHandle(c->team_sync[r]); }
 	if (c->team_fb0 && c->team_rank != 0) cudaIpcCloseMemHandle(c->team_fb0);
@@ -935,7 +1049,7 @@ int b2r_team_export(b2r_ctx* c, unsigned char handles_out[192]) {
 	if (!c || !handles_out) return fail(B2R_ERR_ARG, "null argument");
 	int rc = ensure_device(c); if (rc) return rc;
 	if (!c->d_team) { CU(cudaMalloc(reinterpret_cast<void**>(&c->d_team), sizeof(TeamSync))); }
-	CU(cudaMemsetAsync(c->d_team, 0, sizeof(TeamSync), c->stream)); CU(cudaStreamSynchronize(c->stream));
+	CU(cudaMemsetAsync(c->d_team, 0, sizeof(TeamSync), c->stream)); CU(sync_main(c));
 	cudaIpcMemHandle_t h;
 	CU(cudaIpcGetMemHandle(&h, c->d_acc)); std::memcpy(handles_out, &h, 64);
 	CU(cudaIpcGetMemHandle(&h, c->d_fb)); std::memcpy(handles_out + 64, &h, 64);
@@ -1017,7 +1131,7 @@ int b2r_team_resolve(b2r_ctx* c, float* rgba_out_host, int tonemap, int async) {
 	}
 	if (rgba_out_host) CU(cudaMemcpyAsync(rgba_out_host, c->d_fb, bytes, cudaMemcpyDeviceToHost, c->stream));
 	if ((rc = team_signal(c, c->stream, TEAM_COPIED, f))) return rc;
-	if (rgba_out_host) { CU(cudaStreamSynchronize(c->stream)); return collect_timings(c); }
+	if (rgba_out_host) { CU(sync_main(c)); return collect_timings(c); }
 	return B2R_OK;
 }
 int b2r_team_error(b2r_ctx* c, uint32_t* out) {
@@ -1026,7 +1140,7 @@ int b2r_team_error(b2r_ctx* c, uint32_t* out) {
 	if (!c->d_team) return B2R_OK;
 	int rc = ensure_device(c); if (rc) return rc;
 	CU(cudaMemcpyAsync(out, &c->d_team->error, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-	CU(cudaStreamSynchronize(c->stream));
+	CU(sync_main(c));
 	return B2R_OK;
 }
 
@@ -1050,7 +1164,7 @@ int b2r_read_buckets(b2r_ctx* c, float* out_host) {
 	if (!c || !out_host) return fail(B2R_ERR_ARG, "null argument");
 	int rc = ensure_device(c); if (rc) return rc;
 	CU(cudaMemcpyAsync(out_host, c->d_acc, static_cast<size_t>(c->cfg.buckets) * 3 * c->params.frame.npix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-	CU(cudaStreamSynchronize(c->stream));
+	CU(sync_main(c));
 	return collect_timings(c);
 }
 int b2r_write_buckets(b2r_ctx* c, const float* in_host) {
@@ -1058,7 +1172,7 @@ int b2r_write_buckets(b2r_ctx* c, const float* in_host) {
 	int rc = ensure_device(c); if (rc) return rc;
 	drop_speculation(c);
 	CU(cudaMemcpyAsync(c->d_acc, in_host, static_cast<size_t>(c->cfg.buckets) * 3 * c->params.frame.npix * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-	CU(cudaStreamSynchronize(c->stream));
+	CU(sync_main(c));
 	return B2R_OK;
 }
 
@@ -1120,7 +1234,7 @@ int b2r_read_counters(b2r_ctx* c, uint64_t out[10]) {
 	int rc = ensure_device(c); if (rc) return rc;
 	unsigned long long h[ST_COUNT];
 	CU(cudaMemcpyAsync(h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost, c->stream));
-	CU(cudaStreamSynchronize(c->stream));
+	CU(sync_main(c));
 	out[0] = h[ST_EXT]; out[1] = h[ST_SHADOW]; out[2] = h[ST_HITS]; out[3] = h[ST_TERM]; out[4] = h[ST_DROPPED]; out[5] = h[ST_SPHERE]; out[6] = h[ST_BOX];
 	out[7] = c->launches; out[8] = h[ST_EVENTS]; out[9] = 0;
 	return collect_timings(c);
@@ -1131,8 +1245,8 @@ int b2r_read_bounce_counts(b2r_ctx* c, uint32_t* paths_out, uint32_t* shadow_out
 	const uint32_t mb = c->cfg.max_bounces;
 	const size_t block = (static_cast<size_t>(mb) + 1) * 4;
 	std::vector<uint32_t> h(block * kMaxLanes);  // the last batch's counters: one block per lane (unused lanes' blocks stay zero)
-	CU(cudaMemcpyAsync(h.data(), c->d_counts, kMaxLanes * c->counts_bytes, cudaMemcpyDeviceToHost, c->stream));
-	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaMemcpyAsync(h.data(), c->d_counts + static_cast<size_t>(c->counts_first) * block, kMaxLanes * c->counts_bytes, cudaMemcpyDeviceToHost, c->stream));
+	CU(sync_main(c));
 	for (uint32_t b = 0; b < n; b++) {
 		paths_out[b] = 0u; shadow_out[b] = 0u;
 		for (uint32_t j = 0; j < kMaxLanes; j++) { if (b <= mb) paths_out[b] += h[j * block + b]; if (b < mb) shadow_out[b] += h[j * block + mb + 1 + b]; }
@@ -1143,7 +1257,7 @@ int b2r_reset_counters(b2r_ctx* c) {
 	if (!c) return fail(B2R_ERR_ARG, "null context");
 	int rc = ensure_device(c); if (rc) return rc;
 	CU(cudaMemsetAsync(c->d_stats, 0, ST_COUNT * sizeof(unsigned long long), c->stream));
-	c->launches = 0;
+	c->launches = 0; c->scene_epoch++;
 	return B2R_OK;
 }
 int b2r_read_kernel_times(b2r_ctx* c, double ms_out[8], uint64_t launches_out[8], int reset) {
@@ -1163,7 +1277,7 @@ int b2r_generate_rays(b2r_ctx* c, uint32_t acc, float* out_host) {
 	k_tap_generate<<<c->grid_stream, kBlock, 0, c->stream>>>(c->params, acc, d);
 	cudaError_t e = cudaGetLastError();
 	if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	if (e == cudaSuccess) e = sync_main(c);
 	cudaFree(d); c->launches++;
 	if (e != cudaSuccess) return fail(B2R_ERR_CUDA, cudaGetErrorString(e));
 	return B2R_OK;
@@ -1192,7 +1306,7 @@ static int trace_common(b2r_ctx* c, const float* rays, const float* tfar_in, uin
 	}
 	if (e == cudaSuccess && !shadow) { e = cudaMemcpyAsync(tfar_out, d_tout, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost, c->stream); if (e == cudaSuccess) e = cudaMemcpyAsync(prim_out, d_prim, static_cast<size_t>(n) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream); }
 	if (e == cudaSuccess && shadow) e = cudaMemcpyAsync(occ_out, d_occ, static_cast<size_t>(n), cudaMemcpyDeviceToHost, c->stream);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	if (e == cudaSuccess) e = sync_main(c);
 	if (e != cudaSuccess) return fail(B2R_ERR_CUDA, cudaGetErrorString(e));
 	return B2R_OK;
 }
@@ -1218,7 +1332,7 @@ int b2r_read_wide_nodes(b2r_ctx* c, void* out_host, uint32_t* n_wide_nodes, uint
 	if (out_host && c->wide_refit) {  // after b2r_refit_scene the device holds the current boxes
 		int rc = ensure_device(c); if (rc) return rc;
 		CU(cudaMemcpyAsync(out_host, c->d_wide, static_cast<size_t>(c->n_wide) * sizeof(WideNode), cudaMemcpyDeviceToHost, c->stream));
-		CU(cudaStreamSynchronize(c->stream));
+		CU(sync_main(c));
 	} else if (out_host) std::memcpy(out_host, c->wide_host.nodes.data(), c->wide_host.nodes.size() * sizeof(WideNode));
 	return B2R_OK;
 }

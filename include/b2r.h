@@ -169,6 +169,11 @@ int  b2r_resolve(b2r_ctx* ctx, float* rgba_out_host, int tonemap);
  * computation with the hand-over made explicit. */
 int  b2r_resolve_async(b2r_ctx* ctx, float* rgba_out_host, int tonemap);
 int  b2r_frame_wait(b2r_ctx* ctx);   /* blocks until the frame of the last b2r_resolve_async has landed in host memory */
+/* Render() into the device framebuffer (b2r_device_framebuffer) without waiting for it: only enqueues the resolve kernel, so frames enqueued
+ * back to back are pipelined on the device — the library traces consecutive batches on alternating halves of its queue memory ("sides"), and
+ * the thin last bounces of frame N, its fold and its resolve run under the first bounces of frame N+1. b2r_sync (or any synchronising call)
+ * before the frame is read. Same return values as b2r_resolve. */
+int  b2r_resolve_device(b2r_ctx* ctx, int tonemap);
 /* Same, reading the K bucket sums from another device array of the same layout (e.g. the NCCL-combined buckets of a
  * multi-GPU frame) instead of this context's own accumulator. dev_buckets == NULL means the context's own. */
 int  b2r_resolve_from(b2r_ctx* ctx, const void* dev_buckets, float* rgba_out_host, int tonemap);

@@ -664,6 +664,37 @@ def test_async_resolve_delivers_the_same_frames():
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("n,flags", [(9, 0), (3000, 0), (3000, b2r.FLAG_GGX)])
+def test_frames_enqueued_back_to_back_equal_frames_waited_for(n, flags):
+    """b2r_resolve_device: frames enqueued without a host wait are traced on alternating halves of the queue memory ("sides", on the library's
+    own streams) while the previous frame's last bounces, fold and resolve still run — reset, fold and resolve stay on the caller's stream in
+    call order. Buckets after every frame (read back once the pipeline has drained) and the frames themselves equal those of a renderer that
+    waits after every call, bit for bit; a scene edit and a camera move between two pipelined frames land between exactly those frames."""
+    sc = scenes.default_scene() if n == 9 else scenes.ggx_random_scene(n, light_every=30)
+    w, h, mb, K = 256, 160, 8, 4
+    a = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=K, flags=flags); b = b2r.Renderer(sc, w, h, max_bounces=mb, buckets=K, flags=flags)
+    rs = np.random.RandomState(3)
+    geo2 = _moved_geometry(sc["geometry"], rs, jitter=0.3)
+    sc2 = scenes.Scene(sc); sc2["geometry"] = geo2
+    cam2 = dict(sc["camera"]); cam2["eye"] = tuple(np.asarray(cam2["eye"], np.float64) + np.array([0.05, 0.02, -0.1]))
+    want = []
+    for i in range(6):
+        if i == 3: a.SetScene(b2r.PreparedScene(sc2, w, h))
+        if i == 4: a.SetCamera(b2r.PreparedScene(dict(sc2, camera=cam2), w, h).camera)
+        a.ResetAccumulator(); a.Accumulate(3 * K); assert a.Render(); a.sync(); want.append((a.buckets_host().copy(), a.framebuffer.copy()))
+    got = []
+    for i in range(6):  # nothing in this loop waits for the device
+        if i == 3: b.SetScene(b2r.PreparedScene(sc2, w, h))
+        if i == 4: b.SetCamera(b2r.PreparedScene(dict(sc2, camera=cam2), w, h).camera)
+        b.ResetAccumulator(); b.Accumulate(3 * K); assert b.RenderDevice()
+        if i in (2, 5):  # drain and look: the frame on the device is frame i
+            b.sync(); bk = b.buckets_host().copy(); assert b.Render(); got.append((i, bk, b.framebuffer.copy()))
+    for i, bk, fb in got:
+        assert bk.tobytes() == want[i][0].tobytes() and fb.tobytes() == want[i][1].tobytes(), i
+    b.Accumulate(1); assert not b.RenderDevice()  # accumulations % K != 0: no-op like Renderer::Render (Renderer.hpp:437)
+    a.close(); b.close()
+
+
 # ------------------------------------------------------------------------------------------------ scene edit: GPU refit
 def _moved_geometry(geo, rs, jitter=0.5, far=0):
     """Every sphere moves by up to `jitter` radii and changes radius by up to 20 %; `far` of them jump anywhere in the scene."""
