@@ -120,6 +120,10 @@ struct Renderer {
 		const int rc = b2r_resolve(ctx, reinterpret_cast<float*>(framebuffer.data()), 1);
 		if (rc < 0) check(rc);  // B2R_ERR_NOT_READY (accumulations % buckets != 0) is the reference's silent early return (:437)
 	}
+	// Render() into the DEVICE framebuffer without waiting (b2r_resolve_device): for a display path that reads device memory (b2r_device_framebuffer);
+	// frames enqueued back to back are pipelined on the device. Sync() before the frame is read.
+	void RenderDevice() { const int rc = b2r_resolve_device(ctx, 1); if (rc < 0) check(rc); }
+	void Sync() { check(b2r_sync(ctx)); }
 	// BoundingVolumeHierarchy::Traverse on caller rays (focus picking, Application.cpp:282-298): rays = n x {origin, dir}
 	void Traverse(const float* rays, uint32_t n, float* tfar_out, int32_t* prim_out) { check(b2r_trace_closest(ctx, rays, n, tfar_out, prim_out)); }
 	// BoundingVolumeHierarchy::Traverse_shadow (BVH.hpp:362): occluded_out[i] = 1 when anything lies within [0, tfar[i]) along ray i
