@@ -255,65 +255,63 @@ template <typename F> int launch(b2r_ctx* c, int kind, bool profile, F&& f) {
 	return B2R_OK;
 }
 
+// The kernel variants a context's flags select (template instantiations of b2r_device.cuh), chosen once per enqueue instead of at every launch.
+using BounceKernel = void (*)(const Params, const uint32_t);
+struct KernelSet {
+	BounceKernel brute_first, brute, brute_finish, packet, closest, shade, shadow;
+	int g_brute_first, g_brute, g_brute_finish;
+};
+KernelSet pick_kernels(const b2r_ctx* c) {
+	const bool count = (c->cfg.flags & B2R_FLAG_COUNT_TESTS) != 0, exact = (c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) != 0, ggx = (c->cfg.flags & B2R_FLAG_GGX) != 0;
+	const bool tn16 = c->params.scene.stack_tn_bits == 16u;  // stack entries split 16/16 (up to 65536 wide nodes: C3) get immediate shifts; other sizes read the split from the scene
+	KernelSet k{};
+	// brute-force pipeline: <FIRST, COUNT, EXACT, GGX> (the GGX closure's kernels are built without the sphere-test counters)
+	if (ggx)        { k.brute_first = k_bounce_brute<true, false, false, true>; k.brute = k_bounce_brute<false, false, false, true>; k.g_brute_first = c->grid_brute_first_ggx; k.g_brute = c->grid_brute_ggx; }
+	else if (exact) { k.brute_first = count ? k_bounce_brute<true, true, true> : k_bounce_brute<true, false, true>; k.brute = count ? k_bounce_brute<false, true, true> : k_bounce_brute<false, false, true>; k.g_brute_first = c->grid_brute_first_exact; k.g_brute = c->grid_brute_exact; }
+	else            { k.brute_first = count ? k_bounce_brute<true, true, false> : k_bounce_brute<true, false, false>; k.brute = count ? k_bounce_brute<false, true, false> : k_bounce_brute<false, false, false>; k.g_brute_first = c->grid_brute_first; k.g_brute = c->grid_brute; }
+	k.brute_finish = ggx ? k_brute_finish<false, true> : count ? k_brute_finish<true> : k_brute_finish<false>;
+	k.g_brute_finish = ggx ? c->grid_brute_finish_ggx : c->grid_brute_finish;
+	// BVH pipeline
+	k.packet = count ? k_intersect_packet<true, B2R_PACKET_RPL> : k_intersect_packet<false, B2R_PACKET_RPL>;
+	if (exact) k.closest = count ? (tn16 ? k_intersect_closest<true, true, 16u> : k_intersect_closest<true, true, 0u>) : (tn16 ? k_intersect_closest<false, true, 16u> : k_intersect_closest<false, true, 0u>);
+	else       k.closest = count ? (tn16 ? k_intersect_closest<true, false, 16u> : k_intersect_closest<true, false, 0u>) : (tn16 ? k_intersect_closest<false, false, 16u> : k_intersect_closest<false, false, 0u>);
+	k.shade = ggx ? k_shade<false, true> : exact ? k_shade<true> : k_shade<false>;
+	k.shadow = count ? k_intersect_shadow<true> : k_intersect_shadow<false>;
+	return k;
+}
+
 // The max_bounces rounds of one batch — or of one lane's half of it — on stream st; p carries that batch's queues, counters and descriptor.
 int enqueue_rounds(b2r_ctx* c, const Params& p_in, cudaStream_t st, bool profile, float grid_frac = 1.0f) {
-	const Params& p = p_in;
 	// (measurement tap, B2R_LANE_GRID: the lanes of a twin batch may be given a fraction of the resident-CTA grid each, so that the two lanes'
 	// kernels sit on every SM side by side instead of taking turns)
 	auto G = [&](int g) { const int per_sm = g / c->sm_count; int k = static_cast<int>(per_sm * grid_frac + 0.5f); if (k < 1) k = 1; return k * c->sm_count; };
-	const bool count = (c->cfg.flags & B2R_FLAG_COUNT_TESTS) != 0;
+	const bool exact = (c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) != 0, ggx = (c->cfg.flags & B2R_FLAG_GGX) != 0;
+	if (exact && c->params.scene.n_mat > 64) return fail(B2R_ERR_STATE, "B2R_FLAG_REFERENCE_EXACT: at most 64 materials (RendererPolicy::max_materialID, Renderer.hpp:23)");
+	const KernelSet k = pick_kernels(c);
 	const uint32_t mb = c->cfg.max_bounces;
+	Params p = p_in;
 	int rc;
+	auto run = [&](int kind, BounceKernel fn, int grid, int block, uint32_t b) { return launch(c, kind, profile, [&] { fn<<<grid, block, 0, st>>>(p, b); }); };
 	if (!c->use_bvh) {
-		const bool exact = (c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) != 0;
-		if (exact && c->params.scene.n_mat > 64) return fail(B2R_ERR_STATE, "B2R_FLAG_REFERENCE_EXACT: at most 64 materials (RendererPolicy::max_materialID, Renderer.hpp:23)");
-		const bool ggx = (c->cfg.flags & B2R_FLAG_GGX) != 0;  // the GGX closure's kernels are built without the sphere-test counters
-		const bool finish = !exact && c->params.frame.finish_below != 0u && c->params.scene.n_prims <= static_cast<uint32_t>(kBruteTile);
-		Params p = p_in;  // (shadows the reference above) the hand-over threshold only reaches the kernels when k_brute_finish is launched too
-		if (!finish) p.frame.finish_below = 0u;
+		const bool finish = !exact && p.frame.finish_below != 0u && p.scene.n_prims <= static_cast<uint32_t>(kBruteTile);
+		if (!finish) p.frame.finish_below = 0u;  // the hand-over threshold only reaches the kernels when k_brute_finish is launched too
 		for (uint32_t b = 0; b < mb; b++) {
-			if (finish && b >= p.frame.finish_first && b + 1 < mb) {  // takes the remaining paths over once few enough are left (a no-op launch otherwise)
-				if ((rc = launch(c, KK_BRUTE, profile, [&] { if (ggx) k_brute_finish<false, true><<<c->grid_brute_finish_ggx, kBruteBlock, 0, st>>>(p, b); else if (count) k_brute_finish<true><<<c->grid_brute_finish, kBruteBlock, 0, st>>>(p, b); else k_brute_finish<false><<<c->grid_brute_finish, kBruteBlock, 0, st>>>(p, b); }))) return rc;
-			}
-			rc = launch(c, KK_BRUTE, profile, [&] {
-				if (ggx) {
-					if (b == 0) k_bounce_brute<true, false, false, true><<<c->grid_brute_first_ggx, kBruteBlock, 0, st>>>(p, b);
-					else k_bounce_brute<false, false, false, true><<<c->grid_brute_ggx, kBruteBlock, 0, st>>>(p, b);
-				} else if (exact) {
-					if (b == 0) { if (count) k_bounce_brute<true, true, true><<<c->grid_brute_first_exact, kBruteBlock, 0, st>>>(p, b); else k_bounce_brute<true, false, true><<<c->grid_brute_first_exact, kBruteBlock, 0, st>>>(p, b); }
-					else { if (count) k_bounce_brute<false, true, true><<<c->grid_brute_exact, kBruteBlock, 0, st>>>(p, b); else k_bounce_brute<false, false, true><<<c->grid_brute_exact, kBruteBlock, 0, st>>>(p, b); }
-				} else {
-					if (b == 0) { if (count) k_bounce_brute<true, true, false><<<c->grid_brute_first, kBruteBlock, 0, st>>>(p, b); else k_bounce_brute<true, false, false><<<c->grid_brute_first, kBruteBlock, 0, st>>>(p, b); }
-					else { if (count) k_bounce_brute<false, true, false><<<c->grid_brute, kBruteBlock, 0, st>>>(p, b); else k_bounce_brute<false, false, false><<<c->grid_brute, kBruteBlock, 0, st>>>(p, b); }
-				}
-			});
-			if (rc) return rc;
+			// k_brute_finish takes the remaining paths over once few enough are left (a no-op launch otherwise)
+			if (finish && b >= p.frame.finish_first && b + 1 < mb && (rc = run(KK_BRUTE, k.brute_finish, k.g_brute_finish, kBruteBlock, b))) return rc;
+			if ((rc = b == 0 ? run(KK_BRUTE, k.brute_first, k.g_brute_first, kBruteBlock, b) : run(KK_BRUTE, k.brute, k.g_brute, kBruteBlock, b))) return rc;
 			// the reference's stream order for the next bounce (the ranking kernel's time is booked under the brute kind)
-			if (exact && b + 1 < mb) { if ((rc = launch(c, KK_BRUTE, profile, [&] { k_stream_rank<<<c->grid_stream, 256, 0, st>>>(p, b); }))) return rc; }
+			if (exact && b + 1 < mb && (rc = run(KK_BRUTE, k_stream_rank, c->grid_stream, 256, b))) return rc;
 		}
-	} else {
-		if (!c->packet_primary) { if ((rc = launch(c, KK_GENERATE, profile, [&] { k_generate<<<c->grid_stream, kBlock, 0, st>>>(p); }))) return rc; }  // (the packet kernel generates the camera rays itself)
-		const bool mis = !(c->cfg.flags & B2R_FLAG_NO_MIS);
-		const bool exact = (c->cfg.flags & B2R_FLAG_REFERENCE_EXACT) != 0;
-		if (exact && c->params.scene.n_mat > 64) return fail(B2R_ERR_STATE, "B2R_FLAG_REFERENCE_EXACT: at most 64 materials (RendererPolicy::max_materialID, Renderer.hpp:23)");
-		for (uint32_t b = 0; b < mb; b++) {
-			if (b == 0 && c->packet_primary) {  // camera rays: one walk per warp (k_intersect_packet)
-				if ((rc = launch(c, KK_CLOSEST, profile, [&] { if (count) k_intersect_packet<true, B2R_PACKET_RPL><<<G(c->grid_packet), kTravBlock, 0, st>>>(p, b); else k_intersect_packet<false, B2R_PACKET_RPL><<<G(c->grid_packet), kTravBlock, 0, st>>>(p, b); }))) return rc;
-			} else
-			if ((rc = launch(c, KK_CLOSEST, profile, [&] {
-				// stack entries split 16/16 (up to 65536 wide nodes: C3) get immediate shifts; other sizes read the split from the scene
-				const bool tn16 = c->params.scene.stack_tn_bits == 16u;
-#define B2R_CLOSEST(COUNT, EXACT) do { if (tn16) k_intersect_closest<COUNT, EXACT, 16u><<<G(c->grid_closest), kTravBlock, 0, st>>>(p, b); else k_intersect_closest<COUNT, EXACT, 0u><<<G(c->grid_closest), kTravBlock, 0, st>>>(p, b); } while (0)
-				if (exact) { if (count) B2R_CLOSEST(true, true); else B2R_CLOSEST(false, true); }
-				else { if (count) B2R_CLOSEST(true, false); else B2R_CLOSEST(false, false); }
-#undef B2R_CLOSEST
-			}))) return rc;
-			if ((rc = launch(c, KK_SHADE, profile, [&] { if (c->cfg.flags & B2R_FLAG_GGX) k_shade<false, true><<<G(c->grid_shade_ggx), kBruteBlock, 0, st>>>(p, b); else if (exact) k_shade<true><<<G(c->grid_shade), kBruteBlock, 0, st>>>(p, b); else k_shade<false><<<G(c->grid_shade), kBruteBlock, 0, st>>>(p, b); }))) return rc;
-			if (exact && b + 1 < mb) { if ((rc = launch(c, KK_SHADE, profile, [&] { k_stream_rank<<<c->grid_stream, 256, 0, st>>>(p, b); }))) return rc; }
-			if (mis && b + 1 < mb) {
-				if ((rc = launch(c, KK_SHADOW, profile, [&] { if (count) k_intersect_shadow<true><<<G(c->grid_shadow), kTravBlock, 0, st>>>(p, b); else k_intersect_shadow<false><<<G(c->grid_shadow), kTravBlock, 0, st>>>(p, b); }))) return rc;
-			}
-		}
+		return B2R_OK;
+	}
+	if (!c->packet_primary && (rc = launch(c, KK_GENERATE, profile, [&] { k_generate<<<c->grid_stream, kBlock, 0, st>>>(p); }))) return rc;  // (the packet kernel generates the camera rays itself)
+	const bool mis = !(c->cfg.flags & B2R_FLAG_NO_MIS);
+	for (uint32_t b = 0; b < mb; b++) {
+		if (b == 0 && c->packet_primary) { if ((rc = run(KK_CLOSEST, k.packet, G(c->grid_packet), kTravBlock, b))) return rc; }  // camera rays: one walk per warp
+		else if ((rc = run(KK_CLOSEST, k.closest, G(c->grid_closest), kTravBlock, b))) return rc;
+		if ((rc = run(KK_SHADE, k.shade, G(ggx ? c->grid_shade_ggx : c->grid_shade), kBruteBlock, b))) return rc;
+		if (exact && b + 1 < mb && (rc = run(KK_SHADE, k_stream_rank, c->grid_stream, 256, b))) return rc;
+		if (mis && b + 1 < mb && (rc = run(KK_SHADOW, k.shadow, G(c->grid_shadow), kTravBlock, b))) return rc;
 	}
 	return B2R_OK;
 }
