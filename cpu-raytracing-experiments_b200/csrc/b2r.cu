@@ -281,7 +281,7 @@ KernelSet pick_kernels(const b2r_ctx* c) {
 }
 
 // The max_bounces rounds of one batch — or of one lane's half of it — on stream st; p carries that batch's queues, counters and descriptor.
-int enqueue_rounds(b2r_ctx* c, const Params& p_in, cudaStream_t st, bool profile, float grid_frac = 1.0f) {
+int enqueue_rounds(b2r_ctx* c, const Params& p_in, cudaStream_t st, bool profile, float grid_frac = 1.0f, uint32_t lanes = 1) {
 	// (measurement tap, B2R_LANE_GRID: the lanes of a twin batch may be given a fraction of the resident-CTA grid each, so that the two lanes'
 	// kernels sit on every SM side by side instead of taking turns)
 	auto G = [&](int g) { const int per_sm = g / c->sm_count; int k = static_cast<int>(per_sm * grid_frac + 0.5f); if (k < 1) k = 1; return k * c->sm_count; };
@@ -295,6 +295,7 @@ int enqueue_rounds(b2r_ctx* c, const Params& p_in, cudaStream_t st, bool profile
 	if (!c->use_bvh) {
 		const bool finish = !exact && p.frame.finish_below != 0u && p.scene.n_prims <= static_cast<uint32_t>(kBruteTile);
 		if (!finish) p.frame.finish_below = 0u;  // the hand-over threshold only reaches the kernels when k_brute_finish is launched too
+		else if (lanes > 1u) p.frame.finish_below /= lanes;  // the threshold is a batch's; a lane sees 1 / lanes of its paths (C2, two lanes: 13.15 -> 12.80 ms per frame)
 		for (uint32_t b = 0; b < mb; b++) {
 			// k_brute_finish takes the remaining paths over once few enough are left (a no-op launch otherwise)
 			if (finish && b >= p.frame.finish_first && b + 1 < mb && (rc = run(KK_BRUTE, k.brute_finish, k.g_brute_finish, kBruteBlock, b))) return rc;
@@ -353,7 +354,7 @@ int enqueue_trace(b2r_ctx* c, uint32_t sidx, uint32_t lanes) {
 	if (lanes <= 1u) { Params p = lane_params(c, 0, 1, sidx); p.batch = c->d_batch + sidx * (1u + kMaxLanes); return enqueue_rounds(c, p, st, false); }  // one lane: the whole-batch descriptor is the lane's
 	CU(cudaEventRecord(S.ev_fork, st));
 	for (uint32_t j = 1; j < lanes; j++) CU(cudaStreamWaitEvent(S.lane_stream[j], S.ev_fork, 0));
-	for (uint32_t j = 0; j < lanes; j++) if ((rc = enqueue_rounds(c, lane_params(c, j, lanes, sidx), j ? S.lane_stream[j] : st, false, c->lane_grid_frac))) return rc;
+	for (uint32_t j = 0; j < lanes; j++) if ((rc = enqueue_rounds(c, lane_params(c, j, lanes, sidx), j ? S.lane_stream[j] : st, false, c->lane_grid_frac, lanes))) return rc;
 	for (uint32_t j = 1; j < lanes; j++) { CU(cudaEventRecord(S.ev_join[j], S.lane_stream[j])); CU(cudaStreamWaitEvent(st, S.ev_join[j], 0)); }
 	return B2R_OK;
 }
@@ -368,7 +369,7 @@ int enqueue_batch(b2r_ctx* c, bool profile, uint32_t lanes) {
 		// fork: lane 0's rounds on the main stream, the others' on their own; join before the fold (which adds in sample order over all lanes)
 		CU(cudaEventRecord(c->ev_fork, st));
 		for (uint32_t j = 1; j < lanes; j++) CU(cudaStreamWaitEvent(c->lane_stream[j], c->ev_fork, 0));
-		for (uint32_t j = 0; j < lanes; j++) if ((rc = enqueue_rounds(c, lane_params(c, j, lanes), j ? c->lane_stream[j] : st, false, c->lane_grid_frac))) return rc;
+		for (uint32_t j = 0; j < lanes; j++) if ((rc = enqueue_rounds(c, lane_params(c, j, lanes), j ? c->lane_stream[j] : st, false, c->lane_grid_frac, lanes))) return rc;
 		for (uint32_t j = 1; j < lanes; j++) { CU(cudaEventRecord(c->ev_join[j], c->lane_stream[j])); CU(cudaStreamWaitEvent(st, c->ev_join[j], 0)); }
 	}
 	return launch(c, KK_ACCUMULATE, profile, [&] { k_accumulate<<<c->grid_stream, kBlock, 0, st>>>(c->params); });
