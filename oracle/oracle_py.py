@@ -19,7 +19,7 @@ def build(force=False):
     need = force or not all(os.path.exists(os.path.join(_HERE, n)) for n in ("liboracle.so", "liboracle_fast.so"))
     if need:
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so", "liboracle_fast.so"], stdout=subprocess.DEVNULL)
-    if os.path.isdir("/root/reference") and (force or not all(os.path.exists(os.path.join(_HERE, "_ref", n)) for n in ("librefrng.so", "librefsampling.so", "librefbvh.so", "librefrenderer.so"))):
+    if os.path.isdir("/root/reference") and (force or not all(os.path.exists(os.path.join(_HERE, "_ref", n)) for n in ("librefrng.so", "librefsampling.so", "librefbvh.so", "librefrenderer.so", "librefrenderer_ggx.so"))):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
 
