@@ -4,7 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c5] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-One STEP = one frame of the workload: ResetAccumulator, Accumulate() for the workload's sample count, Render().
+One STEP = one frame of the workload: ResetAccumulator, Accumulate() for the workload's sample count, Render(). In the device-timed pass
+(`value`) the frame is resolved into the device framebuffer and the next step is enqueued behind it without a host wait (b2r_resolve_device;
+CUDA events bracket the K steps, max over ranks); in the `e2e` pass every frame is uploaded from and copied back to host memory.
 Default workload = the north-star configuration, BASELINE.json configs[2] (C3): random 100k-sphere BVH scene, 1920x1080 (rendered
 1920x1088), 16 spp, median-of-means with 8 buckets, max_bounces 16, light sampling + MIS. `value` is Mrays/s (extension +
 shadow rays actually traced, counted on the device) with the scene resident in HBM; `e2e` is the same through the public API with host
