@@ -76,7 +76,9 @@ typedef struct b2r_config {
 	int32_t  device;             /* CUDA ordinal */
 	uint32_t bucket_first;       /* multi-GPU: this context renders the samples whose bucket b = acc % buckets */
 	uint32_t bucket_stride;      /*            satisfies b % bucket_stride == bucket_first (0/1 => all)   */
-	uint32_t samples_in_flight;  /* samples traced together per wavefront batch (<= 64); 0 = auto (~128M paths, 4..64) */
+	uint32_t samples_in_flight;  /* samples the queue memory holds (<= 64); 0 = auto (~128M paths, 4..64). A wavefront batch traces up to this many together —
+	                              * half of it on the BVH pipeline when the number is even: consecutive batches then alternate between the two halves ("sides")
+	                              * and overlap on the device; inside a batch the samples may be traced as two lanes on two streams. Results never depend on it. */
 } b2r_config;
 
 enum {
