@@ -120,10 +120,21 @@ struct b2r_ctx {
 		cudaStream_t stream = nullptr, lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
 		cudaEvent_t ev_traced = nullptr, ev_folded = nullptr, ev_sync = nullptr, ev_fork = nullptr, ev_join[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
 		bool folded_valid = false; uint64_t epoch = ~0ull;
+		// the side's own copy of the scene arrays (refreshed from the primary ones, device to device, on the side's stream when scene_version has
+		// moved on): tracing never reads the primary arrays, so a scene upload does not have to wait for the batch in flight
+		float4 *prims = nullptr, *mat_albedo = nullptr, *mat_emission = nullptr, *mat_f0 = nullptr, *light_sphere = nullptr, *light_emit = nullptr, *hdri = nullptr;
+		int32_t* prim_mat = nullptr; WideNode* wide = nullptr; uint32_t *parent = nullptr, *leaf_node = nullptr;
+		bool have_copy = false, refreshed_valid = false; uint64_t scene_version = ~0ull; cudaEvent_t ev_refreshed = nullptr;
 		cudaGraphExec_t exec[kMaxLanes + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr}; bool valid[kMaxLanes + 1] = {false, false, false, false, false}; uint64_t launches[kMaxLanes + 1] = {0, 0, 0, 0, 0};
 	} side[2];
 	uint32_t sides = 2, next_side = 0, last_side = 0, spec_side = 0, counts_first = 0;  // counts_first: first counter block of the last batch
-	uint64_t scene_epoch = 0;  // bumped by everything the side streams must not run ahead of (scene copies, refits, counter resets)
+	uint64_t scene_epoch = 0;  // bumped by what the side streams must not run ahead of on the caller's stream (counter resets)
+	// scene writes (upload, refit, origin-box refit, device tree build): on the caller's stream, or — when the scene is traced through the sides —
+	// on the library's upload stream, so that frame N+1's scene copies run while frame N is still tracing from the sides' own copies
+	cudaStream_t up_stream = nullptr, scene_st = nullptr; cudaEvent_t ev_uploaded = nullptr, ev_main_mark = nullptr; bool uploaded_valid = false;
+	uint64_t scene_version = 0;     // bumped by every scene write
+	bool main_reads_scene = false;  // work that reads the primary scene arrays has been enqueued on the caller's stream since the last scene write
+	size_t hdri_texels = 0;         // texels of the current sky (side copies)
 	uint64_t launches = 0;
 	// profiling (B2R_FLAG_NO_GRAPH): events around every launch
 	struct Timed { int kind; cudaEvent_t a, b; };
@@ -322,7 +333,8 @@ int enqueue_rounds(b2r_ctx* c, const Params& p_in, cudaStream_t st, bool profile
 // of the whole batch, which is how k_accumulate (whole-batch descriptor) finds it.
 // (BVH pipeline only: a side holds half of the samples in flight, and the brute-force pipeline — C2: one 64-sample batch per frame — loses more to
 // the smaller batches than the overlap gives back: 13.16 -> 13.09 ms per frame device-resident, but e2e 29.0 -> 28.1 Grays/s)
-bool use_sides(const b2r_ctx* c) { return c->sides == 2u && c->use_bvh && !(c->cfg.flags & (B2R_FLAG_NO_GRAPH | B2R_FLAG_REFERENCE_EXACT)) && c->slots >= 2u && c->slots % 2u == 0u; }
+bool sides_for(const b2r_ctx* c, bool use_bvh) { return c->sides == 2u && use_bvh && !(c->cfg.flags & (B2R_FLAG_NO_GRAPH | B2R_FLAG_REFERENCE_EXACT)) && c->slots >= 2u && c->slots % 2u == 0u; }
+bool use_sides(const b2r_ctx* c) { return sides_for(c, c->use_bvh); }
 uint32_t batch_cap(const b2r_ctx* c) { return use_sides(c) ? c->slots / 2u : c->slots; }   // samples one batch can hold
 uint32_t lane_slots_of(const b2r_ctx* c, uint32_t lanes) { return (batch_cap(c) + lanes - 1u) / lanes; }
 // (side = 0 with sides off: the batch owns all the queue memory)
@@ -336,6 +348,12 @@ Params lane_params(const b2r_ctx* c, uint32_t which, uint32_t lanes, uint32_t si
 	p.cnt.paths += blk * block; p.cnt.shadow += blk * block; p.cnt.work_a += blk * block; p.cnt.work_b += blk * block;
 	p.batch = c->d_batch + side * (1u + kMaxLanes) + 1u + which;
 	p.rad += 3 * off;
+	if (use_sides(c)) {  // a side traces from its own copy of the scene arrays (refresh_side_scene)
+		const b2r_ctx::Side& S = c->side[side]; SceneDev& sc = p.scene;
+		sc.prims = S.prims; sc.prim_mat = S.prim_mat; sc.mat_albedo = S.mat_albedo; sc.mat_emission = S.mat_emission; sc.mat_f0 = S.mat_f0;
+		sc.light_sphere = S.light_sphere; sc.light_emit = S.light_emit; sc.wide = S.wide; sc.parent = S.parent; sc.leaf_node = S.leaf_node;
+		if (sc.hdri) sc.hdri = S.hdri;
+	}
 	return p;
 }
 // what k_accumulate sees of a side: that side's whole-batch descriptor and its part of RAD
@@ -375,6 +393,7 @@ int enqueue_batch(b2r_ctx* c, bool profile, uint32_t lanes) {
 	return launch(c, KK_ACCUMULATE, profile, [&] { k_accumulate<<<c->grid_stream, kBlock, 0, st>>>(c->params); });
 }
 
+int refresh_side_scene(b2r_ctx* c, uint32_t sidx);
 // One wavefront batch of args.n samples (args.acc[0..n) in sample order). Two or more samples are traced as lanes: run_batch moves every
 // lane's samples to the slots that lane owns and leaves args in that layout (the caller may keep it: samples traced ahead).
 int run_batch(b2r_ctx* c, BatchArgs& args) {
@@ -415,6 +434,7 @@ int run_batch(b2r_ctx* c, BatchArgs& args) {
 		// RAD before the previous batch it traced has been folded
 		if (S.epoch != c->scene_epoch) { CU(cudaEventRecord(S.ev_sync, c->stream)); CU(cudaStreamWaitEvent(S.stream, S.ev_sync, 0)); S.epoch = c->scene_epoch; }
 		if (S.folded_valid) CU(cudaStreamWaitEvent(S.stream, S.ev_folded, 0));
+		{ const int rc = refresh_side_scene(c, sidx); if (rc) return rc; }
 		k_set_batch<<<1, kMaxSlots, 0, S.stream>>>(c->d_batch + sidx * (1u + kMaxLanes), args);
 		CU(cudaGetLastError());
 		if (!S.valid[lanes]) {
@@ -443,7 +463,7 @@ int run_batch(b2r_ctx* c, BatchArgs& args) {
 		c->last_side = sidx; c->counts_first = sidx * kMaxLanes;
 		return B2R_OK;
 	}
-	c->counts_first = 0;
+	c->counts_first = 0; c->main_reads_scene = true;  // (this batch traces from the primary scene arrays, on the caller's stream)
 	k_set_batch<<<1, kMaxSlots, 0, c->stream>>>(c->d_batch, args);
 	CU(cudaGetLastError());
 	if (no_graph) return enqueue_batch(c, true, 1);
@@ -493,14 +513,72 @@ bool owns_sample(const b2r_ctx* c, uint32_t acc) {
 }
 
 
+// Scene writes. begin: picks the stream (see b2r_ctx::up_stream) and orders it behind whatever still reads the primary arrays — a side's
+// device-to-device refresh, or work on the caller's stream. end: the caller's stream is ordered behind the write (nothing it enqueued
+// earlier waits), and the sides learn that their copies are stale.
+void free_side_scenes(b2r_ctx* c) {
+	for (auto& S : c->side) {
+		dev_free(&S.prims); dev_free(&S.mat_albedo); dev_free(&S.mat_emission); dev_free(&S.mat_f0); dev_free(&S.light_sphere); dev_free(&S.light_emit); dev_free(&S.hdri);
+		dev_free(&S.prim_mat); dev_free(&S.wide); dev_free(&S.parent); dev_free(&S.leaf_node);
+		S.have_copy = false; S.scene_version = ~0ull;
+		for (uint32_t l = 0; l <= kMaxLanes; l++) S.valid[l] = false;  // the captured graphs hold the old addresses
+	}
+}
+int begin_scene_write(b2r_ctx* c, bool traced_through_sides) {
+	cudaStream_t st = c->stream;
+	if (traced_through_sides) {
+		if (!c->up_stream) { CU(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&c->ev_main_mark, cudaEventDisableTiming)); }
+		st = c->up_stream;
+		if (c->main_reads_scene) { CU(cudaEventRecord(c->ev_main_mark, c->stream)); CU(cudaStreamWaitEvent(st, c->ev_main_mark, 0)); c->main_reads_scene = false; }
+	}
+	for (auto& S : c->side) if (S.refreshed_valid) CU(cudaStreamWaitEvent(st, S.ev_refreshed, 0));
+	c->scene_st = st;
+	return B2R_OK;
+}
+int end_scene_write(b2r_ctx* c) {
+	if (!c->ev_uploaded) CU(cudaEventCreateWithFlags(&c->ev_uploaded, cudaEventDisableTiming));
+	CU(cudaEventRecord(c->ev_uploaded, c->scene_st)); c->uploaded_valid = true;
+	if (c->scene_st != c->stream) CU(cudaStreamWaitEvent(c->stream, c->ev_uploaded, 0));
+	else c->main_reads_scene = true;  // (written on the caller's stream: the next write on the upload stream has to get behind it)
+	c->scene_version++;
+	c->scene_st = c->stream;
+	return B2R_OK;
+}
+// A side's copy of the scene, brought up to date on the side's own stream before it traces.
+int refresh_side_scene(b2r_ctx* c, uint32_t sidx) {
+	b2r_ctx::Side& S = c->side[sidx];
+	if (S.have_copy && S.scene_version == c->scene_version) return B2R_OK;
+	const SceneDev& sc = c->params.scene;
+	if (!S.have_copy) {
+		int rc;
+		if ((rc = dev_alloc(&S.prims, c->cap_prims)) || (rc = dev_alloc(&S.prim_mat, c->cap_prim_mat)) || (rc = dev_alloc(&S.mat_albedo, c->cap_mat_albedo)) ||
+		    (rc = dev_alloc(&S.mat_emission, c->cap_mat_emission)) || (rc = dev_alloc(&S.mat_f0, c->cap_mat_f0)) || (rc = dev_alloc(&S.light_sphere, c->cap_light_sphere)) ||
+		    (rc = dev_alloc(&S.light_emit, c->cap_light_emit)) || (rc = dev_alloc(&S.wide, c->cap_wide)) || (rc = dev_alloc(&S.parent, c->cap_parent)) ||
+		    (rc = dev_alloc(&S.leaf_node, c->cap_leaf_node)) || (rc = dev_alloc(&S.hdri, c->cap_hdri))) return rc;
+		if (!S.ev_refreshed) CU(cudaEventCreateWithFlags(&S.ev_refreshed, cudaEventDisableTiming));
+		S.have_copy = true;
+		for (uint32_t l = 0; l <= kMaxLanes; l++) S.valid[l] = false;
+	}
+	if (c->uploaded_valid) CU(cudaStreamWaitEvent(S.stream, c->ev_uploaded, 0));
+	auto copy = [&](void* dst, const void* src, size_t bytes) -> cudaError_t { return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, S.stream) : cudaSuccess; };
+	const size_t n_l = sc.n_lights ? sc.n_lights : 1u;
+	CU(copy(S.prims, c->d_prims, sc.n_prims * sizeof(float4))); CU(copy(S.prim_mat, c->d_prim_mat, sc.n_prims * sizeof(int32_t)));
+	CU(copy(S.mat_albedo, c->d_mat_albedo, sc.n_mat * sizeof(float4))); CU(copy(S.mat_emission, c->d_mat_emission, sc.n_mat * sizeof(float4))); CU(copy(S.mat_f0, c->d_mat_f0, sc.n_mat * sizeof(float4)));
+	CU(copy(S.light_sphere, c->d_light_sphere, n_l * sizeof(float4))); CU(copy(S.light_emit, c->d_light_emit, n_l * sizeof(float4)));
+	CU(copy(S.wide, c->d_wide, static_cast<size_t>(c->n_wide) * sizeof(WideNode))); CU(copy(S.parent, c->d_parent, static_cast<size_t>(c->n_wide) * sizeof(uint32_t)));
+	CU(copy(S.leaf_node, c->d_leaf_node, sc.n_prims * sizeof(uint32_t)));
+	if (sc.hdri) CU(copy(S.hdri, c->d_hdri, c->hdri_texels * sizeof(float4)));
+	CU(cudaEventRecord(S.ev_refreshed, S.stream)); S.refreshed_valid = true; S.scene_version = c->scene_version;
+	return B2R_OK;
+}
+
 // Boxes of the device tree for the current origin box: one k_refit_level launch per BFS level, deepest first (stream order is the
 // dependency). remap (device, may be null) re-links leaves into a new BVH order.
 int launch_refit_levels(b2r_ctx* c, const uint32_t* d_remap) {
-	c->scene_epoch++;
 	const std::vector<uint32_t>& lf = c->wide_host.level_first;
 	for (size_t l = lf.size() - 1; l-- > 0;) {
 		const uint32_t first = lf[l], count = lf[l + 1] - lf[l];
-		k_refit_level<<<(count * 4u + kBlock - 1u) / kBlock, kBlock, 0, c->stream>>>(reinterpret_cast<float4*>(c->d_wide), c->d_prims, d_remap, c->obox, first, count);
+		k_refit_level<<<(count * 4u + kBlock - 1u) / kBlock, kBlock, 0, c->scene_st>>>(reinterpret_cast<float4*>(c->d_wide), c->d_prims, d_remap, c->obox, first, count);
 		c->launches++;
 	}
 	CU(cudaGetLastError());
@@ -508,8 +586,7 @@ int launch_refit_levels(b2r_ctx* c, const uint32_t* d_remap) {
 }
 // parent[] / leaf_node[] of the device tree (where k_intersect_shadow starts and how it climbs), read off the tree itself
 int launch_link_tables(b2r_ctx* c) {
-	c->scene_epoch++;
-	k_link_tables<<<(c->n_wide * 4u + kBlock - 1u) / kBlock, kBlock, 0, c->stream>>>(reinterpret_cast<const float4*>(c->d_wide), c->n_wide, c->d_parent, c->d_leaf_node);
+	k_link_tables<<<(c->n_wide * 4u + kBlock - 1u) / kBlock, kBlock, 0, c->scene_st>>>(reinterpret_cast<const float4*>(c->d_wide), c->n_wide, c->d_parent, c->d_leaf_node);
 	CU(cudaGetLastError()); c->launches++;
 	return B2R_OK;
 }
@@ -523,7 +600,11 @@ int ensure_origin_box(b2r_ctx* c, const float* points, uint32_t n_points) {
 	if (c->obox_valid) { extra.insert(extra.end(), c->obox.lo, c->obox.lo + 3); extra.insert(extra.end(), c->obox.hi, c->obox.hi + 3); }  // never shrinks between uploads
 	c->obox = origin_box_rule(c->sph_lo, c->sph_hi, extra.data(), static_cast<uint32_t>(extra.size() / 3)); c->obox_valid = true;
 	if (c->have_wide && !c->gpu_tree) wide_fill_boxes(c->wide_host, c->wide_host.prims.data(), c->obox);  // the host copy (and its reference cost) follows: same routine, same result
-	if (c->have_scene && c->have_wide) return launch_refit_levels(c, nullptr);
+	if (c->have_scene && c->have_wide) {
+		int rc = begin_scene_write(c, use_sides(c)); if (rc) return rc;
+		if ((rc = launch_refit_levels(c, nullptr))) return rc;
+		return end_scene_write(c);
+	}
 	return B2R_OK;
 }
 
@@ -582,7 +663,11 @@ void b2r_destroy(b2r_ctx* c) {
 	if (c->h_stage) cudaFreeHost(c->h_stage);
 	if (c->ev_stage) cudaEventDestroy(c->ev_stage);
 	if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); cudaEventDestroy(c->ev_resolved); cudaEventDestroy(c->ev_copied); }
+	free_side_scenes(c);
+	if (c->up_stream) { cudaStreamSynchronize(c->up_stream); cudaStreamDestroy(c->up_stream); cudaEventDestroy(c->ev_main_mark); }
+	if (c->ev_uploaded) cudaEventDestroy(c->ev_uploaded);
 	for (auto& S : c->side) {
+		if (S.ev_refreshed) cudaEventDestroy(S.ev_refreshed);
 		for (uint32_t j = 1; j < kMaxLanes; j++) if (S.lane_stream[j]) { cudaStreamDestroy(S.lane_stream[j]); cudaEventDestroy(S.ev_join[j]); }
 		if (S.stream) { cudaStreamDestroy(S.stream); cudaEventDestroy(S.ev_traced); cudaEventDestroy(S.ev_folded); cudaEventDestroy(S.ev_sync); cudaEventDestroy(S.ev_fork); }
 	}
@@ -665,11 +750,10 @@ int stage_upload(b2r_ctx* c, const UploadPart* parts, size_t n_parts) {
 	size_t off = 0;
 	for (size_t i = 0; i < n_parts; i++) {
 		const UploadPart& q = parts[i];
-		if (q.bytes) { std::memcpy(c->h_stage + off, q.src, q.bytes); CU(cudaMemcpyAsync(q.dst, c->h_stage + off, q.bytes, cudaMemcpyHostToDevice, c->stream)); }
+		if (q.bytes) { std::memcpy(c->h_stage + off, q.src, q.bytes); CU(cudaMemcpyAsync(q.dst, c->h_stage + off, q.bytes, cudaMemcpyHostToDevice, c->scene_st)); }
 		off += (q.bytes + 255) & ~static_cast<size_t>(255);
 	}
-	CU(cudaEventRecord(c->ev_stage, c->stream)); c->stage_busy = true;
-	c->scene_epoch++;  // the side streams may not trace the next batch before these copies have landed
+	CU(cudaEventRecord(c->ev_stage, c->scene_st)); c->stage_busy = true;
 	return B2R_OK;
 }
 }  // namespace
@@ -743,7 +827,11 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 	const bool grow = h_prims.size() > c->cap_prims || h_pm.size() > c->cap_prim_mat || h_alb.size() > c->cap_mat_albedo || h_em.size() > c->cap_mat_emission || h_f0.size() > c->cap_mat_f0 ||
 	                  h_ls.size() > c->cap_light_sphere || h_le.size() > c->cap_light_emit || c->n_wide > c->cap_wide || c->n_wide > c->cap_parent || n_prims > c->cap_leaf_node ||
 	                  (has_ambient && static_cast<size_t>(hdri_w) * hdri_h > c->cap_hdri);
-	if (grow) CU(sync_main(c));  // device arrays in use are about to be replaced (first upload, or a larger scene)
+	if (grow) {  // device arrays in use are about to be replaced (first upload, or a larger scene): nothing may be running, and the sides' copies go too
+		CU(sync_main(c)); if (c->up_stream) CU(cudaStreamSynchronize(c->up_stream));
+		for (auto& S : c->side) if (S.stream) CU(cudaStreamSynchronize(S.stream));
+		free_side_scenes(c);
+	}
 	if ((rc = dev_reserve(&c->d_prims, &c->cap_prims, h_prims.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_prim_mat, &c->cap_prim_mat, h_pm.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_mat_albedo, &c->cap_mat_albedo, h_alb.size()))) return rc;
@@ -762,29 +850,33 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 		{c->d_light_sphere, h_ls.data(), h_ls.size() * sizeof(float4)}, {c->d_light_emit, h_le.data(), h_le.size() * sizeof(float4)},
 		{c->d_wide, c->wide_host.nodes.data(), gpu_tree ? 0 : c->wide_host.nodes.size() * sizeof(WideNode)}, {c->d_hdri, hdri_rgba, texels * sizeof(float4)},
 	};
+	const bool bvh_next = (c->cfg.flags & B2R_FLAG_FORCE_BVH) ? true : (c->cfg.flags & B2R_FLAG_FORCE_BRUTE) ? false : n_prims > 32;
+	if ((rc = begin_scene_write(c, sides_for(c, bvh_next)))) return rc;
 	if ((rc = stage_upload(c, parts, sizeof parts / sizeof parts[0]))) return rc;
+	c->hdri_texels = texels;
 	c->wide_refit = false; c->cur_geom_of_prim.clear(); drop_speculation(c);
 	if (gpu_tree) {  // Morton keys -> stable radix sort -> implicit 4-ary links -> boxes, all on the stream behind the copies above
 		if (n_prims > c->cap_mkey) { for (int k = 0; k < 2; k++) { size_t cap = 0; if ((rc = dev_reserve(&c->d_mkey[k], &cap, n_prims)) || (cap = 0, rc = dev_reserve(&c->d_midx[k], &cap, n_prims))) return rc; } c->cap_mkey = n_prims; }
 		float scale[3]; morton_scale(c->sph_lo, c->sph_hi, scale);
-		k_morton_keys<<<(n_prims + kBlock - 1u) / kBlock, kBlock, 0, c->stream>>>(c->d_prims, n_prims, c->sph_lo[0], c->sph_lo[1], c->sph_lo[2], scale[0], scale[1], scale[2], c->d_mkey[0], c->d_midx[0]);
+		k_morton_keys<<<(n_prims + kBlock - 1u) / kBlock, kBlock, 0, c->scene_st>>>(c->d_prims, n_prims, c->sph_lo[0], c->sph_lo[1], c->sph_lo[2], scale[0], scale[1], scale[2], c->d_mkey[0], c->d_midx[0]);
 		size_t tmp = 0;
-		CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_mkey[0], c->d_mkey[1], c->d_midx[0], c->d_midx[1], static_cast<int>(n_prims), 0, 30, c->stream));
+		CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_mkey[0], c->d_mkey[1], c->d_midx[0], c->d_midx[1], static_cast<int>(n_prims), 0, 30, c->scene_st));
 		if ((rc = dev_reserve(&c->d_sort_tmp, &c->cap_sort_tmp, tmp))) return rc;
-		CU(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, tmp, c->d_mkey[0], c->d_mkey[1], c->d_midx[0], c->d_midx[1], static_cast<int>(n_prims), 0, 30, c->stream));
+		CU(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, tmp, c->d_mkey[0], c->d_mkey[1], c->d_midx[0], c->d_midx[1], static_cast<int>(n_prims), 0, 30, c->scene_st));
 		PackedLevels lv{}; lv.levels = c->wide_host.depth;
 		if (lv.levels + 1u > sizeof lv.first / sizeof lv.first[0]) return fail(B2R_ERR_BVH, "packed tree deeper than 23 levels");
 		for (uint32_t l = 0; l <= lv.levels; l++) lv.first[l] = c->wide_host.level_first[l];
-		k_packed_links<<<(c->n_wide * 4u + kBlock - 1u) / kBlock, kBlock, 0, c->stream>>>(reinterpret_cast<float4*>(c->d_wide), lv, n_prims, c->d_midx[1]);
+		k_packed_links<<<(c->n_wide * 4u + kBlock - 1u) / kBlock, kBlock, 0, c->scene_st>>>(reinterpret_cast<float4*>(c->d_wide), lv, n_prims, c->d_midx[1]);
 		CU(cudaGetLastError()); c->launches += 3;
 		if ((rc = launch_refit_levels(c, nullptr))) return rc;
 		if (!c->d_cost_base) { size_t cap = 0; if ((rc = dev_reserve(&c->d_cost_base, &cap, 1))) return rc; }
-		CU(cudaMemsetAsync(c->d_cost_base, 0, sizeof(double), c->stream));
-		k_tree_cost<<<c->sm_count * 4, kBlock, 0, c->stream>>>(reinterpret_cast<const float4*>(c->d_wide), c->n_wide, c->d_cost_base);  // what a later refit's quality ratio is measured against
+		CU(cudaMemsetAsync(c->d_cost_base, 0, sizeof(double), c->scene_st));
+		k_tree_cost<<<c->sm_count * 4, kBlock, 0, c->scene_st>>>(reinterpret_cast<const float4*>(c->d_wide), c->n_wide, c->d_cost_base);  // what a later refit's quality ratio is measured against
 		c->launches++;
 		c->wide_refit = true;  // the device holds the only copy of this tree
 	}
 	if ((rc = launch_link_tables(c))) return rc;
+	if ((rc = end_scene_write(c))) return rc;
 	const SceneDev before = c->params.scene; const bool bvh_before = c->use_bvh;
 	SceneDev& s = c->params.scene;
 	s.prims = c->d_prims; s.prim_mat = c->d_prim_mat; s.mat_albedo = c->d_mat_albedo; s.mat_emission = c->d_mat_emission; s.mat_f0 = c->d_mat_f0;
@@ -833,7 +925,11 @@ int b2r_refit_scene(b2r_ctx* c, const b2r_sphere* prims, uint32_t n_prims, const
 	if ((rc = dev_reserve(&c->d_remap, &c->cap_remap, remap.size()))) return rc;
 	const bool grow = ps.mat_albedo.size() > c->cap_mat_albedo || ps.mat_emission.size() > c->cap_mat_emission || ps.mat_f0.size() > c->cap_mat_f0 ||
 	                  ps.light_sphere.size() > c->cap_light_sphere || ps.light_emit.size() > c->cap_light_emit;
-	if (grow) CU(sync_main(c));  // more materials or lights than before: those (small) arrays are replaced
+	if (grow) {  // more materials or lights than before: those (small) arrays are replaced
+		CU(sync_main(c)); if (c->up_stream) CU(cudaStreamSynchronize(c->up_stream));
+		for (auto& S : c->side) if (S.stream) CU(cudaStreamSynchronize(S.stream));
+		free_side_scenes(c);
+	}
 	if ((rc = dev_reserve(&c->d_mat_albedo, &c->cap_mat_albedo, ps.mat_albedo.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_mat_emission, &c->cap_mat_emission, ps.mat_emission.size()))) return rc;
 	if ((rc = dev_reserve(&c->d_mat_f0, &c->cap_mat_f0, ps.mat_f0.size()))) return rc;
@@ -846,6 +942,7 @@ int b2r_refit_scene(b2r_ctx* c, const b2r_sphere* prims, uint32_t n_prims, const
 		{c->d_light_sphere, ps.light_sphere.data(), ps.light_sphere.size() * sizeof(float4)}, {c->d_light_emit, ps.light_emit.data(), ps.light_emit.size() * sizeof(float4)},
 		{c->d_remap, remap.data(), remap.size() * sizeof(uint32_t)},
 	};
+	if ((rc = begin_scene_write(c, use_sides(c)))) return rc;
 	if ((rc = stage_upload(c, parts, sizeof parts / sizeof parts[0]))) return rc;
 	if (!same_order) c->cur_geom_of_prim.swap(new_geom);
 	// boxes bottom-up on the device, for an origin box that holds the moved spheres
@@ -860,6 +957,7 @@ int b2r_refit_scene(b2r_ctx* c, const b2r_sphere* prims, uint32_t n_prims, const
 	}
 	if ((rc = launch_refit_levels(c, same_order ? nullptr : c->d_remap))) return rc;
 	if (!same_order && (rc = launch_link_tables(c))) return rc;  // leaves were re-linked into the new BVH order
+	if ((rc = end_scene_write(c))) return rc;
 	c->wide_refit = true; drop_speculation(c);
 	const SceneDev before = c->params.scene;
 	SceneDev& s = c->params.scene;
@@ -867,6 +965,7 @@ int b2r_refit_scene(b2r_ctx* c, const b2r_sphere* prims, uint32_t n_prims, const
 	s.n_mat = n_mat; s.n_lights = n_lights; s.light_sel_pdf = n_lights ? 1.0f / static_cast<float>(n_lights) : 0.0f;  // Renderer.hpp:78
 	if (std::memcmp(&before, &s, sizeof s) != 0) drop_graph(c);
 	if (quality_out) {  // optional: costs one launch and a stream synchronisation
+		c->main_reads_scene = true;
 		CU(cudaMemsetAsync(c->d_cost, 0, sizeof(double), c->stream));
 		k_tree_cost<<<c->sm_count * 4, kBlock, 0, c->stream>>>(reinterpret_cast<const float4*>(c->d_wide), c->n_wide, c->d_cost);
 		c->launches++;
@@ -1292,6 +1391,7 @@ static int trace_common(b2r_ctx* c, const float* rays, const float* tfar_in, uin
 		for (uint32_t i = 0; i < n; i++) for (int k = 0; k < 3; k++) { const float v = rays[6 * static_cast<size_t>(i) + k]; if (v == v && fabsf(v) <= FLT_MAX) { pts[k] = fminf(pts[k], v); pts[3 + k] = fmaxf(pts[3 + k], v); } }
 		if (pts[0] <= pts[3] && (rc = ensure_origin_box(c, pts, 2))) return rc;
 	}
+	c->main_reads_scene = true;  // (k_tap_trace reads the primary scene arrays on the caller's stream)
 	// one grow-only device block per context, carved into the five arrays (focus picking calls this per mouse click, Application.cpp:282-298)
 	const size_t n6 = (static_cast<size_t>(n) * 6 * sizeof(float) + 255) & ~static_cast<size_t>(255), n4 = (static_cast<size_t>(n) * 4 + 255) & ~static_cast<size_t>(255), n1 = (static_cast<size_t>(n) + 255) & ~static_cast<size_t>(255);
 	if ((rc = dev_reserve(&c->d_trace, &c->cap_trace, n6 + 3 * n4 + n1))) return rc;
@@ -1330,6 +1430,7 @@ int b2r_read_wide_nodes(b2r_ctx* c, void* out_host, uint32_t* n_wide_nodes, uint
 	if (max_stack) *max_stack = c->wide_host.max_stack;
 	if (out_host && c->wide_refit) {  // after b2r_refit_scene the device holds the current boxes
 		int rc = ensure_device(c); if (rc) return rc;
+		c->main_reads_scene = true;
 		CU(cudaMemcpyAsync(out_host, c->d_wide, static_cast<size_t>(c->n_wide) * sizeof(WideNode), cudaMemcpyDeviceToHost, c->stream));
 		CU(sync_main(c));
 	} else if (out_host) std::memcpy(out_host, c->wide_host.nodes.data(), c->wide_host.nodes.size() * sizeof(WideNode));
