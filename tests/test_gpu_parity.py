@@ -695,6 +695,35 @@ def test_frames_enqueued_back_to_back_equal_frames_waited_for(n, flags):
     a.close(); b.close()
 
 
+def test_a_scene_upload_every_frame_does_not_wait_for_the_frame_in_flight():
+    """The e2e pattern, stressed: a DIFFERENT scene is uploaded (or refitted) before every frame and nothing waits for the device. Scene writes
+    go to the library's upload stream while the previous frame still traces from its side's own copy of the scene arrays; every frame must
+    still see exactly the scene uploaded before it."""
+    w, h, mb, K = 192, 128, 6, 2
+    sc_a = scenes.random_scene(2500, light_every=40); rs = np.random.RandomState(11)
+    sc_b = scenes.Scene(sc_a); sc_b["geometry"] = _moved_geometry(sc_a["geometry"], rs, jitter=0.4)
+    sc_c = scenes.random_scene(1800, light_every=25, seed=0x1234567)           # another sphere count: other array sizes, other tree
+    geo_d = _moved_geometry(sc_a["geometry"], rs, jitter=0.2)                  # reached by a refit of sc_a
+    plan = ["a", "b", "a", "c", "a", "refit_d", "b", "c"]
+    def drive(r, wait):
+        out = []
+        for step in plan:
+            if step == "refit_d": r.RefitScene(geo_d, want_quality=False)
+            else: r.SetScene(b2r.PreparedScene({"a": sc_a, "b": sc_b, "c": sc_c}[step], w, h))
+            r.ResetAccumulator(); r.Accumulate(2 * K)
+            if wait: assert r.Render(); out.append(r.buckets_host().copy())
+            else: assert r.RenderDevice()
+        return out
+    a = b2r.Renderer(sc_a, w, h, max_bounces=mb, buckets=K); want = drive(a, True)
+    for upto in (len(plan), 5, 6):   # drain after the whole plan, and after prefixes that end on other sides / other kinds of write
+        b = b2r.Renderer(sc_a, w, h, max_bounces=mb, buckets=K)
+        full = plan[:]; del plan[upto:]
+        drive(b, False); b.sync()
+        assert b.buckets_host().tobytes() == want[upto - 1].tobytes(), upto
+        plan[:] = full; b.close()
+    a.close()
+
+
 # ------------------------------------------------------------------------------------------------ scene edit: GPU refit
 def _moved_geometry(geo, rs, jitter=0.5, far=0):
     """Every sphere moves by up to `jitter` radii and changes radius by up to 20 %; `far` of them jump anywhere in the scene."""
