@@ -483,7 +483,24 @@ B2R_HD uint32_t morton_spread10(uint32_t v) { v &= 1023u; v = (v | (v << 16)) & 
 B2R_HD uint32_t morton_key(float cx, float cy, float cz, const float lo[3], const float scale[3]) {
 	const float fx = (cx - lo[0]) * scale[0], fy = (cy - lo[1]) * scale[1], fz = (cz - lo[2]) * scale[2];
 	const uint32_t qx = static_cast<uint32_t>(sel_min(sel_max(fx, 0.0f), 1023.0f)), qy = static_cast<uint32_t>(sel_min(sel_max(fy, 0.0f), 1023.0f)), qz = static_cast<uint32_t>(sel_min(sel_max(fz, 0.0f), 1023.0f));
+#if defined(B2R_MORTON_ORDER)
 	return (morton_spread10(qx) << 2) | (morton_spread10(qy) << 1) | morton_spread10(qz);
+#else
+	// Hilbert index of the cell (Skilling's transpose form, 10 bits per axis): unlike a Z curve, a run of consecutive cells is always a
+	// connected, compact set, and the packed tree's nodes ARE runs of consecutive keys
+	uint32_t x0 = qx, x1 = qy, x2 = qz;
+	for (uint32_t q = 512u; q > 1u; q >>= 1) {
+		const uint32_t m = q - 1u; uint32_t t;
+		if (x0 & q) x0 ^= m;
+		if (x1 & q) x0 ^= m; else { t = (x0 ^ x1) & m; x0 ^= t; x1 ^= t; }
+		if (x2 & q) x0 ^= m; else { t = (x0 ^ x2) & m; x0 ^= t; x2 ^= t; }
+	}
+	x1 ^= x0; x2 ^= x1;
+	uint32_t t = 0u;
+	for (uint32_t q = 512u; q > 1u; q >>= 1) if (x2 & q) t ^= q - 1u;
+	x0 ^= t; x1 ^= t; x2 ^= t;
+	return (morton_spread10(x0) << 2) | (morton_spread10(x1) << 1) | morton_spread10(x2);
+#endif
 }
 B2R_HD void morton_scale(const float lo[3], const float hi[3], float scale[3]) { for (int k = 0; k < 3; k++) { const float e = hi[k] - lo[k]; scale[k] = e > 0.0f ? 1024.0f / e : 0.0f; } }
 B2R_HD float slot_half_area(const float4 /*a*/, const float4 b) { return 4.0f * (b.x * b.y + b.y * b.w + b.w * b.x); }

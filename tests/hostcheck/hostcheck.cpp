@@ -154,6 +154,12 @@ int hc_packed_tree(const b2r_sphere* prims, uint32_t n, const float* box6, void*
 	if (out) std::memcpy(out, w.nodes.data(), w.nodes.size() * sizeof(WideNode));
 	return 0;
 }
+// the sort key of build_packed_tree / k_morton_keys (b2r_shade.h: morton_key) for sphere centres inside [lo, hi]
+int hc_curve_keys(const b2r_sphere* prims, uint32_t n, const float lo[3], const float hi[3], uint32_t* keys_out) {
+	std::vector<uint32_t> keys; morton_keys(prims, n, lo, hi, keys);
+	std::memcpy(keys_out, keys.data(), n * sizeof(uint32_t));
+	return 0;
+}
 // validate_reference_bvh tap (what b2r_upload_scene checks before it flattens a caller's node array)
 int hc_validate(const b2r_bvh_node* nodes, uint32_t n_nodes, uint32_t n_prims) { return validate_reference_bvh(nodes, n_nodes, n_prims) ? 1 : 0; }
 // match_prims_to_geometry tap: geom_of_prim[n]; returns 1 when prims is a permutation of geometry

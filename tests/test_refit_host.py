@@ -237,3 +237,22 @@ def test_packed_morton_tree_host_twin(hostcheck, n):
     bt = np.zeros(m, np.float32); bp = np.zeros(m, np.int32)
     hostcheck.hc_closest_brute(vp(prims), n, vp(rays), m, vp(bt), vp(bp))
     assert np.array_equal(bp, pr)
+
+
+def test_packed_tree_sort_key_is_a_hilbert_curve(hostcheck):
+    """The key build_packed_tree / k_morton_keys sort by (b2r_shade.h: morton_key) is the Hilbert index of the sphere centre's cell on a
+    1024^3 grid: a bijection on aligned blocks whose consecutive cells are face neighbours — so a node of the packed tree, a run of
+    consecutive keys, is a connected set of cells (a Z curve's runs are not: 58 -> 28 node visits per ray on the 100k-sphere scene)."""
+    def keys_of(cells):
+        p = np.zeros(len(cells), scenes.SPHERE_DTYPE); p["position"] = cells.astype(np.float32) + 0.5
+        lo = np.zeros(3, np.float32); hi = np.full(3, 1024, np.float32); k = np.zeros(len(cells), np.uint32)
+        hostcheck.hc_curve_keys(vp(p), len(cells), vp(lo), vp(hi), vp(k)); return k
+    g = np.stack(np.meshgrid(*[np.arange(8)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    k = keys_of(g << 7) >> 21                                               # the 8^3 coarse cells: the leading 9 key bits
+    assert sorted(k.tolist()) == list(range(512))
+    assert (np.abs(np.diff(g[np.argsort(k)], axis=0)).sum(1) == 1).all()
+    for off in ([0, 0, 0], [512, 96, 992], [224, 608, 960]):                # whole 32^3 blocks anywhere on the grid
+        g = np.stack(np.meshgrid(*[np.arange(32)] * 3, indexing="ij"), -1).reshape(-1, 3) + np.array(off)
+        k = keys_of(g)
+        assert len(set(k.tolist())) == 32 ** 3 and int(k.max()) - int(k.min()) == 32 ** 3 - 1
+        assert (np.abs(np.diff(g[np.argsort(k)], axis=0)).sum(1) == 1).all()
