@@ -425,6 +425,74 @@ void build_packed_tree(const b2r_sphere* prims, uint32_t n, WideBvh& out, const 
 	out.tn_bits = std::min(32u - node_bits, 29u);
 }
 
+bool build_sweep_tree(const b2r_sphere* prims, uint32_t n, WideBvh& out, const OriginBox* ob_in) {
+	if (n < 2u) { build_packed_tree(prims, n, out, ob_in); return true; }
+	out.nodes.clear(); out.prims.clear(); out.geom_of_prim.clear(); out.cost = 0.0;
+	sphere_bounds(prims, n, out.sphere_lo, out.sphere_hi);
+	const OriginBox ob = ob_in ? *ob_in : origin_box_rule(out.sphere_lo, out.sphere_hi, nullptr, 0);
+	std::vector<uint32_t> keys; morton_keys(prims, n, out.sphere_lo, out.sphere_hi, keys);
+	std::vector<uint32_t> order(n); std::iota(order.begin(), order.end(), 0u);
+	std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+	std::vector<SweepItem> box(n);
+	for (uint32_t p = 0; p < n; p++) { const b2r_sphere& sp = prims[order[p]]; sweep_sphere_box(make_float4(sp.position[0], sp.position[1], sp.position[2], sp.radius_sq), &box[p]); }
+	// what the device works out for every run with two segmented scans and an atomic minimum, here one run at a time: the cheapest cut
+	// and the area of the run's box, both filed under the run's first position
+	std::vector<unsigned long long> cut_of(n, ~0ull); std::vector<float> area_of(n, 0.0f); std::vector<SweepItem> suffix;
+	auto survey = [&](uint32_t a, uint32_t b) {
+		if (b - a < 2u) return;
+		suffix.resize(b - a);
+		SweepItem acc = box[b - 1]; acc.flag = 0u; suffix[b - 1 - a] = acc;
+		for (uint32_t p = b - 1; p-- > a;) { SweepItem it = box[p]; it.flag = 0u; acc = sweep_join(it, acc); suffix[p - a] = acc; }
+		unsigned long long best = ~0ull;
+		acc = box[a]; acc.flag = 0u;
+		for (uint32_t p = a + 1; p < b; p++) {
+			const unsigned long long key = sweep_key(sweep_area(acc), p - a, sweep_area(suffix[p - a]), b - p, p);
+			if (key < best) best = key;
+			SweepItem it = box[p]; it.flag = 0u; acc = sweep_join(acc, it);
+		}
+		cut_of[a] = best; area_of[a] = sweep_area(acc);
+	};
+	struct Run { uint32_t a, b; };
+	std::vector<Run> cur(1, Run{0u, n}), next;
+	out.level_first.assign(1, 0u);
+	auto set_link = [](WideNode& w, int k, int32_t link) {
+		for (int j = 0; j < 8; j++) w.slot[k][j] = 0.0f;
+		if (link == kEmptyLink) w.slot[k][4] = w.slot[k][5] = w.slot[k][7] = -1.0e30f;
+		w.slot[k][6] = int_as_float(link);
+	};
+	while (!cur.empty()) {
+		if (out.level_first.size() > kSweepMaxLevels) return false;  // deeper than the traversal stack allows: the caller builds the packed tree instead
+		const uint32_t child_level_first = out.level_first.back() + static_cast<uint32_t>(cur.size());
+		out.level_first.push_back(child_level_first);
+		next.clear();
+		for (const Run& r : cur) {
+			SweepKids K{}; K.a[0] = r.a; K.b[0] = r.b; K.n = 1u;
+			survey(r.a, r.b);
+			for (int round = 0; round < 3; round++) {
+				if (!sweep_open(K, cut_of.data(), area_of.data())) break;
+				// the two runs the cut made are surveyed for the next round (the device re-surveys every run of the array every round)
+				const uint32_t right = K.n - 1u;
+				survey(K.a[right], K.b[right]);
+				for (uint32_t k = 0; k < right; k++) if (K.b[k] == K.a[right]) survey(K.a[k], K.b[k]);  // the shortened left part
+			}
+			int32_t link[4]; uint32_t ca[4], cb[4];
+			const uint32_t ni = sweep_links(K, order.data(), child_level_first + static_cast<uint32_t>(next.size()), link, ca, cb);
+			for (uint32_t i = 0; i < ni; i++) next.push_back(Run{ca[i], cb[i]});
+			WideNode w; for (int k = 0; k < 4; k++) set_link(w, k, link[k]);
+			out.nodes.push_back(w);
+		}
+		cur.swap(next);
+	}
+	const uint32_t levels = static_cast<uint32_t>(out.level_first.size()) - 1u;
+	out.depth = levels; out.max_stack = 3u * levels;
+	out.prims.resize(n);
+	for (uint32_t i = 0; i < n; i++) out.prims[i] = make_float4(prims[i].position[0], prims[i].position[1], prims[i].position[2], prims[i].radius_sq);
+	wide_fill_boxes(out, out.prims.data(), ob);
+	uint32_t node_bits = 1; while ((1ull << node_bits) < out.nodes.size()) node_bits++;
+	out.tn_bits = std::min(32u - node_bits, 29u);
+	return true;
+}
+
 void pack_scene(const b2r_sphere* prims, uint32_t n_prims, const b2r_material* materials, uint32_t n_mat,
                 const int32_t* light_geom_idx, uint32_t n_lights, const b2r_sphere* geometry, PackedScene& out) {
 	auto f4 = [](float x, float y, float z, float w) { float4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; };

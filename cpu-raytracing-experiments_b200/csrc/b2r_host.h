@@ -57,6 +57,11 @@ void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* 
 // alone; the boxes are then filled by the refit routine. This is its host twin (tests compare the device tree with it bit for bit).
 void morton_keys(const b2r_sphere* prims, uint32_t n, const float lo[3], const float hi[3], std::vector<uint32_t>& keys);
 void build_packed_tree(const b2r_sphere* prims, uint32_t n, WideBvh& out, const OriginBox* ob = nullptr);
+// The better tree the GPU can build by itself (B2R_FLAG_GPU_TREE | B2R_FLAG_GPU_SAH; k_sweep_* in b2r_device.cuh): the spheres stay in curve
+// order, and every node is a run of that order cut top-down where the surface-area heuristic is smallest ALONG THE CURVE, opened 2 -> 4 wide
+// like flatten_bvh's collapse (b2r_shade.h: sweep_*). Host twin, bit for bit. Returns false (out unusable) when the tree would be deeper
+// than kSweepMaxLevels — the caller then builds the packed tree.
+bool build_sweep_tree(const b2r_sphere* prims, uint32_t n, WideBvh& out, const OriginBox* ob = nullptr);
 // level sizes of the packed tree for n spheres, root level first (level_first has one more entry than there are levels)
 void packed_levels(uint32_t n, std::vector<uint32_t>& level_first);
 // (Re)compute every slot box of a flattened topology for the spheres `prims` and the origin box `ob` (what flatten_bvh ends with).

@@ -502,6 +502,53 @@ B2R_HD uint32_t morton_key(float cx, float cy, float cz, const float lo[3], cons
 	return (morton_spread10(x0) << 2) | (morton_spread10(x1) << 1) | morton_spread10(x2);
 #endif
 }
+// ---- sweep build of the device tree (B2R_FLAG_GPU_SAH): arithmetic shared by k_sweep_* (b2r_device.cuh) and the host twin build_sweep_tree (b2r_host.cpp).
+// The spheres stay in curve order; a node is a run [a, b) of that order, split where area(left) * count(left) + area(right) * count(right)
+// is smallest (a surface-area-heuristic sweep along the curve instead of along three axes), the run with the largest box opened first
+// until a node has four runs — the same greedy 2 -> 4 collapse flatten_bvh applies to a binary tree.
+struct SweepItem { float lo0, lo1, lo2; uint32_t pos; float hi0, hi1, hi2; uint32_t flag; };  // a box + the segmented-scan bookkeeping (32 B)
+B2R_HD SweepItem sweep_join(const SweepItem& a, const SweepItem& b) {  // segmented union, associative: an item that starts a segment forgets what is left of it
+	if (b.flag) return b;
+	SweepItem r;
+	r.lo0 = sel_min(a.lo0, b.lo0); r.lo1 = sel_min(a.lo1, b.lo1); r.lo2 = sel_min(a.lo2, b.lo2);
+	r.hi0 = sel_max(a.hi0, b.hi0); r.hi1 = sel_max(a.hi1, b.hi1); r.hi2 = sel_max(a.hi2, b.hi2);
+	r.pos = a.pos; r.flag = a.flag;
+	return r;
+}
+struct SweepJoin { B2R_HD SweepItem operator()(const SweepItem& a, const SweepItem& b) const { return sweep_join(a, b); } };
+B2R_HD float sweep_area(const SweepItem& s) { const float ex = s.hi0 - s.lo0, ey = s.hi1 - s.lo1, ez = s.hi2 - s.lo2; return ex * ey + ey * ez + ez * ex; }
+B2R_HD void sweep_sphere_box(const float4 s, SweepItem* it) {
+	const float r = sqrtf(s.w);
+	it->lo0 = s.x - r; it->lo1 = s.y - r; it->lo2 = s.z - r; it->hi0 = s.x + r; it->hi1 = s.y + r; it->hi2 = s.z + r; it->pos = 0u; it->flag = 0u;
+}
+// cost of cutting a run in front of position `pos`, packed so that an unsigned minimum picks the cheapest cut and, among equals, the first
+B2R_HD unsigned long long sweep_key(float area_l, uint32_t n_l, float area_r, uint32_t n_r, uint32_t pos) {
+	const float cost = area_l * static_cast<float>(n_l) + area_r * static_cast<float>(n_r);
+	return (static_cast<unsigned long long>(bits(cost)) << 32) | pos;
+}
+struct SweepKids { uint32_t a[4], b[4], n; };  // the runs of one node while it is being opened (list order = slot order of flatten_bvh's collapse)
+// one opening round: the run with the largest box among those holding two or more spheres is cut at its best position (cut_of[start of the
+// run], area_of[start of the run]); the left part keeps its place in the list, the right part goes to the end. Returns the cut or 0 (none).
+B2R_HD uint32_t sweep_open(SweepKids& K, const unsigned long long* cut_of, const float* area_of) {
+	if (K.n >= 4u) return 0u;
+	int pick = -1; float best = -1.0f;
+	for (uint32_t k = 0; k < K.n; k++) if (K.b[k] - K.a[k] >= 2u) { const float ar = area_of[K.a[k]]; if (ar > best) { best = ar; pick = static_cast<int>(k); } }
+	if (pick < 0) return 0u;
+	const uint32_t pos = static_cast<uint32_t>(cut_of[K.a[pick]] & 0xffffffffull);
+	K.a[K.n] = pos; K.b[K.n] = K.b[pick]; K.b[pick] = pos; K.n++;
+	return pos;
+}
+// the four links of a finished node: runs of two or more spheres first (children child_first, child_first + 1, ... of the next level, their
+// ranges returned), then single spheres (~index in the caller's sphere order), both in list order, then empty slots. Returns the child count.
+B2R_HD uint32_t sweep_links(const SweepKids& K, const uint32_t* order, uint32_t child_first, int32_t link[4], uint32_t child_a[4], uint32_t child_b[4]) {
+	uint32_t ni = 0u; int s = 0;
+	for (uint32_t k = 0; k < K.n; k++) if (K.b[k] - K.a[k] >= 2u) { link[s++] = static_cast<int32_t>(child_first + ni); child_a[ni] = K.a[k]; child_b[ni] = K.b[k]; ni++; }
+	for (uint32_t k = 0; k < K.n; k++) if (K.b[k] - K.a[k] == 1u) link[s++] = ~static_cast<int32_t>(order[K.a[k]]);
+	for (; s < 4; s++) link[s] = kEmptyLink;
+	return ni;
+}
+constexpr uint32_t kSweepMaxLevels = 20u;  // 3 stack entries per level must fit kTraversalStack; a deeper tree falls back to the packed one
+
 B2R_HD void morton_scale(const float lo[3], const float hi[3], float scale[3]) { for (int k = 0; k < 3; k++) { const float e = hi[k] - lo[k]; scale[k] = e > 0.0f ? 1024.0f / e : 0.0f; } }
 B2R_HD float slot_half_area(const float4 /*a*/, const float4 b) { return 4.0f * (b.x * b.y + b.y * b.w + b.w * b.x); }
 

@@ -256,3 +256,40 @@ def test_packed_tree_sort_key_is_a_hilbert_curve(hostcheck):
         k = keys_of(g)
         assert len(set(k.tolist())) == 32 ** 3 and int(k.max()) - int(k.min()) == 32 ** 3 - 1
         assert (np.abs(np.diff(g[np.argsort(k)], axis=0)).sum(1) == 1).all()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 17, 300, 5000])
+def test_sweep_tree_host_twin(hostcheck, n):
+    """The tree b2r_upload_scene builds on the GPU with B2R_FLAG_GPU_TREE | B2R_FLAG_GPU_SAH, through its host twin (build_sweep_tree): every
+    sphere in exactly one leaf, boxes conservative and tight, the closest hit through it equals brute force (indices included) — and it is
+    the better tree: fewer node visits than the packed one on the same rays."""
+    rs = np.random.RandomState(n)
+    sc = scenes.random_scene(max(n, 2), light_every=5)
+    _, prims, _ = b2r.build_bvh(sc["geometry"][:n])
+    nw = C.c_uint32(0); ms = C.c_uint32(0)
+    assert hostcheck.hc_sweep_tree(vp(prims), n, None, None, C.byref(nw), C.byref(ms)) == 0
+    wide = np.zeros((nw.value, 4, 8), np.float32)
+    assert hostcheck.hc_sweep_tree(vp(prims), n, None, vp(wide), C.byref(nw), C.byref(ms)) == 0
+    assert ms.value + 3 <= 64
+    check_contains(wide, prims)
+    rays = camera_rays(2000, rs, prims) if n > 1 else np.ascontiguousarray(np.concatenate([prims["position"][[0] * 50] + rs.uniform(3, 9, (50, 3)), -np.ones((50, 3)) / np.sqrt(3)], 1), np.float32)
+    m = len(rays); st = np.zeros(m, np.uint32); bx = np.zeros(m, np.uint32); sp = np.zeros(m, np.uint32); pr = np.zeros(m, np.int32)
+    assert hostcheck.hc_trace_stats(None, 0xfffffffe, vp(prims), n, vp(rays), m, vp(st), vp(bx), vp(sp), vp(pr)) == 0
+    bt = np.zeros(m, np.float32); bp = np.zeros(m, np.int32)
+    hostcheck.hc_closest_brute(vp(prims), n, vp(rays), m, vp(bt), vp(bp))
+    assert np.array_equal(bp, pr)
+    if n >= 300:
+        st2 = np.zeros(m, np.uint32)
+        hostcheck.hc_trace_stats(None, 0xffffffff, vp(prims), n, vp(rays), m, vp(st2), vp(bx), vp(sp), vp(pr))
+        assert st.sum() < st2.sum()
+
+
+def test_sweep_tree_gives_up_on_a_tree_deeper_than_the_stack(hostcheck):
+    """Concentric spheres whose radii grow by half from one to the next: the cheapest cut always peels the largest one off, so the sweep tree
+    would be dozens of levels deep; build_sweep_tree says so and the library falls back to the balanced packed tree."""
+    n = 100
+    geo = np.zeros(n, scenes.SPHERE_DTYPE); geo["radius_sq"] = ((1.5 ** np.arange(n)) ** 2).astype(np.float32); geo["position"][:, 0] = 0.3
+    nw = C.c_uint32(0); ms = C.c_uint32(0)
+    assert hostcheck.hc_sweep_tree(vp(geo), n, None, None, C.byref(nw), C.byref(ms)) == 1
+    hostcheck.hc_packed_tree(vp(geo), n, None, None, C.byref(nw), C.byref(ms))
+    assert ms.value + 3 <= 64
