@@ -633,7 +633,13 @@ def run_workload(args, name, rank, world, local, stream, dev, secondary=False):
         t3 = time.perf_counter(); r.SetScene(ps2); r.sync(); t4 = time.perf_counter()
         ms_gpu_tree = steps_ms()
         edit_line["gpu_tree"] = {"upload_scene_ms": (t4 - t3) * 1e3, "ms_per_step": ms_gpu_tree,
-                                 "note": "b2r_upload_scene with B2R_FLAG_GPU_TREE: pack + H2D on the host side, Morton keys + radix sort + implicit 4-ary links + refit passes on the device, host wall clock incl. stream sync; the balanced Morton tree needs more node visits than the SAH tree (ms_per_step), so it is the instant tree after an edit, replaced by a default upload when the host build is done"}
+                                 "note": "b2r_upload_scene with B2R_FLAG_GPU_TREE: pack + H2D on the host side, Hilbert keys + radix sort + implicit 4-ary links + refit passes on the device, host wall clock incl. stream sync; the balanced packed tree needs more node visits than the SAH tree (ms_per_step), so it is the instant tree after an edit, replaced by a default upload when the host build is done"}
+        # the same with B2R_FLAG_GPU_SAH: the device cuts the curve order where the surface-area heuristic along the curve is smallest (k_sweep_*)
+        r.set_flags(b2r.FLAG_GPU_TREE | b2r.FLAG_GPU_SAH | b.base_flags); r.SetCamera(b.ps.camera); r.SetScene(ps2); r.sync()
+        t5 = time.perf_counter(); r.SetScene(ps2); r.sync(); t6 = time.perf_counter()
+        ms_gpu_sweep = steps_ms()
+        edit_line["gpu_sweep_tree"] = {"upload_scene_ms": (t6 - t5) * 1e3, "ms_per_step": ms_gpu_sweep, "wide_nodes": int(len(r.wide_nodes()[0])),
+                                       "note": "b2r_upload_scene with B2R_FLAG_GPU_TREE | B2R_FLAG_GPU_SAH: as gpu_tree, but the topology is the sweep tree — per level three rounds of two segmented scans + cost + open kernels over the curve order, one 4-byte read-back per level; device tree == host twin build_sweep_tree bit for bit (tests)"}
         r.set_flags(b.base_flags); r.SetCamera(b.ps.camera)
         r.SetScene(b.ps)
 

@@ -3,6 +3,7 @@
 #include "b2r_device.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <cstdio>
 #include <cstdlib>
@@ -81,7 +82,7 @@ struct b2r_ctx {
 	WideBvh wide_host; uint64_t wide_key = 0; std::vector<unsigned char> wide_blob; bool have_wide = false;
 	uint32_t n_wide = 0;  // wide nodes of the current tree
 	// B2R_FLAG_GPU_TREE: the tree was built on the device (no host copy of its nodes); sort scratch; the arrays a later refit needs to match
-	bool gpu_tree = false; uint32_t *d_mkey[2] = {nullptr, nullptr}, *d_midx[2] = {nullptr, nullptr}; size_t cap_mkey = 0; uint8_t* d_sort_tmp = nullptr; size_t cap_sort_tmp = 0;
+	bool gpu_tree = false; uint32_t *d_mkey[2] = {nullptr, nullptr}, *d_midx[2] = {nullptr, nullptr}; size_t cap_mkey = 0; uint8_t* d_sort_tmp = nullptr; size_t cap_sort_tmp = 0; uint8_t* d_sweep = nullptr; size_t cap_sweep = 0;  // d_sweep: scratch of the sweep build (B2R_FLAG_GPU_SAH)
 	std::vector<b2r_sphere> lazy_prims, lazy_geom; double* d_cost_base = nullptr;
 	std::vector<uint32_t> cur_geom_of_prim;  // after a refit into a new BVH order: that order's index -> geometry index (empty: wide_host's)
 	uint32_t* d_remap = nullptr; size_t cap_remap = 0;
@@ -572,6 +573,70 @@ int refresh_side_scene(b2r_ctx* c, uint32_t sidx) {
 	return B2R_OK;
 }
 
+// B2R_FLAG_GPU_TREE | B2R_FLAG_GPU_SAH: links of the sweep tree over the spheres in curve order (`order` = the radix sort's output), written
+// into c->d_wide level by level (b2r_device.cuh k_sweep_*; host twin build_sweep_tree). One 4-byte read-back per level tells the host how
+// many nodes the next level has. *built stays false when the tree would be deeper than kSweepMaxLevels (the caller links the packed tree).
+int sweep_build(b2r_ctx* c, const uint32_t* order, uint32_t n, bool* built) {
+	*built = false;
+	cudaStream_t st = c->scene_st;
+	const size_t cap = n / 2u + 1u;  // runs of two or more spheres on one level
+	size_t t_scan = 0, t_sum = 0;
+	CU(cub::DeviceScan::InclusiveScan(nullptr, t_scan, static_cast<SweepItem*>(nullptr), static_cast<SweepItem*>(nullptr), SweepJoin(), static_cast<int>(n), st));
+	CU(cub::DeviceScan::ExclusiveSum(nullptr, t_sum, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), static_cast<int>(cap + 1u), st));
+	size_t t_cub = t_scan > t_sum ? t_scan : t_sum;
+	size_t off = 0; auto take = [&](size_t bytes) { const size_t at = off; off += (bytes + 255u) & ~static_cast<size_t>(255u); return at; };
+	const size_t o_box = take(n * sizeof(SweepItem)), o_fwd = take(n * sizeof(SweepItem)), o_bwd = take(n * sizeof(SweepItem)), o_cut = take(n * sizeof(unsigned long long)),
+	             o_area = take(n * sizeof(float)), o_head = take(n * sizeof(uint32_t)), o_run0 = take(cap * sizeof(SweepRun)), o_run1 = take(cap * sizeof(SweepRun)),
+	             o_kids = take(cap * sizeof(SweepKids)), o_inner = take((cap + 1u) * sizeof(uint32_t)), o_before = take((cap + 1u) * sizeof(uint32_t)), o_cub = take(t_cub);
+	int rc; if ((rc = dev_reserve(&c->d_sweep, &c->cap_sweep, off))) return rc;
+	uint8_t* base = c->d_sweep;
+	SweepItem *box = reinterpret_cast<SweepItem*>(base + o_box), *fwd = reinterpret_cast<SweepItem*>(base + o_fwd), *bwd = reinterpret_cast<SweepItem*>(base + o_bwd);
+	unsigned long long* cut_of = reinterpret_cast<unsigned long long*>(base + o_cut); float* area_of = reinterpret_cast<float*>(base + o_area); uint32_t* head = reinterpret_cast<uint32_t*>(base + o_head);
+	SweepRun* runs[2] = {reinterpret_cast<SweepRun*>(base + o_run0), reinterpret_cast<SweepRun*>(base + o_run1)};
+	SweepKids* kids = reinterpret_cast<SweepKids*>(base + o_kids); uint32_t *inner = reinterpret_cast<uint32_t*>(base + o_inner), *before = reinterpret_cast<uint32_t*>(base + o_before);
+	void* cub_tmp = base + o_cub;
+	auto grid = [](uint32_t threads) { return (threads + kBlock - 1u) / kBlock; };
+	k_sweep_boxes<<<grid(n), kBlock, 0, st>>>(c->d_prims, order, n, box, head);
+	const SweepRun root{0u, n};
+	CU(cudaMemcpyAsync(runs[0], &root, sizeof root, cudaMemcpyHostToDevice, st)); CU(cudaStreamSynchronize(st));  // (`root` is a local)
+	c->launches++;
+	std::vector<uint32_t> lf(1, 0u);
+	uint32_t m = 1u; int cur = 0;
+	while (m) {
+		if (lf.size() > kSweepMaxLevels) return B2R_OK;
+		const uint32_t first = lf.back(), child_first = first + m;
+		if (child_first > n) return fail(B2R_ERR_BVH, "sweep build: more nodes than spheres");
+		lf.push_back(child_first);
+		k_sweep_begin<<<grid(m), kBlock, 0, st>>>(runs[cur], m, kids);
+		for (int round = 0; round < 3; round++) {
+			k_sweep_items<<<grid(n), kBlock, 0, st>>>(box, head, n, fwd, bwd, cut_of);
+			size_t t = t_cub;
+			CU(cub::DeviceScan::InclusiveScan(cub_tmp, t, fwd, fwd, SweepJoin(), static_cast<int>(n), st));
+			t = t_cub;
+			CU(cub::DeviceScan::InclusiveScan(cub_tmp, t, bwd, bwd, SweepJoin(), static_cast<int>(n), st));
+			k_sweep_cost<<<grid(n), kBlock, 0, st>>>(fwd, bwd, head, n, cut_of, area_of);
+			k_sweep_open<<<grid(m), kBlock, 0, st>>>(kids, m, cut_of, area_of, head);
+		}
+		k_sweep_count<<<grid(m + 1u), kBlock, 0, st>>>(kids, m, inner);
+		size_t t = t_cub;
+		CU(cub::DeviceScan::ExclusiveSum(cub_tmp, t, inner, before, static_cast<int>(m + 1u), st));
+		k_sweep_emit<<<grid(m), kBlock, 0, st>>>(kids, m, before, order, reinterpret_cast<float4*>(c->d_wide), first, child_first, runs[cur ^ 1]);
+		c->launches += 12;
+		uint32_t total = 0u;
+		CU(cudaMemcpyAsync(&total, before + m, sizeof total, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st));
+		CU(cudaGetLastError());
+		if (total > cap) return fail(B2R_ERR_BVH, "sweep build: inconsistent run count");
+		m = total; cur ^= 1;
+	}
+	WideBvh& w = c->wide_host;
+	w.level_first = lf; w.depth = static_cast<uint32_t>(lf.size()) - 1u; w.max_stack = 3u * w.depth;
+	c->n_wide = lf.back();
+	uint32_t node_bits = 1; while ((1ull << node_bits) < c->n_wide) node_bits++;
+	w.tn_bits = 32u - node_bits < 29u ? 32u - node_bits : 29u;
+	*built = true;
+	return B2R_OK;
+}
+
 // Boxes of the device tree for the current origin box: one k_refit_level launch per BFS level, deepest first (stream order is the
 // dependency). remap (device, may be null) re-links leaves into a new BVH order.
 int launch_refit_levels(b2r_ctx* c, const uint32_t* d_remap) {
@@ -653,7 +718,7 @@ void b2r_destroy(b2r_ctx* c) {
 	drop_graph(c);
 	for (auto& t : c->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
 	dev_free(&c->d_prims); dev_free(&c->d_mat_albedo); dev_free(&c->d_mat_emission); dev_free(&c->d_mat_f0); dev_free(&c->d_light_sphere); dev_free(&c->d_light_emit);
-	dev_free(&c->d_hdri); dev_free(&c->d_prim_mat); dev_free(&c->d_wide); dev_free(&c->d_cost); dev_free(&c->d_remap); dev_free(&c->d_trace); dev_free(&c->d_cost_base); dev_free(&c->d_sort_tmp);
+	dev_free(&c->d_hdri); dev_free(&c->d_prim_mat); dev_free(&c->d_wide); dev_free(&c->d_cost); dev_free(&c->d_remap); dev_free(&c->d_trace); dev_free(&c->d_cost_base); dev_free(&c->d_sort_tmp); dev_free(&c->d_sweep);
 	for (int k = 0; k < 2; k++) { dev_free(&c->d_mkey[k]); dev_free(&c->d_midx[k]); }
 	for (int s = 0; s < 2; s++) { dev_free(&c->d_A[s]); dev_free(&c->d_B[s]); dev_free(&c->d_T[s]); }
 	dev_free(&c->d_H); dev_free(&c->d_SA); dev_free(&c->d_SB); dev_free(&c->d_SL); dev_free(&c->d_SS); dev_free(&c->d_parent); dev_free(&c->d_leaf_node); dev_free(&c->d_rad); dev_free(&c->d_acc); dev_free(&c->d_fb);
@@ -791,6 +856,7 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 		c->n_wide = w.level_first.back();
 		uint32_t node_bits = 1; while ((1ull << node_bits) < c->n_wide) node_bits++;
 		w.tn_bits = 32u - node_bits < 29u ? 32u - node_bits : 29u;
+		if ((c->cfg.flags & B2R_FLAG_GPU_SAH) && n_prims >= 2u && n_prims > c->n_wide) c->n_wide = n_prims;  // the sweep tree: fewer nodes than spheres, how many is known once it is built (reserve for the bound)
 		c->wide_key = 0; c->wide_blob.clear(); c->have_wide = true; c->gpu_tree = true;
 		c->lazy_prims.assign(prims, prims + n_prims); c->lazy_geom.assign(geometry, geometry + n_geom);  // matched by value only if a refit ever asks
 	} else {
@@ -863,11 +929,17 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 		CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_mkey[0], c->d_mkey[1], c->d_midx[0], c->d_midx[1], static_cast<int>(n_prims), 0, 30, c->scene_st));
 		if ((rc = dev_reserve(&c->d_sort_tmp, &c->cap_sort_tmp, tmp))) return rc;
 		CU(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, tmp, c->d_mkey[0], c->d_mkey[1], c->d_midx[0], c->d_midx[1], static_cast<int>(n_prims), 0, 30, c->scene_st));
-		PackedLevels lv{}; lv.levels = c->wide_host.depth;
-		if (lv.levels + 1u > sizeof lv.first / sizeof lv.first[0]) return fail(B2R_ERR_BVH, "packed tree deeper than 23 levels");
-		for (uint32_t l = 0; l <= lv.levels; l++) lv.first[l] = c->wide_host.level_first[l];
-		k_packed_links<<<(c->n_wide * 4u + kBlock - 1u) / kBlock, kBlock, 0, c->scene_st>>>(reinterpret_cast<float4*>(c->d_wide), lv, n_prims, c->d_midx[1]);
-		CU(cudaGetLastError()); c->launches += 3;
+		bool swept = false;
+		if ((c->cfg.flags & B2R_FLAG_GPU_SAH) && n_prims >= 2u && (rc = sweep_build(c, c->d_midx[1], n_prims, &swept))) return rc;
+		if (!swept) {
+			c->n_wide = c->wide_host.level_first.back();  // (the packed shape worked out above)
+			PackedLevels lv{}; lv.levels = c->wide_host.depth;
+			if (lv.levels + 1u > sizeof lv.first / sizeof lv.first[0]) return fail(B2R_ERR_BVH, "packed tree deeper than 23 levels");
+			for (uint32_t l = 0; l <= lv.levels; l++) lv.first[l] = c->wide_host.level_first[l];
+			k_packed_links<<<(c->n_wide * 4u + kBlock - 1u) / kBlock, kBlock, 0, c->scene_st>>>(reinterpret_cast<float4*>(c->d_wide), lv, n_prims, c->d_midx[1]);
+			c->launches++;
+		}
+		CU(cudaGetLastError()); c->launches += 2;
 		if ((rc = launch_refit_levels(c, nullptr))) return rc;
 		if (!c->d_cost_base) { size_t cap = 0; if ((rc = dev_reserve(&c->d_cost_base, &cap, 1))) return rc; }
 		CU(cudaMemsetAsync(c->d_cost_base, 0, sizeof(double), c->scene_st));

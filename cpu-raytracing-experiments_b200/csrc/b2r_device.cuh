@@ -1079,11 +1079,12 @@ __global__ void __launch_bounds__(kBlock) k_link_tables(const float4* __restrict
 }
 // ---------------------------------------------------------------------------------------------- GPU tree build (B2R_FLAG_GPU_TREE)
 // The traversal tree built on the device for edits that add or remove spheres (the reference rebuilds its BVH on every edit,
-// Application.cpp:508-509): 30-bit Morton keys of the sphere centres, a stable radix sort (CUB), then an implicit, perfectly balanced
+// Application.cpp:508-509): 30-bit curve keys of the sphere centres (the Hilbert index of the centre's cell, b2r_shade.h morton_key — a run of
+// consecutive Hilbert keys is a connected set of cells, a Z-curve run is not), a stable radix sort (CUB), then an implicit, perfectly balanced
 // 4-ary topology over the sorted order — four spheres to a bottom node, four nodes to a parent — whose links follow from the sphere count
 // alone (k_packed_links), and the boxes from the same k_refit_level passes a scene edit uses. Results do not depend on the tree; its
-// quality does: on C3's overlapping spheres it needs ~3.5x the node visits of the host's SAH tree, so it is the instant tree
-// after an edit, not the default. Host twin: build_packed_tree (b2r_host.cpp); the tests compare the two bit for bit.
+// quality does: on C3's overlapping spheres it needs ~2x the node visits of the host's SAH tree (4x when it sorted by Morton code),
+// so it is the instant tree after an edit, not the default; the sweep tree below (B2R_FLAG_GPU_SAH) is the better one. Host twin: build_packed_tree (b2r_host.cpp); the tests compare the two bit for bit.
 struct PackedLevels { uint32_t first[24]; uint32_t levels; };   // level_first of packed_levels(): root level first
 __global__ void __launch_bounds__(kBlock) k_morton_keys(const float4* __restrict__ prims, const uint32_t n, const float lo0, const float lo1, const float lo2,
                                                         const float s0, const float s1, const float s2, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
@@ -1103,6 +1104,82 @@ __global__ void __launch_bounds__(kBlock) k_packed_links(float4* __restrict__ wi
 	float4* slot = wide + static_cast<size_t>(node) * 8 + 2 * k;
 	if (c >= child_count) { slot[0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); slot[1] = make_float4(-1.0e30f, -1.0e30f, __int_as_float(kEmptyLink), -1.0e30f); }
 	else { slot[0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); slot[1] = make_float4(0.0f, 0.0f, __int_as_float(bottom ? ~static_cast<int32_t>(order[c]) : static_cast<int32_t>(lv.first[l + 1] + c)), 0.0f); }
+}
+// ---- sweep build (B2R_FLAG_GPU_TREE | B2R_FLAG_GPU_SAH; host twin build_sweep_tree, shared arithmetic b2r_shade.h sweep_*). The spheres stay
+// in curve order (the radix sort above); `head[p]` says that position p starts a run. One opening round = k_sweep_items (every position's
+// box with the run bookkeeping, forwards and backwards) -> two in-place segmented inclusive scans (cub::DeviceScan, operator sweep_join:
+// fwd[p] = box of [run start, p], bwd[n-1-p] = box of [p, run end)) -> k_sweep_cost (every possible cut of every run costed, the cheapest
+// filed under the run's start with one atomic minimum per warp or lane) -> k_sweep_open (one thread per node of the level: cut the run
+// with the largest box). Three rounds make a node's four runs; k_sweep_count / an exclusive sum / k_sweep_emit then write the level's
+// links and the next level's nodes. The host reads one count per level (how many nodes the next level has).
+struct SweepRun { uint32_t a, b; };
+__global__ void __launch_bounds__(kBlock) k_sweep_boxes(const float4* __restrict__ prims, const uint32_t* __restrict__ order, const uint32_t n, SweepItem* __restrict__ box, uint32_t* __restrict__ head) {
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n) return;
+	SweepItem it; sweep_sphere_box(prims[order[p]], &it);
+	box[p] = it; head[p] = p == 0u ? 1u : 0u;
+}
+__global__ void __launch_bounds__(kBlock) k_sweep_items(const SweepItem* __restrict__ box, const uint32_t* __restrict__ head, const uint32_t n, SweepItem* __restrict__ fwd, SweepItem* __restrict__ bwd,
+                                                        unsigned long long* __restrict__ cut_of) {
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n) return;
+	SweepItem it = box[p];
+	it.pos = p; it.flag = head[p]; fwd[p] = it;                                            // a run's first position carries its start ...
+	it.pos = p + 1u; it.flag = (p + 1u == n || head[p + 1u] != 0u) ? 1u : 0u; bwd[n - 1u - p] = it;   // ... its last position its end, in the reversed array
+	cut_of[p] = ~0ull;
+}
+__global__ void __launch_bounds__(kBlock) k_sweep_cost(const SweepItem* __restrict__ fwd, const SweepItem* __restrict__ bwd, const uint32_t* __restrict__ head, const uint32_t n,
+                                                       unsigned long long* __restrict__ cut_of, float* __restrict__ area_of) {
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long key = ~0ull; uint32_t start = 0xffffffffu;
+	if (p < n) {
+		const SweepItem f = fwd[p], b = bwd[n - 1u - p];
+		start = f.pos; const uint32_t end = b.pos;
+		if (head[p] == 0u) key = sweep_key(sweep_area(fwd[p - 1u]), p - start, sweep_area(b), end - p, p);   // cut in front of p: [start, p) | [p, end)
+		if (p + 1u == end) area_of[start] = sweep_area(f);
+	}
+	// one atomic per warp while the whole warp sits in one run (the top of the tree), one per lane otherwise
+	const uint32_t s0 = __shfl_sync(0xffffffffu, start, 0);
+	if (__all_sync(0xffffffffu, start == s0 || p >= n)) {
+		for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o); key = other < key ? other : key; }
+		if (lane_id() == 0u && key != ~0ull) atomicMin(cut_of + s0, key);
+	} else if (key != ~0ull) atomicMin(cut_of + start, key);
+}
+__global__ void __launch_bounds__(kBlock) k_sweep_begin(const SweepRun* __restrict__ runs, const uint32_t m, SweepKids* __restrict__ kids) {
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= m) return;
+	SweepKids K; for (int k = 0; k < 4; k++) { K.a[k] = 0u; K.b[k] = 0u; }
+	K.a[0] = runs[j].a; K.b[0] = runs[j].b; K.n = 1u;
+	kids[j] = K;
+}
+__global__ void __launch_bounds__(kBlock) k_sweep_open(SweepKids* __restrict__ kids, const uint32_t m, const unsigned long long* __restrict__ cut_of, const float* __restrict__ area_of, uint32_t* __restrict__ head) {
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= m) return;
+	SweepKids K = kids[j];
+	const uint32_t pos = sweep_open(K, cut_of, area_of);
+	if (pos) { kids[j] = K; head[pos] = 1u; }
+}
+__global__ void __launch_bounds__(kBlock) k_sweep_count(const SweepKids* __restrict__ kids, const uint32_t m, uint32_t* __restrict__ inner) {
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j > m) return;
+	uint32_t ni = 0u;
+	if (j < m) { const SweepKids K = kids[j]; for (uint32_t k = 0; k < K.n; k++) ni += (K.b[k] - K.a[k] >= 2u) ? 1u : 0u; }
+	inner[j] = ni;   // inner[m] = 0: the exclusive sum leaves the level's total there
+}
+__global__ void __launch_bounds__(kBlock) k_sweep_emit(const SweepKids* __restrict__ kids, const uint32_t m, const uint32_t* __restrict__ inner_before, const uint32_t* __restrict__ order,
+                                                       float4* __restrict__ wide, const uint32_t level_first, const uint32_t child_level_first, SweepRun* __restrict__ next_runs) {
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= m) return;
+	const SweepKids K = kids[j];
+	int32_t link[4]; uint32_t ca[4], cb[4];
+	const uint32_t before = inner_before[j];
+	const uint32_t ni = sweep_links(K, order, child_level_first + before, link, ca, cb);
+	for (uint32_t i = 0; i < ni; i++) next_runs[before + i] = SweepRun{ca[i], cb[i]};
+	float4* node = wide + static_cast<size_t>(level_first + j) * 8;
+	for (int k = 0; k < 4; k++) {
+		node[2 * k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		node[2 * k + 1] = link[k] == kEmptyLink ? make_float4(-1.0e30f, -1.0e30f, __int_as_float(kEmptyLink), -1.0e30f) : make_float4(0.0f, 0.0f, __int_as_float(link[k]), 0.0f);
+	}
 }
 // Sum of the inner-slot half areas (the quantity a refit is judged by: cost now / cost when the tree was built).
 __global__ void __launch_bounds__(kBlock) k_tree_cost(const float4* __restrict__ wide, const uint32_t n_nodes, double* __restrict__ out) {

@@ -52,7 +52,7 @@ bool origin_box_holds(const OriginBox& ob, const float* points, uint32_t n_point
 // Collapse the binary tree 2 -> 4 wide, inline the leaf spheres and compute every slot box bottom-up (the refit routine, level by level).
 void flatten_bvh(const b2r_bvh_node* nodes, uint32_t n_nodes, const b2r_sphere* prims, uint32_t n_prims, WideBvh& out, const OriginBox* ob = nullptr);
 // The traversal tree the GPU can build by itself (b2r_upload_scene with B2R_FLAG_GPU_TREE; k_morton_keys / k_packed_links in
-// b2r_device.cuh): spheres sorted by the 30-bit Morton code of their centre (stable), packed four to a bottom node, nodes packed four to
+// b2r_device.cuh): spheres sorted by the 30-bit curve key of their centre (its cell's Hilbert index, b2r_shade.h morton_key; stable), packed four to a bottom node, nodes packed four to
 // a parent, level by level up to the root — an implicit, perfectly balanced 4-ary topology whose links follow from the sphere count
 // alone; the boxes are then filled by the refit routine. This is its host twin (tests compare the device tree with it bit for bit).
 void morton_keys(const b2r_sphere* prims, uint32_t n, const float lo[3], const float hi[3], std::vector<uint32_t>& keys);

@@ -478,7 +478,8 @@ B2R_HD void refit_slot(float4* __restrict__ wide /*8 float4 per node*/, const fl
 	float4 a, b; refit_child_box(wide + static_cast<size_t>(link) * 8, &a, &b, link);
 	slot[0] = a; slot[1] = b;
 }
-// 30-bit Morton code of a sphere centre inside the sphere bounds [lo, hi] (10 bits per axis); shared by the GPU tree build and its host twin
+// 30-bit curve key of a sphere centre inside the sphere bounds [lo, hi] (10 bits per axis: the cell's Hilbert index; -DB2R_MORTON_ORDER = the Z-curve
+// code it replaced, for A/B runs); shared by the GPU tree builds and their host twins
 B2R_HD uint32_t morton_spread10(uint32_t v) { v &= 1023u; v = (v | (v << 16)) & 0x030000ffu; v = (v | (v << 8)) & 0x0300f00fu; v = (v | (v << 4)) & 0x030c30c3u; v = (v | (v << 2)) & 0x09249249u; return v; }
 B2R_HD uint32_t morton_key(float cx, float cy, float cz, const float lo[3], const float scale[3]) {
 	const float fx = (cx - lo[0]) * scale[0], fy = (cy - lo[1]) * scale[1], fz = (cz - lo[2]) * scale[2];

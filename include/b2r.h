@@ -58,9 +58,13 @@ enum {
 	                                     * formula (BVH.hpp:250-286: the last `active % 8` rays of each 16x16 tile's stream take the scalar tail;
 	                                     * stream order = stable counting sort by material, DataStreams.hpp:236-253). Results are then bit-identical
 	                                     * to the reference's own Renderer::Accumulate, at the price of one extra ranking kernel per bounce. */
-	B2R_FLAG_GPU_TREE = 1u << 8,       /* b2r_upload_scene builds the traversal tree ON THE GPU (Morton keys, radix sort, implicit balanced 4-ary topology, refit passes):
-	                                    * milliseconds instead of the host's SAH build, for edits that add or remove spheres; same results, ~3.5x the node visits
+	B2R_FLAG_GPU_TREE = 1u << 8,       /* b2r_upload_scene builds the traversal tree ON THE GPU (Hilbert keys, radix sort, implicit balanced 4-ary topology, refit passes):
+	                                    * milliseconds instead of the host's SAH build, for edits that add or remove spheres; same results, ~2x the node visits
 	                                    * of the SAH tree on C3's overlapping spheres. May be toggled with b2r_set_flags between uploads. */
+	B2R_FLAG_GPU_SAH = 1u << 10,       /* with B2R_FLAG_GPU_TREE: the device builds the SWEEP tree instead — the spheres stay in curve order and every node is a run of that
+	                                    * order, cut top-down where the surface-area heuristic along the curve is smallest (segmented scans + one atomic minimum per
+	                                    * run and round), opened 2 -> 4 wide like the host's collapse: ~1.1x the node visits of the host's SAH tree. A scene whose sweep
+	                                    * tree would be deeper than the traversal stack allows gets the packed tree. */
 	B2R_FLAG_GGX = 1u << 9,            /* the reference's `#define BRDF 1` build (Renderer.hpp:70,207-213): Closure<GGX> (DataStreams.hpp:184-219) from the materials'
 	                                    * F0 and roughness instead of the Lambertian closure; gloss_decay_table (never declared by the reference) is all zeros and
 	                                    * Closure<GGX>::pdf returns 0 as it does there. Not combinable with B2R_FLAG_REFERENCE_EXACT. */

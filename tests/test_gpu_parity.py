@@ -8,6 +8,7 @@ divergent pixels reported (asserted small); converged image RMSE < 1e-3. The bru
 import hashlib
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -938,6 +939,42 @@ def test_gpu_built_tree_equals_host_twin_and_brute_force(n, hostcheck):
     wide2, _ = r.wide_nodes(); s_wide, _ = s.wide_nodes()
     assert r.buckets_host().tobytes() == got.tobytes() and wide2.shape == s_wide.shape
     r.close(); b.close(); s.close()
+
+
+@pytest.mark.parametrize("n", [2, 5, 6, 17, 700, 20000])
+def test_gpu_sweep_tree_equals_host_twin_and_sah_tree_frame(n):
+    """B2R_FLAG_GPU_TREE | B2R_FLAG_GPU_SAH: the device cuts the curve order top-down where the surface-area heuristic along the curve is
+    smallest (k_sweep_*: segmented scans, an atomic minimum per run and round, one 4-byte read-back per level). The device tree equals the host
+    twin build_sweep_tree bit for bit, and the frame rendered through it the default SAH tree's (tests/gpucheck/sweep_tree_check.py)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "gpucheck"))
+    import sweep_tree_check
+    assert sweep_tree_check.check(n)
+
+
+def test_gpu_sweep_tree_falls_back_to_the_packed_tree_when_too_deep(hostcheck):
+    """A hundred copies of one sphere: every cut of that run costs the same, the first is taken, so the sweep tree peels them off one by one
+    and would be deeper than the traversal stack allows (the host twin gives up); the upload links the packed tree instead (device tree ==
+    packed twin), the frame equals brute force, and the next scene gets its sweep tree again."""
+    import ctypes as C
+    sc = scenes.Scene(scenes.default_scene()); d = sc["geometry"]
+    sc["geometry"] = np.ascontiguousarray(np.concatenate([d, np.repeat(d[3:4], 100)])); n = len(sc["geometry"])
+    flags = b2r.FLAG_FORCE_BVH | b2r.FLAG_GPU_TREE | b2r.FLAG_GPU_SAH
+    r = b2r.Renderer(sc, 96, 64, max_bounces=4, buckets=2, flags=flags); r.Accumulate(2)
+    wide, ms = r.wide_nodes(); obox = r.origin_box(); prims = np.ascontiguousarray(r.scene.prims)
+    nw = C.c_uint32(0); m2 = C.c_uint32(0)
+    assert hostcheck.hc_sweep_tree(C.c_void_p(prims.ctypes.data), n, C.c_void_p(obox.ctypes.data), None, C.byref(nw), C.byref(m2)) == 1
+    twin = np.zeros_like(wide)
+    hostcheck.hc_packed_tree(C.c_void_p(prims.ctypes.data), n, C.c_void_p(obox.ctypes.data), C.c_void_p(twin.ctypes.data), C.byref(nw), C.byref(m2))
+    assert nw.value == len(wide) and m2.value == ms and wide.tobytes() == twin.tobytes()
+    b = b2r.Renderer(sc, 96, 64, max_bounces=4, buckets=2, flags=b2r.FLAG_FORCE_BRUTE); b.Accumulate(2)
+    assert r.buckets_host().tobytes() == b.buckets_host().tobytes()
+    sc2 = scenes.random_scene(300, light_every=20)
+    r.SetScene(sc2); r.ResetAccumulator(); r.Accumulate(2); b.SetScene(sc2); b.ResetAccumulator(); b.Accumulate(2)
+    assert r.buckets_host().tobytes() == b.buckets_host().tobytes()
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "gpucheck"))
+    import sweep_tree_check
+    assert len(r.wide_nodes()[0]) == sweep_tree_check.twin_nodes(np.ascontiguousarray(r.scene.prims), r.origin_box())
+    r.close(); b.close()
 
 
 def test_packet_traversal_of_camera_rays_equals_per_lane_walks():

@@ -293,3 +293,7 @@ def test_sweep_tree_gives_up_on_a_tree_deeper_than_the_stack(hostcheck):
     assert hostcheck.hc_sweep_tree(vp(geo), n, None, None, C.byref(nw), C.byref(ms)) == 1
     hostcheck.hc_packed_tree(vp(geo), n, None, None, C.byref(nw), C.byref(ms))
     assert ms.value + 3 <= 64
+    # the same with copies of one sphere: every cut of the run costs the same and the first one is taken
+    d = scenes.default_scene()["geometry"]; geo = np.ascontiguousarray(np.concatenate([d, np.repeat(d[3:4], 100)]), dtype=scenes.SPHERE_DTYPE)
+    assert hostcheck.hc_sweep_tree(vp(geo), len(geo), None, None, C.byref(nw), C.byref(ms)) == 1
+    assert hostcheck.hc_sweep_tree(vp(np.ascontiguousarray(geo[:40])), 40, None, None, C.byref(nw), C.byref(ms)) == 0 and ms.value + 3 <= 64
