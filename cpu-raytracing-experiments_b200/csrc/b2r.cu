@@ -581,24 +581,21 @@ int sweep_build(b2r_ctx* c, const uint32_t* order, uint32_t n, bool* built) {
 	cudaStream_t st = c->scene_st;
 	const size_t cap = n / 2u + 1u;  // runs of two or more spheres on one level
 	size_t t_scan = 0, t_sum = 0;
-	CU(cub::DeviceScan::InclusiveScan(nullptr, t_scan, static_cast<SweepItem*>(nullptr), static_cast<SweepItem*>(nullptr), SweepJoin(), static_cast<int>(n), st));
+	if (n > 0x3fffffffu) return fail(B2R_ERR_ARG, "sweep build: too many spheres");
+	CU(cub::DeviceScan::InclusiveScan(nullptr, t_scan, static_cast<SweepItem*>(nullptr), static_cast<SweepItem*>(nullptr), SweepJoin(), static_cast<int>(2u * n), st));
 	CU(cub::DeviceScan::ExclusiveSum(nullptr, t_sum, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), static_cast<int>(cap + 1u), st));
 	size_t t_cub = t_scan > t_sum ? t_scan : t_sum;
 	size_t off = 0; auto take = [&](size_t bytes) { const size_t at = off; off += (bytes + 255u) & ~static_cast<size_t>(255u); return at; };
-	const size_t o_box = take(n * sizeof(SweepItem)), o_fwd = take(n * sizeof(SweepItem)), o_bwd = take(n * sizeof(SweepItem)), o_cut = take(n * sizeof(unsigned long long)),
-	             o_area = take(n * sizeof(float)), o_head = take(n * sizeof(uint32_t)), o_run0 = take(cap * sizeof(SweepRun)), o_run1 = take(cap * sizeof(SweepRun)),
-	             o_kids = take(cap * sizeof(SweepKids)), o_inner = take((cap + 1u) * sizeof(uint32_t)), o_before = take((cap + 1u) * sizeof(uint32_t)), o_cub = take(t_cub);
+	const size_t o_box = take(n * sizeof(SweepItem)), o_items = take(2u * static_cast<size_t>(n) * sizeof(SweepItem)), o_cut = take(n * sizeof(unsigned long long)),
+	             o_area = take(n * sizeof(float)), o_head = take(n * sizeof(uint32_t)), o_kids0 = take(cap * sizeof(SweepKids)), o_kids1 = take(cap * sizeof(SweepKids)), o_inner = take((cap + 1u) * sizeof(uint32_t)), o_before = take((cap + 1u) * sizeof(uint32_t)), o_cub = take(t_cub);
 	int rc; if ((rc = dev_reserve(&c->d_sweep, &c->cap_sweep, off))) return rc;
 	uint8_t* base = c->d_sweep;
-	SweepItem *box = reinterpret_cast<SweepItem*>(base + o_box), *fwd = reinterpret_cast<SweepItem*>(base + o_fwd), *bwd = reinterpret_cast<SweepItem*>(base + o_bwd);
+	SweepItem *box = reinterpret_cast<SweepItem*>(base + o_box), *items = reinterpret_cast<SweepItem*>(base + o_items);
 	unsigned long long* cut_of = reinterpret_cast<unsigned long long*>(base + o_cut); float* area_of = reinterpret_cast<float*>(base + o_area); uint32_t* head = reinterpret_cast<uint32_t*>(base + o_head);
-	SweepRun* runs[2] = {reinterpret_cast<SweepRun*>(base + o_run0), reinterpret_cast<SweepRun*>(base + o_run1)};
-	SweepKids* kids = reinterpret_cast<SweepKids*>(base + o_kids); uint32_t *inner = reinterpret_cast<uint32_t*>(base + o_inner), *before = reinterpret_cast<uint32_t*>(base + o_before);
+	SweepKids* kids[2] = {reinterpret_cast<SweepKids*>(base + o_kids0), reinterpret_cast<SweepKids*>(base + o_kids1)}; uint32_t *inner = reinterpret_cast<uint32_t*>(base + o_inner), *before = reinterpret_cast<uint32_t*>(base + o_before);
 	void* cub_tmp = base + o_cub;
 	auto grid = [](uint32_t threads) { return (threads + kBlock - 1u) / kBlock; };
-	k_sweep_boxes<<<grid(n), kBlock, 0, st>>>(c->d_prims, order, n, box, head);
-	const SweepRun root{0u, n};
-	CU(cudaMemcpyAsync(runs[0], &root, sizeof root, cudaMemcpyHostToDevice, st)); CU(cudaStreamSynchronize(st));  // (`root` is a local)
+	k_sweep_boxes<<<grid(n), kBlock, 0, st>>>(c->d_prims, order, n, box, head, kids[0]);
 	c->launches++;
 	std::vector<uint32_t> lf(1, 0u);
 	uint32_t m = 1u; int cur = 0;
@@ -607,21 +604,17 @@ int sweep_build(b2r_ctx* c, const uint32_t* order, uint32_t n, bool* built) {
 		const uint32_t first = lf.back(), child_first = first + m;
 		if (child_first > n) return fail(B2R_ERR_BVH, "sweep build: more nodes than spheres");
 		lf.push_back(child_first);
-		k_sweep_begin<<<grid(m), kBlock, 0, st>>>(runs[cur], m, kids);
 		for (int round = 0; round < 3; round++) {
-			k_sweep_items<<<grid(n), kBlock, 0, st>>>(box, head, n, fwd, bwd, cut_of);
+			k_sweep_items<<<grid(n), kBlock, 0, st>>>(box, head, n, items, cut_of);
 			size_t t = t_cub;
-			CU(cub::DeviceScan::InclusiveScan(cub_tmp, t, fwd, fwd, SweepJoin(), static_cast<int>(n), st));
-			t = t_cub;
-			CU(cub::DeviceScan::InclusiveScan(cub_tmp, t, bwd, bwd, SweepJoin(), static_cast<int>(n), st));
-			k_sweep_cost<<<grid(n), kBlock, 0, st>>>(fwd, bwd, head, n, cut_of, area_of);
-			k_sweep_open<<<grid(m), kBlock, 0, st>>>(kids, m, cut_of, area_of, head);
+			CU(cub::DeviceScan::InclusiveScan(cub_tmp, t, items, items, SweepJoin(), static_cast<int>(2u * n), st));
+			k_sweep_cost<<<grid(n), kBlock, 0, st>>>(items, head, n, cut_of, area_of);
+			k_sweep_open<<<grid(m + 1u), kBlock, 0, st>>>(kids[cur], m, cut_of, area_of, head, round == 2 ? inner : nullptr);
 		}
-		k_sweep_count<<<grid(m + 1u), kBlock, 0, st>>>(kids, m, inner);
 		size_t t = t_cub;
 		CU(cub::DeviceScan::ExclusiveSum(cub_tmp, t, inner, before, static_cast<int>(m + 1u), st));
-		k_sweep_emit<<<grid(m), kBlock, 0, st>>>(kids, m, before, order, reinterpret_cast<float4*>(c->d_wide), first, child_first, runs[cur ^ 1]);
-		c->launches += 12;
+		k_sweep_emit<<<grid(m), kBlock, 0, st>>>(kids[cur], m, before, order, reinterpret_cast<float4*>(c->d_wide), first, child_first, kids[cur ^ 1]);
+		c->launches += 10;
 		uint32_t total = 0u;
 		CU(cudaMemcpyAsync(&total, before + m, sizeof total, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st));
 		CU(cudaGetLastError());

@@ -1107,20 +1107,23 @@ __global__ void __launch_bounds__(kBlock) k_packed_links(float4* __restrict__ wi
 }
 // ---- sweep build (B2R_FLAG_GPU_TREE | B2R_FLAG_GPU_SAH; host twin build_sweep_tree, shared arithmetic b2r_shade.h sweep_*). The spheres stay
 // in curve order (the radix sort above); `head[p]` says that position p starts a run. One opening round = k_sweep_items (every position's
-// box with the run bookkeeping, forwards and backwards) -> two in-place segmented inclusive scans (cub::DeviceScan, operator sweep_join:
-// fwd[p] = box of [run start, p], bwd[n-1-p] = box of [p, run end)) -> k_sweep_cost (every possible cut of every run costed, the cheapest
-// filed under the run's start with one atomic minimum per warp or lane) -> k_sweep_open (one thread per node of the level: cut the run
-// with the largest box). Three rounds make a node's four runs; k_sweep_count / an exclusive sum / k_sweep_emit then write the level's
-// links and the next level's nodes. The host reads one count per level (how many nodes the next level has).
-struct SweepRun { uint32_t a, b; };
-__global__ void __launch_bounds__(kBlock) k_sweep_boxes(const float4* __restrict__ prims, const uint32_t* __restrict__ order, const uint32_t n, SweepItem* __restrict__ box, uint32_t* __restrict__ head) {
+// box with the run bookkeeping, forwards in items[0, n) and backwards in items[n, 2n)) -> ONE in-place segmented inclusive scan over the 2n
+// items (cub::DeviceScan, operator sweep_join; the backward half starts with a run end, i.e. with a segment head: fwd[p] = box of
+// [run start, p], bwd[n-1-p] = box of [p, run end)) -> k_sweep_cost (every possible cut of every run costed, the cheapest filed under the
+// run's start with one atomic minimum per warp or lane) -> k_sweep_open (one thread per node of the level: cut the run with the largest
+// box; the third round also counts the node's runs of two or more spheres). Three rounds make a node's four runs; an exclusive sum of the
+// counts and k_sweep_emit then write the level's links and the next level's nodes (18 launches per level). The host reads one count per
+// level (how many nodes the next level has).
+__global__ void __launch_bounds__(kBlock) k_sweep_boxes(const float4* __restrict__ prims, const uint32_t* __restrict__ order, const uint32_t n, SweepItem* __restrict__ box, uint32_t* __restrict__ head, SweepKids* __restrict__ root) {
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= n) return;
 	SweepItem it; sweep_sphere_box(prims[order[p]], &it);
 	box[p] = it; head[p] = p == 0u ? 1u : 0u;
+	if (p == 0u) { SweepKids K; for (int k = 0; k < 4; k++) { K.a[k] = 0u; K.b[k] = 0u; } K.b[0] = n; K.n = 1u; *root = K; }   // the root node: one run, everything
 }
-__global__ void __launch_bounds__(kBlock) k_sweep_items(const SweepItem* __restrict__ box, const uint32_t* __restrict__ head, const uint32_t n, SweepItem* __restrict__ fwd, SweepItem* __restrict__ bwd,
+__global__ void __launch_bounds__(kBlock) k_sweep_items(const SweepItem* __restrict__ box, const uint32_t* __restrict__ head, const uint32_t n, SweepItem* __restrict__ items /*[2n]*/,
                                                         unsigned long long* __restrict__ cut_of) {
+	SweepItem *fwd = items, *bwd = items + n;
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= n) return;
 	SweepItem it = box[p];
@@ -1128,8 +1131,9 @@ __global__ void __launch_bounds__(kBlock) k_sweep_items(const SweepItem* __restr
 	it.pos = p + 1u; it.flag = (p + 1u == n || head[p + 1u] != 0u) ? 1u : 0u; bwd[n - 1u - p] = it;   // ... its last position its end, in the reversed array
 	cut_of[p] = ~0ull;
 }
-__global__ void __launch_bounds__(kBlock) k_sweep_cost(const SweepItem* __restrict__ fwd, const SweepItem* __restrict__ bwd, const uint32_t* __restrict__ head, const uint32_t n,
+__global__ void __launch_bounds__(kBlock) k_sweep_cost(const SweepItem* __restrict__ items /*[2n], scanned*/, const uint32_t* __restrict__ head, const uint32_t n,
                                                        unsigned long long* __restrict__ cut_of, float* __restrict__ area_of) {
+	const SweepItem *fwd = items, *bwd = items + n;
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	unsigned long long key = ~0ull; uint32_t start = 0xffffffffu;
 	if (p < n) {
@@ -1145,36 +1149,25 @@ __global__ void __launch_bounds__(kBlock) k_sweep_cost(const SweepItem* __restri
 		if (lane_id() == 0u && key != ~0ull) atomicMin(cut_of + s0, key);
 	} else if (key != ~0ull) atomicMin(cut_of + start, key);
 }
-__global__ void __launch_bounds__(kBlock) k_sweep_begin(const SweepRun* __restrict__ runs, const uint32_t m, SweepKids* __restrict__ kids) {
+__global__ void __launch_bounds__(kBlock) k_sweep_open(SweepKids* __restrict__ kids, const uint32_t m, const unsigned long long* __restrict__ cut_of, const float* __restrict__ area_of, uint32_t* __restrict__ head,
+                                                       uint32_t* __restrict__ inner /*last round of a level: [m + 1] counts of runs that become nodes; else null*/) {
 	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= m) return;
-	SweepKids K; for (int k = 0; k < 4; k++) { K.a[k] = 0u; K.b[k] = 0u; }
-	K.a[0] = runs[j].a; K.b[0] = runs[j].b; K.n = 1u;
-	kids[j] = K;
-}
-__global__ void __launch_bounds__(kBlock) k_sweep_open(SweepKids* __restrict__ kids, const uint32_t m, const unsigned long long* __restrict__ cut_of, const float* __restrict__ area_of, uint32_t* __restrict__ head) {
-	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= m) return;
+	if (j > m) return;
+	if (j == m) { if (inner) inner[m] = 0u; return; }   // the exclusive sum leaves the level's total there
 	SweepKids K = kids[j];
 	const uint32_t pos = sweep_open(K, cut_of, area_of);
 	if (pos) { kids[j] = K; head[pos] = 1u; }
-}
-__global__ void __launch_bounds__(kBlock) k_sweep_count(const SweepKids* __restrict__ kids, const uint32_t m, uint32_t* __restrict__ inner) {
-	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j > m) return;
-	uint32_t ni = 0u;
-	if (j < m) { const SweepKids K = kids[j]; for (uint32_t k = 0; k < K.n; k++) ni += (K.b[k] - K.a[k] >= 2u) ? 1u : 0u; }
-	inner[j] = ni;   // inner[m] = 0: the exclusive sum leaves the level's total there
+	if (inner) { uint32_t ni = 0u; for (uint32_t k = 0; k < K.n; k++) ni += (K.b[k] - K.a[k] >= 2u) ? 1u : 0u; inner[j] = ni; }
 }
 __global__ void __launch_bounds__(kBlock) k_sweep_emit(const SweepKids* __restrict__ kids, const uint32_t m, const uint32_t* __restrict__ inner_before, const uint32_t* __restrict__ order,
-                                                       float4* __restrict__ wide, const uint32_t level_first, const uint32_t child_level_first, SweepRun* __restrict__ next_runs) {
+                                                       float4* __restrict__ wide, const uint32_t level_first, const uint32_t child_level_first, SweepKids* __restrict__ next_kids) {
 	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= m) return;
 	const SweepKids K = kids[j];
 	int32_t link[4]; uint32_t ca[4], cb[4];
 	const uint32_t before = inner_before[j];
 	const uint32_t ni = sweep_links(K, order, child_level_first + before, link, ca, cb);
-	for (uint32_t i = 0; i < ni; i++) next_runs[before + i] = SweepRun{ca[i], cb[i]};
+	for (uint32_t i = 0; i < ni; i++) { SweepKids C; for (int k = 0; k < 4; k++) { C.a[k] = 0u; C.b[k] = 0u; } C.a[0] = ca[i]; C.b[0] = cb[i]; C.n = 1u; next_kids[before + i] = C; }   // the next level's nodes, one run each
 	float4* node = wide + static_cast<size_t>(level_first + j) * 8;
 	for (int k = 0; k < 4; k++) {
 		node[2 * k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);

@@ -44,9 +44,17 @@ def check(n, w=160, h=96, spp=2):
     same_tree = same_shape and wide.tobytes() == twin.tobytes()
     s = b2r.Renderer(sc, w, h, max_bounces=6, buckets=2, flags=b2r.FLAG_FORCE_BVH); s.Accumulate(spp)
     same_frame = r.buckets_host().tobytes() == s.buckets_host().tobytes()
-    print(f"n={n}: nodes {len(wide)} (twin {nw.value}) max_stack {ms} (twin {m2.value}) links_equal={same_links} tree_equal={same_tree} frame_equal_sah_tree={same_frame}", flush=True)
+    # a scene edit afterwards: the device-built tree is refitted (leaves matched to geometry lazily), the SAH-tree renderer gets a fresh upload
+    rs = np.random.RandomState(n); geo2 = np.ascontiguousarray(r.scene.geometry).copy()
+    geo2["position"] += (rs.uniform(-0.3, 0.3, (n, 3)) * np.sqrt(geo2["radius_sq"])[:, None]).astype(np.float32)
+    r.RefitScene(geo2); r.ResetAccumulator(); r.Accumulate(spp)
+    sc2 = dict(sc); sc2["geometry"] = geo2
+    s.SetScene(sc2); s.ResetAccumulator(); s.Accumulate(spp)
+    same_after_refit = r.buckets_host().tobytes() == s.buckets_host().tobytes()
+    print(f"n={n}: nodes {len(wide)} (twin {nw.value}) max_stack {ms} (twin {m2.value}) links_equal={same_links} tree_equal={same_tree} frame_equal_sah_tree={same_frame} "
+          f"frame_equal_after_refit={same_after_refit}", flush=True)
     r.close(); s.close()
-    return same_tree and same_frame
+    return same_tree and same_frame and same_after_refit
 
 
 def perf(n=100000, w=1920, h=1088, spp=4):
@@ -67,6 +75,8 @@ def perf(n=100000, w=1920, h=1088, spp=4):
 
 if __name__ == "__main__":
     ok = all([check(n) for n in (2, 3, 5, 6, 17, 700, 20000)])
+    if "--big" in sys.argv:
+        ok = check(1000000, 320, 192, 1) and ok
     if "--perf" in sys.argv:
         ok = check(100000, 320, 192, 1) and ok
         perf()
