@@ -580,17 +580,16 @@ int sweep_build(b2r_ctx* c, const uint32_t* order, uint32_t n, bool* built) {
 	*built = false;
 	cudaStream_t st = c->scene_st;
 	const size_t cap = n / 2u + 1u;  // runs of two or more spheres on one level
-	size_t t_scan = 0, t_sum = 0;
-	if (n > 0x3fffffffu) return fail(B2R_ERR_ARG, "sweep build: too many spheres");
-	CU(cub::DeviceScan::InclusiveScan(nullptr, t_scan, static_cast<SweepItem*>(nullptr), static_cast<SweepItem*>(nullptr), SweepJoin(), static_cast<int>(2u * n), st));
+	size_t t_sum = 0;
 	CU(cub::DeviceScan::ExclusiveSum(nullptr, t_sum, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), static_cast<int>(cap + 1u), st));
-	size_t t_cub = t_scan > t_sum ? t_scan : t_sum;
+	const size_t t_cub = t_sum;
+	const uint32_t tiles = (n + kSweepTile - 1u) / kSweepTile;
 	size_t off = 0; auto take = [&](size_t bytes) { const size_t at = off; off += (bytes + 255u) & ~static_cast<size_t>(255u); return at; };
-	const size_t o_box = take(n * sizeof(SweepItem)), o_items = take(2u * static_cast<size_t>(n) * sizeof(SweepItem)), o_cut = take(n * sizeof(unsigned long long)),
+	const size_t o_box = take(n * sizeof(SweepItem)), o_tiles = take(4u * static_cast<size_t>(tiles) * sizeof(SweepItem)), o_cut = take(n * sizeof(unsigned long long)),
 	             o_area = take(n * sizeof(float)), o_head = take(n * sizeof(uint32_t)), o_kids0 = take(cap * sizeof(SweepKids)), o_kids1 = take(cap * sizeof(SweepKids)), o_inner = take((cap + 1u) * sizeof(uint32_t)), o_before = take((cap + 1u) * sizeof(uint32_t)), o_cub = take(t_cub);
 	int rc; if ((rc = dev_reserve(&c->d_sweep, &c->cap_sweep, off))) return rc;
 	uint8_t* base = c->d_sweep;
-	SweepItem *box = reinterpret_cast<SweepItem*>(base + o_box), *items = reinterpret_cast<SweepItem*>(base + o_items);
+	SweepItem *box = reinterpret_cast<SweepItem*>(base + o_box), *tile_f = reinterpret_cast<SweepItem*>(base + o_tiles), *tile_b = tile_f + tiles, *carry_f = tile_b + tiles, *carry_b = carry_f + tiles;
 	unsigned long long* cut_of = reinterpret_cast<unsigned long long*>(base + o_cut); float* area_of = reinterpret_cast<float*>(base + o_area); uint32_t* head = reinterpret_cast<uint32_t*>(base + o_head);
 	SweepKids* kids[2] = {reinterpret_cast<SweepKids*>(base + o_kids0), reinterpret_cast<SweepKids*>(base + o_kids1)}; uint32_t *inner = reinterpret_cast<uint32_t*>(base + o_inner), *before = reinterpret_cast<uint32_t*>(base + o_before);
 	void* cub_tmp = base + o_cub;
@@ -605,16 +604,15 @@ int sweep_build(b2r_ctx* c, const uint32_t* order, uint32_t n, bool* built) {
 		if (child_first > n) return fail(B2R_ERR_BVH, "sweep build: more nodes than spheres");
 		lf.push_back(child_first);
 		for (int round = 0; round < 3; round++) {
-			k_sweep_items<<<grid(n), kBlock, 0, st>>>(box, head, n, items, cut_of);
-			size_t t = t_cub;
-			CU(cub::DeviceScan::InclusiveScan(cub_tmp, t, items, items, SweepJoin(), static_cast<int>(2u * n), st));
-			k_sweep_cost<<<grid(n), kBlock, 0, st>>>(items, head, n, cut_of, area_of);
+			k_sweep_tiles<<<tiles, kSweepTile, 0, st>>>(box, head, n, tile_f, tile_b, cut_of);
+			k_sweep_carry<<<2, kSweepTile, 0, st>>>(tile_f, tile_b, tiles, carry_f, carry_b);
+			k_sweep_cuts<<<tiles, kSweepTile, 0, st>>>(box, head, n, carry_f, carry_b, cut_of, area_of);
 			k_sweep_open<<<grid(m + 1u), kBlock, 0, st>>>(kids[cur], m, cut_of, area_of, head, round == 2 ? inner : nullptr);
 		}
 		size_t t = t_cub;
 		CU(cub::DeviceScan::ExclusiveSum(cub_tmp, t, inner, before, static_cast<int>(m + 1u), st));
 		k_sweep_emit<<<grid(m), kBlock, 0, st>>>(kids[cur], m, before, order, reinterpret_cast<float4*>(c->d_wide), first, child_first, kids[cur ^ 1]);
-		c->launches += 10;
+		c->launches += 13;
 		uint32_t total = 0u;
 		CU(cudaMemcpyAsync(&total, before + m, sizeof total, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st));
 		CU(cudaGetLastError());

@@ -1106,14 +1106,12 @@ __global__ void __launch_bounds__(kBlock) k_packed_links(float4* __restrict__ wi
 	else { slot[0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); slot[1] = make_float4(0.0f, 0.0f, __int_as_float(bottom ? ~static_cast<int32_t>(order[c]) : static_cast<int32_t>(lv.first[l + 1] + c)), 0.0f); }
 }
 // ---- sweep build (B2R_FLAG_GPU_TREE | B2R_FLAG_GPU_SAH; host twin build_sweep_tree, shared arithmetic b2r_shade.h sweep_*). The spheres stay
-// in curve order (the radix sort above); `head[p]` says that position p starts a run. One opening round = k_sweep_items (every position's
-// box with the run bookkeeping, forwards in items[0, n) and backwards in items[n, 2n)) -> ONE in-place segmented inclusive scan over the 2n
-// items (cub::DeviceScan, operator sweep_join; the backward half starts with a run end, i.e. with a segment head: fwd[p] = box of
-// [run start, p], bwd[n-1-p] = box of [p, run end)) -> k_sweep_cost (every possible cut of every run costed, the cheapest filed under the
-// run's start with one atomic minimum per warp or lane) -> k_sweep_open (one thread per node of the level: cut the run with the largest
-// box; the third round also counts the node's runs of two or more spheres). Three rounds make a node's four runs; an exclusive sum of the
-// counts and k_sweep_emit then write the level's links and the next level's nodes (18 launches per level). The host reads one count per
-// level (how many nodes the next level has).
+// in curve order (the radix sort above); `head[p]` says that position p starts a run. One opening round = two segmented inclusive scans of the
+// sphere boxes (operator sweep_join: fwd[p] = box of [run start, p], bwd[p] = box of [p, run end)), every possible cut of every run costed
+// from them and the cheapest filed under the run's start with an atomic minimum (k_sweep_tiles / k_sweep_carry / k_sweep_cuts below), then
+// k_sweep_open (one thread per node of the level: cut the run with the largest box; the third round also counts the node's runs of two or
+// more spheres). Three rounds make a node's four runs; an exclusive sum of the counts and k_sweep_emit then write the level's links and the
+// next level's nodes (15 launches per level). The host reads one count per level (how many nodes the next level has).
 __global__ void __launch_bounds__(kBlock) k_sweep_boxes(const float4* __restrict__ prims, const uint32_t* __restrict__ order, const uint32_t n, SweepItem* __restrict__ box, uint32_t* __restrict__ head, SweepKids* __restrict__ root) {
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= n) return;
@@ -1121,25 +1119,93 @@ __global__ void __launch_bounds__(kBlock) k_sweep_boxes(const float4* __restrict
 	box[p] = it; head[p] = p == 0u ? 1u : 0u;
 	if (p == 0u) { SweepKids K; for (int k = 0; k < 4; k++) { K.a[k] = 0u; K.b[k] = 0u; } K.b[0] = n; K.n = 1u; *root = K; }   // the root node: one run, everything
 }
-__global__ void __launch_bounds__(kBlock) k_sweep_items(const SweepItem* __restrict__ box, const uint32_t* __restrict__ head, const uint32_t n, SweepItem* __restrict__ items /*[2n]*/,
-                                                        unsigned long long* __restrict__ cut_of) {
-	SweepItem *fwd = items, *bwd = items + n;
-	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-	if (p >= n) return;
+// The segmented scans, hand-written for this item (a 24-byte box + run bookkeeping) and fused with what produces and consumes them, so that
+// no scanned array ever reaches memory: a tile is kSweepTile consecutive positions = one block.
+//   k_sweep_tiles  the join of each tile's items, forwards and backwards (2 x 32 B per tile); also resets cut_of
+//   k_sweep_carry  block 0 / block 1: exclusive scan of the tile joins from the left / from the right = what enters each tile
+//   k_sweep_cuts   each tile again: both inclusive scans in shared memory (warp shuffles, then the carried-in item), every cut costed,
+//                  the cheapest of a run filed under its first position
+// (cub::DeviceScan over materialised items took 35 us per round at 100k spheres against 3 x ~5 us for these.)
+constexpr uint32_t kSweepTile = 256u;
+__device__ __forceinline__ SweepItem sweep_nothing() { SweepItem e; e.lo0 = e.lo1 = e.lo2 = FLT_MAX; e.hi0 = e.hi1 = e.hi2 = -FLT_MAX; e.pos = 0u; e.flag = 0u; return e; }   // past the end of the array: joins to nothing
+// position p as an item of the forward sequence (a run's first position is a segment head and carries the run's start) or of the backward
+// one (a run's last position is the head and carries the run's end)
+__device__ __forceinline__ SweepItem sweep_item(const SweepItem* __restrict__ box, const uint32_t* __restrict__ head, const uint32_t n, const uint32_t p, const bool backward) {
+	if (p >= n) return sweep_nothing();
 	SweepItem it = box[p];
-	it.pos = p; it.flag = head[p]; fwd[p] = it;                                            // a run's first position carries its start ...
-	it.pos = p + 1u; it.flag = (p + 1u == n || head[p + 1u] != 0u) ? 1u : 0u; bwd[n - 1u - p] = it;   // ... its last position its end, in the reversed array
-	cut_of[p] = ~0ull;
+	if (!backward) { it.pos = p; it.flag = head[p]; }
+	else { it.pos = p + 1u; it.flag = (p + 1u == n || head[p + 1u] != 0u) ? 1u : 0u; }
+	return it;
 }
-__global__ void __launch_bounds__(kBlock) k_sweep_cost(const SweepItem* __restrict__ items /*[2n], scanned*/, const uint32_t* __restrict__ head, const uint32_t n,
-                                                       unsigned long long* __restrict__ cut_of, float* __restrict__ area_of) {
-	const SweepItem *fwd = items, *bwd = items + n;
-	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ SweepItem sweep_shfl_up(const SweepItem& v, const int o) {
+	SweepItem r;
+	r.lo0 = __shfl_up_sync(0xffffffffu, v.lo0, o); r.lo1 = __shfl_up_sync(0xffffffffu, v.lo1, o); r.lo2 = __shfl_up_sync(0xffffffffu, v.lo2, o); r.pos = __shfl_up_sync(0xffffffffu, v.pos, o);
+	r.hi0 = __shfl_up_sync(0xffffffffu, v.hi0, o); r.hi1 = __shfl_up_sync(0xffffffffu, v.hi1, o); r.hi2 = __shfl_up_sync(0xffffffffu, v.hi2, o); r.flag = __shfl_up_sync(0xffffffffu, v.flag, o);
+	return r;
+}
+// inclusive scan (operator sweep_join) of one item per thread in thread order over a block of kSweepTile threads; s_warp: kSweepTile / 32 items.
+// Every thread must call it; *total (may be null) receives the join of all items in every thread.
+__device__ __forceinline__ SweepItem sweep_block_scan(SweepItem v, SweepItem* s_warp, SweepItem* total) {
+	const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const SweepItem u = sweep_shfl_up(v, o); if (lane >= static_cast<uint32_t>(o)) v = sweep_join(u, v); }
+	__syncthreads();                      // (s_warp may still be read by a previous call)
+	if (lane == 31u) s_warp[w] = v;
+	__syncthreads();
+	if (w > 0u) { SweepItem pre = s_warp[0]; for (uint32_t k = 1; k < w; k++) pre = sweep_join(pre, s_warp[k]); v = sweep_join(pre, v); }
+	if (total) { SweepItem t = s_warp[0]; for (uint32_t k = 1; k < kSweepTile / 32u; k++) t = sweep_join(t, s_warp[k]); *total = t; }
+	return v;
+}
+__global__ void __launch_bounds__(kSweepTile) k_sweep_tiles(const SweepItem* __restrict__ box, const uint32_t* __restrict__ head, const uint32_t n, SweepItem* __restrict__ tile_f, SweepItem* __restrict__ tile_b,
+                                                            unsigned long long* __restrict__ cut_of) {
+	__shared__ SweepItem s_warp[kSweepTile / 32u];
+	const uint32_t t0 = blockIdx.x * kSweepTile, i = threadIdx.x;
+	if (t0 + i < n) cut_of[t0 + i] = ~0ull;
+	SweepItem tf, tb;
+	sweep_block_scan(sweep_item(box, head, n, t0 + i, false), s_warp, &tf);
+	sweep_block_scan(sweep_item(box, head, n, t0 + (kSweepTile - 1u - i), true), s_warp, &tb);   // thread order = descending positions
+	if (i == 0u) { tile_f[blockIdx.x] = tf; tile_b[blockIdx.x] = tb; }
+}
+// carry_f[t] = join of tiles 0 .. t-1 in ascending order (t >= 1), carry_b[t] = join of tiles T-1 .. t+1 in descending order (t <= T-2)
+__global__ void __launch_bounds__(kSweepTile) k_sweep_carry(const SweepItem* __restrict__ tile_f, const SweepItem* __restrict__ tile_b, const uint32_t tiles, SweepItem* __restrict__ carry_f, SweepItem* __restrict__ carry_b) {
+	__shared__ SweepItem s_warp[kSweepTile / 32u];
+	__shared__ SweepItem s_part[kSweepTile];
+	const bool backward = blockIdx.x == 1u;
+	const SweepItem* in = backward ? tile_b : tile_f; SweepItem* out = backward ? carry_b : carry_f;
+	const uint32_t chunk = (tiles + kSweepTile - 1u) / kSweepTile, j0 = threadIdx.x * chunk;   // this thread's stretch of the sequence
+	auto tile_of = [&](uint32_t j) { return backward ? tiles - 1u - j : j; };
+	SweepItem mine = sweep_nothing(); bool any = false;
+	for (uint32_t j = j0; j < j0 + chunk && j < tiles; j++) { const SweepItem v = in[tile_of(j)]; mine = any ? sweep_join(mine, v) : v; any = true; }
+	s_part[threadIdx.x] = sweep_block_scan(mine, s_warp, nullptr);   // (stretches past the end hold `nothing` and come last)
+	__syncthreads();
+	SweepItem run = threadIdx.x ? s_part[threadIdx.x - 1u] : sweep_nothing(); bool have = threadIdx.x != 0u;
+	for (uint32_t j = j0; j < j0 + chunk && j < tiles; j++) {
+		if (have) out[tile_of(j)] = run;
+		const SweepItem v = in[tile_of(j)]; run = have ? sweep_join(run, v) : v; have = true;
+	}
+}
+__global__ void __launch_bounds__(kSweepTile) k_sweep_cuts(const SweepItem* __restrict__ box, const uint32_t* __restrict__ head, const uint32_t n, const SweepItem* __restrict__ carry_f, const SweepItem* __restrict__ carry_b,
+                                                           unsigned long long* __restrict__ cut_of, float* __restrict__ area_of) {
+	__shared__ SweepItem s_warp[kSweepTile / 32u];
+	__shared__ SweepItem s_f[kSweepTile], s_b[kSweepTile];   // by position within the tile: box of [run start, p] / of [p, run end)
+	const uint32_t tile = blockIdx.x, t0 = tile * kSweepTile, i = threadIdx.x, p = t0 + i;
+	{
+		SweepItem f = sweep_block_scan(sweep_item(box, head, n, p, false), s_warp, nullptr);
+		if (tile > 0u) f = sweep_join(carry_f[tile], f);
+		s_f[i] = f;
+		SweepItem b = sweep_block_scan(sweep_item(box, head, n, t0 + (kSweepTile - 1u - i), true), s_warp, nullptr);
+		if (tile + 1u < gridDim.x) b = sweep_join(carry_b[tile], b);
+		s_b[kSweepTile - 1u - i] = b;
+	}
+	__syncthreads();
 	unsigned long long key = ~0ull; uint32_t start = 0xffffffffu;
 	if (p < n) {
-		const SweepItem f = fwd[p], b = bwd[n - 1u - p];
+		const SweepItem f = s_f[i], b = s_b[i];
 		start = f.pos; const uint32_t end = b.pos;
-		if (head[p] == 0u) key = sweep_key(sweep_area(fwd[p - 1u]), p - start, sweep_area(b), end - p, p);   // cut in front of p: [start, p) | [p, end)
+		if (head[p] == 0u) {   // cut in front of p: [start, p) | [p, end); position 0 is a head, so p - 1 exists
+			const SweepItem left = i ? s_f[i - 1u] : carry_f[tile];
+			key = sweep_key(sweep_area(left), p - start, sweep_area(b), end - p, p);
+		}
 		if (p + 1u == end) area_of[start] = sweep_area(f);
 	}
 	// one atomic per warp while the whole warp sits in one run (the top of the tree), one per lane otherwise
