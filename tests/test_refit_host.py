@@ -297,3 +297,45 @@ def test_sweep_tree_gives_up_on_a_tree_deeper_than_the_stack(hostcheck):
     d = scenes.default_scene()["geometry"]; geo = np.ascontiguousarray(np.concatenate([d, np.repeat(d[3:4], 100)]), dtype=scenes.SPHERE_DTYPE)
     assert hostcheck.hc_sweep_tree(vp(geo), len(geo), None, None, C.byref(nw), C.byref(ms)) == 1
     assert hostcheck.hc_sweep_tree(vp(np.ascontiguousarray(geo[:40])), 40, None, None, C.byref(nw), C.byref(ms)) == 0 and ms.value + 3 <= 64
+
+
+def _odd_sphere_sets(rs):
+    """Sphere sets a scene editor can produce and a curve order dislikes: clusters, a line, coincident centres, a shell around everything,
+    points (radius 0), all in one cell, twins."""
+    def arr(pos, r):
+        g = np.zeros(len(pos), scenes.SPHERE_DTYPE); g["position"] = np.asarray(pos, np.float32); g["radius_sq"] = (np.asarray(r, np.float32) ** 2); return g
+    n = 600
+    c = rs.uniform(-50, 50, (6, 3)); yield "clusters", arr(c[rs.randint(0, 6, n)] + rs.normal(0, 0.4, (n, 3)), rs.uniform(0.01, 0.3, n))
+    t = np.linspace(0, 1, n)[:, None]; yield "line", arr(t * np.array([30.0, 20.0, -10.0]), rs.uniform(0.01, 0.2, n))
+    yield "coincident centres", arr(np.zeros((40, 3)) + 0.5, np.linspace(0.1, 3.0, 40))
+    yield "shell", arr(np.concatenate([rs.uniform(-5, 5, (n - 1, 3)), [[0, 0, 0]]]), np.concatenate([rs.uniform(0.05, 0.5, n - 1), [40.0]]))
+    yield "points", arr(rs.uniform(-5, 5, (n, 3)), np.where(rs.uniform(size=n) < 0.5, 0.0, 0.2))
+    yield "one cell", arr(1000.0 + rs.uniform(0, 1e-3, (50, 3)), rs.uniform(1e-4, 2e-4, 50))
+    g = arr(rs.uniform(-5, 5, (n // 2, 3)), rs.uniform(0.05, 0.5, n // 2)); yield "twins", np.concatenate([g, g[: n // 4], g])
+    yield "plane", arr(np.concatenate([rs.uniform(-20, 20, (n, 2)), np.zeros((n, 1))], 1), rs.uniform(0.05, 0.6, n))
+
+
+@pytest.mark.parametrize("builder", ["packed", "sweep"])
+def test_device_tree_twins_on_awkward_sphere_sets(hostcheck, builder):
+    """Both trees the GPU builds by itself, through their host twins, on sphere sets that stress a curve order (see _odd_sphere_sets): the tree
+    is valid (every sphere once, boxes conservative and tight), fits the traversal stack, and the closest hit through it equals brute force,
+    indices included; where the sweep tree would be too deep the twin says so (the library then links the packed tree)."""
+    rs = np.random.RandomState(11)
+    for name, prims in _odd_sphere_sets(rs):
+        prims = np.ascontiguousarray(prims, dtype=scenes.SPHERE_DTYPE); n = len(prims)
+        nw = C.c_uint32(0); ms = C.c_uint32(0)
+        build = hostcheck.hc_sweep_tree if builder == "sweep" else hostcheck.hc_packed_tree
+        rc = build(vp(prims), n, None, None, C.byref(nw), C.byref(ms))
+        if rc != 0:
+            assert builder == "sweep", name      # too deep: only the sweep tree can be
+            continue
+        wide = np.zeros((nw.value, 4, 8), np.float32)
+        build(vp(prims), n, None, vp(wide), C.byref(nw), C.byref(ms))
+        assert ms.value + 3 <= 64, name
+        check_contains(wide, prims)
+        rays = camera_rays(1500, rs, prims)
+        m = len(rays); st = np.zeros(m, np.uint32); bx = np.zeros(m, np.uint32); sp = np.zeros(m, np.uint32); pr = np.zeros(m, np.int32)
+        assert hostcheck.hc_trace_stats(None, 0xfffffffe if builder == "sweep" else 0xffffffff, vp(prims), n, vp(rays), m, vp(st), vp(bx), vp(sp), vp(pr)) == 0
+        bt = np.zeros(m, np.float32); bp = np.zeros(m, np.int32)
+        hostcheck.hc_closest_brute(vp(prims), n, vp(rays), m, vp(bt), vp(bp))
+        assert np.array_equal(bp, pr), name
