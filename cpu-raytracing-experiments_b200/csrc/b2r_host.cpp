@@ -493,6 +493,84 @@ bool build_sweep_tree(const b2r_sphere* prims, uint32_t n, WideBvh& out, const O
 	return true;
 }
 
+bool build_sweep3_tree(const b2r_sphere* prims, uint32_t n, WideBvh& out, const OriginBox* ob_in) {
+	if (n < 2u) { build_packed_tree(prims, n, out, ob_in); return true; }
+	out.nodes.clear(); out.prims.clear(); out.geom_of_prim.clear(); out.cost = 0.0;
+	sphere_bounds(prims, n, out.sphere_lo, out.sphere_hi);
+	const OriginBox ob = ob_in ? *ob_in : origin_box_rule(out.sphere_lo, out.sphere_hi, nullptr, 0);
+	std::vector<SweepItem> box(n);   // by sphere index
+	for (uint32_t i = 0; i < n; i++) sweep_sphere_box(make_float4(prims[i].position[0], prims[i].position[1], prims[i].position[2], prims[i].radius_sq), &box[i]);
+	std::vector<uint32_t> ord[3], tmp(n); std::vector<unsigned char> right(n, 0);
+	for (int ax = 0; ax < 3; ax++) {
+		ord[ax].resize(n); std::iota(ord[ax].begin(), ord[ax].end(), 0u);
+		std::stable_sort(ord[ax].begin(), ord[ax].end(), [&](uint32_t a, uint32_t b) { return float_order_key(prims[a].position[ax]) < float_order_key(prims[b].position[ax]); });  // == a stable radix sort by key
+	}
+	std::vector<unsigned long long> cut_of(n, ~0ull); std::vector<float> area_of(n, 0.0f); std::vector<SweepItem> suffix;
+	auto survey = [&](uint32_t a, uint32_t b) {
+		if (b - a < 2u) return;
+		suffix.resize(b - a);
+		unsigned long long best = ~0ull; SweepItem acc;
+		for (uint32_t ax = 0; ax < 3u; ax++) {
+			const uint32_t* o = ord[ax].data();
+			acc = box[o[b - 1]]; acc.flag = 0u; suffix[b - 1 - a] = acc;
+			for (uint32_t p = b - 1; p-- > a;) { SweepItem it = box[o[p]]; it.flag = 0u; acc = sweep_join(it, acc); suffix[p - a] = acc; }
+			acc = box[o[a]]; acc.flag = 0u;
+			for (uint32_t p = a + 1; p < b; p++) {
+				const unsigned long long key = sweep_key3(sweep_area(acc), p - a, sweep_area(suffix[p - a]), b - p, p, ax);
+				if (key < best) best = key;
+				SweepItem it = box[o[p]]; it.flag = 0u; acc = sweep_join(acc, it);
+			}
+		}
+		cut_of[a] = best; area_of[a] = sweep_area(acc);
+	};
+	struct Run { uint32_t a, b; };
+	std::vector<Run> cur(1, Run{0u, n}), next;
+	out.level_first.assign(1, 0u);
+	auto set_link = [](WideNode& w, int k, int32_t link) {
+		for (int j = 0; j < 8; j++) w.slot[k][j] = 0.0f;
+		if (link == kEmptyLink) w.slot[k][4] = w.slot[k][5] = w.slot[k][7] = -1.0e30f;
+		w.slot[k][6] = int_as_float(link);
+	};
+	while (!cur.empty()) {
+		if (out.level_first.size() > kSweepMaxLevels) return false;
+		const uint32_t child_level_first = out.level_first.back() + static_cast<uint32_t>(cur.size());
+		out.level_first.push_back(child_level_first);
+		next.clear();
+		for (const Run& r : cur) {
+			SweepKids K{}; K.a[0] = r.a; K.b[0] = r.b; K.n = 1u;
+			survey(r.a, r.b);
+			for (int round = 0; round < 3; round++) {
+				uint32_t ax = 0, a = 0, b = 0;
+				const uint32_t pos = sweep_open3(K, cut_of.data(), area_of.data(), &ax, &a, &b);
+				if (!pos) break;
+				// the cut run [a, b): the first pos - a spheres of the chosen axis' order go left; the other two orders are partitioned to match, stably
+				for (uint32_t p = a; p < b; p++) right[ord[ax][p]] = p >= pos ? 1 : 0;
+				for (uint32_t a2 = 0; a2 < 3u; a2++) {
+					if (a2 == ax) continue;
+					uint32_t l = a, rr = pos;
+					for (uint32_t p = a; p < b; p++) { const uint32_t id = ord[a2][p]; if (right[id]) tmp[rr++] = id; else tmp[l++] = id; }
+					std::copy(tmp.begin() + a, tmp.begin() + b, ord[a2].begin() + a);
+				}
+				survey(a, pos); survey(pos, b);
+			}
+			int32_t link[4]; uint32_t ca[4], cb[4];
+			const uint32_t ni = sweep_links(K, ord[0].data(), child_level_first + static_cast<uint32_t>(next.size()), link, ca, cb);
+			for (uint32_t i = 0; i < ni; i++) next.push_back(Run{ca[i], cb[i]});
+			WideNode w; for (int k = 0; k < 4; k++) set_link(w, k, link[k]);
+			out.nodes.push_back(w);
+		}
+		cur.swap(next);
+	}
+	const uint32_t levels = static_cast<uint32_t>(out.level_first.size()) - 1u;
+	out.depth = levels; out.max_stack = 3u * levels;
+	out.prims.resize(n);
+	for (uint32_t i = 0; i < n; i++) out.prims[i] = make_float4(prims[i].position[0], prims[i].position[1], prims[i].position[2], prims[i].radius_sq);
+	wide_fill_boxes(out, out.prims.data(), ob);
+	uint32_t node_bits = 1; while ((1ull << node_bits) < out.nodes.size()) node_bits++;
+	out.tn_bits = std::min(32u - node_bits, 29u);
+	return true;
+}
+
 void pack_scene(const b2r_sphere* prims, uint32_t n_prims, const b2r_material* materials, uint32_t n_mat,
                 const int32_t* light_geom_idx, uint32_t n_lights, const b2r_sphere* geometry, PackedScene& out) {
 	auto f4 = [](float x, float y, float z, float w) { float4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; };

@@ -62,6 +62,9 @@ void build_packed_tree(const b2r_sphere* prims, uint32_t n, WideBvh& out, const 
 // like flatten_bvh's collapse (b2r_shade.h: sweep_*). Host twin, bit for bit. Returns false (out unusable) when the tree would be deeper
 // than kSweepMaxLevels — the caller then builds the packed tree.
 bool build_sweep_tree(const b2r_sphere* prims, uint32_t n, WideBvh& out, const OriginBox* ob = nullptr);
+// The same with three orders instead of one curve (B2R_FLAG_GPU_SAH3): the spheres sorted by centre x, y and z, every cut the cheapest over all
+// three (a full-sweep surface-area-heuristic build, as the classic CPU builders do it), the two other orders partitioned to match. Host twin.
+bool build_sweep3_tree(const b2r_sphere* prims, uint32_t n, WideBvh& out, const OriginBox* ob = nullptr);
 // level sizes of the packed tree for n spheres, root level first (level_first has one more entry than there are levels)
 void packed_levels(uint32_t n, std::vector<uint32_t>& level_first);
 // (Re)compute every slot box of a flattened topology for the spheres `prims` and the origin box `ob` (what flatten_bvh ends with).

@@ -548,6 +548,23 @@ B2R_HD uint32_t sweep_links(const SweepKids& K, const uint32_t* order, uint32_t 
 	for (; s < 4; s++) link[s] = kEmptyLink;
 	return ni;
 }
+// ---- the three-axis variant (B2R_FLAG_GPU_SAH3): the same top-down sweep over three orders at once — the spheres sorted by centre x, y and z —
+// every run being the same index range [a, b) of all three; a cut is (axis, position): the first position - a spheres of that axis' order go left.
+B2R_HD uint32_t float_order_key(float f) { const uint32_t u = bits(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }  // unsigned order == float order
+B2R_HD unsigned long long sweep_key3(float area_l, uint32_t n_l, float area_r, uint32_t n_r, uint32_t pos, uint32_t axis) {   // cheapest cost, then lowest position, then lowest axis
+	const float cost = area_l * static_cast<float>(n_l) + area_r * static_cast<float>(n_r);
+	return (static_cast<unsigned long long>(bits(cost)) << 32) | (pos << 2) | axis;
+}
+B2R_HD uint32_t sweep_open3(SweepKids& K, const unsigned long long* cut_of, const float* area_of, uint32_t* axis, uint32_t* run_a, uint32_t* run_b) {
+	if (K.n >= 4u) return 0u;
+	int pick = -1; float best = -1.0f;
+	for (uint32_t k = 0; k < K.n; k++) if (K.b[k] - K.a[k] >= 2u) { const float ar = area_of[K.a[k]]; if (ar > best) { best = ar; pick = static_cast<int>(k); } }
+	if (pick < 0) return 0u;
+	const uint32_t low = static_cast<uint32_t>(cut_of[K.a[pick]] & 0xffffffffull), pos = low >> 2;
+	*axis = low & 3u; *run_a = K.a[pick]; *run_b = K.b[pick];
+	K.a[K.n] = pos; K.b[K.n] = K.b[pick]; K.b[pick] = pos; K.n++;
+	return pos;
+}
 constexpr uint32_t kSweepMaxLevels = 20u;  // 3 stack entries per level must fit kTraversalStack; a deeper tree falls back to the packed one
 
 B2R_HD void morton_scale(const float lo[3], const float hi[3], float scale[3]) { for (int k = 0; k < 3; k++) { const float e = hi[k] - lo[k]; scale[k] = e > 0.0f ? 1024.0f / e : 0.0f; } }

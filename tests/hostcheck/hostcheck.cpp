@@ -163,6 +163,13 @@ int hc_sweep_tree(const b2r_sphere* prims, uint32_t n, const float* box6, void* 
 	if (out) std::memcpy(out, w.nodes.data(), w.nodes.size() * sizeof(WideNode));
 	return 0;
 }
+int hc_sweep3_tree(const b2r_sphere* prims, uint32_t n, const float* box6, void* out, uint32_t* n_wide, uint32_t* max_stack) {
+	const OriginBox ob = origin_box_of(prims, n, box6, nullptr, 0);
+	WideBvh w; if (!build_sweep3_tree(prims, n, w, &ob)) return 1;
+	*n_wide = static_cast<uint32_t>(w.nodes.size()); *max_stack = w.max_stack;
+	if (out) std::memcpy(out, w.nodes.data(), w.nodes.size() * sizeof(WideNode));
+	return 0;
+}
 // the sort key of build_packed_tree / k_morton_keys (b2r_shade.h: morton_key) for sphere centres inside [lo, hi]
 int hc_curve_keys(const b2r_sphere* prims, uint32_t n, const float lo[3], const float hi[3], uint32_t* keys_out) {
 	std::vector<uint32_t> keys; morton_keys(prims, n, lo, hi, keys);
@@ -225,6 +232,7 @@ extern "C" int hc_trace_stats(const b2r_bvh_node* nodes, uint32_t n_nodes, const
 	float ro[6]; ray_origin_bounds(rays, n, ro);
 	const OriginBox ob = origin_box_of(prims, n_prims, nullptr, ro, 2);
 	if (n_nodes == 0xffffffffu) build_packed_tree(prims, n_prims, w, &ob);   // the packed tree the GPU builds by itself
+	else if (n_nodes == 0xfffffffdu) { if (!build_sweep3_tree(prims, n_prims, w, &ob)) return 1; }  // the three-axis sweep tree
 	else if (n_nodes == 0xfffffffeu) { if (!build_sweep_tree(prims, n_prims, w, &ob)) return 1; }  // the sweep tree the GPU builds by itself
 	else if (n_nodes == 0) { std::vector<b2r_bvh_node> tn; build_traversal_tree(prims, n_prims, tn); flatten_bvh(tn.data(), static_cast<uint32_t>(tn.size()), prims, n_prims, w, &ob); }
 	else flatten_bvh(nodes, n_nodes, prims, n_prims, w, &ob);
