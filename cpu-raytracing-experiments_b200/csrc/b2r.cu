@@ -5,6 +5,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -573,46 +574,87 @@ int refresh_side_scene(b2r_ctx* c, uint32_t sidx) {
 	return B2R_OK;
 }
 
-// B2R_FLAG_GPU_TREE | B2R_FLAG_GPU_SAH: links of the sweep tree over the spheres in curve order (`order` = the radix sort's output), written
-// into c->d_wide level by level (b2r_device.cuh k_sweep_*; host twin build_sweep_tree). One 4-byte read-back per level tells the host how
-// many nodes the next level has. *built stays false when the tree would be deeper than kSweepMaxLevels (the caller links the packed tree).
-int sweep_build(b2r_ctx* c, const uint32_t* order, uint32_t n, bool* built) {
+// B2R_FLAG_GPU_TREE | B2R_FLAG_GPU_SAH / B2R_FLAG_GPU_SAH3: links of the sweep tree, written into c->d_wide level by level (b2r_device.cuh
+// k_sweep_*; host twins build_sweep_tree / build_sweep3_tree). `curve_order` = the radix sort's output for the curve sweep (the spheres in
+// Hilbert order), null for the three-axis sweep (which sorts the spheres by centre x, y and z itself). One 4-byte read-back per level tells
+// the host how many nodes the next level has. *built stays false when the tree would be deeper than kSweepMaxLevels (the caller links the
+// packed tree).
+int sweep_build(b2r_ctx* c, const uint32_t* curve_order, uint32_t n, bool* built) {
 	*built = false;
+	const bool three = curve_order == nullptr;
 	cudaStream_t st = c->scene_st;
+	if (n > 0x3fffffffu) return fail(B2R_ERR_ARG, "sweep build: too many spheres");
 	const size_t cap = n / 2u + 1u;  // runs of two or more spheres on one level
-	size_t t_sum = 0;
+	const size_t n3 = three ? 3u * static_cast<size_t>(n) : 0u;
+	size_t t_sum = 0, t_sum3 = 0, t_sort = 0;
 	CU(cub::DeviceScan::ExclusiveSum(nullptr, t_sum, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), static_cast<int>(cap + 1u), st));
-	const size_t t_cub = t_sum;
+	if (three) {
+		CU(cub::DeviceScan::ExclusiveSum(nullptr, t_sum3, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), static_cast<int>(n3), st));
+		CU(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), static_cast<int>(n), 0, 32, st));
+	}
+	const size_t t_cub = std::max(t_sum, std::max(t_sum3, t_sort));
 	const uint32_t tiles = (n + kSweepTile - 1u) / kSweepTile;
 	size_t off = 0; auto take = [&](size_t bytes) { const size_t at = off; off += (bytes + 255u) & ~static_cast<size_t>(255u); return at; };
 	const size_t o_box = take(n * sizeof(SweepItem)), o_tiles = take(4u * static_cast<size_t>(tiles) * sizeof(SweepItem)), o_cut = take(n * sizeof(unsigned long long)),
-	             o_area = take(n * sizeof(float)), o_head = take(n * sizeof(uint32_t)), o_kids0 = take(cap * sizeof(SweepKids)), o_kids1 = take(cap * sizeof(SweepKids)), o_inner = take((cap + 1u) * sizeof(uint32_t)), o_before = take((cap + 1u) * sizeof(uint32_t)), o_cub = take(t_cub);
+	             o_area = take(n * sizeof(float)), o_head = take(n * sizeof(uint32_t)), o_kids0 = take(cap * sizeof(SweepKids)), o_kids1 = take(cap * sizeof(SweepKids)),
+	             o_inner = take((cap + 1u) * sizeof(uint32_t)), o_before = take((cap + 1u) * sizeof(uint32_t)), o_cub = take(t_cub),
+	             // three-axis sweep only: keys / orders (ping-pong) / per-position run start / per-run cut notes / per-sphere side / partition counts
+	             o_keys = take(n3 * 4u), o_keys2 = take(three ? n * 4u : 0u), o_ord0 = take(n3 * 4u), o_ord1 = take(n3 * 4u), o_start = take(three ? n * 4u : 0u), o_tag = take(three ? n * 4u : 0u),
+	             o_spos = take(three ? n * 4u : 0u), o_sax = take(three ? n * 4u : 0u), o_right = take(three ? n * 4u : 0u), o_left = take(n3 * 4u), o_lsum = take(n3 * 4u);
 	int rc; if ((rc = dev_reserve(&c->d_sweep, &c->cap_sweep, off))) return rc;
 	uint8_t* base = c->d_sweep;
+	auto u32 = [&](size_t o) { return reinterpret_cast<uint32_t*>(base + o); };
 	SweepItem *box = reinterpret_cast<SweepItem*>(base + o_box), *tile_f = reinterpret_cast<SweepItem*>(base + o_tiles), *tile_b = tile_f + tiles, *carry_f = tile_b + tiles, *carry_b = carry_f + tiles;
-	unsigned long long* cut_of = reinterpret_cast<unsigned long long*>(base + o_cut); float* area_of = reinterpret_cast<float*>(base + o_area); uint32_t* head = reinterpret_cast<uint32_t*>(base + o_head);
-	SweepKids* kids[2] = {reinterpret_cast<SweepKids*>(base + o_kids0), reinterpret_cast<SweepKids*>(base + o_kids1)}; uint32_t *inner = reinterpret_cast<uint32_t*>(base + o_inner), *before = reinterpret_cast<uint32_t*>(base + o_before);
+	unsigned long long* cut_of = reinterpret_cast<unsigned long long*>(base + o_cut); float* area_of = reinterpret_cast<float*>(base + o_area); uint32_t* head = u32(o_head);
+	SweepKids* kids[2] = {reinterpret_cast<SweepKids*>(base + o_kids0), reinterpret_cast<SweepKids*>(base + o_kids1)}; uint32_t *inner = u32(o_inner), *before = u32(o_before);
+	uint32_t *keys = u32(o_keys), *keys2 = u32(o_keys2), *ord[2] = {u32(o_ord0), u32(o_ord1)}, *start_of = u32(o_start), *split_tag = u32(o_tag), *split_pos = u32(o_spos), *split_axis = u32(o_sax),
+	         *right = u32(o_right), *goes_left = u32(o_left), *left_before = u32(o_lsum);
 	void* cub_tmp = base + o_cub;
-	auto grid = [](uint32_t threads) { return (threads + kBlock - 1u) / kBlock; };
-	k_sweep_boxes<<<grid(n), kBlock, 0, st>>>(c->d_prims, order, n, box, head, kids[0]);
+	auto grid = [](size_t threads) { return static_cast<uint32_t>((threads + kBlock - 1u) / kBlock); };
+	int oc = 0;  // which of ord[] holds the current orders
+	if (!three) k_sweep_boxes<<<grid(n), kBlock, 0, st>>>(c->d_prims, curve_order, n, box, head, kids[0]);
+	else {
+		k_sweep3_boxes<<<grid(n), kBlock, 0, st>>>(c->d_prims, n, box, keys, ord[1], head, split_tag, kids[0]);   // ord[1]: 0 .. n-1 three times
+		for (uint32_t ax = 0; ax < 3u; ax++) {   // stable: equal coordinates keep the sphere order
+			size_t t = t_cub;
+			CU(cub::DeviceRadixSort::SortPairs(cub_tmp, t, keys + ax * static_cast<size_t>(n), keys2, ord[1] + ax * static_cast<size_t>(n), ord[0] + ax * static_cast<size_t>(n), static_cast<int>(n), 0, 32, st));
+		}
+	}
 	c->launches++;
 	std::vector<uint32_t> lf(1, 0u);
-	uint32_t m = 1u; int cur = 0;
+	uint32_t m = 1u, tag = 0u; int cur = 0;
 	while (m) {
 		if (lf.size() > kSweepMaxLevels) return B2R_OK;
 		const uint32_t first = lf.back(), child_first = first + m;
 		if (child_first > n) return fail(B2R_ERR_BVH, "sweep build: more nodes than spheres");
 		lf.push_back(child_first);
 		for (int round = 0; round < 3; round++) {
-			k_sweep_tiles<<<tiles, kSweepTile, 0, st>>>(box, head, n, tile_f, tile_b, cut_of);
-			k_sweep_carry<<<2, kSweepTile, 0, st>>>(tile_f, tile_b, tiles, carry_f, carry_b);
-			k_sweep_cuts<<<tiles, kSweepTile, 0, st>>>(box, head, n, carry_f, carry_b, cut_of, area_of);
-			k_sweep_open<<<grid(m + 1u), kBlock, 0, st>>>(kids[cur], m, cut_of, area_of, head, round == 2 ? inner : nullptr);
+			if (!three) {
+				k_sweep_tiles<<<tiles, kSweepTile, 0, st>>>(box, nullptr, head, n, tile_f, tile_b, cut_of);
+				k_sweep_carry<<<2, kSweepTile, 0, st>>>(tile_f, tile_b, tiles, carry_f, carry_b);
+				k_sweep_cuts<<<tiles, kSweepTile, 0, st>>>(box, nullptr, head, n, carry_f, carry_b, cut_of, area_of, 0xffffffffu, nullptr);
+				k_sweep_open<<<grid(m + 1u), kBlock, 0, st>>>(kids[cur], m, cut_of, area_of, head, round == 2 ? inner : nullptr);
+				continue;
+			}
+			tag++;
+			for (uint32_t ax = 0; ax < 3u; ax++) {
+				const uint32_t* o = ord[oc] + ax * static_cast<size_t>(n);
+				k_sweep_tiles<<<tiles, kSweepTile, 0, st>>>(box, o, head, n, tile_f, tile_b, ax == 0u ? cut_of : nullptr);
+				k_sweep_carry<<<2, kSweepTile, 0, st>>>(tile_f, tile_b, tiles, carry_f, carry_b);
+				k_sweep_cuts<<<tiles, kSweepTile, 0, st>>>(box, o, head, n, carry_f, carry_b, cut_of, area_of, ax, ax == 0u ? start_of : nullptr);
+			}
+			k_sweep3_open<<<grid(m + 1u), kBlock, 0, st>>>(kids[cur], m, cut_of, area_of, head, split_tag, split_pos, split_axis, tag, round == 2 ? inner : nullptr);
+			k_sweep3_mark<<<grid(n), kBlock, 0, st>>>(ord[oc], n, start_of, split_tag, split_pos, split_axis, tag, right);
+			k_sweep3_flags<<<grid(n3), kBlock, 0, st>>>(ord[oc], n, start_of, split_tag, tag, right, goes_left);
+			size_t t = t_cub;
+			CU(cub::DeviceScan::ExclusiveSum(cub_tmp, t, goes_left, left_before, static_cast<int>(n3), st));
+			k_sweep3_scatter<<<grid(n3), kBlock, 0, st>>>(ord[oc], n, start_of, split_tag, split_pos, tag, right, left_before, ord[oc ^ 1]);
+			oc ^= 1;
 		}
 		size_t t = t_cub;
 		CU(cub::DeviceScan::ExclusiveSum(cub_tmp, t, inner, before, static_cast<int>(m + 1u), st));
-		k_sweep_emit<<<grid(m), kBlock, 0, st>>>(kids[cur], m, before, order, reinterpret_cast<float4*>(c->d_wide), first, child_first, kids[cur ^ 1]);
-		c->launches += 13;
+		k_sweep_emit<<<grid(m), kBlock, 0, st>>>(kids[cur], m, before, three ? ord[oc] : curve_order, reinterpret_cast<float4*>(c->d_wide), first, child_first, kids[cur ^ 1]);
+		c->launches += three ? 40u : 13u;
 		uint32_t total = 0u;
 		CU(cudaMemcpyAsync(&total, before + m, sizeof total, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st));
 		CU(cudaGetLastError());
@@ -847,7 +889,7 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 		c->n_wide = w.level_first.back();
 		uint32_t node_bits = 1; while ((1ull << node_bits) < c->n_wide) node_bits++;
 		w.tn_bits = 32u - node_bits < 29u ? 32u - node_bits : 29u;
-		if ((c->cfg.flags & B2R_FLAG_GPU_SAH) && n_prims >= 2u && n_prims > c->n_wide) c->n_wide = n_prims;  // the sweep tree: fewer nodes than spheres, how many is known once it is built (reserve for the bound)
+		if ((c->cfg.flags & (B2R_FLAG_GPU_SAH | B2R_FLAG_GPU_SAH3)) && n_prims >= 2u && n_prims > c->n_wide) c->n_wide = n_prims;  // the sweep tree: fewer nodes than spheres, how many is known once it is built (reserve for the bound)
 		c->wide_key = 0; c->wide_blob.clear(); c->have_wide = true; c->gpu_tree = true;
 		c->lazy_prims.assign(prims, prims + n_prims); c->lazy_geom.assign(geometry, geometry + n_geom);  // matched by value only if a refit ever asks
 	} else {
@@ -921,7 +963,7 @@ int b2r_upload_scene(b2r_ctx* c, const b2r_sphere* prims, const b2r_bvh_node* no
 		if ((rc = dev_reserve(&c->d_sort_tmp, &c->cap_sort_tmp, tmp))) return rc;
 		CU(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, tmp, c->d_mkey[0], c->d_mkey[1], c->d_midx[0], c->d_midx[1], static_cast<int>(n_prims), 0, 30, c->scene_st));
 		bool swept = false;
-		if ((c->cfg.flags & B2R_FLAG_GPU_SAH) && n_prims >= 2u && (rc = sweep_build(c, c->d_midx[1], n_prims, &swept))) return rc;
+		if ((c->cfg.flags & (B2R_FLAG_GPU_SAH | B2R_FLAG_GPU_SAH3)) && n_prims >= 2u && (rc = sweep_build(c, (c->cfg.flags & B2R_FLAG_GPU_SAH3) ? nullptr : c->d_midx[1], n_prims, &swept))) return rc;
 		if (!swept) {
 			c->n_wide = c->wide_host.level_first.back();  // (the packed shape worked out above)
 			PackedLevels lv{}; lv.levels = c->wide_host.depth;

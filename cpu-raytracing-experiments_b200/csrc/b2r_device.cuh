@@ -1130,9 +1130,10 @@ constexpr uint32_t kSweepTile = 256u;
 __device__ __forceinline__ SweepItem sweep_nothing() { SweepItem e; e.lo0 = e.lo1 = e.lo2 = FLT_MAX; e.hi0 = e.hi1 = e.hi2 = -FLT_MAX; e.pos = 0u; e.flag = 0u; return e; }   // past the end of the array: joins to nothing
 // position p as an item of the forward sequence (a run's first position is a segment head and carries the run's start) or of the backward
 // one (a run's last position is the head and carries the run's end)
-__device__ __forceinline__ SweepItem sweep_item(const SweepItem* __restrict__ box, const uint32_t* __restrict__ head, const uint32_t n, const uint32_t p, const bool backward) {
+// (`order`: null = the boxes are stored in position order (curve sweep); else position p holds sphere order[p] (three-axis sweep: one order per axis))
+__device__ __forceinline__ SweepItem sweep_item(const SweepItem* __restrict__ box, const uint32_t* __restrict__ order, const uint32_t* __restrict__ head, const uint32_t n, const uint32_t p, const bool backward) {
 	if (p >= n) return sweep_nothing();
-	SweepItem it = box[p];
+	SweepItem it = box[order ? order[p] : p];
 	if (!backward) { it.pos = p; it.flag = head[p]; }
 	else { it.pos = p + 1u; it.flag = (p + 1u == n || head[p + 1u] != 0u) ? 1u : 0u; }
 	return it;
@@ -1156,14 +1157,14 @@ __device__ __forceinline__ SweepItem sweep_block_scan(SweepItem v, SweepItem* s_
 	if (total) { SweepItem t = s_warp[0]; for (uint32_t k = 1; k < kSweepTile / 32u; k++) t = sweep_join(t, s_warp[k]); *total = t; }
 	return v;
 }
-__global__ void __launch_bounds__(kSweepTile) k_sweep_tiles(const SweepItem* __restrict__ box, const uint32_t* __restrict__ head, const uint32_t n, SweepItem* __restrict__ tile_f, SweepItem* __restrict__ tile_b,
-                                                            unsigned long long* __restrict__ cut_of) {
+__global__ void __launch_bounds__(kSweepTile) k_sweep_tiles(const SweepItem* __restrict__ box, const uint32_t* __restrict__ order, const uint32_t* __restrict__ head, const uint32_t n, SweepItem* __restrict__ tile_f, SweepItem* __restrict__ tile_b,
+                                                            unsigned long long* __restrict__ cut_of /*null: keep (a later axis of the same round)*/) {
 	__shared__ SweepItem s_warp[kSweepTile / 32u];
 	const uint32_t t0 = blockIdx.x * kSweepTile, i = threadIdx.x;
-	if (t0 + i < n) cut_of[t0 + i] = ~0ull;
+	if (cut_of && t0 + i < n) cut_of[t0 + i] = ~0ull;
 	SweepItem tf, tb;
-	sweep_block_scan(sweep_item(box, head, n, t0 + i, false), s_warp, &tf);
-	sweep_block_scan(sweep_item(box, head, n, t0 + (kSweepTile - 1u - i), true), s_warp, &tb);   // thread order = descending positions
+	sweep_block_scan(sweep_item(box, order, head, n, t0 + i, false), s_warp, &tf);
+	sweep_block_scan(sweep_item(box, order, head, n, t0 + (kSweepTile - 1u - i), true), s_warp, &tb);   // thread order = descending positions
 	if (i == 0u) { tile_f[blockIdx.x] = tf; tile_b[blockIdx.x] = tb; }
 }
 // carry_f[t] = join of tiles 0 .. t-1 in ascending order (t >= 1), carry_b[t] = join of tiles T-1 .. t+1 in descending order (t <= T-2)
@@ -1184,16 +1185,16 @@ __global__ void __launch_bounds__(kSweepTile) k_sweep_carry(const SweepItem* __r
 		const SweepItem v = in[tile_of(j)]; run = have ? sweep_join(run, v) : v; have = true;
 	}
 }
-__global__ void __launch_bounds__(kSweepTile) k_sweep_cuts(const SweepItem* __restrict__ box, const uint32_t* __restrict__ head, const uint32_t n, const SweepItem* __restrict__ carry_f, const SweepItem* __restrict__ carry_b,
-                                                           unsigned long long* __restrict__ cut_of, float* __restrict__ area_of) {
+__global__ void __launch_bounds__(kSweepTile) k_sweep_cuts(const SweepItem* __restrict__ box, const uint32_t* __restrict__ order, const uint32_t* __restrict__ head, const uint32_t n, const SweepItem* __restrict__ carry_f, const SweepItem* __restrict__ carry_b,
+                                                           unsigned long long* __restrict__ cut_of, float* __restrict__ area_of, const uint32_t axis /*0xffffffff: curve sweep (key = sweep_key)*/, uint32_t* __restrict__ start_of /*may be null*/) {
 	__shared__ SweepItem s_warp[kSweepTile / 32u];
 	__shared__ SweepItem s_f[kSweepTile], s_b[kSweepTile];   // by position within the tile: box of [run start, p] / of [p, run end)
 	const uint32_t tile = blockIdx.x, t0 = tile * kSweepTile, i = threadIdx.x, p = t0 + i;
 	{
-		SweepItem f = sweep_block_scan(sweep_item(box, head, n, p, false), s_warp, nullptr);
+		SweepItem f = sweep_block_scan(sweep_item(box, order, head, n, p, false), s_warp, nullptr);
 		if (tile > 0u) f = sweep_join(carry_f[tile], f);
 		s_f[i] = f;
-		SweepItem b = sweep_block_scan(sweep_item(box, head, n, t0 + (kSweepTile - 1u - i), true), s_warp, nullptr);
+		SweepItem b = sweep_block_scan(sweep_item(box, order, head, n, t0 + (kSweepTile - 1u - i), true), s_warp, nullptr);
 		if (tile + 1u < gridDim.x) b = sweep_join(carry_b[tile], b);
 		s_b[kSweepTile - 1u - i] = b;
 	}
@@ -1204,9 +1205,10 @@ __global__ void __launch_bounds__(kSweepTile) k_sweep_cuts(const SweepItem* __re
 		start = f.pos; const uint32_t end = b.pos;
 		if (head[p] == 0u) {   // cut in front of p: [start, p) | [p, end); position 0 is a head, so p - 1 exists
 			const SweepItem left = i ? s_f[i - 1u] : carry_f[tile];
-			key = sweep_key(sweep_area(left), p - start, sweep_area(b), end - p, p);
+			key = axis == 0xffffffffu ? sweep_key(sweep_area(left), p - start, sweep_area(b), end - p, p) : sweep_key3(sweep_area(left), p - start, sweep_area(b), end - p, p, axis);
 		}
 		if (p + 1u == end) area_of[start] = sweep_area(f);
+		if (start_of) start_of[p] = start;
 	}
 	// one atomic per warp while the whole warp sits in one run (the top of the tree), one per lane otherwise
 	const uint32_t s0 = __shfl_sync(0xffffffffu, start, 0);
@@ -1239,6 +1241,60 @@ __global__ void __launch_bounds__(kBlock) k_sweep_emit(const SweepKids* __restri
 		node[2 * k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 		node[2 * k + 1] = link[k] == kEmptyLink ? make_float4(-1.0e30f, -1.0e30f, __int_as_float(kEmptyLink), -1.0e30f) : make_float4(0.0f, 0.0f, __int_as_float(link[k]), 0.0f);
 	}
+}
+// ---- three-axis sweep (B2R_FLAG_GPU_SAH3; host twin build_sweep3_tree): three orders of the spheres (sorted by centre x, y, z: ord[axis * n + p]),
+// every run the same index range of all three. A round surveys the runs once per axis (the kernels above with `order` and `axis`; the atomic
+// minimum then also picks the axis), k_sweep3_open cuts the largest run of every node and notes (tag, position, axis) under the run's start,
+// k_sweep3_mark says for every sphere of a cut run whether it goes right, and the three orders are partitioned to match, stably: an exclusive
+// sum over "goes left" flags of all 3n entries (CUB) gives every entry its place (k_sweep3_flags / k_sweep3_scatter).
+__global__ void __launch_bounds__(kBlock) k_sweep3_boxes(const float4* __restrict__ prims, const uint32_t n, SweepItem* __restrict__ box, uint32_t* __restrict__ keys /*[3n]*/, uint32_t* __restrict__ ids /*[3n]*/,
+                                                         uint32_t* __restrict__ head, uint32_t* __restrict__ split_tag, SweepKids* __restrict__ root) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float4 s = prims[i];
+	SweepItem it; sweep_sphere_box(s, &it); box[i] = it;
+	keys[i] = float_order_key(s.x); keys[n + i] = float_order_key(s.y); keys[2u * n + i] = float_order_key(s.z);
+	ids[i] = i; ids[n + i] = i; ids[2u * n + i] = i;
+	head[i] = i == 0u ? 1u : 0u; split_tag[i] = 0u;
+	if (i == 0u) { SweepKids K; for (int k = 0; k < 4; k++) { K.a[k] = 0u; K.b[k] = 0u; } K.b[0] = n; K.n = 1u; *root = K; }
+}
+__global__ void __launch_bounds__(kBlock) k_sweep3_open(SweepKids* __restrict__ kids, const uint32_t m, const unsigned long long* __restrict__ cut_of, const float* __restrict__ area_of, uint32_t* __restrict__ head,
+                                                        uint32_t* __restrict__ split_tag, uint32_t* __restrict__ split_pos, uint32_t* __restrict__ split_axis, const uint32_t tag, uint32_t* __restrict__ inner) {
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j > m) return;
+	if (j == m) { if (inner) inner[m] = 0u; return; }
+	SweepKids K = kids[j];
+	uint32_t axis = 0u, a = 0u, b = 0u;
+	const uint32_t pos = sweep_open3(K, cut_of, area_of, &axis, &a, &b);
+	if (pos) { kids[j] = K; head[pos] = 1u; split_tag[a] = tag; split_pos[a] = pos; split_axis[a] = axis; }
+	if (inner) { uint32_t ni = 0u; for (uint32_t k = 0; k < K.n; k++) ni += (K.b[k] - K.a[k] >= 2u) ? 1u : 0u; inner[j] = ni; }
+}
+__global__ void __launch_bounds__(kBlock) k_sweep3_mark(const uint32_t* __restrict__ ord, const uint32_t n, const uint32_t* __restrict__ start_of, const uint32_t* __restrict__ split_tag, const uint32_t* __restrict__ split_pos,
+                                                        const uint32_t* __restrict__ split_axis, const uint32_t tag, uint32_t* __restrict__ right) {
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n) return;
+	const uint32_t s = start_of[p];
+	if (split_tag[s] != tag) return;
+	right[ord[split_axis[s] * n + p]] = p >= split_pos[s] ? 1u : 0u;   // the first pos - start spheres of the chosen axis' order go left
+}
+__global__ void __launch_bounds__(kBlock) k_sweep3_flags(const uint32_t* __restrict__ ord, const uint32_t n, const uint32_t* __restrict__ start_of, const uint32_t* __restrict__ split_tag, const uint32_t tag,
+                                                         const uint32_t* __restrict__ right, uint32_t* __restrict__ goes_left /*[3n]*/) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= 3u * n) return;
+	const uint32_t p = t % n;
+	goes_left[t] = (split_tag[start_of[p]] == tag && right[ord[t]] == 0u) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(kBlock) k_sweep3_scatter(const uint32_t* __restrict__ ord, const uint32_t n, const uint32_t* __restrict__ start_of, const uint32_t* __restrict__ split_tag, const uint32_t* __restrict__ split_pos,
+                                                           const uint32_t tag, const uint32_t* __restrict__ right, const uint32_t* __restrict__ left_before /*[3n]: exclusive sum of goes_left*/, uint32_t* __restrict__ ord_out) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= 3u * n) return;
+	const uint32_t axis_base = (t / n) * n, p = t - axis_base, id = ord[t], s = start_of[p];
+	uint32_t dest = p;
+	if (split_tag[s] == tag) {
+		const uint32_t k = left_before[t] - left_before[axis_base + s];   // entries of this run in front of p that go left
+		dest = right[id] == 0u ? s + k : split_pos[s] + (p - s - k);
+	}
+	ord_out[axis_base + dest] = id;
 }
 // Sum of the inner-slot half areas (the quantity a refit is judged by: cost now / cost when the tree was built).
 __global__ void __launch_bounds__(kBlock) k_tree_cost(const float4* __restrict__ wide, const uint32_t n_nodes, double* __restrict__ out) {

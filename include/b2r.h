@@ -65,6 +65,9 @@ enum {
 	                                    * order, cut top-down where the surface-area heuristic along the curve is smallest (segmented scans + one atomic minimum per
 	                                    * run and round), opened 2 -> 4 wide like the host's collapse: ~1.1x the node visits of the host's SAH tree, built in ~1.2 ms of device time at 100k spheres. A scene whose sweep
 	                                    * tree would be deeper than the traversal stack allows gets the packed tree. */
+	B2R_FLAG_GPU_SAH3 = 1u << 11,      /* with B2R_FLAG_GPU_TREE (wins over B2R_FLAG_GPU_SAH): the three-axis sweep — the device keeps the spheres sorted by centre x, y and z, every
+	                                    * cut is the cheapest over all three orders (a full-sweep SAH build), the other two orders are partitioned to match: the node visits
+	                                    * of the host's SAH tree, built on the device. Same depth fall-back as B2R_FLAG_GPU_SAH. */
 	B2R_FLAG_GGX = 1u << 9,            /* the reference's `#define BRDF 1` build (Renderer.hpp:70,207-213): Closure<GGX> (DataStreams.hpp:184-219) from the materials'
 	                                    * F0 and roughness instead of the Lambertian closure; gloss_decay_table (never declared by the reference) is all zeros and
 	                                    * Closure<GGX>::pdf returns 0 as it does there. Not combinable with B2R_FLAG_REFERENCE_EXACT. */
