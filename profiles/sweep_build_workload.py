@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Workload for the ncu launch list of the device tree builds: C3's scene (N=100000), b2r_upload_scene with B2R_FLAG_GPU_TREE (packed tree)
-and with B2R_FLAG_GPU_TREE | B2R_FLAG_GPU_SAH (sweep tree), twice each (the first call allocates), one small frame after each. Prints host
+with B2R_FLAG_GPU_TREE | B2R_FLAG_GPU_SAH (curve sweep tree) and with B2R_FLAG_GPU_TREE | B2R_FLAG_GPU_SAH3 (three-axis sweep tree), b2r_create's upload + three more each, one small frame after each. Prints host
 wall-clock times (never under ncu for a reported number). numpy only: no torch import."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -9,7 +9,7 @@ import b2r, scenes
 
 n = int(os.environ.get("N", "100000"))
 ps = b2r.PreparedScene(scenes.random_scene(n), 320, 192)
-for name, flags in (("packed", b2r.FLAG_GPU_TREE), ("sweep", b2r.FLAG_GPU_TREE | b2r.FLAG_GPU_SAH)):
+for name, flags in (("packed", b2r.FLAG_GPU_TREE), ("sweep", b2r.FLAG_GPU_TREE | b2r.FLAG_GPU_SAH), ("sweep3", b2r.FLAG_GPU_TREE | b2r.FLAG_GPU_SAH3)):
     r = b2r.Renderer(ps, 320, 192, max_bounces=4, buckets=1, flags=b2r.FLAG_FORCE_BVH | flags); r.sync()
     ts = []
     for _ in range(3):

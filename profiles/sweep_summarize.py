@@ -10,13 +10,13 @@ with open(src) as f:
 starts = [i for i, x in enumerate(rows) if "k_morton_keys" in x[0]]
 out = ["ncu --metrics gpu__time_duration.sum --clock-control none, python profiles/sweep_build_workload.py (C3's scene, 100k spheres): per b2r_upload_scene call,",
        "launches and summed device time per kernel (cold-cache, serialised: shares, not absolutes). Calls 0-3: packed tree (B2R_FLAG_GPU_TREE; call 0 = b2r_create's",
-       "upload + origin-box refit), calls 4-7: sweep tree (| B2R_FLAG_GPU_SAH).", ""]
+       "upload + origin-box refit), calls 4-7: curve sweep tree (| B2R_FLAG_GPU_SAH), calls 8-11: three-axis sweep tree (| B2R_FLAG_GPU_SAH3).", ""]
 for k, a in enumerate(starts):
     b = starts[k + 1] if k + 1 < len(starts) else len(rows)
     agg = collections.OrderedDict()
     for name, v in rows[a:b]:
         short = re.sub(r"<.*", "", name.split("(")[0]).split("::")[-1]
-        if "Scan" in name: short = "cub::DeviceScan (exclusive sum of the run counts): " + short
+        if "Scan" in name: short = "cub::DeviceScan (exclusive sums: run counts, partition places): " + short
         if "Radix" in name: short = "cub::DeviceRadixSort: " + short
         d = agg.setdefault(short, [0, 0.0]); d[0] += 1; d[1] += v
     out.append(f"call {k}")

@@ -941,14 +941,16 @@ def test_gpu_built_tree_equals_host_twin_and_brute_force(n, hostcheck):
     r.close(); b.close(); s.close()
 
 
+@pytest.mark.parametrize("three", [False, True])
 @pytest.mark.parametrize("n", [2, 5, 6, 17, 700, 20000])
-def test_gpu_sweep_tree_equals_host_twin_and_sah_tree_frame(n):
+def test_gpu_sweep_tree_equals_host_twin_and_sah_tree_frame(n, three):
     """B2R_FLAG_GPU_TREE | B2R_FLAG_GPU_SAH: the device cuts the curve order top-down where the surface-area heuristic along the curve is
     smallest (k_sweep_*: segmented scans, an atomic minimum per run and round, one 4-byte read-back per level). The device tree equals the host
-    twin build_sweep_tree bit for bit, and the frame rendered through it the default SAH tree's (tests/gpucheck/sweep_tree_check.py)."""
+    twin build_sweep_tree bit for bit, and the frame rendered through it the default SAH tree's, also after a refit (tests/gpucheck/
+    sweep_tree_check.py). three: B2R_FLAG_GPU_SAH3, the same sweep over the x, y and z orders at once (k_sweep3_*; twin build_sweep3_tree)."""
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "gpucheck"))
     import sweep_tree_check
-    assert sweep_tree_check.check(n)
+    assert sweep_tree_check.check(n, three=three)
 
 
 def test_gpu_sweep_tree_falls_back_to_the_packed_tree_when_too_deep(hostcheck):

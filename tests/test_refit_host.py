@@ -258,29 +258,32 @@ def test_packed_tree_sort_key_is_a_hilbert_curve(hostcheck):
         assert (np.abs(np.diff(g[np.argsort(k)], axis=0)).sum(1) == 1).all()
 
 
+@pytest.mark.parametrize("three", [False, True])
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 17, 300, 5000])
-def test_sweep_tree_host_twin(hostcheck, n):
-    """The tree b2r_upload_scene builds on the GPU with B2R_FLAG_GPU_TREE | B2R_FLAG_GPU_SAH, through its host twin (build_sweep_tree): every
-    sphere in exactly one leaf, boxes conservative and tight, the closest hit through it equals brute force (indices included) — and it is
-    the better tree: fewer node visits than the packed one on the same rays."""
+def test_sweep_tree_host_twin(hostcheck, n, three):
+    """The trees b2r_upload_scene builds on the GPU with B2R_FLAG_GPU_TREE | B2R_FLAG_GPU_SAH (curve sweep) or B2R_FLAG_GPU_SAH3 (three-axis
+    sweep), through their host twins (build_sweep_tree / build_sweep3_tree): every sphere in exactly one leaf, boxes conservative and tight,
+    the closest hit through it equals brute force (indices included) — and they are the better trees: fewer node visits than the packed one
+    on the same rays, the three-axis sweep fewer than the curve sweep."""
+    build = hostcheck.hc_sweep3_tree if three else hostcheck.hc_sweep_tree; mode = 0xfffffffd if three else 0xfffffffe
     rs = np.random.RandomState(n)
     sc = scenes.random_scene(max(n, 2), light_every=5)
     _, prims, _ = b2r.build_bvh(sc["geometry"][:n])
     nw = C.c_uint32(0); ms = C.c_uint32(0)
-    assert hostcheck.hc_sweep_tree(vp(prims), n, None, None, C.byref(nw), C.byref(ms)) == 0
+    assert build(vp(prims), n, None, None, C.byref(nw), C.byref(ms)) == 0
     wide = np.zeros((nw.value, 4, 8), np.float32)
-    assert hostcheck.hc_sweep_tree(vp(prims), n, None, vp(wide), C.byref(nw), C.byref(ms)) == 0
+    assert build(vp(prims), n, None, vp(wide), C.byref(nw), C.byref(ms)) == 0
     assert ms.value + 3 <= 64
     check_contains(wide, prims)
     rays = camera_rays(2000, rs, prims) if n > 1 else np.ascontiguousarray(np.concatenate([prims["position"][[0] * 50] + rs.uniform(3, 9, (50, 3)), -np.ones((50, 3)) / np.sqrt(3)], 1), np.float32)
     m = len(rays); st = np.zeros(m, np.uint32); bx = np.zeros(m, np.uint32); sp = np.zeros(m, np.uint32); pr = np.zeros(m, np.int32)
-    assert hostcheck.hc_trace_stats(None, 0xfffffffe, vp(prims), n, vp(rays), m, vp(st), vp(bx), vp(sp), vp(pr)) == 0
+    assert hostcheck.hc_trace_stats(None, mode, vp(prims), n, vp(rays), m, vp(st), vp(bx), vp(sp), vp(pr)) == 0
     bt = np.zeros(m, np.float32); bp = np.zeros(m, np.int32)
     hostcheck.hc_closest_brute(vp(prims), n, vp(rays), m, vp(bt), vp(bp))
     assert np.array_equal(bp, pr)
     if n >= 300:
         st2 = np.zeros(m, np.uint32)
-        hostcheck.hc_trace_stats(None, 0xffffffff, vp(prims), n, vp(rays), m, vp(st2), vp(bx), vp(sp), vp(pr))
+        hostcheck.hc_trace_stats(None, 0xfffffffe if three else 0xffffffff, vp(prims), n, vp(rays), m, vp(st2), vp(bx), vp(sp), vp(pr))
         assert st.sum() < st2.sum()
 
 
@@ -315,7 +318,7 @@ def _odd_sphere_sets(rs):
     yield "plane", arr(np.concatenate([rs.uniform(-20, 20, (n, 2)), np.zeros((n, 1))], 1), rs.uniform(0.05, 0.6, n))
 
 
-@pytest.mark.parametrize("builder", ["packed", "sweep"])
+@pytest.mark.parametrize("builder", ["packed", "sweep", "sweep3"])
 def test_device_tree_twins_on_awkward_sphere_sets(hostcheck, builder):
     """Both trees the GPU builds by itself, through their host twins, on sphere sets that stress a curve order (see _odd_sphere_sets): the tree
     is valid (every sphere once, boxes conservative and tight), fits the traversal stack, and the closest hit through it equals brute force,
@@ -324,10 +327,10 @@ def test_device_tree_twins_on_awkward_sphere_sets(hostcheck, builder):
     for name, prims in _odd_sphere_sets(rs):
         prims = np.ascontiguousarray(prims, dtype=scenes.SPHERE_DTYPE); n = len(prims)
         nw = C.c_uint32(0); ms = C.c_uint32(0)
-        build = hostcheck.hc_sweep_tree if builder == "sweep" else hostcheck.hc_packed_tree
+        build = {"sweep": hostcheck.hc_sweep_tree, "sweep3": hostcheck.hc_sweep3_tree, "packed": hostcheck.hc_packed_tree}[builder]
         rc = build(vp(prims), n, None, None, C.byref(nw), C.byref(ms))
         if rc != 0:
-            assert builder == "sweep", name      # too deep: only the sweep tree can be
+            assert builder != "packed", name      # too deep: only the sweep trees can be
             continue
         wide = np.zeros((nw.value, 4, 8), np.float32)
         build(vp(prims), n, None, vp(wide), C.byref(nw), C.byref(ms))
@@ -335,7 +338,7 @@ def test_device_tree_twins_on_awkward_sphere_sets(hostcheck, builder):
         check_contains(wide, prims)
         rays = camera_rays(1500, rs, prims)
         m = len(rays); st = np.zeros(m, np.uint32); bx = np.zeros(m, np.uint32); sp = np.zeros(m, np.uint32); pr = np.zeros(m, np.int32)
-        assert hostcheck.hc_trace_stats(None, 0xfffffffe if builder == "sweep" else 0xffffffff, vp(prims), n, vp(rays), m, vp(st), vp(bx), vp(sp), vp(pr)) == 0
+        assert hostcheck.hc_trace_stats(None, {"sweep": 0xfffffffe, "sweep3": 0xfffffffd, "packed": 0xffffffff}[builder], vp(prims), n, vp(rays), m, vp(st), vp(bx), vp(sp), vp(pr)) == 0
         bt = np.zeros(m, np.float32); bp = np.zeros(m, np.int32)
         hostcheck.hc_closest_brute(vp(prims), n, vp(rays), m, vp(bt), vp(bp))
         assert np.array_equal(bp, pr), name
