@@ -639,7 +639,7 @@ def run_workload(args, name, rank, world, local, stream, dev, secondary=False):
         t5 = time.perf_counter(); r.SetScene(ps2); r.sync(); t6 = time.perf_counter()
         ms_gpu_sweep = steps_ms()
         edit_line["gpu_sweep_tree"] = {"upload_scene_ms": (t6 - t5) * 1e3, "ms_per_step": ms_gpu_sweep, "wide_nodes": int(len(r.wide_nodes()[0])),
-                                       "note": "b2r_upload_scene with B2R_FLAG_GPU_TREE | B2R_FLAG_GPU_SAH: as gpu_tree, but the topology is the sweep tree — per level three rounds of two segmented scans + cost + open kernels over the curve order, one 4-byte read-back per level; device tree == host twin build_sweep_tree bit for bit (tests)"}
+                                       "note": "b2r_upload_scene with B2R_FLAG_GPU_TREE | B2R_FLAG_GPU_SAH: as gpu_tree, but the topology is the sweep tree — per level three rounds of hand-written segmented scans (tile joins, carries, scans + cut costs in shared memory) + an open kernel over the curve order, one 4-byte read-back per level; device tree == host twin build_sweep_tree bit for bit (tests)"}
         # and with B2R_FLAG_GPU_SAH3: the three-axis sweep (x, y, z orders, the cheapest cut over all three: the host SAH tree's quality)
         r.set_flags(b2r.FLAG_GPU_TREE | b2r.FLAG_GPU_SAH3 | b.base_flags); r.SetCamera(b.ps.camera); r.SetScene(ps2); r.sync()
         t7 = time.perf_counter(); r.SetScene(ps2); r.sync(); t8 = time.perf_counter()

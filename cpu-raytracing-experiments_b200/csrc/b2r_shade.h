@@ -516,7 +516,6 @@ B2R_HD SweepItem sweep_join(const SweepItem& a, const SweepItem& b) {  // segmen
 	r.pos = a.pos; r.flag = a.flag;
 	return r;
 }
-struct SweepJoin { B2R_HD SweepItem operator()(const SweepItem& a, const SweepItem& b) const { return sweep_join(a, b); } };
 B2R_HD float sweep_area(const SweepItem& s) { const float ex = s.hi0 - s.lo0, ey = s.hi1 - s.lo1, ez = s.hi2 - s.lo2; return ex * ey + ey * ez + ez * ex; }
 B2R_HD void sweep_sphere_box(const float4 s, SweepItem* it) {
 	const float r = sqrtf(s.w);

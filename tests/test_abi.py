@@ -19,6 +19,15 @@ def test_header_and_binding_agree():
     assert header_symbols() == sorted(b2r.ABI_SYMBOLS)
 
 
+def test_flag_values_agree_with_the_header():
+    """B2R_FLAG_* of include/b2r.h against the Python binding's FLAG_* constants (the C++ faces include the header itself)."""
+    src = open(os.path.join(ROOT, "include", "b2r.h")).read()
+    flags = {name: 1 << int(bit) for name, bit in re.findall(r"\bB2R_FLAG_([A-Z0-9_]+)\s*=\s*1u\s*<<\s*(\d+)", src)}
+    assert len(flags) >= 12 and len(set(flags.values())) == len(flags)          # every flag its own bit
+    for name, value in flags.items():
+        assert getattr(b2r, "FLAG_" + name) == value, name
+
+
 def test_library_exports_every_symbol():
     L = C.CDLL(b2r.LIB_PATH)
     for s in header_symbols():
