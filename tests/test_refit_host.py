@@ -7,6 +7,7 @@
 * the quality ratio is 1 on identity and grows when spheres are scattered.
 The GPU tier (tests/test_gpu_parity.py::test_refit_*) checks the kernel against this twin and against a fresh upload."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -342,3 +343,12 @@ def test_device_tree_twins_on_awkward_sphere_sets(hostcheck, builder):
         bt = np.zeros(m, np.float32); bp = np.zeros(m, np.int32)
         hostcheck.hc_closest_brute(vp(prims), n, vp(rays), m, vp(bt), vp(bp))
         assert np.array_equal(bp, pr), name
+
+
+def test_device_tree_twins_against_the_committed_digests(hostcheck):
+    """tests/golden/device_tree_digests.json (tests/gen_device_tree_digests.py): the node arrays of the three host twins for fixed scenes,
+    hashed — the builders' arithmetic, tie rules and sort keys are pinned on a CPU-only box; the GPU tests pin the device to the twins."""
+    import json
+    import gen_device_tree_digests as gen
+    want = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "device_tree_digests.json")))
+    assert gen.digests(hostcheck) == want
