@@ -64,7 +64,8 @@ enum {
 	B2R_FLAG_GPU_SAH = 1u << 10,       /* with B2R_FLAG_GPU_TREE: the device builds the SWEEP tree instead — the spheres stay in curve order and every node is a run of that
 	                                    * order, cut top-down where the surface-area heuristic along the curve is smallest (segmented scans + one atomic minimum per
 	                                    * run and round), opened 2 -> 4 wide like the host's collapse: ~1.1x the node visits of the host's SAH tree, built in ~1.2 ms of device time at 100k spheres. A scene whose sweep
-	                                    * tree would be deeper than the traversal stack allows gets the packed tree. */
+	                                    * tree would be deeper than the traversal stack allows gets the packed tree. Node memory is reserved for the bound (one node per
+	                                    * sphere), so the sweep flags take scenes of up to 2^22 spheres. */
 	B2R_FLAG_GPU_SAH3 = 1u << 11,      /* with B2R_FLAG_GPU_TREE (wins over B2R_FLAG_GPU_SAH): the three-axis sweep — the device keeps the spheres sorted by centre x, y and z, every
 	                                    * cut is the cheapest over all three orders (a full-sweep SAH build), the other two orders are partitioned to match: the node visits
 	                                    * of the host's SAH tree, built on the device. Same depth fall-back as B2R_FLAG_GPU_SAH. */
